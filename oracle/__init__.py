@@ -1,0 +1,316 @@
+"""ctypes front-end of the CPU oracle (oracle/bitnuc_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this package.  ``bitnuc_b200`` never does: the product path is CUDA-only.
+
+The wrappers mirror the reference's Rust signatures (``Vec`` arguments become Python lists /
+``bytearray`` that are cleared or appended to exactly as the reference does) so that tests can be
+written the way the reference's own tests are.  Errors surface as :class:`OracleError` carrying the
+``NucleotideError`` variant; inputs on which the reference panics raise :class:`OraclePanic`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libbitnuc_oracle.so"
+
+PATH_NAIVE, PATH_AVX2 = 0, 1
+
+VARIANTS = {
+    1: "InvalidBase",
+    2: "SequenceTooLong",
+    3: "InvalidLength",
+    4: "IndexOutOfBounds",
+    5: "InvalidRange",
+    6: "Unsupported",
+}
+
+
+class OracleError(Exception):
+    def __init__(self, code: int, a: int, b: int, c: int, text: str):
+        super().__init__(text)
+        self.code, self.a, self.b, self.c = code, a, b, c
+        self.variant = VARIANTS.get(code, "?")
+
+    def key(self):
+        n = {1: 1, 2: 1, 3: 1, 4: 2, 5: 3, 6: 0}[self.code]
+        return (self.variant,) + (self.a, self.b, self.c)[:n]
+
+
+class OraclePanic(Exception):
+    """The reference would panic (index out of bounds / arithmetic underflow) on this input."""
+
+
+class _Err(C.Structure):
+    _fields_ = [("code", C.c_int32), ("a", C.c_uint64), ("b", C.c_uint64), ("c", C.c_uint64)]
+
+
+def build(native: bool = False, force: bool = False) -> Path:
+    """Compile the oracle with gcc (seconds).  Building the checker is not using it."""
+    src = _HERE / "bitnuc_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-B", "native" if native else "all"], check=True,
+                       capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(_LIB_PATH))
+        u8p, u64p, szp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)
+        ep = C.POINTER(_Err)
+        sz, u64 = C.c_size_t, C.c_uint64
+        sig = {
+            "orc_error_string": (C.c_int, [ep, C.c_char_p, sz]),
+            "orc_as_2bit": (C.c_int, [C.c_void_p, sz, u64p, ep]),
+            "orc_as_2bit_avx2": (C.c_int, [C.c_void_p, sz, u64p, ep]),
+            "orc_encode": (C.c_int, [C.c_void_p, sz, C.c_void_p, szp, ep]),
+            "orc_encode_avx2": (C.c_int, [C.c_void_p, sz, C.c_void_p, szp, ep]),
+            "orc_from_2bit": (C.c_int, [u64, sz, C.c_void_p, ep]),
+            "orc_from_2bit_avx2": (C.c_int, [u64, sz, C.c_void_p, ep]),
+            "orc_decode": (C.c_int, [C.c_void_p, sz, sz, C.c_void_p, szp, C.c_int, ep]),
+            "orc_hdist_scalar": (C.c_int, [u64, u64, sz, C.POINTER(C.c_uint32), ep]),
+            "orc_hdist": (C.c_int, [C.c_void_p, sz, C.c_void_p, sz, sz, C.POINTER(C.c_uint32), u64p,
+                                    C.c_int, ep]),
+            "orc_seq_get": (C.c_int, [C.c_void_p, sz, sz, u8p, ep]),
+            "orc_seq_slice": (C.c_int, [C.c_void_p, sz, sz, sz, C.c_void_p, ep]),
+            "orc_base_counts": (None, [C.c_void_p, sz, u64p]),
+            "orc_gc_content": (C.c_double, [C.c_void_p, sz]),
+            "orc_split_packed": (C.c_int, [C.c_void_p, sz, sz, sz, C.c_void_p, szp, C.c_void_p, szp, ep]),
+            "orc_splitmix64": (u64, [u64]),
+            "orc_synth_word": (u64, [u64, u64, u64]),
+            "orc_synth_ascii": (None, [u64, u64, u64, sz, C.c_void_p]),
+            "orc_bench_codec": (C.c_double, [C.c_void_p, sz, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p]),
+            "orc_have_avx2": (C.c_int, []),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _raise(rc: int, e: _Err):
+    if rc == 0:
+        return
+    if rc == -100:
+        raise OraclePanic()
+    buf = C.create_string_buffer(160)
+    lib().orc_error_string(C.byref(e), buf, 160)
+    raise OracleError(e.code, e.a, e.b, e.c, buf.value.decode())
+
+
+def _bytes_arr(seq) -> np.ndarray:
+    if isinstance(seq, np.ndarray):
+        return np.ascontiguousarray(seq, dtype=np.uint8)
+    return np.frombuffer(bytes(seq), dtype=np.uint8)
+
+
+def _words_arr(words) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(words, dtype=np.uint64))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p) if a.size else None
+
+
+def have_avx2() -> bool:
+    return bool(lib().orc_have_avx2())
+
+
+# ------------------------------------------------------------------ reference-shaped API ------
+
+def as_2bit(seq, avx2: bool = False) -> int:
+    a = _bytes_arr(seq)
+    out, e = C.c_uint64(0), _Err()
+    fn = lib().orc_as_2bit_avx2 if avx2 else lib().orc_as_2bit
+    _raise(fn(_ptr(a), a.size, C.byref(out), C.byref(e)), e)
+    return out.value
+
+
+def encode(seq, ebuf: list, avx2: bool = False) -> None:
+    """``encode(&[u8], &mut Vec<u64>)``: clears ``ebuf`` first; on error it keeps the words of the
+    chunks before the failing one (/root/reference/src/utils/packing/avx.rs:132,142-143)."""
+    a = _bytes_arr(seq)
+    words = np.zeros(max(1, (a.size + 31) // 32), dtype=np.uint64)
+    n, e = C.c_size_t(0), _Err()
+    fn = lib().orc_encode_avx2 if avx2 else lib().orc_encode
+    rc = fn(_ptr(a), a.size, _ptr(words), C.byref(n), C.byref(e))
+    if rc != -100:
+        ebuf.clear()
+        ebuf.extend(int(x) for x in words[: n.value])
+    _raise(rc, e)
+
+
+def encode_alloc(seq, avx2: bool = False) -> list:
+    ebuf: list = []
+    encode(seq, ebuf, avx2=avx2)
+    return ebuf
+
+
+def encode_np(seq, avx2: bool = False) -> np.ndarray:
+    """Array form for large inputs: returns the packed words or raises."""
+    a = _bytes_arr(seq)
+    words = np.zeros(max(1, (a.size + 31) // 32), dtype=np.uint64)
+    n, e = C.c_size_t(0), _Err()
+    fn = lib().orc_encode_avx2 if avx2 else lib().orc_encode
+    _raise(fn(_ptr(a), a.size, _ptr(words), C.byref(n), C.byref(e)), e)
+    return words[: n.value]
+
+
+def from_2bit(packed: int, expected_size: int, seq: bytearray, avx2: bool = False) -> None:
+    """Appends to ``seq`` (never clears), as the reference does."""
+    out = np.zeros(max(1, min(expected_size, 32)), dtype=np.uint8)
+    e = _Err()
+    fn = lib().orc_from_2bit_avx2 if avx2 else lib().orc_from_2bit
+    _raise(fn(C.c_uint64(packed & (2**64 - 1)), expected_size, _ptr(out), C.byref(e)), e)
+    seq.extend(out[:expected_size].tobytes())
+
+
+def from_2bit_alloc(packed: int, expected_size: int, avx2: bool = False) -> bytearray:
+    seq = bytearray()
+    from_2bit(packed, expected_size, seq, avx2=avx2)
+    return seq
+
+
+def decode_np(ebuf, n_bases: int, path: int = PATH_AVX2) -> np.ndarray:
+    w = _words_arr(ebuf)
+    out = np.zeros(32 * max(1, w.size, (n_bases + 31) // 32), dtype=np.uint8)
+    n, e = C.c_size_t(0), _Err()
+    rc = lib().orc_decode(_ptr(w), w.size, n_bases, _ptr(out), C.byref(n), path, C.byref(e))
+    res = out[: n.value]
+    if rc:
+        try:
+            _raise(rc, e)
+        except (OracleError, OraclePanic) as ex:
+            ex.partial = res  # what the reference had appended before failing
+            raise
+    return res
+
+
+def decode(ebuf, n_bases: int, dbuf: bytearray, path: int = PATH_AVX2) -> None:
+    """``decode(&[u64], usize, &mut Vec<u8>)``: appends to ``dbuf``."""
+    try:
+        dbuf.extend(decode_np(ebuf, n_bases, path).tobytes())
+    except (OracleError, OraclePanic) as ex:
+        dbuf.extend(ex.partial.tobytes())
+        raise
+
+
+def hdist_scalar(u: int, v: int, length: int) -> int:
+    out, e = C.c_uint32(0), _Err()
+    _raise(lib().orc_hdist_scalar(C.c_uint64(u), C.c_uint64(v), length, C.byref(out), C.byref(e)), e)
+    return out.value
+
+
+def hdist(ebuf1, ebuf2, n_bases: int, path: int = PATH_AVX2, wide: bool = False) -> int:
+    """u32 result with release-build wrap-around; ``wide=True`` returns the unwrapped u64."""
+    a, b = _words_arr(ebuf1), _words_arr(ebuf2)
+    out, tot, e = C.c_uint32(0), C.c_uint64(0), _Err()
+    _raise(lib().orc_hdist(_ptr(a), a.size, _ptr(b), b.size, n_bases, C.byref(out), C.byref(tot),
+                           path, C.byref(e)), e)
+    return tot.value if wide else out.value
+
+
+def base_counts(data, length: int) -> list:
+    w = _words_arr(data)
+    counts = (C.c_uint64 * 4)()
+    lib().orc_base_counts(_ptr(w), length, counts)
+    return list(counts)
+
+
+def gc_content(data, length: int) -> float:
+    w = _words_arr(data)
+    return float(lib().orc_gc_content(_ptr(w), length))
+
+
+def split_packed(ebuf, slen: int, idx: int):
+    w = _words_arr(ebuf)
+    lb = np.zeros(w.size + 1, dtype=np.uint64)
+    rb = np.zeros(w.size + 1, dtype=np.uint64)
+    nl, nr, e = C.c_size_t(0), C.c_size_t(0), _Err()
+    _raise(lib().orc_split_packed(_ptr(w), w.size, slen, idx, _ptr(lb), C.byref(nl), _ptr(rb),
+                                  C.byref(nr), C.byref(e)), e)
+    return [int(x) for x in lb[: nl.value]], [int(x) for x in rb[: nr.value]]
+
+
+class PackedSequence:
+    """/root/reference/src/sequence.rs:5-9 restated over the oracle."""
+
+    def __init__(self, seq):
+        seq = bytes(seq)
+        self.data = [] if len(seq) == 0 else encode_alloc(seq)  # sequence.rs:42-46
+        self.length = len(seq)
+
+    def __len__(self):
+        return self.length
+
+    def is_empty(self):
+        return self.length == 0
+
+    def get(self, index: int) -> int:
+        w = _words_arr(self.data)
+        out, e = C.c_uint8(0), _Err()
+        _raise(lib().orc_seq_get(_ptr(w), self.length, index, C.byref(out), C.byref(e)), e)
+        return out.value
+
+    def slice(self, start: int, end: int) -> bytes:
+        w = _words_arr(self.data)
+        out = np.zeros(max(1, end - start if end > start else 1), dtype=np.uint8)
+        e = _Err()
+        _raise(lib().orc_seq_slice(_ptr(w), self.length, start, end, _ptr(out), C.byref(e)), e)
+        return out[: end - start].tobytes()
+
+    def to_vec(self) -> bytes:
+        return self.slice(0, self.length)
+
+    def base_counts(self):
+        return base_counts(self.data, self.length)
+
+    def gc_content(self):
+        return gc_content(self.data, self.length)
+
+    def __eq__(self, other):
+        return (self.data, self.length) == (other.data, other.length)
+
+    def __hash__(self):
+        return hash((tuple(self.data), self.length))
+
+
+# ------------------------------------------------------------------ synthetic input -----------
+
+DEFAULT_SEED = 0x5EEDB17C0DE5
+
+
+def synth_word(seed: int, stream: int, j: int) -> int:
+    return int(lib().orc_synth_word(C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(j)))
+
+
+def synth_ascii(seed: int, stream: int, first_base: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint8)
+    lib().orc_synth_ascii(C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(first_base), n, _ptr(out))
+    return out
+
+
+def bench_codec(seq: np.ndarray, threads: int, reps: int, path: int = PATH_AVX2,
+                do_encode: bool = True, do_decode: bool = True) -> float:
+    """Best-of-``reps`` wall seconds for encode(+decode) of ``seq`` over ``threads`` pthreads."""
+    a = _bytes_arr(seq)
+    ebuf = np.zeros((a.size + 31) // 32 + threads, dtype=np.uint64)
+    dbuf = np.zeros(a.size + 32, dtype=np.uint8)
+    if not do_encode:  # decode-only: pre-fill the packed buffer
+        ebuf[: (a.size + 31) // 32] = encode_np(a)
+    return float(lib().orc_bench_codec(_ptr(a), a.size, threads, reps, path, int(do_encode),
+                                       int(do_decode), _ptr(ebuf), _ptr(dbuf)))

@@ -1,0 +1,534 @@
+/*
+ * bitnuc_oracle.c -- CPU restatement of the bitnuc hot path.  TEST INFRASTRUCTURE ONLY.
+ * See bitnuc_oracle.h for the rules on who may load this.  Citations: /root/reference/<path>:<line>.
+ *
+ * Two layers:
+ *   1. scalar restatements that define the semantics (naive.rs / scalar.rs / sequence.rs /
+ *      analysis.rs), plus a `path` switch for the places where the reference's x86 AVX2 path and
+ *      its naive path disagree on edge behaviour;
+ *   2. AVX2-intrinsic restatements of packing/avx.rs, unpacking/avx.rs and hamming/multi.rs that
+ *      keep the reference's structure (scalar validation scan, 16-lane steps, scalar bit-pack loop,
+ *      32-iteration index extraction, per-word append).  They exist to be TIMED as the CPU
+ *      baseline; tests check they agree with layer 1.
+ */
+#define _GNU_SOURCE
+#include "bitnuc_oracle.h"
+
+#include <immintrin.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+
+static int fail(orc_error *err, int code, uint64_t a, uint64_t b, uint64_t c) {
+    if (err) {
+        err->code = code;
+        err->a = a;
+        err->b = b;
+        err->c = c;
+    }
+    return code;
+}
+
+static int ok(orc_error *err) { return fail(err, ORC_OK, 0, 0, 0); }
+
+/* src/error.rs:20-45 */
+int orc_error_string(const orc_error *e, char *buf, size_t cap) {
+    switch (e->code) {
+    case ORC_OK:
+        return snprintf(buf, cap, "Ok");
+    case ORC_INVALID_BASE: /* the byte is printed as a decimal integer (u8 Display) */
+        return snprintf(buf, cap, "Invalid nucleotide base: %llu", (unsigned long long)e->a);
+    case ORC_SEQUENCE_TOO_LONG:
+        return snprintf(buf, cap, "Sequence length %llu exceeds maximum", (unsigned long long)e->a);
+    case ORC_INVALID_LENGTH:
+        return snprintf(buf, cap, "Invalid length: %llu", (unsigned long long)e->a);
+    case ORC_INDEX_OUT_OF_BOUNDS:
+        return snprintf(buf, cap, "Index %llu out of bounds for sequence of length %llu",
+                        (unsigned long long)e->a, (unsigned long long)e->b);
+    case ORC_INVALID_RANGE:
+        return snprintf(buf, cap, "Invalid range %llu..%llu for sequence of length %llu",
+                        (unsigned long long)e->a, (unsigned long long)e->b, (unsigned long long)e->c);
+    case ORC_UNSUPPORTED:
+        return snprintf(buf, cap, "Unsupported architecture");
+    default:
+        return snprintf(buf, cap, "panic");
+    }
+}
+
+/* ------------------------------------------------------------------ packing (scalar) -------- */
+
+/* match arm of src/utils/packing/naive.rs:10-16; returns 0..3 or -1 */
+static inline int base_code(uint8_t b) {
+    switch (b) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return -1;
+    }
+}
+
+/* src/utils/packing/naive.rs:4-20 */
+int orc_as_2bit(const uint8_t *seq, size_t len, uint64_t *out, orc_error *err) {
+    if (len > 32) return fail(err, ORC_SEQUENCE_TOO_LONG, len, 0, 0);
+    uint64_t packed = 0;
+    for (size_t i = 0; i < len; ++i) {
+        int bits = base_code(seq[i]);
+        if (bits < 0) return fail(err, ORC_INVALID_BASE, seq[i], 0, 0);
+        packed |= (uint64_t)bits << (i * 2);
+    }
+    *out = packed;
+    return ok(err);
+}
+
+/* src/utils/packing/naive.rs:22-43 */
+int orc_encode(const uint8_t *seq, size_t len, uint64_t *ebuf, size_t *n_words, orc_error *err) {
+    *n_words = 0; /* ebuf.clear() */
+    size_t n_chunks = (len + 31) / 32;
+    if (n_chunks == 0) return fail(err, ORC_PANIC, 0, 0, 0); /* 0..n_chunks-1 underflows */
+    size_t l = 0;
+    for (size_t k = 0; k + 1 < n_chunks; ++k) {
+        uint64_t bits;
+        int rc = orc_as_2bit(seq + l, 32, &bits, err);
+        if (rc) return rc;
+        ebuf[(*n_words)++] = bits;
+        l += 32;
+    }
+    uint64_t bits;
+    int rc = orc_as_2bit(seq + l, len - l, &bits, err);
+    if (rc) return rc;
+    ebuf[(*n_words)++] = bits;
+    return ok(err);
+}
+
+/* ------------------------------------------------------------------ unpacking (scalar) ------ */
+
+/* src/utils/unpacking/naive.rs:3-25 */
+int orc_from_2bit(uint64_t packed, size_t expected_size, uint8_t *out, orc_error *err) {
+    static const uint8_t lut[4] = {'A', 'C', 'G', 'T'};
+    if (expected_size > 32) return fail(err, ORC_INVALID_LENGTH, expected_size, 0, 0);
+    for (size_t i = 0; i < expected_size; ++i) out[i] = lut[(packed >> (i * 2)) & 3];
+    return ok(err);
+}
+
+int orc_decode(const uint64_t *ebuf, size_t n_words, size_t n_bases, uint8_t *out, size_t *n_out,
+               int path, orc_error *err) {
+    *n_out = 0;
+    if (path == ORC_PATH_AVX2) {
+        /* src/utils/unpacking/avx.rs:117-153 */
+        size_t full_chunks = n_bases / 32;
+        size_t take = full_chunks < n_words ? full_chunks : n_words; /* .take() never over-runs */
+        for (size_t k = 0; k < take; ++k) {
+            orc_from_2bit(ebuf[k], 32, out + *n_out, NULL);
+            *n_out += 32;
+        }
+        size_t rem = n_bases % 32;
+        if (rem > 0) {
+            if (full_chunks >= n_words) return fail(err, ORC_PANIC, 0, 0, 0); /* ebuf[full_chunks] */
+            orc_from_2bit(ebuf[full_chunks], rem, out + *n_out, NULL);
+            *n_out += rem;
+        }
+        return ok(err);
+    }
+    /* src/utils/unpacking/mod.rs:29-47 */
+    size_t n_chunks = (n_bases + 31) / 32;
+    if (n_chunks == 0) return fail(err, ORC_PANIC, 0, 0, 0); /* n_chunks - 1 underflows (debug) */
+    size_t rem = n_bases % 32 == 0 ? 32 : n_bases % 32;
+    size_t take = n_chunks - 1 < n_words ? n_chunks - 1 : n_words;
+    for (size_t k = 0; k < take; ++k) {
+        orc_from_2bit(ebuf[k], 32, out + *n_out, NULL);
+        *n_out += 32;
+    }
+    if (n_chunks - 1 >= n_words) return fail(err, ORC_INVALID_LENGTH, n_bases, 0, 0); /* .get() = None */
+    orc_from_2bit(ebuf[n_chunks - 1], rem, out + *n_out, NULL);
+    *n_out += rem;
+    return ok(err);
+}
+
+/* ------------------------------------------------------------------ hamming (scalar) -------- */
+
+#define LOWER_BITS 0x5555555555555555ull
+#define UPPER_BITS 0xAAAAAAAAAAAAAAAAull
+
+/* src/utils/functions/hamming/scalar.rs:11-48 */
+int orc_hdist_scalar(uint64_t u, uint64_t v, size_t len, uint32_t *out, orc_error *err) {
+    if (len > 32) return fail(err, ORC_INVALID_LENGTH, len, 0, 0);
+    *out = 0;
+    if (len == 0 || u == v) return ok(err);
+    size_t valid_bits = len * 2;
+    uint64_t mask = valid_bits == 64 ? ~0ull : ((1ull << valid_bits) - 1);
+    uint64_t diff = (u ^ v) & mask;
+    if (diff == 0) return ok(err);
+    uint64_t lower = diff & LOWER_BITS & mask;
+    uint64_t upper = (diff & UPPER_BITS & mask) >> 1;
+    *out = (uint32_t)__builtin_popcountll(lower | upper);
+    return ok(err);
+}
+
+static uint64_t hdist_full_words(const uint64_t *e1, const uint64_t *e2, size_t full_chunks) {
+    uint64_t t = 0;
+    for (size_t k = 0; k < full_chunks; ++k) {
+        uint64_t d = e1[k] ^ e2[k];
+        t += (uint64_t)__builtin_popcountll((d & LOWER_BITS) | ((d & UPPER_BITS) >> 1));
+    }
+    return t;
+}
+
+__attribute__((target("avx2,popcnt"))) static uint32_t
+hdist_multi_avx2(const uint64_t *e1, const uint64_t *e2, size_t full_chunks);
+
+/* src/utils/functions/hamming/multi.rs:122-160 */
+int orc_hdist(const uint64_t *e1, size_t n1, const uint64_t *e2, size_t n2, size_t n_bases,
+              uint32_t *out, uint64_t *total64, int path, orc_error *err) {
+    size_t expected = (n_bases + 31) / 32;
+    if (n1 < expected || n2 < expected) return fail(err, ORC_INVALID_LENGTH, n_bases, 0, 0);
+    size_t full_chunks = n_bases / 32;
+    uint32_t total = 0; /* `let mut total_dist = 0u32` -- wraps in a release build */
+    if (path == ORC_PATH_AVX2 && orc_have_avx2() && full_chunks >= 4)
+        total = hdist_multi_avx2(e1, e2, full_chunks);
+    if (total == 0 && full_chunks > 0) { /* multi.rs:147-151: "SIMD not available" re-scan */
+        for (size_t k = 0; k < full_chunks; ++k) {
+            uint32_t d;
+            orc_hdist_scalar(e1[k], e2[k], 32, &d, NULL);
+            total += d;
+        }
+    }
+    uint64_t wide = hdist_full_words(e1, e2, full_chunks);
+    size_t rem = n_bases % 32;
+    if (rem > 0) {
+        uint32_t d;
+        orc_hdist_scalar(e1[full_chunks], e2[full_chunks], rem, &d, NULL);
+        total += d;
+        wide += d;
+    }
+    *out = total;
+    if (total64) *total64 = wide;
+    return ok(err);
+}
+
+/* ------------------------------------------------------------------ PackedSequence ---------- */
+
+/* src/sequence.rs:116-135 */
+int orc_seq_get(const uint64_t *data, size_t length, size_t index, uint8_t *out, orc_error *err) {
+    static const uint8_t lut[4] = {'A', 'C', 'G', 'T'};
+    if (index >= length) return fail(err, ORC_INDEX_OUT_OF_BOUNDS, index, length, 0);
+    size_t chunk_idx = index / 32, bit_idx = (index % 32) * 2;
+    *out = lut[(data[chunk_idx] >> bit_idx) & 3];
+    return ok(err);
+}
+
+/* src/sequence.rs:198-212 */
+int orc_seq_slice(const uint64_t *data, size_t length, size_t start, size_t end, uint8_t *out,
+                  orc_error *err) {
+    if (start > end || end > length) return fail(err, ORC_INVALID_RANGE, start, end, length);
+    for (size_t i = start; i < end; ++i) {
+        int rc = orc_seq_get(data, length, i, out + (i - start), err);
+        if (rc) return rc;
+    }
+    return ok(err);
+}
+
+/* src/utils/analysis.rs:19-39: to_vec() (= slice(0..len), per-base get) then a byte match loop */
+void orc_base_counts(const uint64_t *data, size_t length, uint64_t counts[4]) {
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (size_t i = 0; i < length; ++i) {
+        uint8_t b;
+        orc_seq_get(data, length, i, &b, NULL);
+        switch (b) {
+        case 'A': counts[0]++; break;
+        case 'C': counts[1]++; break;
+        case 'G': counts[2]++; break;
+        case 'T': counts[3]++; break;
+        default: break;
+        }
+    }
+}
+
+/* src/utils/analysis.rs:3-17: (gc_count as f64 / len as f64) * 100.0, in exactly this order */
+double orc_gc_content(const uint64_t *data, size_t length) {
+    if (length == 0) return 0.0;
+    size_t gc = 0;
+    for (size_t i = 0; i < length; ++i) {
+        uint8_t b;
+        orc_seq_get(data, length, i, &b, NULL);
+        if (b == 'G' || b == 'C') gc++;
+    }
+    volatile double q = (double)gc / (double)length; /* no contraction / reassociation */
+    return q * 100.0;
+}
+
+/* ------------------------------------------------------------------ split_packed ------------ */
+
+/* src/utils/functions/split.rs:14-102 */
+int orc_split_packed(const uint64_t *ebuf, size_t n_words, size_t slen, size_t idx, uint64_t *lbuf,
+                     size_t *n_left, uint64_t *rbuf, size_t *n_right, orc_error *err) {
+    if (idx > slen) return fail(err, ORC_INDEX_OUT_OF_BOUNDS, idx, slen, 0);
+    *n_left = *n_right = 0;
+    if (idx == 0) {
+        memcpy(rbuf, ebuf, n_words * 8);
+        *n_right = n_words;
+        return ok(err);
+    }
+    if (idx == slen) {
+        memcpy(lbuf, ebuf, n_words * 8);
+        *n_left = n_words;
+        return ok(err);
+    }
+    if (n_words == 0) return ok(err);
+    size_t right_chunks = (slen - idx + 31) / 32;
+    size_t chunk_idx = idx / 32, bit_idx = (idx % 32) * 2;
+    if (chunk_idx >= n_words) return fail(err, ORC_PANIC, 0, 0, 0); /* ebuf[chunk_idx] */
+    if (chunk_idx > 0) {
+        memcpy(lbuf, ebuf, chunk_idx * 8);
+        *n_left = chunk_idx;
+    }
+    uint64_t split_mask = bit_idx == 0 ? 0 : ((1ull << bit_idx) - 1);
+    lbuf[(*n_left)++] = ebuf[chunk_idx] & split_mask;
+    uint64_t carry = 0;
+    for (size_t k = chunk_idx; k < n_words; ++k) {
+        uint64_t curr = ebuf[k];
+        rbuf[(*n_right)++] = carry | (curr >> bit_idx);
+        carry = bit_idx == 0 ? 0 : curr << (64 - bit_idx);
+    }
+    if (carry != 0 && *n_right < right_chunks) rbuf[(*n_right)++] = carry;
+    return ok(err);
+}
+
+/* ------------------------------------------------------------------ synthetic input --------- */
+
+uint64_t orc_splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* word j of stream s = splitmix64((seed ^ s*golden) + j) */
+uint64_t orc_synth_word(uint64_t seed, uint64_t stream, uint64_t j) {
+    return orc_splitmix64((seed ^ (stream * 0x9E3779B97F4A7C15ull)) + j);
+}
+
+void orc_synth_ascii(uint64_t seed, uint64_t stream, uint64_t first_base, size_t n, uint8_t *out) {
+    static const uint8_t lut[4] = {'A', 'C', 'G', 'T'};
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t b = first_base + i;
+        uint64_t w = orc_synth_word(seed, stream, b / 32);
+        out[i] = lut[(w >> (2 * (b % 32))) & 3];
+    }
+}
+
+/* ================================================================== AVX2 restatements ======= */
+
+int orc_have_avx2(void) { return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt"); }
+
+/* src/utils/packing/avx.rs:34-74: three (upper|lower) compare masks, select 1/2/3 */
+__attribute__((target("avx2"))) static inline __m256i classify32(__m256i chunk) {
+    __m256i c = _mm256_or_si256(_mm256_cmpeq_epi8(chunk, _mm256_set1_epi8('C')),
+                                _mm256_cmpeq_epi8(chunk, _mm256_set1_epi8('c')));
+    __m256i g = _mm256_or_si256(_mm256_cmpeq_epi8(chunk, _mm256_set1_epi8('G')),
+                                _mm256_cmpeq_epi8(chunk, _mm256_set1_epi8('g')));
+    __m256i t = _mm256_or_si256(_mm256_cmpeq_epi8(chunk, _mm256_set1_epi8('T')),
+                                _mm256_cmpeq_epi8(chunk, _mm256_set1_epi8('t')));
+    __m256i r = _mm256_setzero_si256();
+    r = _mm256_or_si256(_mm256_and_si256(c, _mm256_set1_epi8(1)), _mm256_andnot_si256(c, r));
+    r = _mm256_or_si256(_mm256_and_si256(g, _mm256_set1_epi8(2)), _mm256_andnot_si256(g, r));
+    r = _mm256_or_si256(_mm256_and_si256(t, _mm256_set1_epi8(3)), _mm256_andnot_si256(t, r));
+    return r;
+}
+
+/* src/utils/packing/avx.rs:76-128.  `avail` = bytes readable at seq (the reference's 32-byte load
+ * at seq[chunk_idx..] over-reads its slice, avx.rs:103; here the load is bounced through a
+ * zero-padded temporary when fewer than 32 bytes are readable, which does not change results). */
+__attribute__((target("avx2"))) static int as_2bit_avx2_impl(const uint8_t *seq, size_t len,
+                                                             size_t avail, uint64_t *out,
+                                                             orc_error *err) {
+    if (len > 32) return fail(err, ORC_SEQUENCE_TOO_LONG, len, 0, 0);
+    if (len < 16) return orc_as_2bit(seq, len, out, err);
+    for (size_t i = 0; i < len; ++i) /* scalar validation scan, avx.rs:86-91 */
+        if (base_code(seq[i]) < 0) return fail(err, ORC_INVALID_BASE, seq[i], 0, 0);
+    uint64_t packed = 0;
+    size_t simd_len = len - (len % 16);
+    for (size_t chunk_idx = 0; chunk_idx < simd_len; chunk_idx += 16) {
+        __m256i chunk;
+        if (chunk_idx + 32 <= avail) {
+            chunk = _mm256_loadu_si256((const __m256i *)(seq + chunk_idx));
+        } else {
+            uint8_t pad[32] = {0};
+            memcpy(pad, seq + chunk_idx, avail - chunk_idx);
+            chunk = _mm256_loadu_si256((const __m256i *)pad);
+        }
+        uint8_t temp[32];
+        _mm256_storeu_si256((__m256i *)temp, classify32(chunk));
+        for (size_t i = 0; i < 16; ++i) /* scalar bit-pack loop, avx.rs:109-111 */
+            packed |= (uint64_t)temp[i] << ((chunk_idx + i) * 2);
+    }
+    for (size_t i = simd_len; i < len; ++i) /* scalar tail, avx.rs:115-124 */
+        packed |= (uint64_t)base_code(seq[i]) << (i * 2);
+    *out = packed;
+    return ok(err);
+}
+
+int orc_as_2bit_avx2(const uint8_t *seq, size_t len, uint64_t *out, orc_error *err) {
+    return as_2bit_avx2_impl(seq, len, len, out, err);
+}
+
+/* src/utils/packing/avx.rs:130-151 */
+__attribute__((target("avx2"))) int orc_encode_avx2(const uint8_t *seq, size_t len, uint64_t *ebuf,
+                                                    size_t *n_words, orc_error *err) {
+    *n_words = 0;
+    size_t n_chunks = (len + 31) / 32;
+    if (n_chunks == 0) return fail(err, ORC_PANIC, 0, 0, 0);
+    size_t l = 0;
+    for (size_t k = 0; k + 1 < n_chunks; ++k) {
+        uint64_t bits;
+        int rc = as_2bit_avx2_impl(seq + l, 32, len - l, &bits, err);
+        if (rc) return rc;
+        ebuf[(*n_words)++] = bits;
+        l += 32;
+    }
+    uint64_t bits;
+    int rc = as_2bit_avx2_impl(seq + l, len - l, len - l, &bits, err);
+    if (rc) return rc;
+    ebuf[(*n_words)++] = bits;
+    return ok(err);
+}
+
+/* src/utils/unpacking/avx.rs:26-33: 32 scalar shift/mask steps, one 256-bit load, one vpshufb */
+__attribute__((target("avx2"))) static inline __m256i unpack_32(uint64_t packed, __m256i lookup) {
+    uint8_t idx[32];
+    for (int i = 0; i < 32; ++i) idx[i] = (uint8_t)((packed >> (i * 2)) & 3);
+    return _mm256_shuffle_epi8(lookup, _mm256_loadu_si256((const __m256i *)idx));
+}
+
+__attribute__((target("avx2"))) static inline __m256i acgt_lut(void) {
+    return _mm256_setr_epi8('A', 'C', 'G', 'T', 'A', 'C', 'G', 'T', 'A', 'C', 'G', 'T', 'A', 'C', 'G',
+                            'T', 'A', 'C', 'G', 'T', 'A', 'C', 'G', 'T', 'A', 'C', 'G', 'T', 'A', 'C',
+                            'G', 'T');
+}
+
+/* src/utils/unpacking/avx.rs:50-114, collapsed: every branch yields the low expected_size bases */
+__attribute__((target("avx2"))) int orc_from_2bit_avx2(uint64_t packed, size_t expected_size,
+                                                       uint8_t *out, orc_error *err) {
+    if (expected_size > 32) return fail(err, ORC_INVALID_LENGTH, expected_size, 0, 0);
+    uint8_t temp[32];
+    _mm256_storeu_si256((__m256i *)temp, unpack_32(packed, acgt_lut()));
+    memcpy(out, temp, expected_size);
+    return ok(err);
+}
+
+/* src/utils/unpacking/avx.rs:117-153 (well-formed input only; edge cases live in orc_decode) */
+__attribute__((target("avx2"))) static void decode_avx2(const uint64_t *ebuf, size_t n_bases,
+                                                        uint8_t *out) {
+    __m256i lookup = acgt_lut();
+    size_t full_chunks = n_bases / 32;
+    uint8_t temp[32];
+    for (size_t k = 0; k < full_chunks; ++k) {
+        _mm256_storeu_si256((__m256i *)temp, unpack_32(ebuf[k], lookup));
+        memcpy(out + 32 * k, temp, 32); /* extend_from_slice(&temp) */
+    }
+    size_t rem = n_bases % 32;
+    if (rem) {
+        _mm256_storeu_si256((__m256i *)temp, unpack_32(ebuf[full_chunks], lookup));
+        memcpy(out + 32 * full_chunks, temp, rem);
+    }
+}
+
+/* src/utils/functions/hamming/multi.rs:12-67 */
+__attribute__((target("avx2,popcnt"))) static uint32_t
+hdist_multi_avx2(const uint64_t *e1, const uint64_t *e2, size_t full_chunks) {
+    uint32_t total = 0;
+    size_t quad = full_chunks / 4;
+    __m256i lower = _mm256_set1_epi64x((long long)LOWER_BITS);
+    __m256i upper = _mm256_set1_epi64x((long long)UPPER_BITS);
+    for (size_t i = 0; i < quad; ++i) {
+        __m256i u = _mm256_loadu_si256((const __m256i *)(e1 + 4 * i));
+        __m256i v = _mm256_loadu_si256((const __m256i *)(e2 + 4 * i));
+        __m256i diff = _mm256_xor_si256(u, v);
+        if (_mm256_testz_si256(diff, diff) == 1) continue;
+        __m256i comb = _mm256_or_si256(_mm256_and_si256(diff, lower),
+                                       _mm256_srli_epi64(_mm256_and_si256(diff, upper), 1));
+        total += (uint32_t)__builtin_popcountll((uint64_t)_mm256_extract_epi64(comb, 0)) +
+                 (uint32_t)__builtin_popcountll((uint64_t)_mm256_extract_epi64(comb, 1)) +
+                 (uint32_t)__builtin_popcountll((uint64_t)_mm256_extract_epi64(comb, 2)) +
+                 (uint32_t)__builtin_popcountll((uint64_t)_mm256_extract_epi64(comb, 3));
+    }
+    for (size_t k = quad * 4; k < full_chunks; ++k) {
+        uint32_t d = 0;
+        orc_hdist_scalar(e1[k], e2[k], 32, &d, NULL); /* .unwrap_or(0) */
+        total += d;
+    }
+    return total;
+}
+
+/* ================================================================== timed baseline harness == */
+
+typedef struct {
+    const uint8_t *seq;
+    size_t n;
+    uint64_t *ebuf;
+    uint8_t *dbuf;
+    int path, do_encode, do_decode, rc;
+} codec_job;
+
+static void *codec_worker(void *p) {
+    codec_job *j = (codec_job *)p;
+    j->rc = 0;
+    if (j->n == 0) return NULL;
+    size_t nw = 0;
+    if (j->do_encode) {
+        orc_error e;
+        j->rc = (j->path == ORC_PATH_AVX2 ? orc_encode_avx2 : orc_encode)(j->seq, j->n, j->ebuf, &nw, &e);
+        if (j->rc) return NULL;
+    }
+    if (j->do_decode) {
+        if (j->path == ORC_PATH_AVX2) {
+            decode_avx2(j->ebuf, j->n, j->dbuf);
+        } else {
+            size_t n_out;
+            orc_error e;
+            j->rc = orc_decode(j->ebuf, (j->n + 31) / 32, j->n, j->dbuf, &n_out, ORC_PATH_NAIVE, &e);
+        }
+    }
+    return NULL;
+}
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+double orc_bench_codec(const uint8_t *seq, size_t n, int n_threads, int reps, int path,
+                       int do_encode, int do_decode, uint64_t *ebuf, uint8_t *dbuf) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 1024) n_threads = 1024;
+    if (path == ORC_PATH_AVX2 && !orc_have_avx2()) return -2.0;
+    codec_job jobs[1024];
+    pthread_t tids[1024];
+    size_t n_words = (n + 31) / 32;
+    size_t words_per = (n_words + (size_t)n_threads - 1) / (size_t)n_threads;
+    double best = -1.0;
+    for (int r = 0; r < reps; ++r) {
+        double t0 = now_s();
+        for (int t = 0; t < n_threads; ++t) {
+            size_t w0 = (size_t)t * words_per;
+            if (w0 > n_words) w0 = n_words;
+            size_t w1 = w0 + words_per < n_words ? w0 + words_per : n_words;
+            size_t b0 = w0 * 32, b1 = w1 * 32 < n ? w1 * 32 : n;
+            jobs[t] = (codec_job){seq + b0, b1 - b0, ebuf + w0, dbuf ? dbuf + b0 : NULL,
+                                  path, do_encode, do_decode, 0};
+            if (n_threads == 1)
+                codec_worker(&jobs[t]);
+            else
+                pthread_create(&tids[t], NULL, codec_worker, &jobs[t]);
+        }
+        if (n_threads > 1)
+            for (int t = 0; t < n_threads; ++t) pthread_join(tids[t], NULL);
+        double dt = now_s() - t0;
+        for (int t = 0; t < n_threads; ++t)
+            if (jobs[t].rc) return -1.0;
+        if (best < 0 || dt < best) best = dt;
+    }
+    return best;
+}

@@ -1,0 +1,105 @@
+/*
+ * bitnuc_oracle.h -- CPU restatement of the bitnuc hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is the parity oracle: a plain-C restatement of the reference's algorithms, checked against
+ * every known-answer vector in the reference's own unit tests (tests/golden/reference_kats.json).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it.  Nothing under bitnuc_b200/ links, imports or calls it; the product path is CUDA-only.
+ *
+ * The reference is Rust and cannot be compiled in this image (no cargo/rustc), so there is no
+ * oracle/_ref build.  Parity is pinned through the reference's own test vectors instead.
+ *
+ * All citations are relative to /root/reference/.
+ */
+#ifndef BITNUC_ORACLE_H
+#define BITNUC_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* NucleotideError variants in declaration order (src/error.rs:4-18). 0 = Ok. */
+enum {
+    ORC_OK = 0,
+    ORC_INVALID_BASE = 1,       /* a = offending byte                       */
+    ORC_SEQUENCE_TOO_LONG = 2,  /* a = length                               */
+    ORC_INVALID_LENGTH = 3,     /* a = length                               */
+    ORC_INDEX_OUT_OF_BOUNDS = 4,/* a = index, b = length                    */
+    ORC_INVALID_RANGE = 5,      /* a = start, b = end, c = length           */
+    ORC_UNSUPPORTED = 6,
+    ORC_PANIC = -100            /* the reference would panic on this input  */
+};
+
+typedef struct {
+    int32_t code;
+    uint64_t a, b, c;
+} orc_error;
+
+/* which of the reference's two x86 code paths to follow where their edge behaviour differs */
+enum { ORC_PATH_NAIVE = 0, ORC_PATH_AVX2 = 1 };
+
+/* src/error.rs:20-45 -- Display strings. Returns bytes written (excluding NUL). */
+int orc_error_string(const orc_error *e, char *buf, size_t cap);
+
+/* src/utils/packing/naive.rs:4-20 (semantics) ; avx.rs:76-128 has identical results */
+int orc_as_2bit(const uint8_t *seq, size_t len, uint64_t *out, orc_error *err);
+/* AVX2 restatement of src/utils/packing/avx.rs:76-128, used as the timed CPU baseline */
+int orc_as_2bit_avx2(const uint8_t *seq, size_t len, uint64_t *out, orc_error *err);
+
+/* src/utils/packing/naive.rs:22-43 == avx.rs:130-151. ebuf needs ceil(len/32) words.
+ * *n_words = words pushed (on error: words of the chunks before the failing chunk).
+ * len == 0 -> ORC_PANIC (0..n_chunks-1 underflow, avx.rs:138). */
+int orc_encode(const uint8_t *seq, size_t len, uint64_t *ebuf, size_t *n_words, orc_error *err);
+int orc_encode_avx2(const uint8_t *seq, size_t len, uint64_t *ebuf, size_t *n_words, orc_error *err);
+
+/* src/utils/unpacking/naive.rs:3-25 ; avx.rs:50-114 gives the same bytes.
+ * Writes expected_size bytes at out (the caller models Vec append). */
+int orc_from_2bit(uint64_t packed, size_t expected_size, uint8_t *out, orc_error *err);
+int orc_from_2bit_avx2(uint64_t packed, size_t expected_size, uint8_t *out, orc_error *err);
+
+/* decode == from_2bit_multi: src/utils/unpacking/mod.rs:10-48 (naive path) and
+ * src/utils/unpacking/avx.rs:117-153 (AVX2 path).  out needs room for
+ * 32*max(n_words, ceil(n_bases/32)) bytes; *n_out = bytes appended. */
+int orc_decode(const uint64_t *ebuf, size_t n_words, size_t n_bases, uint8_t *out, size_t *n_out,
+               int path, orc_error *err);
+
+/* src/utils/functions/hamming/scalar.rs:11-48 */
+int orc_hdist_scalar(uint64_t u, uint64_t v, size_t len, uint32_t *out, orc_error *err);
+/* src/utils/functions/hamming/multi.rs:122-160; u32 accumulator wraps as in a release build.
+ * *total64 (optional) receives the unwrapped count. path selects :12-67 or the scalar loop. */
+int orc_hdist(const uint64_t *e1, size_t n1, const uint64_t *e2, size_t n2, size_t n_bases,
+              uint32_t *out, uint64_t *total64, int path, orc_error *err);
+
+/* PackedSequence (src/sequence.rs) as (data, n_words, length) */
+int orc_seq_get(const uint64_t *data, size_t length, size_t index, uint8_t *out, orc_error *err);   /* :116-135 */
+int orc_seq_slice(const uint64_t *data, size_t length, size_t start, size_t end, uint8_t *out,
+                  orc_error *err);                                                                   /* :198-212 */
+/* src/utils/analysis.rs:19-39 and :3-17 (decode every base with get(), then count bytes) */
+void orc_base_counts(const uint64_t *data, size_t length, uint64_t counts[4]);
+double orc_gc_content(const uint64_t *data, size_t length);
+
+/* src/utils/functions/split.rs:14-102.  lbuf/rbuf need n_words+1 words each. */
+int orc_split_packed(const uint64_t *ebuf, size_t n_words, size_t slen, size_t idx, uint64_t *lbuf,
+                     size_t *n_left, uint64_t *rbuf, size_t *n_right, orc_error *err);
+
+/* ---- synthetic input: counter-based splitmix64 stream --------------------- */
+uint64_t orc_splitmix64(uint64_t x);
+uint64_t orc_synth_word(uint64_t seed, uint64_t stream, uint64_t j);
+void orc_synth_ascii(uint64_t seed, uint64_t stream, uint64_t first_base, size_t n, uint8_t *out);
+
+/* ---- timed CPU baseline (bench.py only) ---------------------------------------------------
+ * Runs encode (+ decode when do_decode) over seq[0..n) split on 32-base boundaries across
+ * n_threads pthreads, each thread calling the single-threaded reference restatement on its slice
+ * (the chunking belongs to the harness; the reference is single-threaded).  Returns wall seconds
+ * of the best of `reps` repetitions, or <0 on error.  path = ORC_PATH_AVX2 | ORC_PATH_NAIVE. */
+double orc_bench_codec(const uint8_t *seq, size_t n, int n_threads, int reps, int path,
+                       int do_encode, int do_decode, uint64_t *ebuf, uint8_t *dbuf);
+int orc_have_avx2(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,137 @@
+"""Independent numpy restatement of the bitnuc hot path.  TEST INFRASTRUCTURE ONLY.
+
+A second, array-at-a-time statement of the same semantics as ``bitnuc_oracle.c``; the two are
+written differently on purpose (lookup tables + reshapes here, per-base loops there) and tests
+require them to agree with each other and with the reference's known-answer vectors.  Citations are
+relative to /root/reference/.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_CODE = np.full(256, 255, dtype=np.uint8)  # src/utils/packing/naive.rs:10-16
+for _ch, _v in ((b"Aa", 0), (b"Cc", 1), (b"Gg", 2), (b"Tt", 3)):
+    for _b in _ch:
+        _CODE[_b] = _v
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)  # src/utils/unpacking/naive.rs:15-21
+_SHIFTS = (2 * np.arange(32, dtype=np.uint64)).reshape(1, 32)
+M64 = (1 << 64) - 1
+
+
+class NpError(Exception):
+    def __init__(self, variant: str, *payload: int):
+        super().__init__(f"{variant}{payload}")
+        self.variant, self.payload = variant, payload
+
+    def key(self):
+        return (self.variant,) + tuple(self.payload)
+
+
+def first_invalid(seq: np.ndarray):
+    """(offset, byte) of the first non-ACGTacgt byte, or None."""
+    bad = np.flatnonzero(_CODE[seq] == 255)
+    return (int(bad[0]), int(seq[bad[0]])) if bad.size else None
+
+
+def encode(seq) -> np.ndarray:
+    """src/utils/packing/naive.rs:22-43 -- ceil(n/32) LSB-first words, zero-padded tail."""
+    seq = np.frombuffer(bytes(seq), dtype=np.uint8) if not isinstance(seq, np.ndarray) else seq
+    if seq.size == 0:
+        raise ZeroDivisionError("reference panics on encode(b'')")  # avx.rs:138
+    inv = first_invalid(seq)
+    if inv is not None:
+        raise NpError("InvalidBase", inv[1])
+    n_words = (seq.size + 31) // 32
+    codes = np.zeros(n_words * 32, dtype=np.uint64)
+    codes[: seq.size] = _CODE[seq]
+    return np.bitwise_or.reduce(codes.reshape(n_words, 32) << _SHIFTS, axis=1)
+
+
+def as_2bit(seq) -> int:
+    seq = np.frombuffer(bytes(seq), dtype=np.uint8)
+    if seq.size > 32:
+        raise NpError("SequenceTooLong", seq.size)  # checked before content, naive.rs:5-7
+    if seq.size == 0:
+        return 0
+    return int(encode(seq)[0])
+
+
+def decode(words, n_bases: int) -> np.ndarray:
+    """src/utils/unpacking/avx.rs:117-153 for well-formed input (enough words)."""
+    words = np.asarray(words, dtype=np.uint64)
+    if words.size < (n_bases + 31) // 32:
+        raise NpError("InvalidLength", n_bases)  # src/utils/unpacking/mod.rs:42-45
+    w = words[: (n_bases + 31) // 32].reshape(-1, 1)
+    return _ASCII[((w >> _SHIFTS) & np.uint64(3)).astype(np.uint8).reshape(-1)[:n_bases]]
+
+
+def from_2bit(packed: int, expected_size: int) -> bytes:
+    if expected_size > 32:
+        raise NpError("InvalidLength", expected_size)
+    return decode(np.array([packed & M64], dtype=np.uint64), expected_size).tobytes()
+
+
+def _popcount64(x: np.ndarray) -> np.ndarray:
+    return np.unpackbits(x.view(np.uint8).reshape(-1, 8), axis=1).sum(axis=1, dtype=np.uint64)
+
+
+def hdist_pairs(u, v, length: int) -> np.ndarray:
+    """src/utils/functions/hamming/scalar.rs:11-48, one result per (u[i], v[i])."""
+    if length > 32:
+        raise NpError("InvalidLength", length)
+    u, v = np.asarray(u, dtype=np.uint64), np.asarray(v, dtype=np.uint64)
+    mask = np.uint64(M64 if length == 32 else (1 << (2 * length)) - 1)
+    d = (u ^ v) & mask
+    d = (d | (d >> np.uint64(1))) & np.uint64(0x5555555555555555)
+    return _popcount64(np.ascontiguousarray(d)).astype(np.uint32)
+
+
+def hdist(e1, e2, n_bases: int) -> int:
+    """src/utils/functions/hamming/multi.rs:122-160; exact (unwrapped) total."""
+    e1, e2 = np.asarray(e1, dtype=np.uint64), np.asarray(e2, dtype=np.uint64)
+    need = (n_bases + 31) // 32
+    if e1.size < need or e2.size < need:
+        raise NpError("InvalidLength", n_bases)
+    full, rem = divmod(n_bases, 32)
+    total = int(hdist_pairs(e1[:full], e2[:full], 32).sum(dtype=np.uint64)) if full else 0
+    if rem:
+        total += int(hdist_pairs(e1[full : full + 1], e2[full : full + 1], rem)[0])
+    return total
+
+
+def base_counts(words, length: int) -> list:
+    """src/utils/analysis.rs:19-39 -- counts over the `length` decoded bases only."""
+    if length == 0:
+        return [0, 0, 0, 0]
+    asc = decode(words, length)
+    return [int((asc == ch).sum()) for ch in b"ACGT"]
+
+
+def gc_content(words, length: int) -> float:
+    """src/utils/analysis.rs:3-17 -- (gc as f64 / len as f64) * 100.0 in that order."""
+    if length == 0:
+        return 0.0
+    c = base_counts(words, length)
+    return float((np.float64(c[1] + c[2]) / np.float64(length)) * np.float64(100.0))
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def synth_words(seed: int, stream: int, first_word: int, n_words: int) -> np.ndarray:
+    """word j of stream s = splitmix64((seed ^ s*golden) + j)."""
+    base = (seed ^ ((stream * 0x9E3779B97F4A7C15) & M64)) & M64
+    with np.errstate(over="ignore"):
+        j = np.arange(first_word, first_word + n_words, dtype=np.uint64) + np.uint64(base)
+    return splitmix64(j)
+
+
+def synth_ascii(seed: int, stream: int, n_bases: int) -> np.ndarray:
+    """ASCII bases 0..n of a stream; by construction encode(synth_ascii) == synth_words (tail masked)."""
+    w = synth_words(seed, stream, 0, (n_bases + 31) // 32)
+    return decode(w, n_bases)

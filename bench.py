@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the bitnuc hot path on B200.
+
+Workload (BASELINE.json configs[1]): encode + decode of one contiguous 1 Gbase random sequence,
+device-resident, per GPU.  A "step" encodes the sequence and decodes it back: every base goes through
+the encode kernel once and the decode kernel once, so a step codes 2 x n_bases bases and
+``value`` = 2 x n_bases x n_gpus / step time, in Gbases/s.  At N > 1 every rank owns its own
+1 Gbase shard of an N-Gbase stream (contiguous range sharding on 64-base boundaries, no data-path
+collective) -> "scaling": "weak".  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  Inputs (1 GB ASCII, 250 MB packed) are larger than the
+126 MB L2, so no flush is needed between iterations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--bases B]
+
+``--impl reference`` times the reference's own CPU algorithm on the host cores: the reference is a
+Rust crate and there is no Rust toolchain in this image, so the arm runs the oracle's C/AVX2
+restatement of it (oracle/bitnuc_oracle.c, kind "port"), chunked over all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "encode+decode Gbases/s (device-timed; each base encoded once and decoded once per step)"
+UNIT = "Gbases/s"
+BYTES_PER_BASE = 1.25  # encode: 1 B read + 0.25 B written; decode: 0.25 B read + 1 B written
+SEED = 0x5EEDB17C0DE5
+SAMPLE_BASES = 1 << 28  # bounded CPU sample (reference arm / cpu_baseline)
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return None
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_codec_gbases(sample_bases: int, threads: int, reps: int):
+    """Times the oracle's AVX2 restatement of the reference (encode + decode) on the host cores."""
+    import oracle
+    from oracle import oracle_np as onp
+    seq = onp.synth_ascii(SEED, 0, sample_bases)
+    path = oracle.PATH_AVX2 if oracle.have_avx2() else oracle.PATH_NAIVE
+    t = oracle.CodecBench(seq, threads).run(reps=reps, path=path)
+    if t <= 0:
+        raise RuntimeError("oracle bench failed")
+    return 2 * sample_bases / t / 1e9, ("avx2" if path == oracle.PATH_AVX2 else "scalar")
+
+
+def run_reference(args):
+    """The reference arm: the reference's CPU implementation (C/AVX2 restatement) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    try:
+        oracle.build(native=True, force=True)  # the analogue of -C target-cpu=native on this box
+    except Exception:
+        oracle.build()
+    threads = host_threads()
+    sample = min(args.bases, SAMPLE_BASES)
+    from oracle import oracle_np as onp
+    seq = onp.synth_ascii(SEED, 0, sample)
+    path = oracle.PATH_AVX2 if oracle.have_avx2() else oracle.PATH_NAIVE
+    cb = oracle.CodecBench(seq, threads)
+    for _ in range(max(1, args.warmup)):
+        cb.run(1, path)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if cb.run(1, path) <= 0:
+            raise RuntimeError("oracle bench failed")
+    dt = time.perf_counter() - t0
+    value = 2 * sample * args.steps / dt / 1e9
+    single, _ = cpu_codec_gbases(min(sample, 1 << 26), 1, 2)
+    line = {
+        "impl": "reference", "metric": METRIC.replace("device-timed", "host wall-clock"), "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"encode+decode of a contiguous random sequence, CPU, bounded sample of {sample} bases per step "
+                               "(BASELINE.json configs[1] is 1e9 bases)", "bases_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} bases/step, {args.steps} steps, oracle C restatement of packing/avx.rs + "
+                                   f"unpacking/avx.rs ({'AVX2' if path == oracle.PATH_AVX2 else 'scalar'}), chunked over {threads} threads; "
+                                   f"single thread: {single:.3f} Gbases/s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import bitnuc_b200 as bn
+    from bitnuc_b200 import device as dv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.bases
+    # rank r owns bases [r*n, (r+1)*n) of stream 0: contiguous shards on 64-base boundaries
+    first_base = rank * ((n + 63) // 64 * 64)
+    asc = dv.synth_ascii(SEED, 0, first_base, n, device=dev)
+    words = torch.empty(dv.words_for(n), dtype=torch.int64, device=dev)
+    back = torch.empty(n, dtype=torch.uint8, device=dev)
+    status = dv.Status(dev)
+
+    def step():
+        dv.encode(asc, out=words, status=status)
+        dv.decode(words, n, out=back)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    status.check()
+    # parity inside the bench: the encode of a generated stream is the word stream itself
+    expect = dv.synth_words(SEED, 0, first_base // 32, dv.words_for(n), device=dev)
+    if n % 32:
+        expect[-1] &= (1 << (2 * (n % 32))) - 1
+    if not (torch.equal(words, expect) and torch.equal(back, asc)):
+        raise SystemExit("bench.py: encode/decode output is wrong; refusing to report a number")
+    del expect
+
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t_wall0 = time.time()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(K):
+        ev[i][0].record()
+        dv.encode(asc, out=words, status=status)
+        ev[i][1].record()
+        dv.decode(words, n, out=back)
+        ev[i][2].record()
+    end.record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    total_ms = start.elapsed_time(end)
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    status.check()
+
+    # ---- end to end through the public host API: pinned host buffers, H2D + kernels + D2H timed
+    ctx = bn.default_context(local)
+    h_seq = ctx.pinned_empty(n, np.uint8)
+    h_words = ctx.pinned_empty(dv.words_for(n), np.uint64)
+    h_back = ctx.pinned_empty(n, np.uint8)
+    h_seq[:] = asc.cpu().numpy()
+    e2e_steps = max(1, min(K, 5))
+    bn.encode_np(h_seq, ctx, out=h_words)  # warm-up: allocates the staging buffers
+    bn.decode_np(h_words, n, ctx, out=h_back)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        bn.encode_np(h_seq, ctx, out=h_words)
+        bn.decode_np(h_words, n, ctx, out=h_back)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if not np.array_equal(h_back, h_seq):
+        raise SystemExit("bench.py: end-to-end round trip is wrong")
+
+    times = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms, e2e_ms = times.tolist()
+
+    if rank == 0:
+        ms_per_step = total_ms / K
+        value = 2.0 * n * world / (ms_per_step * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        dom = "encode_kernel" if enc_ms >= dec_ms else "decode_kernel"
+        dom_ms = max(enc_ms, dec_ms)
+        achieved = BYTES_PER_BASE * n / (dom_ms * 1e-3) / 1e9
+        traffic = recorded_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: encode + decode of one contiguous random sequence, device-resident",
+                       "bases_per_gpu": n, "sharding": "contiguous base ranges on 64-base boundaries, no data-path collective",
+                       "l2": "inputs larger than L2 (1 GB ASCII + 0.25 GB packed per GPU vs 126 MB), no flush between iterations",
+                       "generator": "splitmix64 counter stream 0 (SURVEY.md 8d)"},
+            "kernels": {"encode_ms": enc_ms, "decode_ms": dec_ms,
+                        "encode_gbases_s": n / (enc_ms * 1e-3) / 1e9, "decode_gbases_s": n / (dec_ms * 1e-3) / 1e9,
+                        "encode_gbs": BYTES_PER_BASE * n / (enc_ms * 1e-3) / 1e9, "decode_gbs": BYTES_PER_BASE * n / (dec_ms * 1e-3) / 1e9},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": BYTES_PER_BASE * n,
+                         "traffic": (traffic or {}).get(dom) if traffic else None},
+            "e2e": {"value": 2.0 * n * world / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n + dv.words_for(n) * 8,
+                    "d2h_bytes_per_step": dv.words_for(n) * 8 + n, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "bitnuc_b200.encode_np + decode_np (bn_encode/bn_decode, pinned host buffers, chunked 3-stage pipeline)"},
+            "gpu_launches": 2 * K,
+            "clocks": clocks,
+        }
+        if world == 1:
+            try:
+                import oracle
+                try:
+                    oracle.build(native=True, force=True)
+                except Exception:
+                    oracle.build()
+                threads = host_threads()
+                v_all, isa = cpu_codec_gbases(SAMPLE_BASES, threads, 3)
+                v_one, _ = cpu_codec_gbases(1 << 26, 1, 3)
+                line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port",
+                                        "single_thread_value": v_one,
+                                        "sample": f"{SAMPLE_BASES} bases encode+decode, best of 3, C restatement of the reference's "
+                                                  f"{isa} path (oracle/bitnuc_oracle.c), chunked over {threads} host threads"}
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"error": str(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bases", type=int, default=1_000_000_000, help="bases per GPU (BASELINE configs[1]: 1e9)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,112 @@
+"""ctypes binding of libbitnuc_cuda.so -- one prototype per symbol declared in include/bitnuc_cuda.h."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from .errors import BitnucCudaError, NucleotideError, ReferencePanic
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libbitnuc_cuda.so"
+
+BN_OK = 0
+BN_ERR_CUDA, BN_ERR_ARGUMENT, BN_ERR_EMPTY_ENCODE, BN_ERR_NOMEM = -1, -2, -3, -4
+
+
+class BnError(C.Structure):
+    _fields_ = [("code", C.c_int32), ("base", C.c_uint8), ("pad_", C.c_uint8 * 3), ("a", C.c_uint64),
+                ("b", C.c_uint64), ("c", C.c_uint64), ("offset", C.c_uint64), ("record", C.c_uint64),
+                ("cuda_error", C.c_int32), ("pad2_", C.c_int32)]
+
+
+_vp, _sz, _u64, _u32, _int = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
+_errp = C.POINTER(BnError)
+
+# name -> (restype, argtypes); must list every symbol of include/bitnuc_cuda.h
+PROTOTYPES = {
+    "bn_abi_version": (_int, []),
+    "bn_device_count": (_int, []),
+    "bn_error_string": (_int, [_errp, C.c_char_p, _sz]),
+    "bn_ctx_create": (_int, [_int, C.POINTER(_vp)]),
+    "bn_ctx_destroy": (None, [_vp]),
+    "bn_ctx_device": (_int, [_vp]),
+    "bn_ctx_stream": (_vp, [_vp]),
+    "bn_ctx_synchronize": (_int, [_vp]),
+    "bn_ctx_set_chunk_bytes": (_int, [_vp, _sz]),
+    "bn_dev_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
+    "bn_dev_free": (_int, [_vp, _vp]),
+    "bn_host_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
+    "bn_host_free": (_int, [_vp, _vp]),
+    "bn_copy_h2d": (_int, [_vp, _vp, _vp, _sz]),
+    "bn_copy_d2h": (_int, [_vp, _vp, _vp, _sz]),
+    "bn_encode": (_int, [_vp, _vp, _sz, _vp, C.POINTER(_sz), _errp]),
+    "bn_decode": (_int, [_vp, _vp, _sz, _sz, _vp, _errp]),
+    "bn_as_2bit_batch": (_int, [_vp, _vp, _sz, _u32, _sz, _vp, _errp]),
+    "bn_from_2bit_batch": (_int, [_vp, _vp, _sz, _u32, _vp, _sz, _errp]),
+    "bn_hdist": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(_u64), _errp]),
+    "bn_hdist_pairs": (_int, [_vp, _vp, _vp, _sz, _u32, _vp, _errp]),
+    "bn_base_counts": (_int, [_vp, _vp, _sz, _sz, C.POINTER(_u64), C.POINTER(C.c_double), _errp]),
+    "bn_base_counts_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _errp]),
+    "bn_encode_batch": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _errp]),
+    "bn_encode_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "bn_decode_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "bn_as_2bit_batch_dev": (_int, [_vp, _vp, _vp, _sz, _u32, _sz, _vp, _vp]),
+    "bn_from_2bit_batch_dev": (_int, [_vp, _vp, _vp, _sz, _u32, _vp, _sz]),
+    "bn_hdist_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "bn_hdist_pairs_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "bn_base_counts_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "bn_base_counts_batch_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "bn_encode_batch_scratch_bytes": (_sz, [_sz]),
+    "bn_encode_batch_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),
+    "bn_synth_words_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
+    "bn_synth_ascii_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library.  There is no fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise BitnucCudaError(
+                f"{LIB_PATH} is missing: build it with `python -m bitnuc_b200.build` (needs nvcc). "
+                "bitnuc_b200 has no CPU fallback.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError here = header and library disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def error_string(err: BnError) -> str:
+    buf = C.create_string_buffer(256)
+    load().bn_error_string(C.byref(err), buf, 256)
+    return buf.value.decode()
+
+
+def raise_for(rc: int, err: BnError | None = None):
+    """Translate a bn_status into the reference's error vocabulary."""
+    if rc == BN_OK:
+        return
+    if rc == 1:
+        raise NucleotideError.InvalidBase(err.base if err is not None else 0)
+    if rc == 2:
+        raise NucleotideError.SequenceTooLong(err.a)
+    if rc == 3:
+        raise NucleotideError.InvalidLength(err.a)
+    if rc == 4:
+        raise NucleotideError.IndexOutOfBounds(err.a, err.b)
+    if rc == 5:
+        raise NucleotideError.InvalidRange(err.a, err.b, err.c)
+    if rc == 6:
+        raise NucleotideError.Unsupported()
+    if rc == BN_ERR_EMPTY_ENCODE:
+        raise ReferencePanic("encode of an empty sequence: the reference panics (packing/avx.rs:138)")
+    if err is not None and err.code == rc:
+        raise BitnucCudaError(error_string(err))
+    raise BitnucCudaError({BN_ERR_CUDA: "CUDA failure (no usable sm_100 device?)", BN_ERR_ARGUMENT: "invalid argument",
+                           BN_ERR_NOMEM: "out of memory"}.get(rc, f"bn_status {rc}"))

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's public API over the C ABI (host-pointer entry points).
+
+Same names, argument meaning and error behaviour as the functions re-exported at
+/root/reference/src/lib.rs:214-220.  ``Vec<u64>`` arguments are Python lists of ints that are
+cleared/filled, ``Vec<u8>`` arguments are ``bytearray``s that are appended to -- exactly what the
+reference does to them -- so the parity tests read like the reference's own tests.  The ``*_np``
+and ``*_batch`` functions are the array forms for real workloads.
+
+Every function runs CUDA kernels through libbitnuc_cuda.so; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import BnError, raise_for
+from .errors import NucleotideError
+
+M64 = (1 << 64) - 1
+
+
+class Context:
+    """A bn_ctx bound to one CUDA device (streams, staging buffers, status words)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        raise_for(self.lib.bn_ctx_create(device, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bn_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        raise_for(self.lib.bn_ctx_synchronize(self.handle))
+
+    def set_chunk_bytes(self, n: int):
+        raise_for(self.lib.bn_ctx_set_chunk_bytes(self.handle, n))
+
+    def pinned_empty(self, n: int, dtype=np.uint8) -> np.ndarray:
+        """A page-locked numpy array (freed with the context); host-pointer calls on it overlap."""
+        dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        raise_for(self.lib.bn_host_alloc(self.handle, max(1, n * dtype.itemsize), C.byref(p)))
+        buf = (C.c_uint8 * (n * dtype.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return arr
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device: int | None = None) -> Context:
+    if device is None:
+        device = _current_device()
+    with _default_lock:
+        ctx = _default.get(device)
+        if ctx is None:
+            ctx = _default[device] = Context(device)
+        return ctx
+
+
+def _current_device() -> int:
+    import os
+    return int(os.environ.get("BITNUC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def _u8(seq) -> np.ndarray:
+    if isinstance(seq, np.ndarray):
+        return np.ascontiguousarray(seq, dtype=np.uint8)
+    return np.frombuffer(bytes(seq), dtype=np.uint8)
+
+
+def _u64(words) -> np.ndarray:
+    if isinstance(words, np.ndarray) and words.dtype == np.uint64:
+        return np.ascontiguousarray(words)
+    return np.array([int(w) & M64 for w in words], dtype=np.uint64)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p) if a.size else None
+
+
+# ------------------------------------------------------------------ encode / decode ----------
+
+def encode_np(seq, ctx: Context | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """Packed words of ``seq`` (array form of ``encode_alloc``)."""
+    words, n, rc, err = _encode_raw(seq, ctx, out)
+    raise_for(rc, err)
+    return words[:n]
+
+
+def _encode_raw(seq, ctx, out=None):
+    ctx = ctx or default_context()
+    a = _u8(seq)
+    need = (a.size + 31) // 32
+    words = out if out is not None else np.empty(max(1, need), dtype=np.uint64)
+    n, err = C.c_size_t(0), BnError()
+    rc = ctx.lib.bn_encode(ctx.handle, _p(a), a.size, _p(words), C.byref(n), C.byref(err))
+    return words, n.value, rc, err
+
+
+def encode(sequence, ebuf: list, ctx: Context | None = None) -> None:
+    """``encode(&[u8], &mut Vec<u64>)`` (src/utils/mod.rs:22-25): clears ``ebuf``, then fills it.
+    On ``InvalidBase`` ``ebuf`` keeps the words of the chunks before the failing chunk
+    (src/utils/packing/avx.rs:132,142-143)."""
+    words, n, rc, err = _encode_raw(sequence, ctx)
+    if rc != _lib.BN_ERR_EMPTY_ENCODE:  # the reference panics before it clears anything useful
+        ebuf.clear()
+        ebuf.extend(int(w) for w in words[:n])
+    raise_for(rc, err)
+
+
+def encode_alloc(sequence, ctx: Context | None = None) -> list:
+    """``encode_alloc(&[u8]) -> Vec<u64>`` (src/utils/mod.rs:38-42)."""
+    ebuf: list = []
+    encode(sequence, ebuf, ctx)
+    return ebuf
+
+
+def decode_np(ebuf, n_bases: int, ctx: Context | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    ctx = ctx or default_context()
+    w = _u64(ebuf)
+    res = out if out is not None else np.empty(max(1, n_bases), dtype=np.uint8)
+    err = BnError()
+    raise_for(ctx.lib.bn_decode(ctx.handle, _p(w), w.size, n_bases, _p(res), C.byref(err)), err)
+    return res[:n_bases]
+
+
+def decode(ebuf, n_bases: int, dbuf: bytearray, ctx: Context | None = None) -> None:
+    """``decode(&[u64], usize, &mut Vec<u8>)`` (src/utils/mod.rs:60-62): appends to ``dbuf``."""
+    dbuf.extend(decode_np(ebuf, n_bases, ctx).tobytes())
+
+
+# ------------------------------------------------------------------ k-mers -------------------
+
+def as_2bit_batch(recs, n: int, k: int, stride: int | None = None, ctx: Context | None = None) -> np.ndarray:
+    """``as_2bit`` over ``n`` records of ``k`` bases laid out every ``stride`` bytes."""
+    ctx = ctx or default_context()
+    stride = k if stride is None else stride
+    a = _u8(recs)
+    if n and k <= 32 and a.size < (n - 1) * stride + k:
+        raise ValueError("record buffer too small")
+    out = np.empty(max(1, n), dtype=np.uint64)
+    err = BnError()
+    rc = ctx.lib.bn_as_2bit_batch(ctx.handle, _p(a), n, k, stride, _p(out), C.byref(err))
+    if rc == 1:
+        e = NucleotideError.InvalidBase(err.base)
+        e.record, e.offset = int(err.record), int(err.offset)
+        raise e
+    raise_for(rc, err)
+    return out[:n]
+
+
+def as_2bit(seq, ctx: Context | None = None) -> int:
+    """``as_2bit(&[u8]) -> Result<u64>`` (src/utils/packing/mod.rs:81-110)."""
+    a = _u8(seq)
+    return int(as_2bit_batch(a, 1, a.size, max(1, a.size), ctx)[0])
+
+
+def from_2bit_batch(packed, k: int, stride: int | None = None, ctx: Context | None = None,
+                    out: np.ndarray | None = None) -> np.ndarray:
+    """``from_2bit`` over an array of words; returns the ``(n-1)*stride + k`` output bytes."""
+    ctx = ctx or default_context()
+    stride = k if stride is None else stride
+    w = _u64(packed)
+    n = w.size
+    nbytes = (n - 1) * stride + k if n and k <= 32 else 0
+    res = out if out is not None else np.zeros(max(1, nbytes), dtype=np.uint8)
+    err = BnError()
+    raise_for(ctx.lib.bn_from_2bit_batch(ctx.handle, _p(w), n, k, _p(res), stride, C.byref(err)), err)
+    return res[:nbytes]
+
+
+def from_2bit(packed: int, expected_size: int, sequence: bytearray, ctx: Context | None = None) -> None:
+    """``from_2bit(u64, usize, &mut Vec<u8>)`` (src/utils/unpacking/mod.rs:119-147): appends."""
+    w = np.array([int(packed) & M64], dtype=np.uint64)
+    sequence.extend(from_2bit_batch(w, expected_size, max(1, expected_size), ctx).tobytes())
+
+
+def from_2bit_alloc(packed: int, expected_size: int, ctx: Context | None = None) -> bytearray:
+    """``from_2bit_alloc(u64, usize) -> Vec<u8>`` (src/utils/unpacking/mod.rs:178-182)."""
+    seq = bytearray()
+    from_2bit(packed, expected_size, seq, ctx)
+    return seq
+
+
+# ------------------------------------------------------------------ hamming ------------------
+
+def hdist_total(ebuf1, ebuf2, n_bases: int, ctx: Context | None = None) -> int:
+    """Exact (u64) mismatch count of two packed sequences."""
+    ctx = ctx or default_context()
+    a, b = _u64(ebuf1), _u64(ebuf2)
+    total, err = C.c_uint64(0), BnError()
+    raise_for(ctx.lib.bn_hdist(ctx.handle, _p(a), a.size, _p(b), b.size, n_bases, C.byref(total), C.byref(err)), err)
+    return int(total.value)
+
+
+def hdist(ebuf1, ebuf2, n_bases: int, ctx: Context | None = None) -> int:
+    """``hdist(&[u64], &[u64], usize) -> Result<u32>`` (src/utils/functions/hamming/multi.rs:122-160).
+    The reference accumulates in a ``u32`` (:130) that wraps in release builds; so does this."""
+    return hdist_total(ebuf1, ebuf2, n_bases, ctx) & 0xFFFFFFFF
+
+
+def hdist_pairs(u, v, length: int, ctx: Context | None = None) -> np.ndarray:
+    """``hdist_scalar`` over arrays of words: one u32 per pair."""
+    ctx = ctx or default_context()
+    a, b = _u64(u), _u64(v)
+    if a.size != b.size:
+        raise ValueError("u and v differ in length")
+    out = np.empty(max(1, a.size), dtype=np.uint32)
+    err = BnError()
+    raise_for(ctx.lib.bn_hdist_pairs(ctx.handle, _p(a), _p(b), a.size, length, _p(out), C.byref(err)), err)
+    return out[: a.size]
+
+
+def hdist_scalar(u: int, v: int, length: int, ctx: Context | None = None) -> int:
+    """``hdist_scalar(u64, u64, usize) -> Result<u32>`` (src/utils/functions/hamming/scalar.rs:11-48)."""
+    return int(hdist_pairs(np.array([u & M64], dtype=np.uint64), np.array([v & M64], dtype=np.uint64), length, ctx)[0])
+
+
+# ------------------------------------------------------------------ analysis -----------------
+
+def base_counts_gc(words, n_bases: int, ctx: Context | None = None):
+    """([A,C,G,T], gc%) of one packed sequence (src/utils/analysis.rs:3-39)."""
+    ctx = ctx or default_context()
+    w = _u64(words)
+    counts, gc, err = (C.c_uint64 * 4)(), C.c_double(0.0), BnError()
+    raise_for(ctx.lib.bn_base_counts(ctx.handle, _p(w), w.size, n_bases, counts, C.byref(gc), C.byref(err)), err)
+    return [int(x) for x in counts], float(gc.value)
+
+
+def base_counts_batch(words, word_offsets, lens, ctx: Context | None = None):
+    """Per-read ``base_counts`` / ``gc_content`` for a batch of packed reads.
+    Returns (counts[n,4] u64, gc[n] f64, totals[4])."""
+    ctx = ctx or default_context()
+    w, wo, ln = _u64(words), _u64(word_offsets), _u64(lens)
+    n = ln.size
+    counts = np.empty((max(1, n), 4), dtype=np.uint64)
+    gc = np.empty(max(1, n), dtype=np.float64)
+    totals, err = (C.c_uint64 * 4)(), BnError()
+    raise_for(ctx.lib.bn_base_counts_batch(ctx.handle, _p(w), w.size, _p(wo), _p(ln), n, _p(counts), _p(gc), totals,
+                                           C.byref(err)), err)
+    return counts[:n], gc[:n], [int(x) for x in totals]
+
+
+def encode_batch(data, offsets, ctx: Context | None = None, per_read_status: bool = False):
+    """``PackedSequence::new`` over a batch of reads ``data[offsets[r]:offsets[r+1]]``.
+    Returns (words, word_offsets[, read_status]); raises ``InvalidBase`` (with ``.record``,
+    ``.position`` and ``.offset`` attributes) for the first invalid base in input order unless
+    ``per_read_status`` is set, in which case the per-read first-invalid positions are returned."""
+    ctx = ctx or default_context()
+    a, off = _u8(data), _u64(offsets)
+    n = off.size - 1
+    if n < 0:
+        raise ValueError("offsets needs n_reads + 1 entries")
+    max_words = int((off[-1] - off[0]) // np.uint64(32)) + n if n else 0
+    words = np.empty(max(1, max_words), dtype=np.uint64)
+    wo = np.zeros(n + 1, dtype=np.uint64)
+    status = np.empty(max(1, n), dtype=np.uint32) if per_read_status else None
+    err = BnError()
+    rc = ctx.lib.bn_encode_batch(ctx.handle, _p(a), _p(off), n, _p(words), _p(wo), _p(status) if status is not None else None,
+                                 C.byref(err))
+    if rc == 1 and not per_read_status:
+        e = NucleotideError.InvalidBase(err.base)
+        e.record, e.position, e.offset = int(err.record), int(err.b), int(err.offset)
+        raise e
+    if rc != 1:
+        raise_for(rc, err)
+    words = words[: int(wo[n])]
+    return (words, wo, status[:n]) if per_read_status else (words, wo)

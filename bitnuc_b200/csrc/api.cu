@@ -1,0 +1,668 @@
+// api.cu -- the C ABI of libbitnuc_cuda.so (see include/bitnuc_cuda.h): contexts, the device-pointer
+// entry points (enqueue only) and the host-pointer entry points (H2D -> kernel -> D2H, chunked and
+// multi-stream for the streaming codec so PCIe copies overlap the kernels).
+#include "../../include/bitnuc_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "kernels.h"
+
+using bn::DeviceInfo;
+
+namespace {
+
+constexpr int kStages = 3;                       // pipeline depth of the host-pointer codec calls
+constexpr size_t kDefaultChunk = 64ull << 20;    // ASCII bytes per stage
+constexpr int kSlots = 8;                        // reusable device scratch buffers
+constexpr unsigned long long kNoError = ~0ull;
+
+struct Buffer {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct bn_ctx {
+    DeviceInfo di;
+    cudaStream_t stream = nullptr;               // context stream (device-pointer calls default to it)
+    cudaStream_t stage_stream[kStages] = {};
+    cudaEvent_t stage_done[kStages] = {};
+    Buffer stage_in[kStages], stage_out[kStages];
+    Buffer slot[kSlots];
+    unsigned long long* d_words = nullptr;       // 16 device status / accumulator words
+    unsigned long long* h_words = nullptr;       // pinned mirror
+    size_t chunk = kDefaultChunk;
+    std::mutex mu;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int set_err(bn_error_t* err, int code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
+    if (err) {
+        std::memset(err, 0, sizeof(*err));
+        err->code = code;
+        err->a = a;
+        err->b = b;
+        err->c = c;
+        if (code == BN_INVALID_BASE) err->base = (uint8_t)a;
+    }
+    return code;
+}
+
+int cuda_fail(bn_error_t* err, cudaError_t e) {
+    set_err(err, BN_ERR_CUDA);
+    if (err) err->cuda_error = (int32_t)e;
+    cudaGetLastError();  // clear the sticky-less error state
+    return BN_ERR_CUDA;
+}
+
+int invalid_base(bn_error_t* err, unsigned long long key, uint64_t base_offset) {
+    set_err(err, BN_INVALID_BASE, key & 0xFFu);
+    if (err) err->offset = (key >> 8) + base_offset;
+    return BN_INVALID_BASE;
+}
+
+#define BN_CUDA(expr)                                   \
+    do {                                                \
+        cudaError_t e__ = (expr);                       \
+        if (e__ != cudaSuccess) return cuda_fail(err, e__); \
+    } while (0)
+
+cudaError_t ensure(Buffer& b, size_t bytes) {
+    if (bytes <= b.cap) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e == cudaSuccess) b.cap = want;
+    return e;
+}
+
+cudaStream_t pick(bn_ctx* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ library / context -------
+
+int bn_abi_version(void) { return BN_ABI_VERSION; }
+
+int bn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int bn_error_string(const bn_error_t* e, char* buf, size_t cap) {
+    if (!e || !buf || cap == 0) return 0;
+    switch (e->code) {
+    case BN_OK: return snprintf(buf, cap, "Ok");
+    case BN_INVALID_BASE: return snprintf(buf, cap, "Invalid nucleotide base: %u", (unsigned)e->base);
+    case BN_SEQUENCE_TOO_LONG: return snprintf(buf, cap, "Sequence length %llu exceeds maximum", (unsigned long long)e->a);
+    case BN_INVALID_LENGTH: return snprintf(buf, cap, "Invalid length: %llu", (unsigned long long)e->a);
+    case BN_INDEX_OUT_OF_BOUNDS:
+        return snprintf(buf, cap, "Index %llu out of bounds for sequence of length %llu", (unsigned long long)e->a,
+                        (unsigned long long)e->b);
+    case BN_INVALID_RANGE:
+        return snprintf(buf, cap, "Invalid range %llu..%llu for sequence of length %llu", (unsigned long long)e->a,
+                        (unsigned long long)e->b, (unsigned long long)e->c);
+    case BN_UNSUPPORTED: return snprintf(buf, cap, "Unsupported architecture");
+    case BN_ERR_CUDA: return snprintf(buf, cap, "CUDA error %d: %s", e->cuda_error, cudaGetErrorString((cudaError_t)e->cuda_error));
+    case BN_ERR_ARGUMENT: return snprintf(buf, cap, "invalid argument");
+    case BN_ERR_EMPTY_ENCODE: return snprintf(buf, cap, "encode of an empty sequence (the reference panics)");
+    case BN_ERR_NOMEM: return snprintf(buf, cap, "out of memory");
+    default: return snprintf(buf, cap, "unknown error %d", e->code);
+    }
+}
+
+int bn_ctx_create(int device, bn_ctx** out) {
+    if (!out) return BN_ERR_ARGUMENT;
+    *out = nullptr;
+    int n = bn_device_count();
+    if (device < 0 || device >= n) return n == 0 ? BN_ERR_CUDA : BN_ERR_ARGUMENT;
+    bn_ctx* ctx = new (std::nothrow) bn_ctx();
+    if (!ctx) return BN_ERR_NOMEM;
+    DeviceGuard g(device);
+    ctx->di.device = device;
+    cudaDeviceProp prop;
+    bool ok = cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok) ctx->di.sm_count = prop.multiProcessorCount;
+    ok = ok && prop.major >= 10;  // kernels are built for sm_100a only; no fallback
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int s = 0; ok && s < kStages; ++s) {
+        ok = cudaStreamCreateWithFlags(&ctx->stage_stream[s], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->stage_done[s], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&ctx->d_words, 16 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_words, 16 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        bn_ctx_destroy(ctx);
+        return BN_ERR_CUDA;
+    }
+    *out = ctx;
+    return BN_OK;
+}
+
+void bn_ctx_destroy(bn_ctx* ctx) {
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx->di.device);
+        cudaDeviceSynchronize();
+        for (int s = 0; s < kStages; ++s) {
+            if (ctx->stage_stream[s]) cudaStreamDestroy(ctx->stage_stream[s]);
+            if (ctx->stage_done[s]) cudaEventDestroy(ctx->stage_done[s]);
+            if (ctx->stage_in[s].p) cudaFree(ctx->stage_in[s].p);
+            if (ctx->stage_out[s].p) cudaFree(ctx->stage_out[s].p);
+        }
+        for (auto& b : ctx->slot)
+            if (b.p) cudaFree(b.p);
+        if (ctx->d_words) cudaFree(ctx->d_words);
+        if (ctx->h_words) cudaFreeHost(ctx->h_words);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        cudaGetLastError();
+    }
+    delete ctx;
+}
+
+int bn_ctx_device(const bn_ctx* ctx) { return ctx ? ctx->di.device : -1; }
+void* bn_ctx_stream(const bn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int bn_ctx_synchronize(bn_ctx* ctx) {
+    if (!ctx) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    bn_error_t* err = nullptr;
+    BN_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < kStages; ++s) BN_CUDA(cudaStreamSynchronize(ctx->stage_stream[s]));
+    return BN_OK;
+}
+
+int bn_ctx_set_chunk_bytes(bn_ctx* ctx, size_t bytes) {
+    if (!ctx) return BN_ERR_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (bytes == 0) bytes = kDefaultChunk;
+    ctx->chunk = std::max<size_t>(4096, (bytes + 4095) & ~(size_t)4095);  // whole words, 16-byte aligned shards
+    return BN_OK;
+}
+
+int bn_dev_alloc(bn_ctx* ctx, size_t bytes, void** out) {
+    bn_error_t* err = nullptr;
+    if (!ctx || !out) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return BN_OK;
+}
+int bn_dev_free(bn_ctx* ctx, void* ptr) {
+    bn_error_t* err = nullptr;
+    if (!ctx) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_CUDA(cudaFree(ptr));
+    return BN_OK;
+}
+int bn_host_alloc(bn_ctx* ctx, size_t bytes, void** out) {
+    bn_error_t* err = nullptr;
+    if (!ctx || !out) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return BN_OK;
+}
+int bn_host_free(bn_ctx* ctx, void* ptr) {
+    bn_error_t* err = nullptr;
+    if (!ctx) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_CUDA(cudaFreeHost(ptr));
+    return BN_OK;
+}
+int bn_copy_h2d(bn_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    bn_error_t* err = nullptr;
+    if (!ctx) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    BN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BN_OK;
+}
+int bn_copy_d2h(bn_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    bn_error_t* err = nullptr;
+    if (!ctx) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BN_OK;
+}
+
+// ------------------------------------------------------------------ device-pointer calls ----
+
+#define BN_LAUNCH(expr)                                  \
+    do {                                                 \
+        cudaError_t e__ = (expr);                        \
+        if (e__ != cudaSuccess) {                        \
+            cudaGetLastError();                          \
+            return BN_ERR_CUDA;                          \
+        }                                                \
+    } while (0)
+
+int bn_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_seq, size_t n, uint64_t* d_out, uint64_t* d_status) {
+    if (!ctx || !d_status || (n && (!d_seq || !d_out))) return BN_ERR_ARGUMENT;
+    if (n == 0) return BN_ERR_EMPTY_ENCODE;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_encode(ctx->di, d_seq, n, d_out, reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_decode_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_words, size_t n_bases, uint8_t* d_out) {
+    if (!ctx || (n_bases && (!d_words || !d_out))) return BN_ERR_ARGUMENT;
+    if (n_words < (n_bases + 31) / 32) return BN_INVALID_LENGTH;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_decode(ctx->di, d_words, n_bases, d_out, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_as_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_recs, size_t n, uint32_t k, size_t stride,
+                         uint64_t* d_out, uint64_t* d_status) {
+    if (!ctx || !d_status || (n && (!d_out || (k && !d_recs)))) return BN_ERR_ARGUMENT;
+    if (k > 32) return BN_SEQUENCE_TOO_LONG;
+    if (stride < k) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_as_2bit_batch(ctx->di, d_recs, n, k, stride, d_out, reinterpret_cast<unsigned long long*>(d_status),
+                                       pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_from_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_packed, size_t n, uint32_t k, uint8_t* d_out,
+                           size_t stride) {
+    if (!ctx || (n && k && (!d_packed || !d_out))) return BN_ERR_ARGUMENT;
+    if (k > 32) return BN_INVALID_LENGTH;
+    if (stride < k) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_from_2bit_batch(ctx->di, d_packed, n, k, d_out, stride, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_hdist_dev(bn_ctx* ctx, void* stream, const uint64_t* d_a, const uint64_t* d_b, size_t n_bases, uint64_t* d_total) {
+    if (!ctx || !d_total || (n_bases && (!d_a || !d_b))) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_hdist(ctx->di, d_a, d_b, n_bases, reinterpret_cast<unsigned long long*>(d_total), pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_hdist_pairs_dev(bn_ctx* ctx, void* stream, const uint64_t* d_u, const uint64_t* d_v, size_t n_pairs, uint32_t len,
+                       uint32_t* d_out) {
+    if (!ctx || (n_pairs && (!d_u || !d_v || !d_out))) return BN_ERR_ARGUMENT;
+    if (len > 32) return BN_INVALID_LENGTH;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_hdist_pairs(ctx->di, d_u, d_v, n_pairs, len, d_out, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_base_counts_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_bases, uint64_t* d_counts, double* d_gc) {
+    if (!ctx || !d_counts || (n_bases && !d_words)) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_base_counts(ctx->di, d_words, n_bases, reinterpret_cast<unsigned long long*>(d_counts), d_gc,
+                                     pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_base_counts_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_words,
+                             const uint64_t* d_word_offsets, const uint64_t* d_lens, size_t n_reads, uint64_t* d_counts4,
+                             double* d_gc, uint64_t* d_totals) {
+    if (!ctx || (n_reads && (!d_word_offsets || !d_lens))) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_base_counts_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, n_words,
+                                           reinterpret_cast<unsigned long long*>(d_counts4), d_gc,
+                                           reinterpret_cast<unsigned long long*>(d_totals), pick(ctx, stream)));
+    return BN_OK;
+}
+
+size_t bn_encode_batch_scratch_bytes(size_t n_reads) { return bn::encode_batch_scratch_bytes(n_reads); }
+
+int bn_encode_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads,
+                        uint64_t* d_out_words, uint64_t* d_out_word_offsets, uint32_t* d_read_status, uint64_t* d_status,
+                        void* d_scratch) {
+    if (!ctx || !d_status || !d_out_word_offsets || (n_reads && (!d_offsets || !d_scratch))) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_encode_batch(ctx->di, d_bytes, d_offsets, n_reads, d_out_words, d_out_word_offsets, d_read_status,
+                                      reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, bn_error_t* err) {
+    if (!ctx || !d_status) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t s = pick(ctx, stream);
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words, d_status, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    BN_CUDA(cudaStreamSynchronize(s));
+    const unsigned long long key = ctx->h_words[0];
+    if (key == kNoError) return set_err(err, BN_OK);
+    return invalid_base(err, key, 0);
+}
+
+int bn_synth_words_dev(bn_ctx* ctx, void* stream, uint64_t seed, uint64_t stream_id, uint64_t first_word, size_t n_words,
+                       uint64_t* d_out) {
+    if (!ctx || (n_words && !d_out)) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_synth_words(ctx->di, seed, stream_id, first_word, n_words, d_out, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_synth_ascii_dev(bn_ctx* ctx, void* stream, uint64_t seed, uint64_t stream_id, uint64_t first_base, size_t n,
+                       uint8_t* d_out) {
+    if (!ctx || (n && !d_out) || (first_base % 32)) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_synth_ascii(ctx->di, seed, stream_id, first_base, n, d_out, pick(ctx, stream)));
+    return BN_OK;
+}
+
+// ------------------------------------------------------------------ host-pointer calls ------
+// encode / decode: the sequence is cut into chunks of ctx->chunk bases (a multiple of 4096, so every
+// chunk starts on a word boundary and all device buffers stay 16-byte aligned).  Chunk c runs on
+// stage c % kStages: H2D -> kernel -> D2H on that stage's stream, so with pinned host buffers the
+// upload of chunk c+1 overlaps the kernel of chunk c and the download of chunk c-1.
+
+int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* n_words, bn_error_t* err) {
+    if (n_words) *n_words = 0;
+    if (!ctx || (n && (!seq || !out))) return set_err(err, BN_ERR_ARGUMENT);
+    if (n == 0) return set_err(err, BN_ERR_EMPTY_ENCODE);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t chunk = ctx->chunk;
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
+    for (int s = 0; s < kStages && (size_t)s < n_chunks; ++s) {
+        BN_CUDA(ensure(ctx->stage_in[s], std::min(chunk, n)));
+        BN_CUDA(ensure(ctx->stage_out[s], (std::min(chunk, n) + 31) / 32 * 8));
+    }
+    auto retire = [&](size_t c) -> cudaError_t {
+        const int s = (int)(c % kStages);
+        cudaError_t e = cudaEventSynchronize(ctx->stage_done[s]);
+        if (e != cudaSuccess) return e;
+        const unsigned long long key = ctx->h_words[s];
+        if (key != kNoError) {
+            const unsigned long long global = (((key >> 8) + (unsigned long long)c * chunk) << 8) | (key & 0xFFu);
+            best = std::min(best, global);
+        }
+        return cudaSuccess;
+    };
+    size_t issued = 0, retired = 0;
+    while (retired < n_chunks && (issued < n_chunks || retired < issued)) {
+        if (issued < n_chunks && issued - retired < (size_t)kStages && best == kNoError) {
+            const size_t c = issued, off = c * chunk, len = std::min(chunk, n - off);
+            const int s = (int)(c % kStages);
+            cudaStream_t st = ctx->stage_stream[s];
+            unsigned long long* d_status = ctx->d_words + s;
+            BN_CUDA(cudaMemcpyAsync(ctx->stage_in[s].p, seq + off, len, cudaMemcpyHostToDevice, st));
+            BN_CUDA(bn::launch_encode(ctx->di, static_cast<const uint8_t*>(ctx->stage_in[s].p), len,
+                                      static_cast<uint64_t*>(ctx->stage_out[s].p), d_status, st));
+            BN_CUDA(cudaMemcpyAsync(out + off / 32, ctx->stage_out[s].p, (len + 31) / 32 * 8, cudaMemcpyDeviceToHost, st));
+            BN_CUDA(cudaMemcpyAsync(ctx->h_words + s, d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
+            ++issued;
+        } else if (retired < issued) {
+            BN_CUDA(retire(retired));
+            ++retired;
+        } else {
+            break;  // an error stopped the issue of further chunks and everything issued has retired
+        }
+    }
+    if (best != kNoError) {
+        if (n_words) *n_words = (size_t)((best >> 8) / 32);
+        return invalid_base(err, best, 0);
+    }
+    if (n_words) *n_words = (n + 31) / 32;
+    return set_err(err, BN_OK);
+}
+
+int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases, uint8_t* out, bn_error_t* err) {
+    if (!ctx || (n_bases && (!words || !out))) return set_err(err, BN_ERR_ARGUMENT);
+    if (n_words < (n_bases + 31) / 32) return set_err(err, BN_INVALID_LENGTH, n_bases);
+    if (n_bases == 0) return set_err(err, BN_OK);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t chunk = ctx->chunk;
+    const size_t n_chunks = (n_bases + chunk - 1) / chunk;
+    for (int s = 0; s < kStages && (size_t)s < n_chunks; ++s) {
+        BN_CUDA(ensure(ctx->stage_out[s], std::min(chunk, n_bases)));
+        BN_CUDA(ensure(ctx->stage_in[s], (std::min(chunk, n_bases) + 31) / 32 * 8));
+    }
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t off = c * chunk, len = std::min(chunk, n_bases - off);
+        const int s = (int)(c % kStages);
+        cudaStream_t st = ctx->stage_stream[s];
+        if (c >= (size_t)kStages) BN_CUDA(cudaEventSynchronize(ctx->stage_done[s]));
+        BN_CUDA(cudaMemcpyAsync(ctx->stage_in[s].p, words + off / 32, (len + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
+        BN_CUDA(bn::launch_decode(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), len,
+                                  static_cast<uint8_t*>(ctx->stage_out[s].p), st));
+        BN_CUDA(cudaMemcpyAsync(out + off, ctx->stage_out[s].p, len, cudaMemcpyDeviceToHost, st));
+        BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
+    }
+    for (int s = 0; s < kStages; ++s) BN_CUDA(cudaStreamSynchronize(ctx->stage_stream[s]));
+    return set_err(err, BN_OK);
+}
+
+// The remaining host-pointer calls stage whole buffers through reusable device scratch slots.
+
+int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, size_t stride, uint64_t* out, bn_error_t* err) {
+    if (!ctx || (n && (!out || (k && !recs)))) return set_err(err, BN_ERR_ARGUMENT);
+    if (k > 32) return set_err(err, BN_SEQUENCE_TOO_LONG, k);  // checked before any content (naive.rs:5-7)
+    if (stride < k) return set_err(err, BN_ERR_ARGUMENT);
+    if (n == 0) return set_err(err, BN_OK);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const size_t in_bytes = k ? (n - 1) * stride + k : 0;
+    BN_CUDA(ensure(ctx->slot[0], in_bytes ? in_bytes : 1));
+    BN_CUDA(ensure(ctx->slot[1], n * 8));
+    if (in_bytes) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, recs, in_bytes, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_as_2bit_batch(ctx->di, static_cast<const uint8_t*>(ctx->slot[0].p), n, k, stride,
+                                     static_cast<uint64_t*>(ctx->slot[1].p), ctx->d_words + 8, st));
+    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[1].p, n * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long key = ctx->h_words[8];
+    if (key != kNoError) {
+        invalid_base(err, key, 0);
+        if (err) err->record = (key >> 8) / stride;
+        return BN_INVALID_BASE;
+    }
+    return set_err(err, BN_OK);
+}
+
+int bn_from_2bit_batch(bn_ctx* ctx, const uint64_t* packed, size_t n, uint32_t k, uint8_t* out, size_t stride, bn_error_t* err) {
+    if (!ctx || (n && k && (!packed || !out))) return set_err(err, BN_ERR_ARGUMENT);
+    if (k > 32) return set_err(err, BN_INVALID_LENGTH, k);
+    if (stride < k) return set_err(err, BN_ERR_ARGUMENT);
+    if (n == 0 || k == 0) return set_err(err, BN_OK);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const size_t out_bytes = (n - 1) * stride + k;
+    BN_CUDA(ensure(ctx->slot[0], n * 8));
+    BN_CUDA(ensure(ctx->slot[1], out_bytes));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, packed, n * 8, cudaMemcpyHostToDevice, st));
+    if (stride != k)  // bytes between records must come back untouched
+        BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, out, out_bytes, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_from_2bit_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), n, k,
+                                       static_cast<uint8_t*>(ctx->slot[1].p), stride, st));
+    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[1].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    return set_err(err, BN_OK);
+}
+
+int bn_hdist(bn_ctx* ctx, const uint64_t* a, size_t n_words_a, const uint64_t* b, size_t n_words_b, size_t n_bases,
+             uint64_t* total, bn_error_t* err) {
+    if (!ctx || !total) return set_err(err, BN_ERR_ARGUMENT);
+    const size_t need = (n_bases + 31) / 32;
+    if (n_words_a < need || n_words_b < need) return set_err(err, BN_INVALID_LENGTH, n_bases);  // multi.rs:124-127
+    *total = 0;
+    if (n_bases == 0) return set_err(err, BN_OK);
+    if (!a || !b) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->slot[0], need * 8));
+    BN_CUDA(ensure(ctx->slot[1], need * 8));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, a, need * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, b, need * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_hdist(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
+                             n_bases, ctx->d_words + 8, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    *total = ctx->h_words[8];
+    return set_err(err, BN_OK);
+}
+
+int bn_hdist_pairs(bn_ctx* ctx, const uint64_t* u, const uint64_t* v, size_t n_pairs, uint32_t len, uint32_t* out, bn_error_t* err) {
+    if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
+    if (len > 32) return set_err(err, BN_INVALID_LENGTH, len);  // scalar.rs:13-15
+    if (n_pairs == 0) return set_err(err, BN_OK);
+    if (!u || !v || !out) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->slot[0], n_pairs * 8));
+    BN_CUDA(ensure(ctx->slot[1], n_pairs * 8));
+    BN_CUDA(ensure(ctx->slot[2], n_pairs * 4));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, u, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, v, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_hdist_pairs(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
+                                   n_pairs, len, static_cast<uint32_t*>(ctx->slot[2].p), st));
+    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[2].p, n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    return set_err(err, BN_OK);
+}
+
+int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases, uint64_t counts[4], double* gc, bn_error_t* err) {
+    if (!ctx || !counts) return set_err(err, BN_ERR_ARGUMENT);
+    const size_t need = (n_bases + 31) / 32;
+    if (n_words < need) return set_err(err, BN_INVALID_LENGTH, n_bases);
+    if (n_bases && !words) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->slot[0], need ? need * 8 : 8));
+    if (need) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, need * 8, cudaMemcpyHostToDevice, st));
+    double* d_gc = reinterpret_cast<double*>(ctx->d_words + 12);
+    BN_CUDA(bn::launch_base_counts(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), n_bases, ctx->d_words + 8, d_gc, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 5 * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) counts[i] = ctx->h_words[8 + i];
+    if (gc) std::memcpy(gc, ctx->h_words + 12, sizeof(double));
+    return set_err(err, BN_OK);
+}
+
+int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens,
+                         size_t n_reads, uint64_t* counts4, double* gc, uint64_t totals[4], bn_error_t* err) {
+    if (!ctx || (n_reads && (!word_offsets || !lens))) return set_err(err, BN_ERR_ARGUMENT);
+    for (size_t r = 0; r < n_reads; ++r) {  // every read must lie inside `words` (InvalidLength as in decode/hdist)
+        const uint64_t need = (lens[r] + 31) / 32;
+        if (word_offsets[r] > n_words || need > n_words - word_offsets[r]) {
+            set_err(err, BN_INVALID_LENGTH, lens[r]);
+            if (err) err->record = r;
+            return BN_INVALID_LENGTH;
+        }
+    }
+    if (totals) totals[0] = totals[1] = totals[2] = totals[3] = 0;
+    if (n_reads == 0) return set_err(err, BN_OK);
+    if (n_words && !words) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
+    BN_CUDA(ensure(ctx->slot[1], n_reads * 8));
+    BN_CUDA(ensure(ctx->slot[2], n_reads * 8));
+    if (counts4) BN_CUDA(ensure(ctx->slot[3], n_reads * 32));
+    if (gc) BN_CUDA(ensure(ctx->slot[4], n_reads * 8));
+    if (n_words) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, n_words * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, n_reads * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[2].p, lens, n_reads * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p),
+                                         static_cast<const uint64_t*>(ctx->slot[1].p), static_cast<const uint64_t*>(ctx->slot[2].p),
+                                         n_reads, n_words, counts4 ? static_cast<unsigned long long*>(ctx->slot[3].p) : nullptr,
+                                         gc ? static_cast<double*>(ctx->slot[4].p) : nullptr, ctx->d_words + 8, st));
+    if (counts4) BN_CUDA(cudaMemcpyAsync(counts4, ctx->slot[3].p, n_reads * 32, cudaMemcpyDeviceToHost, st));
+    if (gc) BN_CUDA(cudaMemcpyAsync(gc, ctx->slot[4].p, n_reads * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 4 * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    if (totals)
+        for (int i = 0; i < 4; ++i) totals[i] = ctx->h_words[8 + i];
+    return set_err(err, BN_OK);
+}
+
+int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, size_t n_reads, uint64_t* out_words,
+                    uint64_t* out_word_offsets, uint32_t* read_status, bn_error_t* err) {
+    if (!ctx || !out_word_offsets || (n_reads && !offsets)) return set_err(err, BN_ERR_ARGUMENT);
+    if (n_reads == 0) {
+        out_word_offsets[0] = 0;
+        return set_err(err, BN_OK);
+    }
+    for (size_t r = 0; r < n_reads; ++r)
+        if (offsets[r + 1] < offsets[r]) return set_err(err, BN_ERR_ARGUMENT);
+    const uint64_t lo = offsets[0], hi = offsets[n_reads];
+    if (hi > lo && (!bytes || !out_words)) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const size_t max_words = (size_t)((hi - lo) / 32 + n_reads);
+    // the byte buffer is staged at the same 16-byte phase as bytes+lo so offsets can be used unchanged
+    const size_t phase = lo & 15u;
+    BN_CUDA(ensure(ctx->slot[0], (hi - lo) + phase + 16));
+    BN_CUDA(ensure(ctx->slot[1], (n_reads + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[2], max_words * 8 + 8));
+    BN_CUDA(ensure(ctx->slot[3], (n_reads + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[4], bn::encode_batch_scratch_bytes(n_reads)));
+    if (read_status) BN_CUDA(ensure(ctx->slot[5], n_reads * 4));
+    uint8_t* d_bytes = static_cast<uint8_t*>(ctx->slot[0].p) + phase;
+    if (hi > lo) BN_CUDA(cudaMemcpyAsync(d_bytes, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_encode_batch(ctx->di, d_bytes - lo, static_cast<const uint64_t*>(ctx->slot[1].p), n_reads,
+                                    static_cast<uint64_t*>(ctx->slot[2].p), static_cast<uint64_t*>(ctx->slot[3].p),
+                                    read_status ? static_cast<uint32_t*>(ctx->slot[5].p) : nullptr, ctx->d_words + 8,
+                                    ctx->slot[4].p, st));
+    BN_CUDA(cudaMemcpyAsync(out_word_offsets, ctx->slot[3].p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
+    if (read_status) BN_CUDA(cudaMemcpyAsync(read_status, ctx->slot[5].p, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const size_t total_words = (size_t)out_word_offsets[n_reads];
+    if (total_words) {
+        BN_CUDA(cudaMemcpyAsync(out_words, ctx->slot[2].p, total_words * 8, cudaMemcpyDeviceToHost, st));
+        BN_CUDA(cudaStreamSynchronize(st));
+    }
+    const unsigned long long key = ctx->h_words[8];
+    if (key != kNoError) {
+        invalid_base(err, key, 0);
+        if (err) {
+            const uint64_t off = key >> 8;
+            const size_t r = (size_t)(std::upper_bound(offsets, offsets + n_reads + 1, off) - offsets) - 1;
+            err->record = r;
+            err->b = off - offsets[r];  // position inside the read
+        }
+        return BN_INVALID_BASE;
+    }
+    return set_err(err, BN_OK);
+}
+
+}  // extern "C"

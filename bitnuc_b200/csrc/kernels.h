@@ -1,0 +1,55 @@
+// kernels.h -- host-side launchers of the sm_100a kernels (internal to libbitnuc_cuda.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace bn {
+
+// Launch geometry shared by the streaming kernels: persistent grid of sm_count * blocks_per_sm CTAs.
+struct DeviceInfo {
+    int device = 0;
+    int sm_count = 148;
+};
+
+// codec.cu
+cudaError_t launch_encode(const DeviceInfo& di, const uint8_t* d_seq, size_t n, uint64_t* d_out,
+                          unsigned long long* d_status, cudaStream_t s);
+cudaError_t launch_decode(const DeviceInfo& di, const uint64_t* d_words, size_t n_bases, uint8_t* d_out,
+                          cudaStream_t s);
+
+// kmer.cu
+cudaError_t launch_as_2bit_batch(const DeviceInfo& di, const uint8_t* d_recs, size_t n, uint32_t k, size_t stride,
+                                 uint64_t* d_out, unsigned long long* d_status, cudaStream_t s);
+cudaError_t launch_from_2bit_batch(const DeviceInfo& di, const uint64_t* d_packed, size_t n, uint32_t k,
+                                   uint8_t* d_out, size_t stride, cudaStream_t s);
+
+// hamming.cu
+cudaError_t launch_hdist(const DeviceInfo& di, const uint64_t* d_a, const uint64_t* d_b, size_t n_bases,
+                         unsigned long long* d_total, cudaStream_t s);
+cudaError_t launch_hdist_pairs(const DeviceInfo& di, const uint64_t* d_u, const uint64_t* d_v, size_t n_pairs,
+                               uint32_t len, uint32_t* d_out, cudaStream_t s);
+
+// counts.cu
+cudaError_t launch_base_counts(const DeviceInfo& di, const uint64_t* d_words, size_t n_bases,
+                               unsigned long long* d_counts, double* d_gc, cudaStream_t s);
+cudaError_t launch_base_counts_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets,
+                                     const uint64_t* d_lens, size_t n_reads, size_t n_words_hint,
+                                     unsigned long long* d_counts4,
+                                     double* d_gc, unsigned long long* d_totals, cudaStream_t s);
+
+// batch.cu
+size_t encode_batch_scratch_bytes(size_t n_reads);
+cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets,
+                                size_t n_reads, uint64_t* d_out_words, uint64_t* d_out_word_offsets,
+                                uint32_t* d_read_status, unsigned long long* d_status, void* d_scratch,
+                                cudaStream_t s);
+
+// synth.cu
+cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,
+                               size_t n_words, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_synth_ascii(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_base,
+                               size_t n, uint8_t* d_out, cudaStream_t s);
+
+}  // namespace bn

@@ -1,0 +1,182 @@
+"""Device-resident variants: the same operations on torch CUDA tensors, enqueued on the current
+torch stream through the ``*_dev`` entry points of the C ABI.  torch is plumbing here (device
+memory, streams, torch.distributed); every kernel is ours.
+
+ASCII buffers are ``torch.uint8`` tensors, packed buffers ``torch.int64`` tensors (bit-identical to
+the reference's ``u64`` words).  Nothing synchronises unless stated: validation results live in a
+device status word (``Status``) that is read back lazily.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, api
+from ._lib import BnError, raise_for
+
+
+def _ptr(t: torch.Tensor | None):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ctx_for(t: torch.Tensor) -> api.Context:
+    if not t.is_cuda:
+        raise _lib.BitnucCudaError("device-resident calls need CUDA tensors (there is no CPU fallback)")
+    return api.default_context(t.device.index)
+
+
+class Status:
+    """Device-side validation status: min over invalid bases of (offset << 8 | byte)."""
+
+    def __init__(self, device):
+        self.word = torch.empty(1, dtype=torch.int64, device=device)
+        self.ctx = api.default_context(torch.device(device).index or 0)
+
+    def check(self):
+        """Synchronises the current stream; raises ``NucleotideError.InvalidBase`` if set."""
+        err = BnError()
+        rc = self.ctx.lib.bn_status_fetch(self.ctx.handle, _stream(), _ptr(self.word), C.byref(err))
+        if rc == 1:
+            e = _lib.NucleotideError.InvalidBase(err.base)
+            e.offset = int(err.offset)
+            raise e
+        raise_for(rc, err)
+
+
+def words_for(n_bases: int) -> int:
+    return (n_bases + 31) // 32
+
+
+def encode(seq: torch.Tensor, out: torch.Tensor | None = None, status: Status | None = None):
+    """ASCII ``uint8[n]`` -> packed ``int64[ceil(n/32)]``.  Returns (words, status)."""
+    ctx = _ctx_for(seq)
+    n = seq.numel()
+    if out is None:
+        out = torch.empty(words_for(n), dtype=torch.int64, device=seq.device)
+    status = status or Status(seq.device)
+    raise_for(ctx.lib.bn_encode_dev(ctx.handle, _stream(), _ptr(seq), n, _ptr(out), _ptr(status.word)))
+    return out, status
+
+
+def decode(words: torch.Tensor, n_bases: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    ctx = _ctx_for(words)
+    if out is None:
+        out = torch.empty(n_bases, dtype=torch.uint8, device=words.device)
+    rc = ctx.lib.bn_decode_dev(ctx.handle, _stream(), _ptr(words), words.numel(), n_bases, _ptr(out))
+    if rc == 3:
+        raise _lib.NucleotideError.InvalidLength(n_bases)
+    raise_for(rc)
+    return out
+
+
+def as_2bit_batch(recs: torch.Tensor, n: int, k: int, stride: int | None = None, out=None, status=None):
+    ctx = _ctx_for(recs)
+    stride = k if stride is None else stride
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=recs.device)
+    status = status or Status(recs.device)
+    rc = ctx.lib.bn_as_2bit_batch_dev(ctx.handle, _stream(), _ptr(recs), n, k, stride, _ptr(out), _ptr(status.word))
+    if rc == 2:
+        raise _lib.NucleotideError.SequenceTooLong(k)
+    raise_for(rc)
+    return out, status
+
+
+def from_2bit_batch(packed: torch.Tensor, k: int, stride: int | None = None, out=None) -> torch.Tensor:
+    ctx = _ctx_for(packed)
+    stride = k if stride is None else stride
+    n = packed.numel()
+    if out is None:
+        out = torch.zeros((n - 1) * stride + k if n and k <= 32 else 0, dtype=torch.uint8, device=packed.device)
+    rc = ctx.lib.bn_from_2bit_batch_dev(ctx.handle, _stream(), _ptr(packed), n, k, _ptr(out), stride)
+    if rc == 3:
+        raise _lib.NucleotideError.InvalidLength(k)
+    raise_for(rc)
+    return out
+
+
+def hdist(a: torch.Tensor, b: torch.Tensor, n_bases: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Exact mismatch count as a device ``int64[1]`` (``.item() & 0xFFFFFFFF`` is the reference's u32)."""
+    ctx = _ctx_for(a)
+    need = words_for(n_bases)
+    if a.numel() < need or b.numel() < need:
+        raise _lib.NucleotideError.InvalidLength(n_bases)
+    if out is None:
+        out = torch.empty(1, dtype=torch.int64, device=a.device)
+    raise_for(ctx.lib.bn_hdist_dev(ctx.handle, _stream(), _ptr(a), _ptr(b), n_bases, _ptr(out)))
+    return out
+
+
+def hdist_pairs(u: torch.Tensor, v: torch.Tensor, length: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    ctx = _ctx_for(u)
+    if out is None:
+        out = torch.empty(u.numel(), dtype=torch.int32, device=u.device)
+    rc = ctx.lib.bn_hdist_pairs_dev(ctx.handle, _stream(), _ptr(u), _ptr(v), u.numel(), length, _ptr(out))
+    if rc == 3:
+        raise _lib.NucleotideError.InvalidLength(length)
+    raise_for(rc)
+    return out
+
+
+def base_counts(words: torch.Tensor, n_bases: int, counts=None, gc=None):
+    """(counts int64[4] = [A,C,G,T], gc float64[1]) on the device."""
+    ctx = _ctx_for(words)
+    if words.numel() < words_for(n_bases):
+        raise _lib.NucleotideError.InvalidLength(n_bases)
+    counts = counts if counts is not None else torch.empty(4, dtype=torch.int64, device=words.device)
+    gc = gc if gc is not None else torch.empty(1, dtype=torch.float64, device=words.device)
+    raise_for(ctx.lib.bn_base_counts_dev(ctx.handle, _stream(), _ptr(words), n_bases, _ptr(counts), _ptr(gc)))
+    return counts, gc
+
+
+def base_counts_batch(words, word_offsets, lens, counts4=None, gc=None, totals=None, want_counts=True, want_gc=True):
+    """Per-read counts ``int64[n,4]``, gc ``float64[n]`` and totals ``int64[4]`` on the device."""
+    ctx = _ctx_for(words)
+    n = lens.numel()
+    dev = words.device
+    if counts4 is None and want_counts:
+        counts4 = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    if gc is None and want_gc:
+        gc = torch.empty(n, dtype=torch.float64, device=dev)
+    if totals is None:
+        totals = torch.empty(4, dtype=torch.int64, device=dev)
+    raise_for(ctx.lib.bn_base_counts_batch_dev(ctx.handle, _stream(), _ptr(words), words.numel(), _ptr(word_offsets),
+                                               _ptr(lens), n, _ptr(counts4), _ptr(gc), _ptr(totals)))
+    return counts4, gc, totals
+
+
+def encode_batch(data: torch.Tensor, offsets: torch.Tensor, max_words: int | None = None, read_status: bool = False,
+                 status: Status | None = None):
+    """Variable-length reads -> (words, word_offsets, read_status|None, status), all on the device."""
+    ctx = _ctx_for(data)
+    n = offsets.numel() - 1
+    dev = data.device
+    if max_words is None:
+        max_words = data.numel() // 32 + n
+    words = torch.empty(max_words, dtype=torch.int64, device=dev)
+    wo = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    rs = torch.empty(n, dtype=torch.int32, device=dev) if read_status else None
+    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n), dtype=torch.uint8, device=dev)
+    status = status or Status(dev)
+    raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, _stream(), _ptr(data), _ptr(offsets), n, _ptr(words), _ptr(wo),
+                                          _ptr(rs), _ptr(status.word), _ptr(scratch)))
+    return words, wo, rs, status
+
+
+def synth_words(seed: int, stream_id: int, first_word: int, n_words: int, device="cuda") -> torch.Tensor:
+    ctx = api.default_context(torch.device(device).index or 0)
+    out = torch.empty(n_words, dtype=torch.int64, device=device)
+    raise_for(ctx.lib.bn_synth_words_dev(ctx.handle, _stream(), seed, stream_id, first_word, n_words, _ptr(out)))
+    return out
+
+
+def synth_ascii(seed: int, stream_id: int, first_base: int, n: int, device="cuda") -> torch.Tensor:
+    ctx = api.default_context(torch.device(device).index or 0)
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    raise_for(ctx.lib.bn_synth_ascii_dev(ctx.handle, _stream(), seed, stream_id, first_base, n, _ptr(out)))
+    return out

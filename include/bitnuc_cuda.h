@@ -1,0 +1,184 @@
+/*
+ * bitnuc_cuda.h -- C ABI of the B200-native bitnuc hot path (libbitnuc_cuda.so).
+ *
+ * This is the drop-in boundary.  The reference (drbh/bitnuc, a pure-Rust crate) has no FFI of its
+ * own: its boundary is the set of safe-Rust functions re-exported at /root/reference/src/lib.rs:214-220.
+ * Each entry point below names the reference function it replaces (paths relative to
+ * /root/reference); the `bitnuc-cuda` Rust crate (rust/bitnuc-cuda) binds these
+ * symbols 1:1 and re-creates the reference signatures on top of them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  `stream` arguments are a cudaStream_t
+ *     passed as void* (NULL = the context's own stream).
+ *   - every function returns a bn_status: 0 = Ok, 1..6 = the six NucleotideError variants in
+ *     declaration order (src/error.rs:4-18), negative = failure outside the reference's vocabulary.
+ *   - `bn_error_t *err` (may be NULL) receives the variant payload.
+ *   - Packed layout is the reference's: base i of a word at bits [2i,2i+1], A=00 C=01 G=10 T=11,
+ *     32 bases per uint64_t, zero-padded tail (src/utils/packing/mod.rs:13-20, src/lib.rs:96-98).
+ *   - There is no CPU fallback: every call runs CUDA kernels built for sm_100a and fails with
+ *     BN_ERR_CUDA when no such device is usable.
+ *   - Host-pointer calls are synchronous and include the PCIe copies (pinned buffers from
+ *     bn_host_alloc make them fully asynchronous inside the call).  `_dev` calls take device
+ *     pointers, only enqueue work on `stream`, and report validation results through a device-side
+ *     status word that is read back later with bn_status_fetch.
+ *   - A context is bound to one device and is internally synchronised: it may be shared by host
+ *     threads, calls on one context serialise.  Use one context per thread for concurrency.
+ */
+#ifndef BITNUC_CUDA_H
+#define BITNUC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BN_ABI_VERSION 1
+
+typedef enum bn_status {
+    BN_OK = 0,
+    BN_INVALID_BASE = 1,        /* NucleotideError::InvalidBase(u8)                 src/error.rs:5  */
+    BN_SEQUENCE_TOO_LONG = 2,   /* NucleotideError::SequenceTooLong(usize)          src/error.rs:6  */
+    BN_INVALID_LENGTH = 3,      /* NucleotideError::InvalidLength(usize)            src/error.rs:7  */
+    BN_INDEX_OUT_OF_BOUNDS = 4, /* NucleotideError::IndexOutOfBounds{index,length}  src/error.rs:8  */
+    BN_INVALID_RANGE = 5,       /* NucleotideError::InvalidRange{start,end,length}  src/error.rs:12 */
+    BN_UNSUPPORTED = 6,         /* NucleotideError::Unsupported                     src/error.rs:17 */
+    BN_ERR_CUDA = -1,           /* CUDA runtime failure; err->cuda_error holds the cudaError_t */
+    BN_ERR_ARGUMENT = -2,       /* NULL / misaligned / inconsistent arguments */
+    BN_ERR_EMPTY_ENCODE = -3,   /* encode of an empty sequence: the reference panics
+                                   (src/utils/packing/avx.rs:138); bindings should panic too */
+    BN_ERR_NOMEM = -4
+} bn_status;
+
+typedef struct bn_error {
+    int32_t code;        /* bn_status */
+    uint8_t base;        /* InvalidBase: the offending byte (printed as a decimal integer) */
+    uint8_t pad_[3];
+    uint64_t a, b, c;    /* payload fields in declaration order (length | index,length | start,end,length) */
+    uint64_t offset;     /* InvalidBase: byte offset of the first invalid base in the input */
+    uint64_t record;     /* batched calls: index of the first failing record / read */
+    int32_t cuda_error;  /* BN_ERR_CUDA: cudaError_t */
+    int32_t pad2_;
+} bn_error_t;
+
+typedef struct bn_ctx bn_ctx;
+
+/* ------------------------------------------------------------------ library / context ------- */
+
+int bn_abi_version(void);
+/* Number of usable CUDA devices (0 when none; never negative). */
+int bn_device_count(void);
+/* Display string of an error (src/error.rs:20-45).  Returns bytes written excluding the NUL. */
+int bn_error_string(const bn_error_t *err, char *buf, size_t cap);
+
+int bn_ctx_create(int device, bn_ctx **out);
+void bn_ctx_destroy(bn_ctx *ctx);
+int bn_ctx_device(const bn_ctx *ctx);
+void *bn_ctx_stream(const bn_ctx *ctx);        /* the context's cudaStream_t */
+int bn_ctx_synchronize(bn_ctx *ctx);
+/* Staging chunk (bytes of ASCII per pipeline stage) used by the host-pointer calls. 0 = default. */
+int bn_ctx_set_chunk_bytes(bn_ctx *ctx, size_t bytes);
+
+/* Memory helpers for callers without their own CUDA runtime binding. */
+int bn_dev_alloc(bn_ctx *ctx, size_t bytes, void **out);
+int bn_dev_free(bn_ctx *ctx, void *ptr);
+int bn_host_alloc(bn_ctx *ctx, size_t bytes, void **out);   /* pinned, 256-byte aligned */
+int bn_host_free(bn_ctx *ctx, void *ptr);
+int bn_copy_h2d(bn_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* synchronous */
+int bn_copy_d2h(bn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);   /* synchronous */
+
+/* ------------------------------------------------------------------ host-pointer calls ------ */
+
+/* bitnuc::encode / encode_alloc (src/utils/mod.rs:22-25,38-42 -> src/utils/packing/avx.rs:130-151).
+ * out needs ceil(n/32) words.  On BN_INVALID_BASE, *n_words = offset/32 = the words the reference
+ * leaves in ebuf (those of the chunks before the failing chunk); out[0..*n_words) is valid.
+ * n == 0 -> BN_ERR_EMPTY_ENCODE. */
+int bn_encode(bn_ctx *ctx, const uint8_t *seq, size_t n, uint64_t *out, size_t *n_words, bn_error_t *err);
+
+/* bitnuc::decode (src/utils/mod.rs:60-62 -> src/utils/unpacking/avx.rs:117-153).  Writes n_bases
+ * bytes at out (the binding appends them to the caller's Vec).  n_words < ceil(n_bases/32) ->
+ * BN_INVALID_LENGTH(n_bases) (src/utils/unpacking/mod.rs:42-45); n_bases == 0 writes nothing. */
+int bn_decode(bn_ctx *ctx, const uint64_t *words, size_t n_words, size_t n_bases, uint8_t *out, bn_error_t *err);
+
+/* bitnuc::as_2bit over n records (src/utils/packing/mod.rs:81-110; the caller's `for kmer in ..`
+ * loop with `?`, README.md:52-56).  Record r = recs[r*stride .. r*stride+k).  k > 32 ->
+ * BN_SEQUENCE_TOO_LONG(k) before any content is looked at; otherwise the first failing record in
+ * index order reports BN_INVALID_BASE (err->record, err->offset = byte offset inside recs).
+ * k == 0 gives 0 for every record. stride >= k. */
+int bn_as_2bit_batch(bn_ctx *ctx, const uint8_t *recs, size_t n, uint32_t k, size_t stride, uint64_t *out, bn_error_t *err);
+
+/* bitnuc::from_2bit over n words (src/utils/unpacking/mod.rs:119-147).  Writes the low k bases of
+ * packed[r] at out[r*stride .. r*stride+k); bytes between records are not touched.  k > 32 ->
+ * BN_INVALID_LENGTH(k). */
+int bn_from_2bit_batch(bn_ctx *ctx, const uint64_t *packed, size_t n, uint32_t k, uint8_t *out, size_t stride, bn_error_t *err);
+
+/* bitnuc::hdist (src/utils/functions/hamming/multi.rs:122-160).  *total is the exact count; the
+ * reference's u32 result is (uint32_t)*total (its accumulator wraps in release builds, :130).
+ * n_words_a or n_words_b < ceil(n_bases/32) -> BN_INVALID_LENGTH(n_bases). */
+int bn_hdist(bn_ctx *ctx, const uint64_t *a, size_t n_words_a, const uint64_t *b, size_t n_words_b, size_t n_bases, uint64_t *total, bn_error_t *err);
+
+/* bitnuc::hdist_scalar over n pairs (src/utils/functions/hamming/scalar.rs:11-48):
+ * out[i] = mismatches among the low len bases of (u[i], v[i]).  len > 32 -> BN_INVALID_LENGTH(len). */
+int bn_hdist_pairs(bn_ctx *ctx, const uint64_t *u, const uint64_t *v, size_t n_pairs, uint32_t len, uint32_t *out, bn_error_t *err);
+
+/* BaseCount::base_counts + GCContent::gc_content of one packed sequence
+ * (src/utils/analysis.rs:19-39, :3-17).  counts = [A,C,G,T] over the n_bases valid bases only
+ * (tail padding is not counted as A); *gc = (gc as f64 / len as f64) * 100.0, 0.0 when empty.
+ * n_words < ceil(n_bases/32) -> BN_INVALID_LENGTH(n_bases).  gc may be NULL. */
+int bn_base_counts(bn_ctx *ctx, const uint64_t *words, size_t n_words, size_t n_bases, uint64_t counts[4], double *gc, bn_error_t *err);
+
+/* The same per read for a batch of packed reads: read r = words[word_offsets[r] ..) holding lens[r]
+ * bases.  counts4 = n_reads x [A,C,G,T] (may be NULL), gc = n_reads doubles (may be NULL),
+ * totals[4] = sum over reads (may be NULL). */
+int bn_base_counts_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, size_t n_reads, uint64_t *counts4, double *gc, uint64_t totals[4], bn_error_t *err);
+
+/* PackedSequence::new over a batch of variable-length reads (src/sequence.rs:40-52 -> encode):
+ * read r = bytes[offsets[r] .. offsets[r+1]); every read starts on a fresh word.
+ * out_word_offsets[n_reads+1] receives the exclusive prefix sum of ceil(len/32) (empty reads take
+ * no words, src/sequence.rs:42-46); out_words needs out_word_offsets[n_reads] words (an upper bound
+ * is (offsets[n_reads]-offsets[0])/32 + n_reads).  The first invalid base in input order reports
+ * BN_INVALID_BASE with err->record = read index, err->b = position in the read, err->offset = byte
+ * offset in bytes.  read_status (may be NULL) receives per read the position of its first invalid
+ * base or UINT32_MAX when the read is clean (the non-short-circuit variant). */
+int bn_encode_batch(bn_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, size_t n_reads, uint64_t *out_words, uint64_t *out_word_offsets, uint32_t *read_status, bn_error_t *err);
+
+/* ------------------------------------------------------------------ device-pointer calls ---- */
+/* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.
+ * Pointers are device pointers.  ASCII buffers and packed buffers must be 16-byte aligned.
+ * d_status is one device uint64_t that the call resets and the kernel updates with the smallest
+ * (offset << 8 | byte) of any invalid base; read it back with bn_status_fetch. */
+
+int bn_encode_dev(bn_ctx *ctx, void *stream, const uint8_t *d_seq, size_t n, uint64_t *d_out, uint64_t *d_status);
+int bn_decode_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_t n_words, size_t n_bases, uint8_t *d_out);
+int bn_as_2bit_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_recs, size_t n, uint32_t k, size_t stride, uint64_t *d_out, uint64_t *d_status);
+int bn_from_2bit_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_packed, size_t n, uint32_t k, uint8_t *d_out, size_t stride);
+/* *d_total (device uint64_t) is reset by the call, then accumulated. */
+int bn_hdist_dev(bn_ctx *ctx, void *stream, const uint64_t *d_a, const uint64_t *d_b, size_t n_bases, uint64_t *d_total);
+int bn_hdist_pairs_dev(bn_ctx *ctx, void *stream, const uint64_t *d_u, const uint64_t *d_v, size_t n_pairs, uint32_t len, uint32_t *d_out);
+/* d_counts = 4 device uint64_t [A,C,G,T]; d_gc = device double or NULL. */
+int bn_base_counts_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_t n_bases, uint64_t *d_counts, double *d_gc);
+/* d_totals (4 device uint64_t, may be NULL) is reset, then accumulated over the reads.  n_words (the
+ * size of d_words) only selects the thread-per-read or warp-per-read kernel; 0 = unknown. */
+int bn_base_counts_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_t n_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, uint64_t *d_counts4, double *d_gc, uint64_t *d_totals);
+/* d_out_word_offsets[n_reads+1] is produced by a device scan; d_scratch needs
+ * bn_encode_batch_scratch_bytes(n_reads) bytes. */
+size_t bn_encode_batch_scratch_bytes(size_t n_reads);
+int bn_encode_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const uint64_t *d_offsets, size_t n_reads, uint64_t *d_out_words, uint64_t *d_out_word_offsets, uint32_t *d_read_status, uint64_t *d_status, void *d_scratch);
+
+/* Synchronises `stream`, reads *d_status back and translates it: BN_OK, or BN_INVALID_BASE with
+ * err->base / err->offset filled (record/a are filled by the host-pointer wrappers). */
+int bn_status_fetch(bn_ctx *ctx, void *stream, const uint64_t *d_status, bn_error_t *err);
+
+/* ------------------------------------------------------------------ synthetic input --------- */
+/* Counter-based generator used by the benchmarks and parity tests: word j of
+ * stream s is splitmix64((seed ^ s*0x9E3779B97F4A7C15) + j); base 32j+i = "ACGT"[(W >> 2i) & 3].
+ * bn_synth_words_dev writes words [first_word, first_word+n_words); bn_synth_ascii_dev writes the
+ * ASCII of bases [first_base, first_base+n) with first_base a multiple of 32. */
+int bn_synth_words_dev(bn_ctx *ctx, void *stream, uint64_t seed, uint64_t stream_id, uint64_t first_word, size_t n_words, uint64_t *d_out);
+int bn_synth_ascii_dev(bn_ctx *ctx, void *stream, uint64_t seed, uint64_t stream_id, uint64_t first_base, size_t n, uint8_t *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BITNUC_CUDA_H */

@@ -1,0 +1,478 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's known-answer
+vectors.  Every test here needs a B200: run with ``pytest -m gpu``.
+
+The bar is bit-exact for every integer/byte result and exact ``==`` for gc_content (f64 computed in
+the reference's operation order from exact integer counts).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import OracleError, PATH_AVX2
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+ACGT_MIXED = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def bn():
+    import bitnuc_b200
+    assert bitnuc_b200._lib.load().bn_device_count() >= 1
+    return bitnuc_b200
+
+
+def rand_seq(rng, n, mixed=False):
+    a = ACGT_MIXED if mixed else ACGT
+    return a[rng.integers(0, a.size, n)]
+
+
+def gpu_error(bn, fn, *args):
+    with pytest.raises(bn.NucleotideError) as ei:
+        fn(*args)
+    return ei.value
+
+
+# ------------------------------------------------------------------ known-answer vectors -----
+
+def test_as_2bit_kats(bn, kats, to_int):
+    for k in kats["as_2bit"]:
+        assert bn.as_2bit(k["seq"].encode()) == to_int(k["packed"]), k["src"]
+    for k in kats["as_2bit_equal"]:
+        assert bn.as_2bit(k["a"].encode()) == bn.as_2bit(k["b"].encode())
+    for k in kats["as_2bit_errors"]:
+        seq = k["seq"].encode() if "seq" in k else k["seq_repeat"][0].encode() * k["seq_repeat"][1]
+        assert gpu_error(bn, bn.as_2bit, seq).key() == tuple(k["error"]), k["src"]
+    assert gpu_error(bn, bn.as_2bit, b"N" * 40).key() == ("SequenceTooLong", 40)  # length outranks content
+    assert bn.as_2bit(b"") == 0
+
+
+def test_from_2bit_kats(bn, kats, to_int):
+    for k in kats["from_2bit"]:
+        assert bytes(bn.from_2bit_alloc(to_int(k["packed"]), k["n"])) == k["seq"].encode(), k["src"]
+    for k in kats["from_2bit_errors"]:
+        assert gpu_error(bn, bn.from_2bit_alloc, to_int(k["packed"]), k["n"]).key() == tuple(k["error"])
+    k = kats["from_2bit_append"]
+    packed, buf = bn.as_2bit(k["seq"].encode()), bytearray()
+    for _ in range(k["calls"]):
+        bn.from_2bit(packed, k["n"], buf)
+    assert bytes(buf) == k["expected"].encode()
+    k = kats["from_2bit_prefixes"]
+    for n in range(k["lengths"][0], k["lengths"][1] + 1):
+        s = k["seq"].encode()[:n]
+        assert bytes(bn.from_2bit_alloc(bn.as_2bit(s), n)) == s
+    assert bytes(bn.from_2bit_alloc(0xFFFF, 0)) == b""
+
+
+def test_roundtrip_kats(bn, kats):
+    for s in kats["roundtrip_short"]["seqs"]:
+        b = s.encode()
+        assert bytes(bn.from_2bit_alloc(bn.as_2bit(b), len(b))) == b
+    rng = np.random.default_rng(1)
+    lo, hi = kats["roundtrip_lengths"]["lengths"]
+    for n in range(lo, hi + 1):  # every length 1..=1000, as src/utils/mod.rs:114-133
+        seq = rand_seq(rng, n)
+        ebuf, dbuf = [], bytearray()
+        bn.encode(seq, ebuf)
+        assert ebuf == oracle.encode_alloc(seq)
+        bn.decode(ebuf, n, dbuf)
+        assert bytes(dbuf) == seq.tobytes()
+
+
+def test_hdist_kats(bn, kats, to_int):
+    for k in kats["hdist_scalar"]:
+        assert bn.hdist_scalar(to_int(k["u"]), to_int(k["v"]), k["len"]) == k["dist"], k["src"]
+    for k in kats["hdist_scalar_seqs"]:
+        assert bn.hdist_scalar(bn.as_2bit(k["a"].encode()), bn.as_2bit(k["b"].encode()), len(k["a"])) == k["dist"]
+    for k in kats["hdist_scalar_errors"]:
+        assert gpu_error(bn, bn.hdist_scalar, to_int(k["u"]), to_int(k["v"]), k["len"]).key() == tuple(k["error"])
+    h = kats["hdist"]
+    z = [0] * h["too_small"]["n_words"]
+    assert gpu_error(bn, bn.hdist, z, z, h["too_small"]["n_bases"]).key() == tuple(h["too_small"]["error"])
+    s = h["identical"]["seq_repeat"][0].encode() * h["identical"]["seq_repeat"][1]
+    buf = bn.encode_alloc(s)
+    assert bn.hdist(buf, buf, len(s)) == 0
+    lo, hi = h["a_vs_t_lengths"]["lengths"]
+    for n in range(lo, hi + 1):
+        assert bn.hdist(bn.encode_alloc(b"A" * n), bn.encode_alloc(b"T" * n), n) == n
+    for k in h["mod4_vs_mod3"]:
+        s1 = bytes(b"ACGT"[i % 4] for i in range(k["n"]))
+        s2 = bytes(b"ACGT"[i % 3] for i in range(k["n"]))
+        assert bn.hdist(bn.encode_alloc(s1), bn.encode_alloc(s2), k["n"]) == k["dist"], k["src"]
+    a, t = bn.encode_alloc(b"A" * 70), bn.encode_alloc(b"T" * 70)
+    assert bn.hdist(a + [7], t + [9, 9], 33) == 33  # extra words ignored, tail masked
+
+
+def test_analysis_and_packed_sequence_kats(bn, kats):
+    for k in kats["analysis"]:
+        ps = bn.PackedSequence(k["seq"].encode())
+        assert ps.base_counts() == k["counts"], k["src"]
+        assert ps.gc_content() == k["gc"], k["src"]
+    ps = bn.PackedSequence(b"CAA")
+    assert ps.gc_content() == (1.0 / 3.0) * 100.0 != 100.0 * 1.0 / 3.0  # operation order is the reference's
+    assert bn.PackedSequence(b"T" * 33).base_counts() == [0, 0, 0, 33]    # padding is not 'A'
+    p = kats["packed_sequence"]
+    assert gpu_error(bn, bn.PackedSequence, p["new_error"]["seq"].encode()).key() == tuple(p["new_error"]["error"])
+    ps = bn.PackedSequence(p["get"]["seq"].encode())
+    assert bytes(ps.get(i) for i in range(len(ps))) == p["get"]["values"].encode()
+    ps = bn.PackedSequence(p["get_oob"]["seq"].encode())
+    assert gpu_error(bn, ps.get, p["get_oob"]["index"]).key() == tuple(p["get_oob"]["error"])
+    for k in p["slice"]:
+        assert bn.PackedSequence(k["seq"].encode()).slice(k["start"], k["end"]) == k["out"].encode()
+    for k in p["slice_errors"]:
+        ps = bn.PackedSequence(k["seq"].encode())
+        assert gpu_error(bn, ps.slice, k["start"], k["end"]).key() == tuple(k["error"])
+    for s in p["to_vec"]:
+        ps = bn.PackedSequence(s.encode())
+        assert ps.to_vec() == s.encode() and len(ps) == len(s) and ps.is_empty() == (len(s) == 0)
+    a, b = (bn.PackedSequence(s.encode()) for s in p["eq_hash"]["same"])
+    c = bn.PackedSequence(p["eq_hash"]["different"][1].encode())
+    assert a == b and a != c and hash(a) == hash(b) and c not in {a}
+    for k in kats["error_display"]:
+        assert str(bn.NucleotideError(*k["error"])) == k["text"], k["src"]
+
+
+# ------------------------------------------------------------------ differential vs oracle ---
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 2047, 2048, 2049, 4096 + 7,
+                               100_003, 1_000_000, (1 << 22) + 17])
+def test_encode_decode_matches_oracle(bn, n):
+    rng = np.random.default_rng(n)
+    seq = rand_seq(rng, n, mixed=True)
+    words = bn.encode_np(seq)
+    assert np.array_equal(words, oracle.encode_np(seq))
+    assert np.array_equal(words, onp.encode(seq))
+    dec = bn.decode_np(words, n)
+    assert np.array_equal(dec, oracle.decode_np(words, n, PATH_AVX2))
+    # extra words are ignored; partial decodes are prefixes
+    for m in {0, 1, n // 2, n - 1}:
+        assert np.array_equal(bn.decode_np(np.concatenate([words, words[:1]]), m), dec[:m])
+
+
+def test_encode_chunked_pipeline_matches_oracle(bn):
+    ctx = bn.Context(0)
+    ctx.set_chunk_bytes(8192)  # many chunks, ragged last one, all three stages in flight
+    rng = np.random.default_rng(5)
+    for n in [8192 * 7 + 13, 8192 * 3, 8191, 100_000]:
+        seq = rand_seq(rng, n, mixed=True)
+        words = bn.encode_np(seq, ctx)
+        assert np.array_equal(words, oracle.encode_np(seq))
+        assert np.array_equal(bn.decode_np(words, n, ctx), oracle.decode_np(words, n))
+        bad = seq.copy()
+        pos = [n - 1, 8192 * 2 + 5, 8192 * 2 + 4000]
+        for p in pos:
+            if p < n:
+                bad[p] = ord("N") if p != pos[1] else ord("x")
+        ebuf = []
+        err = gpu_error(bn, bn.encode, bad, ebuf, ctx)
+        first = min(p for p in pos if p < n)
+        assert err.key() == ("InvalidBase", int(bad[first]))
+        assert ebuf == [int(w) for w in oracle.encode_np(seq)[: first // 32]]
+    ctx.close()
+
+
+def test_encode_error_parity(bn):
+    rng = np.random.default_rng(11)
+    for n in [1, 5, 31, 32, 33, 64, 100, 1000, 70_001]:
+        seq = rand_seq(rng, n)
+        positions = sorted({0, n // 2, n - 1, max(0, n - 17), min(n - 1, 31), min(n - 1, 32)})
+        for pos in positions:
+            for byte in (ord("N"), ord("n"), 0, 255, ord("B"), ord("U"), ord("@"), ord("d"), ord(" ")):
+                bad = seq.copy()
+                bad[pos] = byte
+                ebuf, obuf = [1, 2, 3], []
+                err = gpu_error(bn, bn.encode, bad, ebuf)
+                with pytest.raises(OracleError) as oe:
+                    oracle.encode(bad, obuf)
+                assert err.key() == oe.value.key() == ("InvalidBase", byte)
+                assert ebuf == obuf and len(ebuf) == pos // 32
+    # several invalid bytes: the first in sequence order wins
+    bad = rand_seq(rng, 5000)
+    bad[[4999, 1234, 1235, 3000]] = [ord("X"), ord("Y"), ord("Z"), ord("N")]
+    assert gpu_error(bn, bn.encode_np, bad).key() == ("InvalidBase", ord("Y"))
+    with pytest.raises(bn.ReferencePanic):
+        bn.encode(b"", [])
+    # every byte value, alone in an otherwise valid sequence
+    base = rand_seq(rng, 100)
+    valid = set(b"ACGTacgt")
+    for b in range(256):
+        s = base.copy()
+        s[37] = b
+        if b in valid:
+            assert np.array_equal(bn.encode_np(s), oracle.encode_np(s))
+        else:
+            assert gpu_error(bn, bn.encode_np, s).key() == ("InvalidBase", b)
+
+
+def test_decode_length_contract(bn):
+    w = bn.encode_alloc(b"ACGT" * 16)
+    dbuf = bytearray(b"xx")
+    bn.decode(w, 40, dbuf)
+    assert bytes(dbuf) == b"xx" + b"ACGT" * 10  # appends, never clears
+    # short ebuf -> InvalidLength(n_bases), the reference's naive-path contract (unpacking/mod.rs:42-45)
+    assert gpu_error(bn, bn.decode, w[:1], 64, bytearray()).key() == ("InvalidLength", 64)
+    assert gpu_error(bn, bn.decode, w[:1], 40, bytearray()).key() == ("InvalidLength", 40)
+    dbuf = bytearray()
+    bn.decode(w, 0, dbuf)
+    assert bytes(dbuf) == b""
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 8, 15, 16, 17, 21, 31, 32])
+@pytest.mark.parametrize("layout", ["tight", "pad32", "pad40", "pad100"])
+def test_kmer_batches_match_oracle(bn, k, layout):
+    stride = {"tight": k, "pad32": 32, "pad40": 40, "pad100": 100}[layout]
+    rng = np.random.default_rng(1000 * k + stride)
+    for n in [1, 2, 255, 256, 257, 5000]:
+        buf = rng.integers(0, 256, (n - 1) * stride + k).astype(np.uint8)  # garbage between records
+        recs = rand_seq(rng, n * k, mixed=True).reshape(n, k)
+        for r in range(n):
+            buf[r * stride : r * stride + k] = recs[r]
+        expect = np.array([oracle.as_2bit(recs[r]) for r in range(n)], dtype=np.uint64)
+        got = bn.as_2bit_batch(buf, n, k, stride)
+        assert np.array_equal(got, expect)
+        # from_2bit: exactly k bytes per record, bytes between records untouched
+        noise = rng.integers(0, 2**63, n).astype(np.uint64) << np.uint64(1)  # bits above 2k are ignored
+        packed = expect | (noise << np.uint64(2 * k) if k < 32 else np.uint64(0))
+        out = np.full((n - 1) * stride + k, ord("#"), dtype=np.uint8)
+        res = bn.from_2bit_batch(packed, k, stride, out=out)
+        want = np.full((n - 1) * stride + k, ord("#"), dtype=np.uint8)
+        for r in range(n):
+            want[r * stride : r * stride + k] = np.frombuffer(bytes(oracle.from_2bit_alloc(int(expect[r]), k)), dtype=np.uint8)
+        assert np.array_equal(res, want)
+        # error parity: first failing record in index order, first bad byte inside it
+        if n >= 2:
+            bad = buf.copy()
+            r_bad = [n - 1, n // 2]
+            for r in r_bad:
+                bad[r * stride + (k - 1)] = ord("N")
+                bad[r * stride + k // 2] = ord("Z") if k // 2 != k - 1 else ord("N")
+            err = gpu_error(bn, bn.as_2bit_batch, bad, n, k, stride)
+            first_r = min(r_bad)
+            with pytest.raises(OracleError) as oe:
+                oracle.as_2bit(bad[first_r * stride : first_r * stride + k])
+            assert err.key() == oe.value.key()
+            assert err.record == first_r and err.offset == first_r * stride + k // 2
+
+
+def test_kmer_batch_argument_errors(bn):
+    assert gpu_error(bn, bn.as_2bit_batch, np.zeros(400, np.uint8), 10, 33, 40).key() == ("SequenceTooLong", 33)
+    assert gpu_error(bn, bn.from_2bit_batch, np.zeros(4, np.uint64), 33, 40).key() == ("InvalidLength", 33)
+    assert np.array_equal(bn.as_2bit_batch(np.zeros(0, np.uint8), 5, 0, 0), np.zeros(5, np.uint64))
+
+
+@pytest.mark.parametrize("length", [0, 1, 2, 15, 16, 17, 31, 32])
+def test_hdist_pairs_match_oracle(bn, length):
+    rng = np.random.default_rng(length)
+    for n in [1, 2, 3, 255, 256, 1001, 100_000]:
+        u = rng.integers(0, 2**64, n, dtype=np.uint64)
+        v = rng.integers(0, 2**64, n, dtype=np.uint64)
+        v[::3] = u[::3]
+        got = bn.hdist_pairs(u, v, length)
+        assert np.array_equal(got, onp.hdist_pairs(u, v, length))
+        for i in (0, n // 2, n - 1):
+            assert int(got[i]) == oracle.hdist_scalar(int(u[i]), int(v[i]), length)
+    assert gpu_error(bn, bn.hdist_pairs, [0], [0], 33).key() == ("InvalidLength", 33)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 4096, 4097, 1_000_003])
+def test_hdist_and_counts_match_oracle(bn, n):
+    rng = np.random.default_rng(n + 1)
+    nw = (n + 31) // 32
+    a = rng.integers(0, 2**64, nw + 2, dtype=np.uint64)  # two extra garbage words, unmasked tail bits
+    b = a.copy()
+    flip = rng.random(nw + 2) < 0.5
+    b[flip] = rng.integers(0, 2**64, int(flip.sum()), dtype=np.uint64)
+    assert bn.hdist_total(a, b, n) == oracle.hdist(a, b, n, wide=True) == onp.hdist(a, b, n)
+    assert bn.hdist(a, b, n) == oracle.hdist(a, b, n)
+    counts, gc = bn.base_counts_gc(a, n)
+    if n:
+        mask = np.uint64((1 << (2 * (n % 32))) - 1) if n % 32 else np.uint64(2**64 - 1)
+        clean = a[:nw].copy()
+        clean[-1] &= mask
+    else:
+        clean = a[:0]
+    assert counts == oracle.base_counts(clean, n) == onp.base_counts(clean, n)
+    assert gc == oracle.gc_content(clean, n)
+    assert sum(counts) == n
+    if n:
+        assert gpu_error(bn, bn.base_counts_gc, a[: nw - 1], n).key() == ("InvalidLength", n)
+        assert gpu_error(bn, bn.hdist, a[: nw - 1], b, n).key() == ("InvalidLength", n)
+
+
+def test_gc_content_is_bit_exact_for_awkward_ratios(bn):
+    rng = np.random.default_rng(3)
+    for n in [3, 7, 9, 11, 13, 33, 49, 97, 101, 150, 151, 1021]:
+        for _ in range(20):
+            seq = rand_seq(rng, n)
+            ps, ref = bn.PackedSequence(seq), oracle.PackedSequence(seq.tobytes())
+            assert ps.gc_content() == ref.gc_content()
+            assert ps.base_counts() == ref.base_counts()
+
+
+@pytest.mark.parametrize("read_len", [150, "mixed", "long"])
+def test_base_counts_batch_matches_oracle(bn, read_len):
+    rng = np.random.default_rng(17)
+    n_reads = 3000 if read_len != "long" else 40
+    if read_len == 150:
+        lens = np.full(n_reads, 150, dtype=np.uint64)
+    elif read_len == "mixed":
+        lens = rng.integers(0, 400, n_reads).astype(np.uint64)
+        lens[[0, 5, n_reads - 1]] = 0
+    else:
+        lens = rng.integers(2000, 9000, n_reads).astype(np.uint64)
+    nws = (lens + np.uint64(31)) // np.uint64(32)
+    wo = np.concatenate([[0], np.cumsum(nws)]).astype(np.uint64)
+    words = np.zeros(int(wo[-1]), dtype=np.uint64)
+    exp_counts, exp_gc = [], []
+    for r in range(n_reads):
+        seq = rand_seq(rng, int(lens[r]))
+        ps = oracle.PackedSequence(seq.tobytes())
+        words[int(wo[r]) : int(wo[r + 1])] = np.array(ps.data, dtype=np.uint64)
+        exp_counts.append(ps.base_counts())
+        exp_gc.append(ps.gc_content())
+    # unmasked garbage above the tail of every read must not matter
+    dirty = words.copy()
+    for r in range(n_reads):
+        rem = int(lens[r]) % 32
+        if rem:
+            dirty[int(wo[r + 1]) - 1] |= np.uint64(((1 << 64) - 1) ^ ((1 << (2 * rem)) - 1))
+    for w in (words, dirty):
+        counts, gc, totals = bn.base_counts_batch(w, wo[:-1], lens)
+        assert np.array_equal(counts, np.array(exp_counts, dtype=np.uint64).reshape(n_reads, 4))
+        assert np.array_equal(gc, np.array(exp_gc))  # exact f64 equality
+        assert totals == [int(x) for x in np.array(exp_counts, dtype=np.uint64).sum(axis=0)]
+
+
+def make_reads(rng, lens, mixed=True):
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = rand_seq(rng, int(offsets[-1]), mixed=mixed)
+    return data, offsets
+
+
+@pytest.mark.parametrize("profile", ["short", "cfg5", "with_empties", "single"])
+def test_encode_batch_matches_oracle(bn, profile):
+    rng = np.random.default_rng(23)
+    lens = {
+        "short": rng.integers(1, 70, 4000),
+        "cfg5": 50 + rng.integers(0, 9951, 300),   # 50 bp .. 10 kbp, SURVEY.md 8(d) cfg 5
+        "with_empties": np.where(rng.random(3000) < 0.3, 0, rng.integers(1, 200, 3000)),
+        "single": np.array([100_001]),
+    }[profile]
+    data, offsets = make_reads(rng, lens)
+    words, wo = bn.encode_batch(data, offsets)
+    exp_words, exp_wo = [], [0]
+    for r in range(len(lens)):
+        ps = oracle.PackedSequence(data[int(offsets[r]) : int(offsets[r + 1])].tobytes())
+        exp_words.extend(ps.data)
+        exp_wo.append(exp_wo[-1] + len(ps.data))
+    assert np.array_equal(wo, np.array(exp_wo, dtype=np.uint64))
+    assert np.array_equal(words, np.array(exp_words, dtype=np.uint64))
+    # the batch may start anywhere in the byte buffer (offsets[0] != 0)
+    shifted = np.concatenate([np.full(13, ord("#"), dtype=np.uint8), data])
+    w2, wo2 = bn.encode_batch(shifted, offsets + np.uint64(13))
+    assert np.array_equal(w2, words) and np.array_equal(wo2, wo)
+    # injected N: first invalid base in input order, with read index and position (cfg 5 error parity)
+    nonempty = [r for r in range(len(lens)) if lens[r] > 0]
+    victims = sorted(set(rng.choice(nonempty, size=min(5, len(nonempty)), replace=False).tolist()))
+    bad = data.copy()
+    where = {}
+    for r in victims:
+        pos = int(rng.integers(0, lens[r]))
+        bad[int(offsets[r]) + pos] = ord("N")
+        where[r] = pos
+    err = gpu_error(bn, bn.encode_batch, bad, offsets)
+    r0 = victims[0]
+    assert err.key() == ("InvalidBase", ord("N"))
+    assert (err.record, err.position, err.offset) == (r0, where[r0], int(offsets[r0]) + where[r0])
+    _, _, status = bn.encode_batch(bad, offsets, per_read_status=True)
+    expect = np.full(len(lens), 0xFFFFFFFF, dtype=np.uint32)
+    for r, pos in where.items():
+        expect[r] = pos
+    assert np.array_equal(status, expect)
+
+
+# ------------------------------------------------------------------ device-resident path -----
+
+def test_device_resident_codec_properties_at_scale(bn):
+    """Size-independent properties on 2^28+17 bases (ragged tail), all on the device:
+    encode(synth_ascii) == synth_words with the tail masked; decode(encode(x)) == x."""
+    import torch
+    from bitnuc_b200 import device as dv
+    seed, n = oracle.DEFAULT_SEED, (1 << 28) + 17
+    asc = dv.synth_ascii(seed, 0, 0, n)
+    words, status = dv.encode(asc)
+    status.check()
+    expect = dv.synth_words(seed, 0, 0, dv.words_for(n))
+    expect[-1] &= (1 << (2 * (n % 32))) - 1
+    assert torch.equal(words, expect)
+    back = dv.decode(words, n)
+    assert torch.equal(back, asc)
+    # the generator itself against the oracle on a window
+    assert np.array_equal(asc[: 10_000].cpu().numpy(), oracle.synth_ascii(seed, 0, 0, 10_000))
+    assert np.array_equal(asc[-4113:].cpu().numpy(), oracle.synth_ascii(seed, 0, n - 4113, 4113))
+    # whole-sequence reductions against independent torch arithmetic on the same device data
+    counts, gc = dv.base_counts(words, n)
+    hist = torch.bincount(asc.to(torch.int64), minlength=256)
+    want = [int(hist[c]) for c in b"ACGT"]
+    assert counts.tolist() == want
+    assert gc.item() == (float(want[1] + want[2]) / float(n)) * 100.0
+    other = dv.synth_words(seed, 3, 0, dv.words_for(n))
+    other_ascii = dv.decode(other, n)
+    assert dv.hdist(words, other, n).item() == int((asc != other_ascii).sum().item())
+    # an injected invalid base far into the buffer is located exactly
+    asc[(1 << 27) + 12345] = ord("N")
+    asc[(1 << 27) + 99999] = ord("Q")
+    _, st = dv.encode(asc)
+    with pytest.raises(bn.NucleotideError) as ei:
+        st.check()
+    assert ei.value.key() == ("InvalidBase", ord("N")) and ei.value.offset == (1 << 27) + 12345
+
+
+def test_device_resident_misaligned_pointers(bn):
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(9)
+    n = 100_000 + 5
+    seq = rand_seq(rng, n + 3, mixed=True)
+    t = torch.from_numpy(seq).cuda()
+    for shift in (1, 3):
+        words, st = dv.encode(t[shift : shift + n])
+        st.check()
+        assert np.array_equal(words.cpu().numpy().view(np.uint64), oracle.encode_np(seq[shift : shift + n]))
+        out = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+        dv.decode(words, n, out=out[shift : shift + n])
+        assert np.array_equal(out[shift : shift + n].cpu().numpy(), oracle.decode_np(words.cpu().numpy().view(np.uint64), n))
+    # packed buffers that are only 8-byte aligned
+    w = torch.from_numpy(rng.integers(0, 2**63, 5001, dtype=np.int64)).cuda()
+    a, b = w[1:2500], w[2501:5000]
+    nb = 2499 * 32 - 9
+    an, bnp = a.cpu().numpy().view(np.uint64), b.cpu().numpy().view(np.uint64)
+    assert dv.hdist(a, b, nb).item() == onp.hdist(an, bnp, nb)
+    assert np.array_equal(dv.hdist_pairs(a, b, 31).cpu().numpy().view(np.uint32), onp.hdist_pairs(an, bnp, 31))
+    clean = an.copy()
+    clean[-1] &= np.uint64((1 << (2 * (nb % 32))) - 1)
+    assert dv.base_counts(a, nb)[0].tolist() == onp.base_counts(clean, nb)
+
+
+def test_device_resident_kmers_cfg3_shape(bn):
+    """cfg 3 at reduced count: 31-mers, record r = first 31 bases of word r of stream 1."""
+    import torch
+    from bitnuc_b200 import device as dv
+    seed, n = oracle.DEFAULT_SEED, (1 << 20) + 3
+    words = dv.synth_words(seed, 1, 0, n)
+    expect = words & ((1 << 62) - 1)
+    recs = dv.from_2bit_batch(words, 31)                   # tight 31-byte records
+    assert recs.numel() == 31 * n
+    packed, st = dv.as_2bit_batch(recs, n, 31)
+    st.check()
+    assert torch.equal(packed, expect)
+    host = recs[: 31 * 100].cpu().numpy().reshape(100, 31)
+    for r in range(100):
+        assert host[r].tobytes() == bytes(oracle.from_2bit_alloc(int(expect[r].item()) & (2**64 - 1), 31))
+    padded = torch.zeros(32 * n, dtype=torch.uint8, device="cuda")
+    dv.from_2bit_batch(words, 32, 32, out=padded)
+    p2, st = dv.as_2bit_batch(padded, n, 31, 32)          # padded records, k < stride
+    st.check()
+    assert torch.equal(p2, expect)

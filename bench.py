@@ -232,6 +232,20 @@ def run_ours(args):
     status.check()
 
     # ---- end to end through the public host API: pinned host buffers, H2D + kernels + D2H timed
+    e2e_steps, e2e_s = 0, float("nan")
+    if not args.skip_e2e:
+        e2e_steps, e2e_s = run_e2e(bn, dv, np, torch, barrier, asc, n, local, K)
+
+    times = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms, e2e_ms = times.tolist()
+    report(args, world, rank, n, K, total_ms, enc_ms, dec_ms, e2e_ms, e2e_steps, clocks, dv)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(bn, dv, np, torch, barrier, asc, n, local, K):
     ctx = bn.default_context(local)
     h_seq = ctx.pinned_empty(n, np.uint8)
     h_words = ctx.pinned_empty(dv.words_for(n), np.uint64)
@@ -249,12 +263,10 @@ def run_ours(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if not np.array_equal(h_back, h_seq):
         raise SystemExit("bench.py: end-to-end round trip is wrong")
+    return e2e_steps, e2e_s
 
-    times = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms, e2e_ms = times.tolist()
 
+def report(args, world, rank, n, K, total_ms, enc_ms, dec_ms, e2e_ms, e2e_steps, clocks, dv):
     if rank == 0:
         ms_per_step = total_ms / K
         value = 2.0 * n * world / (ms_per_step * 1e-3) / 1e9
@@ -284,7 +296,9 @@ def run_ours(args):
             "gpu_launches": 2 * K,
             "clocks": clocks,
         }
-        if world == 1:
+        if args.skip_e2e:
+            line["e2e"] = None
+        if world == 1 and not args.skip_cpu:
             try:
                 import oracle
                 try:
@@ -301,8 +315,6 @@ def run_ours(args):
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"error": str(ex)}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -312,6 +324,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bases", type=int, default=1_000_000_000, help="bases per GPU (BASELINE configs[1]: 1e9)")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -20,8 +20,12 @@ def _ptr(t: torch.Tensor | None):
     return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None
 
 
+_CUDA_STREAM_LEGACY = 0x1  # cudaStreamLegacy: the C ABI reads NULL as "the context's own stream"
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream as a cudaStream_t, so torch events and tensors order with our kernels."""
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream or _CUDA_STREAM_LEGACY)
 
 
 def _ctx_for(t: torch.Tensor) -> api.Context:

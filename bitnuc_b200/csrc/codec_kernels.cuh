@@ -1,0 +1,238 @@
+// codec_kernels.cuh -- the ASCII <-> 2-bit streaming codec kernels, parametrised so that the
+// production build (codec.cu) and the tuning harness (tools/tune_codec.cu) compile the same code.
+//
+// Replaces the reference's per-ISA kernels behind encode/decode:
+//   encode: /root/reference/src/utils/packing/avx.rs:76-151 (naive.rs:4-43 defines the results)
+//   decode: /root/reference/src/utils/unpacking/avx.rs:26-33,117-153 (naive.rs:3-25)
+//
+// Data layout: the ASCII stream is viewed as 16-byte vectors, the packed stream as 32-bit words;
+// vector i <-> word i, so lane l of a warp always touches element tile_base + 32*j + l and every
+// global access is a fully coalesced 512-byte (vector) or 128-byte (word) warp transaction.
+// A "tile" is 32*U vectors (U loads in flight per thread, all issued before the first use).
+//
+// Template knobs
+//   U        vectors / words per thread per tile
+//   THREADS  CTA size
+//   SCHED    0: persistent grid, tiles strided over all warps (static partition)
+//            1: one CTA per chunk of (THREADS/32)*T tiles, handed out by the hardware CTA scheduler
+//               (dynamic load balance across the two dies)
+//   T        tiles per warp when SCHED == 1
+//   LP / SP  load / store cache policy
+//   DEC      decode flavour: 0 per-lane replicated 256-entry LUT in shared memory (conflict-free),
+//            1 single 1 KB LUT, 2 register-only (nibble spread + PRMT as a 4-entry byte LUT)
+#pragma once
+
+#include "common.cuh"
+
+namespace bn {
+
+enum { LD_NC_NOALLOC = 0, LD_PLAIN = 1, LD_CS = 2, LD_LU = 3 };
+enum { ST_CS = 0, ST_PLAIN = 1, ST_WT = 2, ST_NOALLOC = 3 };
+
+template <int LP>
+__device__ __forceinline__ uint4 ld128(const uint4* p) {
+    uint4 r;
+    if (LP == LD_NC_NOALLOC)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (LP == LD_PLAIN)
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (LP == LD_CS)
+        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else
+        asm volatile("ld.global.lu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <int LP>
+__device__ __forceinline__ uint32_t ld32(const uint32_t* p) {
+    uint32_t r;
+    if (LP == LD_NC_NOALLOC)
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    else if (LP == LD_PLAIN)
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    else if (LP == LD_CS)
+        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    else
+        asm volatile("ld.global.lu.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <int SP>
+__device__ __forceinline__ void st32(uint32_t* p, uint32_t v) {
+    if (SP == ST_CS)
+        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if (SP == ST_PLAIN)
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if (SP == ST_WT)
+        asm volatile("st.global.wt.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int SP>
+__device__ __forceinline__ void st128(uint4* p, uint4 v) {
+    if (SP == ST_CS)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (SP == ST_PLAIN)
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (SP == ST_WT)
+        asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Maps (CTA, warp, round) to tile indices for the two scheduling modes.
+template <int THREADS, int SCHED, int T>
+struct TileWalk {
+    static constexpr unsigned kWarps = THREADS / 32;
+    unsigned long long first, step, end;
+    __device__ __forceinline__ TileWalk(unsigned long long n_tiles) {
+        const unsigned warp = threadIdx.x >> 5;
+        if (SCHED == 0) {
+            first = (unsigned long long)blockIdx.x * kWarps + warp;
+            step = (unsigned long long)gridDim.x * kWarps;
+            end = n_tiles;
+        } else {  // CTA b owns tiles [b*kWarps*T, (b+1)*kWarps*T): round i, warp w -> b*kWarps*T + i*kWarps + w
+            first = (unsigned long long)blockIdx.x * (kWarps * T) + warp;
+            step = kWarps;
+            const unsigned long long stop = (unsigned long long)(blockIdx.x + 1) * (kWarps * T);
+            end = stop < n_tiles ? stop : n_tiles;
+        }
+    }
+    // grid size for n_tiles
+    static unsigned long long ctas(unsigned long long n_tiles) { return (n_tiles + kWarps * T - 1) / (kWarps * T); }
+};
+
+// ============================================================================ encode =========
+
+// Rare path: re-read this thread's vectors (address order = j order) and report the first invalid byte.
+static __device__ __noinline__ void report_first_invalid(const uint4* p, int n_vec, unsigned long long vec_index,
+                                                         unsigned long long* status) {
+    for (int j = 0; j < n_vec; ++j) {
+        const uint4 v = p[32 * j];
+        const int idx = first_invalid16(v);
+        if (idx < 16) {
+            const uint32_t w = idx < 4 ? v.x : idx < 8 ? v.y : idx < 12 ? v.z : v.w;
+            report_invalid(status, (vec_index + 32ull * j) * 16ull + idx, w >> (8 * (idx & 3)));
+            return;
+        }
+    }
+}
+
+// n_vec full 16-byte vectors, then `tail` (< 16) trailing bytes; out32 holds total32 = 2*ceil(n/32) words.
+template <int U, int THREADS, int SCHED, int T, int LP, int SP>
+__global__ void __launch_bounds__(THREADS)
+encode_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ out, unsigned long long n_vec, unsigned tail,
+              unsigned long long total32, unsigned long long* __restrict__ status) {
+    const unsigned lane = threadIdx.x & 31;
+    constexpr unsigned kTile = 32 * U;
+    const unsigned long long n_tiles = n_vec / kTile;
+    const TileWalk<THREADS, SCHED, T> walk(n_tiles);
+
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
+        const unsigned long long vec0 = t * kTile;
+        const uint4* p = in + vec0 + lane;
+        uint4 v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) v[j] = ld128<LP>(p + 32 * j);
+        uint32_t bad = 0, r[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) r[j] = pack16(v[j], bad);
+        uint32_t* q = out + vec0 + lane;
+#pragma unroll
+        for (int j = 0; j < U; ++j) st32<SP>(q + 32 * j, r[j]);
+        if (bad & kValidMask) report_first_invalid(p, U, vec0 + lane, status);
+    }
+
+    // ragged end (last CTA): the vectors after the last full tile, the trailing bytes (< 16) and the
+    // zero padding of the last 64-bit word
+    if (blockIdx.x == gridDim.x - 1) {
+        for (unsigned long long i = n_tiles * kTile + threadIdx.x; i < n_vec; i += THREADS) {
+            const uint4 v = ld128<LP>(in + i);
+            uint32_t bad = 0;
+            out[i] = pack16(v, bad);
+            if (bad & kValidMask) report_first_invalid(in + i, 1, i, status);
+        }
+        if (threadIdx.x == 0) {
+            const uint8_t* bytes = reinterpret_cast<const uint8_t*>(in + n_vec);
+            unsigned long long w = n_vec;
+            if (tail) {
+                uint32_t packed = 0;
+                for (unsigned i = 0; i < tail; ++i) {
+                    const uint32_t b = bytes[i];
+                    if (!byte_is_valid(b)) {
+                        report_invalid(status, n_vec * 16ull + i, b);
+                        break;
+                    }
+                    packed |= (((b >> 1) ^ (b >> 2)) & 3u) << (2 * i);
+                }
+                out[w++] = packed;
+            }
+            for (; w < total32; ++w) out[w] = 0;
+        }
+    }
+}
+
+// ============================================================================ decode =========
+
+constexpr int kLutWords = 256 * 32;
+
+// DEC == 2: no table in memory at all.  Each half-word (8 bases) is spread so that every 2-bit code
+// sits in its own nibble, then PRMT with the constant "ACGT" word acts as a 4-entry byte LUT whose
+// selector nibbles are the codes.
+__device__ __forceinline__ uint32_t spread_codes(uint32_t t /* [b_lo, 0, b_hi, 0] */) {
+    t = (t | (t << 4)) & 0x0F0F0F0Fu;
+    return (t | (t << 2)) & 0x33333333u;
+}
+__device__ __forceinline__ uint4 decode16_prmt(uint32_t w) {
+    constexpr uint32_t kAcgt = 0x54474341u;  // 'A','C','G','T'
+    const uint32_t lo = spread_codes(__byte_perm(w, 0, 0x4140));
+    const uint32_t hi = spread_codes(__byte_perm(w, 0, 0x4342));
+    return make_uint4(__byte_perm(kAcgt, kAcgt, lo), __byte_perm(kAcgt, kAcgt, lo >> 16),
+                      __byte_perm(kAcgt, kAcgt, hi), __byte_perm(kAcgt, kAcgt, hi >> 16));
+}
+
+template <int DEC>
+__device__ __forceinline__ uint4 decode16(uint32_t w, const uint32_t* lut_lane) {
+    if (DEC == 2) return decode16_prmt(w);
+    constexpr int kShift = DEC == 0 ? 5 : 0;  // replicated: entry e of lane l at word e*32 + l
+    return make_uint4(lut_lane[(w & 0xFFu) << kShift], lut_lane[((w >> 8) & 0xFFu) << kShift],
+                      lut_lane[((w >> 16) & 0xFFu) << kShift], lut_lane[(w >> 24) << kShift]);
+}
+
+// n_w32 full 32-bit words (16 bases each), then `tail` (< 16) bases from one more word.
+template <int U, int THREADS, int SCHED, int T, int LP, int SP, int DEC>
+__global__ void __launch_bounds__(THREADS)
+decode_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, unsigned long long n_w32, unsigned tail) {
+    __shared__ uint32_t lut[DEC == 0 ? kLutWords : DEC == 1 ? 256 : 1];
+    const unsigned lane = threadIdx.x & 31;
+    if (DEC == 0) {
+        for (int i = threadIdx.x; i < kLutWords; i += THREADS) lut[i] = ascii4_of_byte((uint32_t)i >> 5);
+        __syncthreads();
+    } else if (DEC == 1) {
+        for (int i = threadIdx.x; i < 256; i += THREADS) lut[i] = ascii4_of_byte((uint32_t)i);
+        __syncthreads();
+    }
+    const uint32_t* lut_lane = DEC == 0 ? lut + lane : lut;
+    constexpr unsigned kTile = 32 * U;
+    const unsigned long long n_tiles = n_w32 / kTile;
+    const TileWalk<THREADS, SCHED, T> walk(n_tiles);
+
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
+        const uint32_t* p = in + t * kTile + lane;
+        uint32_t w[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) w[j] = ld32<LP>(p + 32 * j);
+        uint4* q = out + t * kTile + lane;
+#pragma unroll
+        for (int j = 0; j < U; ++j) st128<SP>(q + 32 * j, decode16<DEC>(w[j], lut_lane));
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (unsigned long long i = n_tiles * kTile + threadIdx.x; i < n_w32; i += THREADS)
+            st128<SP>(out + i, decode16<DEC>(ld32<LP>(in + i), lut_lane));
+        if (tail && threadIdx.x == 0) {
+            const uint32_t w = in[n_w32];
+            uint8_t* o = reinterpret_cast<uint8_t*>(out + n_w32);
+            for (unsigned i = 0; i < tail; ++i) o[i] = (uint8_t)(0x54474341u >> (8 * ((w >> (2 * i)) & 3u)));
+        }
+    }
+}
+
+}  // namespace bn

@@ -8,7 +8,7 @@
 //   1. word offsets = exclusive prefix sum of ceil(len/32) over the reads (block sums, one-CTA scan
 //      of the sums, block-local scan + offset);
 //   2. encode, one thread per OUTPUT word: the word's read is found by a search of the word-offset
-//      array that is narrowed per CTA tile first, its <= 32 source bytes are fetched as nine aligned
+//      array that is narrowed per CTA tile first (tiles are pulled from a global atomic counter), its <= 32 source bytes are fetched as nine aligned
 //      32-bit loads and funnel-shifted into place, bytes past the end of the read are replaced by 'A'.
 // Work per thread is uniform whatever the length mix (50 bp .. 10 kbp).  HBM-bound at
 // 1 B/base in + 8 B per word out + 16 B per read of offsets.
@@ -129,15 +129,21 @@ constexpr int kBatchTile = kThreads * kBatchItems;      // output words per CTA 
 __global__ void __launch_bounds__(kThreads)
 encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ offsets, unsigned long long n_reads,
                     const uint64_t* __restrict__ word_offsets, uint64_t* __restrict__ out,
-                    uint32_t* __restrict__ read_status, unsigned long long* __restrict__ status) {
+                    uint32_t* __restrict__ read_status, unsigned long long* __restrict__ status,
+                    unsigned long long* __restrict__ tile_counter) {
     __shared__ unsigned long long range[2];
+    __shared__ unsigned long long tile_s;
     const unsigned long long total_words = word_offsets[n_reads];
     const unsigned long long buf_lo = offsets[0], buf_hi = offsets[n_reads];  // valid byte range of `bytes`
     const unsigned long long n_tiles = ceil_div(total_words, kBatchTile);
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (;;) {  // persistent CTAs pull tiles from a global counter: dynamic balance, word count unknown to the host
+        __syncthreads();
+        if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1ull);
+        __syncthreads();
+        const unsigned long long tile = tile_s;
+        if (tile >= n_tiles) break;
         const unsigned long long w0 = tile * kBatchTile;
         const unsigned long long w1 = w0 + kBatchTile < total_words ? w0 + kBatchTile : total_words;
-        __syncthreads();
         if (threadIdx.x < 2) range[threadIdx.x] = owner_read(word_offsets, 0, n_reads - 1, threadIdx.x ? w1 - 1 : w0);
         __syncthreads();
         const unsigned long long r_lo = range[0], r_hi = range[1];
@@ -192,7 +198,7 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
 }
 
 size_t encode_batch_scratch_bytes(size_t n_reads) {
-    return (ceil_div(n_reads ? n_reads : 1, kScanTile) + 1) * sizeof(unsigned long long);
+    return (ceil_div(n_reads ? n_reads : 1, kScanTile) + 2) * sizeof(unsigned long long);  // block sums, total, tile counter
 }
 
 cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets,
@@ -208,13 +214,16 @@ cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, co
     }
     unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
     const unsigned long long n_blocks = ceil_div(n_reads, kScanTile);
+    unsigned long long* tile_counter = sums + n_blocks + 1;
+    e = cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
     batch_block_sums_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(d_offsets, n_reads, sums);
     batch_scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n_blocks);
     batch_word_offsets_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(d_offsets, n_reads, sums, n_blocks, d_out_word_offsets);
     static const int resident = resident_blocks(encode_batch_kernel, kThreads, di);
     // the number of output words is only known on the device: launch a full persistent grid
     encode_batch_kernel<<<resident, kThreads, 0, s>>>(d_bytes, d_offsets, n_reads, d_out_word_offsets, d_out_words,
-                                                      d_read_status, d_status);
+                                                      d_read_status, d_status, tile_counter);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,82 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return r;
 }
 
+// ---------------------------------------------------------------- cache policies, tile walk ---
+
+enum { LD_NC_NOALLOC = 0, LD_PLAIN = 1, LD_CS = 2, LD_LU = 3 };
+enum { ST_CS = 0, ST_PLAIN = 1, ST_WT = 2, ST_NOALLOC = 3 };
+
+template <int LP>
+__device__ __forceinline__ uint4 ld128(const uint4* p) {
+    uint4 r;
+    if (LP == LD_NC_NOALLOC)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (LP == LD_PLAIN)
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (LP == LD_CS)
+        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else
+        asm volatile("ld.global.lu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <int LP>
+__device__ __forceinline__ uint32_t ld32(const uint32_t* p) {
+    uint32_t r;
+    if (LP == LD_NC_NOALLOC)
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    else if (LP == LD_PLAIN)
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    else if (LP == LD_CS)
+        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    else
+        asm volatile("ld.global.lu.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <int SP>
+__device__ __forceinline__ void st32(uint32_t* p, uint32_t v) {
+    if (SP == ST_CS)
+        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if (SP == ST_PLAIN)
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if (SP == ST_WT)
+        asm volatile("st.global.wt.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int SP>
+__device__ __forceinline__ void st128(uint4* p, uint4 v) {
+    if (SP == ST_CS)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (SP == ST_PLAIN)
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (SP == ST_WT)
+        asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Maps (CTA, warp, round) to tile indices for the two scheduling modes.
+template <int THREADS, int SCHED, int T>
+struct TileWalk {
+    static constexpr unsigned kWarps = THREADS / 32;
+    unsigned long long first, step, end;
+    __device__ __forceinline__ TileWalk(unsigned long long n_tiles) {
+        const unsigned warp = threadIdx.x >> 5;
+        if (SCHED == 0) {
+            first = (unsigned long long)blockIdx.x * kWarps + warp;
+            step = (unsigned long long)gridDim.x * kWarps;
+            end = n_tiles;
+        } else {  // CTA b owns tiles [b*kWarps*T, (b+1)*kWarps*T): round i, warp w -> b*kWarps*T + i*kWarps + w
+            first = (unsigned long long)blockIdx.x * (kWarps * T) + warp;
+            step = kWarps;
+            const unsigned long long stop = (unsigned long long)(blockIdx.x + 1) * (kWarps * T);
+            end = stop < n_tiles ? stop : n_tiles;
+        }
+    }
+    // grid size for n_tiles
+    static unsigned long long ctas(unsigned long long n_tiles) { return (n_tiles + kWarps * T - 1) / (kWarps * T); }
+};
+
 // ---------------------------------------------------------------- nucleotide arithmetic ------
 // ASCII -> 2-bit code, 4 bases per 32-bit word w (little-endian: byte k = base k):
 //   code  = ((b >> 1) ^ (b >> 2)) & 3        A/a=0 C/c=1 G/g=2 T/t=3   (bit 5 = case is ignored)
@@ -104,6 +180,21 @@ __device__ __forceinline__ uint32_t ascii4_of_byte(uint32_t e) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) r |= ((kAcgt >> (8 * ((e >> (2 * k)) & 3u))) & 0xFFu) << (8 * k);
     return r;
+}
+
+// Register-only decode: no table in memory at all.  Each half-word (8 bases) is spread so that every 2-bit code
+// sits in its own nibble, then PRMT with the constant "ACGT" word acts as a 4-entry byte LUT whose
+// selector nibbles are the codes.
+__device__ __forceinline__ uint32_t spread_codes(uint32_t t /* [b_lo, 0, b_hi, 0] */) {
+    t = (t | (t << 4)) & 0x0F0F0F0Fu;
+    return (t | (t << 2)) & 0x33333333u;
+}
+__device__ __forceinline__ uint4 decode16_prmt(uint32_t w) {
+    constexpr uint32_t kAcgt = 0x54474341u;  // 'A','C','G','T'
+    const uint32_t lo = spread_codes(__byte_perm(w, 0, 0x4140));
+    const uint32_t hi = spread_codes(__byte_perm(w, 0, 0x4342));
+    return make_uint4(__byte_perm(kAcgt, kAcgt, lo), __byte_perm(kAcgt, kAcgt, lo >> 16),
+                      __byte_perm(kAcgt, kAcgt, hi), __byte_perm(kAcgt, kAcgt, hi >> 16));
 }
 
 // per-base mismatch mask of two packed words: bit 2i set iff base i differs

@@ -44,39 +44,49 @@ __device__ __forceinline__ double gc_percent(unsigned long long gc, unsigned lon
     return __dmul_rn(__ddiv_rn(__ull2double_rn(gc), __ull2double_rn(len)), 100.0);
 }
 
+constexpr int kCntU = 4;
+constexpr int kCntThreads = 512;
+constexpr int kCntT = 4;  // tiles per warp: fewer CTAs -> fewer atomics on the three accumulators
+
 // acc[1] += popc(lo), acc[2] += popc(hi), acc[3] += popc(lo & hi) over the first n_bases bases.
-template <int U>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kCntThreads)
 base_counts_kernel(const uint4* __restrict__ in, unsigned long long n_vec, unsigned long long n_bases,
                    unsigned long long* __restrict__ acc) {
     __shared__ unsigned long long scratch[32];
     const unsigned lane = threadIdx.x & 31;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
-    const unsigned long long warp = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    constexpr unsigned kTile = 32 * U;
-    const unsigned long long n_tiles = ceil_div(n_vec, kTile);
-    unsigned long long l = 0, h = 0, t = 0;
-    for (unsigned long long tile = warp; tile < n_tiles; tile += n_warps) {
+    constexpr unsigned kTile = 32 * kCntU;
+    const unsigned long long n_tiles = n_vec / kTile;
+    const TileWalk<kCntThreads, 1, kCntT> walk(n_tiles);
+    Lht c = {0, 0, 0};  // <= kCntT * kCntU * 64 per thread
+    for (unsigned long long tile = walk.first; tile < walk.end; tile += walk.step) {
         const unsigned long long i0 = tile * kTile + lane;
-        uint4 v[U];
+        uint4 v[kCntU];
 #pragma unroll
-        for (int j = 0; j < U; ++j) v[j] = i0 + 32 * j < n_vec ? ld_stream_v4(in + i0 + 32 * j) : make_uint4(0, 0, 0, 0);
-        Lht c = {0, 0, 0};
+        for (int j = 0; j < kCntU; ++j) v[j] = ld128<LD_PLAIN>(in + i0 + 32 * j);
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
+        for (int j = 0; j < kCntU; ++j) {
             count2(v[j].x, v[j].y, c);
             count2(v[j].z, v[j].w, c);
         }
-        l += c.l;
-        h += c.h;
-        t += c.t;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // words after the last full vector, tail word masked
-        const uint64_t* w = reinterpret_cast<const uint64_t*>(in);
-        const unsigned long long full = n_bases / 32;
-        for (unsigned long long i = n_vec * 2; i < full; ++i) count_word64(w[i], l, h, t);
-        const unsigned rem = (unsigned)(n_bases % 32);
-        if (rem) count_word64(w[full] & ((1ull << (2 * rem)) - 1ull), l, h, t);
+    unsigned long long l = c.l, h = c.h, t = c.t;
+    if (blockIdx.x == gridDim.x - 1) {  // vectors after the last full tile, then single words, tail word masked
+        Lht d = {0, 0, 0};
+        for (unsigned long long i = n_tiles * kTile + threadIdx.x; i < n_vec; i += kCntThreads) {
+            const uint4 v = ld128<LD_PLAIN>(in + i);
+            count2(v.x, v.y, d);
+            count2(v.z, v.w, d);
+        }
+        l += d.l;
+        h += d.h;
+        t += d.t;
+        if (threadIdx.x == 0) {
+            const uint64_t* w = reinterpret_cast<const uint64_t*>(in);
+            const unsigned long long full = n_bases / 32;
+            for (unsigned long long i = n_vec * 2; i < full; ++i) count_word64(w[i], l, h, t);
+            const unsigned rem = (unsigned)(n_bases % 32);
+            if (rem) count_word64(w[full] & ((1ull << (2 * rem)) - 1ull), l, h, t);
+        }
     }
     l = block_sum_u64(l, scratch);
     h = block_sum_u64(h, scratch);
@@ -189,11 +199,10 @@ cudaError_t launch_base_counts(const DeviceInfo& di, const uint64_t* d_words, si
             base_counts_scalar_kernel<<<grid_for(ceil_div(ceil_div(n_bases, 32), kThreads), resident), kThreads, 0, s>>>(
                 d_words, n_bases, d_counts);
         } else {
-            constexpr int U = 4;
-            static const int resident = resident_blocks(base_counts_kernel<U>, kThreads, di);
             const unsigned long long n_vec = n_bases / 64;
-            base_counts_kernel<U><<<grid_for(ceil_div(ceil_div(n_vec, 32 * U), kWarpsPerBlock), resident), kThreads, 0, s>>>(
-                reinterpret_cast<const uint4*>(d_words), n_vec, n_bases, d_counts);
+            const unsigned long long ctas = TileWalk<kCntThreads, 1, kCntT>::ctas(n_vec / (32 * kCntU));
+            base_counts_kernel<<<(unsigned)(ctas ? ctas : 1), kCntThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_words), n_vec,
+                                                                                   n_bases, d_counts);
         }
     }
     base_counts_finalize_kernel<<<1, 1, 0, s>>>(d_counts, n_bases, d_gc);

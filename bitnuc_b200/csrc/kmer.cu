@@ -38,52 +38,56 @@ __device__ __noinline__ void report_record_invalid(const uint8_t* rec, unsigned 
     }
 }
 
+constexpr int kKmerU = 4;
+constexpr int kKmerThreads = 512;
+
 // stride == 32, aligned: lane parity selects the low/high half of a record.
-template <int U>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kKmerThreads)
 as_2bit_padded_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ out, unsigned long long n_vec, int k,
                       unsigned long long* __restrict__ status) {
     const unsigned lane = threadIdx.x & 31;
-    const int half = (lane & 1) * 16;  // vectors 32*j + lane keep the lane's parity
+    const int half = (lane & 1) * 16;  // vectors 32*j + lane keep the lane's parity (ragged loop: THREADS is even too)
     const uint32_t m0 = keep_bytes(k - half), m1 = keep_bytes(k - half - 4), m2 = keep_bytes(k - half - 8),
                    m3 = keep_bytes(k - half - 12);
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
-    const unsigned long long warp = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    constexpr unsigned kTile = 32 * U;
-    const unsigned long long n_tiles = ceil_div(n_vec, kTile);
-    for (unsigned long long t = warp; t < n_tiles; t += n_warps) {
-        const unsigned long long v0 = t * kTile + lane;
-        uint4 v[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-            v[j] = v0 + 32 * j < n_vec ? ld_stream_v4(in + v0 + 32 * j) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-        uint32_t bad = 0, r[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            v[j].x = (v[j].x & m0) | (0x41414141u & ~m0);
-            v[j].y = (v[j].y & m1) | (0x41414141u & ~m1);
-            v[j].z = (v[j].z & m2) | (0x41414141u & ~m2);
-            v[j].w = (v[j].w & m3) | (0x41414141u & ~m3);
-            r[j] = pack16(v[j], bad);
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-            if (v0 + 32 * j < n_vec) st_stream_u32(out + v0 + 32 * j, r[j]);
-        if (bad & kValidMask) {
-            for (int j = 0; j < U; ++j) {
-                const unsigned long long vi = v0 + 32 * j;
-                if (vi >= n_vec) break;
-                const int kk = k - half < 0 ? 0 : (k - half > 16 ? 16 : k - half);
-                const uint8_t* rec = reinterpret_cast<const uint8_t*>(in + vi);
-                bool found = false;
-                for (int i = 0; i < kk; ++i)
-                    if (!byte_is_valid(rec[i])) {
-                        report_invalid(status, vi * 16ull + i, rec[i]);
-                        found = true;
-                        break;
-                    }
-                if (found) break;
+    const int kk = k - half < 0 ? 0 : (k - half > 16 ? 16 : k - half);  // bases of this half-record
+    constexpr unsigned kTile = 32 * kKmerU;
+    const unsigned long long n_tiles = n_vec / kTile;
+    const TileWalk<kKmerThreads, 1, 1> walk(n_tiles);
+    auto masked = [&](uint4 v) {
+        v.x = (v.x & m0) | (0x41414141u & ~m0);
+        v.y = (v.y & m1) | (0x41414141u & ~m1);
+        v.z = (v.z & m2) | (0x41414141u & ~m2);
+        v.w = (v.w & m3) | (0x41414141u & ~m3);
+        return v;
+    };
+    auto report = [&](unsigned long long vi) {
+        const uint8_t* rec = reinterpret_cast<const uint8_t*>(in + vi);
+        for (int i = 0; i < kk; ++i)
+            if (!byte_is_valid(rec[i])) {
+                report_invalid(status, vi * 16ull + i, rec[i]);
+                return true;
             }
+        return false;
+    };
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
+        const unsigned long long v0 = t * kTile + lane;
+        uint4 v[kKmerU];
+#pragma unroll
+        for (int j = 0; j < kKmerU; ++j) v[j] = ld128<LD_PLAIN>(in + v0 + 32 * j);
+        uint32_t bad = 0, r[kKmerU];
+#pragma unroll
+        for (int j = 0; j < kKmerU; ++j) r[j] = pack16(masked(v[j]), bad);
+#pragma unroll
+        for (int j = 0; j < kKmerU; ++j) st_stream_u32(out + v0 + 32 * j, r[j]);
+        if (bad & kValidMask)
+            for (int j = 0; j < kKmerU; ++j)
+                if (report(v0 + 32 * j)) break;
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (unsigned long long i = n_tiles * kTile + threadIdx.x; i < n_vec; i += kKmerThreads) {
+            uint32_t bad = 0;
+            out[i] = pack16(masked(ld128<LD_PLAIN>(in + i)), bad);
+            if (bad & kValidMask) report(i);
         }
     }
 }
@@ -98,21 +102,19 @@ as_2bit_staged_kernel(const uint8_t* __restrict__ recs, unsigned long long n, un
                       uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
     __shared__ __align__(16) uint8_t smem[kStageBytes];
     const unsigned long long total_bytes = (n - 1) * stride + k;
-    const unsigned long long n_groups = ceil_div(n, kStageRecords);
-    for (unsigned long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const unsigned long long r0 = g * kStageRecords;
+    {   // one group of kStageRecords records per CTA, handed out by the hardware CTA scheduler
+        const unsigned long long r0 = (unsigned long long)blockIdx.x * kStageRecords;
         const unsigned cnt = (unsigned)(n - r0 < kStageRecords ? n - r0 : kStageRecords);
         const unsigned long long b0 = r0 * stride;                               // first byte of the span
         const unsigned long long b1 = b0 + (unsigned long long)(cnt - 1) * stride + k;  // one past the last
         const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(recs) + b0) & 15u);
         const uint8_t* base = recs + b0 - mis;                                    // 16-byte aligned
         const unsigned n_vec = (unsigned)((mis + (b1 - b0) + 15) / 16);
-        __syncthreads();  // previous group's readers are done
         for (unsigned i = threadIdx.x; i < n_vec; i += blockDim.x) {
             const long long lo = (long long)i * 16 - mis;  // span-relative offset of this vector
             uint4 v;
             if ((long long)b0 + lo >= 0 && (long long)b0 + lo + 16 <= (long long)total_bytes) {
-                v = ld_stream_v4(reinterpret_cast<const uint4*>(base) + i);
+                v = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(base) + i);
             } else {  // vector straddles the buffer edge: byte loads with bounds
                 uint32_t w[4] = {0, 0, 0, 0};
                 for (int j = 0; j < 16; ++j) {
@@ -166,35 +168,26 @@ as_2bit_generic_kernel(const uint8_t* __restrict__ recs, unsigned long long n, u
 
 // ============================================================================ from_2bit ======
 
-constexpr int kLutWords = 256 * 32;  // per-lane replicated 256-entry table, see codec.cu
-
-__device__ __forceinline__ void lut_init(uint32_t* lut) {
-    for (int i = threadIdx.x; i < kLutWords; i += blockDim.x) lut[i] = ascii4_of_byte((uint32_t)i >> 5);
-    __syncthreads();
-}
-__device__ __forceinline__ uint4 lut_decode16(uint32_t w, const uint32_t* lut_lane) {
-    return make_uint4(lut_lane[(w & 0xFFu) << 5], lut_lane[((w >> 8) & 0xFFu) << 5],
-                      lut_lane[((w >> 16) & 0xFFu) << 5], lut_lane[(w >> 24) << 5]);
-}
+constexpr int kTightChunks = 8;  // 16-byte output chunks per thread
 
 // Tightly packed records (stride == k, 16 <= k <= 32), 16-byte aligned output: one thread per
-// 16-byte output chunk; a chunk spans at most two records.
-__global__ void __launch_bounds__(kThreads)
+// 16-byte output chunk; a chunk spans at most two records.  A CTA owns kKmerThreads * kTightChunks
+// consecutive chunks; (record, position) is found by one division per thread, then advanced.
+__global__ void __launch_bounds__(kKmerThreads)
 from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n, unsigned k,
                        uint8_t* __restrict__ out) {
-    __shared__ uint32_t lut[kLutWords];
-    lut_init(lut);
-    const uint32_t* lut_lane = lut + (threadIdx.x & 31);
     const unsigned long long total = n * k;
     const unsigned long long n_chunks = total / 16;
-    const unsigned long long T = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // (record, position) of byte 16*first, advanced incrementally by 16*T bytes per round
-    unsigned long long r = (first * 16) / k;
-    unsigned pos = (unsigned)((first * 16) % k);
-    const unsigned long long dr = (T * 16) / k;
-    const unsigned dpos = (unsigned)((T * 16) % k);
-    for (unsigned long long c = first; c < n_chunks; c += T) {
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * (kKmerThreads * kTightChunks) + threadIdx.x;
+    unsigned long long r = (c0 * 16) / k;
+    unsigned pos = (unsigned)((c0 * 16) % k);
+    constexpr unsigned kStepBytes = kKmerThreads * 16;
+    const unsigned long long dr = kStepBytes / k;
+    const unsigned dpos = kStepBytes % k;
+#pragma unroll 2
+    for (int it = 0; it < kTightChunks; ++it) {
+        const unsigned long long c = c0 + (unsigned long long)it * kKmerThreads;
+        if (c >= n_chunks) break;
         const unsigned avail = k - pos;
         const uint64_t w0 = __ldg(packed + r);
         uint32_t x = (uint32_t)(w0 >> (2 * pos));
@@ -202,7 +195,7 @@ from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n
             const uint64_t w1 = __ldg(packed + r + 1);  // exists: the chunk is full, so bytes follow
             x = (x & ((1u << (2 * avail)) - 1u)) | (uint32_t)(w1 << (2 * avail));
         }
-        st_stream_v4(reinterpret_cast<uint4*>(out) + c, lut_decode16(x, lut_lane));
+        st_stream_v4(reinterpret_cast<uint4*>(out) + c, decode16_prmt(x));
         r += dr;
         pos += dpos;
         if (pos >= k) {
@@ -210,7 +203,7 @@ from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n
             ++r;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // trailing < 16 bytes
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // trailing < 16 bytes
         for (unsigned long long b = n_chunks * 16; b < total; ++b) {
             const uint64_t w = packed[b / k];
             out[b] = (uint8_t)(0x54474341u >> (8 * (unsigned)((w >> (2 * (b % k))) & 3u)));
@@ -219,26 +212,23 @@ from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n
 }
 
 // stride == 32, 16-byte aligned output: word r -> vectors 2r, 2r+1 (all 32 slots are written).
-template <int U>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kKmerThreads)
 from_2bit_padded_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, unsigned long long n_w32) {
-    __shared__ uint32_t lut[kLutWords];
-    lut_init(lut);
     const unsigned lane = threadIdx.x & 31;
-    const uint32_t* lut_lane = lut + lane;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
-    const unsigned long long warp = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    constexpr unsigned kTile = 32 * U;
-    const unsigned long long n_tiles = ceil_div(n_w32, kTile);
-    for (unsigned long long t = warp; t < n_tiles; t += n_warps) {
+    constexpr unsigned kTile = 32 * kKmerU;
+    const unsigned long long n_tiles = n_w32 / kTile;
+    const TileWalk<kKmerThreads, 1, 1> walk(n_tiles);
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
         const unsigned long long i0 = t * kTile + lane;
-        uint32_t w[U];
+        uint32_t w[kKmerU];
 #pragma unroll
-        for (int j = 0; j < U; ++j) w[j] = i0 + 32 * j < n_w32 ? ld_stream_u32(in + i0 + 32 * j) : 0u;
+        for (int j = 0; j < kKmerU; ++j) w[j] = ld32<LD_PLAIN>(in + i0 + 32 * j);
 #pragma unroll
-        for (int j = 0; j < U; ++j)
-            if (i0 + 32 * j < n_w32) st_stream_v4(out + i0 + 32 * j, lut_decode16(w[j], lut_lane));
+        for (int j = 0; j < kKmerU; ++j) st_stream_v4(out + i0 + 32 * j, decode16_prmt(w[j]));
     }
+    if (blockIdx.x == gridDim.x - 1)
+        for (unsigned long long i = n_tiles * kTile + threadIdx.x; i < n_w32; i += kKmerThreads)
+            st_stream_v4(out + i, decode16_prmt(ld32<LD_PLAIN>(in + i)));
 }
 
 // any k / stride: one thread per record, byte stores of exactly k bytes.
@@ -261,15 +251,13 @@ cudaError_t launch_as_2bit_batch(const DeviceInfo& di, const uint8_t* d_recs, si
     if (e != cudaSuccess || n == 0) return e;
     if (k == 0) return cudaMemsetAsync(d_out, 0, n * sizeof(uint64_t), s);
     if (stride == 32 && (reinterpret_cast<uintptr_t>(d_recs) & 15u) == 0) {
-        constexpr int U = 4;
-        static const int resident = resident_blocks(as_2bit_padded_kernel<U>, kThreads, di);
         const unsigned long long n_vec = 2ull * n;
-        as_2bit_padded_kernel<U><<<grid_for(ceil_div(ceil_div(n_vec, 32 * U), kWarpsPerBlock), resident), kThreads, 0, s>>>(
+        const unsigned long long ctas = TileWalk<kKmerThreads, 1, 1>::ctas(n_vec / (32 * kKmerU));
+        as_2bit_padded_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(
             reinterpret_cast<const uint4*>(d_recs), reinterpret_cast<uint32_t*>(d_out), n_vec, (int)k, d_status);
     } else if (stride <= (size_t)kStageMaxStride) {
-        static const int resident = resident_blocks(as_2bit_staged_kernel, kThreads, di);
-        as_2bit_staged_kernel<<<grid_for(ceil_div(n, kStageRecords), resident), kThreads, 0, s>>>(
-            d_recs, n, k, (unsigned)stride, d_out, d_status);
+        as_2bit_staged_kernel<<<(unsigned)ceil_div(n, kStageRecords), kThreads, 0, s>>>(d_recs, n, k, (unsigned)stride, d_out,
+                                                                                         d_status);
     } else {
         static const int resident = resident_blocks(as_2bit_generic_kernel, kThreads, di);
         as_2bit_generic_kernel<<<grid_for(ceil_div(n, kThreads), resident), kThreads, 0, s>>>(d_recs, n, k, stride, d_out,
@@ -283,15 +271,14 @@ cudaError_t launch_from_2bit_batch(const DeviceInfo& di, const uint64_t* d_packe
     if (n == 0 || k == 0) return cudaSuccess;
     const bool aligned = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
     if (aligned && stride == 32 && k == 32) {
-        constexpr int U = 4;
-        static const int resident = resident_blocks(from_2bit_padded_kernel<U>, kThreads, di);
         const unsigned long long n_w32 = 2ull * n;
-        from_2bit_padded_kernel<U><<<grid_for(ceil_div(ceil_div(n_w32, 32 * U), kWarpsPerBlock), resident), kThreads, 0, s>>>(
+        const unsigned long long ctas = TileWalk<kKmerThreads, 1, 1>::ctas(n_w32 / (32 * kKmerU));
+        from_2bit_padded_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(
             reinterpret_cast<const uint32_t*>(d_packed), reinterpret_cast<uint4*>(d_out), n_w32);
     } else if (aligned && stride == k && k >= 16) {
-        static const int resident = resident_blocks(from_2bit_tight_kernel, kThreads, di);
         const unsigned long long chunks = (unsigned long long)n * k / 16;
-        from_2bit_tight_kernel<<<grid_for(ceil_div(chunks + 1, kThreads), resident), kThreads, 0, s>>>(d_packed, n, k, d_out);
+        from_2bit_tight_kernel<<<(unsigned)ceil_div(chunks + 1, kKmerThreads * kTightChunks), kKmerThreads, 0, s>>>(d_packed, n, k,
+                                                                                                                 d_out);
     } else {
         static const int resident = resident_blocks(from_2bit_generic_kernel, kThreads, di);
         from_2bit_generic_kernel<<<grid_for(ceil_div(n, kThreads), resident), kThreads, 0, s>>>(d_packed, n, k, d_out, stride);

@@ -1,0 +1,208 @@
+#!/usr/bin/env python
+"""Per-kernel measurements of BASELINE.json configs 2-5 on one B200 (device-resident, CUDA events).
+
+Every line reports the kernel's algorithmic bytes over its event-timed duration against
+the measured HBM peak, after checking the result against a size-independent property.  Not the
+headline benchmark (that is bench.py); this is the evidence behind the per-kernel rooflines in
+DESIGN.md.
+
+    python tools/bench_configs.py [--scale 1.0] [--reps 10] [--only cfg3,cfg4,...]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+import torch
+
+from bitnuc_b200 import device as dv
+
+SEED = 0x5EEDB17C0DE5
+M64 = (1 << 64) - 1
+
+
+def peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    return float(json.loads(p.read_text())["hbm_gbs"]) if p.exists() else 6650.0
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def report(name, ms, nbytes, units, unit_name, extra=None):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    line = {"kernel": name, "ms": round(ms, 5), "algorithmic_bytes": nbytes, "GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak(), 4),
+            "frac_of_8000": round(gbs / 8000.0, 4), unit_name + "/s": round(units / (ms * 1e-3) / 1e9, 3), "unit": "G" + unit_name}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def cfg2(scale, reps):
+    """encode + decode of one contiguous sequence (also a ragged 2^30+17 one)."""
+    for n in (int(1_000_000_000 * scale), int(((1 << 30) + 17) * scale)):
+        asc = dv.synth_ascii(SEED, 0, 0, n)
+        words = torch.empty(dv.words_for(n), dtype=torch.int64, device="cuda")
+        back = torch.empty(n, dtype=torch.uint8, device="cuda")
+        st = dv.Status("cuda")
+        ms_e = timed(lambda: dv.encode(asc, out=words, status=st), reps)
+        ms_d = timed(lambda: dv.decode(words, n, out=back), reps)
+        st.check()
+        expect = dv.synth_words(SEED, 0, 0, dv.words_for(n))
+        if n % 32:
+            expect[-1] &= (1 << (2 * (n % 32))) - 1
+        assert torch.equal(words, expect) and torch.equal(back, asc)
+        report(f"cfg2 encode n={n}", ms_e, 1.25 * n, n, "bases")
+        report(f"cfg2 decode n={n}", ms_d, 1.25 * n, n, "bases")
+        del asc, words, back, expect
+
+
+def cfg3(scale, reps):
+    """batched as_2bit / from_2bit of 2^28 31-mers (tight 31-byte records and 32-byte padded records)."""
+    n = int((1 << 28) * scale)
+    words = dv.synth_words(SEED, 1, 0, n)
+    expect = words & ((1 << 62) - 1)
+    for layout, stride in (("tight", 31), ("padded", 32)):
+        recs = torch.zeros((n - 1) * stride + 31 + (1 if stride == 32 else 0), dtype=torch.uint8, device="cuda")
+        if stride == 32:
+            dv.from_2bit_batch(words, 32, 32, out=recs)  # fills all 32 slots (k = 32 fast path)
+            ms_f = timed(lambda: dv.from_2bit_batch(words, 32, 32, out=recs), reps)
+            kf = 32
+        else:
+            ms_f = timed(lambda: dv.from_2bit_batch(words, 31, 31, out=recs), reps)
+            kf = 31
+        packed = torch.empty(n, dtype=torch.int64, device="cuda")
+        st = dv.Status("cuda")
+        ms_a = timed(lambda: dv.as_2bit_batch(recs, n, 31, stride, out=packed, status=st), reps)
+        st.check()
+        assert torch.equal(packed, expect), layout
+        report(f"cfg3 as_2bit k=31 {layout} n={n}", ms_a, (stride + 8) * n, n, "kmers")
+        report(f"cfg3 from_2bit k={kf} {layout} n={n}", ms_f, (stride + 8) * n, n, "kmers")
+        del recs, packed
+    del words, expect
+
+
+def cfg4(scale, reps):
+    """hdist over 2^30 pairs of packed 32-mers (+ whole-sequence total), base_counts/gc on 10M x 150 bp reads."""
+    n = int((1 << 30) * scale)
+    u, v = dv.synth_words(SEED, 2, 0, n), dv.synth_words(SEED, 3, 0, n)
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    tot = torch.empty(1, dtype=torch.int64, device="cuda")
+    ms_p = timed(lambda: dv.hdist_pairs(u, v, 32, out=out), reps)
+    ms_t = timed(lambda: dv.hdist(u, v, 32 * n, out=tot), reps)
+    assert int(out.sum(dtype=torch.int64).item()) == int(tot.item())  # checksum of checksums
+    x = (u[:100000] ^ v[:100000]).cpu().numpy().view(np.uint64)
+    m = (x | (x >> np.uint64(1))) & np.uint64(0x5555555555555555)
+    ref = np.unpackbits(m.view(np.uint8).reshape(-1, 8), axis=1).sum(axis=1)
+    assert np.array_equal(out[:100000].cpu().numpy(), ref.astype(np.int32))
+    report(f"cfg4 hdist_pairs len=32 n={n}", ms_p, 20 * n, n, "pairs")
+    report(f"cfg4 hdist whole-sequence n_bases={32 * n}", ms_t, 16 * n, 32 * n, "bases", {"total": int(tot.item())})
+    ms_c = timed(lambda: dv.base_counts(u, 32 * n), reps)
+    counts, gc = dv.base_counts(u, 32 * n)
+    assert int(counts.sum().item()) == 32 * n
+    report(f"cfg4 base_counts whole-sequence n_bases={32 * n}", ms_c, 8 * n, 32 * n, "bases", {"counts": counts.tolist(), "gc": gc.item()})
+    del u, v, out
+
+    reads = int(10_000_000 * scale)
+    words = dv.synth_words(SEED, 4, 0, 5 * reads)
+    words.view(reads, 5)[:, 4] &= (1 << 44) - 1  # 150 = 4*32 + 22 bases: mask the tail of word 4
+    wo = torch.arange(reads, dtype=torch.int64, device="cuda") * 5
+    lens = torch.full((reads,), 150, dtype=torch.int64, device="cuda")
+    counts4 = torch.empty((reads, 4), dtype=torch.int64, device="cuda")
+    gcs = torch.empty(reads, dtype=torch.float64, device="cuda")
+    totals = torch.empty(4, dtype=torch.int64, device="cuda")
+    ms_b = timed(lambda: dv.base_counts_batch(words, wo, lens, counts4=counts4, gc=gcs, totals=totals), reps)
+    assert torch.equal(counts4.sum(dim=0), totals) and int(totals.sum().item()) == 150 * reads
+    gc_np = (counts4[:, 1] + counts4[:, 2]).cpu().numpy().astype(np.float64)
+    assert np.array_equal(gcs.cpu().numpy(), (gc_np / np.float64(150.0)) * np.float64(100.0))  # reference operation order
+    report(f"cfg4 base_counts+gc per read reads={reads} x 150bp", ms_b, 80 * reads, reads, "reads", {"totals": totals.tolist()})
+
+
+def cfg5(scale, reps):
+    """variable-length read batch (50 bp - 10 kbp, ~32 Gbases at scale 1), offset-indexed, with injected N."""
+    target = int(32e9 * scale)
+    n_guess = int(target / 5025 * 1.02) + 16
+    r = np.arange(n_guess, dtype=np.uint64)
+    from oracle import oracle_np as onp  # only the counter hash of the generator (test infrastructure)
+    lens = (50 + onp.splitmix64(r + np.uint64(SEED + 5)) % np.uint64(9951)).astype(np.uint64)
+    cum = np.cumsum(lens)
+    n_reads = int(np.searchsorted(cum, target)) + 1
+    lens = lens[:n_reads]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    total = int(offsets[-1])
+    data = dv.synth_ascii(SEED, 5, 0, total)
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    max_words = total // 32 + n_reads
+    words = torch.empty(max_words, dtype=torch.int64, device="cuda")
+    wo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    rs = torch.empty(n_reads, dtype=torch.int32, device="cuda")
+    ctx = dv.api.default_context(0)
+    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n_reads), dtype=torch.uint8, device="cuda")
+    st = dv.Status("cuda")
+
+    def run():
+        dv.raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, dv._ptr(words),
+                                                 dv._ptr(wo), dv._ptr(rs), dv._ptr(st.word), dv._ptr(scratch)))
+
+    ms = timed(run, max(2, reps // 2))
+    st.check()
+    n_words = int(wo[-1].item())
+    assert n_words == int(((lens + np.uint64(31)) // np.uint64(32)).sum())
+    # round trip of a few reads through decode
+    for ridx in (0, 1, n_reads // 2, n_reads - 1):
+        w0, ln = int(wo[ridx].item()), int(lens[ridx])
+        back = dv.decode(words[w0 : w0 + (ln + 31) // 32].contiguous(), ln)
+        assert torch.equal(back, data[int(offsets[ridx]) : int(offsets[ridx]) + ln])
+    nbytes = total + 8 * n_words + 16 * n_reads
+    report(f"cfg5 encode_batch reads={n_reads} bases={total}", ms, nbytes, total, "bases")
+    # injected N: read r gets 'N' at h2(r) % len iff h1(r) % 100003 == 0
+    h1 = onp.splitmix64(r[:n_reads] + np.uint64(0xABCDEF)) % np.uint64(100003)
+    victims = np.flatnonzero(h1 == 0)
+    if victims.size == 0:
+        victims = np.array([n_reads // 3])
+    pos = (onp.splitmix64(victims.astype(np.uint64) + np.uint64(0x123457)) % lens[victims]).astype(np.int64)
+    idx = torch.from_numpy((offsets[victims].astype(np.int64) + pos)).cuda()
+    data[idx] = ord("N")
+    run()
+    try:
+        st.check()
+        raise AssertionError("InvalidBase not reported")
+    except dv._lib.NucleotideError as e:
+        assert e.key() == ("InvalidBase", ord("N")) and e.offset == int(offsets[victims[0]]) + int(pos[0]), (e.key(), e.offset)
+    bad = torch.nonzero(rs != -1).flatten().cpu().numpy()
+    assert np.array_equal(bad, victims) and np.array_equal(rs[torch.from_numpy(victims).cuda()].cpu().numpy().astype(np.int64), pos)
+    print(json.dumps({"cfg5 error parity": "ok", "injected": int(victims.size), "first": [int(victims[0]), int(pos[0])]}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="cfg2,cfg3,cfg4,cfg5")
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    print(json.dumps({"device": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak(), "scale": args.scale}), flush=True)
+    for name in args.only.split(","):
+        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[name](args.scale, args.reps)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

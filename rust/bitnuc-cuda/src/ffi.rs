@@ -1,0 +1,68 @@
+//! Raw `extern "C"` bindings, 1:1 with `include/bitnuc_cuda.h`.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Debug, Default, Clone, Copy)]
+pub struct bn_error_t {
+    pub code: i32,
+    pub base: u8,
+    pub pad_: [u8; 3],
+    pub a: u64,
+    pub b: u64,
+    pub c: u64,
+    pub offset: u64,
+    pub record: u64,
+    pub cuda_error: i32,
+    pub pad2_: i32,
+}
+
+#[repr(C)]
+pub struct bn_ctx {
+    _private: [u8; 0],
+}
+
+pub const BN_OK: c_int = 0;
+pub const BN_ERR_EMPTY_ENCODE: c_int = -3;
+
+extern "C" {
+    pub fn bn_abi_version() -> c_int;
+    pub fn bn_device_count() -> c_int;
+    pub fn bn_error_string(err: *const bn_error_t, buf: *mut c_char, cap: usize) -> c_int;
+    pub fn bn_ctx_create(device: c_int, out: *mut *mut bn_ctx) -> c_int;
+    pub fn bn_ctx_destroy(ctx: *mut bn_ctx);
+    pub fn bn_ctx_device(ctx: *const bn_ctx) -> c_int;
+    pub fn bn_ctx_stream(ctx: *const bn_ctx) -> *mut c_void;
+    pub fn bn_ctx_synchronize(ctx: *mut bn_ctx) -> c_int;
+    pub fn bn_ctx_set_chunk_bytes(ctx: *mut bn_ctx, bytes: usize) -> c_int;
+    pub fn bn_dev_alloc(ctx: *mut bn_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn bn_dev_free(ctx: *mut bn_ctx, ptr: *mut c_void) -> c_int;
+    pub fn bn_host_alloc(ctx: *mut bn_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn bn_host_free(ctx: *mut bn_ctx, ptr: *mut c_void) -> c_int;
+    pub fn bn_copy_h2d(ctx: *mut bn_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn bn_copy_d2h(ctx: *mut bn_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+
+    pub fn bn_encode(ctx: *mut bn_ctx, seq: *const u8, n: usize, out: *mut u64, n_words: *mut usize, err: *mut bn_error_t) -> c_int;
+    pub fn bn_decode(ctx: *mut bn_ctx, words: *const u64, n_words: usize, n_bases: usize, out: *mut u8, err: *mut bn_error_t) -> c_int;
+    pub fn bn_as_2bit_batch(ctx: *mut bn_ctx, recs: *const u8, n: usize, k: u32, stride: usize, out: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_from_2bit_batch(ctx: *mut bn_ctx, packed: *const u64, n: usize, k: u32, out: *mut u8, stride: usize, err: *mut bn_error_t) -> c_int;
+    pub fn bn_hdist(ctx: *mut bn_ctx, a: *const u64, n_words_a: usize, b: *const u64, n_words_b: usize, n_bases: usize, total: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_hdist_pairs(ctx: *mut bn_ctx, u: *const u64, v: *const u64, n_pairs: usize, len: u32, out: *mut u32, err: *mut bn_error_t) -> c_int;
+    pub fn bn_base_counts(ctx: *mut bn_ctx, words: *const u64, n_words: usize, n_bases: usize, counts: *mut u64, gc: *mut f64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_base_counts_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, n_reads: usize, counts4: *mut u64, gc: *mut f64, totals: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_encode_batch(ctx: *mut bn_ctx, bytes: *const u8, offsets: *const u64, n_reads: usize, out_words: *mut u64, out_word_offsets: *mut u64, read_status: *mut u32, err: *mut bn_error_t) -> c_int;
+
+    pub fn bn_encode_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_seq: *const u8, n: usize, d_out: *mut u64, d_status: *mut u64) -> c_int;
+    pub fn bn_decode_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, n_words: usize, n_bases: usize, d_out: *mut u8) -> c_int;
+    pub fn bn_as_2bit_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_recs: *const u8, n: usize, k: u32, stride: usize, d_out: *mut u64, d_status: *mut u64) -> c_int;
+    pub fn bn_from_2bit_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_packed: *const u64, n: usize, k: u32, d_out: *mut u8, stride: usize) -> c_int;
+    pub fn bn_hdist_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_a: *const u64, d_b: *const u64, n_bases: usize, d_total: *mut u64) -> c_int;
+    pub fn bn_hdist_pairs_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_u: *const u64, d_v: *const u64, n_pairs: usize, len: u32, d_out: *mut u32) -> c_int;
+    pub fn bn_base_counts_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, n_bases: usize, d_counts: *mut u64, d_gc: *mut f64) -> c_int;
+    pub fn bn_base_counts_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, n_words: usize, d_word_offsets: *const u64, d_lens: *const u64, n_reads: usize, d_counts4: *mut u64, d_gc: *mut f64, d_totals: *mut u64) -> c_int;
+    pub fn bn_encode_batch_scratch_bytes(n_reads: usize) -> usize;
+    pub fn bn_encode_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_bytes: *const u8, d_offsets: *const u64, n_reads: usize, d_out_words: *mut u64, d_out_word_offsets: *mut u64, d_read_status: *mut u32, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
+    pub fn bn_status_fetch(ctx: *mut bn_ctx, stream: *mut c_void, d_status: *const u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_synth_words_dev(ctx: *mut bn_ctx, stream: *mut c_void, seed: u64, stream_id: u64, first_word: u64, n_words: usize, d_out: *mut u64) -> c_int;
+    pub fn bn_synth_ascii_dev(ctx: *mut bn_ctx, stream: *mut c_void, seed: u64, stream_id: u64, first_base: u64, n: usize, d_out: *mut u8) -> c_int;
+}

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "bn_hdist_pairs_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
     "bn_base_counts_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "bn_base_counts_batch_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "bn_base_counts_fixed_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp]),
     "bn_encode_batch_scratch_bytes": (_sz, [_sz]),
     "bn_encode_batch_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),

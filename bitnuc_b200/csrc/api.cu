@@ -274,8 +274,9 @@ int bn_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_seq, size_t n, uin
 }
 
 int bn_decode_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_words, size_t n_bases, uint8_t* d_out) {
-    if (!ctx || (n_bases && (!d_words || !d_out))) return BN_ERR_ARGUMENT;
+    if (!ctx) return BN_ERR_ARGUMENT;
     if (n_words < (n_bases + 31) / 32) return BN_INVALID_LENGTH;
+    if (n_bases && (!d_words || !d_out)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
     BN_LAUNCH(bn::launch_decode(ctx->di, d_words, n_bases, d_out, pick(ctx, stream)));
     return BN_OK;
@@ -283,9 +284,9 @@ int bn_decode_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_w
 
 int bn_as_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_recs, size_t n, uint32_t k, size_t stride,
                          uint64_t* d_out, uint64_t* d_status) {
-    if (!ctx || !d_status || (n && (!d_out || (k && !d_recs)))) return BN_ERR_ARGUMENT;
+    if (!ctx) return BN_ERR_ARGUMENT;
     if (k > 32) return BN_SEQUENCE_TOO_LONG;
-    if (stride < k) return BN_ERR_ARGUMENT;
+    if (stride < k || !d_status || (n && (!d_out || (k && !d_recs)))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
     BN_LAUNCH(bn::launch_as_2bit_batch(ctx->di, d_recs, n, k, stride, d_out, reinterpret_cast<unsigned long long*>(d_status),
                                        pick(ctx, stream)));
@@ -294,9 +295,9 @@ int bn_as_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_recs, size_
 
 int bn_from_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_packed, size_t n, uint32_t k, uint8_t* d_out,
                            size_t stride) {
-    if (!ctx || (n && k && (!d_packed || !d_out))) return BN_ERR_ARGUMENT;
+    if (!ctx) return BN_ERR_ARGUMENT;
     if (k > 32) return BN_INVALID_LENGTH;
-    if (stride < k) return BN_ERR_ARGUMENT;
+    if (stride < k || (n && k && (!d_packed || !d_out))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
     BN_LAUNCH(bn::launch_from_2bit_batch(ctx->di, d_packed, n, k, d_out, stride, pick(ctx, stream)));
     return BN_OK;
@@ -311,8 +312,9 @@ int bn_hdist_dev(bn_ctx* ctx, void* stream, const uint64_t* d_a, const uint64_t*
 
 int bn_hdist_pairs_dev(bn_ctx* ctx, void* stream, const uint64_t* d_u, const uint64_t* d_v, size_t n_pairs, uint32_t len,
                        uint32_t* d_out) {
-    if (!ctx || (n_pairs && (!d_u || !d_v || !d_out))) return BN_ERR_ARGUMENT;
+    if (!ctx) return BN_ERR_ARGUMENT;
     if (len > 32) return BN_INVALID_LENGTH;
+    if (n_pairs && (!d_u || !d_v || !d_out)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
     BN_LAUNCH(bn::launch_hdist_pairs(ctx->di, d_u, d_v, n_pairs, len, d_out, pick(ctx, stream)));
     return BN_OK;
@@ -331,7 +333,17 @@ int bn_base_counts_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words,
                              double* d_gc, uint64_t* d_totals) {
     if (!ctx || (n_reads && (!d_word_offsets || !d_lens))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
-    BN_LAUNCH(bn::launch_base_counts_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, n_words,
+    BN_LAUNCH(bn::launch_base_counts_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, 0, n_words,
+                                           reinterpret_cast<unsigned long long*>(d_counts4), d_gc,
+                                           reinterpret_cast<unsigned long long*>(d_totals), pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_base_counts_fixed_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_reads, size_t read_len,
+                             uint64_t* d_counts4, double* d_gc, uint64_t* d_totals) {
+    if (!ctx || (n_reads && read_len && !d_words)) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_base_counts_batch(ctx->di, d_words, nullptr, nullptr, n_reads, read_len, n_reads * ((read_len + 31) / 32),
                                            reinterpret_cast<unsigned long long*>(d_counts4), d_gc,
                                            reinterpret_cast<unsigned long long*>(d_totals), pick(ctx, stream)));
     return BN_OK;
@@ -437,9 +449,10 @@ int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* 
 }
 
 int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases, uint8_t* out, bn_error_t* err) {
-    if (!ctx || (n_bases && (!words || !out))) return set_err(err, BN_ERR_ARGUMENT);
-    if (n_words < (n_bases + 31) / 32) return set_err(err, BN_INVALID_LENGTH, n_bases);
+    if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
+    if (n_words < (n_bases + 31) / 32) return set_err(err, BN_INVALID_LENGTH, n_bases);  // before any pointer is looked at
     if (n_bases == 0) return set_err(err, BN_OK);
+    if (!words || !out) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t chunk = ctx->chunk;
@@ -466,9 +479,9 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
 // The remaining host-pointer calls stage whole buffers through reusable device scratch slots.
 
 int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, size_t stride, uint64_t* out, bn_error_t* err) {
-    if (!ctx || (n && (!out || (k && !recs)))) return set_err(err, BN_ERR_ARGUMENT);
+    if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
     if (k > 32) return set_err(err, BN_SEQUENCE_TOO_LONG, k);  // checked before any content (naive.rs:5-7)
-    if (stride < k) return set_err(err, BN_ERR_ARGUMENT);
+    if (stride < k || (n && (!out || (k && !recs)))) return set_err(err, BN_ERR_ARGUMENT);
     if (n == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -492,9 +505,9 @@ int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, siz
 }
 
 int bn_from_2bit_batch(bn_ctx* ctx, const uint64_t* packed, size_t n, uint32_t k, uint8_t* out, size_t stride, bn_error_t* err) {
-    if (!ctx || (n && k && (!packed || !out))) return set_err(err, BN_ERR_ARGUMENT);
-    if (k > 32) return set_err(err, BN_INVALID_LENGTH, k);
-    if (stride < k) return set_err(err, BN_ERR_ARGUMENT);
+    if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
+    if (k > 32) return set_err(err, BN_INVALID_LENGTH, k);  // unpacking/naive.rs:8-10
+    if (stride < k || (n && k && (!packed || !out))) return set_err(err, BN_ERR_ARGUMENT);
     if (n == 0 || k == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -601,7 +614,7 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
     BN_CUDA(cudaMemcpyAsync(ctx->slot[2].p, lens, n_reads * 8, cudaMemcpyHostToDevice, st));
     BN_CUDA(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p),
                                          static_cast<const uint64_t*>(ctx->slot[1].p), static_cast<const uint64_t*>(ctx->slot[2].p),
-                                         n_reads, n_words, counts4 ? static_cast<unsigned long long*>(ctx->slot[3].p) : nullptr,
+                                         n_reads, 0, n_words, counts4 ? static_cast<unsigned long long*>(ctx->slot[3].p) : nullptr,
                                          gc ? static_cast<double*>(ctx->slot[4].p) : nullptr, ctx->d_words + 8, st));
     if (counts4) BN_CUDA(cudaMemcpyAsync(counts4, ctx->slot[3].p, n_reads * 32, cudaMemcpyDeviceToHost, st));
     if (gc) BN_CUDA(cudaMemcpyAsync(gc, ctx->slot[4].p, n_reads * 8, cudaMemcpyDeviceToHost, st));

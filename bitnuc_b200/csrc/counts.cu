@@ -129,25 +129,28 @@ __global__ void base_counts_finalize_kernel(unsigned long long* counts, unsigned
     if (gc) *gc = gc_percent(c + g, n_bases);
 }
 
+constexpr int kBatchRounds = 4;  // reads per thread (or per warp): fewer CTAs -> fewer atomics on the totals
+
 // Per-read batch.  LANES = lanes cooperating on one read (1 for short reads, 32 for long ones).
 template <int LANES>
 __global__ void __launch_bounds__(kThreads)
 base_counts_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets,
-                         const uint64_t* __restrict__ lens, unsigned long long n_reads,
+                         const uint64_t* __restrict__ lens, unsigned long long n_reads, unsigned long long fixed_len,
                          unsigned long long* __restrict__ counts4, double* __restrict__ gc,
                          unsigned long long* __restrict__ totals) {
+    // lens == nullptr: fixed-length reads, read r = words[r * ceil(fixed_len/32) ..) (no index arrays to fetch)
     __shared__ unsigned long long scratch[32];
+    // a CTA owns kBatchRounds * (kThreads / LANES) consecutive reads (hardware CTA scheduling, see codec.cu)
     const unsigned sub = threadIdx.x % LANES;
-    const unsigned long long groups = (unsigned long long)gridDim.x * (blockDim.x / LANES);
-    const unsigned long long group = (unsigned long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
+    constexpr unsigned kGroups = kThreads / LANES;
+    const unsigned long long first = (unsigned long long)blockIdx.x * (kGroups * kBatchRounds) + threadIdx.x / LANES;
     unsigned long long ta = 0, tc = 0, tg = 0, tt = 0;
-    const unsigned long long rounds = ceil_div(n_reads, groups);
-    for (unsigned long long it = 0; it < rounds; ++it) {  // uniform trip count: shuffles stay converged
-        const unsigned long long r = it * groups + group;
+    for (int it = 0; it < kBatchRounds; ++it) {  // uniform trip count: shuffles stay converged
+        const unsigned long long r = first + (unsigned long long)it * kGroups;
         unsigned long long l = 0, h = 0, t = 0, len = 0;
         if (r < n_reads) {
-            len = lens[r];
-            const uint64_t* w = words + word_offsets[r];
+            len = lens ? lens[r] : fixed_len;
+            const uint64_t* w = words + (lens ? word_offsets[r] : r * ((fixed_len + 31) / 32));
             const unsigned long long full = len / 32;
             const unsigned rem = (unsigned)(len % 32);
             for (unsigned long long i = sub; i < full; i += LANES) count_word64(__ldg(w + i), l, h, t);
@@ -210,7 +213,7 @@ cudaError_t launch_base_counts(const DeviceInfo& di, const uint64_t* d_words, si
 }
 
 cudaError_t launch_base_counts_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets,
-                                     const uint64_t* d_lens, size_t n_reads, size_t n_words_hint,
+                                     const uint64_t* d_lens, size_t n_reads, size_t fixed_len, size_t n_words_hint,
                                      unsigned long long* d_counts4, double* d_gc, unsigned long long* d_totals,
                                      cudaStream_t s) {
     if (d_totals) {
@@ -219,13 +222,11 @@ cudaError_t launch_base_counts_batch(const DeviceInfo& di, const uint64_t* d_wor
     }
     if (n_reads == 0) return cudaSuccess;
     if (n_words_hint / n_reads >= 64) {  // long reads: a warp per read
-        static const int resident = resident_blocks(base_counts_batch_kernel<32>, kThreads, di);
-        base_counts_batch_kernel<32><<<grid_for(ceil_div(n_reads, kWarpsPerBlock), resident), kThreads, 0, s>>>(
-            d_words, d_word_offsets, d_lens, n_reads, d_counts4, d_gc, d_totals);
+        base_counts_batch_kernel<32><<<(unsigned)ceil_div(n_reads, kWarpsPerBlock * kBatchRounds), kThreads, 0, s>>>(
+            d_words, d_word_offsets, d_lens, n_reads, fixed_len, d_counts4, d_gc, d_totals);
     } else {
-        static const int resident = resident_blocks(base_counts_batch_kernel<1>, kThreads, di);
-        base_counts_batch_kernel<1><<<grid_for(ceil_div(n_reads, kThreads), resident), kThreads, 0, s>>>(
-            d_words, d_word_offsets, d_lens, n_reads, d_counts4, d_gc, d_totals);
+        base_counts_batch_kernel<1><<<(unsigned)ceil_div(n_reads, kThreads * kBatchRounds), kThreads, 0, s>>>(
+            d_words, d_word_offsets, d_lens, n_reads, fixed_len, d_counts4, d_gc, d_totals);
     }
     return cudaGetLastError();
 }

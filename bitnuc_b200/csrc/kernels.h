@@ -35,7 +35,7 @@ cudaError_t launch_hdist_pairs(const DeviceInfo& di, const uint64_t* d_u, const 
 cudaError_t launch_base_counts(const DeviceInfo& di, const uint64_t* d_words, size_t n_bases,
                                unsigned long long* d_counts, double* d_gc, cudaStream_t s);
 cudaError_t launch_base_counts_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets,
-                                     const uint64_t* d_lens, size_t n_reads, size_t n_words_hint,
+                                     const uint64_t* d_lens, size_t n_reads, size_t fixed_len, size_t n_words_hint,
                                      unsigned long long* d_counts4,
                                      double* d_gc, unsigned long long* d_totals, cudaStream_t s);
 

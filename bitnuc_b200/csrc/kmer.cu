@@ -7,8 +7,10 @@
 // HBM-bound at (k + 8) bytes per record.  Three layouts per direction:
 //   stride == 32 (padded records, 16-byte aligned): record r is vectors 2r, 2r+1 <-> word r, i.e. the
 //       streaming codec layout with bytes >= k masked;
-//   stride <= 64 (e.g. tightly packed 31-mers): the CTA's byte span is staged through shared memory
-//       with coalesced 128-bit loads, then each thread assembles its record with funnel shifts;
+//   stride == k (tightly packed, e.g. 31-mers): vectors are packed as in the streaming encode and each
+//       record is assembled from the <= 3 vectors it straddles with warp shuffles + funnel shifts;
+//   stride <= 64: the CTA's byte span is staged through shared memory with coalesced 128-bit loads,
+//       then each thread assembles its record with funnel shifts;
 //   anything else: one thread per record with byte accesses (correct, not tuned).
 #include "common.cuh"
 #include "launch.cuh"
@@ -41,53 +43,163 @@ __device__ __noinline__ void report_record_invalid(const uint8_t* rec, unsigned 
 constexpr int kKmerU = 4;
 constexpr int kKmerThreads = 512;
 
+// Rare path of the padded kernel: first invalid byte among the kk bases of up to n_vec vectors (32 apart).
+static __device__ __noinline__ void report_padded_invalid(const uint4* p, int n_vec, int kk, unsigned long long vec_index,
+                                                          unsigned long long* status) {
+    for (int j = 0; j < n_vec; ++j) {
+        const uint8_t* rec = reinterpret_cast<const uint8_t*>(p + 32 * j);
+        for (int i = 0; i < kk; ++i)
+            if (!byte_is_valid(rec[i])) {
+                report_invalid(status, (vec_index + 32ull * j) * 16ull + i, rec[i]);
+                return;
+            }
+    }
+}
+
 // stride == 32, aligned: lane parity selects the low/high half of a record.
-__global__ void __launch_bounds__(kKmerThreads)
+__global__ void __launch_bounds__(kKmerThreads, 2)
 as_2bit_padded_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ out, unsigned long long n_vec, int k,
                       unsigned long long* __restrict__ status) {
     const unsigned lane = threadIdx.x & 31;
     const int half = (lane & 1) * 16;  // vectors 32*j + lane keep the lane's parity (ragged loop: THREADS is even too)
-    const uint32_t m0 = keep_bytes(k - half), m1 = keep_bytes(k - half - 4), m2 = keep_bytes(k - half - 8),
-                   m3 = keep_bytes(k - half - 12);
     const int kk = k - half < 0 ? 0 : (k - half > 16 ? 16 : k - half);  // bases of this half-record
+    const uint32_t m0 = keep_bytes(kk), m1 = keep_bytes(kk - 4), m2 = keep_bytes(kk - 8), m3 = keep_bytes(kk - 12);
     constexpr unsigned kTile = 32 * kKmerU;
     const unsigned long long n_tiles = n_vec / kTile;
     const TileWalk<kKmerThreads, 1, 1> walk(n_tiles);
-    auto masked = [&](uint4 v) {
-        v.x = (v.x & m0) | (0x41414141u & ~m0);
-        v.y = (v.y & m1) | (0x41414141u & ~m1);
-        v.z = (v.z & m2) | (0x41414141u & ~m2);
-        v.w = (v.w & m3) | (0x41414141u & ~m3);
-        return v;
-    };
-    auto report = [&](unsigned long long vi) {
-        const uint8_t* rec = reinterpret_cast<const uint8_t*>(in + vi);
-        for (int i = 0; i < kk; ++i)
-            if (!byte_is_valid(rec[i])) {
-                report_invalid(status, vi * 16ull + i, rec[i]);
-                return true;
-            }
-        return false;
-    };
     for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
         const unsigned long long v0 = t * kTile + lane;
+        const uint4* p = in + v0;
         uint4 v[kKmerU];
 #pragma unroll
-        for (int j = 0; j < kKmerU; ++j) v[j] = ld128<LD_PLAIN>(in + v0 + 32 * j);
+        for (int j = 0; j < kKmerU; ++j) v[j] = ld128<LD_PLAIN>(p + 32 * j);
         uint32_t bad = 0, r[kKmerU];
 #pragma unroll
-        for (int j = 0; j < kKmerU; ++j) r[j] = pack16(masked(v[j]), bad);
+        for (int j = 0; j < kKmerU; ++j) {  // bytes past k read as 'A': valid, code 0
+            v[j].x = (v[j].x & m0) | (0x41414141u & ~m0);
+            v[j].y = (v[j].y & m1) | (0x41414141u & ~m1);
+            v[j].z = (v[j].z & m2) | (0x41414141u & ~m2);
+            v[j].w = (v[j].w & m3) | (0x41414141u & ~m3);
+            r[j] = pack16(v[j], bad);
+        }
+        uint32_t* q = out + v0;
 #pragma unroll
-        for (int j = 0; j < kKmerU; ++j) st_stream_u32(out + v0 + 32 * j, r[j]);
-        if (bad & kValidMask)
-            for (int j = 0; j < kKmerU; ++j)
-                if (report(v0 + 32 * j)) break;
+        for (int j = 0; j < kKmerU; ++j) st_stream_u32(q + 32 * j, r[j]);
+        if (bad & kValidMask) report_padded_invalid(p, kKmerU, kk, v0, status);
     }
     if (blockIdx.x == gridDim.x - 1) {
         for (unsigned long long i = n_tiles * kTile + threadIdx.x; i < n_vec; i += kKmerThreads) {
+            uint4 v = ld128<LD_PLAIN>(in + i);
+            v.x = (v.x & m0) | (0x41414141u & ~m0);
+            v.y = (v.y & m1) | (0x41414141u & ~m1);
+            v.z = (v.z & m2) | (0x41414141u & ~m2);
+            v.w = (v.w & m3) | (0x41414141u & ~m3);
             uint32_t bad = 0;
-            out[i] = pack16(masked(ld128<LD_PLAIN>(in + i)), bad);
-            if (bad & kValidMask) report(i);
+            out[i] = pack16(v, bad);
+            if (bad & kValidMask) report_padded_invalid(in + i, 1, kk, i, status);
+        }
+    }
+}
+
+// Tightly packed records (stride == k): every byte of the buffer belongs to a record, so the bytes
+// are packed exactly like the streaming encode (one aligned 16-byte vector per lane, coalesced, validated
+// as a whole) and each record is then assembled from the <= 3 vectors it straddles with three warp
+// shuffles and two funnel shifts.  A warp owns kTightGroups groups of `rpw` records; the byte span of a
+// group fits the warp's 32 vectors, and the loads of all groups are issued before the first use.
+constexpr int kTightGroups = 4;
+
+__device__ __noinline__ uint4 load_vector_at_edge(const uint8_t* recs, long long vbyte, unsigned long long total) {
+    uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};  // 'A' outside the buffer
+    for (int j = 0; j < 16; ++j) {
+        const long long o = vbyte + j;
+        if (o >= 0 && (unsigned long long)o < total)
+            w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)recs[o] << (8 * (j & 3)));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __noinline__ void report_vector_invalid(uint4 v, long long vbyte, unsigned long long* status) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        if (!byte_is_valid(b)) {
+            report_invalid(status, (unsigned long long)(vbyte + j), b);
+            return;
+        }
+    }
+}
+
+// one group of <= rpw records starting at record r0 (any position in the buffer, any count)
+__device__ __noinline__ void as_2bit_tight_group_slow(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k,
+                                                      unsigned rpw, unsigned long long r0, uint64_t* __restrict__ out,
+                                                      unsigned long long* __restrict__ status) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned cnt = (unsigned)(n - r0 < rpw ? n - r0 : rpw);
+    const unsigned long long total = n * k, span0 = r0 * k;
+    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(recs) + span0) & 15u);
+    const long long vbyte = (long long)span0 - mis + 16ll * lane;  // buffer offset of this lane's vector (may be < 0)
+    uint32_t code = 0;
+    if (vbyte < (long long)(span0 + (unsigned long long)cnt * k)) {
+        const uint4 v = (vbyte >= 0 && (unsigned long long)vbyte + 16 <= total)
+                            ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(recs + vbyte))
+                            : load_vector_at_edge(recs, vbyte, total);
+        uint32_t bad = 0;
+        code = pack16(v, bad);
+        if (bad & kValidMask) report_vector_invalid(v, vbyte, status);
+    }
+    __syncwarp();
+    const unsigned rel = mis + lane * k;
+    const unsigned vi = rel >> 4, sh = 2 * (rel & 15u);
+    const uint32_t c0 = __shfl_sync(0xffffffffu, code, vi & 31);
+    const uint32_t c1 = __shfl_sync(0xffffffffu, code, (vi + 1) & 31);
+    const uint32_t c2 = __shfl_sync(0xffffffffu, code, (vi + 2) & 31);
+    if (lane < cnt) {
+        const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+        out[r0 + lane] = (((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh)) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(kKmerThreads)
+as_2bit_tight_kernel(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k, unsigned rpw,
+                     uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = (unsigned long long)blockIdx.x * (kKmerThreads / 32) + (threadIdx.x >> 5);
+    const unsigned long long rw = warp * ((unsigned long long)kTightGroups * rpw);  // first record of the warp
+    if (rw >= n) return;
+    const unsigned gbytes = rpw * k;                                              // bytes per full group (<= 497)
+    const uint8_t* wbase = recs + rw * k;
+    const unsigned m0 = (unsigned)(reinterpret_cast<uintptr_t>(wbase) & 15u);
+    const uint8_t* abase = wbase - m0;                                            // 16-byte aligned
+    // interior warp: all groups full and every vector it may touch lies inside the buffer
+    const bool interior = rw + (unsigned long long)kTightGroups * rpw <= n && abase >= recs &&
+                          abase + (kTightGroups - 1) * gbytes + m0 + 528 <= recs + n * k;
+    if (!interior) {
+        for (int g = 0; g < kTightGroups; ++g)
+            if (rw + (unsigned long long)g * rpw < n) as_2bit_tight_group_slow(recs, n, k, rpw, rw + (unsigned long long)g * rpw, out, status);
+        return;
+    }
+    uint4 v[kTightGroups];
+#pragma unroll
+    for (int g = 0; g < kTightGroups; ++g)
+        v[g] = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(abase + ((m0 + g * gbytes) & ~15u)) + lane);
+    const uint32_t mlo = k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u;
+    const uint32_t mhi = k >= 32 ? 0xFFFFFFFFu : k <= 16 ? 0u : (1u << (2 * k - 32)) - 1u;
+    uint64_t* o = out + rw + lane;
+#pragma unroll
+    for (int g = 0; g < kTightGroups; ++g) {
+        uint32_t bad = 0;
+        const uint32_t code = pack16(v[g], bad);
+        if (bad & kValidMask)
+            report_vector_invalid(v[g], (long long)(abase - recs) + ((m0 + g * gbytes) & ~15u) + 16 * lane, status);
+        const unsigned rel = ((m0 + g * gbytes) & 15u) + lane * k;  // byte offset of the record from the group's first vector
+        const unsigned vi = rel >> 4, sh = 2 * (rel & 15u);
+        const uint32_t c0 = __shfl_sync(0xffffffffu, code, vi & 31);
+        const uint32_t c1 = __shfl_sync(0xffffffffu, code, (vi + 1) & 31);
+        const uint32_t c2 = __shfl_sync(0xffffffffu, code, (vi + 2) & 31);
+        if (lane < rpw) {
+            uint2 w;
+            w.x = __funnelshift_r(c0, c1, sh) & mlo;
+            w.y = __funnelshift_r(c1, c2, sh) & mhi;
+            *reinterpret_cast<uint2*>(o + g * rpw) = w;
         }
     }
 }
@@ -168,12 +280,12 @@ as_2bit_generic_kernel(const uint8_t* __restrict__ recs, unsigned long long n, u
 
 // ============================================================================ from_2bit ======
 
-constexpr int kTightChunks = 8;  // 16-byte output chunks per thread
+constexpr int kTightChunks = 4;  // 16-byte output chunks per thread, all loads issued before the first use
 
 // Tightly packed records (stride == k, 16 <= k <= 32), 16-byte aligned output: one thread per
 // 16-byte output chunk; a chunk spans at most two records.  A CTA owns kKmerThreads * kTightChunks
 // consecutive chunks; (record, position) is found by one division per thread, then advanced.
-__global__ void __launch_bounds__(kKmerThreads)
+__global__ void __launch_bounds__(kKmerThreads, 2)
 from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n, unsigned k,
                        uint8_t* __restrict__ out) {
     const unsigned long long total = n * k;
@@ -182,26 +294,30 @@ from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n
     unsigned long long r = (c0 * 16) / k;
     unsigned pos = (unsigned)((c0 * 16) % k);
     constexpr unsigned kStepBytes = kKmerThreads * 16;
-    const unsigned long long dr = kStepBytes / k;
-    const unsigned dpos = kStepBytes % k;
-#pragma unroll 2
+    const unsigned dr = kStepBytes / k, dpos = kStepBytes % k;
+    uint64_t w0[kTightChunks], w1[kTightChunks];
+    unsigned p[kTightChunks];
+#pragma unroll
     for (int it = 0; it < kTightChunks; ++it) {
-        const unsigned long long c = c0 + (unsigned long long)it * kKmerThreads;
-        if (c >= n_chunks) break;
-        const unsigned avail = k - pos;
-        const uint64_t w0 = __ldg(packed + r);
-        uint32_t x = (uint32_t)(w0 >> (2 * pos));
-        if (avail < 16) {
-            const uint64_t w1 = __ldg(packed + r + 1);  // exists: the chunk is full, so bytes follow
-            x = (x & ((1u << (2 * avail)) - 1u)) | (uint32_t)(w1 << (2 * avail));
-        }
-        st_stream_v4(reinterpret_cast<uint4*>(out) + c, decode16_prmt(x));
+        p[it] = pos;
+        const bool live = c0 + (unsigned long long)it * kKmerThreads < n_chunks;
+        w0[it] = live ? __ldg(packed + r) : 0ull;
+        w1[it] = live && r + 1 < n ? __ldg(packed + r + 1) : 0ull;  // only used when the chunk crosses into record r+1
         r += dr;
         pos += dpos;
         if (pos >= k) {
             pos -= k;
             ++r;
         }
+    }
+#pragma unroll
+    for (int it = 0; it < kTightChunks; ++it) {
+        const unsigned long long c = c0 + (unsigned long long)it * kKmerThreads;
+        if (c >= n_chunks) break;
+        const unsigned avail = k - p[it];
+        uint32_t x = (uint32_t)(w0[it] >> (2 * p[it]));
+        if (avail < 16) x = (x & ((1u << (2 * avail)) - 1u)) | (uint32_t)(w1[it] << (2 * avail));
+        st_stream_v4(reinterpret_cast<uint4*>(out) + c, decode16_prmt(x));
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // trailing < 16 bytes
         for (unsigned long long b = n_chunks * 16; b < total; ++b) {
@@ -255,6 +371,10 @@ cudaError_t launch_as_2bit_batch(const DeviceInfo& di, const uint8_t* d_recs, si
         const unsigned long long ctas = TileWalk<kKmerThreads, 1, 1>::ctas(n_vec / (32 * kKmerU));
         as_2bit_padded_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(
             reinterpret_cast<const uint4*>(d_recs), reinterpret_cast<uint32_t*>(d_out), n_vec, (int)k, d_status);
+    } else if (stride == k) {
+        const unsigned rpw = 497u / k < 32u ? 497u / k : 32u;  // 15 + rpw*k <= 512: the span fits the warp's 32 vectors
+        const unsigned long long warps = ceil_div(n, (unsigned long long)rpw * kTightGroups);
+        as_2bit_tight_kernel<<<(unsigned)ceil_div(warps, kKmerThreads / 32), kKmerThreads, 0, s>>>(d_recs, n, k, rpw, d_out, d_status);
     } else if (stride <= (size_t)kStageMaxStride) {
         as_2bit_staged_kernel<<<(unsigned)ceil_div(n, kStageRecords), kThreads, 0, s>>>(d_recs, n, k, (unsigned)stride, d_out,
                                                                                          d_status);

@@ -154,6 +154,20 @@ def base_counts_batch(words, word_offsets, lens, counts4=None, gc=None, totals=N
     return counts4, gc, totals
 
 
+def base_counts_fixed(words, n_reads: int, read_len: int, counts4=None, gc=None, totals=None):
+    """Per-read counts / gc / totals for ``n_reads`` fixed-length reads of ``ceil(read_len/32)`` words each."""
+    ctx = _ctx_for(words)
+    dev = words.device
+    counts4 = counts4 if counts4 is not None else torch.empty((n_reads, 4), dtype=torch.int64, device=dev)
+    gc = gc if gc is not None else torch.empty(n_reads, dtype=torch.float64, device=dev)
+    totals = totals if totals is not None else torch.empty(4, dtype=torch.int64, device=dev)
+    if words.numel() < n_reads * words_for(read_len):
+        raise _lib.NucleotideError.InvalidLength(read_len)
+    raise_for(ctx.lib.bn_base_counts_fixed_dev(ctx.handle, _stream(), _ptr(words), n_reads, read_len, _ptr(counts4), _ptr(gc),
+                                               _ptr(totals)))
+    return counts4, gc, totals
+
+
 def encode_batch(data: torch.Tensor, offsets: torch.Tensor, max_words: int | None = None, read_status: bool = False,
                  status: Status | None = None):
     """Variable-length reads -> (words, word_offsets, read_status|None, status), all on the device."""

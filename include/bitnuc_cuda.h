@@ -161,6 +161,9 @@ int bn_base_counts_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_
 /* d_totals (4 device uint64_t, may be NULL) is reset, then accumulated over the reads.  n_words (the
  * size of d_words) only selects the thread-per-read or warp-per-read kernel; 0 = unknown. */
 int bn_base_counts_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_t n_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, uint64_t *d_counts4, double *d_gc, uint64_t *d_totals);
+/* Fixed-length reads (e.g. 10 M x 150 bp): read r = d_words[r*ceil(read_len/32) ..), read_len bases each.
+ * Same outputs as bn_base_counts_batch_dev without the 16 bytes per read of offset/length arrays. */
+int bn_base_counts_fixed_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_t n_reads, size_t read_len, uint64_t *d_counts4, double *d_gc, uint64_t *d_totals);
 /* d_out_word_offsets[n_reads+1] is produced by a device scan; d_scratch needs
  * bn_encode_batch_scratch_bytes(n_reads) bytes. */
 size_t bn_encode_batch_scratch_bytes(size_t n_reads);

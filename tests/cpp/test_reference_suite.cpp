@@ -198,6 +198,7 @@ int main() {
     for (const auto& t : tests) {
         t.second();
         std::printf("ok %s\n", t.first);
+        std::fflush(stdout);
     }
     std::printf("reference suite passed: %d checks\n", g_checks);
     return 0;

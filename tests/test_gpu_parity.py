@@ -476,3 +476,26 @@ def test_device_resident_kmers_cfg3_shape(bn):
     p2, st = dv.as_2bit_batch(padded, n, 31, 32)          # padded records, k < stride
     st.check()
     assert torch.equal(p2, expect)
+
+
+@pytest.mark.parametrize("read_len", [1, 31, 32, 33, 150, 1000])
+def test_device_fixed_length_counts_match_oracle(bn, read_len):
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(read_len)
+    n_reads = 777
+    wpr = (read_len + 31) // 32
+    words = np.zeros(n_reads * wpr, dtype=np.uint64)
+    exp_counts, exp_gc = [], []
+    for r in range(n_reads):
+        ps = oracle.PackedSequence(rand_seq(rng, read_len).tobytes())
+        words[r * wpr : (r + 1) * wpr] = np.array(ps.data, dtype=np.uint64)
+        exp_counts.append(ps.base_counts())
+        exp_gc.append(ps.gc_content())
+    if read_len % 32:  # garbage above the tail must not matter
+        words[wpr - 1 :: wpr] |= np.uint64(((1 << 64) - 1) ^ ((1 << (2 * (read_len % 32))) - 1))
+    d = torch.from_numpy(words.view(np.int64)).cuda()
+    counts, gc, totals = dv.base_counts_fixed(d, n_reads, read_len)
+    assert np.array_equal(counts.cpu().numpy(), np.array(exp_counts, dtype=np.int64))
+    assert np.array_equal(gc.cpu().numpy(), np.array(exp_gc))
+    assert totals.tolist() == np.array(exp_counts).sum(axis=0).tolist()

@@ -132,7 +132,12 @@ def cfg4(scale, reps):
     assert torch.equal(counts4.sum(dim=0), totals) and int(totals.sum().item()) == 150 * reads
     gc_np = (counts4[:, 1] + counts4[:, 2]).cpu().numpy().astype(np.float64)
     assert np.array_equal(gcs.cpu().numpy(), (gc_np / np.float64(150.0)) * np.float64(100.0))  # reference operation order
-    report(f"cfg4 base_counts+gc per read reads={reads} x 150bp", ms_b, 80 * reads, reads, "reads", {"totals": totals.tolist()})
+    report(f"cfg4 base_counts+gc per read (offset-indexed) reads={reads} x 150bp", ms_b, 80 * reads, reads, "reads",
+           {"totals": totals.tolist(), "note": "also fetches 16 B/read of offsets+lengths: 96 B/read of real traffic"})
+    c2, g2, t2 = torch.empty_like(counts4), torch.empty_like(gcs), torch.empty_like(totals)
+    ms_f = timed(lambda: dv.base_counts_fixed(words, reads, 150, counts4=c2, gc=g2, totals=t2), reps)
+    assert torch.equal(c2, counts4) and torch.equal(g2, gcs) and torch.equal(t2, totals)
+    report(f"cfg4 base_counts+gc per read (fixed length) reads={reads} x 150bp", ms_f, 80 * reads, reads, "reads")
 
 
 def cfg5(scale, reps):

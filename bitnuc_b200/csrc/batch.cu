@@ -7,10 +7,10 @@
 // Two steps on the device:
 //   1. word offsets = exclusive prefix sum of ceil(len/32) over the reads (block sums, one-CTA scan
 //      of the sums, block-local scan + offset);
-//   2. encode, one thread per OUTPUT word: the word's read is found by a search of the word-offset
-//      array that is narrowed per CTA tile first (tiles are pulled from a global atomic counter), its <= 32 source bytes are fetched as nine aligned
-//      32-bit loads and funnel-shifted into place, bytes past the end of the read are replaced by 'A'.
-// Work per thread is uniform whatever the length mix (50 bp .. 10 kbp).  HBM-bound at
+//   2. encode, one thread per 16-base HALF of an output word (see encode_batch_kernel): warps walk
+//      consecutive output words, tiles of words are pulled from a global atomic counter, the owning
+//      read is found once per warp range by a search narrowed per tile and then advanced linearly.
+// Work per warp step is uniform whatever the length mix (50 bp .. 10 kbp).  HBM-bound at
 // 1 B/base in + 8 B per word out + 16 B per read of offsets.
 #include "common.cuh"
 #include "launch.cuh"
@@ -123,19 +123,119 @@ __device__ __forceinline__ unsigned long long owner_read(const uint64_t* __restr
     return lo;
 }
 
-constexpr int kBatchItems = 8;                          // output words per thread
-constexpr int kBatchTile = kThreads * kBatchItems;      // output words per CTA tile
+// Same result as owner_read over [0, n_reads-1], by a whole warp: 32 probes per step instead of one, so the
+// dependent chain is ~log32(n) loads long instead of log2(n).  All lanes return the answer.
+__device__ __forceinline__ unsigned long long owner_read_warp(const uint64_t* __restrict__ wo, unsigned long long n_reads,
+                                                              unsigned long long w) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long lo = 0, hi = n_reads - 1;  // invariant: wo[lo] <= w, answer in [lo, hi]
+    while (hi > lo) {
+        const unsigned long long step = (hi - lo) / 32 + 1;   // probes lo + (l+1)*step, l = 0..31, cover (lo, hi]
+        const unsigned long long p = lo + (lane + 1ull) * step;
+        const bool le = p <= hi && __ldg(wo + p) <= w;
+        const unsigned k = __popc(__ballot_sync(0xffffffffu, le));  // probes are monotone: the first k are true
+        const unsigned long long nlo = lo + k * step, nhi = nlo + step - 1;
+        lo = nlo;
+        hi = nhi < hi ? nhi : hi;
+    }
+    return lo;
+}
 
-__global__ void __launch_bounds__(kThreads)
+constexpr int kWarpWords = 512;                          // consecutive output words per warp per tile
+constexpr int kBatchTile = kWarpsPerBlock * kWarpWords;  // output words per CTA tile
+constexpr int kGroupWords = 16;                          // words per warp step: one 16-base half-word per lane
+
+// Rare paths, out of line: byte-wise fetch of a lane's (<= 16) bytes, and the first invalid byte of them.
+static __device__ __noinline__ uint4 batch_load_bytes(const uint8_t* p, int nb) {
+    uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
+    for (int j = 0; j < nb; ++j) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)p[j] << (8 * (j & 3)));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+static __device__ __noinline__ void batch_report_invalid(const uint8_t* bytes, unsigned long long src, int nb, unsigned long long rb,
+                                                         unsigned long long r, uint32_t* read_status, unsigned long long* status) {
+    for (int j = 0; j < nb; ++j) {
+        const uint32_t b = bytes[src + j];
+        if (!byte_is_valid(b)) {
+            report_invalid(status, src + j, b);
+            if (read_status) atomicMin(read_status + r, (uint32_t)(src + j - rb));
+            return;
+        }
+    }
+}
+
+// 16 bytes starting 4*WS + sh8/8 bytes into the aligned vector pair (v, n)
+template <int WS>
+__device__ __forceinline__ uint4 align16(uint4 v, uint4 n, unsigned sh8) {
+    const uint32_t w[8] = {v.x, v.y, v.z, v.w, n.x, n.y, n.z, n.w};
+    return make_uint4(__funnelshift_r(w[WS], w[WS + 1], sh8), __funnelshift_r(w[WS + 1], w[WS + 2], sh8),
+                      __funnelshift_r(w[WS + 2], w[WS + 3], sh8), __funnelshift_r(w[WS + 3], w[WS + 4], sh8));
+}
+__device__ __forceinline__ uint4 align16_dyn(uint4 v, uint4 n, unsigned s) {
+    switch (s >> 2) {
+    case 0: return align16<0>(v, n, 8 * (s & 3u));
+    case 1: return align16<1>(v, n, 8 * (s & 3u));
+    case 2: return align16<2>(v, n, 8 * (s & 3u));
+    default: return align16<3>(v, n, 8 * (s & 3u));
+    }
+}
+
+// Fast path body: `n_iter` steps of U groups (16 complete words each) of one read.  p = this lane's first
+// aligned vector, q = this lane's first output half-word; WS < 0 means the read starts 16-byte aligned.
+// Returns the number of the first step (0-based) in which this lane saw an invalid byte, or ~0u.
+template <int WS, int U>
+__device__ __forceinline__ unsigned fast_groups(const uint4* __restrict__ p, uint32_t* __restrict__ q, unsigned n_iter, unsigned sh8) {
+    unsigned first_bad = ~0u;
+    for (unsigned it = 0; it < n_iter; ++it) {
+        uint4 x[U], y[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) x[j] = ld128<LD_PLAIN>(p + 32 * j);
+        if (WS >= 0) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) y[j] = ld128<LD_PLAIN>(p + 32 * j + 1);
+        }
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint4 v = WS >= 0 ? align16<(WS >= 0 ? WS : 0)>(x[j], y[j], sh8) : x[j];
+            st_stream_u32(q + 32 * j, pack16(v, bad));
+        }
+        if ((bad & kValidMask) && first_bad == ~0u) first_bad = it;
+        p += 32 * U;
+        q += 32 * U;
+    }
+    return first_bad;
+}
+
+template <int U>
+__device__ __forceinline__ unsigned fast_groups_any(const uint4* p, uint32_t* q, unsigned n_iter, unsigned s) {
+    if (s == 0) return fast_groups<-1, U>(p, q, n_iter, 0);
+    const unsigned sh8 = 8 * (s & 3u);
+    switch (s >> 2) {
+    case 0: return fast_groups<0, U>(p, q, n_iter, sh8);
+    case 1: return fast_groups<1, U>(p, q, n_iter, sh8);
+    case 2: return fast_groups<2, U>(p, q, n_iter, sh8);
+    default: return fast_groups<3, U>(p, q, n_iter, sh8);
+    }
+}
+
+// One thread per 16-base HALF of an output word.  A warp walks kWarpWords consecutive output words read
+// by read (warp-uniform loop): inside a read, the 32 half-words of 16 consecutive words are one contiguous,
+// uniformly misaligned 512-byte run, fetched with two coalesced aligned 128-bit loads per lane and put in
+// place by a funnel shift whose word part is a template constant; the last (< 16 complete + 1 ragged)
+// words of a read take one masked pass in which the lanes past the end of the read idle.
+__global__ void __launch_bounds__(kThreads, 4)
 encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ offsets, unsigned long long n_reads,
                     const uint64_t* __restrict__ word_offsets, uint64_t* __restrict__ out,
                     uint32_t* __restrict__ read_status, unsigned long long* __restrict__ status,
                     unsigned long long* __restrict__ tile_counter) {
     __shared__ unsigned long long range[2];
     __shared__ unsigned long long tile_s;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane & 1;
     const unsigned long long total_words = word_offsets[n_reads];
-    const unsigned long long buf_lo = offsets[0], buf_hi = offsets[n_reads];  // valid byte range of `bytes`
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(bytes) + offsets[0];        // valid address range of the bytes
+    const uintptr_t buf_hi = reinterpret_cast<uintptr_t>(bytes) + offsets[n_reads];
     const unsigned long long n_tiles = ceil_div(total_words, kBatchTile);
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
     for (;;) {  // persistent CTAs pull tiles from a global counter: dynamic balance, word count unknown to the host
         __syncthreads();
         if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1ull);
@@ -144,54 +244,108 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
         if (tile >= n_tiles) break;
         const unsigned long long w0 = tile * kBatchTile;
         const unsigned long long w1 = w0 + kBatchTile < total_words ? w0 + kBatchTile : total_words;
-        if (threadIdx.x < 2) range[threadIdx.x] = owner_read(word_offsets, 0, n_reads - 1, threadIdx.x ? w1 - 1 : w0);
+        if (warp < 2) {  // warps 0 and 1 locate the reads of the tile's first and last word
+            const unsigned long long rr = owner_read_warp(word_offsets, n_reads, warp ? w1 - 1 : w0);
+            if (lane == 0) range[warp] = rr;
+        }
         __syncthreads();
-        const unsigned long long r_lo = range[0], r_hi = range[1];
-#pragma unroll 2
-        for (int it = 0; it < kBatchItems; ++it) {
-            const unsigned long long w = w0 + (unsigned long long)it * kThreads + threadIdx.x;
-            if (w >= w1) break;
-            const unsigned long long r = owner_read(word_offsets, r_lo, r_hi, w);
-            const unsigned long long rb = __ldg(offsets + r), re = __ldg(offsets + r + 1);
-            const unsigned long long src = rb + (w - __ldg(word_offsets + r)) * 32ull;  // byte offset in `bytes`
-            const int nb = (int)(re - src < 32 ? re - src : 32);                        // bases in this word
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(bytes) + src;
-            const unsigned sh = 8 * (unsigned)(addr & 3u);
-            uint32_t x[9];
-            const unsigned long long a0 = src - (addr & 3u);  // may wrap below buf_lo: checked next
-            if ((addr & 3u) <= src - buf_lo && a0 + 36 <= buf_hi) {
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) x[i] = __ldg(p + i);
-            } else {  // the aligned window pokes outside the buffer: byte loads with bounds
-#pragma unroll
-                for (int i = 0; i < 9; ++i) x[i] = 0;
-                for (int j = 0; j < nb; ++j) {
-                    const unsigned q = (unsigned)(addr & 3u) + j;
-                    x[q >> 2] |= (uint32_t)bytes[src + j] << (8 * (q & 3));
+        const unsigned long long ww0 = w0 + (unsigned long long)warp * kWarpWords;   // this warp's words [ww0, ww1)
+        const unsigned long long ww1 = ww0 + kWarpWords < w1 ? ww0 + kWarpWords : w1;
+        if (ww0 >= ww1) continue;
+        unsigned long long r = owner_read(word_offsets, range[0], range[1], ww0);    // warp-uniform
+        unsigned long long wo_next = __ldg(word_offsets + r + 1);
+        {   // The warp's source bytes are one contiguous run (reads are adjacent in the byte buffer) of at most
+            // 32 bytes per word: pull it into L2 now, so the dependent per-group loads below see L2 latency,
+            // not DRAM latency.
+            const uintptr_t p0 = (reinterpret_cast<uintptr_t>(bytes) + __ldg(offsets + r) + (ww0 - __ldg(word_offsets + r)) * 32ull) & ~(uintptr_t)127;
+            uintptr_t p1 = p0 + (ww1 - ww0) * 32ull + 128;
+            if (p1 > buf_hi) p1 = buf_hi;
+            for (uintptr_t p = p0 + 128ull * lane; p < p1; p += 128ull * 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+        unsigned long long cached_r = ~0ull, rb = 0, re = 0, wo = 0, full_end = 0;
+        unsigned s = 0;
+        unsigned long long wb = ww0;
+        while (wb < ww1) {
+            while (wo_next <= wb) wo_next = __ldg(word_offsets + (++r) + 1);  // read owning word wb (skips empty reads)
+            if (r != cached_r) {  // per-read constants (warp-uniform)
+                cached_r = r;
+                rb = __ldg(offsets + r), re = __ldg(offsets + r + 1), wo = __ldg(word_offsets + r);
+                full_end = wo + (re - rb) / 32;                                           // words [wo, full_end) are complete
+                s = (unsigned)((reinterpret_cast<uintptr_t>(bytes) + rb) & 15u);          // misalignment of every 16-base half
+            }
+            // ---- fast path: groups of 16 complete words of read r.  The lanes' bytes are one contiguous,
+            // uniformly misaligned 512-byte run: two coalesced aligned 128-bit loads + a uniform funnel shift.
+            const unsigned long long seg_end = wo_next < ww1 ? wo_next : ww1;            // this read's words in the warp's range
+            // ---- fast path: groups of 16 complete words of read r.  The 32 lanes' bytes are one contiguous,
+            // uniformly misaligned 512-byte run: two coalesced aligned 128-bit loads + a funnel shift each.
+            {
+                const unsigned long long lim = full_end < seg_end ? full_end : seg_end;
+                unsigned long long groups = lim > wb ? (lim - wb) / kGroupWords : 0;       // complete groups ahead in this read
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(bytes) + rb + (wb - wo) * 32ull - s;  // aligned start of the run
+                if (a0 < buf_lo || a0 + 32 > buf_hi) groups = 0;                           // first vector of the batch: tail pass
+                else if (groups > (buf_hi - a0 - 32) / 512) groups = (buf_hi - a0 - 32) / 512;   // keep every aligned load inside the buffer
+                if (groups) {
+                    constexpr int U = 2;
+                    const uint4* p = reinterpret_cast<const uint4*>(a0) + lane;
+                    uint32_t* q = out32 + 2 * wb + lane;
+                    const unsigned n2 = (unsigned)(groups / U), n1 = (unsigned)(groups % U);
+                    unsigned fb = fast_groups_any<U>(p, q, n2, s);
+                    if (fb != ~0u) fb *= U;
+                    if (n1) {
+                        const unsigned f1 = fast_groups_any<1>(p + 32 * U * n2, q + 32 * U * n2, n1, s);
+                        if (fb == ~0u && f1 != ~0u) fb = U * n2 + f1;
+                    }
+                    if (fb != ~0u) {  // rare: this lane saw an invalid byte from group `fb` on (U groups checked together)
+                        for (unsigned long long g = fb; g < groups; ++g) {
+                            const unsigned long long src = rb + (wb + g * kGroupWords - wo) * 32ull + 16u * lane;
+                            bool found = false;
+                            for (int j = 0; j < 16 && !found; ++j) found = !byte_is_valid(bytes[src + j]);
+                            if (found) {
+                                batch_report_invalid(bytes, src, 16, rb, r, read_status, status);
+                                break;
+                            }
+                        }
+                    }
+                    wb += groups * kGroupWords;
                 }
             }
-            uint32_t v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t f = __funnelshift_r(x[i], x[i + 1], sh);
-                const int keep = nb - 4 * i;
-                const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u);
-                v[i] = (f & m) | (0x41414141u & ~m);
-            }
-            uint32_t bad = 0;
-            const uint32_t lo = pack16(make_uint4(v[0], v[1], v[2], v[3]), bad);
-            const uint32_t hi = pack16(make_uint4(v[4], v[5], v[6], v[7]), bad);
-            out[w] = ((uint64_t)hi << 32) | lo;
-            if (bad & kValidMask) {
-                for (int j = 0; j < nb; ++j) {
-                    const uint32_t b = bytes[src + j];
-                    if (!byte_is_valid(b)) {
-                        report_invalid(status, src + j, b);
-                        if (read_status) atomicMin(read_status + r, (uint32_t)(src + j - rb));
-                        break;
+            // ---- tail pass: the (< 16 complete + 1 ragged) last words of the read, or a group at a batch edge.
+            // Lanes past the end of the read idle; bytes past the end of the read are replaced by 'A'.
+            if (wb < seg_end) {
+                const unsigned long long word = wb + (lane >> 1);
+                const bool active = word < seg_end;
+                const unsigned long long src = rb + (word - wo) * 32ull + half * 16u;  // byte offset of this lane's 16 bases
+                const int nb = !active || src >= re ? 0 : (re - src < 16 ? (int)(re - src) : 16);
+                uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+                if (nb > 0) {
+                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(bytes) + src - s;
+                    const bool two = s + (unsigned)nb > 16u;
+                    if (a0 >= buf_lo && a0 + (two ? 32 : 16) <= buf_hi) {
+                        const uint4 x = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0));
+                        const uint4 y = two ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0) + 1) : x;
+                        v = s ? align16_dyn(x, y, s) : x;
+                    } else {  // the aligned window pokes outside the byte buffer (first / last vector of the batch)
+                        v = batch_load_bytes(bytes + src, nb);
+                    }
+                    if (nb < 16) {  // ragged last word: bytes past the end of the read read as 'A'
+                        const uint32_t m0 = nb >= 4 ? ~0u : (1u << (8 * nb)) - 1u;
+                        const uint32_t m1 = nb >= 8 ? ~0u : nb <= 4 ? 0u : (1u << (8 * (nb - 4))) - 1u;
+                        const uint32_t m2 = nb >= 12 ? ~0u : nb <= 8 ? 0u : (1u << (8 * (nb - 8))) - 1u;
+                        const uint32_t m3 = nb <= 12 ? 0u : (1u << (8 * (nb - 12))) - 1u;
+                        v.x = (v.x & m0) | (0x41414141u & ~m0);
+                        v.y = (v.y & m1) | (0x41414141u & ~m1);
+                        v.z = (v.z & m2) | (0x41414141u & ~m2);
+                        v.w = (v.w & m3) | (0x41414141u & ~m3);
                     }
                 }
+                uint32_t bad = 0;
+                const uint32_t code = pack16(v, bad);
+                if (active) {
+                    out32[2 * word + half] = code;
+                    if (bad & kValidMask) batch_report_invalid(bytes, src, nb, rb, r, read_status, status);
+                }
+                wb = wb + kGroupWords < seg_end ? wb + kGroupWords : seg_end;
             }
         }
     }

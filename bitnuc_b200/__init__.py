@@ -1,7 +1,7 @@
 """bitnuc_b200 -- B200-native (sm_100a CUDA) implementation of bitnuc's data-parallel hot path.
 
 The public names are the reference's (/root/reference/src/lib.rs:214-220): ``as_2bit``, ``from_2bit``,
-``from_2bit_alloc``, ``encode``, ``encode_alloc``, ``decode``, ``hdist``, ``hdist_scalar``,
+``from_2bit_alloc``, ``encode``, ``encode_alloc``, ``decode``, ``hdist``, ``hdist_scalar``, ``split_packed``,
 ``PackedSequence`` (with ``base_counts`` / ``gc_content``) and ``NucleotideError``; plus array/batch
 forms and, in ``bitnuc_b200.device``, device-resident variants on torch CUDA tensors.
 
@@ -11,12 +11,12 @@ All computation happens in hand-written CUDA kernels behind the C ABI of ``libbi
 from .errors import BitnucCudaError, NucleotideError, ReferencePanic
 from .api import (Context, as_2bit, as_2bit_batch, base_counts_batch, base_counts_gc, decode, decode_np,
                   default_context, encode, encode_alloc, encode_batch, encode_np, from_2bit, from_2bit_alloc,
-                  from_2bit_batch, hdist, hdist_pairs, hdist_scalar, hdist_total)
+                  from_2bit_batch, hdist, hdist_pairs, hdist_scalar, hdist_total, split_packed, split_packed_batch)
 from .sequence import PackedSequence
 
 __all__ = [
     "NucleotideError", "ReferencePanic", "BitnucCudaError", "PackedSequence", "Context", "default_context",
     "as_2bit", "from_2bit", "from_2bit_alloc", "encode", "encode_alloc", "decode", "hdist", "hdist_scalar",
     "encode_np", "decode_np", "as_2bit_batch", "from_2bit_batch", "hdist_pairs", "hdist_total",
-    "base_counts_gc", "base_counts_batch", "encode_batch",
+    "base_counts_gc", "base_counts_batch", "encode_batch", "split_packed", "split_packed_batch",
 ]

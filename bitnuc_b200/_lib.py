@@ -59,6 +59,9 @@ PROTOTYPES = {
     "bn_base_counts_fixed_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp]),
     "bn_encode_batch_scratch_bytes": (_sz, [_sz]),
     "bn_encode_batch_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "bn_split_packed_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _errp]),
+    "bn_split_packed_scratch_bytes": (_sz, [_sz]),
+    "bn_split_packed_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),
     "bn_synth_words_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
     "bn_synth_ascii_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),

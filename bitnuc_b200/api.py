@@ -284,3 +284,42 @@ def encode_batch(data, offsets, ctx: Context | None = None, per_read_status: boo
         raise_for(rc, err)
     words = words[: int(wo[n])]
     return (words, wo, status[:n]) if per_read_status else (words, wo)
+
+
+# ------------------------------------------------------------------ split_packed -------------
+
+def split_packed_batch(words, word_offsets, lens, idx, ctx: Context | None = None):
+    """``split_packed`` (src/utils/functions/split.rs:14-102) over a batch of packed reads: read ``r`` is
+    ``words[word_offsets[r]:word_offsets[r+1]]`` holding ``lens[r]`` bases, split at base ``idx[r]``.
+    Returns (left, left_offsets, right, right_offsets); raises ``IndexOutOfBounds`` (with ``.record``)
+    for the first read with ``idx > len``."""
+    ctx = ctx or default_context()
+    w, wo, ln, ix = _u64(words), _u64(word_offsets), _u64(lens), _u64(idx)
+    n = ln.size
+    if wo.size != n + 1 or ix.size != n:
+        raise ValueError("word_offsets needs n_reads + 1 entries, idx n_reads")
+    left = np.empty(max(1, w.size + n), dtype=np.uint64)
+    right = np.empty(max(1, w.size), dtype=np.uint64)
+    lo = np.zeros(n + 1, dtype=np.uint64)
+    ro = np.zeros(n + 1, dtype=np.uint64)
+    err = BnError()
+    rc = ctx.lib.bn_split_packed_batch(ctx.handle, _p(w), w.size, _p(wo), _p(ln), _p(ix), n, _p(left), _p(lo), _p(right), _p(ro),
+                                       C.byref(err))
+    if rc in (3, 4):
+        e = NucleotideError.IndexOutOfBounds(err.a, err.b) if rc == 4 else NucleotideError.InvalidLength(err.a)
+        e.record = int(err.record)
+        raise e
+    raise_for(rc, err)
+    return left[: int(lo[n])], lo, right[: int(ro[n])], ro
+
+
+def split_packed(ebuf, slen: int, idx: int, lbuf: list, rbuf: list, ctx: Context | None = None) -> None:
+    """``split_packed(&[u64], usize, usize, &mut Vec<u64>, &mut Vec<u64>)`` (src/utils/functions/split.rs:14-20):
+    validates ``idx <= slen`` first, then clears both buffers and fills them."""
+    w = _u64(ebuf)
+    left, _, right, _ = split_packed_batch(w, np.array([0, w.size], dtype=np.uint64), np.array([slen], dtype=np.uint64),
+                                           np.array([idx], dtype=np.uint64), ctx)
+    lbuf.clear()
+    rbuf.clear()
+    lbuf.extend(int(x) for x in left)
+    rbuf.extend(int(x) for x in right)

@@ -361,6 +361,21 @@ int bn_encode_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const
     return BN_OK;
 }
 
+size_t bn_split_packed_scratch_bytes(size_t n_reads) { return bn::split_packed_scratch_bytes(n_reads); }
+
+int bn_split_packed_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const uint64_t* d_word_offsets,
+                              const uint64_t* d_lens, const uint64_t* d_idx, size_t n_reads, uint64_t* d_left,
+                              uint64_t* d_left_offsets, uint64_t* d_right, uint64_t* d_right_offsets, uint64_t* d_status,
+                              void* d_scratch) {
+    if (!ctx || !d_status || !d_left_offsets || !d_right_offsets || (n_reads && (!d_word_offsets || !d_lens || !d_idx || !d_scratch)))
+        return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_split_packed_batch(ctx->di, d_words, d_word_offsets, d_lens, d_idx, n_reads, d_left, d_left_offsets, d_right,
+                                            d_right_offsets, reinterpret_cast<unsigned long long*>(d_status), d_scratch,
+                                            pick(ctx, stream)));
+    return BN_OK;
+}
+
 int bn_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, bn_error_t* err) {
     if (!ctx || !d_status) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
@@ -610,7 +625,7 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
     if (counts4) BN_CUDA(ensure(ctx->slot[3], n_reads * 32));
     if (gc) BN_CUDA(ensure(ctx->slot[4], n_reads * 8));
     if (n_words) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, n_words * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, n_reads * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     BN_CUDA(cudaMemcpyAsync(ctx->slot[2].p, lens, n_reads * 8, cudaMemcpyHostToDevice, st));
     BN_CUDA(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p),
                                          static_cast<const uint64_t*>(ctx->slot[1].p), static_cast<const uint64_t*>(ctx->slot[2].p),
@@ -675,6 +690,57 @@ int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, 
         }
         return BN_INVALID_BASE;
     }
+    return set_err(err, BN_OK);
+}
+
+int bn_split_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens,
+                          const uint64_t* idx, size_t n_reads, uint64_t* left, uint64_t* left_offsets, uint64_t* right,
+                          uint64_t* right_offsets, bn_error_t* err) {
+    if (!ctx || !left_offsets || !right_offsets || (n_reads && (!word_offsets || !lens || !idx))) return set_err(err, BN_ERR_ARGUMENT);
+    for (size_t r = 0; r < n_reads; ++r) {  // first failing read in index order, as the caller's loop with `?` would report
+        if (idx[r] > lens[r]) {
+            set_err(err, BN_INDEX_OUT_OF_BOUNDS, idx[r], lens[r]);  // split.rs:22-27
+            if (err) err->record = r;
+            return BN_INDEX_OUT_OF_BOUNDS;
+        }
+        if (word_offsets[r + 1] < word_offsets[r] || word_offsets[r + 1] > n_words) return set_err(err, BN_ERR_ARGUMENT);
+        const uint64_t have = word_offsets[r + 1] - word_offsets[r];
+        if (idx[r] && idx[r] < lens[r] && have && have < (lens[r] + 31) / 32) {  // the reference panics (split.rs:77) or truncates the right half
+            set_err(err, BN_INVALID_LENGTH, lens[r]);
+            if (err) err->record = r;
+            return BN_INVALID_LENGTH;
+        }
+    }
+    left_offsets[0] = right_offsets[0] = 0;
+    if (n_reads == 0) return set_err(err, BN_OK);
+    if (n_words && (!words || !left || !right)) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
+    BN_CUDA(ensure(ctx->slot[1], (n_reads + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[2], n_reads * 8));
+    BN_CUDA(ensure(ctx->slot[3], n_reads * 8));
+    BN_CUDA(ensure(ctx->slot[4], (n_words + n_reads) * 8 + 8));
+    BN_CUDA(ensure(ctx->slot[5], n_words * 8 + 8));
+    BN_CUDA(ensure(ctx->slot[6], 2 * (n_reads + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[7], bn::split_packed_scratch_bytes(n_reads)));
+    uint64_t* d_lo = static_cast<uint64_t*>(ctx->slot[6].p);
+    uint64_t* d_ro = d_lo + n_reads + 1;
+    if (n_words) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, n_words * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[2].p, lens, n_reads * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[3].p, idx, n_reads * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_split_packed_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
+                                          static_cast<const uint64_t*>(ctx->slot[2].p), static_cast<const uint64_t*>(ctx->slot[3].p), n_reads,
+                                          static_cast<uint64_t*>(ctx->slot[4].p), d_lo, static_cast<uint64_t*>(ctx->slot[5].p), d_ro,
+                                          ctx->d_words + 8, ctx->slot[7].p, st));
+    BN_CUDA(cudaMemcpyAsync(left_offsets, d_lo, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(right_offsets, d_ro, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    if (left_offsets[n_reads]) BN_CUDA(cudaMemcpyAsync(left, ctx->slot[4].p, left_offsets[n_reads] * 8, cudaMemcpyDeviceToHost, st));
+    if (right_offsets[n_reads]) BN_CUDA(cudaMemcpyAsync(right, ctx->slot[5].p, right_offsets[n_reads] * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
     return set_err(err, BN_OK);
 }
 

@@ -14,104 +14,17 @@
 // 1 B/base in + 8 B per word out + 16 B per read of offsets.
 #include "common.cuh"
 #include "launch.cuh"
+#include "scan.cuh"
 
 namespace bn {
 
-constexpr int kScanItems = 4;                          // reads per thread in the scan kernels
-constexpr int kScanTile = kThreads * kScanItems;       // reads per CTA
-
-__device__ __forceinline__ unsigned long long words_of_read(const uint64_t* __restrict__ offsets, unsigned long long r) {
-    return (offsets[r + 1] - offsets[r] + 31) / 32;
-}
-
-__global__ void __launch_bounds__(kThreads)
-batch_block_sums_kernel(const uint64_t* __restrict__ offsets, unsigned long long n_reads, unsigned long long* __restrict__ sums) {
-    __shared__ unsigned long long scratch[32];
-    const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    unsigned long long s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-        if (r0 + i < n_reads) s += words_of_read(offsets, r0 + i);
-    s = block_sum_u64(s, scratch);
-    if (threadIdx.x == 0) sums[blockIdx.x] = s;
-}
-
-// exclusive scan of sums[0..n) in place by one CTA; sums[n] = total
-__global__ void __launch_bounds__(1024) batch_scan_sums_kernel(unsigned long long* __restrict__ sums, unsigned long long n) {
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned long long base = 0; base < n; base += blockDim.x) {
-        const unsigned long long i = base + threadIdx.x;
-        const unsigned long long v = i < n ? sums[i] : 0;
-        unsigned long long inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (unsigned)o) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_tot[lane], winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= (unsigned)o) winc += t;
-            }
-            warp_tot[lane] = winc - w;  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const unsigned long long carry = carry_s;
-        if (i < n) sums[i] = carry + warp_tot[warp] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[warp] + inc;
-        __syncthreads();
+// words taken by read r: ceil(len/32); an empty read takes none
+struct WordsOfRead {
+    const uint64_t* offsets;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long r) const {
+        return (offsets[r + 1] - offsets[r] + 31) / 32;
     }
-    if (threadIdx.x == 0) sums[n] = carry_s;
-}
-
-__global__ void __launch_bounds__(kThreads)
-batch_word_offsets_kernel(const uint64_t* __restrict__ offsets, unsigned long long n_reads,
-                          const unsigned long long* __restrict__ sums, unsigned long long n_blocks,
-                          uint64_t* __restrict__ word_offsets) {
-    __shared__ unsigned long long warp_tot[32];
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    unsigned long long c[kScanItems], s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        c[i] = r0 + i < n_reads ? words_of_read(offsets, r0 + i) : 0;
-        s += c[i];
-    }
-    unsigned long long inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (unsigned)o) inc += t;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = lane < kWarpsPerBlock ? warp_tot[lane] : 0, winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= (unsigned)o) winc += t;
-        }
-        if (lane < kWarpsPerBlock) warp_tot[lane] = winc - w;
-    }
-    __syncthreads();
-    unsigned long long run = sums[blockIdx.x] + warp_tot[warp] + inc - s;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        if (r0 + i < n_reads) word_offsets[r0 + i] = run;
-        run += c[i];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) word_offsets[n_reads] = sums[n_blocks];
-}
+};
 
 // index of the read owning output word w: the last r in [lo, hi] with word_offsets[r] <= w
 __device__ __forceinline__ unsigned long long owner_read(const uint64_t* __restrict__ wo, unsigned long long lo,
@@ -352,7 +265,7 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
 }
 
 size_t encode_batch_scratch_bytes(size_t n_reads) {
-    return (ceil_div(n_reads ? n_reads : 1, kScanTile) + 2) * sizeof(unsigned long long);  // block sums, total, tile counter
+    return scan_scratch_bytes(n_reads) + sizeof(unsigned long long);  // block sums + total, then the tile counter
 }
 
 cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets,
@@ -367,13 +280,10 @@ cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, co
         if (e != cudaSuccess) return e;
     }
     unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
-    const unsigned long long n_blocks = ceil_div(n_reads, kScanTile);
-    unsigned long long* tile_counter = sums + n_blocks + 1;
+    unsigned long long* tile_counter = sums + scan_scratch_bytes(n_reads) / sizeof(unsigned long long);
     e = cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    batch_block_sums_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(d_offsets, n_reads, sums);
-    batch_scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n_blocks);
-    batch_word_offsets_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(d_offsets, n_reads, sums, n_blocks, d_out_word_offsets);
+    launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s);
     static const int resident = resident_blocks(encode_batch_kernel, kThreads, di);
     // the number of output words is only known on the device: launch a full persistent grid
     encode_batch_kernel<<<resident, kThreads, 0, s>>>(d_bytes, d_offsets, n_reads, d_out_word_offsets, d_out_words,

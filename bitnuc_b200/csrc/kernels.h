@@ -46,6 +46,13 @@ cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, co
                                 uint32_t* d_read_status, unsigned long long* d_status, void* d_scratch,
                                 cudaStream_t s);
 
+// split.cu
+size_t split_packed_scratch_bytes(size_t n_reads);
+cudaError_t launch_split_packed_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets,
+                                      const uint64_t* d_lens, const uint64_t* d_idx, size_t n_reads, uint64_t* d_left,
+                                      uint64_t* d_left_offsets, uint64_t* d_right, uint64_t* d_right_offsets,
+                                      unsigned long long* d_status, void* d_scratch, cudaStream_t s);
+
 // synth.cu
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,
                                size_t n_words, uint64_t* d_out, cudaStream_t s);

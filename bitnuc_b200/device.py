@@ -186,6 +186,47 @@ def encode_batch(data: torch.Tensor, offsets: torch.Tensor, max_words: int | Non
     return words, wo, rs, status
 
 
+class SplitStatus:
+    """Device-side status of ``split_packed_batch``: min over failing reads of (read << 1 | kind)."""
+
+    def __init__(self, device):
+        self.word = torch.empty(1, dtype=torch.int64, device=device)
+
+    def check(self, lens: torch.Tensor, idx: torch.Tensor):
+        """Synchronises (reads the word back); raises the first failing read's error."""
+        key = int(self.word.item()) & api.M64
+        if key == api.M64:
+            return
+        r = key >> 1
+        if key & 1:
+            e = _lib.NucleotideError.InvalidLength(int(lens[r].item()))
+        else:
+            e = _lib.NucleotideError.IndexOutOfBounds(int(idx[r].item()), int(lens[r].item()))
+        e.record = r
+        raise e
+
+
+def split_packed_batch(words: torch.Tensor, word_offsets: torch.Tensor, lens: torch.Tensor, idx: torch.Tensor,
+                       status: SplitStatus | None = None):
+    """Batched ``split_packed`` on the device: returns (left, left_offsets, right, right_offsets, status).
+    ``left`` / ``right`` are over-allocated (n_words + n_reads / n_words); the valid prefix length is the last
+    entry of the offsets arrays."""
+    ctx = _ctx_for(words if words.numel() else lens)
+    n = lens.numel()
+    dev = lens.device
+    if word_offsets.numel() != n + 1 or idx.numel() != n:
+        raise ValueError("word_offsets needs n_reads + 1 entries, idx n_reads")
+    left = torch.empty(words.numel() + n, dtype=torch.int64, device=dev)
+    right = torch.empty(words.numel(), dtype=torch.int64, device=dev)
+    lo = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    ro = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(ctx.lib.bn_split_packed_scratch_bytes(n), dtype=torch.uint8, device=dev)
+    status = status or SplitStatus(dev)
+    raise_for(ctx.lib.bn_split_packed_batch_dev(ctx.handle, _stream(), _ptr(words), _ptr(word_offsets), _ptr(lens), _ptr(idx), n,
+                                                _ptr(left), _ptr(lo), _ptr(right), _ptr(ro), _ptr(status.word), _ptr(scratch)))
+    return left, lo, right, ro, status
+
+
 def synth_words(seed: int, stream_id: int, first_word: int, n_words: int, device="cuda") -> torch.Tensor:
     ctx = api.default_context(torch.device(device).index or 0)
     out = torch.empty(n_words, dtype=torch.int64, device=device)

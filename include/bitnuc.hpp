@@ -180,6 +180,20 @@ inline uint32_t hdist_scalar(uint64_t u, uint64_t v, size_t len) {  // hamming/s
     return out;
 }
 
+// src/utils/functions/split.rs:14-20 -- validates idx <= slen, then clears both buffers and fills them
+inline void split_packed(Words ebuf, size_t slen, size_t idx, std::vector<uint64_t>& lbuf, std::vector<uint64_t>& rbuf) {
+    const uint64_t word_offsets[2] = {0, ebuf.len}, len64 = slen, idx64 = idx;
+    uint64_t lo[2] = {0, 0}, ro[2] = {0, 0};
+    std::vector<uint64_t> left(ebuf.len + 1), right(ebuf.len + 1);
+    bn_error_t e{};
+    detail::check(bn_split_packed_batch(detail::ctx(), ebuf.ptr, ebuf.len, word_offsets, &len64, &idx64, 1, left.data(), lo,
+                                        right.data(), ro, &e), e);
+    left.resize(lo[1]);
+    right.resize(ro[1]);
+    lbuf.swap(left);
+    rbuf.swap(right);
+}
+
 // src/sequence.rs:5-9 + src/utils/analysis.rs
 class PackedSequence {
 public:

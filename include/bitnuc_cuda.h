@@ -143,6 +143,16 @@ int bn_base_counts_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, con
  * base or UINT32_MAX when the read is clean (the non-short-circuit variant). */
 int bn_encode_batch(bn_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, size_t n_reads, uint64_t *out_words, uint64_t *out_word_offsets, uint32_t *read_status, bn_error_t *err);
 
+/* bitnuc::split_packed over a batch of packed reads (src/utils/functions/split.rs:14-102): read r
+ * (lens[r] bases, ebuf = words[word_offsets[r] .. word_offsets[r+1]); word_offsets has n_reads+1 entries, e.g.
+ * the out_word_offsets of bn_encode_batch) is split at base idx[r].  left needs n_words + n_reads words,
+ * right needs n_words words; left_offsets / right_offsets [n_reads+1] receive the exclusive prefix sums of
+ * the per-read word counts (left: 0, ebuf.len() or idx/32 + 1; right: ebuf.len(), 0 or ebuf.len() - idx/32).
+ * The reference's carry order is reproduced bit for bit (see csrc/split.cu).
+ * idx[r] > lens[r] -> BN_INDEX_OUT_OF_BOUNDS{idx, len} for the first such read (err->record); a non-empty
+ * ebuf shorter than ceil(len/32) words (the reference panics or truncates) -> BN_INVALID_LENGTH(len). */
+int bn_split_packed_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, const uint64_t *idx, size_t n_reads, uint64_t *left, uint64_t *left_offsets, uint64_t *right, uint64_t *right_offsets, bn_error_t *err);
+
 /* ------------------------------------------------------------------ device-pointer calls ---- */
 /* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.
  * Pointers are device pointers.  ASCII buffers and packed buffers must be 16-byte aligned.
@@ -168,6 +178,12 @@ int bn_base_counts_fixed_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words,
  * bn_encode_batch_scratch_bytes(n_reads) bytes. */
 size_t bn_encode_batch_scratch_bytes(size_t n_reads);
 int bn_encode_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const uint64_t *d_offsets, size_t n_reads, uint64_t *d_out_words, uint64_t *d_out_word_offsets, uint32_t *d_read_status, uint64_t *d_status, void *d_scratch);
+
+/* d_status (device uint64_t) receives min(read index << 1 | kind) over failing reads (kind 0: idx > len,
+ * kind 1: ebuf too short), or UINT64_MAX; failing reads produce no output words.
+ * d_scratch needs bn_split_packed_scratch_bytes(n_reads) bytes. */
+size_t bn_split_packed_scratch_bytes(size_t n_reads);
+int bn_split_packed_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, const uint64_t *d_idx, size_t n_reads, uint64_t *d_left, uint64_t *d_left_offsets, uint64_t *d_right, uint64_t *d_right_offsets, uint64_t *d_status, void *d_scratch);
 
 /* Synchronises `stream`, reads *d_status back and translates it: BN_OK, or BN_INVALID_BASE with
  * err->base / err->offset filled (record/a are filled by the host-pointer wrappers). */

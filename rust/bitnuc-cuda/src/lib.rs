@@ -112,6 +112,25 @@ pub fn hdist_scalar(u: u64, v: u64, len: usize) -> Result<u32, NucleotideError> 
     check(rc, &e).map(|_| out)
 }
 
+/// `bitnuc::split_packed` (src/utils/functions/split.rs:14-20): validates, then clears and fills both buffers.
+pub fn split_packed(ebuf: &[u64], slen: usize, idx: usize, lbuf: &mut Vec<u64>, rbuf: &mut Vec<u64>) -> Result<(), NucleotideError> {
+    let word_offsets = [0u64, ebuf.len() as u64];
+    let (len64, idx64) = (slen as u64, idx as u64);
+    let (mut lo, mut ro) = ([0u64; 2], [0u64; 2]);
+    let (mut left, mut right) = (vec![0u64; ebuf.len() + 1], vec![0u64; ebuf.len() + 1]);
+    let mut e = bn_error_t::default();
+    let rc = with_ctx(|c| unsafe {
+        bn_split_packed_batch(c, ebuf.as_ptr(), ebuf.len(), word_offsets.as_ptr(), &len64, &idx64, 1, left.as_mut_ptr(), lo.as_mut_ptr(),
+                              right.as_mut_ptr(), ro.as_mut_ptr(), &mut e)
+    });
+    check(rc, &e)?;
+    left.truncate(lo[1] as usize);
+    right.truncate(ro[1] as usize);
+    *lbuf = left;
+    *rbuf = right;
+    Ok(())
+}
+
 /// Batched `as_2bit`: `n` records of `k` bases every `stride` bytes (an addition to the reference API).
 pub fn as_2bit_batch(recs: &[u8], n: usize, k: usize, stride: usize) -> Result<Vec<u64>, NucleotideError> {
     assert!(n == 0 || k > 32 || recs.len() >= (n - 1) * stride + k);

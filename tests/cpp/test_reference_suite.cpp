@@ -191,10 +191,48 @@ static void test_errors() {
     CHECK(panicked);
 }
 
+// src/utils/functions/split.rs:110-225
+static void test_split_packed() {
+    auto dec = [](const std::vector<uint64_t>& w, size_t n) {
+        std::vector<uint8_t> out;
+        decode(w, n, out);
+        return std::string(out.begin(), out.end());
+    };
+    std::vector<uint64_t> lbuf, rbuf;
+    {
+        const std::string seq = "ACTGACTG";
+        split_packed(encode_alloc(seq), seq.size(), 4, lbuf, rbuf);
+        CHECK(lbuf.size() == 1 && rbuf.size() == 1);
+        CHECK(dec(lbuf, 4) == "ACTG" && dec(rbuf, 4) == "ACTG");
+    }
+    {
+        const std::string seq = "ACTG";
+        const auto ebuf = encode_alloc(seq);
+        split_packed(ebuf, seq.size(), 0, lbuf, rbuf);
+        CHECK(dec(rbuf, seq.size()) == seq && lbuf.size() == 0 && rbuf.size() == 1);
+        split_packed(ebuf, seq.size(), seq.size(), lbuf, rbuf);
+        CHECK(dec(lbuf, seq.size()) == seq && lbuf.size() == 1 && rbuf.size() == 0);
+        CHECK(expect_err([&] { split_packed(ebuf, seq.size(), seq.size() + 1, lbuf, rbuf); }) == E(E::IndexOutOfBounds, 5, 4));
+    }
+    {
+        const std::string seq = "ACTGACTGAC";
+        split_packed(encode_alloc(seq), seq.size(), 7, lbuf, rbuf);
+        CHECK(lbuf.size() == 1 && rbuf.size() == 1);
+        CHECK(dec(lbuf, 7) == "ACTGACT" && dec(rbuf, 3) == "GAC");
+    }
+    {
+        const std::string seq = repeat("ACTG", 10);
+        split_packed(encode_alloc(seq), seq.size(), 32, lbuf, rbuf);
+        CHECK(lbuf.size() == 2 && rbuf.size() == 1);
+        CHECK(dec(lbuf, 32) == seq.substr(0, 32) && dec(rbuf, 8) == seq.substr(32));
+    }
+}
+
 int main() {
     const std::pair<const char*, std::function<void()>> tests[] = {
         {"as_2bit", test_as_2bit}, {"from_2bit", test_from_2bit}, {"roundtrips", test_roundtrips},
-        {"hdist", test_hdist},     {"packed_sequence", test_packed_sequence}, {"errors", test_errors}};
+        {"hdist", test_hdist},     {"packed_sequence", test_packed_sequence}, {"errors", test_errors},
+        {"split_packed", test_split_packed}};
     for (const auto& t : tests) {
         t.second();
         std::printf("ok %s\n", t.first);

@@ -499,3 +499,94 @@ def test_device_fixed_length_counts_match_oracle(bn, read_len):
     assert np.array_equal(counts.cpu().numpy(), np.array(exp_counts, dtype=np.int64))
     assert np.array_equal(gc.cpu().numpy(), np.array(exp_gc))
     assert totals.tolist() == np.array(exp_counts).sum(axis=0).tolist()
+
+
+# ------------------------------------------------------------------ split_packed ----
+
+def test_split_packed_kats(bn, kats):
+    for k in kats["split_packed"]:
+        s = k["seq"].encode()
+        left, right = [123], [456]           # cleared, then filled (split.rs:30-31)
+        bn.split_packed(bn.encode_alloc(s), len(s), k["idx"], left, right)
+        assert (len(left), len(right)) == (k["n_left"], k["n_right"]), k["src"]
+        assert bytes(bn.decode_np(left, k["idx"])) == k["left"].encode()
+        assert bytes(bn.decode_np(right, len(s) - k["idx"])) == k["right"].encode()
+    for k in kats["split_packed_errors"]:
+        s = k["seq"].encode()
+        left, right = [123], [456]
+        err = gpu_error(bn, bn.split_packed, bn.encode_alloc(s), len(s), k["idx"], left, right)
+        assert err.key() == tuple(k["error"])
+        assert (left, right) == ([123], [456])  # validation comes before the clears (split.rs:22-31)
+
+
+def _split_case(rng, n_reads, max_len, extra_words=False):
+    lens = rng.integers(0, max_len + 1, n_reads)
+    lens[rng.random(n_reads) < 0.05] = 0
+    idx = (rng.random(n_reads) * (lens + 1)).astype(np.int64)
+    pick = rng.random(n_reads)
+    idx = np.where(pick < 0.1, 0, np.where(pick < 0.2, lens, np.where(pick < 0.35, (idx // 32) * 32, idx)))
+    idx = np.minimum(idx, lens)
+    words, wo = [], [0]
+    for r in range(n_reads):
+        w = oracle.PackedSequence(rand_seq(rng, int(lens[r])).tobytes()).data
+        if extra_words and r % 3 == 0:
+            w = list(w) + [int(x) for x in rng.integers(0, 2**63, int(rng.integers(1, 3)))]  # ebuf longer than needed
+        words.extend(w)
+        wo.append(wo[-1] + len(w))
+    return (np.array(words, dtype=np.uint64), np.array(wo, dtype=np.uint64), lens.astype(np.uint64), idx.astype(np.uint64))
+
+
+def _split_expect(words, wo, lens, idx):
+    L, R, lo, ro = [], [], [0], [0]
+    for r in range(lens.size):
+        left, right = oracle.split_packed(words[int(wo[r]) : int(wo[r + 1])], int(lens[r]), int(idx[r]))
+        L.extend(left)
+        R.extend(right)
+        lo.append(len(L))
+        ro.append(len(R))
+    return (np.array(L, dtype=np.uint64), np.array(lo, dtype=np.uint64), np.array(R, dtype=np.uint64), np.array(ro, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("profile", ["barcode", "long", "extra_words", "one"])
+def test_split_packed_batch_matches_oracle(bn, profile):
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(41)
+    n_reads, max_len = {"barcode": (5000, 280), "long": (300, 5000), "extra_words": (2000, 200), "one": (1, 100)}[profile]
+    words, wo, lens, idx = _split_case(rng, n_reads, max_len, extra_words=profile == "extra_words")
+    exp = _split_expect(words, wo, lens, idx)
+    got = bn.split_packed_batch(words, wo, lens, idx)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+    # device-resident form
+    t = [torch.from_numpy(a.view(np.int64)).cuda() for a in (words, wo, lens, idx)]
+    left, lo, right, ro, st = dv.split_packed_batch(*t)
+    st.check(t[2], t[3])
+    assert np.array_equal(lo.cpu().numpy().view(np.uint64), exp[1]) and np.array_equal(ro.cpu().numpy().view(np.uint64), exp[3])
+    assert np.array_equal(left[: int(lo[-1])].cpu().numpy().view(np.uint64), exp[0])
+    assert np.array_equal(right[: int(ro[-1])].cpu().numpy().view(np.uint64), exp[2])
+    # first failing read in index order
+    if n_reads > 10:
+        bad = idx.copy()
+        for r in (n_reads // 2, n_reads // 3):
+            bad[r] = lens[r] + np.uint64(1 + r % 5)
+        err = gpu_error(bn, bn.split_packed_batch, words, wo, lens, bad)
+        r0 = n_reads // 3
+        assert err.key() == ("IndexOutOfBounds", int(bad[r0]), int(lens[r0])) and err.record == r0
+        tb = torch.from_numpy(bad.view(np.int64)).cuda()
+        *_, st = dv.split_packed_batch(t[0], t[1], t[2], tb)
+        with pytest.raises(bn.NucleotideError) as ei:
+            st.check(t[2], tb)
+        assert ei.value.key() == err.key() and ei.value.record == r0
+
+
+def test_split_packed_empty_batch_and_short_buffer(bn):
+    got = bn.split_packed_batch(np.zeros(0, np.uint64), np.zeros(1, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint64))
+    assert [g.size for g in got] == [0, 1, 0, 1]
+    # empty ebuf in the general case: both halves empty (split.rs:45-47)
+    left, right = [1], [2]
+    bn.split_packed([], 10, 3, left, right)
+    assert (left, right) == ([], [])
+    # a non-empty ebuf that cannot hold slen bases: the reference panics or truncates; rejected here
+    err = gpu_error(bn, bn.split_packed, [0x1B], 100, 40, [], [])
+    assert err.key() == ("InvalidLength", 100)

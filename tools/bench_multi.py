@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3] under torchrun: hdist over 2^30 pairs of packed 32-mers plus base_counts / gc_content
+on 10 M x 150 bp reads, sharded over N GPUs (one process per GPU) with ONE NCCL all-reduce of the four base
+counters (and one of the hdist partial).  Every rank generates only its own shard (counter-based streams), so
+there is no data-path collective; the reduced totals are checked against closed-form expectations that do not
+depend on N: the same totals must come out at N = 1, 2, 4, 8.
+
+    torchrun --nproc-per-node N tools/bench_multi.py [--scale 1.0] [--reps 10]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch
+import torch.distributed as dist
+
+from bitnuc_b200 import device as dv
+from bitnuc_b200 import sharding as sh
+
+SEED = 0x5EEDB17C0DE5
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(t.item())
+
+    out = {"n_gpus": world}
+    # ---- hdist over pairs, sharded by pair index on even boundaries (16-byte aligned shards)
+    n_pairs = int((1 << 30) * args.scale)
+    p0, p1 = sh.shard_range(n_pairs, rank, world, align=2)
+    u = dv.synth_words(SEED, 2, p0, p1 - p0, device=dev)
+    v = dv.synth_words(SEED, 3, p0, p1 - p0, device=dev)
+    d = torch.empty(p1 - p0, dtype=torch.int32, device=dev)
+    tot = torch.empty(1, dtype=torch.int64, device=dev)
+
+    def hd():
+        dv.hdist_pairs(u, v, 32, out=d)
+        dv.hdist(u, v, 32 * (p1 - p0), out=tot)
+        sh.allreduce_sum(tot)
+
+    ms = timed(hd)
+    total = int(tot.item())
+    check = d.sum(dtype=torch.int64)
+    sh.allreduce_sum(check)
+    assert int(check.item()) == total, "sum of per-pair distances != whole-sequence distance"
+    out["hdist"] = {"pairs": n_pairs, "ms": ms, "Gpairs_s": n_pairs / ms / 1e6, "total_mismatches": total,
+                    "GB_s_aggregate": (20 + 16) * n_pairs / ms / 1e6}
+    del u, v, d
+
+    # ---- base_counts / gc on fixed-length reads, sharded by read index, NCCL all-reduce of the four counters
+    n_reads = int(10_000_000 * args.scale)
+    r0, r1 = sh.shard_range(n_reads, rank, world)
+    words = dv.synth_words(SEED, 4, 5 * r0, 5 * (r1 - r0), device=dev)
+    counts4 = torch.empty((r1 - r0, 4), dtype=torch.int64, device=dev)
+    gcs = torch.empty(r1 - r0, dtype=torch.float64, device=dev)
+    totals = torch.empty(4, dtype=torch.int64, device=dev)
+
+    def bc():
+        dv.base_counts_fixed(words, r1 - r0, 150, counts4=counts4, gc=gcs, totals=totals)
+        sh.allreduce_counts(totals)
+
+    ms = timed(bc)
+    t = totals.tolist()
+    assert sum(t) == 150 * n_reads
+    out["base_counts"] = {"reads": n_reads, "ms": ms, "Greads_s": n_reads / ms / 1e6, "totals": t, "gc_global": sh.gc_from_counts(t),
+                          "GB_s_aggregate": 80 * n_reads / ms / 1e6}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -8,8 +8,9 @@
 //   1. word offsets = exclusive prefix sum of ceil(len/32) over the reads (block sums, one-CTA scan
 //      of the sums, block-local scan + offset);
 //   2. encode, one thread per 16-base HALF of an output word (see encode_batch_kernel): warps walk
-//      consecutive output words, tiles of words are pulled from a global atomic counter, the owning
-//      read is found once per warp range by a search narrowed per tile and then advanced linearly.
+//      consecutive output words, each WARP pulls its tiles of 512 words from a global atomic counter (no
+//      CTA barrier anywhere), the owning read is found once per tile by a 32-ary warp search and then
+//      advanced linearly.
 // Work per warp step is uniform whatever the length mix (50 bp .. 10 kbp).  HBM-bound at
 // 1 B/base in + 8 B per word out + 16 B per read of offsets.
 #include "common.cuh"
@@ -26,18 +27,9 @@ struct WordsOfRead {
     }
 };
 
-// index of the read owning output word w: the last r in [lo, hi] with word_offsets[r] <= w
-__device__ __forceinline__ unsigned long long owner_read(const uint64_t* __restrict__ wo, unsigned long long lo,
-                                                         unsigned long long hi, unsigned long long w) {
-    while (lo < hi) {
-        const unsigned long long mid = lo + (hi - lo + 1) / 2;
-        if (__ldg(wo + mid) <= w) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-// Same result as owner_read over [0, n_reads-1], by a whole warp: 32 probes per step instead of one, so the
-// dependent chain is ~log32(n) loads long instead of log2(n).  All lanes return the answer.
+// Index of the read owning output word w (the last r in [0, n_reads-1] with word_offsets[r] <= w), found by a
+// whole warp: 32 probes per step instead of one, so the dependent chain is ~log32(n) loads long instead of
+// log2(n).  All lanes return the answer.
 __device__ __forceinline__ unsigned long long owner_read_warp(const uint64_t* __restrict__ wo, unsigned long long n_reads,
                                                               unsigned long long w) {
     const unsigned lane = threadIdx.x & 31;
@@ -55,7 +47,6 @@ __device__ __forceinline__ unsigned long long owner_read_warp(const uint64_t* __
 }
 
 constexpr int kWarpWords = 512;                          // consecutive output words per warp per tile
-constexpr int kBatchTile = kWarpsPerBlock * kWarpWords;  // output words per CTA tile
 constexpr int kGroupWords = 16;                          // words per warp step: one 16-base half-word per lane
 
 // Rare paths, out of line: byte-wise fetch of a lane's (<= 16) bytes, and the first invalid byte of them.
@@ -83,13 +74,15 @@ __device__ __forceinline__ uint4 align16(uint4 v, uint4 n, unsigned sh8) {
     return make_uint4(__funnelshift_r(w[WS], w[WS + 1], sh8), __funnelshift_r(w[WS + 1], w[WS + 2], sh8),
                       __funnelshift_r(w[WS + 2], w[WS + 3], sh8), __funnelshift_r(w[WS + 3], w[WS + 4], sh8));
 }
-__device__ __forceinline__ uint4 align16_dyn(uint4 v, uint4 n, unsigned s) {
-    switch (s >> 2) {
-    case 0: return align16<0>(v, n, 8 * (s & 3u));
-    case 1: return align16<1>(v, n, 8 * (s & 3u));
-    case 2: return align16<2>(v, n, 8 * (s & 3u));
-    default: return align16<3>(v, n, 8 * (s & 3u));
-    }
+// 16 bytes starting s (0..15, per lane) bytes into the aligned vector pair (v, n): two levels of word selects, then one funnel shift per word.
+__device__ __forceinline__ uint4 align16_lane(uint4 v, uint4 n, unsigned s) {
+    const bool q2 = s & 8u, q1 = s & 4u;
+    const uint32_t a0 = q2 ? v.z : v.x, a1 = q2 ? v.w : v.y, a2 = q2 ? n.x : v.z, a3 = q2 ? n.y : v.w, a4 = q2 ? n.z : n.x,
+                   a5 = q2 ? n.w : n.y;
+    const uint32_t b0 = q1 ? a1 : a0, b1 = q1 ? a2 : a1, b2 = q1 ? a3 : a2, b3 = q1 ? a4 : a3, b4 = q1 ? a5 : a4;
+    const unsigned sh8 = 8u * (s & 3u);
+    return make_uint4(__funnelshift_r(b0, b1, sh8), __funnelshift_r(b1, b2, sh8), __funnelshift_r(b2, b3, sh8),
+                      __funnelshift_r(b3, b4, sh8));
 }
 
 // Fast path body: `n_iter` steps of U groups (16 complete words each) of one read.  p = this lane's first
@@ -131,41 +124,32 @@ __device__ __forceinline__ unsigned fast_groups_any(const uint4* p, uint32_t* q,
     }
 }
 
-// One thread per 16-base HALF of an output word.  A warp walks kWarpWords consecutive output words read
-// by read (warp-uniform loop): inside a read, the 32 half-words of 16 consecutive words are one contiguous,
-// uniformly misaligned 512-byte run, fetched with two coalesced aligned 128-bit loads per lane and put in
-// place by a funnel shift whose word part is a template constant; the last (< 16 complete + 1 ragged)
-// words of a read take one masked pass in which the lanes past the end of the read idle.
+// One thread per 16-base HALF of an output word.  A warp walks kWarpWords consecutive output words in groups
+// of 16 words (32 half-words).  When the next group(s) lie inside one read, the 32 half-words are one
+// contiguous, uniformly misaligned 512-byte run, fetched with two coalesced aligned 128-bit loads per lane and
+// put in place by a funnel shift whose word part is a template constant (long reads live here).  Otherwise
+// the group takes the mixed pass: every lane finds the read owning its word (shuffle binary search over the
+// next 32 read boundaries) and fetches its bytes with its own alignment, so short reads (several per group)
+// keep all lanes busy too.
 __global__ void __launch_bounds__(kThreads, 4)
 encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ offsets, unsigned long long n_reads,
                     const uint64_t* __restrict__ word_offsets, uint64_t* __restrict__ out,
                     uint32_t* __restrict__ read_status, unsigned long long* __restrict__ status,
                     unsigned long long* __restrict__ tile_counter) {
-    __shared__ unsigned long long range[2];
-    __shared__ unsigned long long tile_s;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane & 1;
+    const unsigned lane = threadIdx.x & 31, half = lane & 1;
     const unsigned long long total_words = word_offsets[n_reads];
     const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(bytes) + offsets[0];        // valid address range of the bytes
     const uintptr_t buf_hi = reinterpret_cast<uintptr_t>(bytes) + offsets[n_reads];
-    const unsigned long long n_tiles = ceil_div(total_words, kBatchTile);
+    const unsigned long long n_tiles = ceil_div(total_words, kWarpWords);
     uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
-    for (;;) {  // persistent CTAs pull tiles from a global counter: dynamic balance, word count unknown to the host
-        __syncthreads();
-        if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1ull);
-        __syncthreads();
-        const unsigned long long tile = tile_s;
+    for (;;) {  // persistent WARPS pull tiles from a global counter: dynamic balance, no CTA barrier anywhere
+        unsigned long long tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        const unsigned long long w0 = tile * kBatchTile;
-        const unsigned long long w1 = w0 + kBatchTile < total_words ? w0 + kBatchTile : total_words;
-        if (warp < 2) {  // warps 0 and 1 locate the reads of the tile's first and last word
-            const unsigned long long rr = owner_read_warp(word_offsets, n_reads, warp ? w1 - 1 : w0);
-            if (lane == 0) range[warp] = rr;
-        }
-        __syncthreads();
-        const unsigned long long ww0 = w0 + (unsigned long long)warp * kWarpWords;   // this warp's words [ww0, ww1)
-        const unsigned long long ww1 = ww0 + kWarpWords < w1 ? ww0 + kWarpWords : w1;
-        if (ww0 >= ww1) continue;
-        unsigned long long r = owner_read(word_offsets, range[0], range[1], ww0);    // warp-uniform
+        const unsigned long long ww0 = tile * kWarpWords;                             // this warp's words [ww0, ww1)
+        const unsigned long long ww1 = ww0 + kWarpWords < total_words ? ww0 + kWarpWords : total_words;
+        unsigned long long r = owner_read_warp(word_offsets, n_reads, ww0);          // warp-uniform
         unsigned long long wo_next = __ldg(word_offsets + r + 1);
         {   // The warp's source bytes are one contiguous run (reads are adjacent in the byte buffer) of at most
             // 32 bytes per word: pull it into L2 now, so the dependent per-group loads below see L2 latency,
@@ -176,27 +160,20 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
             for (uintptr_t p = p0 + 128ull * lane; p < p1; p += 128ull * 32)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
-        unsigned long long cached_r = ~0ull, rb = 0, re = 0, wo = 0, full_end = 0;
-        unsigned s = 0;
         unsigned long long wb = ww0;
         while (wb < ww1) {
             while (wo_next <= wb) wo_next = __ldg(word_offsets + (++r) + 1);  // read owning word wb (skips empty reads)
-            if (r != cached_r) {  // per-read constants (warp-uniform)
-                cached_r = r;
-                rb = __ldg(offsets + r), re = __ldg(offsets + r + 1), wo = __ldg(word_offsets + r);
-                full_end = wo + (re - rb) / 32;                                           // words [wo, full_end) are complete
-                s = (unsigned)((reinterpret_cast<uintptr_t>(bytes) + rb) & 15u);          // misalignment of every 16-base half
-            }
-            // ---- fast path: groups of 16 complete words of read r.  The lanes' bytes are one contiguous,
-            // uniformly misaligned 512-byte run: two coalesced aligned 128-bit loads + a uniform funnel shift.
-            const unsigned long long seg_end = wo_next < ww1 ? wo_next : ww1;            // this read's words in the warp's range
             // ---- fast path: groups of 16 complete words of read r.  The 32 lanes' bytes are one contiguous,
             // uniformly misaligned 512-byte run: two coalesced aligned 128-bit loads + a funnel shift each.
-            {
-                const unsigned long long lim = full_end < seg_end ? full_end : seg_end;
+            if (wo_next - wb >= kGroupWords && ww1 - wb >= kGroupWords) {
+                const unsigned long long rb = __ldg(offsets + r), re = __ldg(offsets + r + 1), wo = __ldg(word_offsets + r);
+                const unsigned long long full_end = wo + (re - rb) / 32;                   // words [wo, full_end) are complete
+                const unsigned s = (unsigned)((reinterpret_cast<uintptr_t>(bytes) + rb) & 15u);  // misalignment of every half
+                unsigned long long lim = wo_next < ww1 ? wo_next : ww1;
+                if (full_end < lim) lim = full_end;
                 unsigned long long groups = lim > wb ? (lim - wb) / kGroupWords : 0;       // complete groups ahead in this read
                 const uintptr_t a0 = reinterpret_cast<uintptr_t>(bytes) + rb + (wb - wo) * 32ull - s;  // aligned start of the run
-                if (a0 < buf_lo || a0 + 32 > buf_hi) groups = 0;                           // first vector of the batch: tail pass
+                if (a0 < buf_lo || a0 + 32 > buf_hi) groups = 0;                           // first vector of the batch: mixed pass
                 else if (groups > (buf_hi - a0 - 32) / 512) groups = (buf_hi - a0 - 32) / 512;   // keep every aligned load inside the buffer
                 if (groups) {
                     constexpr int U = 2;
@@ -221,44 +198,86 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
                         }
                     }
                     wb += groups * kGroupWords;
+                    continue;
                 }
             }
-            // ---- tail pass: the (< 16 complete + 1 ragged) last words of the read, or a group at a batch edge.
-            // Lanes past the end of the read idle; bytes past the end of the read are replaced by 'A'.
-            if (wb < seg_end) {
-                const unsigned long long word = wb + (lane >> 1);
-                const bool active = word < seg_end;
-                const unsigned long long src = rb + (word - wo) * 32ull + half * 16u;  // byte offset of this lane's 16 bases
-                const int nb = !active || src >= re ? 0 : (re - src < 16 ? (int)(re - src) : 16);
-                uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-                if (nb > 0) {
-                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(bytes) + src - s;
-                    const bool two = s + (unsigned)nb > 16u;
-                    if (a0 >= buf_lo && a0 + (two ? 32 : 16) <= buf_hi) {
-                        const uint4 x = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0));
-                        const uint4 y = two ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0) + 1) : x;
-                        v = s ? align16_dyn(x, y, s) : x;
-                    } else {  // the aligned window pokes outside the byte buffer (first / last vector of the batch)
-                        v = batch_load_bytes(bytes + src, nb);
-                    }
-                    if (nb < 16) {  // ragged last word: bytes past the end of the read read as 'A'
-                        const uint32_t m0 = nb >= 4 ? ~0u : (1u << (8 * nb)) - 1u;
-                        const uint32_t m1 = nb >= 8 ? ~0u : nb <= 4 ? 0u : (1u << (8 * (nb - 4))) - 1u;
-                        const uint32_t m2 = nb >= 12 ? ~0u : nb <= 8 ? 0u : (1u << (8 * (nb - 8))) - 1u;
-                        const uint32_t m3 = nb <= 12 ? 0u : (1u << (8 * (nb - 12))) - 1u;
-                        v.x = (v.x & m0) | (0x41414141u & ~m0);
-                        v.y = (v.y & m1) | (0x41414141u & ~m1);
-                        v.z = (v.z & m2) | (0x41414141u & ~m2);
-                        v.w = (v.w & m3) | (0x41414141u & ~m3);
-                    }
+            // ---- mixed pass: the next (<= 16) output words, whatever reads they belong to.  Lane j fetches the
+            // word offset of read r+1+j (one coalesced load); every lane then finds the read owning its word by
+            // a binary search over those 32 boundaries with shuffles, and fetches its 16 bases with its own
+            // alignment.  Bytes past the end of a read are replaced by 'A' (code 0 = the zero padding of the tail).
+            const unsigned long long gend = wb + kGroupWords < ww1 ? wb + kGroupWords : ww1;
+            const unsigned long long bidx = r + 1 + lane;
+            const unsigned long long bj = bidx <= n_reads ? __ldg(word_offsets + bidx) : ~0ull;
+            const unsigned long long word = wb + (lane >> 1);
+            const bool active = word < gend;
+            const bool overflow = __shfl_sync(0xffffffffu, bj, 31) < gend;   // > 32 reads start here (empty reads): rare
+            unsigned long long ri, wo_i;
+            if (!overflow) {
+                unsigned c = 0;  // number of boundaries <= word
+#pragma unroll
+                for (unsigned st = 16; st; st >>= 1) {
+                    const unsigned long long t = __shfl_sync(0xffffffffu, bj, c + st - 1);
+                    if (t <= word) c += st;
                 }
-                uint32_t bad = 0;
-                const uint32_t code = pack16(v, bad);
+                const unsigned long long prev = __shfl_sync(0xffffffffu, bj, (c + 31u) & 31u);  // word offset of read r + c
+                ri = r + c;
+                wo_i = c ? prev : __ldg(word_offsets + r);
+                if (!active) ri = r, wo_i = word;
+            } else {
+                unsigned long long lo = r, hi = n_reads - 1;
                 if (active) {
-                    out32[2 * word + half] = code;
-                    if (bad & kValidMask) batch_report_invalid(bytes, src, nb, rb, r, read_status, status);
+                    while (lo < hi) {
+                        const unsigned long long mid = lo + (hi - lo + 1) / 2;
+                        if (__ldg(word_offsets + mid) <= word) lo = mid; else hi = mid - 1;
+                    }
                 }
-                wb = wb + kGroupWords < seg_end ? wb + kGroupWords : seg_end;
+                ri = lo;
+                wo_i = active ? __ldg(word_offsets + ri) : word;
+            }
+            const unsigned long long rb_i = __ldg(offsets + ri), re_i = __ldg(offsets + ri + 1);
+            const unsigned long long src = rb_i + (word - wo_i) * 32ull + half * 16u;  // byte offset of this lane's 16 bases
+            const int nb = !active || src >= re_i ? 0 : (re_i - src < 16 ? (int)(re_i - src) : 16);
+            uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+            if (nb > 0) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + src;
+                const unsigned s = (unsigned)(a & 15u);
+                const uintptr_t a0 = a - s;
+                const bool two = s + (unsigned)nb > 16u;
+                if (a0 >= buf_lo && a0 + (two ? 32 : 16) <= buf_hi) {
+                    const uint4 x = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0));
+                    const uint4 y = two ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0) + 1) : x;
+                    v = align16_lane(x, y, s);
+                } else {  // the aligned window pokes outside the byte buffer (first / last vector of the batch)
+                    v = batch_load_bytes(bytes + src, nb);
+                }
+                if (nb < 16) {  // ragged last word: bytes past the end of the read read as 'A'
+                    const unsigned long long klo = nb >= 8 ? ~0ull : (1ull << (8 * nb)) - 1ull;
+                    const unsigned long long khi = nb <= 8 ? 0ull : (1ull << (8 * (nb - 8))) - 1ull;
+                    const uint32_t m0 = (uint32_t)klo, m1 = (uint32_t)(klo >> 32), m2 = (uint32_t)khi, m3 = (uint32_t)(khi >> 32);
+                    v.x = (v.x & m0) | (0x41414141u & ~m0);
+                    v.y = (v.y & m1) | (0x41414141u & ~m1);
+                    v.z = (v.z & m2) | (0x41414141u & ~m2);
+                    v.w = (v.w & m3) | (0x41414141u & ~m3);
+                }
+            }
+            uint32_t bad = 0;
+            const uint32_t code = pack16(v, bad);
+            if (active) {
+                out32[2 * word + half] = code;
+                if (bad & kValidMask) batch_report_invalid(bytes, src, nb, rb_i, ri, read_status, status);
+            }
+            // advance to the read owning word `gend`
+            wb = gend;
+            if (wb < ww1) {
+                if (!overflow) {
+                    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, bj <= wb));
+                    const unsigned long long nx = __shfl_sync(0xffffffffu, bj, cnt & 31u);
+                    r += cnt;
+                    wo_next = cnt < 32 ? nx : __ldg(word_offsets + r + 1);
+                } else {
+                    r = owner_read_warp(word_offsets, n_reads, wb);
+                    wo_next = __ldg(word_offsets + r + 1);
+                }
             }
         }
     }

@@ -102,11 +102,8 @@ as_2bit_padded_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ out, 
 }
 
 // Tightly packed records (stride == k): every byte of the buffer belongs to a record, so the bytes
-// are packed exactly like the streaming encode (one aligned 16-byte vector per lane, coalesced, validated
-// as a whole) and each record is then assembled from the <= 3 vectors it straddles with three warp
-// shuffles and two funnel shifts.  A warp owns kTightGroups groups of `rpw` records; the byte span of a
-// group fits the warp's 32 vectors, and the loads of all groups are issued before the first use.
-constexpr int kTightGroups = 4;
+// are packed exactly like the streaming encode (aligned 16-byte vectors, coalesced, validated as a whole)
+// and each record is then assembled from the <= 3 vectors it straddles with two funnel shifts.
 
 __device__ __noinline__ uint4 load_vector_at_edge(const uint8_t* recs, long long vbyte, unsigned long long total) {
     uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};  // 'A' outside the buffer
@@ -128,12 +125,12 @@ __device__ __noinline__ void report_vector_invalid(uint4 v, long long vbyte, uns
     }
 }
 
-// one group of <= rpw records starting at record r0 (any position in the buffer, any count)
+// one group of <= rpw records [r0, min(r0 + rpw, r_end)) (any position in the buffer, any count)
 __device__ __noinline__ void as_2bit_tight_group_slow(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k,
-                                                      unsigned rpw, unsigned long long r0, uint64_t* __restrict__ out,
-                                                      unsigned long long* __restrict__ status) {
+                                                      unsigned rpw, unsigned long long r0, unsigned long long r_end,
+                                                      uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned cnt = (unsigned)(n - r0 < rpw ? n - r0 : rpw);
+    const unsigned cnt = (unsigned)(r_end - r0 < rpw ? r_end - r0 : rpw);
     const unsigned long long total = n * k, span0 = r0 * k;
     const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(recs) + span0) & 15u);
     const long long vbyte = (long long)span0 - mis + 16ll * lane;  // buffer offset of this lane's vector (may be < 0)
@@ -158,49 +155,57 @@ __device__ __noinline__ void as_2bit_tight_group_slow(const uint8_t* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(kKmerThreads)
-as_2bit_tight_kernel(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k, unsigned rpw,
+// Fast kernel.  A warp owns `rpt` (a multiple of 32, <= 256) consecutive records = one contiguous span of at most
+// 2048 + 15 bytes: up to 5 aligned vectors per lane, all loaded before the first use, packed to 32-bit codes and
+// parked in the warp's own shared-memory strip (no CTA barrier).  Then every lane assembles whole records
+// (three LDS + two funnel shifts each) and the warp stores 32 consecutive words per round, all lanes busy.
+constexpr int kTightMaxRounds = 5;
+constexpr int kTightStrip = 32 * kTightMaxRounds + 4;   // + slack: a record may index two codes past its last vector
+
+__global__ void __launch_bounds__(kKmerThreads, 2)
+as_2bit_tight_kernel(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k, unsigned rpt,
                      uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
+    __shared__ uint32_t strips[kKmerThreads / 32][kTightStrip];
     const unsigned lane = threadIdx.x & 31;
+    uint32_t* codes = strips[threadIdx.x >> 5];
     const unsigned long long warp = (unsigned long long)blockIdx.x * (kKmerThreads / 32) + (threadIdx.x >> 5);
-    const unsigned long long rw = warp * ((unsigned long long)kTightGroups * rpw);  // first record of the warp
+    const unsigned long long rw = warp * rpt;                                     // first record of the warp
     if (rw >= n) return;
-    const unsigned gbytes = rpw * k;                                              // bytes per full group (<= 497)
+    const unsigned cnt = (unsigned)(n - rw < rpt ? n - rw : rpt);
     const uint8_t* wbase = recs + rw * k;
     const unsigned m0 = (unsigned)(reinterpret_cast<uintptr_t>(wbase) & 15u);
     const uint8_t* abase = wbase - m0;                                            // 16-byte aligned
-    // interior warp: all groups full and every vector it may touch lies inside the buffer
-    const bool interior = rw + (unsigned long long)kTightGroups * rpw <= n && abase >= recs &&
-                          abase + (kTightGroups - 1) * gbytes + m0 + 528 <= recs + n * k;
-    if (!interior) {
-        for (int g = 0; g < kTightGroups; ++g)
-            if (rw + (unsigned long long)g * rpw < n) as_2bit_tight_group_slow(recs, n, k, rpw, rw + (unsigned long long)g * rpw, out, status);
+    const unsigned nvec = (m0 + cnt * k + 15u) / 16u;                             // <= 129
+    if (abase < recs || abase + 16ull * nvec > recs + n * k) {                    // a vector pokes outside the buffer
+        const unsigned rpw = 497u / k < 32u ? 497u / k : 32u;                     // 15 + rpw*k <= 512: one vector per lane
+        for (unsigned g = 0; g < cnt; g += rpw) as_2bit_tight_group_slow(recs, n, k, rpw, rw + g, rw + cnt, out, status);
         return;
     }
-    uint4 v[kTightGroups];
+    const uint4* src = reinterpret_cast<const uint4*>(abase) + lane;
+    uint4 v[kTightMaxRounds];
 #pragma unroll
-    for (int g = 0; g < kTightGroups; ++g)
-        v[g] = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(abase + ((m0 + g * gbytes) & ~15u)) + lane);
+    for (int g = 0; g < kTightMaxRounds; ++g)
+        if (32u * g + lane < nvec) v[g] = ld128<LD_PLAIN>(src + 32 * g);
+#pragma unroll
+    for (int g = 0; g < kTightMaxRounds; ++g) {
+        if (32u * g + lane < nvec) {
+            uint32_t bad = 0;
+            codes[32 * g + lane] = pack16(v[g], bad);
+            if (bad & kValidMask) report_vector_invalid(v[g], (long long)(abase - recs) + 16ll * (32 * g + lane), status);
+        }
+    }
+    __syncwarp();
     const uint32_t mlo = k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u;
     const uint32_t mhi = k >= 32 ? 0xFFFFFFFFu : k <= 16 ? 0u : (1u << (2 * k - 32)) - 1u;
-    uint64_t* o = out + rw + lane;
-#pragma unroll
-    for (int g = 0; g < kTightGroups; ++g) {
-        uint32_t bad = 0;
-        const uint32_t code = pack16(v[g], bad);
-        if (bad & kValidMask)
-            report_vector_invalid(v[g], (long long)(abase - recs) + ((m0 + g * gbytes) & ~15u) + 16 * lane, status);
-        const unsigned rel = ((m0 + g * gbytes) & 15u) + lane * k;  // byte offset of the record from the group's first vector
+    uint2* o = reinterpret_cast<uint2*>(out + rw);
+    for (unsigned j = lane; j < cnt; j += 32) {
+        const unsigned rel = m0 + j * k;  // byte offset of the record from the span's first vector
         const unsigned vi = rel >> 4, sh = 2 * (rel & 15u);
-        const uint32_t c0 = __shfl_sync(0xffffffffu, code, vi & 31);
-        const uint32_t c1 = __shfl_sync(0xffffffffu, code, (vi + 1) & 31);
-        const uint32_t c2 = __shfl_sync(0xffffffffu, code, (vi + 2) & 31);
-        if (lane < rpw) {
-            uint2 w;
-            w.x = __funnelshift_r(c0, c1, sh) & mlo;
-            w.y = __funnelshift_r(c1, c2, sh) & mhi;
-            *reinterpret_cast<uint2*>(o + g * rpw) = w;
-        }
+        const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
+        uint2 w;
+        w.x = __funnelshift_r(c0, c1, sh) & mlo;
+        w.y = __funnelshift_r(c1, c2, sh) & mhi;
+        st_stream_v2(o + j, w);
     }
 }
 
@@ -372,9 +377,10 @@ cudaError_t launch_as_2bit_batch(const DeviceInfo& di, const uint8_t* d_recs, si
         as_2bit_padded_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(
             reinterpret_cast<const uint4*>(d_recs), reinterpret_cast<uint32_t*>(d_out), n_vec, (int)k, d_status);
     } else if (stride == k) {
-        const unsigned rpw = 497u / k < 32u ? 497u / k : 32u;  // 15 + rpw*k <= 512: the span fits the warp's 32 vectors
-        const unsigned long long warps = ceil_div(n, (unsigned long long)rpw * kTightGroups);
-        as_2bit_tight_kernel<<<(unsigned)ceil_div(warps, kKmerThreads / 32), kKmerThreads, 0, s>>>(d_recs, n, k, rpw, d_out, d_status);
+        const unsigned rounds = 64u / k < 2u ? 2u : 64u / k > 8u ? 8u : 64u / k;  // rpt * k <= 2048 bytes per warp
+        const unsigned rpt = 32u * rounds;
+        const unsigned long long warps = ceil_div(n, rpt);
+        as_2bit_tight_kernel<<<(unsigned)ceil_div(warps, kKmerThreads / 32), kKmerThreads, 0, s>>>(d_recs, n, k, rpt, d_out, d_status);
     } else if (stride <= (size_t)kStageMaxStride) {
         as_2bit_staged_kernel<<<(unsigned)ceil_div(n, kStageRecords), kThreads, 0, s>>>(d_recs, n, k, (unsigned)stride, d_out,
                                                                                          d_status);

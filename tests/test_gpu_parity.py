@@ -351,7 +351,7 @@ def make_reads(rng, lens, mixed=True):
     return data, offsets
 
 
-@pytest.mark.parametrize("profile", ["short", "cfg5", "with_empties", "single"])
+@pytest.mark.parametrize("profile", ["short", "cfg5", "with_empties", "single", "mostly_empty", "illumina", "mixed"])
 def test_encode_batch_matches_oracle(bn, profile):
     rng = np.random.default_rng(23)
     lens = {
@@ -359,6 +359,9 @@ def test_encode_batch_matches_oracle(bn, profile):
         "cfg5": 50 + rng.integers(0, 9951, 300),   # 50 bp .. 10 kbp, SURVEY.md 8(d) cfg 5
         "with_empties": np.where(rng.random(3000) < 0.3, 0, rng.integers(1, 200, 3000)),
         "single": np.array([100_001]),
+        "mostly_empty": np.where(rng.random(20000) < 0.97, 0, rng.integers(1, 40, 20000)),   # > 32 reads start in one group
+        "illumina": rng.integers(100, 152, 6000),
+        "mixed": np.where(rng.random(2500) < 0.9, rng.integers(20, 300, 2500), rng.integers(300, 20000, 2500)),
     }[profile]
     data, offsets = make_reads(rng, lens)
     words, wo = bn.encode_batch(data, offsets)

@@ -6,7 +6,7 @@ the measured HBM peak, after checking the result against a size-independent prop
 headline benchmark (that is bench.py); this is the evidence behind the per-kernel rooflines in
 DESIGN.md.
 
-    python tools/bench_configs.py [--scale 1.0] [--reps 10] [--only cfg3,cfg4,...]
+    python tools/bench_configs.py [--scale 1.0] [--reps 10] [--only cfg3,cfg4,short,...]
 """
 from __future__ import annotations
 
@@ -196,6 +196,62 @@ def cfg5(scale, reps):
     print(json.dumps({"cfg5 error parity": "ok", "injected": int(victims.size), "first": [int(victims[0]), int(pos[0])]}), flush=True)
 
 
+def short_reads(scale, reps):
+    """encode_batch on a short-read profile (40 M x 100-151 bp, Illumina-like) and split_packed of the result
+    at a barcode|UMI boundary (idx = 26) -- SURVEY.md 8(f) rank 1."""
+    n_reads = int(40_000_000 * scale)
+    from oracle import oracle_np as onp  # only the counter hash of the generator (test infrastructure)
+    lens = (100 + onp.splitmix64(np.arange(n_reads, dtype=np.uint64) + np.uint64(SEED + 6)) % np.uint64(52)).astype(np.uint64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    total = int(offsets[-1])
+    data = dv.synth_ascii(SEED, 6, 0, total)
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    words = torch.empty(total // 32 + n_reads, dtype=torch.int64, device="cuda")
+    wo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    ctx = dv.api.default_context(0)
+    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n_reads), dtype=torch.uint8, device="cuda")
+    st = dv.Status("cuda")
+
+    def run():
+        dv.raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, dv._ptr(words),
+                                                 dv._ptr(wo), None, dv._ptr(st.word), dv._ptr(scratch)))
+
+    ms = timed(run, reps)
+    st.check()
+    n_words = int(wo[-1].item())
+    assert n_words == int(((lens + np.uint64(31)) // np.uint64(32)).sum())
+    for ridx in (0, 1, n_reads // 2, n_reads - 1):
+        w0, ln = int(wo[ridx].item()), int(lens[ridx])
+        assert torch.equal(dv.decode(words[w0 : w0 + (ln + 31) // 32].contiguous(), ln), data[int(offsets[ridx]) : int(offsets[ridx]) + ln])
+    report(f"short reads encode_batch reads={n_reads} bases={total}", ms, total + 8 * n_words + 16 * n_reads, total, "bases")
+
+    d_lens = torch.from_numpy(lens.view(np.int64)).cuda()
+    idx = torch.full((n_reads,), 26, dtype=torch.int64, device="cuda")
+    words = words[:n_words]
+    left = torch.empty(n_words + n_reads, dtype=torch.int64, device="cuda")
+    right = torch.empty(n_words, dtype=torch.int64, device="cuda")
+    lo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    ro = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    sscr = torch.empty(ctx.lib.bn_split_packed_scratch_bytes(n_reads), dtype=torch.uint8, device="cuda")
+    sst = dv.SplitStatus("cuda")
+
+    def split():
+        dv.raise_for(ctx.lib.bn_split_packed_batch_dev(ctx.handle, dv._stream(), dv._ptr(words), dv._ptr(wo), dv._ptr(d_lens), dv._ptr(idx),
+                                                       n_reads, dv._ptr(left), dv._ptr(lo), dv._ptr(right), dv._ptr(ro), dv._ptr(sst.word),
+                                                       dv._ptr(sscr)))
+
+    ms = timed(split, reps)
+    sst.check(d_lens, idx)
+    assert int(lo[-1].item()) == n_reads and int(ro[-1].item()) == n_words
+    # the left halves decode to the first 26 bases of each read
+    for ridx in (0, 7, n_reads - 1):
+        got = dv.decode(left[ridx : ridx + 1].contiguous(), 26)
+        o = int(offsets[ridx])
+        assert torch.equal(got, data[o : o + 26])
+    # in: words + offsets + lens + idx; out: left (1 word) + right (same words) + two offsets
+    report(f"split_packed idx=26 reads={n_reads}", ms, 8 * n_words + 24 * n_reads + 8 * n_reads + 8 * n_words + 16 * n_reads, n_reads, "reads")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
@@ -205,7 +261,7 @@ def main():
     torch.cuda.set_device(0)
     print(json.dumps({"device": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak(), "scale": args.scale}), flush=True)
     for name in args.only.split(","):
-        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[name](args.scale, args.reps)
+        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "short": short_reads}[name](args.scale, args.reps)
         torch.cuda.empty_cache()
 
 

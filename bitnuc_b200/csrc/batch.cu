@@ -74,15 +74,21 @@ __device__ __forceinline__ uint4 align16(uint4 v, uint4 n, unsigned sh8) {
     return make_uint4(__funnelshift_r(w[WS], w[WS + 1], sh8), __funnelshift_r(w[WS + 1], w[WS + 2], sh8),
                       __funnelshift_r(w[WS + 2], w[WS + 3], sh8), __funnelshift_r(w[WS + 3], w[WS + 4], sh8));
 }
-// 16 bytes starting s (0..15, per lane) bytes into the aligned vector pair (v, n): two levels of word selects, then one funnel shift per word.
-__device__ __forceinline__ uint4 align16_lane(uint4 v, uint4 n, unsigned s) {
+// 32 bytes starting s (0..15, per lane) bytes into the aligned vector triple (x, y, z): two levels of word
+// selects, then one funnel shift per word.
+__device__ __forceinline__ void align32_lane(uint4 x, uint4 y, uint4 z, unsigned s, uint4& lo, uint4& hi) {
+    const uint32_t w[12] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w, z.x, z.y, z.z, z.w};
     const bool q2 = s & 8u, q1 = s & 4u;
-    const uint32_t a0 = q2 ? v.z : v.x, a1 = q2 ? v.w : v.y, a2 = q2 ? n.x : v.z, a3 = q2 ? n.y : v.w, a4 = q2 ? n.z : n.x,
-                   a5 = q2 ? n.w : n.y;
-    const uint32_t b0 = q1 ? a1 : a0, b1 = q1 ? a2 : a1, b2 = q1 ? a3 : a2, b3 = q1 ? a4 : a3, b4 = q1 ? a5 : a4;
+    uint32_t a[10], b[9];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = q2 ? w[i + 2] : w[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) b[i] = q1 ? a[i + 1] : a[i];
     const unsigned sh8 = 8u * (s & 3u);
-    return make_uint4(__funnelshift_r(b0, b1, sh8), __funnelshift_r(b1, b2, sh8), __funnelshift_r(b2, b3, sh8),
-                      __funnelshift_r(b3, b4, sh8));
+    lo = make_uint4(__funnelshift_r(b[0], b[1], sh8), __funnelshift_r(b[1], b[2], sh8), __funnelshift_r(b[2], b[3], sh8),
+                    __funnelshift_r(b[3], b[4], sh8));
+    hi = make_uint4(__funnelshift_r(b[4], b[5], sh8), __funnelshift_r(b[5], b[6], sh8), __funnelshift_r(b[6], b[7], sh8),
+                    __funnelshift_r(b[7], b[8], sh8));
 }
 
 // Fast path body: `n_iter` steps of U groups (16 complete words each) of one read.  p = this lane's first
@@ -128,15 +134,15 @@ __device__ __forceinline__ unsigned fast_groups_any(const uint4* p, uint32_t* q,
 // of 16 words (32 half-words).  When the next group(s) lie inside one read, the 32 half-words are one
 // contiguous, uniformly misaligned 512-byte run, fetched with two coalesced aligned 128-bit loads per lane and
 // put in place by a funnel shift whose word part is a template constant (long reads live here).  Otherwise
-// the group takes the mixed pass: every lane finds the read owning its word (shuffle binary search over the
-// next 32 read boundaries) and fetches its bytes with its own alignment, so short reads (several per group)
-// keep all lanes busy too.
+// the next 32 words take the mixed pass, one word per lane: every lane finds the read owning its word (shuffle
+// binary search over the next 32 read boundaries) and fetches its bytes with its own alignment, so short reads
+// (several per group) keep all lanes busy too.
 __global__ void __launch_bounds__(kThreads, 4)
 encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ offsets, unsigned long long n_reads,
                     const uint64_t* __restrict__ word_offsets, uint64_t* __restrict__ out,
                     uint32_t* __restrict__ read_status, unsigned long long* __restrict__ status,
                     unsigned long long* __restrict__ tile_counter) {
-    const unsigned lane = threadIdx.x & 31, half = lane & 1;
+    const unsigned lane = threadIdx.x & 31;
     const unsigned long long total_words = word_offsets[n_reads];
     const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(bytes) + offsets[0];        // valid address range of the bytes
     const uintptr_t buf_hi = reinterpret_cast<uintptr_t>(bytes) + offsets[n_reads];
@@ -201,84 +207,83 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
                     continue;
                 }
             }
-            // ---- mixed pass: the next (<= 16) output words, whatever reads they belong to.  Lane j fetches the
-            // word offset of read r+1+j (one coalesced load); every lane then finds the read owning its word by
-            // a binary search over those 32 boundaries with shuffles, and fetches its 16 bases with its own
-            // alignment.  Bytes past the end of a read are replaced by 'A' (code 0 = the zero padding of the tail).
-            const unsigned long long gend = wb + kGroupWords < ww1 ? wb + kGroupWords : ww1;
+            // ---- mixed pass: the next (<= 32) output words, one per lane, whatever reads they belong to.  Lane j
+            // fetches the word offset of read r+1+j (one coalesced load); every lane then finds the read owning
+            // its word by a binary search over those 32 boundaries with shuffles (32-bit, relative to wb), and
+            // fetches its 32 bases with its own alignment: <= 3 aligned vectors, two levels of word selects, one
+            // funnel shift per word.  Bases past the end of a read are cut from the packed word (zero padding).
+            const unsigned gcount = ww1 - wb < 32 ? (unsigned)(ww1 - wb) : 32u;
             const unsigned long long bidx = r + 1 + lane;
             const unsigned long long bj = bidx <= n_reads ? __ldg(word_offsets + bidx) : ~0ull;
-            const unsigned long long word = wb + (lane >> 1);
-            const bool active = word < gend;
-            const bool overflow = __shfl_sync(0xffffffffu, bj, 31) < gend;   // > 32 reads start here (empty reads): rare
-            unsigned long long ri, wo_i;
+            const unsigned long long first_w = wb - __ldg(word_offsets + r);            // index of word wb inside read r
+            const unsigned long long d64 = bj - wb;                                      // > 0: read r owns word wb
+            const unsigned bd = d64 > 0xFFFFFFFEull ? 0xFFFFFFFFu : (unsigned)d64;
+            const bool active = lane < gcount;
+            const bool overflow = __shfl_sync(0xffffffffu, bd, 31) < gcount;             // > 32 reads start here (empty reads): rare
+            unsigned long long ri, wi;   // owning read, index of this lane's word inside it
             if (!overflow) {
-                unsigned c = 0;  // number of boundaries <= word
+                unsigned c = 0;  // number of boundaries <= lane
 #pragma unroll
                 for (unsigned st = 16; st; st >>= 1) {
-                    const unsigned long long t = __shfl_sync(0xffffffffu, bj, c + st - 1);
-                    if (t <= word) c += st;
+                    const unsigned t = __shfl_sync(0xffffffffu, bd, c + st - 1);
+                    if (t <= lane) c += st;
                 }
-                const unsigned long long prev = __shfl_sync(0xffffffffu, bj, (c + 31u) & 31u);  // word offset of read r + c
+                const unsigned prev = __shfl_sync(0xffffffffu, bd, (c + 31u) & 31u);     // first word of read r + c, relative to wb
+                if (!active) c = 0;
                 ri = r + c;
-                wo_i = c ? prev : __ldg(word_offsets + r);
-                if (!active) ri = r, wo_i = word;
+                wi = c ? (unsigned long long)(lane - prev) : first_w + lane;
             } else {
                 unsigned long long lo = r, hi = n_reads - 1;
                 if (active) {
                     while (lo < hi) {
                         const unsigned long long mid = lo + (hi - lo + 1) / 2;
-                        if (__ldg(word_offsets + mid) <= word) lo = mid; else hi = mid - 1;
+                        if (__ldg(word_offsets + mid) <= wb + lane) lo = mid; else hi = mid - 1;
                     }
                 }
                 ri = lo;
-                wo_i = active ? __ldg(word_offsets + ri) : word;
+                wi = wb + lane - __ldg(word_offsets + ri);
             }
             const unsigned long long rb_i = __ldg(offsets + ri), re_i = __ldg(offsets + ri + 1);
-            const unsigned long long src = rb_i + (word - wo_i) * 32ull + half * 16u;  // byte offset of this lane's 16 bases
-            const int nb = !active || src >= re_i ? 0 : (re_i - src < 16 ? (int)(re_i - src) : 16);
-            uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-            if (nb > 0) {
+            const unsigned long long src = rb_i + wi * 32ull;                            // byte offset of this lane's 32 bases
+            const unsigned nb = !active || src >= re_i ? 0u : (re_i - src < 32 ? (unsigned)(re_i - src) : 32u);
+            if (nb) {
                 const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + src;
                 const unsigned s = (unsigned)(a & 15u);
                 const uintptr_t a0 = a - s;
-                const bool two = s + (unsigned)nb > 16u;
-                if (a0 >= buf_lo && a0 + (two ? 32 : 16) <= buf_hi) {
-                    const uint4 x = ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0));
-                    const uint4 y = two ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(a0) + 1) : x;
-                    v = align16_lane(x, y, s);
+                const unsigned nv = (s + nb + 15u) >> 4;                                 // aligned vectors holding the bases: 1..3
+                uint4 lo4, hi4;
+                if (a0 >= buf_lo && a0 + 16u * nv <= buf_hi) {
+                    const uint4* pv = reinterpret_cast<const uint4*>(a0);
+                    const uint4 x = ld128<LD_PLAIN>(pv);
+                    const uint4 y = nv > 1 ? ld128<LD_PLAIN>(pv + 1) : x;
+                    const uint4 z = nv > 2 ? ld128<LD_PLAIN>(pv + 2) : y;
+                    align32_lane(x, y, z, s, lo4, hi4);
                 } else {  // the aligned window pokes outside the byte buffer (first / last vector of the batch)
-                    v = batch_load_bytes(bytes + src, nb);
+                    lo4 = batch_load_bytes(bytes + src, nb < 16 ? (int)nb : 16);
+                    hi4 = batch_load_bytes(bytes + src + 16, nb > 16 ? (int)nb - 16 : 0);
                 }
-                if (nb < 16) {  // ragged last word: bytes past the end of the read read as 'A'
-                    const unsigned long long klo = nb >= 8 ? ~0ull : (1ull << (8 * nb)) - 1ull;
-                    const unsigned long long khi = nb <= 8 ? 0ull : (1ull << (8 * (nb - 8))) - 1ull;
-                    const uint32_t m0 = (uint32_t)klo, m1 = (uint32_t)(klo >> 32), m2 = (uint32_t)khi, m3 = (uint32_t)(khi >> 32);
-                    v.x = (v.x & m0) | (0x41414141u & ~m0);
-                    v.y = (v.y & m1) | (0x41414141u & ~m1);
-                    v.z = (v.z & m2) | (0x41414141u & ~m2);
-                    v.w = (v.w & m3) | (0x41414141u & ~m3);
-                }
+                // Bytes past the end of the read belong to the next read: they are cut from the packed word below
+                // and, should one of them trip the validity test, the exact per-byte check sorts it out.
+                uint32_t bad = 0;
+                const uint32_t c_lo = pack16(lo4, bad), c_hi = pack16(hi4, bad);
+                uint64_t w64 = ((uint64_t)c_hi << 32) | c_lo;
+                if (nb < 32) w64 &= (1ull << (2 * nb)) - 1ull;
+                out[wb + lane] = w64;
+                if (bad & kValidMask) batch_report_invalid(bytes, src, (int)nb, rb_i, ri, read_status, status);
             }
-            uint32_t bad = 0;
-            const uint32_t code = pack16(v, bad);
-            if (active) {
-                out32[2 * word + half] = code;
-                if (bad & kValidMask) batch_report_invalid(bytes, src, nb, rb_i, ri, read_status, status);
-            }
-            // advance to the read owning word `gend`
-            wb = gend;
-            if (wb < ww1) {
+            // advance to the read owning word wb + gcount
+            if (wb + gcount < ww1) {
                 if (!overflow) {
-                    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, bj <= wb));
-                    const unsigned long long nx = __shfl_sync(0xffffffffu, bj, cnt & 31u);
+                    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, bd <= gcount));
+                    const unsigned nx = __shfl_sync(0xffffffffu, bd, cnt & 31u);
                     r += cnt;
-                    wo_next = cnt < 32 ? nx : __ldg(word_offsets + r + 1);
+                    wo_next = cnt < 32 && nx != 0xFFFFFFFFu ? wb + nx : __ldg(word_offsets + r + 1);
                 } else {
-                    r = owner_read_warp(word_offsets, n_reads, wb);
+                    r = owner_read_warp(word_offsets, n_reads, wb + gcount);
                     wo_next = __ldg(word_offsets + r + 1);
                 }
             }
+            wb += gcount;
         }
     }
 }

@@ -57,8 +57,8 @@ PROTOTYPES = {
     "bn_base_counts_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "bn_base_counts_batch_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
     "bn_base_counts_fixed_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp]),
-    "bn_encode_batch_scratch_bytes": (_sz, [_sz]),
-    "bn_encode_batch_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "bn_encode_batch_scratch_bytes": (_sz, [_sz, _sz]),
+    "bn_encode_batch_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "bn_split_packed_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _errp]),
     "bn_split_packed_scratch_bytes": (_sz, [_sz]),
     "bn_split_packed_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),

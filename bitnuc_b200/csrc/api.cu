@@ -349,14 +349,14 @@ int bn_base_counts_fixed_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words,
     return BN_OK;
 }
 
-size_t bn_encode_batch_scratch_bytes(size_t n_reads) { return bn::encode_batch_scratch_bytes(n_reads); }
+size_t bn_encode_batch_scratch_bytes(size_t n_reads, size_t n_bytes) { return bn::encode_batch_scratch_bytes(n_reads, n_bytes); }
 
-int bn_encode_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads,
+int bn_encode_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads, size_t n_bytes,
                         uint64_t* d_out_words, uint64_t* d_out_word_offsets, uint32_t* d_read_status, uint64_t* d_status,
                         void* d_scratch) {
     if (!ctx || !d_status || !d_out_word_offsets || (n_reads && (!d_offsets || !d_scratch))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
-    BN_LAUNCH(bn::launch_encode_batch(ctx->di, d_bytes, d_offsets, n_reads, d_out_words, d_out_word_offsets, d_read_status,
+    BN_LAUNCH(bn::launch_encode_batch(ctx->di, d_bytes, d_offsets, n_reads, n_bytes, d_out_words, d_out_word_offsets, d_read_status,
                                       reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
     return BN_OK;
 }
@@ -661,12 +661,12 @@ int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, 
     BN_CUDA(ensure(ctx->slot[1], (n_reads + 1) * 8));
     BN_CUDA(ensure(ctx->slot[2], max_words * 8 + 8));
     BN_CUDA(ensure(ctx->slot[3], (n_reads + 1) * 8));
-    BN_CUDA(ensure(ctx->slot[4], bn::encode_batch_scratch_bytes(n_reads)));
+    BN_CUDA(ensure(ctx->slot[4], bn::encode_batch_scratch_bytes(n_reads, hi - lo)));
     if (read_status) BN_CUDA(ensure(ctx->slot[5], n_reads * 4));
     uint8_t* d_bytes = static_cast<uint8_t*>(ctx->slot[0].p) + phase;
     if (hi > lo) BN_CUDA(cudaMemcpyAsync(d_bytes, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
     BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_encode_batch(ctx->di, d_bytes - lo, static_cast<const uint64_t*>(ctx->slot[1].p), n_reads,
+    BN_CUDA(bn::launch_encode_batch(ctx->di, d_bytes - lo, static_cast<const uint64_t*>(ctx->slot[1].p), n_reads, hi - lo,
                                     static_cast<uint64_t*>(ctx->slot[2].p), static_cast<uint64_t*>(ctx->slot[3].p),
                                     read_status ? static_cast<uint32_t*>(ctx->slot[5].p) : nullptr, ctx->d_words + 8,
                                     ctx->slot[4].p, st));

@@ -40,9 +40,9 @@ cudaError_t launch_base_counts_batch(const DeviceInfo& di, const uint64_t* d_wor
                                      double* d_gc, unsigned long long* d_totals, cudaStream_t s);
 
 // batch.cu
-size_t encode_batch_scratch_bytes(size_t n_reads);
+size_t encode_batch_scratch_bytes(size_t n_reads, size_t n_bytes);
 cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets,
-                                size_t n_reads, uint64_t* d_out_words, uint64_t* d_out_word_offsets,
+                                size_t n_reads, size_t n_bytes, uint64_t* d_out_words, uint64_t* d_out_word_offsets,
                                 uint32_t* d_read_status, unsigned long long* d_status, void* d_scratch,
                                 cudaStream_t s);
 

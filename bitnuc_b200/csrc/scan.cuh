@@ -60,10 +60,15 @@ static __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long lo
     if (threadIdx.x == 0) sums[n] = carry_s;
 }
 
-template <typename F>
+struct ScanNoHook {
+    __device__ __forceinline__ void operator()(unsigned long long, unsigned long long, unsigned long long) const {}
+};
+
+// hook(i, out[i], count(i)) is called once per item (e.g. to note which item owns a given output position)
+template <typename F, typename H>
 __global__ void __launch_bounds__(kThreads)
 scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __restrict__ sums, unsigned long long n_blocks,
-                    uint64_t* __restrict__ out) {
+                    uint64_t* __restrict__ out, H hook) {
     __shared__ unsigned long long warp_tot[32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -94,7 +99,10 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
     unsigned long long run = sums[blockIdx.x] + warp_tot[warp] + inc - s;
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
-        if (r0 + i < n) out[r0 + i] = run;
+        if (r0 + i < n) {
+            out[r0 + i] = run;
+            hook(r0 + i, run, c[i]);
+        }
         run += c[i];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[n_blocks];
@@ -104,12 +112,12 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
 static inline size_t scan_scratch_bytes(size_t n) { return (ceil_div(n ? n : 1, kScanTile) + 1) * sizeof(unsigned long long); }
 
 // out[i] = sum of count(j), j < i, for i in [0, n]; n >= 1
-template <typename F>
-static void launch_exclusive_scan(F count, size_t n, unsigned long long* sums, uint64_t* out, cudaStream_t s) {
+template <typename F, typename H = ScanNoHook>
+static void launch_exclusive_scan(F count, size_t n, unsigned long long* sums, uint64_t* out, cudaStream_t s, H hook = H()) {
     const unsigned long long n_blocks = ceil_div(n, kScanTile);
     scan_block_sums_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums);
     scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n_blocks);
-    scan_offsets_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, n_blocks, out);
+    scan_offsets_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, n_blocks, out, hook);
 }
 
 }  // namespace bn

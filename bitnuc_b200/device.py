@@ -179,9 +179,9 @@ def encode_batch(data: torch.Tensor, offsets: torch.Tensor, max_words: int | Non
     words = torch.empty(max_words, dtype=torch.int64, device=dev)
     wo = torch.empty(n + 1, dtype=torch.int64, device=dev)
     rs = torch.empty(n, dtype=torch.int32, device=dev) if read_status else None
-    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n), dtype=torch.uint8, device=dev)
+    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n, data.numel()), dtype=torch.uint8, device=dev)
     status = status or Status(dev)
-    raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, _stream(), _ptr(data), _ptr(offsets), n, _ptr(words), _ptr(wo),
+    raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, _stream(), _ptr(data), _ptr(offsets), n, data.numel(), _ptr(words), _ptr(wo),
                                           _ptr(rs), _ptr(status.word), _ptr(scratch)))
     return words, wo, rs, status
 

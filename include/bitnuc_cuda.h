@@ -174,10 +174,11 @@ int bn_base_counts_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words,
 /* Fixed-length reads (e.g. 10 M x 150 bp): read r = d_words[r*ceil(read_len/32) ..), read_len bases each.
  * Same outputs as bn_base_counts_batch_dev without the 16 bytes per read of offset/length arrays. */
 int bn_base_counts_fixed_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, size_t n_reads, size_t read_len, uint64_t *d_counts4, double *d_gc, uint64_t *d_totals);
-/* d_out_word_offsets[n_reads+1] is produced by a device scan; d_scratch needs
- * bn_encode_batch_scratch_bytes(n_reads) bytes. */
-size_t bn_encode_batch_scratch_bytes(size_t n_reads);
-int bn_encode_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const uint64_t *d_offsets, size_t n_reads, uint64_t *d_out_words, uint64_t *d_out_word_offsets, uint32_t *d_read_status, uint64_t *d_status, void *d_scratch);
+/* d_out_word_offsets[n_reads+1] is produced by a device scan.  n_bytes = the bytes the reads span
+ * (d_offsets[n_reads] - d_offsets[0], or any upper bound such as the size of the byte buffer); d_out_words
+ * needs n_bytes/32 + n_reads words and d_scratch bn_encode_batch_scratch_bytes(n_reads, n_bytes) bytes. */
+size_t bn_encode_batch_scratch_bytes(size_t n_reads, size_t n_bytes);
+int bn_encode_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const uint64_t *d_offsets, size_t n_reads, size_t n_bytes, uint64_t *d_out_words, uint64_t *d_out_word_offsets, uint32_t *d_read_status, uint64_t *d_status, void *d_scratch);
 
 /* d_status (device uint64_t) receives min(read index << 1 | kind) over failing reads (kind 0: idx > len,
  * kind 1: ebuf too short), or UINT64_MAX; failing reads produce no output words.

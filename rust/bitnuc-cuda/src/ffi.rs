@@ -61,8 +61,8 @@ extern "C" {
     pub fn bn_base_counts_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, n_bases: usize, d_counts: *mut u64, d_gc: *mut f64) -> c_int;
     pub fn bn_base_counts_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, n_words: usize, d_word_offsets: *const u64, d_lens: *const u64, n_reads: usize, d_counts4: *mut u64, d_gc: *mut f64, d_totals: *mut u64) -> c_int;
     pub fn bn_base_counts_fixed_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, n_reads: usize, read_len: usize, d_counts4: *mut u64, d_gc: *mut f64, d_totals: *mut u64) -> c_int;
-    pub fn bn_encode_batch_scratch_bytes(n_reads: usize) -> usize;
-    pub fn bn_encode_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_bytes: *const u8, d_offsets: *const u64, n_reads: usize, d_out_words: *mut u64, d_out_word_offsets: *mut u64, d_read_status: *mut u32, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
+    pub fn bn_encode_batch_scratch_bytes(n_reads: usize, n_bytes: usize) -> usize;
+    pub fn bn_encode_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_bytes: *const u8, d_offsets: *const u64, n_reads: usize, n_bytes: usize, d_out_words: *mut u64, d_out_word_offsets: *mut u64, d_read_status: *mut u32, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
     pub fn bn_split_packed_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, idx: *const u64, n_reads: usize, left: *mut u64, left_offsets: *mut u64, right: *mut u64, right_offsets: *mut u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_split_packed_scratch_bytes(n_reads: usize) -> usize;
     pub fn bn_split_packed_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, d_word_offsets: *const u64, d_lens: *const u64, d_idx: *const u64, n_reads: usize, d_left: *mut u64, d_left_offsets: *mut u64, d_right: *mut u64, d_right_offsets: *mut u64, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;

@@ -159,11 +159,11 @@ def cfg5(scale, reps):
     wo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
     rs = torch.empty(n_reads, dtype=torch.int32, device="cuda")
     ctx = dv.api.default_context(0)
-    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n_reads), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n_reads, total), dtype=torch.uint8, device="cuda")
     st = dv.Status("cuda")
 
     def run():
-        dv.raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, dv._ptr(words),
+        dv.raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, total, dv._ptr(words),
                                                  dv._ptr(wo), dv._ptr(rs), dv._ptr(st.word), dv._ptr(scratch)))
 
     ms = timed(run, max(2, reps // 2))
@@ -209,11 +209,11 @@ def short_reads(scale, reps):
     words = torch.empty(total // 32 + n_reads, dtype=torch.int64, device="cuda")
     wo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
     ctx = dv.api.default_context(0)
-    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n_reads), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(ctx.lib.bn_encode_batch_scratch_bytes(n_reads, total), dtype=torch.uint8, device="cuda")
     st = dv.Status("cuda")
 
     def run():
-        dv.raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, dv._ptr(words),
+        dv.raise_for(ctx.lib.bn_encode_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, total, dv._ptr(words),
                                                  dv._ptr(wo), None, dv._ptr(st.word), dv._ptr(scratch)))
 
     ms = timed(run, reps)

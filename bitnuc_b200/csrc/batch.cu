@@ -119,7 +119,8 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
                     unsigned long long max_tiles) {
     __shared__ uint32_t codes[kStripCodes];
     __shared__ LongSeg segs[kLongCap];
-    __shared__ unsigned n_segs;
+    __shared__ uint16_t chunks[kTileWords / 32 + kLongCap];   // (segment << 8 | chunk of 32 words), <= 64 chunks per segment
+    __shared__ unsigned n_segs, n_chunks;
     __shared__ unsigned long long tile_s, r_s[2];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long total_words = word_offsets[n_reads];
@@ -131,6 +132,7 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
         if (tid == 0) {
             tile_s = atomicAdd(tile_counter, 1ull);
             n_segs = 0;
+            n_chunks = 0;
         }
         __syncthreads();
         const unsigned long long tile = tile_s;
@@ -157,6 +159,15 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
         const uintptr_t p1 = last ? buf_hi : base + offsets[r1] + (w1 - word_offsets[r1]) * 32ull;
         const uintptr_t a0 = p0 & ~(uintptr_t)15;
         const unsigned nvec = (unsigned)((p1 - a0 + 15) >> 4);                       // <= 2 * kTileWords + 1
+        // phase 2a's first read of this thread: fetch its offsets now, so that their latency hides behind phase 1
+        unsigned long long m_wo = 0, m_rb = 0;
+        unsigned m_nw = 0, m_len = 0;
+        if (r0 + tid <= r1) {
+            m_wo = __ldg(word_offsets + r0 + tid), m_rb = __ldg(offsets + r0 + tid);
+            const unsigned long long nw = __ldg(word_offsets + r0 + tid + 1) - m_wo, len = __ldg(offsets + r0 + tid + 1) - m_rb;
+            m_nw = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)nw;   // 0xFFFFFFFF: too long to keep here, re-fetched below
+            m_len = (unsigned)len;
+        }
         // ---- phase 1: pack the span, 16 bases per thread step, into the code strip
         {
             const uint4* src = reinterpret_cast<const uint4*>(a0);
@@ -188,16 +199,24 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
         __syncthreads();
         // ---- phase 2a: one read per thread; a read's words are consecutive 64-bit windows of the strip, 32 bytes apart
         for (unsigned long long r = r0 + tid; r <= r1; r += kThreads) {
-            const unsigned long long wo_r = __ldg(word_offsets + r), wo_n = __ldg(word_offsets + r + 1);
+            unsigned long long wo_r, wo_n, rb, re;
+            if (r == r0 + tid && m_nw != 0xFFFFFFFFu) {
+                wo_r = m_wo, wo_n = m_wo + m_nw, rb = m_rb, re = m_rb + m_len;   // fetched before phase 1
+            } else {
+                wo_r = __ldg(word_offsets + r), wo_n = __ldg(word_offsets + r + 1);
+                rb = __ldg(offsets + r), re = __ldg(offsets + r + 1);
+            }
             const unsigned long long wf = wo_r > w0 ? wo_r : w0, wl = wo_n < w1 ? wo_n : w1;   // its words inside the tile
             if (wf >= wl) continue;
-            const unsigned long long rb = __ldg(offsets + r), re = __ldg(offsets + r + 1);
             unsigned rel = (unsigned)(base + rb + (wf - wo_r) * 32ull - a0);
             const unsigned cnt = (unsigned)(wl - wf);
             const unsigned tail = wl == wo_n ? (unsigned)(re - rb - (wo_n - 1 - wo_r) * 32ull) : 32u;
             if (cnt > kLongWords) {  // long: leave it to the warps, 32 words at a time
                 const unsigned slot = atomicAdd(&n_segs, 1u);
+                const unsigned nch = (cnt + 31u) / 32u;
+                const unsigned cb = atomicAdd(&n_chunks, nch);
                 segs[slot] = LongSeg{rel, (unsigned)(wf - w0), cnt, tail};
+                for (unsigned c = 0; c < nch; ++c) chunks[cb + c] = (uint16_t)(slot << 8 | c);
                 continue;
             }
             uint64_t* o = out + wf;
@@ -207,11 +226,13 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
             o[cnt - 1] = w;
         }
         __syncthreads();
-        // ---- phase 2b: long segments, chunks of 32 consecutive words per warp (coalesced 256-byte stores)
-        const unsigned ns = n_segs;
-        for (unsigned i = 0; i < ns; ++i) {
-            const LongSeg sg = segs[i];
-            for (unsigned j = warp * 32 + lane; j < sg.count; j += kThreads) {
+        // ---- phase 2b: long segments, one chunk of 32 consecutive words per warp step (coalesced 256-byte stores)
+        const unsigned nc = n_chunks;
+        for (unsigned k = warp; k < nc; k += kWarpsPerBlock) {
+            const unsigned ch = chunks[k];
+            const LongSeg sg = segs[ch >> 8];
+            const unsigned j = (ch & 0xFFu) * 32u + lane;
+            if (j < sg.count) {
                 uint64_t w = cut_word(codes, sg.rel + 32u * j);
                 if (j + 1 == sg.count && sg.tail < 32) w &= (1ull << (2 * sg.tail)) - 1ull;
                 out[w0 + sg.first + j] = w;

@@ -22,11 +22,7 @@
 
 namespace bn {
 
-constexpr int kTileWords = 2048;                   // output words per CTA tile (<= 64 KiB of bases)
-constexpr int kStripCodes = 2 * kTileWords + 8;    // one 32-bit code per aligned 16-byte vector of the span, + slack
 constexpr int kLongWords = 64;                     // a read with more words than this inside the tile is cut into chunks
-constexpr int kLongCap = kTileWords / kLongWords + 1;
-constexpr int kPackU = 4;                          // independent 128-bit loads per thread in phase 1
 
 // words taken by read r: ceil(len/32); an empty read takes none
 struct WordsOfRead {
@@ -39,10 +35,10 @@ struct WordsOfRead {
 // scan hook: read r owns words [start, start + count); note it as the owner of every tile whose first word it holds
 struct NoteTileOwners {
     unsigned long long* tile_owner;
-    unsigned long long max_tiles;
+    unsigned long long max_tiles, tile_words;
     __device__ __forceinline__ void operator()(unsigned long long r, unsigned long long start, unsigned long long count) const {
         if (count == 0) return;
-        for (unsigned long long t = ceil_div(start, kTileWords); t < max_tiles && t * kTileWords < start + count; ++t)
+        for (unsigned long long t = ceil_div(start, tile_words); t < max_tiles && t * tile_words < start + count; ++t)
             tile_owner[t] = r;
     }
 };
@@ -111,12 +107,18 @@ struct LongSeg {
     unsigned tail;   // bases in its last word (32 unless that is the read's ragged last word)
 };
 
-__global__ void __launch_bounds__(kThreads, 6)
+// kTileWords = output words per CTA tile (32 bytes of bases each), kBThreads = CTA size, kMinCtas = CTAs per SM,
+// kPackU = independent 128-bit loads per thread in phase 1
+template <int kTileWords, int kBThreads, int kMinCtas, int kPackU>
+__global__ void __launch_bounds__(kBThreads, kMinCtas)
 encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ offsets, unsigned long long n_reads,
                     const uint64_t* __restrict__ word_offsets, uint64_t* __restrict__ out,
                     uint32_t* __restrict__ read_status, unsigned long long* __restrict__ status,
                     unsigned long long* __restrict__ tile_counter, const unsigned long long* __restrict__ tile_owner,
                     unsigned long long max_tiles) {
+    constexpr int kStripCodes = 2 * kTileWords + 8;    // one 32-bit code per aligned 16-byte vector of the span, + slack
+    constexpr int kLongCap = kTileWords / kLongWords + 1;
+    constexpr int kThreads = kBThreads, kWarpsPerBlock = kBThreads / 32;
     __shared__ uint32_t codes[kStripCodes];
     __shared__ LongSeg segs[kLongCap];
     __shared__ uint16_t chunks[kTileWords / 32 + kLongCap];   // (segment << 8 | chunk of 32 words), <= 64 chunks per segment
@@ -241,13 +243,29 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
     }
 }
 
-static inline unsigned long long batch_max_tiles(size_t n_reads, size_t n_bytes) {
-    return ceil_div((unsigned long long)n_bytes / 32 + n_reads, kTileWords) + 2;
+constexpr int kMinTileWords = 2048;  // the owner table is sized for the smallest tile any variant uses
+
+static inline unsigned long long batch_max_tiles(size_t n_reads, size_t n_bytes, unsigned tile_words) {
+    return ceil_div((unsigned long long)n_bytes / 32 + n_reads, tile_words) + 2;
 }
 
 size_t encode_batch_scratch_bytes(size_t n_reads, size_t n_bytes) {
     // block sums + total, the tile counter, then the tile-owner table
-    return scan_scratch_bytes(n_reads) + sizeof(unsigned long long) * (1 + batch_max_tiles(n_reads, n_bytes));
+    return scan_scratch_bytes(n_reads) + sizeof(unsigned long long) * (1 + batch_max_tiles(n_reads, n_bytes, kMinTileWords));
+}
+
+template <int kTileWords, int kBThreads, int kMinCtas, int kPackU = 4>
+static cudaError_t launch_encode_batch_variant(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads,
+                                               size_t n_bytes, uint64_t* d_out_words, uint64_t* d_out_word_offsets, uint32_t* d_read_status,
+                                               unsigned long long* d_status, unsigned long long* sums, unsigned long long* tile_counter,
+                                               unsigned long long* tile_owner, cudaStream_t s) {
+    const unsigned long long max_tiles = batch_max_tiles(n_reads, n_bytes, kTileWords);
+    launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s, NoteTileOwners{tile_owner, max_tiles, kTileWords});
+    static const int resident = resident_blocks(encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU>, kBThreads, di);
+    // the number of output words is only known on the device: launch a full persistent grid
+    encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU><<<resident, kBThreads, 0, s>>>(
+        d_bytes, d_offsets, n_reads, d_out_word_offsets, d_out_words, d_read_status, d_status, tile_counter, tile_owner, max_tiles);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets,
@@ -264,15 +282,12 @@ cudaError_t launch_encode_batch(const DeviceInfo& di, const uint8_t* d_bytes, co
     unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
     unsigned long long* tile_counter = sums + scan_scratch_bytes(n_reads) / sizeof(unsigned long long);
     unsigned long long* tile_owner = tile_counter + 1;
-    const unsigned long long max_tiles = batch_max_tiles(n_reads, n_bytes);
     e = cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s, NoteTileOwners{tile_owner, max_tiles});
-    static const int resident = resident_blocks(encode_batch_kernel, kThreads, di);
-    // the number of output words is only known on the device: launch a full persistent grid
-    encode_batch_kernel<<<resident, kThreads, 0, s>>>(d_bytes, d_offsets, n_reads, d_out_word_offsets, d_out_words,
-                                                      d_read_status, d_status, tile_counter, tile_owner, max_tiles);
-    return cudaGetLastError();
+    // tile / CTA shape from an on-device sweep (profiles/r01_sweep_encode_batch.txt): 2048-word tiles, 128 threads
+    // (32 vectors per thread per tile), 10 CTAs per SM
+    return launch_encode_batch_variant<2048, 128, 10>(di, d_bytes, d_offsets, n_reads, n_bytes, d_out_words, d_out_word_offsets,
+                                                      d_read_status, d_status, sums, tile_counter, tile_owner, s);
 }
 
 }  // namespace bn

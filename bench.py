@@ -175,6 +175,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -261,6 +262,7 @@ def run_e2e(bn, dv, np, torch, barrier, asc, n, local, K):
                    while host thread B decodes step i (one bn_ctx per thread, as include/bitnuc_cuda.h asks for
                    concurrency), so the encode's upload and the decode's download share the full-duplex PCIe link.
     Returns (steps, serial seconds per step, pipelined seconds per step)."""
+    print(f"[bench] rank-local e2e leg: {host_threads()} host threads visible", file=sys.stderr)
     ctx_a, ctx_b = bn.Context(local), bn.Context(local)
     h_seq = ctx_a.pinned_empty(n, np.uint8)
     h_words = [ctx_a.pinned_empty(dv.words_for(n), np.uint64) for _ in range(2)]
@@ -287,6 +289,7 @@ def run_e2e(bn, dv, np, torch, barrier, asc, n, local, K):
 
     def encoder():
         try:
+            torch.cuda.set_device(local)
             for i in range(e2e_steps):
                 free[i % 2].acquire()
                 bn.encode_np(h_seq, ctx_a, out=h_words[i % 2])
@@ -298,6 +301,7 @@ def run_e2e(bn, dv, np, torch, barrier, asc, n, local, K):
 
     def decoder():
         try:
+            torch.cuda.set_device(local)
             for i in range(e2e_steps):
                 ready[i % 2].acquire()
                 bn.decode_np(h_words[i % 2], n, ctx_b, out=h_back)

@@ -4,6 +4,7 @@
 #include "../../include/bitnuc_cuda.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -45,11 +46,27 @@ struct bn_ctx {
 
 namespace {
 
+// True when the calling thread already has a CUDA context bound (it chose a device at some point).  A fresh thread
+// reports device 0 without having asked for it, and "restoring" that would create a primary context on GPU 0 --
+// hundreds of milliseconds, on a GPU that may belong to another rank.  Asked through the driver API, resolved at
+// run time so that the library has no link-time dependency on libcuda.
+bool thread_has_context() {
+    using Fn = int (*)(void**);
+    static const Fn fn = [] {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        return h ? reinterpret_cast<Fn>(dlsym(h, "cuCtxGetCurrent")) : nullptr;
+    }();
+    void* cur = nullptr;
+    return fn == nullptr || (fn(&cur) == 0 && cur != nullptr);
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
+        const bool bound = thread_has_context();
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
+        if (!bound || prev == dev) prev = -1;  // nothing to restore
     }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
@@ -155,7 +172,7 @@ int bn_ctx_create(int device, bn_ctx** out) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int s = 0; ok && s < kStages; ++s) {
         ok = cudaStreamCreateWithFlags(&ctx->stage_stream[s], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->stage_done[s], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->stage_done[s], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     }
     ok = ok && cudaMalloc(&ctx->d_words, 16 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaHostAlloc(&ctx->h_words, 16 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
@@ -487,7 +504,8 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
         BN_CUDA(cudaMemcpyAsync(out + off, ctx->stage_out[s].p, len, cudaMemcpyDeviceToHost, st));
         BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
     }
-    for (int s = 0; s < kStages; ++s) BN_CUDA(cudaStreamSynchronize(ctx->stage_stream[s]));
+    for (size_t c = n_chunks > (size_t)kStages ? n_chunks - kStages : 0; c < n_chunks; ++c)  // yield the core while waiting
+        BN_CUDA(cudaEventSynchronize(ctx->stage_done[c % kStages]));
     return set_err(err, BN_OK);
 }
 

@@ -1,7 +1,6 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/hbm_probe.py
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_s13.json 2> gpurun_out/bench_s13.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_s13.json 2>> gpurun_out/bench_s13.err
-python tools/bench_configs.py --only cfg2,cfg3,cfg4,cfg5,short > gpurun_out/configs_s13.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()"
+N=${1:-2}
+nproc; python -c "import os; print(len(os.sched_getaffinity(0)))"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+grep bench gpurun_out/bench_n$N.err
+python bench.py --steps 5 --warmup 3 --skip-cpu > gpurun_out/bench_n1b.json 2> gpurun_out/bench_n1b.err

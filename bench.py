@@ -156,10 +156,30 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Point fd 1 at stderr for the rest of the process and keep the real stdout for the one JSON line: libraries
+    (NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment) cannot interleave with it."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def run_ours(args):
+    claim_stdout()
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -175,7 +195,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -377,7 +396,7 @@ def report(args, world, rank, n, K, total_ms, enc_ms, dec_ms, e2e_ms, e2e_serial
                                                   f"{isa} path (oracle/bitnuc_oracle.c), chunked over {threads} host threads"}
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"error": str(ex)}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from bitnuc_b200 import device as dv
+from bitnuc_b200 import synth
 
 SEED = 0x5EEDB17C0DE5
 M64 = (1 << 64) - 1
@@ -143,13 +144,8 @@ def cfg4(scale, reps):
 def cfg5(scale, reps):
     """variable-length read batch (50 bp - 10 kbp, ~32 Gbases at scale 1), offset-indexed, with injected N."""
     target = int(32e9 * scale)
-    n_guess = int(target / 5025 * 1.02) + 16
-    r = np.arange(n_guess, dtype=np.uint64)
-    from oracle import oracle_np as onp  # only the counter hash of the generator (test infrastructure)
-    lens = (50 + onp.splitmix64(r + np.uint64(SEED + 5)) % np.uint64(9951)).astype(np.uint64)
-    cum = np.cumsum(lens)
-    n_reads = int(np.searchsorted(cum, target)) + 1
-    lens = lens[:n_reads]
+    lens = synth.cfg5_read_lengths(target, SEED)
+    n_reads = lens.size
     offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     total = int(offsets[-1])
     data = dv.synth_ascii(SEED, 5, 0, total)
@@ -178,11 +174,10 @@ def cfg5(scale, reps):
     nbytes = total + 8 * n_words + 16 * n_reads
     report(f"cfg5 encode_batch reads={n_reads} bases={total}", ms, nbytes, total, "bases")
     # injected N: read r gets 'N' at h2(r) % len iff h1(r) % 100003 == 0
-    h1 = onp.splitmix64(r[:n_reads] + np.uint64(0xABCDEF)) % np.uint64(100003)
-    victims = np.flatnonzero(h1 == 0)
+    victims, pos = synth.cfg5_injected_n(n_reads, lens)
     if victims.size == 0:
         victims = np.array([n_reads // 3])
-    pos = (onp.splitmix64(victims.astype(np.uint64) + np.uint64(0x123457)) % lens[victims]).astype(np.int64)
+        pos = np.array([int(lens[n_reads // 3]) // 2], dtype=np.int64)
     idx = torch.from_numpy((offsets[victims].astype(np.int64) + pos)).cuda()
     data[idx] = ord("N")
     run()
@@ -200,8 +195,7 @@ def short_reads(scale, reps):
     """encode_batch on a short-read profile (40 M x 100-151 bp, Illumina-like) and split_packed of the result
     at a barcode|UMI boundary (idx = 26) -- SURVEY.md 8(f) rank 1."""
     n_reads = int(40_000_000 * scale)
-    from oracle import oracle_np as onp  # only the counter hash of the generator (test infrastructure)
-    lens = (100 + onp.splitmix64(np.arange(n_reads, dtype=np.uint64) + np.uint64(SEED + 6)) % np.uint64(52)).astype(np.uint64)
+    lens = (100 + synth.splitmix64(np.arange(n_reads, dtype=np.uint64) + np.uint64(SEED + 6)) % np.uint64(52)).astype(np.uint64)
     offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     total = int(offsets[-1])
     data = dv.synth_ascii(SEED, 6, 0, total)

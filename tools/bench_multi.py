@@ -17,6 +17,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+_STDOUT = os.fdopen(os.dup(1), "w")  # fd 1 goes to stderr from here on (NCCL prints its version banner on stdout);
+os.dup2(2, 1)                        # the JSON line is written to the real stdout at the end
 
 import torch
 import torch.distributed as dist
@@ -38,7 +40,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -102,7 +103,7 @@ def main():
     out["base_counts"] = {"reads": n_reads, "ms": ms, "Greads_s": n_reads / ms / 1e6, "totals": t, "gc_global": sh.gc_from_counts(t),
                           "GB_s_aggregate": 80 * n_reads / ms / 1e6}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -62,6 +62,11 @@ PROTOTYPES = {
     "bn_split_packed_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _errp]),
     "bn_split_packed_scratch_bytes": (_sz, [_sz]),
     "bn_split_packed_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bn_slice_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _errp]),
+    "bn_get_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _errp]),
+    "bn_slice_batch_scratch_bytes": (_sz, [_sz]),
+    "bn_slice_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "bn_get_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),
     "bn_synth_words_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
     "bn_synth_ascii_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),

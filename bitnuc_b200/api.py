@@ -323,3 +323,49 @@ def split_packed(ebuf, slen: int, idx: int, lbuf: list, rbuf: list, ctx: Context
     rbuf.clear()
     lbuf.extend(int(x) for x in left)
     rbuf.extend(int(x) for x in right)
+
+
+# ------------------------------------------------------------------ get / slice --------------
+
+def slice_batch(words, word_offsets, lens, q_read, q_start, q_end, ctx: Context | None = None):
+    """``PackedSequence::slice`` (src/sequence.rs:198-212) over a batch of queries: query ``q`` = bases
+    ``[q_start[q], q_end[q])`` of read ``q_read[q]``.  Returns (bytes, out_offsets); raises ``InvalidRange``
+    (with ``.record``) for the first query with ``start > end`` or ``end > len``."""
+    ctx = ctx or default_context()
+    w, wo, ln = _u64(words), _u64(word_offsets), _u64(lens)
+    qr, qs, qe = _u64(q_read), _u64(q_start), _u64(q_end)
+    nq = qr.size
+    if qs.size != nq or qe.size != nq:
+        raise ValueError("q_read, q_start and q_end differ in length")
+    cap = int(np.maximum(qe.astype(np.int64) - qs.astype(np.int64), 0).sum()) if nq else 0
+    out = np.empty(max(1, cap), dtype=np.uint8)
+    oo = np.zeros(nq + 1, dtype=np.uint64)
+    err = BnError()
+    rc = ctx.lib.bn_slice_batch(ctx.handle, _p(w), w.size, _p(wo), _p(ln), ln.size, _p(qr), _p(qs), _p(qe), nq, _p(out), cap, _p(oo),
+                                C.byref(err))
+    if rc == 5:
+        e = NucleotideError.InvalidRange(err.a, err.b, err.c)
+        e.record = int(err.record)
+        raise e
+    raise_for(rc, err)
+    return out[: int(oo[nq])], oo
+
+
+def get_batch(words, word_offsets, lens, q_read, q_index, ctx: Context | None = None) -> np.ndarray:
+    """``PackedSequence::get`` (src/sequence.rs:116-135) over a batch of queries: one ASCII byte per query; raises
+    ``IndexOutOfBounds`` (with ``.record``) for the first query with ``index >= len``."""
+    ctx = ctx or default_context()
+    w, wo, ln = _u64(words), _u64(word_offsets), _u64(lens)
+    qr, qi = _u64(q_read), _u64(q_index)
+    nq = qr.size
+    if qi.size != nq:
+        raise ValueError("q_read and q_index differ in length")
+    out = np.empty(max(1, nq), dtype=np.uint8)
+    err = BnError()
+    rc = ctx.lib.bn_get_batch(ctx.handle, _p(w), w.size, _p(wo), _p(ln), ln.size, _p(qr), _p(qi), nq, _p(out), C.byref(err))
+    if rc == 4:
+        e = NucleotideError.IndexOutOfBounds(err.a, err.b)
+        e.record = int(err.record)
+        raise e
+    raise_for(rc, err)
+    return out[:nq]

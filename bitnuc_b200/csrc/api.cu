@@ -393,6 +393,28 @@ int bn_split_packed_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words
     return BN_OK;
 }
 
+size_t bn_slice_batch_scratch_bytes(size_t nq) { return bn::slice_batch_scratch_bytes(nq); }
+
+int bn_slice_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
+                       size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_start, const uint64_t* d_q_end, size_t nq, uint8_t* d_out,
+                       uint64_t* d_out_offsets, uint64_t* d_status, void* d_scratch) {
+    if (!ctx || !d_status || !d_out_offsets || (nq && (!d_q_read || !d_q_start || !d_q_end || !d_scratch || !d_word_offsets || !d_lens)))
+        return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_slice_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start, d_q_end, nq, d_out, d_out_offsets,
+                                     reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_get_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens, size_t n_reads,
+                     const uint64_t* d_q_read, const uint64_t* d_q_index, size_t nq, uint8_t* d_out, uint64_t* d_status) {
+    if (!ctx || !d_status || (nq && (!d_q_read || !d_q_index || !d_out || !d_word_offsets || !d_lens))) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_get_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_index, nq, d_out,
+                                   reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+    return BN_OK;
+}
+
 int bn_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, bn_error_t* err) {
     if (!ctx || !d_status) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
@@ -758,6 +780,99 @@ int bn_split_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, co
     BN_CUDA(cudaStreamSynchronize(st));
     if (left_offsets[n_reads]) BN_CUDA(cudaMemcpyAsync(left, ctx->slot[4].p, left_offsets[n_reads] * 8, cudaMemcpyDeviceToHost, st));
     if (right_offsets[n_reads]) BN_CUDA(cudaMemcpyAsync(right, ctx->slot[5].p, right_offsets[n_reads] * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    return set_err(err, BN_OK);
+}
+
+// get / slice: the packed batch and the query arrays are staged whole; validation happens on the host in query order
+// (the caller's loop with `?` stops at the first failing query), so the device never sees a bad query here.
+static int stage_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens,
+                              size_t n_reads, cudaStream_t st, bn_error_t* err) {
+    for (size_t r = 0; r < n_reads; ++r)
+        if (word_offsets[r] > n_words || (lens[r] + 31) / 32 > n_words - word_offsets[r]) {
+            set_err(err, BN_INVALID_LENGTH, lens[r]);
+            if (err) err->record = r;
+            return BN_INVALID_LENGTH;
+        }
+    BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
+    BN_CUDA(ensure(ctx->slot[1], n_reads ? n_reads * 8 : 8));
+    BN_CUDA(ensure(ctx->slot[2], n_reads ? n_reads * 8 : 8));
+    if (n_words) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, n_words * 8, cudaMemcpyHostToDevice, st));
+    if (n_reads) {
+        BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, n_reads * 8, cudaMemcpyHostToDevice, st));
+        BN_CUDA(cudaMemcpyAsync(ctx->slot[2].p, lens, n_reads * 8, cudaMemcpyHostToDevice, st));
+    }
+    return BN_OK;
+}
+
+int bn_slice_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens, size_t n_reads,
+                   const uint64_t* q_read, const uint64_t* q_start, const uint64_t* q_end, size_t nq, uint8_t* out, size_t out_cap,
+                   uint64_t* out_offsets, bn_error_t* err) {
+    if (!ctx || !out_offsets || (n_reads && (!word_offsets || !lens)) || (nq && (!q_read || !q_start || !q_end)))
+        return set_err(err, BN_ERR_ARGUMENT);
+    size_t total = 0;
+    for (size_t q = 0; q < nq; ++q) {
+        if (q_read[q] >= n_reads) return set_err(err, BN_ERR_ARGUMENT);
+        const uint64_t len = lens[q_read[q]];
+        if (q_start[q] > q_end[q] || q_end[q] > len) {  // sequence.rs:199-205
+            set_err(err, BN_INVALID_RANGE, q_start[q], q_end[q], len);
+            if (err) err->record = q;
+            return BN_INVALID_RANGE;
+        }
+        total += q_end[q] - q_start[q];
+    }
+    out_offsets[0] = 0;
+    if (nq == 0) return set_err(err, BN_OK);
+    if (total > out_cap || (total && !out)) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const int rc = stage_packed_batch(ctx, words, n_words, word_offsets, lens, n_reads, st, err);
+    if (rc != BN_OK) return rc;
+    BN_CUDA(ensure(ctx->slot[3], 3 * nq * 8));
+    BN_CUDA(ensure(ctx->slot[4], total + 16));
+    BN_CUDA(ensure(ctx->slot[5], (nq + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[6], bn::slice_batch_scratch_bytes(nq)));
+    uint64_t* dq = static_cast<uint64_t*>(ctx->slot[3].p);
+    BN_CUDA(cudaMemcpyAsync(dq, q_read, nq * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(dq + nq, q_start, nq * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(dq + 2 * nq, q_end, nq * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_slice_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
+                                   static_cast<const uint64_t*>(ctx->slot[2].p), n_reads, dq, dq + nq, dq + 2 * nq, nq,
+                                   static_cast<uint8_t*>(ctx->slot[4].p), static_cast<uint64_t*>(ctx->slot[5].p), ctx->d_words + 8,
+                                   ctx->slot[6].p, st));
+    BN_CUDA(cudaMemcpyAsync(out_offsets, ctx->slot[5].p, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total) BN_CUDA(cudaMemcpyAsync(out, ctx->slot[4].p, total, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    return set_err(err, BN_OK);
+}
+
+int bn_get_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens, size_t n_reads,
+                 const uint64_t* q_read, const uint64_t* q_index, size_t nq, uint8_t* out, bn_error_t* err) {
+    if (!ctx || (n_reads && (!word_offsets || !lens)) || (nq && (!q_read || !q_index || !out))) return set_err(err, BN_ERR_ARGUMENT);
+    for (size_t q = 0; q < nq; ++q) {
+        if (q_read[q] >= n_reads) return set_err(err, BN_ERR_ARGUMENT);
+        if (q_index[q] >= lens[q_read[q]]) {  // sequence.rs:117-122
+            set_err(err, BN_INDEX_OUT_OF_BOUNDS, q_index[q], lens[q_read[q]]);
+            if (err) err->record = q;
+            return BN_INDEX_OUT_OF_BOUNDS;
+        }
+    }
+    if (nq == 0) return set_err(err, BN_OK);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const int rc = stage_packed_batch(ctx, words, n_words, word_offsets, lens, n_reads, st, err);
+    if (rc != BN_OK) return rc;
+    BN_CUDA(ensure(ctx->slot[3], 2 * nq * 8));
+    BN_CUDA(ensure(ctx->slot[4], nq));
+    uint64_t* dq = static_cast<uint64_t*>(ctx->slot[3].p);
+    BN_CUDA(cudaMemcpyAsync(dq, q_read, nq * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(dq + nq, q_index, nq * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_get_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
+                                 static_cast<const uint64_t*>(ctx->slot[2].p), n_reads, dq, dq + nq, nq, static_cast<uint8_t*>(ctx->slot[4].p),
+                                 ctx->d_words + 8, st));
+    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[4].p, nq, cudaMemcpyDeviceToHost, st));
     BN_CUDA(cudaStreamSynchronize(st));
     return set_err(err, BN_OK);
 }

@@ -53,6 +53,15 @@ cudaError_t launch_split_packed_batch(const DeviceInfo& di, const uint64_t* d_wo
                                       uint64_t* d_left_offsets, uint64_t* d_right, uint64_t* d_right_offsets,
                                       unsigned long long* d_status, void* d_scratch, cudaStream_t s);
 
+// gather.cu
+size_t slice_batch_scratch_bytes(size_t nq);
+cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
+                               size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_start, const uint64_t* d_q_end, size_t nq,
+                               uint8_t* d_out, uint64_t* d_out_offsets, unsigned long long* d_status, void* d_scratch, cudaStream_t s);
+cudaError_t launch_get_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
+                             size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_index, size_t nq, uint8_t* d_out,
+                             unsigned long long* d_status, cudaStream_t s);
+
 // synth.cu
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,
                                size_t n_words, uint64_t* d_out, cudaStream_t s);

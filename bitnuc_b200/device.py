@@ -227,6 +227,43 @@ def split_packed_batch(words: torch.Tensor, word_offsets: torch.Tensor, lens: to
     return left, lo, right, ro, status
 
 
+class QueryStatus:
+    """Device-side status of ``slice_batch`` / ``get_batch``: the smallest failing query index."""
+
+    def __init__(self, device):
+        self.word = torch.empty(1, dtype=torch.int64, device=device)
+
+    def first_failing(self):
+        """Synchronises (reads the word back): index of the first failing query, or None."""
+        q = int(self.word.item()) & api.M64
+        return None if q == api.M64 else q
+
+
+def slice_batch(words, word_offsets, lens, q_read, q_start, q_end, out_bytes: int, status: QueryStatus | None = None):
+    """Batched ``PackedSequence::slice`` on the device: (bytes uint8[out_bytes], out_offsets int64[nq+1], status).
+    ``out_bytes`` must cover the sum of the valid range lengths (failing queries take no room)."""
+    ctx = _ctx_for(lens)
+    nq, dev = q_read.numel(), lens.device
+    out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+    oo = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(ctx.lib.bn_slice_batch_scratch_bytes(nq), dtype=torch.uint8, device=dev)
+    status = status or QueryStatus(dev)
+    raise_for(ctx.lib.bn_slice_batch_dev(ctx.handle, _stream(), _ptr(words), _ptr(word_offsets), _ptr(lens), lens.numel(), _ptr(q_read),
+                                         _ptr(q_start), _ptr(q_end), nq, _ptr(out), _ptr(oo), _ptr(status.word), _ptr(scratch)))
+    return out, oo, status
+
+
+def get_batch(words, word_offsets, lens, q_read, q_index, status: QueryStatus | None = None):
+    """Batched ``PackedSequence::get`` on the device: (bytes uint8[nq], status)."""
+    ctx = _ctx_for(lens)
+    nq, dev = q_read.numel(), lens.device
+    out = torch.empty(nq, dtype=torch.uint8, device=dev)
+    status = status or QueryStatus(dev)
+    raise_for(ctx.lib.bn_get_batch_dev(ctx.handle, _stream(), _ptr(words), _ptr(word_offsets), _ptr(lens), lens.numel(), _ptr(q_read),
+                                       _ptr(q_index), nq, _ptr(out), _ptr(status.word)))
+    return out, status
+
+
 def synth_words(seed: int, stream_id: int, first_word: int, n_words: int, device="cuda") -> torch.Tensor:
     ctx = api.default_context(torch.device(device).index or 0)
     out = torch.empty(n_words, dtype=torch.int64, device=device)

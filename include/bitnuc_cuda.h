@@ -153,6 +153,17 @@ int bn_encode_batch(bn_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, 
  * ebuf shorter than ceil(len/32) words (the reference panics or truncates) -> BN_INVALID_LENGTH(len). */
 int bn_split_packed_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, const uint64_t *idx, size_t n_reads, uint64_t *left, uint64_t *left_offsets, uint64_t *right, uint64_t *right_offsets, bn_error_t *err);
 
+/* PackedSequence::slice over a batch of queries (src/sequence.rs:198-212): query q = bases [q_start[q], q_end[q]) of
+ * read q_read[q] (lens[r] bases at words[word_offsets[r]]).  out receives the upper-case ASCII of all queries back to
+ * back (out_cap bytes available), out_offsets[nq+1] the exclusive prefix sums of the range lengths.
+ * start > end || end > len -> BN_INVALID_RANGE{start, end, len} for the first such query (err->record);
+ * q_read[q] >= n_reads or out_cap too small -> BN_ERR_ARGUMENT. */
+int bn_slice_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, size_t n_reads, const uint64_t *q_read, const uint64_t *q_start, const uint64_t *q_end, size_t nq, uint8_t *out, size_t out_cap, uint64_t *out_offsets, bn_error_t *err);
+
+/* PackedSequence::get over a batch of queries (src/sequence.rs:116-135): out[q] = base q_index[q] of read q_read[q].
+ * index >= len -> BN_INDEX_OUT_OF_BOUNDS{index, len} for the first such query (err->record). */
+int bn_get_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, size_t n_reads, const uint64_t *q_read, const uint64_t *q_index, size_t nq, uint8_t *out, bn_error_t *err);
+
 /* ------------------------------------------------------------------ device-pointer calls ---- */
 /* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.
  * Pointers are device pointers.  ASCII buffers and packed buffers must be 16-byte aligned.
@@ -185,6 +196,13 @@ int bn_encode_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const
  * d_scratch needs bn_split_packed_scratch_bytes(n_reads) bytes. */
 size_t bn_split_packed_scratch_bytes(size_t n_reads);
 int bn_split_packed_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, const uint64_t *d_idx, size_t n_reads, uint64_t *d_left, uint64_t *d_left_offsets, uint64_t *d_right, uint64_t *d_right_offsets, uint64_t *d_status, void *d_scratch);
+
+/* d_status (device uint64_t) receives the smallest failing query index, or UINT64_MAX; failing queries produce no
+ * bytes (slice) / a 0 byte (get).  d_out needs the sum of the valid range lengths; d_scratch needs
+ * bn_slice_batch_scratch_bytes(nq) bytes. */
+size_t bn_slice_batch_scratch_bytes(size_t nq);
+int bn_slice_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, const uint64_t *d_q_read, const uint64_t *d_q_start, const uint64_t *d_q_end, size_t nq, uint8_t *d_out, uint64_t *d_out_offsets, uint64_t *d_status, void *d_scratch);
+int bn_get_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, const uint64_t *d_q_read, const uint64_t *d_q_index, size_t nq, uint8_t *d_out, uint64_t *d_status);
 
 /* Synchronises `stream`, reads *d_status back and translates it: BN_OK, or BN_INVALID_BASE with
  * err->base / err->offset filled (record/a are filled by the host-pointer wrappers). */

@@ -66,6 +66,11 @@ extern "C" {
     pub fn bn_split_packed_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, idx: *const u64, n_reads: usize, left: *mut u64, left_offsets: *mut u64, right: *mut u64, right_offsets: *mut u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_split_packed_scratch_bytes(n_reads: usize) -> usize;
     pub fn bn_split_packed_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, d_word_offsets: *const u64, d_lens: *const u64, d_idx: *const u64, n_reads: usize, d_left: *mut u64, d_left_offsets: *mut u64, d_right: *mut u64, d_right_offsets: *mut u64, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
+    pub fn bn_slice_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, n_reads: usize, q_read: *const u64, q_start: *const u64, q_end: *const u64, nq: usize, out: *mut u8, out_cap: usize, out_offsets: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_get_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, n_reads: usize, q_read: *const u64, q_index: *const u64, nq: usize, out: *mut u8, err: *mut bn_error_t) -> c_int;
+    pub fn bn_slice_batch_scratch_bytes(nq: usize) -> usize;
+    pub fn bn_slice_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, d_word_offsets: *const u64, d_lens: *const u64, n_reads: usize, d_q_read: *const u64, d_q_start: *const u64, d_q_end: *const u64, nq: usize, d_out: *mut u8, d_out_offsets: *mut u64, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
+    pub fn bn_get_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, d_word_offsets: *const u64, d_lens: *const u64, n_reads: usize, d_q_read: *const u64, d_q_index: *const u64, nq: usize, d_out: *mut u8, d_status: *mut u64) -> c_int;
     pub fn bn_status_fetch(ctx: *mut bn_ctx, stream: *mut c_void, d_status: *const u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_synth_words_dev(ctx: *mut bn_ctx, stream: *mut c_void, seed: u64, stream_id: u64, first_word: u64, n_words: usize, d_out: *mut u64) -> c_int;
     pub fn bn_synth_ascii_dev(ctx: *mut bn_ctx, stream: *mut c_void, seed: u64, stream_id: u64, first_base: u64, n: usize, d_out: *mut u8) -> c_int;

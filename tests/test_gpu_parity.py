@@ -593,3 +593,76 @@ def test_split_packed_empty_batch_and_short_buffer(bn):
     # a non-empty ebuf that cannot hold slen bases: the reference panics or truncates; rejected here
     err = gpu_error(bn, bn.split_packed, [0x1B], 100, 40, [], [])
     assert err.key() == ("InvalidLength", 100)
+
+
+# ------------------------------------------------------------------ get / slice gathers ----
+
+def _packed_batch(rng, lens):
+    seqs = [rand_seq(rng, int(n)).tobytes() for n in lens]
+    words, wo = [], []
+    for s in seqs:
+        wo.append(len(words))
+        words.extend(oracle.PackedSequence(s).data)
+    return seqs, np.array(words, dtype=np.uint64), np.array(wo, dtype=np.uint64), np.asarray(lens, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("profile", ["windows", "whole_and_empty", "long"])
+def test_slice_and_get_batches_match_oracle(bn, profile):
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(77)
+    lens = {"windows": rng.integers(1, 400, 300), "whole_and_empty": rng.integers(0, 100, 200), "long": rng.integers(5000, 20000, 12)}[profile]
+    seqs, words, wo, ln = _packed_batch(rng, lens)
+    nq = 2000
+    qr = rng.integers(0, len(seqs), nq)
+    a, b = (rng.random(nq) * (lens[qr] + 1)).astype(np.int64), (rng.random(nq) * (lens[qr] + 1)).astype(np.int64)
+    qs, qe = np.minimum(a, b), np.maximum(a, b)
+    if profile == "whole_and_empty":
+        qs[::3], qe[::3] = 0, lens[qr[::3]]      # to_vec
+        qe[1::3] = qs[1::3]                       # empty ranges
+    exp = [seqs[r][s:e] for r, s, e in zip(qr, qs, qe)]
+    data, oo = bn.slice_batch(words, wo, ln, qr, qs, qe)
+    assert np.array_equal(oo, np.concatenate([[0], np.cumsum([len(x) for x in exp])]).astype(np.uint64))
+    assert data.tobytes() == b"".join(exp)
+    for q in range(0, nq, 97):  # the reference's own slice on the same PackedSequence
+        assert oracle.PackedSequence(seqs[qr[q]]).slice(int(qs[q]), int(qe[q])) == exp[q]
+    # device-resident form, arbitrary output alignment comes from the prefix sums
+    t = [torch.from_numpy(np.ascontiguousarray(x).astype(np.uint64).view(np.int64)).cuda() for x in (words, wo, ln, qr, qs, qe)]
+    d_out, d_oo, st = dv.slice_batch(*t, out_bytes=int(oo[-1]))
+    assert st.first_failing() is None
+    assert d_out.cpu().numpy().tobytes() == b"".join(exp) and np.array_equal(d_oo.cpu().numpy().view(np.uint64), oo)
+    # get
+    nz = np.flatnonzero(lens[qr] > 0)
+    gi = (rng.random(nz.size) * lens[qr[nz]]).astype(np.int64)
+    got = bn.get_batch(words, wo, ln, qr[nz], gi)
+    assert got.tobytes() == bytes(seqs[r][i] for r, i in zip(qr[nz], gi))
+    assert all(oracle.PackedSequence(seqs[qr[nz][k]]).get(int(gi[k])) == got[k] for k in range(0, nz.size, 131))
+    d_get, st = dv.get_batch(t[0], t[1], t[2], t[3][torch.from_numpy(nz).cuda()], torch.from_numpy(gi).cuda())
+    assert st.first_failing() is None and np.array_equal(d_get.cpu().numpy(), got)
+    # errors: the first failing query in index order, with the reference's payloads
+    bad_s, bad_e = qs.copy(), qe.copy()
+    q1, q2 = nq // 3, nq // 2
+    bad_e[q1] = lens[qr[q1]] + 3                      # end > len
+    bad_s[q2], bad_e[q2] = 5, 2                       # start > end
+    err = gpu_error(bn, bn.slice_batch, words, wo, ln, qr, bad_s, bad_e)
+    assert err.key() == ("InvalidRange", int(bad_s[q1]), int(bad_e[q1]), int(lens[qr[q1]])) and err.record == q1
+    with pytest.raises(OracleError) as ei:
+        oracle.PackedSequence(seqs[qr[q1]]).slice(int(bad_s[q1]), int(bad_e[q1]))
+    assert ei.value.key() == err.key()
+    *_, st = dv.slice_batch(t[0], t[1], t[2], t[3], torch.from_numpy(bad_s).cuda(), torch.from_numpy(bad_e).cuda(), out_bytes=int(oo[-1]) + 64)
+    assert st.first_failing() == q1
+    bad_i = gi.copy()
+    bad_i[7] = lens[qr[nz[7]]]
+    err = gpu_error(bn, bn.get_batch, words, wo, ln, qr[nz], bad_i)
+    assert err.key() == ("IndexOutOfBounds", int(bad_i[7]), int(lens[qr[nz[7]]])) and err.record == 7
+
+
+def test_slice_kats(bn, kats):
+    """PackedSequence doctests / tests of the reference (src/sequence.rs) through the batched gathers."""
+    ps = oracle.PackedSequence(b"ACGTACGT")
+    w, wo, ln = np.array(ps.data, dtype=np.uint64), np.array([0], dtype=np.uint64), np.array([8], dtype=np.uint64)
+    data, _ = bn.slice_batch(w, wo, ln, [0, 0, 0], [1, 0, 8], [4, 8, 8])
+    assert data.tobytes() == b"CGT" + b"ACGTACGT"
+    assert bn.get_batch(w, wo, ln, [0, 0], [0, 3]).tobytes() == b"AT"
+    assert gpu_error(bn, bn.slice_batch, w, wo, ln, [0], [2], [9]).key() == ("InvalidRange", 2, 9, 8)
+    assert gpu_error(bn, bn.get_batch, w, wo, ln, [0], [8]).key() == ("IndexOutOfBounds", 8, 8)

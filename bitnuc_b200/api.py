@@ -369,3 +369,24 @@ def get_batch(words, word_offsets, lens, q_read, q_index, ctx: Context | None = 
         raise e
     raise_for(rc, err)
     return out[:nq]
+
+
+# ------------------------------------------------------------------ k-mer windows ------------
+
+def kmers(seq, k: int, ctx: Context | None = None) -> np.ndarray:
+    """``[as_2bit(w)? for w in seq.windows(k)]`` (README.md:160-180): one packed word per window.  Raises the error
+    of the first failing window (``.record`` = its index, ``.offset`` = the offending byte, ``.partial`` = the words of
+    the windows before it)."""
+    ctx = ctx or default_context()
+    a = _u8(seq)
+    if k <= 0:
+        raise ValueError("window size must be non-zero (slice::windows panics)")
+    out = np.empty(max(1, a.size - k + 1), dtype=np.uint64)
+    n_out, err = C.c_size_t(0), BnError()
+    rc = ctx.lib.bn_kmers(ctx.handle, _p(a), a.size, k, _p(out), C.byref(n_out), C.byref(err))
+    if rc == 1:
+        e = NucleotideError.InvalidBase(err.base)
+        e.record, e.offset, e.partial = int(err.record), int(err.offset), out[: n_out.value]
+        raise e
+    raise_for(rc, err)
+    return out[: n_out.value]

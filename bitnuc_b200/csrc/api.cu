@@ -393,6 +393,15 @@ int bn_split_packed_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words
     return BN_OK;
 }
 
+int bn_kmers_dev(bn_ctx* ctx, void* stream, const uint8_t* d_seq, size_t n, uint32_t k, uint64_t* d_out, uint64_t* d_status) {
+    if (!ctx || !d_status || k == 0) return BN_ERR_ARGUMENT;
+    if (n >= k && k > 32) return BN_SEQUENCE_TOO_LONG;
+    if (n >= k && (!d_seq || !d_out)) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_kmer_windows(ctx->di, d_seq, n, k, d_out, reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+    return BN_OK;
+}
+
 size_t bn_slice_batch_scratch_bytes(size_t nq) { return bn::slice_batch_scratch_bytes(nq); }
 
 int bn_slice_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
@@ -874,6 +883,38 @@ int bn_get_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint6
                                  ctx->d_words + 8, st));
     BN_CUDA(cudaMemcpyAsync(out, ctx->slot[4].p, nq, cudaMemcpyDeviceToHost, st));
     BN_CUDA(cudaStreamSynchronize(st));
+    return set_err(err, BN_OK);
+}
+
+int bn_kmers(bn_ctx* ctx, const uint8_t* seq, size_t n, uint32_t k, uint64_t* out, size_t* n_out, bn_error_t* err) {
+    if (n_out) *n_out = 0;
+    if (!ctx || k == 0) return set_err(err, BN_ERR_ARGUMENT);
+    if (n < k) return set_err(err, BN_OK);                         // windows(k) yields nothing
+    if (k > 32) return set_err(err, BN_SEQUENCE_TOO_LONG, k);      // the first window already fails (naive.rs:5-7)
+    if (!seq || !out) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const size_t n_win = n - k + 1;
+    BN_CUDA(ensure(ctx->slot[0], n));
+    BN_CUDA(ensure(ctx->slot[1], n_win * 8));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, seq, n, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_kmer_windows(ctx->di, static_cast<const uint8_t*>(ctx->slot[0].p), n, k, static_cast<uint64_t*>(ctx->slot[1].p),
+                                    ctx->d_words + 8, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long key = ctx->h_words[8];
+    if (key != kNoError) {  // windows before the failing one were produced by the caller's loop: hand them over
+        const size_t off = (size_t)(key >> 8), first_bad = off >= k - 1 ? off - (k - 1) : 0;
+        if (first_bad) BN_CUDA(cudaMemcpy(out, ctx->slot[1].p, first_bad * 8, cudaMemcpyDeviceToHost));
+        if (n_out) *n_out = first_bad;
+        invalid_base(err, key, 0);
+        if (err) err->record = first_bad;
+        return BN_INVALID_BASE;
+    }
+    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[1].p, n_win * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    if (n_out) *n_out = n_win;
     return set_err(err, BN_OK);
 }
 

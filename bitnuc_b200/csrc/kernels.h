@@ -62,6 +62,10 @@ cudaError_t launch_get_batch(const DeviceInfo& di, const uint64_t* d_words, cons
                              size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_index, size_t nq, uint8_t* d_out,
                              unsigned long long* d_status, cudaStream_t s);
 
+// windows.cu
+cudaError_t launch_kmer_windows(const DeviceInfo& di, const uint8_t* d_seq, size_t n, uint32_t k, uint64_t* d_out,
+                                unsigned long long* d_status, cudaStream_t s);
+
 // synth.cu
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,
                                size_t n_words, uint64_t* d_out, cudaStream_t s);

@@ -227,6 +227,20 @@ def split_packed_batch(words: torch.Tensor, word_offsets: torch.Tensor, lens: to
     return left, lo, right, ro, status
 
 
+def kmers(seq: torch.Tensor, k: int, out: torch.Tensor | None = None, status: Status | None = None):
+    """Every k-mer of an ASCII sequence: (int64[n-k+1], status); window i = ``as_2bit(seq[i:i+k])``."""
+    ctx = _ctx_for(seq)
+    n = seq.numel()
+    if out is None:
+        out = torch.empty(max(0, n - k + 1), dtype=torch.int64, device=seq.device)
+    status = status or Status(seq.device)
+    rc = ctx.lib.bn_kmers_dev(ctx.handle, _stream(), _ptr(seq), n, k, _ptr(out), _ptr(status.word))
+    if rc == 2:
+        raise _lib.NucleotideError.SequenceTooLong(k)
+    raise_for(rc)
+    return out, status
+
+
 class QueryStatus:
     """Device-side status of ``slice_batch`` / ``get_batch``: the smallest failing query index."""
 

@@ -153,6 +153,13 @@ int bn_encode_batch(bn_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, 
  * ebuf shorter than ceil(len/32) words (the reference panics or truncates) -> BN_INVALID_LENGTH(len). */
 int bn_split_packed_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, const uint64_t *idx, size_t n_reads, uint64_t *left, uint64_t *left_offsets, uint64_t *right, uint64_t *right_offsets, bn_error_t *err);
 
+/* Every k-mer of a sequence: `for w in seq.windows(k) { as_2bit(w)? }` (README.md:160-180 -> src/utils/packing/mod.rs:81-110).
+ * out[i] = as_2bit(seq[i .. i+k]) for i in [0, n-k]; *n_out = n - k + 1 (0 when n < k: no window exists and nothing is
+ * looked at).  k > 32 (and n >= k) -> BN_SEQUENCE_TOO_LONG(k); the first window holding an invalid byte ->
+ * BN_INVALID_BASE (err->offset = the byte's offset, err->record = the window, max(0, offset - k + 1)); k == 0
+ * (slice::windows panics) -> BN_ERR_ARGUMENT. */
+int bn_kmers(bn_ctx *ctx, const uint8_t *seq, size_t n, uint32_t k, uint64_t *out, size_t *n_out, bn_error_t *err);
+
 /* PackedSequence::slice over a batch of queries (src/sequence.rs:198-212): query q = bases [q_start[q], q_end[q]) of
  * read q_read[q] (lens[r] bases at words[word_offsets[r]]).  out receives the upper-case ASCII of all queries back to
  * back (out_cap bytes available), out_offsets[nq+1] the exclusive prefix sums of the range lengths.
@@ -203,6 +210,9 @@ int bn_split_packed_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words
 size_t bn_slice_batch_scratch_bytes(size_t nq);
 int bn_slice_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, const uint64_t *d_q_read, const uint64_t *d_q_start, const uint64_t *d_q_end, size_t nq, uint8_t *d_out, uint64_t *d_out_offsets, uint64_t *d_status, void *d_scratch);
 int bn_get_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, const uint64_t *d_q_read, const uint64_t *d_q_index, size_t nq, uint8_t *d_out, uint64_t *d_status);
+
+/* d_out needs n - k + 1 words; any alignment of d_seq. */
+int bn_kmers_dev(bn_ctx *ctx, void *stream, const uint8_t *d_seq, size_t n, uint32_t k, uint64_t *d_out, uint64_t *d_status);
 
 /* Synchronises `stream`, reads *d_status back and translates it: BN_OK, or BN_INVALID_BASE with
  * err->base / err->offset filled (record/a are filled by the host-pointer wrappers). */

@@ -666,3 +666,49 @@ def test_slice_kats(bn, kats):
     assert bn.get_batch(w, wo, ln, [0, 0], [0, 3]).tobytes() == b"AT"
     assert gpu_error(bn, bn.slice_batch, w, wo, ln, [0], [2], [9]).key() == ("InvalidRange", 2, 9, 8)
     assert gpu_error(bn, bn.get_batch, w, wo, ln, [0], [8]).key() == ("IndexOutOfBounds", 8, 8)
+
+
+# ------------------------------------------------------------------ k-mer windows ----
+
+@pytest.mark.parametrize("k", [1, 4, 15, 16, 17, 21, 31, 32])
+def test_kmer_windows_match_oracle(bn, k):
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(k)
+    for n in [k, k + 1, 100, 2047 + k, 2048 + k, 5000, 70001]:
+        seq = rand_seq(rng, n, mixed=True)
+        got = bn.kmers(seq, k)
+        assert got.size == n - k + 1
+        idx = sorted({0, min(1, n - k), n - k, (n - k) // 2, *rng.integers(0, n - k + 1, 40).tolist()})
+        assert [int(got[i]) for i in idx] == [oracle.as_2bit(seq[i : i + k]) for i in idx]   # the caller's loop
+        enc = oracle.encode_np(seq)                                                        # and all of them, via the packed stream
+        j = np.arange(n - k + 1, dtype=np.uint64)
+        lo = enc[(j >> np.uint64(5)).astype(np.int64)] >> (np.uint64(2) * (j & np.uint64(31)))
+        nxt = np.concatenate([enc[1:], [np.uint64(0)]])[(j >> np.uint64(5)).astype(np.int64)]
+        sh = np.uint64(64) - np.uint64(2) * (j & np.uint64(31))
+        hi = np.where(sh == np.uint64(64), np.uint64(0), nxt << (sh & np.uint64(63)))
+        mask = np.uint64((1 << (2 * k)) - 1)
+        assert np.array_equal(got, (lo | hi) & mask)
+        for shift in (0, 3):  # device-resident, any alignment
+            t = torch.from_numpy(np.concatenate([np.zeros(shift, np.uint8), seq])).cuda()[shift:]
+            d, st = dv.kmers(t, k)
+            st.check()
+            assert np.array_equal(d.cpu().numpy().view(np.uint64), got)
+
+
+def test_kmer_windows_errors(bn):
+    assert bn.kmers(b"ACG", 4).size == 0                       # no window: nothing is looked at, not even ...
+    assert bn.kmers(b"NNN", 4).size == 0                       # ... invalid bytes
+    assert gpu_error(bn, bn.kmers, b"A" * 40, 33).key() == ("SequenceTooLong", 33)
+    assert bn.kmers(b"A" * 10, 33).size == 0
+    seq = bytearray(b"ACGT" * 1000)
+    seq[2500] = ord("N")
+    seq[3000] = ord("x")
+    err = gpu_error(bn, bn.kmers, bytes(seq), 21)
+    assert err.key() == ("InvalidBase", ord("N")) and err.offset == 2500 and err.record == 2480
+    assert [int(x) for x in err.partial] == [oracle.as_2bit(bytes(seq[i : i + 21])) for i in range(2480)]
+    with pytest.raises(OracleError) as ei:                      # the caller's loop stops in window 2480 with the same error
+        [oracle.as_2bit(bytes(seq[i : i + 21])) for i in range(2480, 2482)]
+    assert ei.value.key() == err.key()
+    readme = bn.kmers(b"ACGTACGT", 4)                          # README.md:170-180: "ACGT" occurs twice
+    assert int((readme == np.uint64(bn.as_2bit(b"ACGT"))).sum()) == 2

@@ -28,13 +28,20 @@ struct SliceLen {
     }
 };
 
-// 8 bits = 4 bases starting at base b of the read whose words start at w
-__device__ __forceinline__ uint32_t packed_byte_at(const uint64_t* __restrict__ w, unsigned long long b) {
-    const unsigned long long wi = b >> 5;
-    const unsigned sh = 2u * (unsigned)(b & 31u);
-    uint64_t x = __ldg(w + wi) >> sh;
-    if (sh > 56) x |= __ldg(w + wi + 1) << (64 - sh);  // only reached when all 4 bases exist, so word wi+1 does too
-    return (uint32_t)x & 0xFFu;
+// ASCII of the 4 bases starting at base b of the read whose words (viewed as 32-bit halves) start at w32:
+// a funnel shift of two halves, the low byte spread to one code per nibble, PRMT as a 4-entry LUT.
+__device__ __forceinline__ uint32_t ascii4_at(const uint32_t* __restrict__ w32, unsigned long long b) {
+    const unsigned long long i = b >> 4;
+    const unsigned sh = 2u * (unsigned)(b & 15u);
+    const uint32_t lo = __ldg(w32 + i);
+    const uint32_t hi = sh > 24 ? __ldg(w32 + i + 1) : 0u;  // only reached when all 4 bases exist, so that half does too
+    uint32_t t = __funnelshift_r(lo, hi, sh) & 0xFFu;
+    t = (t | (t << 4)) & 0x0F0Fu;
+    t = (t | (t << 2)) & 0x3333u;
+    return __byte_perm(0x54474341u, 0u, t);
+}
+__device__ __forceinline__ uint8_t ascii1_at(const uint32_t* __restrict__ w32, unsigned long long b) {
+    return (uint8_t)(0x54474341u >> (8u * ((__ldg(w32 + (b >> 4)) >> (2u * (unsigned)(b & 15u))) & 3u)));
 }
 
 constexpr int kSliceLanes = 8;
@@ -52,23 +59,20 @@ slice_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
         if (sub == 0 && q < ld_volatile_u64(status)) atomicMin(status, q);
         return;
     }
-    const uint64_t* w = words + word_offsets[r];
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(words + word_offsets[r]);
     uint8_t* o = out + out_offsets[q];
     const unsigned long long n = e - s;
     // head: bytes up to the first 4-byte aligned output address
-    const unsigned long long head = min((unsigned long long)((4u - (unsigned)(reinterpret_cast<uintptr_t>(o) & 3u)) & 3u), n);
-    if (sub < head) o[sub] = (uint8_t)(0x54474341u >> (8 * ((__ldg(w + ((s + sub) >> 5)) >> (2 * ((s + sub) & 31))) & 3)));
+    const unsigned head = (unsigned)min((unsigned long long)((4u - (unsigned)(reinterpret_cast<uintptr_t>(o) & 3u)) & 3u), n);
+    if (sub < head) o[sub] = ascii1_at(w32, s + sub);
     // body: one aligned 32-bit store of 4 bases per lane step
     const unsigned long long body = (n - head) / 4;
     uint32_t* o32 = reinterpret_cast<uint32_t*>(o + head);
-    for (unsigned long long i = sub; i < body; i += kSliceLanes)
-        o32[i] = ascii4_of_byte(packed_byte_at(w, s + head + 4 * i));
+    const unsigned long long b0 = s + head;
+    for (unsigned long long i = sub; i < body; i += kSliceLanes) o32[i] = ascii4_at(w32, b0 + 4 * i);
     // tail: the last (< 4) bytes
     const unsigned long long done = head + 4 * body;
-    if (done + sub < n) {
-        const unsigned long long b = s + done + sub;
-        o[done + sub] = (uint8_t)(0x54474341u >> (8 * ((__ldg(w + (b >> 5)) >> (2 * (b & 31))) & 3)));
-    }
+    if (done + sub < n) o[done + sub] = ascii1_at(w32, s + done + sub);
 }
 
 __global__ void __launch_bounds__(kThreads)

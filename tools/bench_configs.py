@@ -246,6 +246,51 @@ def short_reads(scale, reps):
     report(f"split_packed idx=26 reads={n_reads}", ms, 8 * n_words + 24 * n_reads + 8 * n_reads + 8 * n_words + 16 * n_reads, n_reads, "reads")
 
 
+def next_rows(scale, reps):
+    """every 31-mer of one sequence (seq.windows(31) -> as_2bit), and slice gathers
+    (10 M windows of 50 bases out of 10 M x 150 bp packed reads)."""
+    n = int(500_000_000 * scale)
+    asc = dv.synth_ascii(SEED, 7, 0, n)
+    out = torch.empty(n - 30, dtype=torch.int64, device="cuda")
+    st = dv.Status("cuda")
+    ms = timed(lambda: dv.kmers(asc, 31, out=out, status=st), reps)
+    st.check()
+    words = dv.synth_words(SEED, 7, 0, dv.words_for(n))
+    pos = torch.tensor([0, 1, 31, 32, 33, 12345, n - 31], device="cuda")
+    for p_ in pos.tolist():  # window p = bits [2p, 2p+62) of the packed stream
+        lo = (int(words[p_ // 32].item()) & M64) >> (2 * (p_ % 32))
+        hi = ((int(words[p_ // 32 + 1].item()) & M64) << (64 - 2 * (p_ % 32))) & M64 if p_ % 32 and p_ // 32 + 1 < words.numel() else 0
+        assert (int(out[p_].item()) & M64) == ((lo | hi) & ((1 << 62) - 1)), p_
+    report(f"kmers (all 31-mers of one sequence) n={n}", ms, n + 8 * (n - 30), n - 30, "kmers")
+    del asc, out, words
+
+    reads = int(10_000_000 * scale)
+    words = dv.synth_words(SEED, 4, 0, 5 * reads)
+    wo = torch.arange(reads, dtype=torch.int64, device="cuda") * 5
+    lens = torch.full((reads,), 150, dtype=torch.int64, device="cuda")
+    qr = torch.arange(reads, dtype=torch.int64, device="cuda")
+    qs = (qr * 7919) % 101
+    qe = qs + 50
+    ctx = dv.api.default_context(0)
+    data = torch.empty(50 * reads, dtype=torch.uint8, device="cuda")
+    oo = torch.empty(reads + 1, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(ctx.lib.bn_slice_batch_scratch_bytes(reads), dtype=torch.uint8, device="cuda")
+    qst = dv.QueryStatus("cuda")
+
+    def run():
+        dv.raise_for(ctx.lib.bn_slice_batch_dev(ctx.handle, dv._stream(), dv._ptr(words), dv._ptr(wo), dv._ptr(lens), reads, dv._ptr(qr),
+                                                dv._ptr(qs), dv._ptr(qe), reads, dv._ptr(data), dv._ptr(oo), dv._ptr(qst.word), dv._ptr(scratch)))
+
+    ms = timed(run, reps)
+    assert qst.first_failing() is None and int(oo[-1].item()) == 50 * reads
+    full = dv.decode(words[:5 * 1000].contiguous(), 160 * 1000).view(1000, 160)   # 150 bases + 10 slots of padding per read
+    for r in (0, 1, 999):
+        s0 = int(qs[r].item())
+        assert torch.equal(data[50 * r : 50 * r + 50], full[r, s0 : s0 + 50])
+    # in: the touched part of each read (~16 B) + 16 B read index arrays + 24 B query arrays; out: 50 B + 8 B offsets
+    report(f"slice gathers: {reads} windows of 50 bases out of 150 bp reads", ms, (16 + 16 + 24 + 50 + 8) * reads, reads, "queries")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
@@ -255,7 +300,7 @@ def main():
     torch.cuda.set_device(0)
     print(json.dumps({"device": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak(), "scale": args.scale}), flush=True)
     for name in args.only.split(","):
-        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "short": short_reads}[name](args.scale, args.reps)
+        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "short": short_reads, "next": next_rows}[name](args.scale, args.reps)
         torch.cuda.empty_cache()
 
 

@@ -23,14 +23,16 @@
 
 namespace bn {
 
+// (left, right) word counts of read r: they depend on (ebuf.len(), len, idx) only
 struct SplitShape {
     const uint64_t *word_offsets, *lens, *idx;
-    bool left;
-    __device__ __forceinline__ unsigned long long operator()(unsigned long long r) const {
+    __device__ __forceinline__ ulonglong2 operator()(unsigned long long r) const {
         const unsigned long long slen = lens[r], i = idx[r], nw = word_offsets[r + 1] - word_offsets[r];
-        if (i > slen || (i && i < slen && nw && nw < (slen + 31) / 32)) return 0;  // reported as an error, takes no room
-        if (left) return i == 0 ? 0 : i == slen ? nw : nw == 0 ? 0 : i / 32 + 1;
-        return i == 0 ? nw : i == slen || nw == 0 ? 0 : nw - i / 32;
+        if (i > slen || (i && i < slen && nw && nw < (slen + 31) / 32)) return make_ulonglong2(0, 0);  // an error, takes no room
+        if (i == 0) return make_ulonglong2(0, nw);
+        if (i == slen) return make_ulonglong2(nw, 0);
+        if (nw == 0) return make_ulonglong2(0, 0);
+        return make_ulonglong2(i / 32 + 1, nw - i / 32);
     }
 };
 
@@ -70,7 +72,7 @@ split_packed_kernel(const uint64_t* __restrict__ words, const uint64_t* __restri
     }
 }
 
-size_t split_packed_scratch_bytes(size_t n_reads) { return scan_scratch_bytes(n_reads); }
+size_t split_packed_scratch_bytes(size_t n_reads) { return scan2_scratch_bytes(n_reads); }
 
 cudaError_t launch_split_packed_batch(const DeviceInfo&, const uint64_t* d_words, const uint64_t* d_word_offsets,
                                       const uint64_t* d_lens, const uint64_t* d_idx, size_t n_reads, uint64_t* d_left,
@@ -83,8 +85,7 @@ cudaError_t launch_split_packed_batch(const DeviceInfo&, const uint64_t* d_words
         return e != cudaSuccess ? e : cudaMemsetAsync(d_right_offsets, 0, sizeof(uint64_t), s);
     }
     unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
-    launch_exclusive_scan(SplitShape{d_word_offsets, d_lens, d_idx, true}, n_reads, sums, d_left_offsets, s);
-    launch_exclusive_scan(SplitShape{d_word_offsets, d_lens, d_idx, false}, n_reads, sums, d_right_offsets, s);
+    launch_exclusive_scan2(SplitShape{d_word_offsets, d_lens, d_idx}, n_reads, sums, d_left_offsets, d_right_offsets, s);
     split_packed_kernel<<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(d_words, d_word_offsets, d_lens, d_idx, n_reads, d_left,
                                                                                     d_left_offsets, d_right, d_right_offsets, d_status);
     return cudaGetLastError();

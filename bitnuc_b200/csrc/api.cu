@@ -37,6 +37,7 @@ struct bn_ctx {
     cudaStream_t stage_stream[kStages] = {};
     cudaEvent_t stage_done[kStages] = {};
     Buffer stage_in[kStages], stage_out[kStages];
+    Buffer stage_aux[kStages][4];                // batch calls: offsets, word offsets, per-read status, scratch
     Buffer slot[kSlots];
     unsigned long long* d_words = nullptr;       // 16 device status / accumulator words
     unsigned long long* h_words = nullptr;       // pinned mirror
@@ -195,6 +196,8 @@ void bn_ctx_destroy(bn_ctx* ctx) {
             if (ctx->stage_done[s]) cudaEventDestroy(ctx->stage_done[s]);
             if (ctx->stage_in[s].p) cudaFree(ctx->stage_in[s].p);
             if (ctx->stage_out[s].p) cudaFree(ctx->stage_out[s].p);
+            for (auto& b : ctx->stage_aux[s])
+                if (b.p) cudaFree(b.p);
         }
         for (auto& b : ctx->slot)
             if (b.p) cudaFree(b.p);
@@ -689,50 +692,87 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
     return set_err(err, BN_OK);
 }
 
+// Variable-length batches are cut into chunks of whole reads (>= ctx->chunk bytes each, so a read longer than the
+// chunk is a chunk of its own) and run through the same 3-stage pipeline as bn_encode: the upload of chunk c+1
+// overlaps the scan + encode of chunk c and the download of chunk c-1.  Word offsets come back relative to their
+// chunk and are rebased on the host; nothing short-circuits (the per-read variant needs every read anyway, and the
+// plain variant reports the minimum offset over all chunks = the first invalid base in input order).
 int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, size_t n_reads, uint64_t* out_words,
                     uint64_t* out_word_offsets, uint32_t* read_status, bn_error_t* err) {
     if (!ctx || !out_word_offsets || (n_reads && !offsets)) return set_err(err, BN_ERR_ARGUMENT);
-    if (n_reads == 0) {
-        out_word_offsets[0] = 0;
-        return set_err(err, BN_OK);
-    }
-    for (size_t r = 0; r < n_reads; ++r)
-        if (offsets[r + 1] < offsets[r]) return set_err(err, BN_ERR_ARGUMENT);
+    out_word_offsets[0] = 0;
+    if (n_reads == 0) return set_err(err, BN_OK);
     const uint64_t lo = offsets[0], hi = offsets[n_reads];
+    struct Chunk {
+        size_t r0, r1;      // reads [r0, r1)
+        uint64_t w0, nw;    // first output word, number of output words
+    };
+    std::vector<Chunk> chunks;
+    {   // one pass over the offsets: validate, count words, cut
+        const size_t want = ctx->chunk;
+        Chunk c{0, 0, 0, 0};
+        uint64_t w = 0;
+        for (size_t r = 0; r < n_reads; ++r) {
+            if (offsets[r + 1] < offsets[r]) return set_err(err, BN_ERR_ARGUMENT);
+            w += (offsets[r + 1] - offsets[r] + 31) / 32;
+            if (offsets[r + 1] - offsets[c.r0] >= want || r + 1 == n_reads) {
+                c.r1 = r + 1;
+                c.nw = w - c.w0;
+                chunks.push_back(c);
+                c = Chunk{r + 1, r + 1, w, 0};
+            }
+        }
+    }
     if (hi > lo && (!bytes || !out_words)) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    const size_t max_words = (size_t)((hi - lo) / 32 + n_reads);
-    // the byte buffer is staged at the same 16-byte phase as bytes+lo so offsets can be used unchanged
-    const size_t phase = lo & 15u;
-    BN_CUDA(ensure(ctx->slot[0], (hi - lo) + phase + 16));
-    BN_CUDA(ensure(ctx->slot[1], (n_reads + 1) * 8));
-    BN_CUDA(ensure(ctx->slot[2], max_words * 8 + 8));
-    BN_CUDA(ensure(ctx->slot[3], (n_reads + 1) * 8));
-    BN_CUDA(ensure(ctx->slot[4], bn::encode_batch_scratch_bytes(n_reads, hi - lo)));
-    if (read_status) BN_CUDA(ensure(ctx->slot[5], n_reads * 4));
-    uint8_t* d_bytes = static_cast<uint8_t*>(ctx->slot[0].p) + phase;
-    if (hi > lo) BN_CUDA(cudaMemcpyAsync(d_bytes, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_encode_batch(ctx->di, d_bytes - lo, static_cast<const uint64_t*>(ctx->slot[1].p), n_reads, hi - lo,
-                                    static_cast<uint64_t*>(ctx->slot[2].p), static_cast<uint64_t*>(ctx->slot[3].p),
-                                    read_status ? static_cast<uint32_t*>(ctx->slot[5].p) : nullptr, ctx->d_words + 8,
-                                    ctx->slot[4].p, st));
-    BN_CUDA(cudaMemcpyAsync(out_word_offsets, ctx->slot[3].p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
-    if (read_status) BN_CUDA(cudaMemcpyAsync(read_status, ctx->slot[5].p, n_reads * 4, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    const size_t total_words = (size_t)out_word_offsets[n_reads];
-    if (total_words) {
-        BN_CUDA(cudaMemcpyAsync(out_words, ctx->slot[2].p, total_words * 8, cudaMemcpyDeviceToHost, st));
-        BN_CUDA(cudaStreamSynchronize(st));
+    unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
+    auto retire = [&](size_t c) -> cudaError_t {
+        const int s = (int)(c % kStages);
+        cudaError_t e = cudaEventSynchronize(ctx->stage_done[s]);
+        if (e != cudaSuccess) return e;
+        best = std::min<unsigned long long>(best, ctx->h_words[s]);  // device offsets are already global (base pointer trick below)
+        if (c) {  // rebase this chunk's word offsets (entry r0 was written by the previous chunk's total, same value)
+            const Chunk& ch = chunks[c];
+            for (size_t r = ch.r0 + 1; r <= ch.r1; ++r) out_word_offsets[r] += ch.w0;
+        }
+        return cudaSuccess;
+    };
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const Chunk& ch = chunks[c];
+        const int s = (int)(c % kStages);
+        cudaStream_t st = ctx->stage_stream[s];
+        if (c >= (size_t)kStages) BN_CUDA(retire(c - kStages));
+        const size_t nr = ch.r1 - ch.r0;
+        const uint64_t b0 = offsets[ch.r0], b1 = offsets[ch.r1];
+        const size_t phase = b0 & 15u;  // staged at the same 16-byte phase as bytes + b0, so the offsets are used unchanged
+        BN_CUDA(ensure(ctx->stage_in[s], (b1 - b0) + phase + 16));
+        BN_CUDA(ensure(ctx->stage_out[s], ch.nw * 8 + 8));
+        BN_CUDA(ensure(ctx->stage_aux[s][0], (nr + 1) * 8));
+        BN_CUDA(ensure(ctx->stage_aux[s][1], (nr + 1) * 8));
+        if (read_status) BN_CUDA(ensure(ctx->stage_aux[s][2], nr * 4));
+        BN_CUDA(ensure(ctx->stage_aux[s][3], bn::encode_batch_scratch_bytes(nr, b1 - b0)));
+        uint8_t* d_bytes = static_cast<uint8_t*>(ctx->stage_in[s].p) + phase;
+        unsigned long long* d_status = ctx->d_words + s;
+        if (b1 > b0) BN_CUDA(cudaMemcpyAsync(d_bytes, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        BN_CUDA(cudaMemcpyAsync(ctx->stage_aux[s][0].p, offsets + ch.r0, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+        BN_CUDA(bn::launch_encode_batch(ctx->di, d_bytes - b0, static_cast<const uint64_t*>(ctx->stage_aux[s][0].p), nr, b1 - b0,
+                                        static_cast<uint64_t*>(ctx->stage_out[s].p), static_cast<uint64_t*>(ctx->stage_aux[s][1].p),
+                                        read_status ? static_cast<uint32_t*>(ctx->stage_aux[s][2].p) : nullptr, d_status,
+                                        ctx->stage_aux[s][3].p, st));
+        if (ch.nw) BN_CUDA(cudaMemcpyAsync(out_words + ch.w0, ctx->stage_out[s].p, ch.nw * 8, cudaMemcpyDeviceToHost, st));
+        // entries r0+1 .. r1 (entry r0 is the previous chunk's last entry; chunk 0 writes its own zero too)
+        BN_CUDA(cudaMemcpyAsync(out_word_offsets + ch.r0 + 1, static_cast<uint64_t*>(ctx->stage_aux[s][1].p) + 1, nr * 8,
+                                cudaMemcpyDeviceToHost, st));
+        if (read_status) BN_CUDA(cudaMemcpyAsync(read_status + ch.r0, ctx->stage_aux[s][2].p, nr * 4, cudaMemcpyDeviceToHost, st));
+        BN_CUDA(cudaMemcpyAsync(ctx->h_words + s, d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
     }
-    const unsigned long long key = ctx->h_words[8];
-    if (key != kNoError) {
-        invalid_base(err, key, 0);
+    for (size_t c = chunks.size() > (size_t)kStages ? chunks.size() - kStages : 0; c < chunks.size(); ++c) BN_CUDA(retire(c));
+    if (best != kNoError) {
+        invalid_base(err, best, 0);
         if (err) {
-            const uint64_t off = key >> 8;
+            const uint64_t off = best >> 8;
             const size_t r = (size_t)(std::upper_bound(offsets, offsets + n_reads + 1, off) - offsets) - 1;
             err->record = r;
             err->b = off - offsets[r];  // position inside the read

@@ -376,6 +376,11 @@ def test_encode_batch_matches_oracle(bn, profile):
     shifted = np.concatenate([np.full(13, ord("#"), dtype=np.uint8), data])
     w2, wo2 = bn.encode_batch(shifted, offsets + np.uint64(13))
     assert np.array_equal(w2, words) and np.array_equal(wo2, wo)
+    # chunked 3-stage pipeline of the host-pointer call: many small chunks of whole reads
+    small = bn.Context(0)
+    small.set_chunk_bytes(4096)
+    w3, wo3 = bn.encode_batch(shifted, offsets + np.uint64(13), ctx=small)
+    assert np.array_equal(w3, words) and np.array_equal(wo3, wo)
     # injected N: first invalid base in input order, with read index and position (cfg 5 error parity)
     nonempty = [r for r in range(len(lens)) if lens[r] > 0]
     victims = sorted(set(rng.choice(nonempty, size=min(5, len(nonempty)), replace=False).tolist()))
@@ -394,6 +399,10 @@ def test_encode_batch_matches_oracle(bn, profile):
     for r, pos in where.items():
         expect[r] = pos
     assert np.array_equal(status, expect)
+    err3 = gpu_error(bn, bn.encode_batch, bad, offsets, small)
+    assert (err3.key(), err3.record, err3.position, err3.offset) == (err.key(), r0, where[r0], int(offsets[r0]) + where[r0])
+    _, wo4, status4 = bn.encode_batch(bad, offsets, ctx=small, per_read_status=True)
+    assert np.array_equal(status4, expect) and np.array_equal(wo4, wo)
 
 
 # ------------------------------------------------------------------ device-resident path -----

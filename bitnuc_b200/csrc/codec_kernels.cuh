@@ -146,4 +146,63 @@ decode_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, unsigned
     }
 }
 
+// ============================================================================ 256-bit variants ==
+// Same work with one 64-bit packed word <-> 32 ASCII bytes per lane step: 256-bit loads (encode) / stores (decode),
+// i.e. one whole 32-byte sector per lane on the ASCII side.  The ASCII buffer must be 32-byte aligned.
+// The ragged end (words after the last full tile, trailing bases, zero padding) is left to the 128-bit kernels'
+// tail code: these kernels only take n_w64 full words.
+// Measured 2 % SLOWER than the 128-bit kernels on B200 (profiles/r01_tune_codec_sweep3.txt: encode 6930 vs 7085 GB/s,
+// decode 6457 vs 6598 GB/s), so the production launchers in codec.cu do not use them; they stay here for the
+// tuning harness.
+
+template <int U, int THREADS, int T, int LP, int SP>
+__global__ void __launch_bounds__(THREADS)
+encode256_kernel(const uint8_t* __restrict__ in, uint2* __restrict__ out, unsigned long long n_tiles,
+                 unsigned long long* __restrict__ status) {
+    const unsigned lane = threadIdx.x & 31;
+    constexpr unsigned kTile = 32 * U;   // 64-bit words per tile
+    const TileWalk<THREADS, 1, T> walk(n_tiles);
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
+        const unsigned long long w0 = t * kTile + lane;
+        const uint8_t* p = in + 32ull * w0;
+        uint8x v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) v[j] = ld256<LP>(p + 1024ull * j);
+        uint32_t bad = 0;
+        uint2 r[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) r[j] = make_uint2(pack16(v[j].lo, bad), pack16(v[j].hi, bad));
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (SP == ST_CS) st_stream_v2(out + w0 + 32 * j, r[j]);
+            else out[w0 + 32 * j] = r[j];
+        }
+        if (bad & kValidMask) {
+#pragma unroll 1
+            for (int j = 0; j < U; ++j)  // vectors 2*(w0 + 32 j) and the one after it
+                report_first_invalid(reinterpret_cast<const uint4*>(p + 1024ull * j), 1, 2 * (w0 + 32ull * j), status),
+                report_first_invalid(reinterpret_cast<const uint4*>(p + 1024ull * j) + 1, 1, 2 * (w0 + 32ull * j) + 1, status);
+        }
+    }
+}
+
+template <int U, int THREADS, int T, int LP, int SP>
+__global__ void __launch_bounds__(THREADS)
+decode256_kernel(const uint2* __restrict__ in, uint8_t* __restrict__ out, unsigned long long n_tiles) {
+    const unsigned lane = threadIdx.x & 31;
+    constexpr unsigned kTile = 32 * U;   // 64-bit words per tile
+    const TileWalk<THREADS, 1, T> walk(n_tiles);
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
+        const unsigned long long w0 = t * kTile + lane;
+        uint2 w[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (LP == LD_NC_NOALLOC) w[j] = ld_stream_v2(in + w0 + 32 * j);
+            else w[j] = __ldg(in + w0 + 32 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) st256<SP>(out + 32ull * (w0 + 32 * j), decode16_prmt(w[j].x), decode16_prmt(w[j].y));
+    }
+}
+
 }  // namespace bn

@@ -100,6 +100,34 @@ __device__ __forceinline__ void st128(uint4* p, uint4 v) {
         asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 256-bit global accesses (sm_100+: LDG.256 / STG.256): one full 32-byte sector per lane.
+struct uint8x {
+    uint4 lo, hi;
+};
+template <int LP>
+__device__ __forceinline__ uint8x ld256(const void* p) {
+    uint8x r;
+    if (LP == LD_NC_NOALLOC)
+        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w) : "l"(p));
+    else
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w) : "l"(p));
+    return r;
+}
+template <int SP>
+__device__ __forceinline__ void st256(void* p, uint4 a, uint4 b) {
+    if (SP == ST_CS)
+        asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                     "r"(b.z), "r"(b.w) : "memory");
+    else if (SP == ST_NOALLOC)
+        asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                     "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+    else
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                     "r"(b.z), "r"(b.w) : "memory");
+}
+
 // Maps (CTA, warp, round) to tile indices for the two scheduling modes.
 template <int THREADS, int SCHED, int T>
 struct TileWalk {

@@ -3,6 +3,7 @@
 // Prints, per variant: isolated encode / decode time (same kernel back to back) and the time of the
 // alternating encode->decode step that bench.py measures, all with CUDA events, plus GB/s at the
 // algorithmic 1.25 B/base.  Every variant's output is checked against the first one.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -67,6 +68,37 @@ void run_decode(const uint64_t* in, size_t n, uint8_t* out, cudaStream_t s) {
     k<<<grid, THREADS, 0, s>>>(reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint4*>(out), n_w32, (unsigned)(n % 16));
 }
 
+// 256-bit variants: full tiles by the wide kernel, the ragged rest by the 128-bit kernel on the remaining range
+template <int U, int THREADS, int T, int LP, int SP>
+void run_encode256(const uint8_t* in, size_t n, uint64_t* out, unsigned long long* status, cudaStream_t s) {
+    const unsigned long long n_tiles = (n / 32) / (32 * U);
+    const size_t done = (size_t)n_tiles * 32 * U * 32;   // bases handled by the wide kernel
+    cudaMemsetAsync(status, 0xFF, 8, s);
+    if (n_tiles)
+        encode256_kernel<U, THREADS, T, LP, SP><<<(unsigned)TileWalk<THREADS, 1, T>::ctas(n_tiles), THREADS, 0, s>>>(
+            in, reinterpret_cast<uint2*>(out), n_tiles, status);
+    if (n > done) {
+        const size_t rest = n - done;
+        encode_kernel<4, 512, 1, 1, LD_PLAIN, ST_CS><<<(unsigned)std::max<unsigned long long>(1, TileWalk<512, 1, 1>::ctas((rest / 16) / 128)), 512, 0, s>>>(
+            reinterpret_cast<const uint4*>(in + done), reinterpret_cast<uint32_t*>(out + done / 32), rest / 16, (unsigned)(rest % 16),
+            2ull * ((rest + 31) / 32), status);
+    }
+}
+template <int U, int THREADS, int T, int LP, int SP>
+void run_decode256(const uint64_t* in, size_t n, uint8_t* out, cudaStream_t s) {
+    const unsigned long long n_tiles = (n / 32) / (32 * U);
+    const size_t done = (size_t)n_tiles * 32 * U * 32;
+    if (n_tiles)
+        decode256_kernel<U, THREADS, T, LP, SP><<<(unsigned)TileWalk<THREADS, 1, T>::ctas(n_tiles), THREADS, 0, s>>>(
+            reinterpret_cast<const uint2*>(in), out, n_tiles);
+    if (n > done) {
+        const size_t rest = n - done;
+        decode_kernel<4, 512, 1, 1, LD_PLAIN, ST_CS, 2><<<(unsigned)std::max<unsigned long long>(1, TileWalk<512, 1, 1>::ctas((rest / 16) / 128)), 512, 0, s>>>(
+            reinterpret_cast<const uint32_t*>(in + done / 32), reinterpret_cast<uint4*>(out + done), rest / 16, (unsigned)(rest % 16));
+    }
+}
+#define W(name, U, TH, T, LP, SP) Variant{name, run_encode256<U, TH, T, LP, SP>, run_decode256<U, TH, T, LP, SP>}
+
 #define V(name, U, TH, SCHED, T, LP, SP, DEC) \
     Variant{name, run_encode<U, TH, SCHED, T, LP, SP>, run_decode<U, TH, SCHED, T, LP, SP, DEC>}
 
@@ -89,26 +121,18 @@ int main(int argc, char** argv) {
 
     std::vector<Variant> vs = {
         // name                                  U  TH  SCHED T  LP             SP       DEC
-        V("base   U4 t256 persist nc/cs lutR", 4, 256, 0, 1, LD_NC_NOALLOC, ST_CS, 0),
-        V("prmt   U4 t256 cta T1  nc/cs     ", 4, 256, 1, 1, LD_NC_NOALLOC, ST_CS, 2),
-        V("prmt   U4 t256 cta T1  plain/cs  ", 4, 256, 1, 1, LD_PLAIN, ST_CS, 2),
         V("prmt   U4 t512 cta T1  plain/cs  ", 4, 512, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U4 t1024 cta T1 plain/cs  ", 4, 1024, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U4 t128 cta T1  plain/cs  ", 4, 128, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U2 t256 cta T1  plain/cs  ", 2, 256, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U2 t512 cta T1  plain/cs  ", 2, 512, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U2 t1024 cta T1 plain/cs  ", 2, 1024, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U8 t256 cta T1  plain/cs  ", 8, 256, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U8 t512 cta T1  plain/cs  ", 8, 512, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U1 t512 cta T1  plain/cs  ", 1, 512, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U1 t1024 cta T1 plain/cs  ", 1, 1024, 1, 1, LD_PLAIN, ST_CS, 2),
-        V("prmt   U4 t512 cta T1  plain/plain", 4, 512, 1, 1, LD_PLAIN, ST_PLAIN, 2),
-        V("prmt   U4 t512 cta T1  plain/wt  ", 4, 512, 1, 1, LD_PLAIN, ST_WT, 2),
-        V("prmt   U4 t512 cta T1  plain/noal", 4, 512, 1, 1, LD_PLAIN, ST_NOALLOC, 2),
-        V("lut1k  U4 t512 cta T1  plain/cs  ", 4, 512, 1, 1, LD_PLAIN, ST_CS, 1),
-        V("lut1k  U4 t256 cta T1  plain/cs  ", 4, 256, 1, 1, LD_PLAIN, ST_CS, 1),
-        V("lutR   U4 t512 cta T8  plain/cs  ", 4, 512, 1, 8, LD_PLAIN, ST_CS, 0),
-        V("prmt   U4 t512 cta T2  plain/cs  ", 4, 512, 1, 2, LD_PLAIN, ST_CS, 2),
+        W("wide256 U2 t512 T1 plain/cs      ", 2, 512, 1, LD_PLAIN, ST_CS),
+        W("wide256 U2 t256 T1 plain/cs      ", 2, 256, 1, LD_PLAIN, ST_CS),
+        W("wide256 U4 t256 T1 plain/cs      ", 4, 256, 1, LD_PLAIN, ST_CS),
+        W("wide256 U4 t512 T1 plain/cs      ", 4, 512, 1, LD_PLAIN, ST_CS),
+        W("wide256 U1 t512 T1 plain/cs      ", 1, 512, 1, LD_PLAIN, ST_CS),
+        W("wide256 U1 t1024 T1 plain/cs     ", 1, 1024, 1, LD_PLAIN, ST_CS),
+        W("wide256 U2 t512 T1 nc/cs         ", 2, 512, 1, LD_NC_NOALLOC, ST_CS),
+        W("wide256 U2 t512 T1 plain/plain   ", 2, 512, 1, LD_PLAIN, ST_PLAIN),
+        W("wide256 U2 t512 T1 plain/noalloc ", 2, 512, 1, LD_PLAIN, ST_NOALLOC),
+        W("wide256 U2 t512 T2 plain/cs      ", 2, 512, 2, LD_PLAIN, ST_CS),
+        W("wide256 U2 t128 T1 plain/cs      ", 2, 128, 1, LD_PLAIN, ST_CS),
     };
 
     cudaEvent_t e0, e1;

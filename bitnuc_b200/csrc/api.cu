@@ -543,7 +543,50 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
     return set_err(err, BN_OK);
 }
 
-// The remaining host-pointer calls stage whole buffers through reusable device scratch slots.
+// The record- and stream-parallel calls below use the same 3-stage pipeline through one helper: chunk c is issued on
+// stage c % kStages (its own stream: H2D -> kernel -> D2H) once the chunk that used the stage before has retired, so
+// with pinned host buffers uploads, kernels and downloads of neighbouring chunks overlap.  Per-stage status /
+// accumulator words live at d_words[s] (status) and d_words[4 + 4 s ..] (up to four accumulators).
+
+}  // extern "C"
+
+namespace {
+
+// issue(c, s, stream) -> cudaError_t enqueues chunk c; retire(c, s) runs on the host once chunk c has completed.
+template <class Issue, class Retire>
+int run_pipeline(bn_ctx* ctx, size_t n_chunks, bn_error_t* err, Issue issue, Retire retire) {
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const int s = (int)(c % kStages);
+        if (c >= (size_t)kStages) {
+            BN_CUDA(cudaEventSynchronize(ctx->stage_done[s]));
+            retire(c - kStages, s);
+        }
+        BN_CUDA(issue(c, s, ctx->stage_stream[s]));
+        BN_CUDA(cudaEventRecord(ctx->stage_done[s], ctx->stage_stream[s]));
+    }
+    for (size_t c = n_chunks > (size_t)kStages ? n_chunks - kStages : 0; c < n_chunks; ++c) {
+        const int s = (int)(c % kStages);
+        BN_CUDA(cudaEventSynchronize(ctx->stage_done[s]));
+        retire(c, s);
+    }
+    return BN_OK;
+}
+
+#define BN_TRY(expr)                        \
+    do {                                    \
+        cudaError_t e__ = (expr);           \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+inline size_t units_per_chunk(const bn_ctx* ctx, size_t bytes_per_unit, size_t multiple) {
+    size_t u = ctx->chunk / (bytes_per_unit ? bytes_per_unit : 1);
+    u = u / multiple * multiple;
+    return u ? u : multiple;
+}
+
+}  // namespace
+
+extern "C" {
 
 int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, size_t stride, uint64_t* out, bn_error_t* err) {
     if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
@@ -552,20 +595,28 @@ int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, siz
     if (n == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    const size_t in_bytes = k ? (n - 1) * stride + k : 0;
-    BN_CUDA(ensure(ctx->slot[0], in_bytes ? in_bytes : 1));
-    BN_CUDA(ensure(ctx->slot[1], n * 8));
-    if (in_bytes) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, recs, in_bytes, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_as_2bit_batch(ctx->di, static_cast<const uint8_t*>(ctx->slot[0].p), n, k, stride,
-                                     static_cast<uint64_t*>(ctx->slot[1].p), ctx->d_words + 8, st));
-    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[1].p, n * 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long key = ctx->h_words[8];
-    if (key != kNoError) {
-        invalid_base(err, key, 0);
-        if (err) err->record = (key >> 8) / stride;
+    const size_t per = units_per_chunk(ctx, stride, 64), n_chunks = (n + per - 1) / per;
+    unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
+    const int rc = run_pipeline(
+        ctx, n_chunks, err,
+        [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+            const size_t r0 = c * per, cnt = std::min(per, n - r0), in_bytes = k ? (cnt - 1) * stride + k : 0;
+            BN_TRY(ensure(ctx->stage_in[s], in_bytes ? in_bytes : 1));
+            BN_TRY(ensure(ctx->stage_out[s], cnt * 8));
+            if (in_bytes) BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, recs + r0 * stride, in_bytes, cudaMemcpyHostToDevice, st));
+            BN_TRY(bn::launch_as_2bit_batch(ctx->di, static_cast<const uint8_t*>(ctx->stage_in[s].p), cnt, k, stride,
+                                            static_cast<uint64_t*>(ctx->stage_out[s].p), ctx->d_words + s, st));
+            BN_TRY(cudaMemcpyAsync(out + r0, ctx->stage_out[s].p, cnt * 8, cudaMemcpyDeviceToHost, st));
+            return cudaMemcpyAsync(ctx->h_words + s, ctx->d_words + s, 8, cudaMemcpyDeviceToHost, st);
+        },
+        [&](size_t c, int s) {
+            const unsigned long long key = ctx->h_words[s];
+            if (key != kNoError) best = std::min(best, (((key >> 8) + (unsigned long long)(c * per * stride)) << 8) | (key & 0xFFu));
+        });
+    if (rc != BN_OK) return rc;
+    if (best != kNoError) {
+        invalid_base(err, best, 0);
+        if (err) err->record = (best >> 8) / stride;
         return BN_INVALID_BASE;
     }
     return set_err(err, BN_OK);
@@ -578,18 +629,22 @@ int bn_from_2bit_batch(bn_ctx* ctx, const uint64_t* packed, size_t n, uint32_t k
     if (n == 0 || k == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    const size_t out_bytes = (n - 1) * stride + k;
-    BN_CUDA(ensure(ctx->slot[0], n * 8));
-    BN_CUDA(ensure(ctx->slot[1], out_bytes));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, packed, n * 8, cudaMemcpyHostToDevice, st));
-    if (stride != k)  // bytes between records must come back untouched
-        BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, out, out_bytes, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_from_2bit_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), n, k,
-                                       static_cast<uint8_t*>(ctx->slot[1].p), stride, st));
-    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[1].p, out_bytes, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    return set_err(err, BN_OK);
+    const size_t per = units_per_chunk(ctx, stride, 64), n_chunks = (n + per - 1) / per;
+    const int rc = run_pipeline(
+        ctx, n_chunks, err,
+        [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+            const size_t r0 = c * per, cnt = std::min(per, n - r0), out_bytes = (cnt - 1) * stride + k;
+            BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
+            BN_TRY(ensure(ctx->stage_out[s], out_bytes));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, packed + r0, cnt * 8, cudaMemcpyHostToDevice, st));
+            if (stride != k)  // bytes between records must come back untouched
+                BN_TRY(cudaMemcpyAsync(ctx->stage_out[s].p, out + r0 * stride, out_bytes, cudaMemcpyHostToDevice, st));
+            BN_TRY(bn::launch_from_2bit_batch(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), cnt, k,
+                                              static_cast<uint8_t*>(ctx->stage_out[s].p), stride, st));
+            return cudaMemcpyAsync(out + r0 * stride, ctx->stage_out[s].p, out_bytes, cudaMemcpyDeviceToHost, st);
+        },
+        [](size_t, int) {});
+    return rc != BN_OK ? rc : set_err(err, BN_OK);
 }
 
 int bn_hdist(bn_ctx* ctx, const uint64_t* a, size_t n_words_a, const uint64_t* b, size_t n_words_b, size_t n_bases,
@@ -602,16 +657,23 @@ int bn_hdist(bn_ctx* ctx, const uint64_t* a, size_t n_words_a, const uint64_t* b
     if (!a || !b) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    BN_CUDA(ensure(ctx->slot[0], need * 8));
-    BN_CUDA(ensure(ctx->slot[1], need * 8));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, a, need * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, b, need * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_hdist(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
-                             n_bases, ctx->d_words + 8, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    *total = ctx->h_words[8];
+    const size_t per = units_per_chunk(ctx, 16, 2), n_chunks = (need + per - 1) / per;  // words per chunk, 16-byte aligned shards
+    unsigned long long sum = 0;
+    const int rc = run_pipeline(
+        ctx, n_chunks, err,
+        [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+            const size_t w0 = c * per, cnt = std::min(per, need - w0), bases = std::min(n_bases - w0 * 32, cnt * 32);
+            BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
+            BN_TRY(ensure(ctx->stage_out[s], cnt * 8));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, a + w0, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_out[s].p, b + w0, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(bn::launch_hdist(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), static_cast<const uint64_t*>(ctx->stage_out[s].p),
+                                    bases, ctx->d_words + s, st));
+            return cudaMemcpyAsync(ctx->h_words + s, ctx->d_words + s, 8, cudaMemcpyDeviceToHost, st);
+        },
+        [&](size_t, int s) { sum += ctx->h_words[s]; });
+    if (rc != BN_OK) return rc;
+    *total = sum;
     return set_err(err, BN_OK);
 }
 
@@ -622,17 +684,23 @@ int bn_hdist_pairs(bn_ctx* ctx, const uint64_t* u, const uint64_t* v, size_t n_p
     if (!u || !v || !out) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    BN_CUDA(ensure(ctx->slot[0], n_pairs * 8));
-    BN_CUDA(ensure(ctx->slot[1], n_pairs * 8));
-    BN_CUDA(ensure(ctx->slot[2], n_pairs * 4));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, u, n_pairs * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, v, n_pairs * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_hdist_pairs(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->slot[1].p),
-                                   n_pairs, len, static_cast<uint32_t*>(ctx->slot[2].p), st));
-    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[2].p, n_pairs * 4, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    return set_err(err, BN_OK);
+    const size_t per = units_per_chunk(ctx, 16, 4), n_chunks = (n_pairs + per - 1) / per;
+    const int rc = run_pipeline(
+        ctx, n_chunks, err,
+        [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+            const size_t p0 = c * per, cnt = std::min(per, n_pairs - p0);
+            BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
+            BN_TRY(ensure(ctx->stage_aux[s][0], cnt * 8));
+            BN_TRY(ensure(ctx->stage_out[s], cnt * 4));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, u + p0, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][0].p, v + p0, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(bn::launch_hdist_pairs(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p),
+                                          static_cast<const uint64_t*>(ctx->stage_aux[s][0].p), cnt, len,
+                                          static_cast<uint32_t*>(ctx->stage_out[s].p), st));
+            return cudaMemcpyAsync(out + p0, ctx->stage_out[s].p, cnt * 4, cudaMemcpyDeviceToHost, st);
+        },
+        [](size_t, int) {});
+    return rc != BN_OK ? rc : set_err(err, BN_OK);
 }
 
 int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases, uint64_t counts[4], double* gc, bn_error_t* err) {
@@ -640,17 +708,30 @@ int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_
     const size_t need = (n_bases + 31) / 32;
     if (n_words < need) return set_err(err, BN_INVALID_LENGTH, n_bases);
     if (n_bases && !words) return set_err(err, BN_ERR_ARGUMENT);
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    if (gc) *gc = 0.0;
+    if (n_bases == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    BN_CUDA(ensure(ctx->slot[0], need ? need * 8 : 8));
-    if (need) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, need * 8, cudaMemcpyHostToDevice, st));
-    double* d_gc = reinterpret_cast<double*>(ctx->d_words + 12);
-    BN_CUDA(bn::launch_base_counts(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p), n_bases, ctx->d_words + 8, d_gc, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 5 * 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 4; ++i) counts[i] = ctx->h_words[8 + i];
-    if (gc) std::memcpy(gc, ctx->h_words + 12, sizeof(double));
+    const size_t per = units_per_chunk(ctx, 8, 2), n_chunks = (need + per - 1) / per;
+    const int rc = run_pipeline(
+        ctx, n_chunks, err,
+        [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+            const size_t w0 = c * per, cnt = std::min(per, need - w0), bases = std::min(n_bases - w0 * 32, cnt * 32);
+            BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, words + w0, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(bn::launch_base_counts(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), bases, ctx->d_words + 4 + 4 * s, nullptr, st));
+            return cudaMemcpyAsync(ctx->h_words + 4 + 4 * s, ctx->d_words + 4 + 4 * s, 4 * 8, cudaMemcpyDeviceToHost, st);
+        },
+        [&](size_t, int s) {
+            for (int i = 0; i < 4; ++i) counts[i] += ctx->h_words[4 + 4 * s + i];
+        });
+    if (rc != BN_OK) return rc;
+    // analysis.rs:14, exactly this operation order on exact integer counts: (gc as f64 / len as f64) * 100.0
+    if (gc) {
+        volatile double q = (double)(counts[1] + counts[2]) / (double)n_bases;
+        *gc = q * 100.0;
+    }
     return set_err(err, BN_OK);
 }
 
@@ -934,26 +1015,33 @@ int bn_kmers(bn_ctx* ctx, const uint8_t* seq, size_t n, uint32_t k, uint64_t* ou
     if (!seq || !out) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
     const size_t n_win = n - k + 1;
-    BN_CUDA(ensure(ctx->slot[0], n));
-    BN_CUDA(ensure(ctx->slot[1], n_win * 8));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, seq, n, cudaMemcpyHostToDevice, st));
-    BN_CUDA(bn::launch_kmer_windows(ctx->di, static_cast<const uint8_t*>(ctx->slot[0].p), n, k, static_cast<uint64_t*>(ctx->slot[1].p),
-                                    ctx->d_words + 8, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long key = ctx->h_words[8];
-    if (key != kNoError) {  // windows before the failing one were produced by the caller's loop: hand them over
-        const size_t off = (size_t)(key >> 8), first_bad = off >= k - 1 ? off - (k - 1) : 0;
-        if (first_bad) BN_CUDA(cudaMemcpy(out, ctx->slot[1].p, first_bad * 8, cudaMemcpyDeviceToHost));
+    const size_t per = units_per_chunk(ctx, 8, 2048), n_chunks = (n_win + per - 1) / per;  // the output (8 B per window) dominates
+    unsigned long long best = kNoError;
+    const int rc = run_pipeline(
+        ctx, n_chunks, err,
+        [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+            const size_t i0 = c * per, cnt = std::min(per, n_win - i0), in_bytes = cnt + k - 1;  // chunks share k-1 bytes of input
+            BN_TRY(ensure(ctx->stage_in[s], in_bytes));
+            BN_TRY(ensure(ctx->stage_out[s], cnt * 8));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, seq + i0, in_bytes, cudaMemcpyHostToDevice, st));
+            BN_TRY(bn::launch_kmer_windows(ctx->di, static_cast<const uint8_t*>(ctx->stage_in[s].p), in_bytes, k,
+                                           static_cast<uint64_t*>(ctx->stage_out[s].p), ctx->d_words + s, st));
+            BN_TRY(cudaMemcpyAsync(out + i0, ctx->stage_out[s].p, cnt * 8, cudaMemcpyDeviceToHost, st));
+            return cudaMemcpyAsync(ctx->h_words + s, ctx->d_words + s, 8, cudaMemcpyDeviceToHost, st);
+        },
+        [&](size_t c, int s) {
+            const unsigned long long key = ctx->h_words[s];
+            if (key != kNoError) best = std::min(best, (((key >> 8) + (unsigned long long)(c * per)) << 8) | (key & 0xFFu));
+        });
+    if (rc != BN_OK) return rc;
+    if (best != kNoError) {  // the windows before the failing one are what the caller's loop had produced: they are in `out`
+        const size_t off = (size_t)(best >> 8), first_bad = off >= k - 1 ? off - (k - 1) : 0;
         if (n_out) *n_out = first_bad;
-        invalid_base(err, key, 0);
+        invalid_base(err, best, 0);
         if (err) err->record = first_bad;
         return BN_INVALID_BASE;
     }
-    BN_CUDA(cudaMemcpyAsync(out, ctx->slot[1].p, n_win * 8, cudaMemcpyDeviceToHost, st));
-    BN_CUDA(cudaStreamSynchronize(st));
     if (n_out) *n_out = n_win;
     return set_err(err, BN_OK);
 }

@@ -721,3 +721,47 @@ def test_kmer_windows_errors(bn):
     assert ei.value.key() == err.key()
     readme = bn.kmers(b"ACGTACGT", 4)                          # README.md:170-180: "ACGT" occurs twice
     assert int((readme == np.uint64(bn.as_2bit(b"ACGT"))).sum()) == 2
+
+
+# ------------------------------------------------------------------ chunked host-pointer pipelines ----
+
+def test_host_pointer_calls_are_chunk_invariant(bn):
+    """Every pipelined host-pointer call gives the same answer with tiny chunks (many pipeline rounds, every stage
+    reused) as the oracle: as_2bit / from_2bit batches, hdist, hdist_pairs, base_counts, kmers, incl. error offsets."""
+    rng = np.random.default_rng(5)
+    ctx = bn.Context(0)
+    ctx.set_chunk_bytes(4096)
+    n = 50_000
+    for k, stride in [(31, 31), (31, 32), (17, 40), (32, 32)]:
+        recs = rand_seq(rng, (n - 1) * stride + k, mixed=True)
+        got = bn.as_2bit_batch(recs, n, k, stride, ctx=ctx)
+        view = np.lib.stride_tricks.as_strided(recs, shape=(n, k), strides=(stride, 1))
+        sample = rng.integers(0, n, 200)
+        assert [int(got[r]) for r in sample] == [oracle.as_2bit(view[r]) for r in sample]
+        assert np.array_equal(got, bn.as_2bit_batch(recs, n, k, stride))          # default (single chunk) context
+        out = np.full((n - 1) * stride + k, ord("#"), dtype=np.uint8)
+        back = bn.from_2bit_batch(got, k, stride, ctx=ctx, out=out)
+        v2 = np.lib.stride_tricks.as_strided(back, shape=(n, k), strides=(stride, 1))
+        assert np.array_equal(v2, np.where(view >= 97, view - 32, view))
+        if stride > k:
+            gaps = np.lib.stride_tricks.as_strided(back[k:], shape=(n - 1, stride - k), strides=(stride, 1))
+            assert (gaps == ord("#")).all()                                       # bytes between records untouched
+        bad = recs.copy()
+        r_bad = 33_333
+        bad[r_bad * stride + 5] = ord("N")
+        bad[(r_bad + 7000) * stride] = ord("x")
+        err = gpu_error(bn, bn.as_2bit_batch, bad, n, k, stride, ctx)
+        assert err.key() == ("InvalidBase", ord("N")) and err.record == r_bad and err.offset == r_bad * stride + 5
+    nb = 1_000_003
+    a, b = rand_seq(rng, nb), rand_seq(rng, nb)
+    wa, wb = oracle.encode_np(a), oracle.encode_np(b)
+    assert bn.hdist_total(wa, wb, nb, ctx=ctx) == oracle.hdist(wa, wb, nb, wide=True)
+    assert np.array_equal(bn.hdist_pairs(wa, wb, 29, ctx=ctx), onp.hdist_pairs(wa, wb, 29))
+    counts, gc = bn.base_counts_gc(wa, nb, ctx=ctx)
+    assert counts == oracle.base_counts(wa, nb) and gc == oracle.gc_content(wa, nb)
+    seq = rand_seq(rng, 100_000, mixed=True)
+    assert np.array_equal(bn.kmers(seq, 27, ctx=ctx), bn.kmers(seq, 27))
+    seq[77_777] = ord("N")
+    err = gpu_error(bn, bn.kmers, seq, 27, ctx)
+    assert err.offset == 77_777 and err.record == 77_777 - 26 and err.partial.size == 77_777 - 26
+    assert [int(x) for x in err.partial[-50:]] == [oracle.as_2bit(seq[i : i + 27]) for i in range(77_777 - 26 - 50, 77_777 - 26)]

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""End-to-end (host pointers, PCIe inside the timed region) throughput of the pipelined host-pointer calls on one
+GPU, pinned buffers: as_2bit / from_2bit batches (cfg 3 shape), hdist_pairs and hdist (cfg 4 shape), base_counts,
+kmers.  The yardstick is the PCIe link (tools/pcie_probe.py): a call is link-bound in its dominant direction."""
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+import torch
+
+import bitnuc_b200 as bn
+from bitnuc_b200 import device as dv
+
+SEED = 0x5EEDB17C0DE5
+ctx = bn.Context(0)
+
+
+def pinned(t: torch.Tensor, dtype):
+    a = ctx.pinned_empty(t.numel(), dtype)
+    a[:] = t.cpu().numpy().view(dtype)
+    return a
+
+
+def timed(fn, reps=3):
+    fn()
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def line(name, s, h2d, d2h, units, unit):
+    print(json.dumps({"call": name, "ms": round(s * 1e3, 3), "h2d_GB": round(h2d / 1e9, 3), "d2h_GB": round(d2h / 1e9, 3),
+                      "h2d_GB_s": round(h2d / s / 1e9, 1), "d2h_GB_s": round(d2h / s / 1e9, 1), f"G{unit}_s": round(units / s / 1e9, 3)}), flush=True)
+
+
+n = 1 << 26
+words = dv.synth_words(SEED, 1, 0, n)
+recs = pinned(dv.from_2bit_batch(words, 31), np.uint8)
+h_words = pinned(words, np.uint64)
+out_w = ctx.pinned_empty(n, np.uint64)
+s = timed(lambda: ctx.lib.bn_as_2bit_batch(ctx.handle, recs.ctypes.data, n, 31, 31, out_w.ctypes.data, None))
+assert np.array_equal(out_w, h_words & np.uint64((1 << 62) - 1))
+line("bn_as_2bit_batch k=31 tight", s, 31 * n, 8 * n, n, "kmers")
+out_r = ctx.pinned_empty(31 * n, np.uint8)
+s = timed(lambda: ctx.lib.bn_from_2bit_batch(ctx.handle, h_words.ctypes.data, n, 31, out_r.ctypes.data, 31, None))
+assert np.array_equal(out_r, recs)
+line("bn_from_2bit_batch k=31 tight", s, 8 * n, 31 * n, n, "kmers")
+del recs, out_r
+
+n = 1 << 27
+u, v = pinned(dv.synth_words(SEED, 2, 0, n), np.uint64), pinned(dv.synth_words(SEED, 3, 0, n), np.uint64)
+d = ctx.pinned_empty(n, np.uint32)
+s = timed(lambda: ctx.lib.bn_hdist_pairs(ctx.handle, u.ctypes.data, v.ctypes.data, n, 32, d.ctypes.data, None))
+line("bn_hdist_pairs len=32", s, 16 * n, 4 * n, n, "pairs")
+import ctypes as C
+tot = C.c_uint64(0)
+s = timed(lambda: ctx.lib.bn_hdist(ctx.handle, u.ctypes.data, n, v.ctypes.data, n, 32 * n, C.byref(tot), None))
+assert tot.value == int(d.astype(np.uint64).sum())
+line("bn_hdist whole sequence", s, 16 * n, 8, 32 * n, "bases")
+counts, gc = (C.c_uint64 * 4)(), C.c_double(0)
+s = timed(lambda: ctx.lib.bn_base_counts(ctx.handle, u.ctypes.data, n, 32 * n, counts, C.byref(gc), None))
+assert sum(counts) == 32 * n
+line("bn_base_counts whole sequence", s, 8 * n, 40, 32 * n, "bases")
+del u, v, d
+
+n = 1 << 27
+seq = pinned(dv.synth_ascii(SEED, 7, 0, n), np.uint8)
+out_k = ctx.pinned_empty(n - 30, np.uint64)
+n_out = C.c_size_t(0)
+s = timed(lambda: ctx.lib.bn_kmers(ctx.handle, seq.ctypes.data, n, 31, out_k.ctypes.data, C.byref(n_out), None))
+assert n_out.value == n - 30
+line("bn_kmers k=31", s, n, 8 * (n - 30), n - 30, "kmers")

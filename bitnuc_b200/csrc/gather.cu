@@ -9,9 +9,9 @@
 // The first failing query in index order is reported (status word = min failing query index); failing queries
 // produce no output (slice) or 0 (get).
 //
-// slice: an exclusive scan of (end - start) places every query's bytes; then 8 lanes per query walk the range four
-// bases (one packed byte -> one 32-bit word of ASCII, PRMT as a 4-entry LUT) at a time: 32 contiguous bytes per
-// 8-lane step, byte stores only for the unaligned head and tail of a range.
+// slice: an exclusive scan of (end - start) places every query's bytes.  Ranges of up to 64 bases are cut one query
+// per thread and staged per warp for coalesced stores (slice_short_kernel); longer ranges are queued and cut a warp
+// per range (slice_long_kernel).
 #include "common.cuh"
 #include "launch.cuh"
 #include "scan.cuh"
@@ -44,35 +44,127 @@ __device__ __forceinline__ uint8_t ascii1_at(const uint32_t* __restrict__ w32, u
     return (uint8_t)(0x54474341u >> (8u * ((__ldg(w32 + (b >> 4)) >> (2u * (unsigned)(b & 15u))) & 3u)));
 }
 
-constexpr int kSliceLanes = 8;
+constexpr unsigned kSliceShort = 64;                      // ranges up to this many bases are cut by one thread each
+constexpr unsigned kSliceStage = 32 * kSliceShort + 16;   // bytes a warp stages for its 32 queries (+ alignment slack)
 
+// Short ranges (<= 64 bases): one thread per query, so a warp keeps 32 independent gathers in flight (this path is
+// a latency-bound chain query -> read offsets -> words).  The 2n bits of a range are pulled into a 128-bit register
+// window (<= 3 words) and leave 4 bases at a time (spread + PRMT as a 4-entry LUT).  The 32 ranges of a warp are
+// adjacent in the output (prefix sums of consecutive queries), so the threads write into a shared-memory image of
+// that span -- laid out at the same 16-byte phase as the global span -- and the warp then stores it with coalesced
+// 128-bit stores.  Longer ranges are queued for slice_long_kernel.
 __global__ void __launch_bounds__(kThreads)
-slice_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ lens,
+slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ lens,
                    unsigned long long n_reads, const uint64_t* __restrict__ q_read, const uint64_t* __restrict__ q_start,
                    const uint64_t* __restrict__ q_end, unsigned long long nq, uint8_t* __restrict__ out,
-                   const uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ status) {
-    const unsigned sub = threadIdx.x % kSliceLanes;
-    const unsigned long long q = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) / kSliceLanes;
-    if (q >= nq) return;
-    const unsigned long long r = q_read[q], s = q_start[q], e = q_end[q];
-    if (r >= n_reads || s > e || e > lens[r]) {
-        if (sub == 0 && q < ld_volatile_u64(status)) atomicMin(status, q);
-        return;
+                   const uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ status,
+                   unsigned long long* __restrict__ long_count, unsigned long long* __restrict__ long_list) {
+    __shared__ __align__(16) uint8_t stage[kWarpsPerBlock][kSliceStage];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long q = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    // this thread's query: n = 0 for lanes past the end, failing queries and ranges left to the long kernel
+    unsigned n = 0, sh_head = 0;
+    unsigned long long s = 0, oo = out_offsets[q < nq ? q : nq];
+    const uint64_t* w = words;
+    unsigned long long last_word = 0;
+    if (q < nq) {
+        const unsigned long long r = q_read[q], s0 = q_start[q], e = q_end[q];
+        const unsigned long long len = r < n_reads ? lens[r] : 0;
+        if (r >= n_reads || s0 > e || e > len) {
+            if (q < ld_volatile_u64(status)) atomicMin(status, q);
+        } else if (e - s0 > kSliceShort) {
+            long_list[atomicAdd(long_count, 1ull)] = q;
+        } else if (e > s0) {
+            n = (unsigned)(e - s0);
+            s = s0;
+            w = words + word_offsets[r];
+            last_word = (len - 1) >> 5;
+        }
     }
-    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(words + word_offsets[r]);
-    uint8_t* o = out + out_offsets[q];
-    const unsigned long long n = e - s;
-    // head: bytes up to the first 4-byte aligned output address
-    const unsigned head = (unsigned)min((unsigned long long)((4u - (unsigned)(reinterpret_cast<uintptr_t>(o) & 3u)) & 3u), n);
-    if (sub < head) o[sub] = ascii1_at(w32, s + sub);
-    // body: one aligned 32-bit store of 4 bases per lane step
-    const unsigned long long body = (n - head) / 4;
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(o + head);
-    const unsigned long long b0 = s + head;
-    for (unsigned long long i = sub; i < body; i += kSliceLanes) o32[i] = ascii4_at(w32, b0 + 4 * i);
-    // tail: the last (< 4) bytes
-    const unsigned long long done = head + 4 * body;
-    if (done + sub < n) o[done + sub] = ascii1_at(w32, s + done + sub);
+    // the warp's output span [span_lo, span_hi) and its staged image; a span with a long range inside is too big to stage
+    const unsigned long long span_lo = __shfl_sync(0xffffffffu, oo, 0);
+    const unsigned long long q_last = (unsigned long long)blockIdx.x * kThreads + 32ull * warp + 32;
+    const unsigned long long span_hi = out_offsets[q_last < nq ? q_last : nq];
+    const uintptr_t g_lo = reinterpret_cast<uintptr_t>(out) + span_lo, g_base = g_lo & ~(uintptr_t)15;
+    const bool staged = g_lo - g_base + (span_hi - span_lo) <= kSliceStage;
+    uint8_t* o = staged ? stage[warp] + (reinterpret_cast<uintptr_t>(out) + oo - g_base) : out + oo;
+    if (n) {
+        // head: bases up to the first 4-byte aligned output address (global and staged addresses share their phase)
+        const unsigned head = min((4u - (unsigned)((reinterpret_cast<uintptr_t>(out) + oo) & 3u)) & 3u, n);
+        if (head) {
+            const unsigned long long wi = s >> 5;
+            const unsigned sh = 2u * (unsigned)(s & 31u);
+            uint64_t x = __ldg(w + wi) >> sh;
+            if (sh > 58 && wi < last_word) x |= __ldg(w + wi + 1) << (64 - sh);   // 3 bases may straddle two words
+            for (unsigned i = 0; i < head; ++i) o[i] = (uint8_t)(0x54474341u >> (8u * ((unsigned)(x >> (2 * i)) & 3u)));
+            s += head;
+            n -= head;
+            sh_head = head;
+        }
+    }
+    if (n) {
+        // 128-bit window of the remaining 2n bits
+        const unsigned long long wi = s >> 5;
+        const unsigned sh = 2u * (unsigned)(s & 31u);
+        const unsigned need_bits = sh + 2u * n;                      // bits needed counted from the start of word wi
+        const uint64_t w0 = __ldg(w + wi);
+        const uint64_t w1 = need_bits > 64 ? __ldg(w + wi + 1) : 0ull;
+        const uint64_t w2 = need_bits > 128 ? __ldg(w + wi + 2) : 0ull;
+        const uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+        const uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(o + sh_head);
+        const unsigned body = n / 4;
+#pragma unroll
+        for (unsigned g = 0; g < kSliceShort / 4; ++g) {
+            if (g < body) {
+                uint32_t t = (uint32_t)((g < 8 ? lo >> (8 * g) : hi >> (8 * (g - 8))) & 0xFFu);
+                t = (t | (t << 4)) & 0x0F0Fu;
+                t = (t | (t << 2)) & 0x3333u;
+                o32[g] = __byte_perm(0x54474341u, 0u, t);
+            }
+        }
+        const unsigned done = 4 * body;
+        if (done < n) {
+            const uint32_t t = (uint32_t)((body < 8 ? lo >> (8 * body) : hi >> (8 * (body - 8))) & 0xFFu);
+            for (unsigned i = 0; done + i < n; ++i) o[sh_head + done + i] = (uint8_t)(0x54474341u >> (8u * ((t >> (2 * i)) & 3u)));
+        }
+    }
+    if (staged) {  // warp-uniform: store the staged span, 16 bytes per lane step; ragged ends byte-wise
+        __syncwarp();
+        const unsigned a = (unsigned)(g_lo - g_base), b = a + (unsigned)(span_hi - span_lo);   // valid bytes [a, b) of the image
+        for (unsigned c = 16 * lane; c < b; c += 16 * 32) {
+            if (c >= a && c + 16 <= b) {
+                *reinterpret_cast<uint4*>(g_base + c) = *reinterpret_cast<const uint4*>(stage[warp] + c);
+            } else {
+                for (unsigned i = c < a ? a : c; i < c + 16 && i < b; ++i) *reinterpret_cast<uint8_t*>(g_base + i) = stage[warp][i];
+            }
+        }
+    }
+}
+
+// Long ranges: a warp per queued query, four bases (one 32-bit store) per lane step = 128 contiguous bytes per warp step.
+__global__ void __launch_bounds__(kThreads)
+slice_long_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ q_read,
+                  const uint64_t* __restrict__ q_start, const uint64_t* __restrict__ q_end, uint8_t* __restrict__ out,
+                  const uint64_t* __restrict__ out_offsets, const unsigned long long* __restrict__ long_count,
+                  const unsigned long long* __restrict__ long_list) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long n_long = *long_count;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n_long; i += n_warps) {
+        const unsigned long long q = long_list[i];
+        const unsigned long long s = q_start[q], n = q_end[q] - s;
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(words + word_offsets[q_read[q]]);
+        uint8_t* o = out + out_offsets[q];
+        const unsigned head = (4u - (unsigned)(reinterpret_cast<uintptr_t>(o) & 3u)) & 3u;   // n > 64 > head
+        if (lane < head) o[lane] = ascii1_at(w32, s + lane);
+        const unsigned long long body = (n - head) / 4;
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(o + head);
+        const unsigned long long b0 = s + head;
+        for (unsigned long long j = lane; j < body; j += 32) o32[j] = ascii4_at(w32, b0 + 4 * j);
+        const unsigned long long done = head + 4 * body;
+        if (done + lane < n) o[done + lane] = ascii1_at(w32, s + done + lane);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -91,18 +183,26 @@ get_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
     out[q] = (uint8_t)(0x54474341u >> (8 * ((x >> (2 * (i & 31))) & 3)));
 }
 
-size_t slice_batch_scratch_bytes(size_t nq) { return scan_scratch_bytes(nq); }
+// scan state, then the queue of long ranges (count + one entry per query)
+size_t slice_batch_scratch_bytes(size_t nq) { return scan_scratch_bytes(nq) + (nq + 1) * sizeof(unsigned long long); }
 
-cudaError_t launch_slice_batch(const DeviceInfo&, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
+cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
                                size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_start, const uint64_t* d_q_end, size_t nq,
                                uint8_t* d_out, uint64_t* d_out_offsets, unsigned long long* d_status, void* d_scratch, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(d_status, 0xFF, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
     if (nq == 0) return cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s);
-    launch_exclusive_scan(SliceLen{d_lens, d_q_read, d_q_start, d_q_end, n_reads}, nq, static_cast<unsigned long long*>(d_scratch),
-                          d_out_offsets, s);
-    slice_batch_kernel<<<(unsigned)ceil_div((unsigned long long)nq * kSliceLanes, kThreads), kThreads, 0, s>>>(
-        d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start, d_q_end, nq, d_out, d_out_offsets, d_status);
+    unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
+    unsigned long long* long_count = sums + scan_scratch_bytes(nq) / sizeof(unsigned long long);
+    e = cudaMemsetAsync(long_count, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    launch_exclusive_scan(SliceLen{d_lens, d_q_read, d_q_start, d_q_end, n_reads}, nq, sums, d_out_offsets, s);
+    slice_short_kernel<<<(unsigned)ceil_div(nq, kThreads), kThreads, 0, s>>>(d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start,
+                                                                           d_q_end, nq, d_out, d_out_offsets, d_status, long_count,
+                                                                           long_count + 1);
+    static const int resident = resident_blocks(slice_long_kernel, kThreads, di);
+    slice_long_kernel<<<grid_for(ceil_div(nq, kWarpsPerBlock), resident), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, d_q_end,
+                                                                                          d_out, d_out_offsets, long_count, long_count + 1);
     return cudaGetLastError();
 }
 

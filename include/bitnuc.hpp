@@ -180,6 +180,16 @@ inline uint32_t hdist_scalar(uint64_t u, uint64_t v, size_t len) {  // hamming/s
     return out;
 }
 
+// `for w in seq.windows(k) { as_2bit(w)? }` (README.md:160-180) in one call: one packed word per window
+inline std::vector<uint64_t> kmers(Bytes seq, size_t k) {
+    std::vector<uint64_t> out(seq.len >= k && k ? seq.len - k + 1 : 0);
+    size_t n_out = 0;
+    bn_error_t e{};
+    detail::check(bn_kmers(detail::ctx(), seq.ptr, seq.len, static_cast<uint32_t>(k > 0xFFFFFFFFu ? 0xFFFFFFFFu : k), out.data(), &n_out, &e), e);
+    out.resize(n_out);
+    return out;
+}
+
 // src/utils/functions/split.rs:14-20 -- validates idx <= slen, then clears both buffers and fills them
 inline void split_packed(Words ebuf, size_t slen, size_t idx, std::vector<uint64_t>& lbuf, std::vector<uint64_t>& rbuf) {
     const uint64_t word_offsets[2] = {0, ebuf.len}, len64 = slen, idx64 = idx;

@@ -112,6 +112,17 @@ pub fn hdist_scalar(u: u64, v: u64, len: usize) -> Result<u32, NucleotideError> 
     check(rc, &e).map(|_| out)
 }
 
+/// `seq.windows(k).map(as_2bit).collect()` in one kernel launch (README.md:160-180): one packed word per window.
+pub fn kmers(seq: &[u8], k: usize) -> Result<Vec<u64>, NucleotideError> {
+    assert!(k != 0, "window size must be non-zero"); // slice::windows panics
+    let mut out = vec![0u64; if seq.len() >= k { seq.len() - k + 1 } else { 0 }];
+    let (mut n_out, mut e) = (0usize, bn_error_t::default());
+    let rc = with_ctx(|c| unsafe { bn_kmers(c, seq.as_ptr(), seq.len(), k.min(u32::MAX as usize) as u32, out.as_mut_ptr(), &mut n_out, &mut e) });
+    check(rc, &e)?;
+    out.truncate(n_out);
+    Ok(out)
+}
+
 /// `bitnuc::split_packed` (src/utils/functions/split.rs:14-20): validates, then clears and fills both buffers.
 pub fn split_packed(ebuf: &[u64], slen: usize, idx: usize, lbuf: &mut Vec<u64>, rbuf: &mut Vec<u64>) -> Result<(), NucleotideError> {
     let word_offsets = [0u64, ebuf.len() as u64];

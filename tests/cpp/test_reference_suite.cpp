@@ -6,6 +6,7 @@
 #include <functional>
 #include <random>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -228,11 +229,23 @@ static void test_split_packed() {
     }
 }
 
+// README.md:160-180 ("Efficient k-mer counting") with the whole window loop in one call
+static void test_readme_kmer_counting() {
+    const std::string sequence = "ACGTACGT";
+    std::unordered_map<uint64_t, int> kmer_counts;
+    for (uint64_t packed : kmers(sequence, 4)) ++kmer_counts[packed];
+    CHECK(kmer_counts[as_2bit("ACGT")] == 2);
+    CHECK(kmers(sequence, 4).size() == 5);
+    for (size_t i = 0; i + 4 <= sequence.size(); ++i) CHECK(kmers(sequence, 4)[i] == as_2bit(sequence.substr(i, 4)));
+    CHECK(expect_err([] { kmers("ACGTNACGT", 3); }) == E(E::InvalidBase, 'N'));
+    CHECK(kmers("ACG", 4).empty());
+}
+
 int main() {
     const std::pair<const char*, std::function<void()>> tests[] = {
         {"as_2bit", test_as_2bit}, {"from_2bit", test_from_2bit}, {"roundtrips", test_roundtrips},
         {"hdist", test_hdist},     {"packed_sequence", test_packed_sequence}, {"errors", test_errors},
-        {"split_packed", test_split_packed}};
+        {"split_packed", test_split_packed}, {"readme_kmer_counting", test_readme_kmer_counting}};
     for (const auto& t : tests) {
         t.second();
         std::printf("ok %s\n", t.first);

@@ -1,5 +1,15 @@
-// scan.cuh -- exclusive prefix sum of a per-item count over n items (u64), as three small kernels:
-// per-CTA sums, a one-CTA scan of the sums, CTA-local scan + offset.  out[n] receives the total.
+// scan.cuh -- exclusive prefix sums of per-item counts (u64) over n items, as three small kernels: per-CTA sums, a
+// one-CTA scan of the sums, CTA-local scan + offset.  out[i] = sum of count(j), j < i, for i in [0, n].
+//
+// Item layout inside a CTA tile of 1024 items is WARP-STRIPED: warp w owns items [128 w, 128 w + 128) of the tile and
+// lane l touches items 128 w + 32 i + l, i < 4 -- every load the count functor makes and every offset store is a
+// coalesced 256-byte warp transaction (a blocked layout, 4 consecutive items per thread, leaves 3/4 of every sector
+// to the L1).  The warp scans its four rows one after the other, carrying the running total from row to row.
+//
+// One channel (count(i) -> u64) or two at once (count(i) -> ulonglong2: split_packed needs the left and right word
+// counts of the same reads), and a hook that runs once per item right where its offsets are known (encode_batch
+// notes the owner of every output tile there).  A single-pass chained scan with decoupled look-back was measured
+// and is slower at this tile size.
 #pragma once
 
 #include "common.cuh"
@@ -10,21 +20,56 @@ namespace bn {
 constexpr int kScanItems = 4;                      // items per thread
 constexpr int kScanTile = kThreads * kScanItems;   // items per CTA
 
-template <typename F>
-__global__ void __launch_bounds__(kThreads)
-scan_block_sums_kernel(F count, unsigned long long n, unsigned long long* __restrict__ sums) {
-    __shared__ unsigned long long scratch[32];
-    const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    unsigned long long s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-        if (r0 + i < n) s += count(r0 + i);
-    s = block_sum_u64(s, scratch);
-    if (threadIdx.x == 0) sums[blockIdx.x] = s;
+struct ScanNoHook {
+    __device__ __forceinline__ void operator()(unsigned long long, unsigned long long, unsigned long long) const {}
+    __device__ __forceinline__ void operator()(unsigned long long, unsigned long long, unsigned long long, unsigned long long,
+                                               unsigned long long) const {}
+};
+
+template <int NCH, typename F>
+__device__ __forceinline__ void scan_counts(const F& count, unsigned long long i, unsigned long long (&v)[NCH]) {
+    if constexpr (NCH == 1) {
+        v[0] = count(i);
+    } else {
+        const ulonglong2 c = count(i);
+        v[0] = c.x;
+        v[1] = c.y;
+    }
 }
 
-// exclusive scan of sums[0..n) in place by one CTA; sums[n] = total
-static __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long long* __restrict__ sums, unsigned long long n) {
+// item index of (row i, this thread) in the warp-striped tile layout
+__device__ __forceinline__ unsigned long long scan_item(unsigned i) {
+    return (unsigned long long)blockIdx.x * kScanTile + (threadIdx.x >> 5) * (32 * kScanItems) + 32 * i + (threadIdx.x & 31);
+}
+
+// sums[ch * (n_blocks + 1) + b] = sum of channel ch over tile b
+template <int NCH, typename F>
+__global__ void __launch_bounds__(kThreads)
+scan_block_sums_kernel(F count, unsigned long long n, unsigned long long n_blocks, unsigned long long* __restrict__ sums) {
+    __shared__ unsigned long long scratch[32];
+    unsigned long long s[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) s[ch] = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const unsigned long long r = scan_item(i);
+        if (r < n) {
+            unsigned long long c[NCH];
+            scan_counts<NCH>(count, r, c);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) s[ch] += c[ch];
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const unsigned long long t = block_sum_u64(s[ch], scratch);
+        if (threadIdx.x == 0) sums[ch * (n_blocks + 1) + blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of each channel's n sums in place, one CTA per channel; entry n receives the channel's total
+static __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long long* __restrict__ all_sums, unsigned long long n) {
+    unsigned long long* sums = all_sums + blockIdx.x * (n + 1);
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -60,193 +105,103 @@ static __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long lo
     if (threadIdx.x == 0) sums[n] = carry_s;
 }
 
-struct ScanNoHook {
-    __device__ __forceinline__ void operator()(unsigned long long, unsigned long long, unsigned long long) const {}
-};
-
-// hook(i, out[i], count(i)) is called once per item (e.g. to note which item owns a given output position)
-template <typename F, typename H>
+// hook(i, out[i], count(i)) -- or hook(i, out_a[i], a(i), out_b[i], b(i)) with two channels -- once per item
+template <int NCH, typename F, typename H>
 __global__ void __launch_bounds__(kThreads)
 scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __restrict__ sums, unsigned long long n_blocks,
-                    uint64_t* __restrict__ out, H hook) {
-    __shared__ unsigned long long warp_tot[32];
+                    uint64_t* __restrict__ out_a, uint64_t* __restrict__ out_b, H hook) {
+    __shared__ unsigned long long warp_tot[NCH][32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    unsigned long long c[kScanItems], s = 0;
+    unsigned long long c[kScanItems][NCH], excl[kScanItems][NCH], carry[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) carry[ch] = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {  // all loads first (independent), the row scans below
+        const unsigned long long r = scan_item(i);
+        if (r < n) {
+            scan_counts<NCH>(count, r, c[i]);
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) c[i][ch] = 0;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
-        c[i] = r0 + i < n ? count(r0 + i) : 0;
-        s += c[i];
-    }
-    unsigned long long inc = s;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (unsigned)o) inc += t;
+        for (int ch = 0; ch < NCH; ++ch) {
+            unsigned long long inc = c[i][ch];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (unsigned)o) inc += t;
+            }
+            excl[i][ch] = carry[ch] + inc - c[i][ch];                   // exclusive prefix inside the warp's 128 items
+            carry[ch] += __shfl_sync(0xffffffffu, inc, 31);
+        }
     }
-    if (lane == 31) warp_tot[warp] = inc;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        if (lane == 0) warp_tot[ch][warp] = carry[ch];
     __syncthreads();
     if (warp == 0) {
-        unsigned long long w = lane < kWarpsPerBlock ? warp_tot[lane] : 0, winc = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= (unsigned)o) winc += t;
-        }
-        if (lane < kWarpsPerBlock) warp_tot[lane] = winc - w;
-    }
-    __syncthreads();
-    unsigned long long run = sums[blockIdx.x] + warp_tot[warp] + inc - s;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        if (r0 + i < n) {
-            out[r0 + i] = run;
-            hook(r0 + i, run, c[i]);
-        }
-        run += c[i];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[n_blocks];
-}
-
-// bytes of scratch (`sums`) the scan needs for n items
-static inline size_t scan_scratch_bytes(size_t n) { return (ceil_div(n ? n : 1, kScanTile) + 1) * sizeof(unsigned long long); }
-
-// out[i] = sum of count(j), j < i, for i in [0, n]; n >= 1
-template <typename F, typename H = ScanNoHook>
-static void launch_exclusive_scan(F count, size_t n, unsigned long long* sums, uint64_t* out, cudaStream_t s, H hook = H()) {
-    const unsigned long long n_blocks = ceil_div(n, kScanTile);
-    scan_block_sums_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums);
-    scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n_blocks);
-    scan_offsets_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, n_blocks, out, hook);
-}
-
-// ---- two channels at once: count(i) returns (a, b); out_a / out_b receive the two exclusive prefix sums.  One pass
-// over the items instead of two when both sums come from the same inputs (split_packed: left and right word counts).
-template <typename F>
-__global__ void __launch_bounds__(kThreads)
-scan2_block_sums_kernel(F count, unsigned long long n, unsigned long long* __restrict__ sums_a, unsigned long long* __restrict__ sums_b) {
-    __shared__ unsigned long long scratch[32];
-    const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    unsigned long long a = 0, b = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-        if (r0 + i < n) {
-            const ulonglong2 c = count(r0 + i);
-            a += c.x;
-            b += c.y;
-        }
-    a = block_sum_u64(a, scratch);
-    b = block_sum_u64(b, scratch);
-    if (threadIdx.x == 0) {
-        sums_a[blockIdx.x] = a;
-        sums_b[blockIdx.x] = b;
-    }
-}
-
-// one CTA per channel
-static __global__ void __launch_bounds__(1024) scan2_sums_kernel(unsigned long long* __restrict__ sums_a, unsigned long long* __restrict__ sums_b,
-                                                                 unsigned long long n) {
-    unsigned long long* sums = blockIdx.x ? sums_b : sums_a;
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned long long base = 0; base < n; base += blockDim.x) {
-        const unsigned long long i = base + threadIdx.x;
-        const unsigned long long v = i < n ? sums[i] : 0;
-        unsigned long long inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (unsigned)o) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_tot[lane], winc = w;
+        for (int ch = 0; ch < NCH; ++ch) {
+            const unsigned long long w = lane < kWarpsPerBlock ? warp_tot[ch][lane] : 0;
+            unsigned long long winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
                 if (lane >= (unsigned)o) winc += t;
             }
-            warp_tot[lane] = winc - w;
+            if (lane < kWarpsPerBlock) warp_tot[ch][lane] = winc - w;   // exclusive prefix of the warp totals
         }
-        __syncthreads();
-        const unsigned long long carry = carry_s;
-        if (i < n) sums[i] = carry + warp_tot[warp] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[warp] + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) sums[n] = carry_s;
-}
-
-// hook(i, out_a[i], a(i), out_b[i], b(i)) is called once per item, right where its offsets are known
-template <typename F, typename H>
-__global__ void __launch_bounds__(kThreads)
-scan2_offsets_kernel(F count, unsigned long long n, const unsigned long long* __restrict__ sums_a, const unsigned long long* __restrict__ sums_b,
-                     unsigned long long n_blocks, uint64_t* __restrict__ out_a, uint64_t* __restrict__ out_b, H hook) {
-    __shared__ unsigned long long warp_a[32], warp_b[32];
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long r0 = (unsigned long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    ulonglong2 c[kScanItems];
-    unsigned long long sa = 0, sb = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        c[i] = r0 + i < n ? count(r0 + i) : make_ulonglong2(0, 0);
-        sa += c[i].x;
-        sb += c[i].y;
-    }
-    unsigned long long ia = sa, ib = sb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= (unsigned)o) ia += ta, ib += tb;
-    }
-    if (lane == 31) warp_a[warp] = ia, warp_b[warp] = ib;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long wa = lane < kWarpsPerBlock ? warp_a[lane] : 0, wb = lane < kWarpsPerBlock ? warp_b[lane] : 0, xa = wa, xb = wb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
-            if (lane >= (unsigned)o) xa += ta, xb += tb;
-        }
-        if (lane < kWarpsPerBlock) warp_a[lane] = xa - wa, warp_b[lane] = xb - wb;
     }
     __syncthreads();
-    unsigned long long ra = sums_a[blockIdx.x] + warp_a[warp] + ia - sa, rb = sums_b[blockIdx.x] + warp_b[warp] + ib - sb;
+    unsigned long long base[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) base[ch] = sums[ch * (n_blocks + 1) + blockIdx.x] + warp_tot[ch][warp];
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
-        if (r0 + i < n) {
-            out_a[r0 + i] = ra;
-            out_b[r0 + i] = rb;
-            hook(r0 + i, ra, c[i].x, rb, c[i].y);
+        const unsigned long long r = scan_item(i);
+        if (r < n) {
+            out_a[r] = base[0] + excl[i][0];
+            if constexpr (NCH == 2) {
+                out_b[r] = base[1] + excl[i][1];
+                hook(r, base[0] + excl[i][0], c[i][0], base[1] + excl[i][1], c[i][1]);
+            } else {
+                hook(r, base[0] + excl[i][0], c[i][0]);
+            }
         }
-        ra += c[i].x;
-        rb += c[i].y;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        out_a[n] = sums_a[n_blocks];
-        out_b[n] = sums_b[n_blocks];
+        out_a[n] = sums[n_blocks];
+        if constexpr (NCH == 2) out_b[n] = sums[(n_blocks + 1) + n_blocks];
     }
 }
 
-struct Scan2NoHook {
-    __device__ __forceinline__ void operator()(unsigned long long, unsigned long long, unsigned long long, unsigned long long,
-                                               unsigned long long) const {}
-};
-
+// bytes of scratch (`sums`) the scans need for n items
+static inline size_t scan_scratch_bytes(size_t n) { return (ceil_div(n ? n : 1, kScanTile) + 1) * sizeof(unsigned long long); }
 static inline size_t scan2_scratch_bytes(size_t n) { return 2 * scan_scratch_bytes(n); }
 
-template <typename F, typename H = Scan2NoHook>
-static void launch_exclusive_scan2(F count, size_t n, unsigned long long* sums, uint64_t* out_a, uint64_t* out_b, cudaStream_t s, H hook = H()) {
+template <int NCH, typename F, typename H>
+static void launch_scan_impl(F count, size_t n, unsigned long long* sums, uint64_t* out_a, uint64_t* out_b, cudaStream_t s, H hook) {
     const unsigned long long n_blocks = ceil_div(n, kScanTile);
-    unsigned long long* sums_b = sums + n_blocks + 1;
-    scan2_block_sums_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, sums_b);
-    scan2_sums_kernel<<<2, 1024, 0, s>>>(sums, sums_b, n_blocks);
-    scan2_offsets_kernel<<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, sums_b, n_blocks, out_a, out_b, hook);
+    scan_block_sums_kernel<NCH><<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, n_blocks, sums);
+    scan_sums_kernel<<<NCH, 1024, 0, s>>>(sums, n_blocks);
+    scan_offsets_kernel<NCH><<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, n_blocks, out_a, out_b, hook);
+}
+
+// out[i] = sum of count(j), j < i, for i in [0, n]; n >= 1
+template <typename F, typename H = ScanNoHook>
+static void launch_exclusive_scan(F count, size_t n, unsigned long long* sums, uint64_t* out, cudaStream_t s, H hook = H()) {
+    launch_scan_impl<1>(count, n, sums, out, nullptr, s, hook);
+}
+
+// two channels: count(i) returns (a, b) as a ulonglong2
+template <typename F, typename H = ScanNoHook>
+static void launch_exclusive_scan2(F count, size_t n, unsigned long long* sums, uint64_t* out_a, uint64_t* out_b, cudaStream_t s,
+                                   H hook = H()) {
+    launch_scan_impl<2>(count, n, sums, out_a, out_b, s, hook);
 }
 
 }  // namespace bn

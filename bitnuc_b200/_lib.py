@@ -64,6 +64,9 @@ PROTOTYPES = {
     "bn_split_packed_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bn_kmers": (_int, [_vp, _vp, _sz, _u32, _vp, C.POINTER(_sz), _errp]),
     "bn_kmers_dev": (_int, [_vp, _vp, _vp, _sz, _u32, _vp, _vp]),
+    "bn_kmers_batch": (_int, [_vp, _vp, _vp, _sz, _u32, _vp, _sz, _vp, _errp]),
+    "bn_kmers_batch_scratch_bytes": (_sz, [_sz, _sz]),
+    "bn_kmers_batch_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _u32, _vp, _vp, _vp, _vp]),
     "bn_slice_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _errp]),
     "bn_get_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _errp]),
     "bn_slice_batch_scratch_bytes": (_sz, [_sz]),

@@ -390,3 +390,26 @@ def kmers(seq, k: int, ctx: Context | None = None) -> np.ndarray:
         raise e
     raise_for(rc, err)
     return out[: n_out.value]
+
+
+def kmers_batch(data, offsets, k: int, ctx: Context | None = None):
+    """``kmers`` per read of a batch ``data[offsets[r]:offsets[r+1]]``: (words, out_offsets).  Windows never cross a
+    read; a read shorter than ``k`` has none and is never validated.  Raises the error of the first failing window in
+    (read, position) order, with ``.record`` / ``.position`` / ``.offset``."""
+    ctx = ctx or default_context()
+    a, off = _u8(data), _u64(offsets)
+    n = off.size - 1
+    if n < 0 or k <= 0:
+        raise ValueError("offsets needs n_reads + 1 entries; window size must be non-zero")
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    cap = int(np.maximum(lens - k + 1, 0).sum()) if n else 0
+    out = np.empty(max(1, cap), dtype=np.uint64)
+    oo = np.zeros(n + 1, dtype=np.uint64)
+    err = BnError()
+    rc = ctx.lib.bn_kmers_batch(ctx.handle, _p(a), _p(off), n, k, _p(out), cap, _p(oo), C.byref(err))
+    if rc == 1:
+        e = NucleotideError.InvalidBase(err.base)
+        e.record, e.position, e.offset = int(err.record), int(err.b), int(err.offset)
+        raise e
+    raise_for(rc, err)
+    return out[:cap], oo

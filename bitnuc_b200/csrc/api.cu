@@ -405,6 +405,18 @@ int bn_kmers_dev(bn_ctx* ctx, void* stream, const uint8_t* d_seq, size_t n, uint
     return BN_OK;
 }
 
+size_t bn_kmers_batch_scratch_bytes(size_t n_reads, size_t n_bytes) { return bn::kmer_windows_batch_scratch_bytes(n_reads, n_bytes); }
+
+int bn_kmers_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads, size_t n_bytes, uint32_t k,
+                       uint64_t* d_out, uint64_t* d_out_offsets, uint64_t* d_status, void* d_scratch) {
+    if (!ctx || !d_status || !d_out_offsets || k == 0 || (n_reads && (!d_offsets || !d_scratch))) return BN_ERR_ARGUMENT;
+    if (k > 32) return BN_SEQUENCE_TOO_LONG;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_kmer_windows_batch(ctx->di, d_bytes, d_offsets, n_reads, n_bytes, k, d_out, d_out_offsets,
+                                            reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
+    return BN_OK;
+}
+
 size_t bn_slice_batch_scratch_bytes(size_t nq) { return bn::slice_batch_scratch_bytes(nq); }
 
 int bn_slice_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
@@ -1043,6 +1055,59 @@ int bn_kmers(bn_ctx* ctx, const uint8_t* seq, size_t n, uint32_t k, uint64_t* ou
         return BN_INVALID_BASE;
     }
     if (n_out) *n_out = n_win;
+    return set_err(err, BN_OK);
+}
+
+int bn_kmers_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, size_t n_reads, uint32_t k, uint64_t* out, size_t out_cap,
+                   uint64_t* out_offsets, bn_error_t* err) {
+    if (!ctx || !out_offsets || k == 0 || (n_reads && !offsets)) return set_err(err, BN_ERR_ARGUMENT);
+    out_offsets[0] = 0;
+    if (n_reads == 0) return set_err(err, BN_OK);
+    size_t total = 0;
+    for (size_t r = 0; r < n_reads; ++r) {
+        if (offsets[r + 1] < offsets[r]) return set_err(err, BN_ERR_ARGUMENT);
+        const uint64_t len = offsets[r + 1] - offsets[r];
+        if (len >= k) {
+            if (k > 32) {  // the first read with a window fails on its first window (naive.rs:5-7)
+                set_err(err, BN_SEQUENCE_TOO_LONG, k);
+                if (err) err->record = r;
+                return BN_SEQUENCE_TOO_LONG;
+            }
+            total += len - k + 1;
+        }
+    }
+    const uint64_t lo = offsets[0], hi = offsets[n_reads];
+    if (total > out_cap || (total && (!bytes || !out))) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const size_t phase = lo & 15u;  // staged at the same 16-byte phase as bytes + lo, so the offsets are used unchanged
+    BN_CUDA(ensure(ctx->slot[0], (hi - lo) + phase + 16));
+    BN_CUDA(ensure(ctx->slot[1], (n_reads + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[2], total * 8 + 8));
+    BN_CUDA(ensure(ctx->slot[3], (n_reads + 1) * 8));
+    BN_CUDA(ensure(ctx->slot[4], bn::kmer_windows_batch_scratch_bytes(n_reads, hi - lo)));
+    uint8_t* d_bytes = static_cast<uint8_t*>(ctx->slot[0].p) + phase;
+    if (hi > lo) BN_CUDA(cudaMemcpyAsync(d_bytes, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_kmer_windows_batch(ctx->di, d_bytes - lo, static_cast<const uint64_t*>(ctx->slot[1].p), n_reads, hi - lo, k,
+                                          static_cast<uint64_t*>(ctx->slot[2].p), static_cast<uint64_t*>(ctx->slot[3].p), ctx->d_words + 8,
+                                          ctx->slot[4].p, st));
+    BN_CUDA(cudaMemcpyAsync(out_offsets, ctx->slot[3].p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total) BN_CUDA(cudaMemcpyAsync(out, ctx->slot[2].p, total * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 8, ctx->d_words + 8, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long key = ctx->h_words[8];
+    if (key != kNoError) {
+        invalid_base(err, key, 0);
+        if (err) {
+            const uint64_t off = key >> 8;
+            const size_t r = (size_t)(std::upper_bound(offsets, offsets + n_reads + 1, off) - offsets) - 1;
+            err->record = r;
+            err->b = off - offsets[r];
+        }
+        return BN_INVALID_BASE;
+    }
     return set_err(err, BN_OK);
 }
 

@@ -66,6 +66,11 @@ cudaError_t launch_get_batch(const DeviceInfo& di, const uint64_t* d_words, cons
 cudaError_t launch_kmer_windows(const DeviceInfo& di, const uint8_t* d_seq, size_t n, uint32_t k, uint64_t* d_out,
                                 unsigned long long* d_status, cudaStream_t s);
 
+size_t kmer_windows_batch_scratch_bytes(size_t n_reads, size_t n_bytes);
+cudaError_t launch_kmer_windows_batch(const DeviceInfo& di, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads, size_t n_bytes,
+                                      uint32_t k, uint64_t* d_out, uint64_t* d_out_offsets, unsigned long long* d_status, void* d_scratch,
+                                      cudaStream_t s);
+
 // synth.cu
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,
                                size_t n_words, uint64_t* d_out, cudaStream_t s);

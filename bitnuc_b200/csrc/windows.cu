@@ -13,6 +13,7 @@
 // first invalid byte of the sequence, so the status word is the usual min(offset << 8 | byte).
 #include "common.cuh"
 #include "launch.cuh"
+#include "scan.cuh"
 
 namespace bn {
 
@@ -68,6 +69,138 @@ kmer_windows_kernel(const uint8_t* __restrict__ seq, unsigned long long n, unsig
         const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
         st_stream_v2(o + i, make_uint2(__funnelshift_r(c0, c1, sh) & mlo, __funnelshift_r(c1, c2, sh) & mhi));
     }
+}
+
+// ============================================================================ per-read windows ==
+// The same for a batch of reads (offset-indexed ASCII, as in encode_batch): out_offsets = exclusive scan of
+// max(0, len - k + 1), windows never cross a read.  Tiles are cut over the INPUT bytes: a CTA owns 4096 consecutive
+// bytes of the batch, packs them (+ the k-1 bytes after them) into a code strip, and every warp walks 1024 of those
+// byte positions 32 at a time (lane = position, so the stores of a warp are consecutive words except across a read
+// end).  A lane finds the read of its first position by a binary search bounded by the tile-owner table (the scan
+// hook notes which read holds the first byte of every tile) and then only advances.
+// Reads shorter than k have no window, so their bytes are never validated (`windows(k)` yields nothing for them).
+
+constexpr int kWinBatchTile = 4096;   // input bytes per CTA
+constexpr int kWinBatchStrip = (kWinBatchTile + 32 + 15 + 15) / 16 + 4;
+
+struct WindowsOfRead {
+    const uint64_t* offsets;
+    unsigned long long k;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long r) const {
+        const unsigned long long len = offsets[r + 1] - offsets[r];
+        return len >= k ? len - k + 1 : 0;
+    }
+};
+
+// scan hook: read r holds bytes [offsets[r], offsets[r+1]); note it as the owner of every byte tile whose first byte it holds
+struct NoteByteTileOwners {
+    const uint64_t* offsets;
+    unsigned long long* tile_owner;
+    unsigned long long max_tiles;
+    __device__ __forceinline__ void operator()(unsigned long long r, unsigned long long, unsigned long long) const {
+        const unsigned long long b0 = offsets[r] - offsets[0], b1 = offsets[r + 1] - offsets[0];
+        for (unsigned long long t = ceil_div(b0, kWinBatchTile); t < max_tiles && t * kWinBatchTile < b1; ++t) tile_owner[t] = r;
+    }
+};
+
+// rare path: report the invalid bytes of the vector at sequence offset `off` that belong to reads with >= k bases
+static __device__ __noinline__ void win_batch_report(uint4 v, long long off, const uint64_t* __restrict__ offsets,
+                                                     unsigned long long n_reads, unsigned k, unsigned long long* status) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        const long long o = off + j;
+        if (byte_is_valid(b) || o < (long long)offsets[0] || o >= (long long)offsets[n_reads]) continue;
+        unsigned long long l = 0, h = n_reads - 1;   // the read holding byte o: the last r with offsets[r] <= o
+        while (l < h) {
+            const unsigned long long mid = l + (h - l + 1) / 2;
+            if (offsets[mid] <= (unsigned long long)o) l = mid; else h = mid - 1;
+        }
+        if (offsets[l + 1] - offsets[l] >= k) report_invalid(status, (unsigned long long)o, b);
+    }
+}
+
+__global__ void __launch_bounds__(kWinThreads)
+kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ offsets, unsigned long long n_reads,
+                          unsigned k, const uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out,
+                          const unsigned long long* __restrict__ tile_owner, unsigned long long n_tiles,
+                          unsigned long long* __restrict__ status) {
+    __shared__ uint32_t codes[kWinBatchStrip];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long b_lo = offsets[0], b_hi = offsets[n_reads];             // the batch's bytes
+    const unsigned long long t_lo = b_lo + (unsigned long long)blockIdx.x * kWinBatchTile;
+    if (t_lo >= b_hi) return;   // the grid is sized from the caller's bound on the byte count
+    n_tiles = ceil_div(b_hi - b_lo, kWinBatchTile);
+    const unsigned long long t_hi = t_lo + kWinBatchTile < b_hi ? t_lo + kWinBatchTile : b_hi;
+    const unsigned long long s_hi = t_hi + k - 1 < b_hi ? t_hi + k - 1 : b_hi;        // the strip also holds the k-1 bytes after the tile
+    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(bytes) + t_lo) & 15u);
+    const long long a0 = (long long)t_lo - mis;                                      // batch offset of the strip's first byte
+    const unsigned nvec = (unsigned)((s_hi - a0 + 15) / 16);
+    for (unsigned v = tid; v < nvec; v += kWinThreads) {
+        const long long off = a0 + 16ll * v;
+        uint4 x;
+        if (off >= (long long)b_lo && (unsigned long long)off + 16 <= b_hi) {
+            x = ld128<LD_NC_NOALLOC>(reinterpret_cast<const uint4*>(bytes + off));
+        } else {  // a vector at the edge of the batch: byte-wise, 'A' outside
+            uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
+            for (int j = 0; j < 16; ++j)
+                if (off + j >= (long long)b_lo && (unsigned long long)(off + j) < b_hi)
+                    w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)bytes[off + j] << (8 * (j & 3)));
+            x = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        uint32_t bad = 0;
+        codes[v] = pack16(x, bad);
+        if (bad & kValidMask) win_batch_report(x, off, offsets, n_reads, k, status);
+    }
+    __syncthreads();
+    // reads of the tile: r_first holds byte t_lo, r_last holds byte t_hi (or is the last read)
+    const unsigned long long r_first = tile_owner[blockIdx.x];
+    const unsigned long long r_last = blockIdx.x + 1 < n_tiles ? tile_owner[blockIdx.x + 1] : n_reads - 1;
+    const uint32_t mlo = k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u;
+    const uint32_t mhi = k >= 32 ? 0xFFFFFFFFu : k <= 16 ? 0u : (1u << (2 * k - 32)) - 1u;
+    unsigned long long p = t_lo + 1024ull * warp + lane;                             // this lane's first byte position
+    if (p >= t_hi) return;
+    unsigned long long r = r_first, hi = r_last;                                     // the last r in [r_first, r_last] with offsets[r] <= p
+    while (r < hi) {
+        const unsigned long long mid = r + (hi - r + 1) / 2;
+        if (__ldg(offsets + mid) <= p) r = mid; else hi = mid - 1;
+    }
+    unsigned long long r_lo = __ldg(offsets + r), r_hi = __ldg(offsets + r + 1), r_out = __ldg(out_offsets + r);
+    const unsigned long long w_end = t_lo + 1024ull * (warp + 1) < t_hi ? t_lo + 1024ull * (warp + 1) : t_hi;
+    for (; p < w_end; p += 32) {
+        while (p >= r_hi) {  // advance to the read holding p (skips empty reads)
+            ++r;
+            r_lo = r_hi;
+            r_hi = __ldg(offsets + r + 1);
+            r_out = __ldg(out_offsets + r);
+        }
+        if (p + k <= r_hi) {  // a whole window of read r starts here
+            const unsigned rel = (unsigned)(p - a0);
+            const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
+            const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
+            st_stream_v2(reinterpret_cast<uint2*>(out + r_out + (p - r_lo)),
+                         make_uint2(__funnelshift_r(c0, c1, sh) & mlo, __funnelshift_r(c1, c2, sh) & mhi));
+        }
+    }
+}
+
+size_t kmer_windows_batch_scratch_bytes(size_t n_reads, size_t n_bytes) {
+    return scan_scratch_bytes(n_reads) + (ceil_div(n_bytes ? n_bytes : 1, kWinBatchTile) + 2) * sizeof(unsigned long long);
+}
+
+cudaError_t launch_kmer_windows_batch(const DeviceInfo&, const uint8_t* d_bytes, const uint64_t* d_offsets, size_t n_reads, size_t n_bytes,
+                                      uint32_t k, uint64_t* d_out, uint64_t* d_out_offsets, unsigned long long* d_status, void* d_scratch,
+                                      cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_status, 0xFF, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    if (n_reads == 0) return cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s);
+    unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
+    unsigned long long* tile_owner = sums + scan_scratch_bytes(n_reads) / sizeof(unsigned long long);
+    const unsigned long long n_tiles = ceil_div(n_bytes, kWinBatchTile);   // the caller's bound on offsets[n] - offsets[0]
+    launch_exclusive_scan(WindowsOfRead{d_offsets, k}, n_reads, sums, d_out_offsets, s, NoteByteTileOwners{d_offsets, tile_owner, n_tiles + 1});
+    if (n_tiles) kmer_windows_batch_kernel<<<(unsigned)n_tiles, kWinThreads, 0, s>>>(d_bytes, d_offsets, n_reads, k, d_out_offsets, d_out,
+                                                                                      tile_owner, n_tiles, d_status);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_kmer_windows(const DeviceInfo&, const uint8_t* d_seq, size_t n, uint32_t k, uint64_t* d_out,

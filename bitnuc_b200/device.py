@@ -241,6 +241,22 @@ def kmers(seq: torch.Tensor, k: int, out: torch.Tensor | None = None, status: St
     return out, status
 
 
+def kmers_batch(data: torch.Tensor, offsets: torch.Tensor, k: int, out_words: int | None = None, status: Status | None = None):
+    """Per-read k-mer windows on the device: (words int64[out_words], out_offsets int64[n+1], status)."""
+    ctx = _ctx_for(data)
+    n, dev = offsets.numel() - 1, data.device
+    out = torch.empty(data.numel() if out_words is None else out_words, dtype=torch.int64, device=dev)
+    oo = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(ctx.lib.bn_kmers_batch_scratch_bytes(n, data.numel()), dtype=torch.uint8, device=dev)
+    status = status or Status(dev)
+    rc = ctx.lib.bn_kmers_batch_dev(ctx.handle, _stream(), _ptr(data), _ptr(offsets), n, data.numel(), k, _ptr(out), _ptr(oo),
+                                    _ptr(status.word), _ptr(scratch))
+    if rc == 2:
+        raise _lib.NucleotideError.SequenceTooLong(k)
+    raise_for(rc)
+    return out, oo, status
+
+
 class QueryStatus:
     """Device-side status of ``slice_batch`` / ``get_batch``: the smallest failing query index."""
 

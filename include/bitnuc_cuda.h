@@ -160,6 +160,13 @@ int bn_split_packed_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, co
  * (slice::windows panics) -> BN_ERR_ARGUMENT. */
 int bn_kmers(bn_ctx *ctx, const uint8_t *seq, size_t n, uint32_t k, uint64_t *out, size_t *n_out, bn_error_t *err);
 
+/* The same per read of a batch (reads = bytes[offsets[r] .. offsets[r+1]), as in bn_encode_batch): windows never cross
+ * a read, a read shorter than k has none (and its bytes are never looked at).  out receives the windows of all reads
+ * back to back (out_cap words available), out_offsets[n_reads+1] the exclusive prefix sums of max(0, len - k + 1).
+ * The first failing window in (read, position) order -> BN_INVALID_BASE (err->record = the read, err->b = the byte's
+ * position inside it, err->offset = its offset in bytes); out_cap too small -> BN_ERR_ARGUMENT. */
+int bn_kmers_batch(bn_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, size_t n_reads, uint32_t k, uint64_t *out, size_t out_cap, uint64_t *out_offsets, bn_error_t *err);
+
 /* PackedSequence::slice over a batch of queries (src/sequence.rs:198-212): query q = bases [q_start[q], q_end[q]) of
  * read q_read[q] (lens[r] bases at words[word_offsets[r]]).  out receives the upper-case ASCII of all queries back to
  * back (out_cap bytes available), out_offsets[nq+1] the exclusive prefix sums of the range lengths.
@@ -203,6 +210,11 @@ int bn_encode_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const
  * d_scratch needs bn_split_packed_scratch_bytes(n_reads) bytes. */
 size_t bn_split_packed_scratch_bytes(size_t n_reads);
 int bn_split_packed_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, const uint64_t *d_idx, size_t n_reads, uint64_t *d_left, uint64_t *d_left_offsets, uint64_t *d_right, uint64_t *d_right_offsets, uint64_t *d_status, void *d_scratch);
+
+/* n_bytes = the bytes the reads span (or an upper bound); d_out needs sum(max(0, len - k + 1)) <= n_bytes words,
+ * d_scratch bn_kmers_batch_scratch_bytes(n_reads, n_bytes) bytes; status word as in bn_encode_batch_dev. */
+size_t bn_kmers_batch_scratch_bytes(size_t n_reads, size_t n_bytes);
+int bn_kmers_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const uint64_t *d_offsets, size_t n_reads, size_t n_bytes, uint32_t k, uint64_t *d_out, uint64_t *d_out_offsets, uint64_t *d_status, void *d_scratch);
 
 /* d_status (device uint64_t) receives the smallest failing query index, or UINT64_MAX; failing queries produce no
  * bytes (slice) / a 0 byte (get).  d_out needs the sum of the valid range lengths; d_scratch needs

@@ -68,6 +68,9 @@ extern "C" {
     pub fn bn_split_packed_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_words: *const u64, d_word_offsets: *const u64, d_lens: *const u64, d_idx: *const u64, n_reads: usize, d_left: *mut u64, d_left_offsets: *mut u64, d_right: *mut u64, d_right_offsets: *mut u64, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
     pub fn bn_kmers(ctx: *mut bn_ctx, seq: *const u8, n: usize, k: u32, out: *mut u64, n_out: *mut usize, err: *mut bn_error_t) -> c_int;
     pub fn bn_kmers_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_seq: *const u8, n: usize, k: u32, d_out: *mut u64, d_status: *mut u64) -> c_int;
+    pub fn bn_kmers_batch(ctx: *mut bn_ctx, bytes: *const u8, offsets: *const u64, n_reads: usize, k: u32, out: *mut u64, out_cap: usize, out_offsets: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_kmers_batch_scratch_bytes(n_reads: usize, n_bytes: usize) -> usize;
+    pub fn bn_kmers_batch_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_bytes: *const u8, d_offsets: *const u64, n_reads: usize, n_bytes: usize, k: u32, d_out: *mut u64, d_out_offsets: *mut u64, d_status: *mut u64, d_scratch: *mut c_void) -> c_int;
     pub fn bn_slice_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, n_reads: usize, q_read: *const u64, q_start: *const u64, q_end: *const u64, nq: usize, out: *mut u8, out_cap: usize, out_offsets: *mut u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_get_batch(ctx: *mut bn_ctx, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, n_reads: usize, q_read: *const u64, q_index: *const u64, nq: usize, out: *mut u8, err: *mut bn_error_t) -> c_int;
     pub fn bn_slice_batch_scratch_bytes(nq: usize) -> usize;

@@ -95,3 +95,45 @@ def test_split_slice_kmers_fuzz(bn, seed):
             got = bn.kmers(long_seq, k)
             pick = rng.integers(0, long_seq.size - k + 1, 50)
             assert [int(got[i]) for i in pick] == [oracle.as_2bit(long_seq[i : i + k]) for i in pick]
+
+
+@pytest.mark.parametrize("kind", ["tile_edges", "empties", "one_giant", "tiny", "heavy_tail"])
+@pytest.mark.parametrize("k", [1, 16, 21, 32])
+def test_kmers_batch_fuzz(bn, kind, k):
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(31 * k + len(kind))
+    n = int(rng.integers(1, 300))
+    lens = _lens(rng, kind, n).astype(np.int64) % 20_000
+    lead = int(rng.integers(0, 40))
+    offsets = (lead + np.concatenate([[0], np.cumsum(lens)])).astype(np.uint64)
+    data = ACGT[rng.integers(0, 8, int(offsets[-1]) + 7)]
+    words, oo = bn.kmers_batch(data, offsets, k)
+    exp_oo = np.concatenate([[0], np.cumsum(np.maximum(lens - k + 1, 0))]).astype(np.uint64)
+    assert np.array_equal(oo, exp_oo) and words.size == int(exp_oo[-1])
+    for r in rng.integers(0, n, 25):   # per read: the single-sequence kernel (itself checked against the as_2bit loop) and the oracle
+        seq = data[int(offsets[r]) : int(offsets[r + 1])]
+        got = words[int(oo[r]) : int(oo[r + 1])]
+        assert np.array_equal(got, bn.kmers(seq, k))
+        for i in rng.integers(0, max(1, got.size), 5):
+            if got.size:
+                assert int(got[i]) == oracle.as_2bit(seq[i : i + k])
+    d_words, d_oo, st = dv.kmers_batch(torch.from_numpy(data).cuda(), torch.from_numpy(offsets.view(np.int64)).cuda(), k)
+    st.check()
+    assert np.array_equal(d_oo.cpu().numpy().view(np.uint64), oo)
+    assert np.array_equal(d_words[: words.size].cpu().numpy().view(np.uint64), words)
+    # an invalid byte in a read that has windows is reported; in a read shorter than k it is not even looked at
+    bad = data.copy()
+    short = np.flatnonzero((lens > 0) & (lens < k))
+    for r in short:
+        bad[int(offsets[r])] = ord("N")
+    w2, _ = bn.kmers_batch(bad, offsets, k)
+    assert np.array_equal(w2, words)
+    full = np.flatnonzero(lens >= k)
+    if full.size:
+        r = int(rng.choice(full))
+        pos = int(rng.integers(0, lens[r]))
+        bad[int(offsets[r]) + pos] = ord("n")
+        with pytest.raises(bn.NucleotideError) as ei:
+            bn.kmers_batch(bad, offsets, k)
+        assert ei.value.key() == ("InvalidBase", ord("n")) and (ei.value.record, ei.value.position) == (r, pos)

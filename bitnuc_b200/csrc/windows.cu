@@ -82,6 +82,7 @@ kmer_windows_kernel(const uint8_t* __restrict__ seq, unsigned long long n, unsig
 
 constexpr int kWinBatchTile = 4096;   // input bytes per CTA
 constexpr int kWinBatchStrip = (kWinBatchTile + 32 + 15 + 15) / 16 + 4;
+constexpr int kWinBatchReads = 512;   // reads of a tile whose offsets are kept in shared memory
 
 struct WindowsOfRead {
     const uint64_t* offsets;
@@ -126,6 +127,8 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
                           const unsigned long long* __restrict__ tile_owner, unsigned long long n_tiles,
                           unsigned long long* __restrict__ status) {
     __shared__ uint32_t codes[kWinBatchStrip];
+    __shared__ long long s_start[kWinBatchReads + 1];
+    __shared__ unsigned long long s_out[kWinBatchReads];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long b_lo = offsets[0], b_hi = offsets[n_reads];             // the batch's bytes
     const unsigned long long t_lo = b_lo + (unsigned long long)blockIdx.x * kWinBatchTile;
@@ -158,28 +161,70 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
     const unsigned long long r_last = blockIdx.x + 1 < n_tiles ? tile_owner[blockIdx.x + 1] : n_reads - 1;
     const uint32_t mlo = k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u;
     const uint32_t mhi = k >= 32 ? 0xFFFFFFFFu : k <= 16 ? 0u : (1u << (2 * k - 32)) - 1u;
+    const unsigned long long w_end = t_lo + 1024ull * (warp + 1) < t_hi ? t_lo + 1024ull * (warp + 1) : t_hi;
     unsigned long long p = t_lo + 1024ull * warp + lane;                             // this lane's first byte position
-    if (p >= t_hi) return;
+    const uint2 keep = make_uint2(mlo, mhi);
+    if (r_last - r_first < (unsigned long long)kWinBatchReads) {
+        // the tile's reads fit the shared table: starts (relative to the tile, may be negative for the first read)
+        // and output offsets are fetched once, coalesced; lanes then search and advance in shared memory
+        const unsigned nr = (unsigned)(r_last - r_first) + 1;
+        for (unsigned i = tid; i <= nr; i += kWinThreads) {
+            s_start[i] = (long long)(__ldg(offsets + r_first + i) - t_lo);
+            if (i < nr) s_out[i] = __ldg(out_offsets + r_first + i);
+        }
+        __syncthreads();
+        if (p >= w_end) return;
+        int q = (int)(p - t_lo);                                                     // byte position relative to the tile: < 4096
+        unsigned i = 0, hi = nr - 1;                                                 // the last i with s_start[i] <= q
+        while (i < hi) {
+            const unsigned mid = i + (hi - i + 1) / 2;
+            if (s_start[mid] <= (long long)q) i = mid; else hi = mid - 1;
+        }
+        // per read: its end relative to the tile (clamped: only compared with positions < 4096) and the address of
+        // the window that would start at tile position 0, so that a window costs one 64-bit add for its address
+        auto end_of = [&](unsigned j) { const long long e = s_start[j + 1]; return e > (1 << 30) ? (1 << 30) : (int)e; };
+        int r_hi = end_of(i);
+        uint64_t* obase = out + s_out[i] - s_start[i];
+        const int q_end = (int)(w_end - t_lo), kk = (int)k;
+        const unsigned mis2 = mis;
+#pragma unroll 4
+        for (; q < q_end; q += 32) {
+            while (q >= r_hi) {  // advance to the read holding this byte (skips empty reads)
+                ++i;
+                r_hi = end_of(i);
+                obase = out + s_out[i] - s_start[i];
+            }
+            if (q + kk <= r_hi) {  // a whole window of that read starts here
+                const unsigned rel = (unsigned)q + mis2;
+                const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
+                const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
+                st_stream_v2(reinterpret_cast<uint2*>(obase + q),
+                             make_uint2(__funnelshift_r(c0, c1, sh) & keep.x, __funnelshift_r(c1, c2, sh) & keep.y));
+            }
+        }
+        return;
+    }
+    // more reads in the tile than the table holds (runs of empty or tiny reads): the same walk on global memory
+    if (p >= w_end) return;
     unsigned long long r = r_first, hi = r_last;                                     // the last r in [r_first, r_last] with offsets[r] <= p
     while (r < hi) {
         const unsigned long long mid = r + (hi - r + 1) / 2;
         if (__ldg(offsets + mid) <= p) r = mid; else hi = mid - 1;
     }
     unsigned long long r_lo = __ldg(offsets + r), r_hi = __ldg(offsets + r + 1), r_out = __ldg(out_offsets + r);
-    const unsigned long long w_end = t_lo + 1024ull * (warp + 1) < t_hi ? t_lo + 1024ull * (warp + 1) : t_hi;
     for (; p < w_end; p += 32) {
-        while (p >= r_hi) {  // advance to the read holding p (skips empty reads)
+        while (p >= r_hi) {
             ++r;
             r_lo = r_hi;
             r_hi = __ldg(offsets + r + 1);
             r_out = __ldg(out_offsets + r);
         }
-        if (p + k <= r_hi) {  // a whole window of read r starts here
+        if (p + k <= r_hi) {
             const unsigned rel = (unsigned)(p - a0);
             const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
             const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
             st_stream_v2(reinterpret_cast<uint2*>(out + r_out + (p - r_lo)),
-                         make_uint2(__funnelshift_r(c0, c1, sh) & mlo, __funnelshift_r(c1, c2, sh) & mhi));
+                         make_uint2(__funnelshift_r(c0, c1, sh) & keep.x, __funnelshift_r(c1, c2, sh) & keep.y));
         }
     }
 }

@@ -264,6 +264,35 @@ def next_rows(scale, reps):
     report(f"kmers (all 31-mers of one sequence) n={n}", ms, n + 8 * (n - 30), n - 30, "kmers")
     del asc, out, words
 
+    # per-read windows: 20 M reads of 100-151 bp, k = 31 (windows never cross a read)
+    n_reads = int(20_000_000 * scale)
+    lens = (100 + synth.splitmix64(np.arange(n_reads, dtype=np.uint64) + np.uint64(SEED + 6)) % np.uint64(52)).astype(np.uint64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    total = int(offsets[-1])
+    data = dv.synth_ascii(SEED, 6, 0, total)
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    n_win = total - 30 * n_reads
+    kout = torch.empty(n_win, dtype=torch.int64, device="cuda")
+    koo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    ctx = dv.api.default_context(0)
+    kscr = torch.empty(ctx.lib.bn_kmers_batch_scratch_bytes(n_reads, total), dtype=torch.uint8, device="cuda")
+    kst = dv.Status("cuda")
+
+    def run_k():
+        dv.raise_for(ctx.lib.bn_kmers_batch_dev(ctx.handle, dv._stream(), dv._ptr(data), dv._ptr(d_off), n_reads, total, 31, dv._ptr(kout),
+                                                dv._ptr(koo), dv._ptr(kst.word), dv._ptr(kscr)))
+
+    ms = timed(run_k, reps)
+    kst.check()
+    assert int(koo[-1].item()) == n_win
+    for r in (0, 3, n_reads - 1):   # against the single-sequence kernel
+        o, ln, w0 = int(offsets[r]), int(lens[r]), int(koo[r].item())
+        ref, st1 = dv.kmers(data[o : o + ln], 31)
+        st1.check()
+        assert torch.equal(kout[w0 : w0 + ln - 30], ref)
+    report(f"kmers per read (k=31) reads={n_reads} x 100-151 bp", ms, total + 8 * n_win + 16 * n_reads, n_win, "kmers")
+    del data, kout, koo, kscr
+
     reads = int(10_000_000 * scale)
     words = dv.synth_words(SEED, 4, 0, 5 * reads)
     wo = torch.arange(reads, dtype=torch.int64, device="cuda") * 5
@@ -271,7 +300,6 @@ def next_rows(scale, reps):
     qr = torch.arange(reads, dtype=torch.int64, device="cuda")
     qs = (qr * 7919) % 101
     qe = qs + 50
-    ctx = dv.api.default_context(0)
     data = torch.empty(50 * reads, dtype=torch.uint8, device="cuda")
     oo = torch.empty(reads + 1, dtype=torch.int64, device="cuda")
     scratch = torch.empty(ctx.lib.bn_slice_batch_scratch_bytes(reads), dtype=torch.uint8, device="cuda")

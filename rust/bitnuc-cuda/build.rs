@@ -31,5 +31,6 @@ fn main() {
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=cudart");
     println!("cargo:rustc-link-lib=stdc++");
+    println!("cargo:rustc-link-lib=dl"); // api.cu resolves cuCtxGetCurrent through dlopen/dlsym
     println!("cargo:rerun-if-changed={}", root.join("include/bitnuc_cuda.h").display());
 }

@@ -7,8 +7,8 @@
 // HBM-bound at (k + 8) bytes per record.  Three layouts per direction:
 //   stride == 32 (padded records, 16-byte aligned): record r is vectors 2r, 2r+1 <-> word r, i.e. the
 //       streaming codec layout with bytes >= k masked;
-//   stride == k (tightly packed, e.g. 31-mers): vectors are packed as in the streaming encode and each
-//       record is assembled from the <= 3 vectors it straddles with warp shuffles + funnel shifts;
+//   stride == k (tightly packed, e.g. 31-mers): a CTA packs its span of records as in the streaming encode into a
+//       shared code strip and cuts each record out of it (three LDS + two funnel shifts);
 //   stride <= 64: the CTA's byte span is staged through shared memory with coalesced 128-bit loads,
 //       then each thread assembles its record with funnel shifts;
 //   anything else: one thread per record with byte accesses (correct, not tuned).
@@ -125,87 +125,59 @@ __device__ __noinline__ void report_vector_invalid(uint4 v, long long vbyte, uns
     }
 }
 
-// one group of <= rpw records [r0, min(r0 + rpw, r_end)) (any position in the buffer, any count)
-__device__ __noinline__ void as_2bit_tight_group_slow(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k,
-                                                      unsigned rpw, unsigned long long r0, unsigned long long r_end,
-                                                      uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned cnt = (unsigned)(r_end - r0 < rpw ? r_end - r0 : rpw);
-    const unsigned long long total = n * k, span0 = r0 * k;
-    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(recs) + span0) & 15u);
-    const long long vbyte = (long long)span0 - mis + 16ll * lane;  // buffer offset of this lane's vector (may be < 0)
-    uint32_t code = 0;
-    if (vbyte < (long long)(span0 + (unsigned long long)cnt * k)) {
-        const uint4 v = (vbyte >= 0 && (unsigned long long)vbyte + 16 <= total)
-                            ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(recs + vbyte))
-                            : load_vector_at_edge(recs, vbyte, total);
-        uint32_t bad = 0;
-        code = pack16(v, bad);
-        if (bad & kValidMask) report_vector_invalid(v, vbyte, status);
-    }
-    __syncwarp();
-    const unsigned rel = mis + lane * k;
-    const unsigned vi = rel >> 4, sh = 2 * (rel & 15u);
-    const uint32_t c0 = __shfl_sync(0xffffffffu, code, vi & 31);
-    const uint32_t c1 = __shfl_sync(0xffffffffu, code, (vi + 1) & 31);
-    const uint32_t c2 = __shfl_sync(0xffffffffu, code, (vi + 2) & 31);
-    if (lane < cnt) {
-        const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-        out[r0 + lane] = (((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh)) & mask;
-    }
-}
-
-// Fast kernel.  A warp owns `rpt` (a multiple of 32, <= 256) consecutive records = one contiguous span of at most
-// 2048 + 15 bytes: up to 5 aligned vectors per lane, all loaded before the first use, packed to 32-bit codes and
-// parked in the warp's own shared-memory strip (no CTA barrier).  Then every lane assembles whole records
-// (three LDS + two funnel shifts each) and the warp stores 32 consecutive words per round, all lanes busy.
-constexpr int kTightMaxRounds = 5;
-constexpr int kTightStrip = 32 * kTightMaxRounds + 4;   // + slack: a record may index two codes past its last vector
-
-__global__ void __launch_bounds__(kKmerThreads, 2)
-as_2bit_tight_kernel(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k, unsigned rpt,
-                     uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
-    __shared__ uint32_t strips[kKmerThreads / 32][kTightStrip];
-    const unsigned lane = threadIdx.x & 31;
-    uint32_t* codes = strips[threadIdx.x >> 5];
-    const unsigned long long warp = (unsigned long long)blockIdx.x * (kKmerThreads / 32) + (threadIdx.x >> 5);
-    const unsigned long long rw = warp * rpt;                                     // first record of the warp
-    if (rw >= n) return;
-    const unsigned cnt = (unsigned)(n - rw < rpt ? n - rw : rpt);
-    const uint8_t* wbase = recs + rw * k;
-    const unsigned m0 = (unsigned)(reinterpret_cast<uintptr_t>(wbase) & 15u);
-    const uint8_t* abase = wbase - m0;                                            // 16-byte aligned
-    const unsigned nvec = (m0 + cnt * k + 15u) / 16u;                             // <= 129
-    if (abase < recs || abase + 16ull * nvec > recs + n * k) {                    // a vector pokes outside the buffer
-        const unsigned rpw = 497u / k < 32u ? 497u / k : 32u;                     // 15 + rpw*k <= 512: one vector per lane
-        for (unsigned g = 0; g < cnt; g += rpw) as_2bit_tight_group_slow(recs, n, k, rpw, rw + g, rw + cnt, out, status);
-        return;
-    }
-    const uint4* src = reinterpret_cast<const uint4*>(abase) + lane;
-    uint4 v[kTightMaxRounds];
+// Pack, then cut: a CTA owns `rpc` consecutive records = one span of <= 64 KiB.  It packs the span as a pure stream
+// (aligned 128-bit loads, U in flight per thread, validated as whole vectors) into a 16 KiB code strip in shared
+// memory, then cuts the records out of the strip -- record j is the 2k-bit field starting 2 * (its byte offset) bits
+// into the strip: three LDS + two funnel shifts -- one record per thread step, consecutive threads -> consecutive
+// output words.  (A per-warp strip with shuffled / warp-private assembly was 83 % of the measured peak, this is
+// 86-88 %; the first version, nine LDS.32 per record from staged raw bytes, 54 %.)
+template <int THREADS, int U, int SPAN_KB = 64>
+__global__ void __launch_bounds__(THREADS)
+as_2bit_tight_kernel(const uint8_t* __restrict__ recs, unsigned long long n, unsigned k, unsigned rpc,
+                         uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
+    __shared__ uint32_t codes[SPAN_KB * 64 + 8];
+    const unsigned tid = threadIdx.x;
+    const unsigned long long r0 = (unsigned long long)blockIdx.x * rpc;
+    const unsigned cnt = (unsigned)(n - r0 < rpc ? n - r0 : rpc);
+    const uint8_t* base = recs + r0 * k;
+    const unsigned m0 = (unsigned)(reinterpret_cast<uintptr_t>(base) & 15u);
+    const uint8_t* abase = base - m0;
+    const unsigned nvec = (m0 + cnt * k + 15u) / 16u;                              // <= 4097
+    const bool interior = abase >= recs && abase + 16ull * nvec <= recs + n * k;
+    const uint4* src = reinterpret_cast<const uint4*>(abase);
+    unsigned v = tid;
+    if (interior) {
+        for (; v + (U - 1) * THREADS < nvec; v += U * THREADS) {
+            uint4 x[U];
 #pragma unroll
-    for (int g = 0; g < kTightMaxRounds; ++g)
-        if (32u * g + lane < nvec) v[g] = ld128<LD_PLAIN>(src + 32 * g);
-#pragma unroll
-    for (int g = 0; g < kTightMaxRounds; ++g) {
-        if (32u * g + lane < nvec) {
+            for (int j = 0; j < U; ++j) x[j] = ld128<LD_NC_NOALLOC>(src + v + j * THREADS);
             uint32_t bad = 0;
-            codes[32 * g + lane] = pack16(v[g], bad);
-            if (bad & kValidMask) report_vector_invalid(v[g], (long long)(abase - recs) + 16ll * (32 * g + lane), status);
+#pragma unroll
+            for (int j = 0; j < U; ++j) codes[v + j * THREADS] = pack16(x[j], bad);
+            if (bad & kValidMask) {
+#pragma unroll 1
+                for (int j = 0; j < U; ++j) report_vector_invalid(x[j], (long long)(abase - recs) + 16ll * (v + j * THREADS), status);
+            }
         }
     }
-    __syncwarp();
+    for (; v < nvec; v += THREADS) {
+        const long long vbyte = (long long)(abase - recs) + 16ll * v;
+        const uint4 x = vbyte >= 0 && (unsigned long long)vbyte + 16 <= n * k ? ld128<LD_NC_NOALLOC>(src + v)
+                                                                              : load_vector_at_edge(recs, vbyte, n * k);
+        uint32_t bad = 0;
+        codes[v] = pack16(x, bad);
+        if (bad & kValidMask) report_vector_invalid(x, vbyte, status);
+    }
+    __syncthreads();
     const uint32_t mlo = k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u;
     const uint32_t mhi = k >= 32 ? 0xFFFFFFFFu : k <= 16 ? 0u : (1u << (2 * k - 32)) - 1u;
-    uint2* o = reinterpret_cast<uint2*>(out + rw);
-    for (unsigned j = lane; j < cnt; j += 32) {
-        const unsigned rel = m0 + j * k;  // byte offset of the record from the span's first vector
+    uint2* o = reinterpret_cast<uint2*>(out + r0);
+#pragma unroll 4
+    for (unsigned j = tid; j < cnt; j += THREADS) {
+        const unsigned rel = m0 + j * k;
         const unsigned vi = rel >> 4, sh = 2 * (rel & 15u);
         const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
-        uint2 w;
-        w.x = __funnelshift_r(c0, c1, sh) & mlo;
-        w.y = __funnelshift_r(c1, c2, sh) & mhi;
-        st_stream_v2(o + j, w);
+        st_stream_v2(o + j, make_uint2(__funnelshift_r(c0, c1, sh) & mlo, __funnelshift_r(c1, c2, sh) & mhi));
     }
 }
 
@@ -377,10 +349,8 @@ cudaError_t launch_as_2bit_batch(const DeviceInfo& di, const uint8_t* d_recs, si
         as_2bit_padded_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(
             reinterpret_cast<const uint4*>(d_recs), reinterpret_cast<uint32_t*>(d_out), n_vec, (int)k, d_status);
     } else if (stride == k) {
-        const unsigned rounds = 64u / k < 2u ? 2u : 64u / k > 8u ? 8u : 64u / k;  // rpt * k <= 2048 bytes per warp
-        const unsigned rpt = 32u * rounds;
-        const unsigned long long warps = ceil_div(n, rpt);
-        as_2bit_tight_kernel<<<(unsigned)ceil_div(warps, kKmerThreads / 32), kKmerThreads, 0, s>>>(d_recs, n, k, rpt, d_out, d_status);
+        const unsigned rpc = (65536u - 32u) / k < 2048u ? ((65536u - 32u) / k) / 256u * 256u : 2048u;   // records per CTA: span <= 64 KiB
+        as_2bit_tight_kernel<256, 4><<<(unsigned)ceil_div(n, rpc), 256, 0, s>>>(d_recs, n, k, rpc, d_out, d_status);
     } else if (stride <= (size_t)kStageMaxStride) {
         as_2bit_staged_kernel<<<(unsigned)ceil_div(n, kStageRecords), kThreads, 0, s>>>(d_recs, n, k, (unsigned)stride, d_out,
                                                                                          d_status);

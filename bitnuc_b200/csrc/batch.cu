@@ -200,13 +200,19 @@ encode_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restric
         }
         __syncthreads();
         // ---- phase 2a: one read per thread; a read's words are consecutive 64-bit windows of the strip, 32 bytes apart
+        // (software-pipelined: the offsets of the thread's next read are in flight while it cuts the current one)
+        unsigned long long c_wo, c_wn, c_rb, c_re;
+        if (m_nw != 0xFFFFFFFFu) {
+            c_wo = m_wo, c_wn = m_wo + m_nw, c_rb = m_rb, c_re = m_rb + m_len;   // fetched before phase 1
+        } else {
+            c_wo = __ldg(word_offsets + r0 + tid), c_wn = __ldg(word_offsets + r0 + tid + 1);
+            c_rb = __ldg(offsets + r0 + tid), c_re = __ldg(offsets + r0 + tid + 1);
+        }
         for (unsigned long long r = r0 + tid; r <= r1; r += kThreads) {
-            unsigned long long wo_r, wo_n, rb, re;
-            if (r == r0 + tid && m_nw != 0xFFFFFFFFu) {
-                wo_r = m_wo, wo_n = m_wo + m_nw, rb = m_rb, re = m_rb + m_len;   // fetched before phase 1
-            } else {
-                wo_r = __ldg(word_offsets + r), wo_n = __ldg(word_offsets + r + 1);
-                rb = __ldg(offsets + r), re = __ldg(offsets + r + 1);
+            const unsigned long long wo_r = c_wo, wo_n = c_wn, rb = c_rb, re = c_re;
+            if (r + kThreads <= r1) {
+                c_wo = __ldg(word_offsets + r + kThreads), c_wn = __ldg(word_offsets + r + kThreads + 1);
+                c_rb = __ldg(offsets + r + kThreads), c_re = __ldg(offsets + r + kThreads + 1);
             }
             const unsigned long long wf = wo_r > w0 ? wo_r : w0, wl = wo_n < w1 ? wo_n : w1;   // its words inside the tile
             if (wf >= wl) continue;

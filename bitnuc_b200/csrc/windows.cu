@@ -127,8 +127,8 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
                           const unsigned long long* __restrict__ tile_owner, unsigned long long n_tiles,
                           unsigned long long* __restrict__ status) {
     __shared__ uint32_t codes[kWinBatchStrip];
-    __shared__ long long s_start[kWinBatchReads + 1];
-    __shared__ unsigned long long s_out[kWinBatchReads];
+    __shared__ int s_end[kWinBatchReads];
+    __shared__ uint64_t* s_obase[kWinBatchReads];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long b_lo = offsets[0], b_hi = offsets[n_reads];             // the batch's bytes
     const unsigned long long t_lo = b_lo + (unsigned long long)blockIdx.x * kWinBatchTile;
@@ -165,37 +165,35 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
     unsigned long long p = t_lo + 1024ull * warp + lane;                             // this lane's first byte position
     const uint2 keep = make_uint2(mlo, mhi);
     if (r_last - r_first < (unsigned long long)kWinBatchReads) {
-        // the tile's reads fit the shared table: starts (relative to the tile, may be negative for the first read)
-        // and output offsets are fetched once, coalesced; lanes then search and advance in shared memory
+        // the tile's reads fit the shared table: per read, its end relative to the tile (clamped: only compared with
+        // positions < 4096) and the address of the window that would start at tile position 0 -- fetched once,
+        // coalesced; lanes then search and advance in shared memory, and a window costs one add for its address
         const unsigned nr = (unsigned)(r_last - r_first) + 1;
-        for (unsigned i = tid; i <= nr; i += kWinThreads) {
-            s_start[i] = (long long)(__ldg(offsets + r_first + i) - t_lo);
-            if (i < nr) s_out[i] = __ldg(out_offsets + r_first + i);
+        for (unsigned i = tid; i < nr; i += kWinThreads) {
+            const long long st = (long long)(__ldg(offsets + r_first + i) - t_lo), en = (long long)(__ldg(offsets + r_first + i + 1) - t_lo);
+            s_end[i] = en > (1 << 30) ? (1 << 30) : (int)en;
+            s_obase[i] = out + __ldg(out_offsets + r_first + i) - st;
         }
         __syncthreads();
         if (p >= w_end) return;
         int q = (int)(p - t_lo);                                                     // byte position relative to the tile: < 4096
-        unsigned i = 0, hi = nr - 1;                                                 // the last i with s_start[i] <= q
+        unsigned i = 0, hi = nr - 1;                                                 // the first i with s_end[i] > q (reads are adjacent)
         while (i < hi) {
-            const unsigned mid = i + (hi - i + 1) / 2;
-            if (s_start[mid] <= (long long)q) i = mid; else hi = mid - 1;
+            const unsigned mid = (i + hi) / 2;
+            if (s_end[mid] > q) hi = mid; else i = mid + 1;
         }
-        // per read: its end relative to the tile (clamped: only compared with positions < 4096) and the address of
-        // the window that would start at tile position 0, so that a window costs one 64-bit add for its address
-        auto end_of = [&](unsigned j) { const long long e = s_start[j + 1]; return e > (1 << 30) ? (1 << 30) : (int)e; };
-        int r_hi = end_of(i);
-        uint64_t* obase = out + s_out[i] - s_start[i];
+        int r_hi = s_end[i];
+        uint64_t* obase = s_obase[i];
         const int q_end = (int)(w_end - t_lo), kk = (int)k;
-        const unsigned mis2 = mis;
-#pragma unroll 4
+#pragma unroll 2
         for (; q < q_end; q += 32) {
             while (q >= r_hi) {  // advance to the read holding this byte (skips empty reads)
                 ++i;
-                r_hi = end_of(i);
-                obase = out + s_out[i] - s_start[i];
+                r_hi = s_end[i];
+                obase = s_obase[i];
             }
             if (q + kk <= r_hi) {  // a whole window of that read starts here
-                const unsigned rel = (unsigned)q + mis2;
+                const unsigned rel = (unsigned)q + mis;
                 const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
                 const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
                 st_stream_v2(reinterpret_cast<uint2*>(obase + q),

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -28,6 +29,10 @@ struct Buffer {
     void* p = nullptr;
     size_t cap = 0;
 };
+struct HostBuffer {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+};
 
 }  // namespace
 
@@ -38,6 +43,7 @@ struct bn_ctx {
     cudaEvent_t stage_done[kStages] = {};
     Buffer stage_in[kStages], stage_out[kStages];
     Buffer stage_aux[kStages][4];                // batch calls: offsets, word offsets, per-read status, scratch
+    HostBuffer hstage_in[kStages][2], hstage_out[kStages];   // pinned bounce buffers for pageable caller memory
     Buffer slot[kSlots];
     unsigned long long* d_words = nullptr;       // 16 device status / accumulator words
     unsigned long long* h_words = nullptr;       // pinned mirror
@@ -114,6 +120,50 @@ cudaError_t ensure(Buffer& b, size_t bytes) {
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e == cudaSuccess) b.cap = want;
     return e;
+}
+
+cudaError_t ensure_host(HostBuffer& b, size_t bytes) {
+    if (bytes <= b.cap) return cudaSuccess;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = (bytes + 4095) & ~(size_t)4095;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) b.cap = want;
+    return e;
+}
+
+// Caller memory that is neither pinned nor device memory: cudaMemcpyAsync on it is staged by the driver through one
+// thread (~10 GB/s here).  The host-pointer calls bounce such buffers through their own pinned stage buffers with a
+// multi-threaded memcpy instead, which keeps the PCIe pipeline fed at several times that rate.
+bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const size_t kMinSlice = 4u << 20;
+    const unsigned t = (unsigned)std::min<size_t>(hw, bytes / kMinSlice);
+    if (t <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = ((bytes + t - 1) / t + 4095) & ~(size_t)4095;
+    std::vector<std::thread> workers;
+    workers.reserve(t - 1);
+    for (unsigned i = 1; i < t; ++i) {
+        const size_t off = i * slice;
+        if (off >= bytes) break;
+        workers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(slice, bytes - off)); });
+    }
+    std::memcpy(dst, src, std::min(slice, bytes));
+    for (auto& w : workers) w.join();
 }
 
 cudaStream_t pick(bn_ctx* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
@@ -198,6 +248,9 @@ void bn_ctx_destroy(bn_ctx* ctx) {
             if (ctx->stage_out[s].p) cudaFree(ctx->stage_out[s].p);
             for (auto& b : ctx->stage_aux[s])
                 if (b.p) cudaFree(b.p);
+            for (auto& b : ctx->hstage_in[s])
+                if (b.p) cudaFreeHost(b.p);
+            if (ctx->hstage_out[s].p) cudaFreeHost(ctx->hstage_out[s].p);
         }
         for (auto& b : ctx->slot)
             if (b.p) cudaFree(b.p);
@@ -481,15 +534,22 @@ int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* 
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t chunk = ctx->chunk;
     const size_t n_chunks = (n + chunk - 1) / chunk;
+    const bool in_pageable = is_pageable(seq), out_pageable = is_pageable(out);
     unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
     for (int s = 0; s < kStages && (size_t)s < n_chunks; ++s) {
         BN_CUDA(ensure(ctx->stage_in[s], std::min(chunk, n)));
         BN_CUDA(ensure(ctx->stage_out[s], (std::min(chunk, n) + 31) / 32 * 8));
+        if (in_pageable) BN_CUDA(ensure_host(ctx->hstage_in[s][0], std::min(chunk, n)));
+        if (out_pageable) BN_CUDA(ensure_host(ctx->hstage_out[s], (std::min(chunk, n) + 31) / 32 * 8));
     }
     auto retire = [&](size_t c) -> cudaError_t {
         const int s = (int)(c % kStages);
         cudaError_t e = cudaEventSynchronize(ctx->stage_done[s]);
         if (e != cudaSuccess) return e;
+        if (out_pageable) {
+            const size_t off = c * chunk, len = std::min(chunk, n - off);
+            parallel_memcpy(out + off / 32, ctx->hstage_out[s].p, (len + 31) / 32 * 8);
+        }
         const unsigned long long key = ctx->h_words[s];
         if (key != kNoError) {
             const unsigned long long global = (((key >> 8) + (unsigned long long)c * chunk) << 8) | (key & 0xFFu);
@@ -504,10 +564,16 @@ int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* 
             const int s = (int)(c % kStages);
             cudaStream_t st = ctx->stage_stream[s];
             unsigned long long* d_status = ctx->d_words + s;
-            BN_CUDA(cudaMemcpyAsync(ctx->stage_in[s].p, seq + off, len, cudaMemcpyHostToDevice, st));
+            const void* src = seq + off;
+            if (in_pageable) {
+                parallel_memcpy(ctx->hstage_in[s][0].p, seq + off, len);
+                src = ctx->hstage_in[s][0].p;
+            }
+            BN_CUDA(cudaMemcpyAsync(ctx->stage_in[s].p, src, len, cudaMemcpyHostToDevice, st));
             BN_CUDA(bn::launch_encode(ctx->di, static_cast<const uint8_t*>(ctx->stage_in[s].p), len,
                                       static_cast<uint64_t*>(ctx->stage_out[s].p), d_status, st));
-            BN_CUDA(cudaMemcpyAsync(out + off / 32, ctx->stage_out[s].p, (len + 31) / 32 * 8, cudaMemcpyDeviceToHost, st));
+            BN_CUDA(cudaMemcpyAsync(out_pageable ? ctx->hstage_out[s].p : static_cast<void*>(out + off / 32), ctx->stage_out[s].p,
+                                    (len + 31) / 32 * 8, cudaMemcpyDeviceToHost, st));
             BN_CUDA(cudaMemcpyAsync(ctx->h_words + s, d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
             ++issued;
@@ -535,23 +601,37 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t chunk = ctx->chunk;
     const size_t n_chunks = (n_bases + chunk - 1) / chunk;
+    const bool in_pageable = is_pageable(words), out_pageable = is_pageable(out);
     for (int s = 0; s < kStages && (size_t)s < n_chunks; ++s) {
         BN_CUDA(ensure(ctx->stage_out[s], std::min(chunk, n_bases)));
         BN_CUDA(ensure(ctx->stage_in[s], (std::min(chunk, n_bases) + 31) / 32 * 8));
+        if (in_pageable) BN_CUDA(ensure_host(ctx->hstage_in[s][0], (std::min(chunk, n_bases) + 31) / 32 * 8));
+        if (out_pageable) BN_CUDA(ensure_host(ctx->hstage_out[s], std::min(chunk, n_bases)));
     }
+    auto retire = [&](size_t c) -> cudaError_t {  // yields the core while waiting (blocking-sync event)
+        const int s = (int)(c % kStages);
+        cudaError_t e = cudaEventSynchronize(ctx->stage_done[s]);
+        if (e == cudaSuccess && out_pageable) parallel_memcpy(out + c * chunk, ctx->hstage_out[s].p, std::min(chunk, n_bases - c * chunk));
+        return e;
+    };
     for (size_t c = 0; c < n_chunks; ++c) {
         const size_t off = c * chunk, len = std::min(chunk, n_bases - off);
         const int s = (int)(c % kStages);
         cudaStream_t st = ctx->stage_stream[s];
-        if (c >= (size_t)kStages) BN_CUDA(cudaEventSynchronize(ctx->stage_done[s]));
-        BN_CUDA(cudaMemcpyAsync(ctx->stage_in[s].p, words + off / 32, (len + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
+        if (c >= (size_t)kStages) BN_CUDA(retire(c - kStages));
+        const void* src = words + off / 32;
+        if (in_pageable) {
+            parallel_memcpy(ctx->hstage_in[s][0].p, src, (len + 31) / 32 * 8);
+            src = ctx->hstage_in[s][0].p;
+        }
+        BN_CUDA(cudaMemcpyAsync(ctx->stage_in[s].p, src, (len + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
         BN_CUDA(bn::launch_decode(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), len,
                                   static_cast<uint8_t*>(ctx->stage_out[s].p), st));
-        BN_CUDA(cudaMemcpyAsync(out + off, ctx->stage_out[s].p, len, cudaMemcpyDeviceToHost, st));
+        BN_CUDA(cudaMemcpyAsync(out_pageable ? ctx->hstage_out[s].p : static_cast<void*>(out + off), ctx->stage_out[s].p, len,
+                                cudaMemcpyDeviceToHost, st));
         BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
     }
-    for (size_t c = n_chunks > (size_t)kStages ? n_chunks - kStages : 0; c < n_chunks; ++c)  // yield the core while waiting
-        BN_CUDA(cudaEventSynchronize(ctx->stage_done[c % kStages]));
+    for (size_t c = n_chunks > (size_t)kStages ? n_chunks - kStages : 0; c < n_chunks; ++c) BN_CUDA(retire(c));
     return set_err(err, BN_OK);
 }
 
@@ -596,6 +676,26 @@ inline size_t units_per_chunk(const bn_ctx* ctx, size_t bytes_per_unit, size_t m
     return u ? u : multiple;
 }
 
+// Pageable caller memory goes through the stage's pinned bounce buffers (see is_pageable): the source of an upload,
+// and the destination of a download (copied out to the caller by `unbounce` once the chunk has retired).
+inline cudaError_t bounce_in(bn_ctx* ctx, int s, int which, const void*& src, size_t bytes, bool pageable) {
+    if (!pageable || bytes == 0) return cudaSuccess;
+    cudaError_t e = ensure_host(ctx->hstage_in[s][which], bytes);
+    if (e != cudaSuccess) return e;
+    parallel_memcpy(ctx->hstage_in[s][which].p, src, bytes);
+    src = ctx->hstage_in[s][which].p;
+    return cudaSuccess;
+}
+inline cudaError_t bounce_out(bn_ctx* ctx, int s, void*& dst, size_t bytes, bool pageable) {
+    if (!pageable || bytes == 0) return cudaSuccess;
+    cudaError_t e = ensure_host(ctx->hstage_out[s], bytes);
+    if (e == cudaSuccess) dst = ctx->hstage_out[s].p;
+    return e;
+}
+inline void unbounce(bn_ctx* ctx, int s, void* user_dst, size_t bytes, bool pageable) {
+    if (pageable && bytes) parallel_memcpy(user_dst, ctx->hstage_out[s].p, bytes);
+}
+
 }  // namespace
 
 extern "C" {
@@ -608,6 +708,7 @@ int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, siz
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t per = units_per_chunk(ctx, stride, 64), n_chunks = (n + per - 1) / per;
+    const bool in_pg = is_pageable(recs), out_pg = is_pageable(out);
     unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
     const int rc = run_pipeline(
         ctx, n_chunks, err,
@@ -615,13 +716,18 @@ int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, siz
             const size_t r0 = c * per, cnt = std::min(per, n - r0), in_bytes = k ? (cnt - 1) * stride + k : 0;
             BN_TRY(ensure(ctx->stage_in[s], in_bytes ? in_bytes : 1));
             BN_TRY(ensure(ctx->stage_out[s], cnt * 8));
-            if (in_bytes) BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, recs + r0 * stride, in_bytes, cudaMemcpyHostToDevice, st));
+            const void* src = recs + r0 * stride;
+            void* dst = out + r0;
+            BN_TRY(bounce_in(ctx, s, 0, src, in_bytes, in_pg));
+            BN_TRY(bounce_out(ctx, s, dst, cnt * 8, out_pg));
+            if (in_bytes) BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, src, in_bytes, cudaMemcpyHostToDevice, st));
             BN_TRY(bn::launch_as_2bit_batch(ctx->di, static_cast<const uint8_t*>(ctx->stage_in[s].p), cnt, k, stride,
                                             static_cast<uint64_t*>(ctx->stage_out[s].p), ctx->d_words + s, st));
-            BN_TRY(cudaMemcpyAsync(out + r0, ctx->stage_out[s].p, cnt * 8, cudaMemcpyDeviceToHost, st));
+            BN_TRY(cudaMemcpyAsync(dst, ctx->stage_out[s].p, cnt * 8, cudaMemcpyDeviceToHost, st));
             return cudaMemcpyAsync(ctx->h_words + s, ctx->d_words + s, 8, cudaMemcpyDeviceToHost, st);
         },
         [&](size_t c, int s) {
+            unbounce(ctx, s, out + c * per, std::min(per, n - c * per) * 8, out_pg);
             const unsigned long long key = ctx->h_words[s];
             if (key != kNoError) best = std::min(best, (((key >> 8) + (unsigned long long)(c * per * stride)) << 8) | (key & 0xFFu));
         });
@@ -642,20 +748,28 @@ int bn_from_2bit_batch(bn_ctx* ctx, const uint64_t* packed, size_t n, uint32_t k
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t per = units_per_chunk(ctx, stride, 64), n_chunks = (n + per - 1) / per;
+    const bool in_pg = is_pageable(packed), out_pg = is_pageable(out);
     const int rc = run_pipeline(
         ctx, n_chunks, err,
         [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
             const size_t r0 = c * per, cnt = std::min(per, n - r0), out_bytes = (cnt - 1) * stride + k;
             BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
             BN_TRY(ensure(ctx->stage_out[s], out_bytes));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, packed + r0, cnt * 8, cudaMemcpyHostToDevice, st));
-            if (stride != k)  // bytes between records must come back untouched
-                BN_TRY(cudaMemcpyAsync(ctx->stage_out[s].p, out + r0 * stride, out_bytes, cudaMemcpyHostToDevice, st));
+            const void* src = packed + r0;
+            void* dst = out + r0 * stride;
+            BN_TRY(bounce_in(ctx, s, 0, src, cnt * 8, in_pg));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, src, cnt * 8, cudaMemcpyHostToDevice, st));
+            if (stride != k) {  // bytes between records must come back untouched
+                const void* gaps = out + r0 * stride;
+                BN_TRY(bounce_in(ctx, s, 1, gaps, out_bytes, out_pg));
+                BN_TRY(cudaMemcpyAsync(ctx->stage_out[s].p, gaps, out_bytes, cudaMemcpyHostToDevice, st));
+            }
+            BN_TRY(bounce_out(ctx, s, dst, out_bytes, out_pg));
             BN_TRY(bn::launch_from_2bit_batch(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), cnt, k,
                                               static_cast<uint8_t*>(ctx->stage_out[s].p), stride, st));
-            return cudaMemcpyAsync(out + r0 * stride, ctx->stage_out[s].p, out_bytes, cudaMemcpyDeviceToHost, st);
+            return cudaMemcpyAsync(dst, ctx->stage_out[s].p, out_bytes, cudaMemcpyDeviceToHost, st);
         },
-        [](size_t, int) {});
+        [&](size_t c, int s) { unbounce(ctx, s, out + c * per * stride, (std::min(per, n - c * per) - 1) * stride + k, out_pg); });
     return rc != BN_OK ? rc : set_err(err, BN_OK);
 }
 
@@ -670,6 +784,7 @@ int bn_hdist(bn_ctx* ctx, const uint64_t* a, size_t n_words_a, const uint64_t* b
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t per = units_per_chunk(ctx, 16, 2), n_chunks = (need + per - 1) / per;  // words per chunk, 16-byte aligned shards
+    const bool a_pg = is_pageable(a), b_pg = is_pageable(b);
     unsigned long long sum = 0;
     const int rc = run_pipeline(
         ctx, n_chunks, err,
@@ -677,8 +792,11 @@ int bn_hdist(bn_ctx* ctx, const uint64_t* a, size_t n_words_a, const uint64_t* b
             const size_t w0 = c * per, cnt = std::min(per, need - w0), bases = std::min(n_bases - w0 * 32, cnt * 32);
             BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
             BN_TRY(ensure(ctx->stage_out[s], cnt * 8));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, a + w0, cnt * 8, cudaMemcpyHostToDevice, st));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_out[s].p, b + w0, cnt * 8, cudaMemcpyHostToDevice, st));
+            const void *sa = a + w0, *sb = b + w0;
+            BN_TRY(bounce_in(ctx, s, 0, sa, cnt * 8, a_pg));
+            BN_TRY(bounce_in(ctx, s, 1, sb, cnt * 8, b_pg));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, sa, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_out[s].p, sb, cnt * 8, cudaMemcpyHostToDevice, st));
             BN_TRY(bn::launch_hdist(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), static_cast<const uint64_t*>(ctx->stage_out[s].p),
                                     bases, ctx->d_words + s, st));
             return cudaMemcpyAsync(ctx->h_words + s, ctx->d_words + s, 8, cudaMemcpyDeviceToHost, st);
@@ -697,6 +815,7 @@ int bn_hdist_pairs(bn_ctx* ctx, const uint64_t* u, const uint64_t* v, size_t n_p
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t per = units_per_chunk(ctx, 16, 4), n_chunks = (n_pairs + per - 1) / per;
+    const bool u_pg = is_pageable(u), v_pg = is_pageable(v), out_pg = is_pageable(out);
     const int rc = run_pipeline(
         ctx, n_chunks, err,
         [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
@@ -704,14 +823,19 @@ int bn_hdist_pairs(bn_ctx* ctx, const uint64_t* u, const uint64_t* v, size_t n_p
             BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
             BN_TRY(ensure(ctx->stage_aux[s][0], cnt * 8));
             BN_TRY(ensure(ctx->stage_out[s], cnt * 4));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, u + p0, cnt * 8, cudaMemcpyHostToDevice, st));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][0].p, v + p0, cnt * 8, cudaMemcpyHostToDevice, st));
+            const void *su = u + p0, *sv = v + p0;
+            void* dst = out + p0;
+            BN_TRY(bounce_in(ctx, s, 0, su, cnt * 8, u_pg));
+            BN_TRY(bounce_in(ctx, s, 1, sv, cnt * 8, v_pg));
+            BN_TRY(bounce_out(ctx, s, dst, cnt * 4, out_pg));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, su, cnt * 8, cudaMemcpyHostToDevice, st));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][0].p, sv, cnt * 8, cudaMemcpyHostToDevice, st));
             BN_TRY(bn::launch_hdist_pairs(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p),
                                           static_cast<const uint64_t*>(ctx->stage_aux[s][0].p), cnt, len,
                                           static_cast<uint32_t*>(ctx->stage_out[s].p), st));
-            return cudaMemcpyAsync(out + p0, ctx->stage_out[s].p, cnt * 4, cudaMemcpyDeviceToHost, st);
+            return cudaMemcpyAsync(dst, ctx->stage_out[s].p, cnt * 4, cudaMemcpyDeviceToHost, st);
         },
-        [](size_t, int) {});
+        [&](size_t c, int s) { unbounce(ctx, s, out + c * per, std::min(per, n_pairs - c * per) * 4, out_pg); });
     return rc != BN_OK ? rc : set_err(err, BN_OK);
 }
 
@@ -726,12 +850,15 @@ int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t per = units_per_chunk(ctx, 8, 2), n_chunks = (need + per - 1) / per;
+    const bool in_pg = is_pageable(words);
     const int rc = run_pipeline(
         ctx, n_chunks, err,
         [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
             const size_t w0 = c * per, cnt = std::min(per, need - w0), bases = std::min(n_bases - w0 * 32, cnt * 32);
             BN_TRY(ensure(ctx->stage_in[s], cnt * 8));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, words + w0, cnt * 8, cudaMemcpyHostToDevice, st));
+            const void* src = words + w0;
+            BN_TRY(bounce_in(ctx, s, 0, src, cnt * 8, in_pg));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, src, cnt * 8, cudaMemcpyHostToDevice, st));
             BN_TRY(bn::launch_base_counts(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), bases, ctx->d_words + 4 + 4 * s, nullptr, st));
             return cudaMemcpyAsync(ctx->h_words + 4 + 4 * s, ctx->d_words + 4 + 4 * s, 4 * 8, cudaMemcpyDeviceToHost, st);
         },
@@ -820,10 +947,12 @@ int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, 
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
+    const bool in_pg = is_pageable(bytes), out_pg = is_pageable(out_words);
     auto retire = [&](size_t c) -> cudaError_t {
         const int s = (int)(c % kStages);
         cudaError_t e = cudaEventSynchronize(ctx->stage_done[s]);
         if (e != cudaSuccess) return e;
+        unbounce(ctx, s, out_words + chunks[c].w0, chunks[c].nw * 8, out_pg);
         best = std::min<unsigned long long>(best, ctx->h_words[s]);  // device offsets are already global (base pointer trick below)
         if (c) {  // rebase this chunk's word offsets (entry r0 was written by the previous chunk's total, same value)
             const Chunk& ch = chunks[c];
@@ -847,13 +976,17 @@ int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, 
         BN_CUDA(ensure(ctx->stage_aux[s][3], bn::encode_batch_scratch_bytes(nr, b1 - b0)));
         uint8_t* d_bytes = static_cast<uint8_t*>(ctx->stage_in[s].p) + phase;
         unsigned long long* d_status = ctx->d_words + s;
-        if (b1 > b0) BN_CUDA(cudaMemcpyAsync(d_bytes, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        const void* src = bytes + b0;
+        void* dst = out_words + ch.w0;
+        BN_CUDA(bounce_in(ctx, s, 0, src, b1 - b0, in_pg));
+        BN_CUDA(bounce_out(ctx, s, dst, ch.nw * 8, out_pg));
+        if (b1 > b0) BN_CUDA(cudaMemcpyAsync(d_bytes, src, b1 - b0, cudaMemcpyHostToDevice, st));
         BN_CUDA(cudaMemcpyAsync(ctx->stage_aux[s][0].p, offsets + ch.r0, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
         BN_CUDA(bn::launch_encode_batch(ctx->di, d_bytes - b0, static_cast<const uint64_t*>(ctx->stage_aux[s][0].p), nr, b1 - b0,
                                         static_cast<uint64_t*>(ctx->stage_out[s].p), static_cast<uint64_t*>(ctx->stage_aux[s][1].p),
                                         read_status ? static_cast<uint32_t*>(ctx->stage_aux[s][2].p) : nullptr, d_status,
                                         ctx->stage_aux[s][3].p, st));
-        if (ch.nw) BN_CUDA(cudaMemcpyAsync(out_words + ch.w0, ctx->stage_out[s].p, ch.nw * 8, cudaMemcpyDeviceToHost, st));
+        if (ch.nw) BN_CUDA(cudaMemcpyAsync(dst, ctx->stage_out[s].p, ch.nw * 8, cudaMemcpyDeviceToHost, st));
         // entries r0+1 .. r1 (entry r0 is the previous chunk's last entry; chunk 0 writes its own zero too)
         BN_CUDA(cudaMemcpyAsync(out_word_offsets + ch.r0 + 1, static_cast<uint64_t*>(ctx->stage_aux[s][1].p) + 1, nr * 8,
                                 cudaMemcpyDeviceToHost, st));
@@ -1029,6 +1162,7 @@ int bn_kmers(bn_ctx* ctx, const uint8_t* seq, size_t n, uint32_t k, uint64_t* ou
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t n_win = n - k + 1;
     const size_t per = units_per_chunk(ctx, 8, 2048), n_chunks = (n_win + per - 1) / per;  // the output (8 B per window) dominates
+    const bool in_pg = is_pageable(seq), out_pg = is_pageable(out);
     unsigned long long best = kNoError;
     const int rc = run_pipeline(
         ctx, n_chunks, err,
@@ -1036,13 +1170,18 @@ int bn_kmers(bn_ctx* ctx, const uint8_t* seq, size_t n, uint32_t k, uint64_t* ou
             const size_t i0 = c * per, cnt = std::min(per, n_win - i0), in_bytes = cnt + k - 1;  // chunks share k-1 bytes of input
             BN_TRY(ensure(ctx->stage_in[s], in_bytes));
             BN_TRY(ensure(ctx->stage_out[s], cnt * 8));
-            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, seq + i0, in_bytes, cudaMemcpyHostToDevice, st));
+            const void* src = seq + i0;
+            void* dst = out + i0;
+            BN_TRY(bounce_in(ctx, s, 0, src, in_bytes, in_pg));
+            BN_TRY(bounce_out(ctx, s, dst, cnt * 8, out_pg));
+            BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, src, in_bytes, cudaMemcpyHostToDevice, st));
             BN_TRY(bn::launch_kmer_windows(ctx->di, static_cast<const uint8_t*>(ctx->stage_in[s].p), in_bytes, k,
                                            static_cast<uint64_t*>(ctx->stage_out[s].p), ctx->d_words + s, st));
-            BN_TRY(cudaMemcpyAsync(out + i0, ctx->stage_out[s].p, cnt * 8, cudaMemcpyDeviceToHost, st));
+            BN_TRY(cudaMemcpyAsync(dst, ctx->stage_out[s].p, cnt * 8, cudaMemcpyDeviceToHost, st));
             return cudaMemcpyAsync(ctx->h_words + s, ctx->d_words + s, 8, cudaMemcpyDeviceToHost, st);
         },
         [&](size_t c, int s) {
+            unbounce(ctx, s, out + c * per, std::min(per, n_win - c * per) * 8, out_pg);
             const unsigned long long key = ctx->h_words[s];
             if (key != kNoError) best = std::min(best, (((key >> 8) + (unsigned long long)(c * per)) << 8) | (key & 0xFFu));
         });

@@ -39,3 +39,40 @@ def test_full_size_properties(cfg, name, capsys):
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     assert '"kernel"' in capsys.readouterr().out
+
+
+def test_more_than_2_pow_32_bases(cfg):
+    """Index arithmetic past 32 bits: encode / decode / base_counts / hdist on 2^32 + 12345 bases (4.3 GB of ASCII),
+    and a read batch holding one read of more than 2^32 bases."""
+    import numpy as np
+    import torch
+    from bitnuc_b200 import device as dv
+    n = (1 << 32) + 12345
+    asc = dv.synth_ascii(cfg.SEED, 9, 0, n)
+    words, st = dv.encode(asc)
+    st.check()
+    expect = dv.synth_words(cfg.SEED, 9, 0, dv.words_for(n))
+    expect[-1] &= (1 << (2 * (n % 32))) - 1
+    assert torch.equal(words, expect)
+    del expect
+    back = dv.decode(words, n)
+    assert torch.equal(back, asc)
+    del back
+    counts, _ = dv.base_counts(words, n)
+    assert int(counts.sum().item()) == n
+    assert int(dv.hdist(words, words, n).item()) == 0
+    asc[n - 7] = ord("N")                                  # an invalid base past offset 2^32
+    _, st = dv.encode(asc, out=words)
+    with pytest.raises(Exception) as ei:
+        st.check()
+    assert ei.value.key() == ("InvalidBase", ord("N")) and ei.value.offset == n - 7
+    asc[n - 7] = ord("A")
+    # the same bytes as a batch of three reads, the middle one longer than 2^32 bases
+    offsets = torch.tensor([0, 1000, n - 5, n], dtype=torch.int64, device="cuda")
+    bw, bwo, _, bst = dv.encode_batch(asc, offsets)
+    bst.check()
+    lens = [1000, n - 1005, 5]
+    assert bwo.tolist() == [0, 32, 32 + (lens[1] + 31) // 32, 32 + (lens[1] + 31) // 32 + 1]
+    mid = dv.decode(bw[32 : 32 + (lens[1] + 31) // 32].contiguous(), lens[1])
+    assert torch.equal(mid[:4096], asc[1000:5096]) and torch.equal(mid[-4096:], asc[n - 5 - 4096 : n - 5])
+    assert torch.equal(dv.decode(bw[-1:].contiguous(), 5), asc[n - 5 :])

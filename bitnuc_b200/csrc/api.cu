@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libbitnuc_cuda.so (see include/bitnuc_cuda.h): contexts, the device-pointer
-// entry points (enqueue only) and the host-pointer entry points (H2D -> kernel -> D2H, chunked and
-// multi-stream for the streaming codec so PCIe copies overlap the kernels).
+// entry points (enqueue only) and the host-pointer entry points (H2D -> kernel -> D2H; the stream-, record- and
+// read-parallel ones are chunked over a 3-stage multi-stream pipeline so PCIe copies overlap the kernels, and
+// pageable caller memory is bounced through pinned stage buffers by a multi-threaded memcpy).
 #include "../../include/bitnuc_cuda.h"
 
 #include <cuda_runtime.h>

@@ -17,8 +17,9 @@
  *     32 bases per uint64_t, zero-padded tail (src/utils/packing/mod.rs:13-20, src/lib.rs:96-98).
  *   - There is no CPU fallback: every call runs CUDA kernels built for sm_100a and fails with
  *     BN_ERR_CUDA when no such device is usable.
- *   - Host-pointer calls are synchronous and include the PCIe copies (pinned buffers from
- *     bn_host_alloc make them fully asynchronous inside the call).  `_dev` calls take device
+ *   - Host-pointer calls are synchronous and include the PCIe copies.  Any host memory works: pinned buffers
+ *     (bn_host_alloc, cudaHostRegister) run at the PCIe link rate, pageable ones are bounced through the
+ *     context's pinned stage buffers by a multi-threaded memcpy.  `_dev` calls take device
  *     pointers, only enqueue work on `stream`, and report validation results through a device-side
  *     status word that is read back later with bn_status_fetch.
  *   - A context is bound to one device and is internally synchronised: it may be shared by host

@@ -181,7 +181,8 @@ int bn_get_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint6
 
 /* ------------------------------------------------------------------ device-pointer calls ---- */
 /* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.
- * Pointers are device pointers.  ASCII buffers and packed buffers must be 16-byte aligned.
+ * Pointers are device pointers.  ASCII and packed buffers should be 16-byte aligned: that selects the fast kernels
+ * (misaligned pointers are served by slower byte- / word-granular kernels; packed buffers always need 8 bytes).
  * d_status is one device uint64_t that the call resets and the kernel updates with the smallest
  * (offset << 8 | byte) of any invalid base; read it back with bn_status_fetch. */
 

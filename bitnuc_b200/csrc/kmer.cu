@@ -154,8 +154,8 @@ as_2bit_tight_kernel(const uint8_t* __restrict__ recs, unsigned long long n, uns
             uint32_t bad = 0;
 #pragma unroll
             for (int j = 0; j < U; ++j) codes[v + j * THREADS] = pack16(x[j], bad);
-            if (bad & kValidMask) {
-#pragma unroll 1
+            if (bad & kValidMask) {  // rare; unrolled so that x[] is never indexed dynamically (that would put it in local memory)
+#pragma unroll
                 for (int j = 0; j < U; ++j) report_vector_invalid(x[j], (long long)(abase - recs) + 16ll * (v + j * THREADS), status);
             }
         }

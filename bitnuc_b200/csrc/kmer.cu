@@ -261,15 +261,26 @@ constexpr int kTightChunks = 4;  // 16-byte output chunks per thread, all loads 
 
 // Tightly packed records (stride == k, 16 <= k <= 32), 16-byte aligned output: one thread per
 // 16-byte output chunk; a chunk spans at most two records.  A CTA owns kKmerThreads * kTightChunks
-// consecutive chunks; (record, position) is found by one division per thread, then advanced.
+// consecutive chunks; (record, position) comes from one 64-bit division per CTA and one 32-bit division per thread,
+// then advances.
 __global__ void __launch_bounds__(kKmerThreads, 2)
 from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n, unsigned k,
                        uint8_t* __restrict__ out) {
     const unsigned long long total = n * k;
     const unsigned long long n_chunks = total / 16;
     const unsigned long long c0 = (unsigned long long)blockIdx.x * (kKmerThreads * kTightChunks) + threadIdx.x;
-    unsigned long long r = (c0 * 16) / k;
-    unsigned pos = (unsigned)((c0 * 16) % k);
+    // (record, position) of the CTA's first byte: one 64-bit division per CTA; the threads then only need a 32-bit one
+    __shared__ unsigned long long r_cta;
+    __shared__ unsigned p_cta;
+    if (threadIdx.x == 0) {
+        const unsigned long long b = (unsigned long long)blockIdx.x * (kKmerThreads * kTightChunks) * 16ull;
+        r_cta = b / k;
+        p_cta = (unsigned)(b % k);
+    }
+    __syncthreads();
+    const unsigned t = p_cta + threadIdx.x * 16u;
+    unsigned long long r = r_cta + t / k;
+    unsigned pos = t % k;
     constexpr unsigned kStepBytes = kKmerThreads * 16;
     const unsigned dr = kStepBytes / k, dpos = kStepBytes % k;
     uint64_t w0[kTightChunks], w1[kTightChunks];

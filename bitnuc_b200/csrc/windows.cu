@@ -175,30 +175,30 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
             s_obase[i] = out + __ldg(out_offsets + r_first + i) - st;
         }
         __syncthreads();
-        if (p >= w_end) return;
-        int q = (int)(p - t_lo);                                                     // byte position relative to the tile: < 4096
-        unsigned i = 0, hi = nr - 1;                                                 // the first i with s_end[i] > q (reads are adjacent)
-        while (i < hi) {
-            const unsigned mid = (i + hi) / 2;
-            if (s_end[mid] > q) hi = mid; else i = mid + 1;
+        // The warp owns the windows that start in its 1024 bytes of the tile.  It walks the reads overlapping that
+        // range one after the other (warp-uniform), and its lanes stride over the window starts of the current read:
+        // no per-lane bookkeeping, consecutive lanes -> consecutive output words.
+        const int lo = 1024 * (int)warp, hi = (int)(w_end - t_lo), kk = (int)k;
+        if (lo >= hi) return;
+        unsigned i = 0, top = nr - 1;                                                // the first read that ends after lo
+        while (i < top) {
+            const unsigned mid = (i + top) / 2;
+            if (s_end[mid] > lo) top = mid; else i = mid + 1;
         }
-        int r_hi = s_end[i];
-        uint64_t* obase = s_obase[i];
-        const int q_end = (int)(w_end - t_lo), kk = (int)k;
-#pragma unroll 2
-        for (; q < q_end; q += 32) {
-            while (q >= r_hi) {  // advance to the read holding this byte (skips empty reads)
-                ++i;
-                r_hi = s_end[i];
-                obase = s_obase[i];
-            }
-            if (q + kk <= r_hi) {  // a whole window of that read starts here
+        int r_lo = lo;                                                               // that read starts at or before lo
+        for (; i < nr; ++i) {
+            const int r_hi = s_end[i];
+            uint64_t* obase = s_obase[i];
+            const int a = r_lo > lo ? r_lo : lo, b = r_hi - kk + 1 < hi ? r_hi - kk + 1 : hi;   // window starts [a, b)
+            for (int q = a + (int)lane; q < b; q += 32) {
                 const unsigned rel = (unsigned)q + mis;
                 const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
                 const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
                 st_stream_v2(reinterpret_cast<uint2*>(obase + q),
                              make_uint2(__funnelshift_r(c0, c1, sh) & keep.x, __funnelshift_r(c1, c2, sh) & keep.y));
             }
+            if (r_hi >= hi) break;
+            r_lo = r_hi;
         }
         return;
     }

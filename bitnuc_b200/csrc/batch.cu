@@ -33,12 +33,13 @@ struct WordsOfRead {
 };
 
 // scan hook: read r owns words [start, start + count); note it as the owner of every tile whose first word it holds
+template <int kTileWords>   // compile-time (a power of two): the division below is per read, it must stay a shift
 struct NoteTileOwners {
     unsigned long long* tile_owner;
-    unsigned long long max_tiles, tile_words;
+    unsigned long long max_tiles;
     __device__ __forceinline__ void operator()(unsigned long long r, unsigned long long start, unsigned long long count) const {
         if (count == 0) return;
-        for (unsigned long long t = ceil_div(start, tile_words); t < max_tiles && t * tile_words < start + count; ++t)
+        for (unsigned long long t = (start + kTileWords - 1) / kTileWords; t < max_tiles && t * kTileWords < start + count; ++t)
             tile_owner[t] = r;
     }
 };
@@ -266,7 +267,7 @@ static cudaError_t launch_encode_batch_variant(const DeviceInfo& di, const uint8
                                                unsigned long long* d_status, unsigned long long* sums, unsigned long long* tile_counter,
                                                unsigned long long* tile_owner, cudaStream_t s) {
     const unsigned long long max_tiles = batch_max_tiles(n_reads, n_bytes, kTileWords);
-    launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s, NoteTileOwners{tile_owner, max_tiles, kTileWords});
+    launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s, NoteTileOwners<kTileWords>{tile_owner, max_tiles});
     static const int resident = resident_blocks(encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU>, kBThreads, di);
     // the number of output words is only known on the device: launch a full persistent grid
     encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU><<<resident, kBThreads, 0, s>>>(

@@ -90,3 +90,11 @@ def test_decode_is_register_only(sass):
     ops = _ops(funcs[name])
     assert not any(o.startswith(("LDS", "STS", "LDL", "STL")) for o in ops)
     assert sum(o == "PRMT" for o in ops) >= 24          # PRMT as the 4-entry byte LUT: 6 per 16 bases, 4 words per thread
+
+
+def test_scan_kernels_have_no_subroutine_calls(sass):
+    """The scans run once per read: a 64-bit division by a run-time value (a CALL to the division subroutine) in
+    the count functors or the per-item hooks would cost more than the scan itself."""
+    funcs, _ = sass
+    for name in _find(funcs, "scan_offsets_kernel") + _find(funcs, "scan_block_sums_kernel"):
+        assert not any(o.startswith("CALL") for o in _ops(funcs[name])), name

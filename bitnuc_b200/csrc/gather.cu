@@ -129,6 +129,9 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
             for (unsigned i = 0; done + i < n; ++i) o[sh_head + done + i] = (uint8_t)(0x54474341u >> (8u * ((t >> (2 * i)) & 3u)));
         }
     }
+    // (A span can hold one long range and still fit the stage when its other queries are empty: the copy-out below
+    // then also writes that range's bytes, with whatever the image holds.  slice_long_kernel runs after this kernel on
+    // the same stream and writes the range itself, so the final bytes are right.)
     if (staged) {  // warp-uniform: store the staged span, 16 bytes per lane step; ragged ends byte-wise
         __syncwarp();
         const unsigned a = (unsigned)(g_lo - g_base), b = a + (unsigned)(span_hi - span_lo);   // valid bytes [a, b) of the image

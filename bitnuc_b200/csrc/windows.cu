@@ -190,6 +190,7 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
             const int r_hi = s_end[i];
             uint64_t* obase = s_obase[i];
             const int a = r_lo > lo ? r_lo : lo, b = r_hi - kk + 1 < hi ? r_hi - kk + 1 : hi;   // window starts [a, b)
+#pragma unroll 1   // three or four trips per 125-bp read: an unrolled body with its remainder ladder costs more than it saves
             for (int q = a + (int)lane; q < b; q += 32) {
                 const unsigned rel = (unsigned)q + mis;
                 const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);

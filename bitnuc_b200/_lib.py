@@ -4,13 +4,13 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-from .errors import BitnucCudaError, NucleotideError, ReferencePanic
+from .errors import BitnucCudaError, FastqError, NucleotideError, ReferencePanic
 
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libbitnuc_cuda.so"
 
 BN_OK = 0
-BN_ERR_CUDA, BN_ERR_ARGUMENT, BN_ERR_EMPTY_ENCODE, BN_ERR_NOMEM = -1, -2, -3, -4
+BN_ERR_CUDA, BN_ERR_ARGUMENT, BN_ERR_EMPTY_ENCODE, BN_ERR_NOMEM, BN_ERR_FASTQ = -1, -2, -3, -4, -5
 
 
 class BnError(C.Structure):
@@ -72,6 +72,14 @@ PROTOTYPES = {
     "bn_slice_batch_scratch_bytes": (_sz, [_sz]),
     "bn_slice_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "bn_get_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "bn_fastq_scan": (_int, [_vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), _errp]),
+    "bn_fastq_encode": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _errp]),
+    "bn_fastq_scratch_bytes": (_sz, [_sz]),
+    "bn_fastq_index_scratch_bytes": (_sz, [_sz]),
+    "bn_fastq_count_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "bn_fastq_index_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bn_fastq_encode_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bn_fastq_status_fetch": (_int, [_vp, _vp, _vp, _u64, _vp, _sz, _errp]),
     "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),
     "bn_synth_words_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
     "bn_synth_ascii_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
@@ -118,6 +126,8 @@ def raise_for(rc: int, err: BnError | None = None):
         raise NucleotideError.InvalidRange(err.a, err.b, err.c)
     if rc == 6:
         raise NucleotideError.Unsupported()
+    if rc == BN_ERR_FASTQ and err is not None:
+        raise FastqError(err.record, err.a)
     if rc == BN_ERR_EMPTY_ENCODE:
         raise ReferencePanic("encode of an empty sequence: the reference panics (packing/avx.rs:138)")
     if err is not None and err.code == rc:

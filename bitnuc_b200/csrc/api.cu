@@ -49,6 +49,11 @@ struct bn_ctx {
     unsigned long long* d_words = nullptr;       // 16 device status / accumulator words
     unsigned long long* h_words = nullptr;       // pinned mirror
     size_t chunk = kDefaultChunk;
+    // bn_fastq_scan -> bn_fastq_encode: the uploaded text and its index stay resident between the two calls
+    Buffer fq[7];                                // text, scratch, index scratch, seq offsets, seq lens, word offsets, out words
+    const void* fq_text = nullptr;
+    size_t fq_bytes = 0, fq_reads = 0, fq_words = 0;
+    bool fq_valid = false;
     std::mutex mu;
 };
 
@@ -204,6 +209,11 @@ int bn_error_string(const bn_error_t* e, char* buf, size_t cap) {
     case BN_ERR_ARGUMENT: return snprintf(buf, cap, "invalid argument");
     case BN_ERR_EMPTY_ENCODE: return snprintf(buf, cap, "encode of an empty sequence (the reference panics)");
     case BN_ERR_NOMEM: return snprintf(buf, cap, "out of memory");
+    case BN_ERR_FASTQ: {
+        static const char* const what[] = {"malformed record", "header line does not start with '@'", "separator line does not start with '+'",
+                                           "quality and sequence lengths differ", "text ends inside the record"};
+        return snprintf(buf, cap, "FASTQ record %llu: %s", (unsigned long long)e->record, what[e->a <= 4 ? e->a : 0]);
+    }
     default: return snprintf(buf, cap, "unknown error %d", e->code);
     }
 }
@@ -254,6 +264,8 @@ void bn_ctx_destroy(bn_ctx* ctx) {
             if (ctx->hstage_out[s].p) cudaFreeHost(ctx->hstage_out[s].p);
         }
         for (auto& b : ctx->slot)
+            if (b.p) cudaFree(b.p);
+        for (auto& b : ctx->fq)
             if (b.p) cudaFree(b.p);
         if (ctx->d_words) cudaFree(ctx->d_words);
         if (ctx->h_words) cudaFreeHost(ctx->h_words);
@@ -491,6 +503,78 @@ int bn_get_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const u
     BN_LAUNCH(bn::launch_get_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_index, nq, d_out,
                                    reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
     return BN_OK;
+}
+
+size_t bn_fastq_scratch_bytes(size_t n_bytes) { return bn::fastq_scratch_bytes(n_bytes); }
+size_t bn_fastq_index_scratch_bytes(size_t n_reads) { return bn::fastq_index_scratch_bytes(n_reads); }
+
+int bn_fastq_count_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines) {
+    if (!ctx || !d_n_lines || (n_bytes && (!d_text || !d_scratch)) || (reinterpret_cast<uintptr_t>(d_text) & 15u)) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_fastq_count(ctx->di, d_text, n_bytes, d_scratch, d_n_lines, pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_fastq_index_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                       void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_status) {
+    if (!ctx || !d_status || !d_word_offsets || (reinterpret_cast<uintptr_t>(d_text) & 15u) ||
+        (reinterpret_cast<uintptr_t>(d_index_scratch) & 15u) ||
+        (n_bytes && (!d_text || !d_scratch)) || (n_reads && (!d_index_scratch || !d_seq_offsets || !d_seq_lens)))
+        return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_fastq_index(ctx->di, d_text, n_bytes, n_reads, d_scratch, d_index_scratch, d_seq_offsets, d_seq_lens, d_word_offsets,
+                                     reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+    return BN_OK;
+}
+
+int bn_fastq_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                        const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets, uint64_t* d_out_words,
+                        uint64_t* d_status) {
+    if (!ctx || !d_status || (reinterpret_cast<uintptr_t>(d_text) & 15u) ||
+        (n_reads && (!d_text || !d_scratch || !d_seq_offsets || !d_seq_lens || !d_word_offsets)))
+        return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    BN_LAUNCH(bn::launch_fastq_encode(ctx->di, d_text, n_bytes, n_reads, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,
+                                      reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+    return BN_OK;
+}
+
+static int fastq_fault(bn_error_t* err, unsigned long long key) {
+    set_err(err, BN_ERR_FASTQ, key & 0xFFu);
+    if (err) err->record = key >> 8;
+    return BN_ERR_FASTQ;
+}
+
+int bn_fastq_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, uint64_t n_lines, const uint64_t* d_seq_offsets,
+                          size_t n_reads, bn_error_t* err) {
+    if (!ctx || !d_status) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t s = pick(ctx, stream);
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words, d_status, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    BN_CUDA(cudaStreamSynchronize(s));
+    unsigned long long fault = ctx->h_words[1];
+    const unsigned long long key = ctx->h_words[0];
+    if (n_lines % 4) fault = std::min<unsigned long long>(fault, ((n_lines / 4) << 8) | BN_FASTQ_TRUNCATED);
+    if (fault != kNoError) return fastq_fault(err, fault);
+    if (key == kNoError) return set_err(err, BN_OK);
+    invalid_base(err, key, 0);
+    if (err && d_seq_offsets && n_reads) {  // the read holding the byte: the last r with seq_offsets[r] <= offset (rare path: a few 8-byte copies)
+        const uint64_t off = key >> 8;
+        size_t lo = 0, hi = n_reads - 1;
+        uint64_t v = 0;
+        while (lo < hi) {
+            const size_t mid = lo + (hi - lo + 1) / 2;
+            BN_CUDA(cudaMemcpyAsync(&v, d_seq_offsets + mid, 8, cudaMemcpyDeviceToHost, s));
+            BN_CUDA(cudaStreamSynchronize(s));
+            if (v <= off) lo = mid; else hi = mid - 1;
+        }
+        BN_CUDA(cudaMemcpyAsync(&v, d_seq_offsets + lo, 8, cudaMemcpyDeviceToHost, s));
+        BN_CUDA(cudaStreamSynchronize(s));
+        err->record = lo;
+        err->b = off - v;
+    }
+    return BN_INVALID_BASE;
 }
 
 int bn_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, bn_error_t* err) {
@@ -1245,6 +1329,95 @@ int bn_kmers_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, s
             const size_t r = (size_t)(std::upper_bound(offsets, offsets + n_reads + 1, off) - offsets) - 1;
             err->record = r;
             err->b = off - offsets[r];
+        }
+        return BN_INVALID_BASE;
+    }
+    return set_err(err, BN_OK);
+}
+
+// FASTQ text -> records -> packed words.  The text is staged whole; scan and encode are two calls because the caller
+// has to allocate the outputs in between.
+int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err) {
+    if (!ctx || !n_reads || !n_words || (n_bytes && !text)) return set_err(err, BN_ERR_ARGUMENT);
+    *n_reads = *n_words = 0;
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->fq_valid = false;
+    ctx->fq_text = text;
+    ctx->fq_bytes = n_bytes;
+    ctx->fq_reads = ctx->fq_words = 0;
+    if (n_bytes == 0) {
+        ctx->fq_valid = true;
+        return set_err(err, BN_OK);
+    }
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->fq[0], n_bytes + 16));
+    BN_CUDA(ensure(ctx->fq[1], bn::fastq_scratch_bytes(n_bytes)));
+    const uint8_t* d_text = static_cast<const uint8_t*>(ctx->fq[0].p);
+    BN_CUDA(cudaMemcpyAsync(ctx->fq[0].p, text, n_bytes, cudaMemcpyHostToDevice, st));
+    BN_CUDA(bn::launch_fastq_count(ctx->di, d_text, n_bytes, ctx->fq[1].p, reinterpret_cast<uint64_t*>(ctx->d_words + 10), st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 10, ctx->d_words + 10, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long n_lines = ctx->h_words[10];
+    const size_t nr = (size_t)(n_lines / 4);
+    BN_CUDA(ensure(ctx->fq[2], bn::fastq_index_scratch_bytes(nr)));
+    BN_CUDA(ensure(ctx->fq[3], nr * 8 + 8));
+    BN_CUDA(ensure(ctx->fq[4], nr * 8 + 8));
+    BN_CUDA(ensure(ctx->fq[5], (nr + 1) * 8));
+    uint64_t* d_wo = static_cast<uint64_t*>(ctx->fq[5].p);
+    BN_CUDA(bn::launch_fastq_index(ctx->di, d_text, n_bytes, nr, ctx->fq[1].p, ctx->fq[2].p, static_cast<uint64_t*>(ctx->fq[3].p),
+                                   static_cast<uint64_t*>(ctx->fq[4].p), d_wo, ctx->d_words + 12, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 11, d_wo + nr, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 12, ctx->d_words + 12, 16, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    unsigned long long fault = ctx->h_words[13];
+    if (n_lines % 4) fault = std::min<unsigned long long>(fault, ((unsigned long long)nr << 8) | BN_FASTQ_TRUNCATED);
+    if (fault != kNoError) return fastq_fault(err, fault);
+    ctx->fq_reads = nr;
+    ctx->fq_words = (size_t)ctx->h_words[11];
+    ctx->fq_valid = true;
+    *n_reads = nr;
+    *n_words = ctx->fq_words;
+    return set_err(err, BN_OK);
+}
+
+int bn_fastq_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t* out_words,
+                    uint64_t* out_word_offsets, uint64_t* seq_offsets, uint64_t* seq_lens, bn_error_t* err) {
+    if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    // only valid right after bn_fastq_scan of the same text on this context
+    if (!ctx->fq_valid || ctx->fq_text != text || ctx->fq_bytes != n_bytes || ctx->fq_reads != n_reads || ctx->fq_words != n_words ||
+        (n_words && !out_words))
+        return set_err(err, BN_ERR_ARGUMENT);
+    if (n_reads == 0) {
+        if (out_word_offsets) out_word_offsets[0] = 0;
+        return set_err(err, BN_OK);
+    }
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->fq[6], n_words * 8 + 8));
+    const uint64_t* d_so = static_cast<const uint64_t*>(ctx->fq[3].p);
+    BN_CUDA(cudaMemsetAsync(ctx->d_words + 12, 0xFF, 8, st));
+    BN_CUDA(bn::launch_fastq_encode(ctx->di, static_cast<const uint8_t*>(ctx->fq[0].p), n_bytes, n_reads, ctx->fq[1].p, d_so,
+                                    static_cast<const uint64_t*>(ctx->fq[4].p), static_cast<const uint64_t*>(ctx->fq[5].p),
+                                    static_cast<uint64_t*>(ctx->fq[6].p), ctx->d_words + 12, st));
+    if (n_words) BN_CUDA(cudaMemcpyAsync(out_words, ctx->fq[6].p, n_words * 8, cudaMemcpyDeviceToHost, st));
+    if (out_word_offsets) BN_CUDA(cudaMemcpyAsync(out_word_offsets, ctx->fq[5].p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (seq_offsets) BN_CUDA(cudaMemcpyAsync(seq_offsets, ctx->fq[3].p, n_reads * 8, cudaMemcpyDeviceToHost, st));
+    if (seq_lens) BN_CUDA(cudaMemcpyAsync(seq_lens, ctx->fq[4].p, n_reads * 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 12, ctx->d_words + 12, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long key = ctx->h_words[12];
+    if (key != kNoError) {
+        invalid_base(err, key, 0);
+        if (err) {
+            std::vector<uint64_t> so(n_reads);
+            BN_CUDA(cudaMemcpyAsync(so.data(), d_so, n_reads * 8, cudaMemcpyDeviceToHost, st));
+            BN_CUDA(cudaStreamSynchronize(st));
+            const uint64_t off = key >> 8;
+            const size_t r = (size_t)(std::upper_bound(so.begin(), so.end(), off) - so.begin()) - 1;
+            err->record = r;
+            err->b = off - so[r];
         }
         return BN_INVALID_BASE;
     }

@@ -1,0 +1,470 @@
+// fastq.cu -- FASTQ text in HBM -> record offsets -> per-read packed words, without the host ever parsing (sm_100a).
+//
+// the reference has no parser; its README shows the caller's loop (/root/reference/README.md:160-180,
+// `for record in reader { PackedSequence::new(record.seq())? }`).  This file replaces that loop AND the host-side
+// construction of the offsets bn_encode_batch wants: the FASTQ bytes are uploaded as they are, the device finds the
+// records and encodes every sequence line on a fresh 64-bit word (src/sequence.rs:40-52).
+//
+// FASTQ as parsed here (strict four-line records): line 4r starts with '@', line 4r+1 is the sequence, line 4r+2
+// starts with '+', line 4r+3 (quality) has the length of the sequence; lines end in "\n" or "\r\n"; the last line
+// may lack its newline.  A format error wins over an invalid base; among errors of a kind the first in file order.
+//
+// Device steps (tiles of 16 KiB of text, handed out by the hardware CTA scheduler):
+//   1. fastq_count_kernel    newlines per tile (word-parallel exact byte compare, one POPC per 16 bytes)
+//      + exclusive scan      -> line index of every tile's first newline, number of lines
+//   2. fastq_index_kernel    every newline writes its position into nl[line]; the thread that owns a newline also
+//                            checks the first byte of the following line ('@' after a quality line, '+' after a
+//                            sequence line) and notes a preceding '\r'
+//      fastq_records_kernel  nl[4r .. 4r+3] -> seq_offsets[r], seq_lens[r]; quality length checked
+//      + exclusive scan      of ceil(len/32) -> word_offsets
+//   3. fastq_encode_kernel   PACK THEN CUT over tiles of 64 KiB of text: the whole tile (headers and qualities too) is
+//                            packed like the contiguous encode -- aligned coalesced 128-bit loads, 16 bytes -> one
+//                            32-bit code, one "contains a non-ACGT byte" flag per vector via a ballot -- into a
+//                            shared-memory strip; then one thread per read that starts in the tile cuts the read's
+//                            words out of the strip (batch.cu's cut_word).  A read is valid when the flags of its
+//                            interior vectors are clear and its two partial end vectors pass a byte-masked test.
+//                            The one read that runs past the tile is finished straight from global memory.
+// HBM traffic: the text is read three times (count, index, encode).  Algorithmic bytes: text once + 8 B per word out
+// + 24 B per read of offsets.
+#include "common.cuh"
+#include "launch.cuh"
+#include "scan.cuh"
+
+namespace bn {
+
+constexpr int kFqTile = 16384;               // bytes of text per line-index tile
+constexpr int kFqThreads = 256;              // x 4 vectors of 16 bytes
+constexpr int kFqEncTile = 65536;            // bytes of text per encode tile
+constexpr int kFqLongWords = 64;             // a read with more words than this inside the strip is cut by whole warps
+constexpr unsigned long long kCrBit = 1ull << 63;
+
+enum { FQ_BAD_HEADER = 1, FQ_BAD_SEPARATOR = 2, FQ_BAD_QUALITY_LENGTH = 3 };   // kinds of format error (4 = truncated: host)
+
+static inline unsigned long long fastq_tiles(size_t n_bytes) { return (unsigned long long)n_bytes / kFqTile + 1; }   // covers position n_bytes
+
+// ---------------------------------------------------------------- text access -------------------------------------
+// The text is read as if a '\n' followed a last line that lacks one, and NUL bytes followed that.
+
+static __device__ __noinline__ uint4 fq_load_edge(const uint8_t* __restrict__ bytes, unsigned long long n, bool virt, unsigned long long pos) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (pos > n) return make_uint4(0u, 0u, 0u, 0u);
+    for (int j = 0; j < 16; ++j) {
+        const unsigned long long i = pos + j;
+        uint32_t b = 0;
+        if (i < n) b = bytes[i];
+        else if (i == n && virt) b = '\n';
+        w[j >> 2] |= b << (8 * (j & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 fq_load(const uint8_t* __restrict__ bytes, unsigned long long n, bool virt, unsigned long long pos) {
+    return pos + 16 <= n ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(bytes + pos)) : fq_load_edge(bytes, n, virt, pos);
+}
+
+// 0x80 in every byte of w that equals the pattern byte (exact: no carries cross a byte)
+__device__ __forceinline__ uint32_t eq_flags(uint32_t w, uint32_t pat4) {
+    const uint32_t x = w ^ pat4;
+    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);
+}
+// the four flags (bits 7, 15, 23, 31) gathered into bits 0..3, byte order kept
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return (((f >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+constexpr uint32_t kNl4 = 0x0A0A0A0Au;
+
+__device__ __forceinline__ uint32_t newline_count16(uint4 v) {
+    return __popc(eq_flags(v.x, kNl4) | (eq_flags(v.y, kNl4) >> 1) | (eq_flags(v.z, kNl4) >> 2) | (eq_flags(v.w, kNl4) >> 3));
+}
+// bit i set iff byte i of the vector is '\n'
+__device__ __forceinline__ uint32_t newline_mask16(uint4 v) {
+    return flags_to_nibble(eq_flags(v.x, kNl4)) | (flags_to_nibble(eq_flags(v.y, kNl4)) << 4) |
+           (flags_to_nibble(eq_flags(v.z, kNl4)) << 8) | (flags_to_nibble(eq_flags(v.w, kNl4)) << 12);
+}
+
+__device__ __forceinline__ void report_min(unsigned long long* word, unsigned long long key) {
+    if (key < ld_volatile_u64(word)) atomicMin(word, key);
+}
+
+// ---------------------------------------------------------------- 1. newlines per tile -----------------------------
+
+__global__ void __launch_bounds__(kFqThreads)
+fastq_count_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned long long scratch[32];
+    const bool virt = n && bytes[n - 1] != '\n';
+    const unsigned long long tile0 = (unsigned long long)blockIdx.x * kFqTile;
+    uint4 x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (threadIdx.x + j * kFqThreads));
+    unsigned c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c += newline_count16(x[j]);
+    const unsigned long long total = block_sum_u64(c, scratch);
+    if (threadIdx.x == 0) counts[blockIdx.x] = total;
+}
+
+struct CountOfTile {
+    const unsigned long long* counts;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long t) const { return counts[t]; }
+};
+
+// ---------------------------------------------------------------- 2. line index ------------------------------------
+
+__global__ void __launch_bounds__(kFqThreads)
+fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
+                   unsigned long long n_reads, uint64_t* __restrict__ nl, unsigned long long* __restrict__ status) {
+    __shared__ __align__(8) uint16_t nlb[kFqTile / 16];
+    __shared__ unsigned warp_tot[kFqThreads / 32];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool virt = n && bytes[n - 1] != '\n';
+    const unsigned long long tile0 = (unsigned long long)blockIdx.x * kFqTile;
+    uint4 x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (tid + j * kFqThreads));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nlb[tid + j * kFqThreads] = (uint16_t)newline_mask16(x[j]);
+    __syncthreads();
+    // thread t owns bytes [64 t, 64 t + 64) of the tile: four consecutive vectors
+    const uint2 mm = *reinterpret_cast<const uint2*>(nlb + 4 * tid);
+    unsigned long long m = ((unsigned long long)mm.y << 32) | mm.x;
+    const unsigned cnt = __popcll(m);
+    unsigned inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned rank = inc - cnt;
+    for (unsigned w = 0; w < warp; ++w) rank += warp_tot[w];
+    const unsigned long long n_whole = 4 * n_reads;              // nl[] holds the lines of whole records
+    const unsigned long long n_lines = line_base[gridDim.x];     // all lines, a trailing partial record included
+    if (blockIdx.x == 0 && tid == 0 && n_lines && bytes[0] != '@') report_min(status + 1, FQ_BAD_HEADER);
+    unsigned long long L = line_base[blockIdx.x] + rank;
+    while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const unsigned long long p = tile0 + 64ull * tid + b;        // <= n (n itself only for the virtual newline)
+        if (L < n_whole) {
+            const bool cr = p > 0 && bytes[p - 1] == '\r';
+            nl[L] = p | (cr ? kCrBit : 0ull);
+        }
+        const unsigned kind = (unsigned)(L & 3);
+        if (L + 1 < n_lines && (kind == 3 || kind == 1)) {
+            // a quality line ends here: the next record must open with '@'; a sequence line: the separator opens with '+'
+            const uint32_t c = p + 1 < n ? bytes[p + 1] : '\n';
+            if (c != (kind == 3 ? '@' : '+'))
+                report_min(status + 1, kind == 3 ? (((L + 1) >> 2) << 8) | FQ_BAD_HEADER : ((L >> 2) << 8) | FQ_BAD_SEPARATOR);
+        }
+        ++L;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fastq_records_kernel(const uint64_t* __restrict__ nl, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
+                     uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n_reads) return;
+    const ulonglong2 ab = reinterpret_cast<const ulonglong2*>(nl)[2 * r], cd = reinterpret_cast<const ulonglong2*>(nl)[2 * r + 1];
+    const unsigned long long s = (ab.x & ~kCrBit) + 1, e = (ab.y & ~kCrBit) - (ab.y >> 63);
+    const unsigned long long qs = (cd.x & ~kCrBit) + 1, qe = (cd.y & ~kCrBit) - (cd.y >> 63);
+    if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
+    seq_off[r] = s;
+    seq_len[r] = e - s;
+}
+
+struct WordsOfLen {
+    const uint64_t* lens;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long r) const { return (lens[r] + 31) / 32; }
+};
+
+// ---------------------------------------------------------------- 3. encode ----------------------------------------
+
+// a vector at the end of the text, fetched byte-wise ('A' beyond it)
+static __device__ __noinline__ uint4 enc_load_edge(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long pos) {
+    uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
+    for (int j = 0; j < 16; ++j)
+        if (pos + j < n) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)bytes[pos + j] << (8 * (j & 3)));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 enc_load_cached(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long pos) {
+    return pos + 16 <= n ? ld128<LD_PLAIN>(reinterpret_cast<const uint4*>(bytes + pos)) : enc_load_edge(bytes, n, pos);
+}
+
+// bytes l..h-1 of a 32-bit word (clamped to the word)
+__device__ __forceinline__ uint32_t byte_range_mask(int l, int h) {
+    l = l < 0 ? 0 : l;
+    h = h > 4 ? 4 : h;
+    if (l >= h) return 0u;
+    return (uint32_t)(((1ull << (8 * h)) - 1ull) & ~((1ull << (8 * l)) - 1ull));
+}
+// does the vector hold a byte outside ACGTacgt at a byte index in [l, h)?
+__device__ __forceinline__ bool bad_in_range(uint4 v, int l, int h) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t s1 = w[i] >> 1, s2 = w[i] >> 2;
+        const uint32_t tcol = s2 & ~s1 & 0x01010101u;
+        const uint32_t expect = tcol * 0x11u + 0x41414141u;
+        acc |= (w[i] ^ expect) & kValidMask & byte_range_mask(l - 4 * i, h - 4 * i);
+    }
+    return acc != 0;
+}
+
+// rare path, out of line: first invalid byte of text[lo, hi) -> status word
+static __device__ __noinline__ void fq_report_range(const uint8_t* __restrict__ bytes, unsigned long long lo, unsigned long long hi,
+                                                    unsigned long long* status) {
+    if ((ld_volatile_u64(status) >> 8) <= lo) return;   // an earlier invalid base is already known
+    for (unsigned long long i = lo; i < hi; ++i) {
+        const uint32_t b = bytes[i];
+        if (!byte_is_valid(b)) {
+            report_invalid(status, i, b);
+            return;
+        }
+    }
+}
+
+// Is there an invalid byte in tile bytes [lo, hi), hi > lo?  Whole vectors by their flags, the partial ones byte-masked.
+__device__ __forceinline__ bool strip_range_invalid(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0,
+                                                    const uint32_t* __restrict__ flags, unsigned lo, unsigned hi) {
+    const unsigned v_lo = (lo + 15u) >> 4, v_hi = hi >> 4;
+    bool bad = false;
+    if (v_lo <= v_hi) {
+        if (lo & 15u) bad |= bad_in_range(enc_load_cached(bytes, n, tile0 + 16ull * (v_lo - 1)), (int)(lo & 15u), 16);
+        if (hi & 15u) bad |= bad_in_range(enc_load_cached(bytes, n, tile0 + 16ull * v_hi), 0, (int)(hi & 15u));
+        if (v_lo < v_hi) {
+            const unsigned w_lo = v_lo >> 5, w_hi = (v_hi - 1u) >> 5;
+            for (unsigned w = w_lo; w <= w_hi; ++w) {
+                uint32_t f = flags[w];
+                if (w == w_lo) f &= 0xFFFFFFFFu << (v_lo & 31u);
+                if (w == w_hi) f &= 0xFFFFFFFFu >> (31u - ((v_hi - 1u) & 31u));
+                bad |= f != 0u;
+            }
+        }
+    } else {  // both ends inside one vector
+        bad = bad_in_range(enc_load_cached(bytes, n, tile0 + 16ull * (lo >> 4)), (int)(lo & 15u), (int)(hi & 15u));
+    }
+    return bad;
+}
+
+// the output word whose first base sits `rel` bytes into the strip (same window as batch.cu)
+__device__ __forceinline__ uint64_t fq_cut_word(const uint32_t* __restrict__ codes, unsigned rel) {
+    const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
+    const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
+    return ((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh);
+}
+
+// one output word straight from global memory: nb (1..32) bases starting at text offset a
+__device__ __forceinline__ uint64_t fq_direct_word(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long a, unsigned nb,
+                                                   bool& bad) {
+    const unsigned long long a0 = a & ~15ull;
+    const unsigned off = (unsigned)(a & 15ull);
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c[k] = 0;
+        if (16u * k < off + nb) {
+            const uint4 x = enc_load_cached(bytes, n, a0 + 16ull * k);
+            uint32_t ignore = 0;
+            c[k] = pack16(x, ignore);
+            bad |= bad_in_range(x, (int)off - 16 * k, (int)(off + nb) - 16 * k);
+        }
+    }
+    const unsigned sh = 2u * off;
+    uint64_t w = ((uint64_t)__funnelshift_r(c[1], c[2], sh) << 32) | __funnelshift_r(c[0], c[1], sh);
+    if (nb < 32) w &= (1ull << (2 * nb)) - 1ull;
+    return w;
+}
+
+struct FqLongSeg {
+    unsigned long long first;  // its first output word
+    unsigned rel;              // byte offset of its first base inside the strip
+    unsigned count;            // words
+    unsigned tail;             // bases in its last word
+    unsigned pad;
+};
+
+template <int kTile, int kBThreads, int kMinCtas>
+__global__ void __launch_bounds__(kBThreads, kMinCtas)
+fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
+                    unsigned long long n_tiles1, unsigned long long n_reads, const uint64_t* __restrict__ seq_off,
+                    const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off, uint64_t* __restrict__ out,
+                    unsigned long long* __restrict__ status) {
+    constexpr int kMainVecs = kTile / 16;
+    constexpr int kOver = 3;                                  // a word that starts in the tile ends at most 47 bytes past it
+    constexpr int kRatio = kTile / kFqTile;
+    constexpr int kLongCap = kTile / (32 * kFqLongWords) + 2;
+    constexpr int kWarps = kBThreads / 32;
+    static_assert(kMainVecs % (4 * kBThreads) == 0, "tile must be a whole number of load rounds");
+    __shared__ uint32_t codes[kMainVecs + 8];
+    __shared__ uint32_t flags[kMainVecs / 32 + 1];
+    __shared__ FqLongSeg segs[kLongCap];
+    __shared__ uint16_t chunks[kMainVecs / 32 + kLongCap + 2];
+    __shared__ unsigned n_segs, n_chunks, spill_j0;
+    __shared__ unsigned long long spill_r;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long tile0 = (unsigned long long)blockIdx.x * kTile;
+    // reads whose header line ends in this tile (so their sequence starts in it, or on the first byte after it)
+    const unsigned long long t1a = (unsigned long long)blockIdx.x * kRatio;
+    const unsigned long long t1b = t1a + kRatio < n_tiles1 ? t1a + kRatio : n_tiles1;
+    unsigned long long ra = (line_base[t1a] + 3) >> 2, rb = (line_base[t1b] + 3) >> 2;
+    ra = ra < n_reads ? ra : n_reads;
+    rb = rb < n_reads ? rb : n_reads;
+    if (ra >= rb) return;   // nothing starts here (e.g. the inside of a long read): the tile is not even loaded
+    if (tid == 0) {
+        n_segs = 0;
+        n_chunks = 0;
+        spill_j0 = 0xFFFFFFFFu;
+    }
+    // ---- phase 1: pack the tile's text, 16 bytes per thread step, into the code strip; one validity flag per vector
+    for (unsigned vb = 0; vb < (unsigned)kMainVecs; vb += 4 * kBThreads) {
+        uint4 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned long long pos = tile0 + 16ull * (vb + j * kBThreads + tid);
+            x[j] = pos + 16 <= n ? ld128<LD_NC_NOALLOC>(reinterpret_cast<const uint4*>(bytes + pos)) : enc_load_edge(bytes, n, pos);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned v = vb + j * kBThreads + tid;
+            uint32_t bad = 0;
+            codes[v] = pack16(x[j], bad);
+            const unsigned fb = __ballot_sync(0xffffffffu, (bad & kValidMask) != 0u);
+            if (lane == 0) flags[v >> 5] = fb;
+        }
+    }
+    if (warp == 0) {   // the overhang (and the slack words cut_word may touch)
+        const unsigned v = kMainVecs + lane;
+        uint32_t bad = 0, c = 0;
+        if (lane < kOver) c = pack16(enc_load_cached(bytes, n, tile0 + 16ull * v), bad);
+        if (lane < 8) codes[v] = c;
+        const unsigned fb = __ballot_sync(0xffffffffu, (bad & kValidMask) != 0u);
+        if (lane == 0) flags[kMainVecs >> 5] = fb;
+    }
+    __syncthreads();
+    // ---- phase 2a: one read per thread
+    for (unsigned long long r = ra + tid; r < rb; r += kBThreads) {
+        const unsigned long long s = __ldg(seq_off + r), len = __ldg(seq_len + r), wo = __ldg(word_off + r);
+        if (len == 0) continue;
+        const unsigned long long nw = (len + 31) >> 5;
+        const unsigned rel = (unsigned)(s - tile0);                              // 1 .. kTile
+        const unsigned cap = (kTile + 16u - rel + 31u) >> 5;                     // words whose first base is < kTile + 16
+        const unsigned n_in = nw < cap ? (unsigned)nw : cap;
+        const unsigned bases_in = len < 32ull * n_in ? (unsigned)len : 32u * n_in;
+        if (strip_range_invalid(bytes, n, tile0, flags, rel, rel + bases_in)) fq_report_range(bytes, s, s + len, status);
+        if (n_in < nw) {   // at most one read runs past the strip
+            spill_r = r;
+            spill_j0 = n_in;
+        }
+        const unsigned tail = n_in == nw ? (unsigned)(len - 32ull * (nw - 1)) : 32u;
+        if (n_in > (unsigned)kFqLongWords) {
+            const unsigned slot = atomicAdd(&n_segs, 1u);
+            const unsigned nch = (n_in + 31u) / 32u;
+            const unsigned cb = atomicAdd(&n_chunks, nch);
+            segs[slot] = FqLongSeg{wo, rel, n_in, tail, 0u};
+            for (unsigned c = 0; c < nch; ++c) chunks[cb + c] = (uint16_t)(slot << 8 | c);
+            continue;
+        }
+        uint64_t* o = out + wo;
+        unsigned q = rel;
+        for (unsigned j = 0; j + 1 < n_in; ++j, q += 32) o[j] = fq_cut_word(codes, q);
+        uint64_t w = fq_cut_word(codes, q);
+        if (tail < 32) w &= (1ull << (2 * tail)) - 1ull;
+        o[n_in - 1] = w;
+    }
+    __syncthreads();
+    // ---- phase 2b: long in-strip segments, 32 consecutive words per warp step
+    const unsigned nc = n_chunks;
+    for (unsigned k = warp; k < nc; k += kWarps) {
+        const unsigned ch = chunks[k];
+        const FqLongSeg sg = segs[ch >> 8];
+        const unsigned j = (ch & 0xFFu) * 32u + lane;
+        if (j < sg.count) {
+            uint64_t w = fq_cut_word(codes, sg.rel + 32u * j);
+            if (j + 1 == sg.count && sg.tail < 32) w &= (1ull << (2 * sg.tail)) - 1ull;
+            out[sg.first + j] = w;
+        }
+    }
+    // ---- phase 2c: the rest of the read that runs past the strip, straight from global memory
+    if (spill_j0 != 0xFFFFFFFFu) {
+        const unsigned long long r = spill_r;
+        const unsigned long long s = __ldg(seq_off + r), len = __ldg(seq_len + r), wo = __ldg(word_off + r);
+        const unsigned long long nw = (len + 31) >> 5;
+        for (unsigned long long j = spill_j0 + tid; j < nw; j += kBThreads) {
+            const unsigned long long a = s + 32ull * j;
+            const unsigned nb = len - 32ull * j < 32ull ? (unsigned)(len - 32ull * j) : 32u;
+            bool bad = false;
+            out[wo + j] = fq_direct_word(bytes, n, a, nb, bad);
+            if (bad) fq_report_range(bytes, a, a + nb, status);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launchers ----------------------------------------
+// d_scratch (fastq_scratch_bytes): counts[n_tiles] | line_base[n_tiles + 1] | scan sums
+// d_index_scratch (fastq_index_scratch_bytes): nl[4 n_reads] | scan sums
+
+static inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+size_t fastq_scratch_bytes(size_t n_bytes) {
+    const size_t t = fastq_tiles(n_bytes);
+    return align16(t * 8) + align16((t + 1) * 8) + scan_scratch_bytes(t);
+}
+size_t fastq_index_scratch_bytes(size_t n_reads) { return align16((n_reads ? n_reads : 1) * 32) + scan_scratch_bytes(n_reads ? n_reads : 1); }
+
+struct FqScratch {
+    unsigned long long* counts;
+    uint64_t* line_base;
+    unsigned long long* sums;
+    unsigned long long n_tiles;
+    FqScratch(void* p, size_t n_bytes) {
+        n_tiles = fastq_tiles(n_bytes);
+        char* c = static_cast<char*>(p);
+        counts = reinterpret_cast<unsigned long long*>(c);
+        line_base = reinterpret_cast<uint64_t*>(c + align16(n_tiles * 8));
+        sums = reinterpret_cast<unsigned long long*>(c + align16(n_tiles * 8) + align16((n_tiles + 1) * 8));
+    }
+};
+
+cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
+                               cudaStream_t s) {
+    if (n_bytes == 0) return cudaMemsetAsync(d_n_lines, 0, sizeof(uint64_t), s);
+    const FqScratch sc(d_scratch, n_bytes);
+    fastq_count_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts);
+    launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(d_n_lines, sc.line_base + sc.n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s);
+}
+
+cudaError_t launch_fastq_index(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
+                               void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets,
+                               unsigned long long* d_status, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_status, 0xFF, 2 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    if (n_bytes == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
+    const FqScratch sc(d_scratch, n_bytes);
+    uint64_t* nl = static_cast<uint64_t*>(d_index_scratch);
+    // runs even without a whole record: the faults of a partial one are found here
+    fastq_index_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status);
+    if (n_reads == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
+    unsigned long long* sums2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(d_index_scratch) + align16(n_reads * 32));
+    fastq_records_kernel<<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens, d_status);
+    launch_exclusive_scan(WordsOfLen{d_seq_lens}, n_reads, sums2, d_word_offsets, s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
+                                const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets,
+                                uint64_t* d_out_words, unsigned long long* d_status, cudaStream_t s) {
+    if (n_reads == 0 || n_bytes == 0) return cudaSuccess;
+    const FqScratch sc(d_scratch, n_bytes);
+    constexpr int kRatio = kFqEncTile / kFqTile;
+    const unsigned long long n_tiles2 = ceil_div(sc.n_tiles, kRatio);
+    fastq_encode_kernel<kFqEncTile, 128, 8><<<(unsigned)n_tiles2, 128, 0, s>>>(d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets,
+                                                                              d_seq_lens, d_word_offsets, d_out_words, d_status);
+    return cudaGetLastError();
+}
+
+}  // namespace bn

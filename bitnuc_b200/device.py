@@ -186,6 +186,51 @@ def encode_batch(data: torch.Tensor, offsets: torch.Tensor, max_words: int | Non
     return words, wo, rs, status
 
 
+class FastqStatus:
+    """Device-side status of ``fastq_encode``: [0] min(text offset << 8 | byte) over invalid bases, [1] min(record << 8 | fault)."""
+
+    def __init__(self, device):
+        self.word = torch.empty(2, dtype=torch.int64, device=device)
+        self.ctx = api.default_context(torch.device(device).index or 0)
+        self.n_lines, self.seq_offsets, self.n_reads = 0, None, 0
+
+    def check(self):
+        """Synchronises the current stream; raises ``FastqError`` first, else ``NucleotideError.InvalidBase``."""
+        err = BnError()
+        rc = self.ctx.lib.bn_fastq_status_fetch(self.ctx.handle, _stream(), _ptr(self.word), self.n_lines, _ptr(self.seq_offsets),
+                                                self.n_reads, C.byref(err))
+        if rc == 1:
+            e = _lib.NucleotideError.InvalidBase(err.base)
+            e.record, e.position, e.offset = int(err.record), int(err.b), int(err.offset)
+            raise e
+        raise_for(rc, err)
+
+
+def fastq_encode(text: torch.Tensor, status: FastqStatus | None = None):
+    """FASTQ text resident in HBM -> (words, word_offsets, seq_offsets, seq_lens, status), all on the device.  Two small
+    read-backs size the outputs (number of lines, number of words); ``status.check()`` reports faults."""
+    ctx = _ctx_for(text)
+    dev, n_bytes = text.device, text.numel()
+    status = status or FastqStatus(dev)
+    scratch = torch.empty(max(16, ctx.lib.bn_fastq_scratch_bytes(n_bytes)), dtype=torch.uint8, device=dev)
+    n_lines_t = torch.zeros(1, dtype=torch.int64, device=dev)
+    raise_for(ctx.lib.bn_fastq_count_dev(ctx.handle, _stream(), _ptr(text), n_bytes, _ptr(scratch), _ptr(n_lines_t)))
+    n_lines = int(n_lines_t.item())
+    n = n_lines // 4
+    iscratch = torch.empty(max(16, ctx.lib.bn_fastq_index_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+    so = torch.empty(max(1, n), dtype=torch.int64, device=dev)
+    sl = torch.empty(max(1, n), dtype=torch.int64, device=dev)
+    wo = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    raise_for(ctx.lib.bn_fastq_index_dev(ctx.handle, _stream(), _ptr(text), n_bytes, n, _ptr(scratch), _ptr(iscratch), _ptr(so), _ptr(sl),
+                                         _ptr(wo), _ptr(status.word)))
+    n_words = int(wo[n].item())
+    words = torch.empty(max(1, n_words), dtype=torch.int64, device=dev)
+    raise_for(ctx.lib.bn_fastq_encode_dev(ctx.handle, _stream(), _ptr(text), n_bytes, n, _ptr(scratch), _ptr(so), _ptr(sl), _ptr(wo),
+                                          _ptr(words), _ptr(status.word)))
+    status.n_lines, status.seq_offsets, status.n_reads = n_lines, so, n
+    return words[:n_words], wo, so[:n], sl[:n], status
+
+
 class SplitStatus:
     """Device-side status of ``split_packed_batch``: min over failing reads of (read << 1 | kind)."""
 

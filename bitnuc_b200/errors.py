@@ -77,3 +77,18 @@ class ReferencePanic(RuntimeError):
 class BitnucCudaError(RuntimeError):
     """CUDA / argument failure below the C ABI: no reference variant exists for these and there is
     no CPU fallback, so they surface loudly."""
+
+
+class FastqError(ValueError):
+    """Malformed FASTQ text (``BN_ERR_FASTQ``): ``record`` is the first faulty record in file order, ``fault`` is
+    1 header without '@', 2 separator without '+', 3 quality and sequence lengths differ, 4 text ends inside the record."""
+
+    FAULTS = {1: "header line does not start with '@'", 2: "separator line does not start with '+'",
+              3: "quality and sequence lengths differ", 4: "text ends inside the record"}
+
+    def __init__(self, record: int, fault: int):
+        super().__init__(f"FASTQ record {record}: {self.FAULTS.get(fault, 'malformed record')}")
+        self.record, self.fault = int(record), int(fault)
+
+    def key(self):
+        return (self.record, self.fault)

@@ -49,8 +49,16 @@ typedef enum bn_status {
     BN_ERR_ARGUMENT = -2,       /* NULL / misaligned / inconsistent arguments */
     BN_ERR_EMPTY_ENCODE = -3,   /* encode of an empty sequence: the reference panics
                                    (src/utils/packing/avx.rs:138); bindings should panic too */
-    BN_ERR_NOMEM = -4
+    BN_ERR_NOMEM = -4,
+    BN_ERR_FASTQ = -5           /* malformed FASTQ text (bn_fastq_*): err->record = the record, err->a = bn_fastq_fault */
 } bn_status;
+
+typedef enum bn_fastq_fault {
+    BN_FASTQ_BAD_HEADER = 1,          /* line 4r does not start with '@' */
+    BN_FASTQ_BAD_SEPARATOR = 2,       /* line 4r+2 does not start with '+' */
+    BN_FASTQ_BAD_QUALITY_LENGTH = 3,  /* line 4r+3 is not as long as the sequence */
+    BN_FASTQ_TRUNCATED = 4            /* the text ends inside record r */
+} bn_fastq_fault;
 
 typedef struct bn_error {
     int32_t code;        /* bn_status */
@@ -179,6 +187,20 @@ int bn_slice_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uin
  * index >= len -> BN_INDEX_OUT_OF_BOUNDS{index, len} for the first such query (err->record). */
 int bn_get_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, size_t n_reads, const uint64_t *q_read, const uint64_t *q_index, size_t nq, uint8_t *out, bn_error_t *err);
 
+/* FASTQ text -> record offsets -> per-read packed words, parsed on the device (the reference has no
+ * parser, README.md:160-180 shows the caller's loop `for record in reader { PackedSequence::new(record.seq())? }`
+ * that this replaces, src/sequence.rs:40-52).  Strict four-line records: '@' header, sequence, '+' separator,
+ * quality as long as the sequence; "\n" or "\r\n" line ends; the last newline may be missing.
+ * bn_fastq_scan uploads the text, finds the records and returns the sizes the caller must allocate:
+ * *n_reads, and *n_words = sum of ceil(len/32).  A malformed record -> BN_ERR_FASTQ (first in file order).
+ * bn_fastq_encode (same text, right after the scan: the context still holds the upload and the index) fills
+ * out_words[n_words], out_word_offsets[n_reads+1] (read r = out_words[out_word_offsets[r] ..), every read on a fresh
+ * word), seq_offsets[n_reads] (byte offset of each sequence line in the text) and seq_lens[n_reads]; any of the last
+ * three may be NULL.  The first byte outside ACGTacgt in file order -> BN_INVALID_BASE (err->record = the read,
+ * err->b = its position inside the read, err->offset = its offset in the text). */
+int bn_fastq_scan(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t *n_reads, size_t *n_words, bn_error_t *err);
+int bn_fastq_encode(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t *out_words, uint64_t *out_word_offsets, uint64_t *seq_offsets, uint64_t *seq_lens, bn_error_t *err);
+
 /* ------------------------------------------------------------------ device-pointer calls ---- */
 /* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.
  * Pointers are device pointers.  ASCII and packed buffers should be 16-byte aligned: that selects the fast kernels
@@ -224,6 +246,24 @@ int bn_kmers_batch_dev(bn_ctx *ctx, void *stream, const uint8_t *d_bytes, const 
 size_t bn_slice_batch_scratch_bytes(size_t nq);
 int bn_slice_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, const uint64_t *d_q_read, const uint64_t *d_q_start, const uint64_t *d_q_end, size_t nq, uint8_t *d_out, uint64_t *d_out_offsets, uint64_t *d_status, void *d_scratch);
 int bn_get_batch_dev(bn_ctx *ctx, void *stream, const uint64_t *d_words, const uint64_t *d_word_offsets, const uint64_t *d_lens, size_t n_reads, const uint64_t *d_q_read, const uint64_t *d_q_index, size_t nq, uint8_t *d_out, uint64_t *d_status);
+
+/* FASTQ on the device, three enqueue-only steps with the two sizes read back by the caller in between.  d_text must
+ * be 16-byte aligned.  d_scratch: bn_fastq_scratch_bytes(n_bytes) bytes, shared by the three calls.
+ *   1. bn_fastq_count_dev: *d_n_lines (device uint64_t) = number of lines.  n_reads = n_lines / 4 (a remainder means
+ *      the text ends inside a record: bn_fastq_status_fetch reports it).
+ *   2. bn_fastq_index_dev: d_seq_offsets[n_reads], d_seq_lens[n_reads], d_word_offsets[n_reads+1] (the last entry is
+ *      the number of output words); d_index_scratch: bn_fastq_index_scratch_bytes(n_reads) bytes, 16-byte aligned.
+ *      d_status = two device uint64_t, reset here: [0] min(text offset << 8 | byte) over invalid bases (written by
+ *      step 3), [1] min(record << 8 | bn_fastq_fault) over malformed records.
+ *   3. bn_fastq_encode_dev: d_out_words[d_word_offsets[n_reads]].
+ * bn_fastq_status_fetch synchronises and translates d_status (n_lines as read back after step 1): BN_ERR_FASTQ first,
+ * then BN_INVALID_BASE with err->record / err->b resolved through d_seq_offsets. */
+size_t bn_fastq_scratch_bytes(size_t n_bytes);
+size_t bn_fastq_index_scratch_bytes(size_t n_reads);
+int bn_fastq_count_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, void *d_scratch, uint64_t *d_n_lines);
+int bn_fastq_index_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, void *d_index_scratch, uint64_t *d_seq_offsets, uint64_t *d_seq_lens, uint64_t *d_word_offsets, uint64_t *d_status);
+int bn_fastq_encode_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, const uint64_t *d_seq_offsets, const uint64_t *d_seq_lens, const uint64_t *d_word_offsets, uint64_t *d_out_words, uint64_t *d_status);
+int bn_fastq_status_fetch(bn_ctx *ctx, void *stream, const uint64_t *d_status, uint64_t n_lines, const uint64_t *d_seq_offsets, size_t n_reads, bn_error_t *err);
 
 /* d_out needs n - k + 1 words; any alignment of d_seq. */
 int bn_kmers_dev(bn_ctx *ctx, void *stream, const uint8_t *d_seq, size_t n, uint32_t k, uint64_t *d_out, uint64_t *d_status);

@@ -297,6 +297,45 @@ int orc_split_packed(const uint64_t *ebuf, size_t n_words, size_t slen, size_t i
 
 /* ------------------------------------------------------------------ synthetic input --------- */
 
+/* FASTQ record scanning: one sequential walk over the lines, the way a reader would do it. */
+int orc_fastq_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *lens, size_t cap, size_t *n_reads,
+                   uint64_t *bad_record, int *fault) {
+    size_t pos = 0, r = 0;
+    *n_reads = 0;
+    while (pos < n) {
+        size_t ls[4], ll[4]; /* start and length (without "\n" / "\r\n") of the record's four lines */
+        int have = 0;
+        for (int k = 0; k < 4 && pos < n; ++k) {
+            size_t e = pos;
+            while (e < n && text[e] != '\n') ++e;
+            size_t len = e - pos;
+            if (len && text[e - 1] == '\r') --len;
+            ls[k] = pos;
+            ll[k] = len;
+            pos = e < n ? e + 1 : n;
+            have = k + 1;
+        }
+        /* faults in file order: the header's first byte, the separator's first byte, the quality length, the end */
+        int f = 0;
+        if (text[ls[0]] != '@') f = 1;
+        else if (have >= 3 && (ls[2] >= n || text[ls[2]] != '+')) f = 2;
+        else if (have == 4 && ll[3] != ll[1]) f = 3;
+        else if (have < 4) f = 4;
+        if (f) {
+            *bad_record = r;
+            *fault = f;
+            return -5;
+        }
+        if (r < cap) {
+            starts[r] = ls[1];
+            lens[r] = ll[1];
+        }
+        ++r;
+        *n_reads = r;
+    }
+    return 0;
+}
+
 uint64_t orc_splitmix64(uint64_t x) {
     uint64_t z = x + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -85,6 +85,15 @@ double orc_gc_content(const uint64_t *data, size_t length);
 int orc_split_packed(const uint64_t *ebuf, size_t n_words, size_t slen, size_t idx, uint64_t *lbuf,
                      size_t *n_left, uint64_t *rbuf, size_t *n_right, orc_error *err);
 
+/* ---- FASTQ record scanning ---------------------------------------------------
+ * The reference has no parser (README.md:160-180 shows the caller's loop over a FASTQ reader); this is the
+ * definition the CUDA path is held to: strict four-line records ('@' header, sequence, '+' separator, quality as long
+ * as the sequence), "\n" or "\r\n" line ends, the last newline may be missing.  Fills starts[r] / lens[r] (byte offset
+ * and length of every sequence line; cap entries available) and *n_reads.  Returns 0, or -5 with *bad_record and
+ * *fault (1 header, 2 separator, 3 quality length, 4 text ends inside the record): the first fault in file order. */
+int orc_fastq_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *lens, size_t cap, size_t *n_reads,
+                   uint64_t *bad_record, int *fault);
+
 /* ---- synthetic input: counter-based splitmix64 stream --------------------- */
 uint64_t orc_splitmix64(uint64_t x);
 uint64_t orc_synth_word(uint64_t seed, uint64_t stream, uint64_t j);

@@ -135,3 +135,32 @@ def synth_ascii(seed: int, stream: int, n_bases: int) -> np.ndarray:
     """ASCII bases 0..n of a stream; by construction encode(synth_ascii) == synth_words (tail masked)."""
     w = synth_words(seed, stream, 0, (n_bases + 31) // 32)
     return decode(w, n_bases)
+
+
+def fastq_scan(text: bytes):
+    """Independent restatement of orc_fastq_scan with Python's own line splitting: [(start, length)] of the sequence
+    lines, or ("fault", record, kind)."""
+    text = bytes(text)
+    lines, pos = [], 0
+    while pos < len(text):
+        e = text.find(b"\n", pos)
+        if e < 0:
+            e = len(text)
+        ln = e - pos
+        if ln and text[e - 1 : e] == b"\r":
+            ln -= 1
+        lines.append((pos, ln))
+        pos = e + 1
+    out = []
+    for r in range((len(lines) + 3) // 4):
+        rec = lines[4 * r : 4 * r + 4]
+        if text[rec[0][0] : rec[0][0] + 1] != b"@":
+            return ("fault", r, 1)
+        if len(rec) >= 3 and text[rec[2][0] : rec[2][0] + 1] != b"+":
+            return ("fault", r, 2)
+        if len(rec) == 4 and rec[3][1] != rec[1][1]:
+            return ("fault", r, 3)
+        if len(rec) < 4:
+            return ("fault", r, 4)
+        out.append(rec[1])
+    return out

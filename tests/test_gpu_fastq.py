@@ -1,0 +1,205 @@
+"""GPU parity of the FASTQ path through the C ABI: bn_fastq_scan / bn_fastq_encode (host pointers)
+and the three *_dev calls (device pointers) against the oracle's reader + per-record encode, on the hand-written
+cases, on random texts with adversarial shapes (reads across tile boundaries, CRLF, empties, long reads), and on
+every fault / invalid-base position class."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from test_oracle_fastq import make_fastq
+
+pytestmark = pytest.mark.gpu
+
+CASES = json.loads((Path(__file__).parent / "golden" / "fastq_cases.json").read_text())
+ENC_TILE = 65536
+
+
+@pytest.fixture(scope="module")
+def bn():
+    import bitnuc_b200
+    return bitnuc_b200
+
+
+@pytest.fixture(scope="module")
+def dv():
+    from bitnuc_b200 import device
+    return device
+
+
+def expected(text: bytes):
+    """('ok', words, wo, so, sl) | ('fault', record, kind) | ('base', byte, record, position, offset)"""
+    try:
+        starts, lens = oracle.fastq_scan(text)
+    except oracle.FastqFault as e:
+        return ("fault", e.record, e.fault)
+    t = np.frombuffer(text, dtype=np.uint8)
+    words, offs = [], [0]
+    for r, (s, l) in enumerate(zip(starts.tolist(), lens.tolist())):
+        if l:
+            try:
+                words.append(oracle.encode_np(t[s : s + l]))
+            except oracle.OracleError as e:
+                seq = text[s : s + l]
+                pos = next(i for i, b in enumerate(seq) if b not in b"ACGTacgt")
+                assert e.key() == ("InvalidBase", seq[pos])
+                return ("base", seq[pos], r, pos, s + pos)
+        offs.append(offs[-1] + (l + 31) // 32)
+    w = np.concatenate(words) if words else np.zeros(0, dtype=np.uint64)
+    return ("ok", w, np.asarray(offs, dtype=np.uint64), starts, lens)
+
+
+def run_host(bn, text: bytes):
+    try:
+        w, wo, so, sl = bn.fastq_encode(np.frombuffer(text, dtype=np.uint8))
+    except bn.FastqError as e:
+        return ("fault", e.record, e.fault)
+    except bn.NucleotideError as e:
+        assert e.variant == "InvalidBase"
+        return ("base", e.payload[0], e.record, e.position, e.offset)
+    return ("ok", w, wo, so, sl)
+
+
+def run_dev(dv, bn, text: bytes):
+    import torch
+    t = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).cuda() if text else torch.empty(0, dtype=torch.uint8, device="cuda")
+    w, wo, so, sl, st = dv.fastq_encode(t)
+    try:
+        st.check()
+    except bn.FastqError as e:
+        return ("fault", e.record, e.fault)
+    except bn.NucleotideError as e:
+        return ("base", e.payload[0], e.record, e.position, e.offset)
+    u = lambda x: x.cpu().numpy().view(np.uint64)
+    return ("ok", u(w), u(wo), u(so), u(sl))
+
+
+def same(a, b):
+    if a[0] != b[0]:
+        return False
+    if a[0] != "ok":
+        return tuple(int(x) for x in a[1:]) == tuple(int(x) for x in b[1:])
+    return all(np.array_equal(np.asarray(x, dtype=np.uint64), np.asarray(y, dtype=np.uint64)) for x, y in zip(a[1:], b[1:]))
+
+
+def check(bn, dv, text: bytes):
+    exp = expected(text)
+    got_h, got_d = run_host(bn, text), run_dev(dv, bn, text)
+    assert same(got_h, exp), (got_h[:1], exp[:1], got_h[1:] if got_h[0] != "ok" else "", exp[1:] if exp[0] != "ok" else "")
+    assert same(got_d, exp), (got_d[:1], exp[:1], got_d[1:] if got_d[0] != "ok" else "", exp[1:] if exp[0] != "ok" else "")
+    return exp
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_cases(bn, dv, case):
+    exp = check(bn, dv, case["text"].encode())
+    if "fault" in case:
+        assert exp == ("fault", *case["fault"])
+    elif exp[0] == "ok":
+        assert [[int(s), int(l)] for s, l in zip(exp[3], exp[4])] == case["reads"]
+
+
+@pytest.mark.parametrize("kind", ["short", "tiny", "empties", "long", "mixed", "giant"])
+@pytest.mark.parametrize("crlf", [False, True])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_texts(bn, dv, kind, crlf, seed):
+    rng = np.random.default_rng(100 * seed + len(kind) + 7 * crlf)
+    n = int(rng.integers(1, 600))
+    if kind == "short":
+        lens = rng.integers(100, 152, n)
+    elif kind == "tiny":
+        lens = rng.integers(0, 6, n)
+    elif kind == "empties":
+        lens = np.where(rng.random(n) < 0.7, 0, rng.integers(1, 80, n))
+    elif kind == "long":
+        lens = rng.integers(1500, 12000, min(n, 40))
+    elif kind == "mixed":
+        lens = (rng.pareto(1.1, n) * 60).astype(np.int64) % 40_000
+    else:
+        lens = rng.integers(1, 200, min(n, 50))
+        lens[int(rng.integers(0, lens.size))] = 200_000 + int(rng.integers(0, 70))
+    text = make_fastq(rng, lens, crlf=crlf, final_newline=bool(rng.integers(0, 2)), alphabet=b"ACGTacgt")
+    exp = check(bn, dv, text)
+    assert exp[0] == "ok" and [int(x) for x in exp[4]] == [int(x) for x in lens]
+
+
+def _text_with_read_at(rng, start: int, length: int, before: int = 3, after: int = 3):
+    """A text whose read `before` has its sequence line starting exactly at byte `start`."""
+    head = make_fastq(rng, rng.integers(20, 60, before))
+    pad = start - len(head) - 1           # header line "@" + pad chars + "\n" puts the sequence at `start`
+    assert pad >= 1
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seq = al[rng.integers(0, 4, length)].tobytes()
+    rec = b"@" + b"h" * (pad - 1) + b"\n" + seq + b"\n+\n" + b"I" * length + b"\n"
+    text = head + rec + make_fastq(rng, rng.integers(20, 60, after))
+    assert text[start : start + length] == seq
+    return text
+
+
+@pytest.mark.parametrize("delta", [-40, -33, -32, -17, -16, -15, -1, 0, 1, 15, 16, 17])
+@pytest.mark.parametrize("length", [1, 31, 32, 33, 47, 48, 49, 150, 5000, 70_000])
+def test_reads_around_a_tile_boundary(bn, dv, delta, length):
+    rng = np.random.default_rng(abs(delta) * 131 + length)
+    text = _text_with_read_at(rng, ENC_TILE + delta, length)
+    exp = check(bn, dv, text)
+    assert exp[0] == "ok"
+
+
+@pytest.mark.parametrize("where", ["first", "head_partial", "interior", "tail_partial", "last", "spill", "spill_last"])
+@pytest.mark.parametrize("byte", [ord("N"), 0, 255, ord("\r") + 1, ord("@")])
+def test_invalid_base_positions(bn, dv, where, byte):
+    rng = np.random.default_rng(len(where) * 17 + byte)
+    length = 400 if not where.startswith("spill") else 3000
+    start = ENC_TILE - (200 if where.startswith("spill") else 5000) + 5      # misaligned on purpose
+    text = bytearray(_text_with_read_at(rng, start, length))
+    pos = {"first": 0, "head_partial": 3, "interior": 201, "tail_partial": length - 2, "last": length - 1,
+           "spill": 1500, "spill_last": length - 1}[where]
+    text[start + pos] = byte
+    exp = check(bn, dv, bytes(text))
+    assert exp[0] == "base" and exp[1:] == (byte, 3, pos, start + pos)
+
+
+def test_first_invalid_base_in_file_order_wins(bn, dv):
+    rng = np.random.default_rng(9)
+    lens = rng.integers(50, 300, 2000)
+    text = bytearray(make_fastq(rng, lens))
+    starts, _ = oracle.fastq_scan(bytes(text))
+    hits = sorted(int(x) for x in rng.choice(2000, 30, replace=False))
+    for r in hits:
+        text[int(starts[r]) + int(rng.integers(0, lens[r]))] = ord("N")
+    exp = check(bn, dv, bytes(text))
+    assert exp[0] == "base" and exp[2] == hits[0]
+
+
+@pytest.mark.parametrize("fault", [1, 2, 3])
+def test_faults_deep_inside_a_text(bn, dv, fault):
+    rng = np.random.default_rng(fault)
+    lens = rng.integers(80, 200, 3000)
+    text = bytearray(make_fastq(rng, lens))
+    starts, _ = oracle.fastq_scan(bytes(text))
+    for r in (2500, 1700):      # two faulty records: the earlier one is reported
+        s, l = int(starts[r]), int(lens[r])
+        if fault == 1:
+            text[text.rfind(b"@", 0, s)] = ord("x")
+        elif fault == 2:
+            text[s + l + 1] = ord("-")
+        else:                    # drop one quality byte (the later record first, so the earlier offsets stay valid)
+            del text[s + l + 3]
+    # an invalid base earlier in the file does not mask the format fault
+    text[int(starts[10]) + 5] = ord("N")
+    exp = check(bn, dv, bytes(text))
+    assert exp == ("fault", 1700, fault)
+
+
+def test_truncated_text_and_large_text(bn, dv):
+    rng = np.random.default_rng(5)
+    lens = rng.integers(100, 152, 60_000)          # ~19 MB of text: several hundred tiles
+    text = make_fastq(rng, lens)
+    exp = check(bn, dv, text)
+    assert exp[0] == "ok" and exp[2][-1] == sum((int(l) + 31) // 32 for l in lens)
+    cut = text[: len(text) - 40]                   # ends inside the last record's quality line: lengths differ
+    assert check(bn, dv, cut)[0] == "fault"
+    cut = text[: text.rfind(b"+")]                 # ends before the last separator
+    assert check(bn, dv, cut) == ("fault", 59_999, 4)

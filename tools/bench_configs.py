@@ -319,6 +319,67 @@ def next_rows(scale, reps):
     report(f"slice gathers: {reads} windows of 50 bases out of 150 bp reads", ms, (16 + 16 + 24 + 50 + 8) * reads, reads, "queries")
 
 
+def fastq(scale, reps):
+    """SURVEY.md 8(f) row 3, first half: FASTQ text resident in HBM -> record offsets -> per-read packed words
+    (count + index + encode), on 20 M x 150 bp reads (23-byte header lines, so every alignment occurs) and on
+    10 kbp reads.  Checked against bn_encode_batch_dev of the same sequences."""
+    ctx = dv.api.default_context(0)
+    for n_reads, rl, hdr in ((int(20_000_000 * scale), 150, 23), (int(300_000 * scale), 10_000, 37)):
+        rec = hdr + rl + 1 + 2 + rl + 1
+        seqs = dv.synth_ascii(SEED, 7, 0, n_reads * rl).view(n_reads, rl)
+        text2 = torch.full((n_reads, rec), ord("I"), dtype=torch.uint8, device="cuda")
+        text2[:, 0] = ord("@")
+        text2[:, 1 : hdr - 1] = ord("h")
+        text2[:, hdr - 1] = 10
+        text2[:, hdr : hdr + rl] = seqs
+        text2[:, hdr + rl] = 10
+        text2[:, hdr + rl + 1] = ord("+")
+        text2[:, hdr + rl + 2] = 10
+        text2[:, rec - 1] = 10
+        text = text2.view(-1)
+        n_bytes = text.numel()
+        scratch = torch.empty(ctx.lib.bn_fastq_scratch_bytes(n_bytes), dtype=torch.uint8, device="cuda")
+        iscratch = torch.empty(ctx.lib.bn_fastq_index_scratch_bytes(n_reads), dtype=torch.uint8, device="cuda")
+        n_lines = torch.zeros(1, dtype=torch.int64, device="cuda")
+        so = torch.empty(n_reads, dtype=torch.int64, device="cuda")
+        sl = torch.empty(n_reads, dtype=torch.int64, device="cuda")
+        wo = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+        wpr = (rl + 31) // 32
+        words = torch.empty(n_reads * wpr, dtype=torch.int64, device="cuda")
+        st = dv.FastqStatus("cuda")
+        P = dv._ptr
+
+        def count():
+            dv.raise_for(ctx.lib.bn_fastq_count_dev(ctx.handle, dv._stream(), P(text), n_bytes, P(scratch), P(n_lines)))
+
+        def index():
+            dv.raise_for(ctx.lib.bn_fastq_index_dev(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, P(scratch), P(iscratch), P(so), P(sl),
+                                                    P(wo), P(st.word)))
+
+        def encode():
+            dv.raise_for(ctx.lib.bn_fastq_encode_dev(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, P(scratch), P(so), P(sl), P(wo),
+                                                     P(words), P(st.word)))
+
+        def whole():
+            count(), index(), encode()
+
+        ms_c, ms_i, ms_e, ms = timed(count, reps), timed(index, reps), timed(encode, reps), timed(whole, reps)
+        st.n_lines, st.seq_offsets, st.n_reads = int(n_lines.item()), so, n_reads
+        st.check()
+        assert st.n_lines == 4 * n_reads and int(wo[-1].item()) == n_reads * wpr
+        assert torch.equal(sl, torch.full_like(sl, rl)) and torch.equal(so, torch.arange(n_reads, device="cuda") * rec + hdr)
+        offs = torch.arange(n_reads + 1, dtype=torch.int64, device="cuda") * rl
+        ref_words, ref_wo, _, bst = dv.encode_batch(seqs.reshape(-1), offs)
+        bst.check()
+        assert torch.equal(ref_wo, wo) and torch.equal(ref_words[: n_reads * wpr], words)
+        del ref_words, ref_wo
+        alg = n_bytes + 8 * n_reads * wpr + 24 * n_reads
+        extra = {"count_ms": round(ms_c, 4), "index_ms": round(ms_i, 4), "encode_ms": round(ms_e, 4), "text_bytes": n_bytes,
+                 "text_GB/s": round(n_bytes / (ms * 1e-3) / 1e9, 1)}
+        report(f"fastq scan+encode reads={n_reads} x {rl} bp", ms, alg, n_reads * rl, "bases", extra)
+        del text, text2, seqs, words, scratch, iscratch
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
@@ -328,7 +389,7 @@ def main():
     torch.cuda.set_device(0)
     print(json.dumps({"device": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak(), "scale": args.scale}), flush=True)
     for name in args.only.split(","):
-        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "short": short_reads, "next": next_rows}[name](args.scale, args.reps)
+        {"cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "short": short_reads, "next": next_rows, "fastq": fastq}[name](args.scale, args.reps)
         torch.cuda.empty_cache()
 
 

@@ -10,13 +10,17 @@
 // may lack its newline.  A format error wins over an invalid base; among errors of a kind the first in file order.
 //
 // Device steps (tiles of 16 KiB of text, handed out by the hardware CTA scheduler):
-//   1. fastq_count_kernel    newlines per tile (word-parallel exact byte compare, one POPC per 16 bytes)
+//   1. fastq_lines_kernel    one pass over the text: newlines per tile (word-parallel exact byte compare), and every
+//                            newline leaves a 32-bit entry in its tile's slot row: position inside the tile, "a '\r'
+//                            precedes it", "the next line opens with '@'", "... with '+'"
 //      + exclusive scan      -> line index of every tile's first newline, number of lines
-//   2. fastq_index_kernel    every newline writes its position into nl[line]; the thread that owns a newline also
-//                            checks the first byte of the following line ('@' after a quality line, '+' after a
-//                            sequence line) and notes a preceding '\r'
-//      fastq_records_kernel  nl[4r .. 4r+3] -> seq_offsets[r], seq_lens[r]; quality length checked
+//   2. fastq_records_slots_kernel   a warp per tile: record r takes its four entries (walking into the following
+//                            tiles where a line crosses a tile boundary) -> seq_offsets[r], seq_lens[r]; header,
+//                            separator and quality length checked.  The text is not read again.
 //      + exclusive scan      of ceil(len/32) -> word_offsets
+//      A tile with more than 2048 lines (average line under 8 bytes) does not fit its slot row: the count pass raises a
+//      flag and step 2 runs the dense form instead (fastq_index_kernel re-reads the text and writes nl[line], then
+//      fastq_records_kernel) -- both forms are launched, the device-side flag decides which one works.
 //   3. fastq_encode_kernel   PACK THEN CUT over tiles of 64 KiB of text: the whole tile (headers and qualities too) is
 //                            packed like the contiguous encode -- aligned coalesced 128-bit loads, 16 bytes -> one
 //                            32-bit code, one "contains a non-ACGT byte" flag per vector via a ballot -- into a
@@ -24,7 +28,7 @@
 //                            words out of the strip (batch.cu's cut_word).  A read is valid when the flags of its
 //                            interior vectors are clear and its two partial end vectors pass a byte-masked test.
 //                            The one read that runs past the tile is finished straight from global memory.
-// HBM traffic: the text is read three times (count, index, encode).  Algorithmic bytes: text once + 8 B per word out
+// HBM traffic: the text is read twice (lines, encode).  Algorithmic bytes: text once + 8 B per word out
 // + 24 B per read of offsets.
 #include "common.cuh"
 #include "launch.cuh"
@@ -37,6 +41,8 @@ constexpr int kFqThreads = 256;              // x 4 vectors of 16 bytes
 constexpr int kFqEncTile = 65536;            // bytes of text per encode tile
 constexpr int kFqLongWords = 64;             // a read with more words than this inside the strip is cut by whole warps
 constexpr unsigned long long kCrBit = 1ull << 63;
+constexpr int kFqSlots = 2048;               // line entries per tile (more lines than this: the dense fallback)
+constexpr uint32_t kSlotPos = 0x3FFFu, kSlotCr = 1u << 14, kSlotAt = 1u << 15, kSlotPlus = 1u << 16;
 
 enum { FQ_BAD_HEADER = 1, FQ_BAD_SEPARATOR = 2, FQ_BAD_QUALITY_LENGTH = 3 };   // kinds of format error (4 = truncated: host)
 
@@ -72,9 +78,6 @@ __device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return (((f >>
 
 constexpr uint32_t kNl4 = 0x0A0A0A0Au;
 
-__device__ __forceinline__ uint32_t newline_count16(uint4 v) {
-    return __popc(eq_flags(v.x, kNl4) | (eq_flags(v.y, kNl4) >> 1) | (eq_flags(v.z, kNl4) >> 2) | (eq_flags(v.w, kNl4) >> 3));
-}
 // bit i set iff byte i of the vector is '\n'
 __device__ __forceinline__ uint32_t newline_mask16(uint4 v) {
     return flags_to_nibble(eq_flags(v.x, kNl4)) | (flags_to_nibble(eq_flags(v.y, kNl4)) << 4) |
@@ -88,18 +91,47 @@ __device__ __forceinline__ void report_min(unsigned long long* word, unsigned lo
 // ---------------------------------------------------------------- 1. newlines per tile -----------------------------
 
 __global__ void __launch_bounds__(kFqThreads)
-fastq_count_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts) {
-    __shared__ unsigned long long scratch[32];
+fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
+                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow) {
+    __shared__ __align__(8) uint16_t nlb[kFqTile / 16];
+    __shared__ unsigned warp_tot[kFqThreads / 32];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool virt = n && bytes[n - 1] != '\n';
     const unsigned long long tile0 = (unsigned long long)blockIdx.x * kFqTile;
     uint4 x[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (threadIdx.x + j * kFqThreads));
-    unsigned c = 0;
+    for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (tid + j * kFqThreads));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c += newline_count16(x[j]);
-    const unsigned long long total = block_sum_u64(c, scratch);
-    if (threadIdx.x == 0) counts[blockIdx.x] = total;
+    for (int j = 0; j < 4; ++j) nlb[tid + j * kFqThreads] = (uint16_t)newline_mask16(x[j]);
+    __syncthreads();
+    // thread t owns bytes [64 t, 64 t + 64) of the tile: four consecutive vectors
+    const uint2 mm = *reinterpret_cast<const uint2*>(nlb + 4 * tid);
+    unsigned long long m = ((unsigned long long)mm.y << 32) | mm.x;
+    const unsigned cnt = __popcll(m);
+    unsigned inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned rank = inc - cnt;
+    for (unsigned w = 0; w < warp; ++w) rank += warp_tot[w];
+    if (tid == kFqThreads - 1) {
+        counts[blockIdx.x] = rank + cnt;
+        if (rank + cnt > (unsigned)kFqSlots) *overflow = 1u;
+    }
+    uint32_t* row = slots + (unsigned long long)blockIdx.x * kFqSlots;
+    while (m && rank < (unsigned)kFqSlots) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const unsigned q = 64u * tid + b;
+        const unsigned long long p = tile0 + q;                      // <= n (n itself only for the virtual newline)
+        const bool cr = p > 0 && bytes[p - 1] == '\r';
+        const uint32_t c = p + 1 < n ? bytes[p + 1] : '\n';
+        row[rank++] = q | (cr ? kSlotCr : 0u) | (c == '@' ? kSlotAt : 0u) | (c == '+' ? kSlotPlus : 0u);
+    }
 }
 
 struct CountOfTile {
@@ -111,9 +143,11 @@ struct CountOfTile {
 
 __global__ void __launch_bounds__(kFqThreads)
 fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
-                   unsigned long long n_reads, uint64_t* __restrict__ nl, unsigned long long* __restrict__ status) {
+                   unsigned long long n_reads, uint64_t* __restrict__ nl, unsigned long long* __restrict__ status,
+                   const unsigned* __restrict__ overflow) {
     __shared__ __align__(8) uint16_t nlb[kFqTile / 16];
     __shared__ unsigned warp_tot[kFqThreads / 32];
+    if (*overflow == 0u) return;   // the slot rows hold every line: fastq_records_slots_kernel does the work
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool virt = n && bytes[n - 1] != '\n';
     const unsigned long long tile0 = (unsigned long long)blockIdx.x * kFqTile;
@@ -162,15 +196,54 @@ fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, cons
 
 __global__ void __launch_bounds__(kThreads)
 fastq_records_kernel(const uint64_t* __restrict__ nl, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
-                     uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status) {
+                     uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow) {
     const unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
-    if (r >= n_reads) return;
+    if (r >= n_reads || *overflow == 0u) return;
     const ulonglong2 ab = reinterpret_cast<const ulonglong2*>(nl)[2 * r], cd = reinterpret_cast<const ulonglong2*>(nl)[2 * r + 1];
     const unsigned long long s = (ab.x & ~kCrBit) + 1, e = (ab.y & ~kCrBit) - (ab.y >> 63);
     const unsigned long long qs = (cd.x & ~kCrBit) + 1, qe = (cd.y & ~kCrBit) - (cd.y >> 63);
     if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
     seq_off[r] = s;
     seq_len[r] = e - s;
+}
+
+// records from the slot rows, a warp per tile: the records whose header line ends in the tile
+constexpr int kFqRecWarps = 8;
+__global__ void __launch_bounds__(32 * kFqRecWarps)
+fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ line_base, const uint32_t* __restrict__ slots,
+                           unsigned long long n_tiles, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
+                           uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow) {
+    if (*overflow != 0u) return;
+    const unsigned long long t = (unsigned long long)blockIdx.x * kFqRecWarps + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long n_lines = line_base[n_tiles];
+    const unsigned long long lb = line_base[t], le = line_base[t + 1];
+    const unsigned long long n_records = (n_lines + 3) >> 2;            // a trailing partial record included (its faults count)
+    unsigned long long ra = (lb + 3) >> 2, rb = (le + 3) >> 2;
+    rb = rb < n_records ? rb : n_records;
+    if (t == 0 && lane == 0 && n_lines && bytes[0] != '@') report_min(status + 1, FQ_BAD_HEADER);
+    for (unsigned long long r = ra + lane; r < rb; r += 32) {
+        unsigned long long pos[4] = {0, 0, 0, 0};
+        uint32_t ent[4] = {0, 0, 0, 0};
+        unsigned long long tt = t;
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long L = 4 * r + k;
+            if (L >= n_lines) break;
+            while (L >= line_base[tt + 1]) ++tt;                      // a line that ends in a later tile
+            ent[k] = slots[tt * kFqSlots + (L - line_base[tt])];
+            pos[k] = tt * kFqTile + (ent[k] & kSlotPos);
+        }
+        if (4 * r + 2 < n_lines && !(ent[1] & kSlotPlus)) report_min(status + 1, (r << 8) | FQ_BAD_SEPARATOR);
+        if (4 * r + 4 < n_lines && !(ent[3] & kSlotAt)) report_min(status + 1, ((r + 1) << 8) | FQ_BAD_HEADER);
+        if (r < n_reads) {
+            const unsigned long long s = pos[0] + 1, e = pos[1] - ((ent[1] & kSlotCr) ? 1 : 0);
+            const unsigned long long qs = pos[2] + 1, qe = pos[3] - ((ent[3] & kSlotCr) ? 1 : 0);
+            if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
+            seq_off[r] = s;
+            seq_len[r] = e - s;
+        }
+    }
 }
 
 struct WordsOfLen {
@@ -409,7 +482,7 @@ static inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 size_t fastq_scratch_bytes(size_t n_bytes) {
     const size_t t = fastq_tiles(n_bytes);
-    return align16(t * 8) + align16((t + 1) * 8) + scan_scratch_bytes(t);
+    return align16(t * 8) + align16((t + 1) * 8) + align16(scan_scratch_bytes(t)) + 16 + t * kFqSlots * sizeof(uint32_t);
 }
 size_t fastq_index_scratch_bytes(size_t n_reads) { return align16((n_reads ? n_reads : 1) * 32) + scan_scratch_bytes(n_reads ? n_reads : 1); }
 
@@ -417,13 +490,20 @@ struct FqScratch {
     unsigned long long* counts;
     uint64_t* line_base;
     unsigned long long* sums;
+    unsigned* overflow;
+    uint32_t* slots;
     unsigned long long n_tiles;
     FqScratch(void* p, size_t n_bytes) {
         n_tiles = fastq_tiles(n_bytes);
         char* c = static_cast<char*>(p);
         counts = reinterpret_cast<unsigned long long*>(c);
-        line_base = reinterpret_cast<uint64_t*>(c + align16(n_tiles * 8));
-        sums = reinterpret_cast<unsigned long long*>(c + align16(n_tiles * 8) + align16((n_tiles + 1) * 8));
+        c += align16(n_tiles * 8);
+        line_base = reinterpret_cast<uint64_t*>(c);
+        c += align16((n_tiles + 1) * 8);
+        sums = reinterpret_cast<unsigned long long*>(c);
+        c += align16(scan_scratch_bytes(n_tiles));
+        overflow = reinterpret_cast<unsigned*>(c);
+        slots = reinterpret_cast<uint32_t*>(c + 16);
     }
 };
 
@@ -431,9 +511,11 @@ cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t
                                cudaStream_t s) {
     if (n_bytes == 0) return cudaMemsetAsync(d_n_lines, 0, sizeof(uint64_t), s);
     const FqScratch sc(d_scratch, n_bytes);
-    fastq_count_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts);
+    cudaError_t e = cudaMemsetAsync(sc.overflow, 0, 16, s);
+    if (e != cudaSuccess) return e;
+    fastq_lines_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow);
     launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(d_n_lines, sc.line_base + sc.n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s);
 }
@@ -446,11 +528,14 @@ cudaError_t launch_fastq_index(const DeviceInfo&, const uint8_t* d_bytes, size_t
     if (n_bytes == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
     const FqScratch sc(d_scratch, n_bytes);
     uint64_t* nl = static_cast<uint64_t*>(d_index_scratch);
-    // runs even without a whole record: the faults of a partial one are found here
-    fastq_index_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status);
+    // both forms are enqueued; the overflow flag left by the count pass lets exactly one of them work.  They run even
+    // without a whole record: the faults of a partial one are found here.
+    fastq_records_slots_kernel<<<(unsigned)ceil_div(sc.n_tiles, kFqRecWarps), 32 * kFqRecWarps, 0, s>>>(
+        d_bytes, sc.line_base, sc.slots, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow);
+    fastq_index_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status, sc.overflow);
     if (n_reads == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
     unsigned long long* sums2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(d_index_scratch) + align16(n_reads * 32));
-    fastq_records_kernel<<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens, d_status);
+    fastq_records_kernel<<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow);
     launch_exclusive_scan(WordsOfLen{d_seq_lens}, n_reads, sums2, d_word_offsets, s);
     return cudaGetLastError();
 }

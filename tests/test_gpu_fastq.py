@@ -125,6 +125,25 @@ def test_random_texts(bn, dv, kind, crlf, seed):
     assert exp[0] == "ok" and [int(x) for x in exp[4]] == [int(x) for x in lens]
 
 
+@pytest.mark.parametrize("mix", ["all_dense", "dense_then_normal", "normal_then_dense"])
+def test_dense_lines_take_the_fallback_index(bn, dv, mix):
+    """More than 2048 lines in a 16 KiB tile (average line under 8 bytes) overflow the slot rows: the dense index runs."""
+    rng = np.random.default_rng(len(mix))
+    dense = rng.integers(0, 4, 6000)
+    normal = rng.integers(100, 152, 300)
+    lens = {"all_dense": dense, "dense_then_normal": np.concatenate([dense, normal]),
+            "normal_then_dense": np.concatenate([normal, dense])}[mix]
+    text = make_fastq(rng, lens, alphabet=b"ACGTacgt")
+    assert text.count(b"\n") * 8 > len(text) or mix != "all_dense"
+    exp = check(bn, dv, text)
+    assert exp[0] == "ok" and [int(x) for x in exp[4]] == [int(x) for x in lens]
+    bad = bytearray(text)
+    sep = int(exp[3][-1]) + int(exp[4][-1]) + 1      # the last record's separator line (quality bytes may hold a '+' too)
+    assert bad[sep] == ord("+")
+    bad[sep] = ord("-")
+    assert check(bn, dv, bytes(bad)) == ("fault", len(lens) - 1, 2)
+
+
 def _text_with_read_at(rng, start: int, length: int, before: int = 3, after: int = 3):
     """A text whose read `before` has its sequence line starting exactly at byte `start`."""
     head = make_fastq(rng, rng.integers(20, 60, before))

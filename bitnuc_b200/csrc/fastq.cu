@@ -25,8 +25,11 @@
 //                            packed like the contiguous encode -- aligned coalesced 128-bit loads, 16 bytes -> one
 //                            32-bit code, one "contains a non-ACGT byte" flag per vector via a ballot -- into a
 //                            shared-memory strip; then one thread per read that starts in the tile cuts the read's
-//                            words out of the strip (batch.cu's cut_word).  A read is valid when the flags of its
-//                            interior vectors are clear and its two partial end vectors pass a byte-masked test.
+//                            words out of the strip (batch.cu's cut_word).  Phase 1 also leaves a 16-bit map of the
+//                            non-ACGT bytes of every vector: a read is valid when the flags of its interior vectors
+//                            are clear and the maps of its two partial end vectors are clear under a byte-range mask
+//                            (the first version re-read the end vectors from global memory: ncu showed 128-byte
+//                            line fills for them, +70 % DRAM traffic).
 //                            The one read that runs past the tile is finished straight from global memory.
 // HBM traffic: the text is read twice (lines, encode).  Algorithmic bytes: text once + 8 B per word out
 // + 24 B per read of offsets.
@@ -42,6 +45,7 @@ constexpr int kFqEncTile = 65536;            // bytes of text per encode tile
 constexpr int kFqLongWords = 64;             // a read with more words than this inside the strip is cut by whole warps
 constexpr unsigned long long kCrBit = 1ull << 63;
 constexpr int kFqSlots = 2048;               // line entries per tile (more lines than this: the dense fallback)
+constexpr int kFqListCap = kFqSlots;        // newlines of a tile finished by the slot path (beyond: overflow anyway)
 constexpr uint32_t kSlotPos = 0x3FFFu, kSlotCr = 1u << 14, kSlotAt = 1u << 15, kSlotPlus = 1u << 16;
 
 enum { FQ_BAD_HEADER = 1, FQ_BAD_SEPARATOR = 2, FQ_BAD_QUALITY_LENGTH = 3 };   // kinds of format error (4 = truncated: host)
@@ -90,24 +94,55 @@ __device__ __forceinline__ void report_min(unsigned long long* word, unsigned lo
 
 // ---------------------------------------------------------------- 1. newlines per tile -----------------------------
 
+// per vector: bit 8k + i set iff byte 4i + k (byte k of word i) is '\n' -- three ALU ops per word, no gather
+__device__ __forceinline__ uint32_t nl_flags(uint32_t w) {       // exact, 0x80 per matching byte
+    const uint32_t t = ((w ^ kNl4) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;  // bit 7 set iff the low seven bits differ from '\n'
+    return ~(t | w | 0x7F7F7F7Fu);                                // ... and bit 7 of the byte itself is clear ('\n' < 0x80)
+}
+__device__ __forceinline__ uint32_t newline_bits_by_word(uint4 v) {
+    return (nl_flags(v.x) >> 7) | (nl_flags(v.y) >> 6) | (nl_flags(v.z) >> 5) | (nl_flags(v.w) >> 4);
+}
+
+// the four vectors a thread loads of a tile (lane-consecutive: coalesced)
+__device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0, unsigned tid,
+                                                uint4 (&x)[4]) {
+    if (tile0 + kFqTile <= n) {
+        const uint4* src = reinterpret_cast<const uint4*>(bytes + tile0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = ld128<LD_NC_NOALLOC>(src + tid + j * kFqThreads);
+    } else {  // the last tile(s): the virtual newline and the NUL padding come from the edge loader
+        const bool virt = n && bytes[n - 1] != '\n';
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (tid + j * kFqThreads));
+    }
+}
+
+// One tile per CTA, handed out by the hardware scheduler.  (Persistent CTAs that prefetch the next tile's vectors into
+// registers while working on the current one were measured: 54 registers, 4 CTAs per SM, 16 % slower.)
 __global__ void __launch_bounds__(kFqThreads)
 fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
-                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow) {
-    __shared__ __align__(8) uint16_t nlb[kFqTile / 16];
+                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long n_tiles) {
+    __shared__ uint4 raw[kFqTile / 16];                   // the tile's text: the bytes next to a newline are looked up here
+    __shared__ __align__(16) uint32_t nlg[kFqTile / 16];  // newline bits of every vector
+    __shared__ uint16_t list[kFqListCap];                 // positions of the tile's newlines
     __shared__ unsigned warp_tot[kFqThreads / 32];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool virt = n && bytes[n - 1] != '\n';
-    const unsigned long long tile0 = (unsigned long long)blockIdx.x * kFqTile;
+    {
+    const unsigned long long tile = blockIdx.x;
+    const unsigned long long tile0 = tile * kFqTile;
     uint4 x[4];
+    lines_load_tile(bytes, n, tile0, tid, x);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (tid + j * kFqThreads));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) nlb[tid + j * kFqThreads] = (uint16_t)newline_mask16(x[j]);
+    for (int j = 0; j < 4; ++j) {
+        raw[tid + j * kFqThreads] = x[j];
+        nlg[tid + j * kFqThreads] = newline_bits_by_word(x[j]);
+    }
     __syncthreads();
     // thread t owns bytes [64 t, 64 t + 64) of the tile: four consecutive vectors
-    const uint2 mm = *reinterpret_cast<const uint2*>(nlb + 4 * tid);
-    unsigned long long m = ((unsigned long long)mm.y << 32) | mm.x;
-    const unsigned cnt = __popcll(m);
+    const uint4 g4 = *reinterpret_cast<const uint4*>(nlg + 4 * tid);
+    // the four vectors' bits in one 64-bit word: bit 32 h + 8 k + 4 jj + i <-> vector 2 h + jj, byte 4 i + k
+    unsigned long long G = ((unsigned long long)(g4.z | (g4.w << 4)) << 32) | (g4.x | (g4.y << 4));
+    const unsigned cnt = __popcll(G);
     unsigned inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -116,21 +151,44 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
     }
     if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    unsigned rank = inc - cnt;
-    for (unsigned w = 0; w < warp; ++w) rank += warp_tot[w];
-    if (tid == kFqThreads - 1) {
-        counts[blockIdx.x] = rank + cnt;
-        if (rank + cnt > (unsigned)kFqSlots) *overflow = 1u;
+    unsigned rank = inc - cnt, total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < kFqThreads / 32; ++w) {
+        const unsigned wt = warp_tot[w];
+        rank += w < warp ? wt : 0u;
+        total += wt;
     }
-    uint32_t* row = slots + (unsigned long long)blockIdx.x * kFqSlots;
-    while (m && rank < (unsigned)kFqSlots) {
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const unsigned q = 64u * tid + b;
-        const unsigned long long p = tile0 + q;                      // <= n (n itself only for the virtual newline)
-        const bool cr = p > 0 && bytes[p - 1] == '\r';
-        const uint32_t c = p + 1 < n ? bytes[p + 1] : '\n';
-        row[rank++] = q | (cr ? kSlotCr : 0u) | (c == '@' ? kSlotAt : 0u) | (c == '+' ? kSlotPlus : 0u);
+    if (tid == 0) {
+        counts[tile] = total;
+        if (total > (unsigned)kFqSlots) *overflow = 1u;
+    }
+    // ---- the thread's newlines go to a shared list at its rank, in any order inside its 64 bytes ...
+    while (G) {
+        const unsigned b = __ffsll((long long)G) - 1;
+        G &= G - 1;
+        const unsigned q = 64u * tid + 32u * (b >> 5) + 16u * ((b >> 2) & 1u) + 4u * (b & 3u) + ((b >> 3) & 3u);
+        if (rank < (unsigned)kFqListCap) list[rank] = (uint16_t)q;
+        ++rank;
+    }
+    __syncthreads();
+    // ---- ... and are finished densely, one list entry per thread: its rank in file order, the bytes next to it, the slot
+    const uint8_t* rb = reinterpret_cast<const uint8_t*>(raw);
+    uint32_t* row = slots + tile * kFqSlots;
+    const unsigned n_list = total < (unsigned)kFqListCap ? total : (unsigned)kFqListCap;
+    for (unsigned e = tid; e < n_list; e += kFqThreads) {
+        const unsigned q = list[e], span = q >> 6;
+        unsigned first = e, smaller = 0;                       // entries of one span are adjacent in the list
+        while (first > 0 && (list[first - 1] >> 6) == span) --first;
+        for (unsigned f = first; f < n_list && (list[f] >> 6) == span; ++f) smaller += list[f] < q ? 1u : 0u;
+        const unsigned slot = first + smaller;
+        uint32_t prev, next;
+        if (q > 0) prev = rb[q - 1];
+        else prev = tile0 ? bytes[tile0 - 1] : 0u;
+        if (q + 1 < (unsigned)kFqTile) next = rb[q + 1];        // past the text the staged bytes are the virtual newline / NUL
+        else next = tile0 + q + 1 < n ? bytes[tile0 + q + 1] : 0u;
+        if (slot < (unsigned)kFqSlots)
+            row[slot] = q | (prev == '\r' ? kSlotCr : 0u) | (next == '@' ? kSlotAt : 0u) | (next == '+' ? kSlotPlus : 0u);
+    }
     }
 }
 
@@ -144,13 +202,15 @@ struct CountOfTile {
 __global__ void __launch_bounds__(kFqThreads)
 fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
                    unsigned long long n_reads, uint64_t* __restrict__ nl, unsigned long long* __restrict__ status,
-                   const unsigned* __restrict__ overflow) {
+                   const unsigned* __restrict__ overflow, unsigned long long n_tiles) {
     __shared__ __align__(8) uint16_t nlb[kFqTile / 16];
     __shared__ unsigned warp_tot[kFqThreads / 32];
     if (*overflow == 0u) return;   // the slot rows hold every line: fastq_records_slots_kernel does the work
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool virt = n && bytes[n - 1] != '\n';
-    const unsigned long long tile0 = (unsigned long long)blockIdx.x * kFqTile;
+    // a modest grid strides over the tiles: launched after every count pass, it must cost nothing when it has no work
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long tile0 = tile * kFqTile;
     uint4 x[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) x[j] = fq_load(bytes, n, virt, tile0 + 16ull * (tid + j * kFqThreads));
@@ -172,9 +232,9 @@ fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, cons
     unsigned rank = inc - cnt;
     for (unsigned w = 0; w < warp; ++w) rank += warp_tot[w];
     const unsigned long long n_whole = 4 * n_reads;              // nl[] holds the lines of whole records
-    const unsigned long long n_lines = line_base[gridDim.x];     // all lines, a trailing partial record included
-    if (blockIdx.x == 0 && tid == 0 && n_lines && bytes[0] != '@') report_min(status + 1, FQ_BAD_HEADER);
-    unsigned long long L = line_base[blockIdx.x] + rank;
+    const unsigned long long n_lines = line_base[n_tiles];     // all lines, a trailing partial record included
+    if (tile == 0 && tid == 0 && n_lines && bytes[0] != '@') report_min(status + 1, FQ_BAD_HEADER);
+    unsigned long long L = line_base[tile] + rank;
     while (m) {
         const int b = __ffsll((long long)m) - 1;
         m &= m - 1;
@@ -192,19 +252,22 @@ fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, cons
         }
         ++L;
     }
+    __syncthreads();   // nlb / warp_tot are reused by the next tile
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
 fastq_records_kernel(const uint64_t* __restrict__ nl, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
                      uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow) {
-    const unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
-    if (r >= n_reads || *overflow == 0u) return;
+    if (*overflow == 0u) return;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; r < n_reads; r += (unsigned long long)gridDim.x * kThreads) {
     const ulonglong2 ab = reinterpret_cast<const ulonglong2*>(nl)[2 * r], cd = reinterpret_cast<const ulonglong2*>(nl)[2 * r + 1];
     const unsigned long long s = (ab.x & ~kCrBit) + 1, e = (ab.y & ~kCrBit) - (ab.y >> 63);
     const unsigned long long qs = (cd.x & ~kCrBit) + 1, qe = (cd.y & ~kCrBit) - (cd.y >> 63);
     if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
     seq_off[r] = s;
     seq_len[r] = e - s;
+    }
 }
 
 // records from the slot rows, a warp per tile: the records whose header line ends in the tile
@@ -298,27 +361,53 @@ static __device__ __noinline__ void fq_report_range(const uint8_t* __restrict__ 
     }
 }
 
-// Is there an invalid byte in tile bytes [lo, hi), hi > lo?  Whole vectors by their flags, the partial ones byte-masked.
-__device__ __forceinline__ bool strip_range_invalid(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0,
-                                                    const uint32_t* __restrict__ flags, unsigned lo, unsigned hi) {
+// 16 ASCII bytes -> 32 bits of packed codes (as pack16), and a 16-bit map of the bytes outside ACGTacgt:
+// bit 4k + i <-> byte k of word i (byte 4i + k of the vector) -- the order the word-parallel test produces.
+__device__ __forceinline__ uint32_t pack4_top_map(uint32_t w, uint32_t& nz) {
+    const uint32_t s1 = w >> 1, s2 = w >> 2;
+    const uint32_t code = (s1 ^ s2) & 0x03030303u;
+    const uint32_t tcol = s2 & ~s1 & 0x01010101u;
+    const uint32_t d = w ^ (tcol * 0x11u + 0x41414141u);    // under kValidMask: zero exactly in the valid bytes
+    const uint32_t t = (d & 0x59595959u) + 0x7F7F7F7Fu;     // bit 7 <- one of the checked low bits differs (no carry leaves a byte)
+    nz = (t | d) & 0x80808080u;                             // ... or bit 7 itself does
+    return code * 0x01041040u;
+}
+__device__ __forceinline__ uint32_t pack16_map(uint4 v, uint32_t& map16) {
+    uint32_t n0, n1, n2, n3;
+    const uint32_t p0 = pack4_top_map(v.x, n0), p1 = pack4_top_map(v.y, n1);
+    const uint32_t p2 = pack4_top_map(v.z, n2), p3 = pack4_top_map(v.w, n3);
+    const uint32_t vb = (n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4);   // bit 8k + i
+    map16 = __byte_perm(vb | (vb >> 4), 0u, 0x4420);                      // bit 4k + i
+    const uint32_t lo = __byte_perm(p0, p1, 0x7373), hi = __byte_perm(p2, p3, 0x7373);
+    return __byte_perm(lo, hi, 0x5410);
+}
+// the map bits of the vector's bytes 0 .. x-1 (x <= 16): whole words i < x/4, and bytes k < x%4 of word x/4
+__device__ __forceinline__ uint32_t map_below(unsigned x) {
+    const unsigned i = x >> 2, k = x & 3u;
+    return (0x1111u * ((1u << i) - 1u)) | ((0x1111u & ((1u << (4u * k)) - 1u)) << i);
+}
+
+// Is there an invalid byte in tile bytes [lo, hi), hi > lo?  Whole vectors by their flags, the partial ones by their maps.
+__device__ __forceinline__ bool strip_range_invalid(const uint32_t* __restrict__ flags, const uint16_t* __restrict__ maps, unsigned lo,
+                                                    unsigned hi) {
     const unsigned v_lo = (lo + 15u) >> 4, v_hi = hi >> 4;
-    bool bad = false;
+    uint32_t bad = 0;
     if (v_lo <= v_hi) {
-        if (lo & 15u) bad |= bad_in_range(enc_load_cached(bytes, n, tile0 + 16ull * (v_lo - 1)), (int)(lo & 15u), 16);
-        if (hi & 15u) bad |= bad_in_range(enc_load_cached(bytes, n, tile0 + 16ull * v_hi), 0, (int)(hi & 15u));
+        if (lo & 15u) bad |= maps[v_lo - 1] & ~map_below(lo & 15u);
+        if (hi & 15u) bad |= maps[v_hi] & map_below(hi & 15u);
         if (v_lo < v_hi) {
             const unsigned w_lo = v_lo >> 5, w_hi = (v_hi - 1u) >> 5;
             for (unsigned w = w_lo; w <= w_hi; ++w) {
                 uint32_t f = flags[w];
                 if (w == w_lo) f &= 0xFFFFFFFFu << (v_lo & 31u);
                 if (w == w_hi) f &= 0xFFFFFFFFu >> (31u - ((v_hi - 1u) & 31u));
-                bad |= f != 0u;
+                bad |= f;
             }
         }
     } else {  // both ends inside one vector
-        bad = bad_in_range(enc_load_cached(bytes, n, tile0 + 16ull * (lo >> 4)), (int)(lo & 15u), (int)(hi & 15u));
+        bad = maps[lo >> 4] & map_below(hi & 15u) & ~map_below(lo & 15u);
     }
-    return bad;
+    return bad != 0u;
 }
 
 // the output word whose first base sits `rel` bytes into the strip (same window as batch.cu)
@@ -371,7 +460,8 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
     constexpr int kWarps = kBThreads / 32;
     static_assert(kMainVecs % (4 * kBThreads) == 0, "tile must be a whole number of load rounds");
     __shared__ uint32_t codes[kMainVecs + 8];
-    __shared__ uint32_t flags[kMainVecs / 32 + 1];
+    __shared__ uint16_t maps[kMainVecs + 8];                  // per vector: which bytes are outside ACGTacgt
+    __shared__ uint32_t flags[kMainVecs / 32 + 1];            // per vector: any
     __shared__ FqLongSeg segs[kLongCap];
     __shared__ uint16_t chunks[kMainVecs / 32 + kLongCap + 2];
     __shared__ unsigned n_segs, n_chunks, spill_j0;
@@ -401,18 +491,22 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned v = vb + j * kBThreads + tid;
-            uint32_t bad = 0;
-            codes[v] = pack16(x[j], bad);
-            const unsigned fb = __ballot_sync(0xffffffffu, (bad & kValidMask) != 0u);
+            uint32_t map16;
+            codes[v] = pack16_map(x[j], map16);
+            maps[v] = (uint16_t)map16;
+            const unsigned fb = __ballot_sync(0xffffffffu, map16 != 0u);
             if (lane == 0) flags[v >> 5] = fb;
         }
     }
     if (warp == 0) {   // the overhang (and the slack words cut_word may touch)
         const unsigned v = kMainVecs + lane;
-        uint32_t bad = 0, c = 0;
-        if (lane < kOver) c = pack16(enc_load_cached(bytes, n, tile0 + 16ull * v), bad);
-        if (lane < 8) codes[v] = c;
-        const unsigned fb = __ballot_sync(0xffffffffu, (bad & kValidMask) != 0u);
+        uint32_t map16 = 0, c = 0;
+        if (lane < kOver) c = pack16_map(enc_load_cached(bytes, n, tile0 + 16ull * v), map16);
+        if (lane < 8) {
+            codes[v] = c;
+            maps[v] = (uint16_t)map16;
+        }
+        const unsigned fb = __ballot_sync(0xffffffffu, map16 != 0u);
         if (lane == 0) flags[kMainVecs >> 5] = fb;
     }
     __syncthreads();
@@ -425,7 +519,7 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
         const unsigned cap = (kTile + 16u - rel + 31u) >> 5;                     // words whose first base is < kTile + 16
         const unsigned n_in = nw < cap ? (unsigned)nw : cap;
         const unsigned bases_in = len < 32ull * n_in ? (unsigned)len : 32u * n_in;
-        if (strip_range_invalid(bytes, n, tile0, flags, rel, rel + bases_in)) fq_report_range(bytes, s, s + len, status);
+        if (strip_range_invalid(flags, maps, rel, rel + bases_in)) fq_report_range(bytes, s, s + len, status);
         if (n_in < nw) {   // at most one read runs past the strip
             spill_r = r;
             spill_j0 = n_in;
@@ -513,7 +607,7 @@ cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t
     const FqScratch sc(d_scratch, n_bytes);
     cudaError_t e = cudaMemsetAsync(sc.overflow, 0, 16, s);
     if (e != cudaSuccess) return e;
-    fastq_lines_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow);
+    fastq_lines_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles);
     launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -532,10 +626,13 @@ cudaError_t launch_fastq_index(const DeviceInfo&, const uint8_t* d_bytes, size_t
     // without a whole record: the faults of a partial one are found here.
     fastq_records_slots_kernel<<<(unsigned)ceil_div(sc.n_tiles, kFqRecWarps), 32 * kFqRecWarps, 0, s>>>(
         d_bytes, sc.line_base, sc.slots, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow);
-    fastq_index_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status, sc.overflow);
+    const unsigned long long dense_grid = sc.n_tiles < 148ull * 8 ? sc.n_tiles : 148ull * 8;
+    fastq_index_kernel<<<(unsigned)dense_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status, sc.overflow, sc.n_tiles);
     if (n_reads == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
     unsigned long long* sums2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(d_index_scratch) + align16(n_reads * 32));
-    fastq_records_kernel<<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow);
+    const unsigned long long rec_blocks = ceil_div(n_reads, kThreads);
+    fastq_records_kernel<<<(unsigned)(rec_blocks < 148ull * 8 ? rec_blocks : 148ull * 8), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens,
+                                                                                                      d_status, sc.overflow);
     launch_exclusive_scan(WordsOfLen{d_seq_lens}, n_reads, sums2, d_word_offsets, s);
     return cudaGetLastError();
 }

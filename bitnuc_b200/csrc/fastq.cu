@@ -33,6 +33,8 @@
 //                            The one read that runs past the tile is finished straight from global memory.
 // HBM traffic: the text is read twice (lines, encode).  Algorithmic bytes: text once + 8 B per word out
 // + 24 B per read of offsets.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.cuh"
 #include "scan.cuh"
@@ -642,10 +644,22 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
                                 uint64_t* d_out_words, unsigned long long* d_status, cudaStream_t s) {
     if (n_reads == 0 || n_bytes == 0) return cudaSuccess;
     const FqScratch sc(d_scratch, n_bytes);
-    constexpr int kRatio = kFqEncTile / kFqTile;
-    const unsigned long long n_tiles2 = ceil_div(sc.n_tiles, kRatio);
-    fastq_encode_kernel<kFqEncTile, 128, 8><<<(unsigned)n_tiles2, 128, 0, s>>>(d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets,
-                                                                              d_seq_lens, d_word_offsets, d_out_words, d_status);
+    // tile / CTA shape: BN_FQ_VARIANT picks one of the measured shapes (profiles/r01_sweep_fastq.txt); default = the fastest
+    static const int variant = [] {
+        const char* v = getenv("BN_FQ_VARIANT");
+        return v ? atoi(v) : 0;
+    }();
+#define BN_FQ_LAUNCH(TILE, THREADS, CTAS)                                                                                              \
+    fastq_encode_kernel<TILE, THREADS, CTAS><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \
+        d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status)
+    switch (variant) {
+    case 1: BN_FQ_LAUNCH(65536, 256, 4); break;
+    case 2: BN_FQ_LAUNCH(32768, 128, 8); break;
+    case 3: BN_FQ_LAUNCH(32768, 128, 12); break;
+    case 4: BN_FQ_LAUNCH(32768, 256, 6); break;
+    default: BN_FQ_LAUNCH(kFqEncTile, 128, 8); break;
+    }
+#undef BN_FQ_LAUNCH
     return cudaGetLastError();
 }
 

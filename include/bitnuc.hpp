@@ -190,6 +190,38 @@ inline std::vector<uint64_t> kmers(Bytes seq, size_t k) {
     return out;
 }
 
+// FASTQ text -> one PackedSequence-shaped record per read, parsed and encoded on the device: the caller's loop
+// `for record in reader { PackedSequence::new(record.seq())? }` (README.md:160-180, src/sequence.rs:40-52).
+struct FastqError : std::runtime_error {   // BN_ERR_FASTQ: the reference has no parser, hence no variant for this
+    uint64_t record;
+    int fault;                             // bn_fastq_fault
+    FastqError(uint64_t r, int f, const std::string& text) : std::runtime_error(text), record(r), fault(f) {}
+};
+struct FastqBatch {
+    std::vector<uint64_t> words, word_offsets;   // read r = words[word_offsets[r] .. word_offsets[r+1])
+    std::vector<uint64_t> seq_offsets, seq_lens; // where each sequence line sits in the text
+    size_t size() const { return seq_lens.size(); }
+};
+inline FastqBatch fastq_encode(Bytes text) {
+    FastqBatch out;
+    size_t n_reads = 0, n_words = 0;
+    bn_error_t e{};
+    int rc = bn_fastq_scan(detail::ctx(), text.ptr, text.len, &n_reads, &n_words, &e);
+    if (rc == BN_ERR_FASTQ) {
+        char buf[160];
+        bn_error_string(&e, buf, sizeof buf);
+        throw FastqError(e.record, static_cast<int>(e.a), buf);
+    }
+    detail::check(rc, e);
+    out.words.resize(n_words);
+    out.word_offsets.resize(n_reads + 1);
+    out.seq_offsets.resize(n_reads);
+    out.seq_lens.resize(n_reads);
+    detail::check(bn_fastq_encode(detail::ctx(), text.ptr, text.len, n_reads, n_words, out.words.data(), out.word_offsets.data(),
+                                  out.seq_offsets.data(), out.seq_lens.data(), &e), e);
+    return out;
+}
+
 // src/utils/functions/split.rs:14-20 -- validates idx <= slen, then clears both buffers and fills them
 inline void split_packed(Words ebuf, size_t slen, size_t idx, std::vector<uint64_t>& lbuf, std::vector<uint64_t>& rbuf) {
     const uint64_t word_offsets[2] = {0, ebuf.len}, len64 = slen, idx64 = idx;

@@ -123,6 +123,43 @@ pub fn kmers(seq: &[u8], k: usize) -> Result<Vec<u64>, NucleotideError> {
     Ok(out)
 }
 
+/// What a FASTQ text holds once it is parsed and packed: read `r` is `words[word_offsets[r]..word_offsets[r+1]]`
+/// (`seq_lens[r]` bases, each read on fresh words like `PackedSequence::new`), its sequence line sits at
+/// `text[seq_offsets[r]..][..seq_lens[r]]`.
+#[derive(Debug, Default, PartialEq, Eq, Clone)]
+pub struct FastqBatch {
+    pub words: Vec<u64>,
+    pub word_offsets: Vec<u64>,
+    pub seq_offsets: Vec<u64>,
+    pub seq_lens: Vec<u64>,
+}
+
+/// Malformed FASTQ or an invalid base: the reference has no parser, so the format faults get their own variant.
+#[derive(Debug, PartialEq, Eq)]
+pub enum FastqError {
+    /// `fault`: 1 header without '@', 2 separator without '+', 3 quality/sequence lengths differ, 4 truncated
+    Malformed { record: u64, fault: u8 },
+    Nucleotide { error: NucleotideError, record: u64, position: u64 },
+}
+
+/// The caller's loop `for record in reader { PackedSequence::new(record.seq())? }` (bitnuc README.md:160-180) in two
+/// calls on the raw text: records are found and encoded on the device.
+pub fn fastq_encode(text: &[u8]) -> Result<FastqBatch, FastqError> {
+    let (mut n_reads, mut n_words, mut e) = (0usize, 0usize, bn_error_t::default());
+    let rc = with_ctx(|c| unsafe { bn_fastq_scan(c, text.as_ptr(), text.len(), &mut n_reads, &mut n_words, &mut e) });
+    if rc == -5 {
+        return Err(FastqError::Malformed { record: e.record, fault: e.a as u8 });
+    }
+    check(rc, &e).map_err(|error| FastqError::Nucleotide { error, record: e.record, position: e.b })?;
+    let mut b = FastqBatch { words: vec![0; n_words], word_offsets: vec![0; n_reads + 1], seq_offsets: vec![0; n_reads], seq_lens: vec![0; n_reads] };
+    let rc = with_ctx(|c| unsafe {
+        bn_fastq_encode(c, text.as_ptr(), text.len(), n_reads, n_words, b.words.as_mut_ptr(), b.word_offsets.as_mut_ptr(),
+                        b.seq_offsets.as_mut_ptr(), b.seq_lens.as_mut_ptr(), &mut e)
+    });
+    check(rc, &e).map_err(|error| FastqError::Nucleotide { error, record: e.record, position: e.b })?;
+    Ok(b)
+}
+
 /// `bitnuc::split_packed` (src/utils/functions/split.rs:14-20): validates, then clears and fills both buffers.
 pub fn split_packed(ebuf: &[u64], slen: usize, idx: usize, lbuf: &mut Vec<u64>, rbuf: &mut Vec<u64>) -> Result<(), NucleotideError> {
     let word_offsets = [0u64, ebuf.len() as u64];

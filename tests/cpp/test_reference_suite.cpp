@@ -241,11 +241,33 @@ static void test_readme_kmer_counting() {
     CHECK(kmers("ACG", 4).empty());
 }
 
+// README.md:160-180: the caller's loop over a FASTQ reader, here one call on the raw text
+static void test_fastq_records() {
+    const std::string text = "@r1\nACGTACGT\n+\nIIIIIIII\n@r2 second\r\nacgtn\r\n+r2\r\n!!!!!\r\n";
+    CHECK(expect_err([&] { fastq_encode(text); }) == E(E::InvalidBase, 'n'));
+    const std::string ok = "@r1\nACGTACGT\n+\nIIIIIIII\n@r2 second\r\nacgtt\r\n+r2\r\n!!!!!\r\n@empty\n\n+\n\n";
+    const FastqBatch b = fastq_encode(ok);
+    CHECK(b.size() == 3);
+    CHECK(b.seq_lens[0] == 8 && b.seq_lens[1] == 5 && b.seq_lens[2] == 0);
+    CHECK(b.word_offsets == (std::vector<uint64_t>{0, 1, 2, 2}));
+    CHECK(b.words[0] == as_2bit("ACGTACGT") && b.words[1] == as_2bit("ACGTT"));
+    CHECK(ok.substr(b.seq_offsets[1], b.seq_lens[1]) == "acgtt");
+    bool threw = false;
+    try {
+        fastq_encode(std::string("@r1\nACGT\n-\nIIII\n"));
+    } catch (const FastqError& f) {
+        threw = f.record == 0 && f.fault == BN_FASTQ_BAD_SEPARATOR;
+    }
+    CHECK(threw);
+    CHECK(fastq_encode(std::string()).size() == 0);
+}
+
 int main() {
     const std::pair<const char*, std::function<void()>> tests[] = {
         {"as_2bit", test_as_2bit}, {"from_2bit", test_from_2bit}, {"roundtrips", test_roundtrips},
         {"hdist", test_hdist},     {"packed_sequence", test_packed_sequence}, {"errors", test_errors},
-        {"split_packed", test_split_packed}, {"readme_kmer_counting", test_readme_kmer_counting}};
+        {"split_packed", test_split_packed}, {"readme_kmer_counting", test_readme_kmer_counting},
+        {"fastq_records", test_fastq_records}};
     for (const auto& t : tests) {
         t.second();
         std::printf("ok %s\n", t.first);

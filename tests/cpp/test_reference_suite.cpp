@@ -244,7 +244,8 @@ static void test_readme_kmer_counting() {
 // README.md:160-180: the caller's loop over a FASTQ reader, here one call on the raw text
 static void test_fastq_records() {
     const std::string text = "@r1\nACGTACGT\n+\nIIIIIIII\n@r2 second\r\nacgtn\r\n+r2\r\n!!!!!\r\n";
-    CHECK(expect_err([&] { fastq_encode(text); }) == E(E::InvalidBase, 'n'));
+    const E bad = expect_err([&] { fastq_encode(text); });   // b carries the position inside the read
+    CHECK(bad.variant == E::InvalidBase && bad.a == 'n' && bad.b == 4);
     const std::string ok = "@r1\nACGTACGT\n+\nIIIIIIII\n@r2 second\r\nacgtt\r\n+r2\r\n!!!!!\r\n@empty\n\n+\n\n";
     const FastqBatch b = fastq_encode(ok);
     CHECK(b.size() == 3);

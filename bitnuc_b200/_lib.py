@@ -33,6 +33,8 @@ PROTOTYPES = {
     "bn_ctx_stream": (_vp, [_vp]),
     "bn_ctx_synchronize": (_int, [_vp]),
     "bn_ctx_set_chunk_bytes": (_int, [_vp, _sz]),
+    "bn_ctx_set_compat": (_int, [_vp, _int]),
+    "bn_ctx_compat": (_int, [_vp]),
     "bn_dev_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
     "bn_dev_free": (_int, [_vp, _vp]),
     "bn_host_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import BnError, raise_for
-from .errors import NucleotideError
+from .errors import NucleotideError, ReferencePanic
 
 M64 = (1 << 64) - 1
 
@@ -48,6 +48,15 @@ class Context:
 
     def set_chunk_bytes(self, n: int):
         raise_for(self.lib.bn_ctx_set_chunk_bytes(self.handle, n))
+
+    def set_compat(self, isa: str):
+        """Which of the reference's per-ISA paths is mirrored where they disagree: ``"x86_64"`` (default; packing/avx.rs,
+        unpacking/avx.rs) or ``"aarch64"`` (packing/aarch64.rs:173-244, unpacking/aarch64.rs:127-130) -- SURVEY.md 8f-4."""
+        raise_for(self.lib.bn_ctx_set_compat(self.handle, {"x86_64": 0, "aarch64": 1}[isa]))
+
+    @property
+    def compat(self) -> str:
+        return ("x86_64", "aarch64")[self.lib.bn_ctx_compat(self.handle)]
 
     def pinned_empty(self, n: int, dtype=np.uint8) -> np.ndarray:
         """A page-locked numpy array (freed with the context); host-pointer calls on it overlap."""
@@ -119,7 +128,19 @@ def encode(sequence, ebuf: list, ctx: Context | None = None) -> None:
     """``encode(&[u8], &mut Vec<u64>)`` (src/utils/mod.rs:22-25): clears ``ebuf``, then fills it.
     On ``InvalidBase`` ``ebuf`` keeps the words of the chunks before the failing chunk
     (src/utils/packing/avx.rs:132,142-143)."""
+    ctx = ctx or default_context()
     words, n, rc, err = _encode_raw(sequence, ctx)
+    if ctx.compat == "aarch64":
+        # packing/aarch64.rs:222-244: under 32 bases one word is PUSHED (nothing is cleared; nothing on error); from
+        # 32 bases on the Vec is resized to ceil(n/32) words, zero-filled and overwritten up to the failing block
+        size = len(_u8(sequence))
+        if size < 32:
+            if rc == 0:
+                ebuf.append(int(words[0]))
+        else:
+            ebuf[:] = [int(w) for w in words[:n]] + [0] * ((size + 31) // 32 - n)
+        raise_for(rc, err)
+        return
     if rc != _lib.BN_ERR_EMPTY_ENCODE:  # the reference panics before it clears anything useful
         ebuf.clear()
         ebuf.extend(int(w) for w in words[:n])
@@ -143,7 +164,19 @@ def decode_np(ebuf, n_bases: int, ctx: Context | None = None, out: np.ndarray | 
 
 
 def decode(ebuf, n_bases: int, dbuf: bytearray, ctx: Context | None = None) -> None:
-    """``decode(&[u64], usize, &mut Vec<u8>)`` (src/utils/mod.rs:60-62): appends to ``dbuf``."""
+    """``decode(&[u64], usize, &mut Vec<u8>)`` (src/utils/mod.rs:60-62): appends to ``dbuf`` -- or, in aarch64 mode,
+    resizes it to ``n_bases`` and overwrites it (src/utils/unpacking/aarch64.rs:127-130), words missing from ``ebuf``
+    reading as zero in the whole 32-base chunks (``input.get(i).copied().unwrap_or(0)``, :113) and panicking in the tail."""
+    ctx = ctx or default_context()
+    if ctx.compat == "aarch64":
+        w = _u64(ebuf)
+        need = (n_bases + 31) // 32
+        if w.size < need:
+            if n_bases % 32 and w.size < need:      # the scalar tail indexes input[j / 32] (:121)
+                raise ReferencePanic("index out of bounds: the reference panics (unpacking/aarch64.rs:121)")
+            w = np.concatenate([w, np.zeros(need - w.size, dtype=np.uint64)])
+        dbuf[:] = decode_np(w, n_bases, ctx).tobytes()
+        return
     dbuf.extend(decode_np(ebuf, n_bases, ctx).tobytes())
 
 

@@ -54,6 +54,7 @@ struct bn_ctx {
     const void* fq_text = nullptr;
     size_t fq_bytes = 0, fq_reads = 0, fq_words = 0;
     bool fq_valid = false;
+    int compat = BN_COMPAT_X86_64;
     std::mutex mu;
 };
 
@@ -294,6 +295,15 @@ int bn_ctx_set_chunk_bytes(bn_ctx* ctx, size_t bytes) {
     ctx->chunk = std::max<size_t>(4096, (bytes + 4095) & ~(size_t)4095);  // whole words, 16-byte aligned shards
     return BN_OK;
 }
+
+int bn_ctx_set_compat(bn_ctx* ctx, int mode) {
+    if (!ctx || (mode != BN_COMPAT_X86_64 && mode != BN_COMPAT_AARCH64)) return BN_ERR_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->compat = mode;
+    return BN_OK;
+}
+
+int bn_ctx_compat(const bn_ctx* ctx) { return ctx ? ctx->compat : BN_ERR_ARGUMENT; }
 
 int bn_dev_alloc(bn_ctx* ctx, size_t bytes, void** out) {
     bn_error_t* err = nullptr;
@@ -614,7 +624,13 @@ int bn_synth_ascii_dev(bn_ctx* ctx, void* stream, uint64_t seed, uint64_t stream
 int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* n_words, bn_error_t* err) {
     if (n_words) *n_words = 0;
     if (!ctx || (n && (!seq || !out))) return set_err(err, BN_ERR_ARGUMENT);
-    if (n == 0) return set_err(err, BN_ERR_EMPTY_ENCODE);
+    if (n == 0) {
+        if (ctx->compat != BN_COMPAT_AARCH64) return set_err(err, BN_ERR_EMPTY_ENCODE);
+        if (!out) return set_err(err, BN_ERR_ARGUMENT);   // aarch64: as_2bit(b"") = 0 is pushed (packing/aarch64.rs:223-227)
+        out[0] = 0;
+        if (n_words) *n_words = 1;
+        return set_err(err, BN_OK);
+    }
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t chunk = ctx->chunk;
@@ -671,7 +687,13 @@ int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* 
     }
     if (best != kNoError) {
         if (n_words) *n_words = (size_t)((best >> 8) / 32);
-        return invalid_base(err, best, 0);
+        invalid_base(err, best, 0);
+        const size_t off = (size_t)(best >> 8);
+        if (ctx->compat == BN_COMPAT_AARCH64 && err && n >= 32 && off < n / 32 * 32) {
+            err->base = seq[off & ~(size_t)31];   // the block's first byte, src/utils/packing/aarch64.rs:194-196
+            err->a = err->base;
+        }
+        return BN_INVALID_BASE;
     }
     if (n_words) *n_words = (n + 31) / 32;
     return set_err(err, BN_OK);

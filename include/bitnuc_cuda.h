@@ -89,6 +89,18 @@ int bn_ctx_synchronize(bn_ctx *ctx);
 /* Staging chunk (bytes of ASCII per pipeline stage) used by the host-pointer calls. 0 = default. */
 int bn_ctx_set_chunk_bytes(bn_ctx *ctx, size_t bytes);
 
+/* Which of the reference's per-ISA paths is mirrored where they disagree.  BN_COMPAT_X86_64 (default):
+ * src/utils/packing/avx.rs, src/utils/unpacking/avx.rs -- what every other comment in this header describes.
+ * BN_COMPAT_AARCH64: src/utils/packing/aarch64.rs:173-219 -- bn_encode reports, for an invalid byte inside a whole
+ * 32-base block, the FIRST byte of that block as err->base (`InvalidBase(*ip)`, aarch64.rs:194-196; err->offset stays
+ * the offending byte's offset); an invalid byte in the ragged tail, or in a sequence shorter than 32, is reported
+ * itself (aarch64.rs:208-214, :223-227); bn_encode of an empty sequence is Ok with one zero word (as_2bit(b"") = 0 is
+ * pushed, aarch64.rs:223-227) instead of BN_ERR_EMPTY_ENCODE.  The Vec semantics that differ (append vs overwrite,
+ * src/utils/unpacking/aarch64.rs:127-130) belong to the language bindings, which read the mode back with bn_ctx_compat. */
+typedef enum bn_compat { BN_COMPAT_X86_64 = 0, BN_COMPAT_AARCH64 = 1 } bn_compat;
+int bn_ctx_set_compat(bn_ctx *ctx, int mode);
+int bn_ctx_compat(const bn_ctx *ctx);
+
 /* Memory helpers for callers without their own CUDA runtime binding. */
 int bn_dev_alloc(bn_ctx *ctx, size_t bytes, void **out);
 int bn_dev_free(bn_ctx *ctx, void *ptr);

@@ -164,3 +164,78 @@ def fastq_scan(text: bytes):
             return ("fault", r, 4)
         out.append(rec[1])
     return out
+
+
+# ---- the aarch64 paths where they differ from x86-64: plain-Python restatements ----------------
+
+_VALID = b"ACGTacgt"
+_CODE = {65: 0, 97: 0, 67: 1, 99: 1, 71: 2, 103: 2, 84: 3, 116: 3}
+
+
+class Aarch64Error(Exception):
+    def __init__(self, variant, value):
+        super().__init__(f"{variant}({value})")
+        self.variant, self.value = variant, value
+
+    def key(self):
+        return (self.variant, self.value)
+
+
+class Aarch64Panic(Exception):
+    pass
+
+
+def _as_2bit_aarch64(seq: bytes) -> int:
+    """src/utils/packing/aarch64.rs:76-128: length first, then the first invalid byte in order."""
+    if len(seq) > 32:
+        raise Aarch64Error("SequenceTooLong", len(seq))
+    for b in seq:
+        if b not in _VALID:
+            raise Aarch64Error("InvalidBase", b)
+    return sum(_CODE[b] << (2 * i) for i, b in enumerate(seq))
+
+
+def encode_aarch64(seq: bytes, ebuf: list) -> None:
+    """src/utils/mod.rs:22-25 -> src/utils/packing/aarch64.rs:222-244 (encode_internal) and :173-219
+    (encode_nucleotides_simd).  Nothing is cleared: a short sequence PUSHES one word; a long one resizes the Vec to
+    ceil(n/32), zero-fills it and overwrites block by block; a bad byte inside a whole block reports the block's
+    FIRST byte (:194-196), one in the tail reports itself (:208-214)."""
+    seq = bytes(seq)
+    if len(seq) < 32:
+        ebuf.append(_as_2bit_aarch64(seq))        # :223-227 (`?` leaves ebuf untouched on error)
+        return
+    n_chunks = (len(seq) + 31) // 32
+    del ebuf[n_chunks:]                           # ebuf.resize(n_chunks, 0), :235
+    ebuf.extend([0] * (n_chunks - len(ebuf)))
+    ebuf[:] = [0] * n_chunks                      # output.fill(0), :185
+    full = len(seq) // 32
+    for blk in range(full):
+        chunk = seq[32 * blk : 32 * blk + 32]
+        if any(b not in _VALID for b in chunk):
+            raise Aarch64Error("InvalidBase", chunk[0])      # InvalidBase(*ip), :194-196
+        ebuf[blk] = sum(_CODE[b] << (2 * i) for i, b in enumerate(chunk))
+    tail = seq[32 * full :]
+    if tail:
+        word = 0
+        for i, b in enumerate(tail):
+            if (b | 0x20) not in b"acgt":
+                raise Aarch64Error("InvalidBase", b)         # :213
+            word |= _CODE[b] << (2 * i)
+        ebuf[full] = word
+
+
+def decode_aarch64(ebuf, n_bases: int, dbuf: bytearray) -> None:
+    """src/utils/unpacking/aarch64.rs:127-130 (fast_decode: out.resize(len, 0), then overwritten) and :100-125
+    (decode_nucleotides_simd: whole chunks read `input.get(i).copied().unwrap_or(0)`, the tail indexes input[j / 32])."""
+    ebuf = [int(w) for w in ebuf]
+    out = bytearray(n_bases)
+    chunks = n_bases // 32
+    for i in range(chunks):
+        w = ebuf[i] if i < len(ebuf) else 0
+        for j in range(32):
+            out[32 * i + j] = b"ACGT"[(w >> (2 * j)) & 3]
+    for j in range(32 * chunks, n_bases):
+        if j // 32 >= len(ebuf):
+            raise Aarch64Panic("index out of bounds")
+        out[j] = b"ACGT"[(ebuf[j // 32] >> (2 * (j % 32))) & 3]
+    dbuf[:] = out

@@ -1357,8 +1357,38 @@ int bn_kmers_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, s
     return set_err(err, BN_OK);
 }
 
-// FASTQ text -> records -> packed words.  The text is staged whole; scan and encode are two calls because the caller
-// has to allocate the outputs in between.
+}  // extern "C"
+
+namespace {
+
+// Upload of a whole host buffer on the context stream.  Pageable caller memory goes through two pinned stage buffers in
+// chunks (multi-threaded memcpy of chunk c+1 while chunk c is on the link) instead of the driver's single-threaded staging.
+int upload_whole(bn_ctx* ctx, void* d_dst, const uint8_t* src, size_t bytes, bn_error_t* err) {
+    cudaStream_t st = ctx->stream;
+    if (!is_pageable(src)) {
+        BN_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return BN_OK;
+    }
+    const size_t chunk = ctx->chunk;
+    for (int s = 0; s < 2; ++s) BN_CUDA(ensure_host(ctx->hstage_in[s][0], std::min(chunk, bytes)));
+    size_t c = 0;
+    for (size_t off = 0; off < bytes; off += chunk, ++c) {
+        const int s = (int)(c & 1);
+        const size_t len = std::min(chunk, bytes - off);
+        if (c >= 2) BN_CUDA(cudaEventSynchronize(ctx->stage_done[s]));   // the copy that last used this stage buffer
+        parallel_memcpy(ctx->hstage_in[s][0].p, src + off, len);
+        BN_CUDA(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, ctx->hstage_in[s][0].p, len, cudaMemcpyHostToDevice, st));
+        BN_CUDA(cudaEventRecord(ctx->stage_done[s], st));
+    }
+    return BN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// FASTQ text -> records -> packed words.  The text is staged whole (pageable text in chunks through pinned buffers);
+// scan and encode are two calls because the caller has to allocate the outputs in between.
 int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err) {
     if (!ctx || !n_reads || !n_words || (n_bytes && !text)) return set_err(err, BN_ERR_ARGUMENT);
     *n_reads = *n_words = 0;
@@ -1376,7 +1406,7 @@ int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_re
     BN_CUDA(ensure(ctx->fq[0], n_bytes + 16));
     BN_CUDA(ensure(ctx->fq[1], bn::fastq_scratch_bytes(n_bytes)));
     const uint8_t* d_text = static_cast<const uint8_t*>(ctx->fq[0].p);
-    BN_CUDA(cudaMemcpyAsync(ctx->fq[0].p, text, n_bytes, cudaMemcpyHostToDevice, st));
+    if (const int rc = upload_whole(ctx, ctx->fq[0].p, text, n_bytes, err)) return rc;
     BN_CUDA(bn::launch_fastq_count(ctx->di, d_text, n_bytes, ctx->fq[1].p, reinterpret_cast<uint64_t*>(ctx->d_words + 10), st));
     BN_CUDA(cudaMemcpyAsync(ctx->h_words + 10, ctx->d_words + 10, 8, cudaMemcpyDeviceToHost, st));
     BN_CUDA(cudaStreamSynchronize(st));

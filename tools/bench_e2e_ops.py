@@ -78,3 +78,31 @@ n_out = C.c_size_t(0)
 s = timed(lambda: ctx.lib.bn_kmers(ctx.handle, seq.ctypes.data, n, 31, out_k.ctypes.data, C.byref(n_out), None))
 assert n_out.value == n - 30
 line("bn_kmers k=31", s, n, 8 * (n - 30), n - 30, "kmers")
+
+# FASTQ text (2 M x 150 bp, 23-byte headers) -> records -> packed reads: scan + encode, text in pinned / pageable memory
+n_reads, rl, hdr = 2_000_000, 150, 23
+rec = hdr + rl + 1 + 2 + rl + 1
+t2 = torch.full((n_reads, rec), ord("I"), dtype=torch.uint8, device="cuda")
+t2[:, 0] = ord("@"); t2[:, 1:hdr - 1] = ord("h"); t2[:, hdr - 1] = 10
+t2[:, hdr:hdr + rl] = dv.synth_ascii(SEED, 7, 0, n_reads * rl).view(n_reads, rl)
+t2[:, hdr + rl] = 10; t2[:, hdr + rl + 1] = ord("+"); t2[:, hdr + rl + 2] = 10; t2[:, rec - 1] = 10
+text_pin = pinned(t2.view(-1), np.uint8)
+text_page = np.array(text_pin)
+nb = text_pin.size
+wpr = (rl + 31) // 32
+out_w = ctx.pinned_empty(n_reads * wpr, np.uint64)
+wo, so, sl = (ctx.pinned_empty(n_reads + 1, np.uint64) for _ in range(3))
+
+
+def fastq(text):
+    nr, nw = C.c_size_t(0), C.c_size_t(0)
+    assert ctx.lib.bn_fastq_scan(ctx.handle, text.ctypes.data, nb, C.byref(nr), C.byref(nw), None) == 0
+    assert nr.value == n_reads and nw.value == n_reads * wpr
+    assert ctx.lib.bn_fastq_encode(ctx.handle, text.ctypes.data, nb, nr.value, nw.value, out_w.ctypes.data, wo.ctypes.data, so.ctypes.data,
+                                   sl.ctypes.data, None) == 0
+
+
+for name, text in (("pinned", text_pin), ("pageable", text_page)):
+    s = timed(lambda: fastq(text))
+    assert int(wo[n_reads]) == n_reads * wpr and int(sl[7]) == rl and int(so[1]) == rec + hdr
+    line(f"bn_fastq_scan + bn_fastq_encode ({name} text)", s, nb, 8 * n_reads * wpr + 24 * n_reads, n_reads * rl, "bases")

@@ -8,6 +8,8 @@
   cfg 5  ~32 Gbases of 50 bp - 10 kbp reads: word count == sum ceil(len/32), sampled reads round-trip through
          decode, injected N bases reported exactly (first in input order + per-read positions)
   next   every 31-mer of a 0.5 Gbase sequence against the packed stream; slice windows against decode
+  fastq  6.5 GB of FASTQ text (2 x 10^7 reads of 150 bp) and 6 GB of 10 kbp reads: line count == 4 x reads, sequence
+         offsets / lengths in closed form, packed words == bn_encode_batch of the same sequences
 
 The functions are the ones tools/bench_configs.py times; here they run once each for their assertions.
 """
@@ -32,7 +34,7 @@ def cfg():
     return bench_configs
 
 
-@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "cfg5", "short_reads", "next_rows"])
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "cfg5", "short_reads", "next_rows", "fastq"])
 def test_full_size_properties(cfg, name, capsys):
     import torch
     getattr(cfg, name)(1.0, 1)

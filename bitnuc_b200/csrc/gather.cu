@@ -18,12 +18,19 @@
 
 namespace bn {
 
+// Length of query q's range, evaluated ONCE per query (the scan caches it): the only place a query is validated and
+// the only place lens[read] -- a random 32-byte sector per query -- is fetched.  A failing query is reported here
+// (status = min failing query index) and takes no room, so the kernels below see it as an empty range.
 struct SliceLen {
     const uint64_t *lens, *q_read, *q_start, *q_end;
     unsigned long long n_reads;
+    unsigned long long* status;
     __device__ __forceinline__ unsigned long long operator()(unsigned long long q) const {
         const unsigned long long r = q_read[q], s = q_start[q], e = q_end[q];
-        if (r >= n_reads || s > e || e > lens[r]) return 0;  // reported as an error, takes no room
+        if (r >= n_reads || s > e || e > lens[r]) {
+            if (q < ld_volatile_u64(status)) atomicMin(status, q);
+            return 0;
+        }
         return e - s;
     }
 };
@@ -54,11 +61,10 @@ constexpr unsigned kSliceStage = 32 * kSliceShort + 16;   // bytes a warp stages
 // that span -- laid out at the same 16-byte phase as the global span -- and the warp then stores it with coalesced
 // 128-bit stores.  Longer ranges are queued for slice_long_kernel.
 __global__ void __launch_bounds__(kThreads)
-slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ lens,
-                   unsigned long long n_reads, const uint64_t* __restrict__ q_read, const uint64_t* __restrict__ q_start,
-                   const uint64_t* __restrict__ q_end, unsigned long long nq, uint8_t* __restrict__ out,
-                   const uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ status,
-                   unsigned long long* __restrict__ long_count, unsigned long long* __restrict__ long_list) {
+slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ q_read,
+                   const uint64_t* __restrict__ q_start, unsigned long long nq, uint8_t* __restrict__ out,
+                   const uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ long_count,
+                   unsigned long long* __restrict__ long_list) {
     __shared__ __align__(16) uint8_t stage[kWarpsPerBlock][kSliceStage];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long q = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
@@ -66,19 +72,16 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
     unsigned n = 0, sh_head = 0;
     unsigned long long s = 0, oo = out_offsets[q < nq ? q : nq];
     const uint64_t* w = words;
-    unsigned long long last_word = 0;
     if (q < nq) {
-        const unsigned long long r = q_read[q], s0 = q_start[q], e = q_end[q];
-        const unsigned long long len = r < n_reads ? lens[r] : 0;
-        if (r >= n_reads || s0 > e || e > len) {
-            if (q < ld_volatile_u64(status)) atomicMin(status, q);
-        } else if (e - s0 > kSliceShort) {
+        // the range length is the difference of two output offsets (the scan validated the query: a failing one is
+        // empty here), so neither lens[read] nor q_end is fetched again
+        const unsigned long long cnt = out_offsets[q + 1] - oo;
+        if (cnt > kSliceShort) {
             long_list[atomicAdd(long_count, 1ull)] = q;
-        } else if (e > s0) {
-            n = (unsigned)(e - s0);
-            s = s0;
-            w = words + word_offsets[r];
-            last_word = (len - 1) >> 5;
+        } else if (cnt) {
+            n = (unsigned)cnt;
+            s = q_start[q];
+            w = words + word_offsets[q_read[q]];
         }
     }
     // the warp's output span [span_lo, span_hi) and its staged image; a span with a long range inside is too big to stage
@@ -95,7 +98,7 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
             const unsigned long long wi = s >> 5;
             const unsigned sh = 2u * (unsigned)(s & 31u);
             uint64_t x = __ldg(w + wi) >> sh;
-            if (sh > 58 && wi < last_word) x |= __ldg(w + wi + 1) << (64 - sh);   // 3 bases may straddle two words
+            if (sh + 2u * head > 64u) x |= __ldg(w + wi + 1) << (64 - sh);   // 3 bases may straddle two words (a valid range: the word exists)
             for (unsigned i = 0; i < head; ++i) o[i] = (uint8_t)(0x54474341u >> (8u * ((unsigned)(x >> (2 * i)) & 3u)));
             s += head;
             n -= head;
@@ -186,8 +189,8 @@ get_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
     out[q] = (uint8_t)(0x54474341u >> (8 * ((x >> (2 * (i & 31))) & 3)));
 }
 
-// scan state, then the queue of long ranges (count + one entry per query)
-size_t slice_batch_scratch_bytes(size_t nq) { return scan_scratch_bytes(nq) + (nq + 1) * sizeof(unsigned long long); }
+// scan state, the queue of long ranges (count + one entry per query), the cached range lengths
+size_t slice_batch_scratch_bytes(size_t nq) { return scan_scratch_bytes(nq) + (2 * nq + 1) * sizeof(unsigned long long); }
 
 cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
                                size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_start, const uint64_t* d_q_end, size_t nq,
@@ -199,10 +202,10 @@ cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, co
     unsigned long long* long_count = sums + scan_scratch_bytes(nq) / sizeof(unsigned long long);
     e = cudaMemsetAsync(long_count, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    launch_exclusive_scan(SliceLen{d_lens, d_q_read, d_q_start, d_q_end, n_reads}, nq, sums, d_out_offsets, s);
-    slice_short_kernel<<<(unsigned)ceil_div(nq, kThreads), kThreads, 0, s>>>(d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start,
-                                                                           d_q_end, nq, d_out, d_out_offsets, d_status, long_count,
-                                                                           long_count + 1);
+    uint64_t* cache = reinterpret_cast<uint64_t*>(long_count + 1 + nq);
+    launch_exclusive_scan_cached(SliceLen{d_lens, d_q_read, d_q_start, d_q_end, n_reads, d_status}, nq, sums, cache, d_out_offsets, s);
+    slice_short_kernel<<<(unsigned)ceil_div(nq, kThreads), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, nq, d_out,
+                                                                           d_out_offsets, long_count, long_count + 1);
     static const int resident = resident_blocks(slice_long_kernel, kThreads, di);
     slice_long_kernel<<<grid_for(ceil_div(nq, kWarpsPerBlock), resident), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, d_q_end,
                                                                                           d_out, d_out_offsets, long_count, long_count + 1);

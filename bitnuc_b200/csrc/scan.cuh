@@ -197,6 +197,30 @@ static void launch_exclusive_scan(F count, size_t n, unsigned long long* sums, u
     launch_scan_impl<1>(count, n, sums, out, nullptr, s, hook);
 }
 
+// The same scan for a count that is expensive to evaluate (a dependent random load): the first pass stores every count
+// in `cache` (n entries), the last pass reads it back from there instead of evaluating the functor a second time.
+template <typename F>
+struct ScanStoreCount {
+    F count;
+    uint64_t* cache;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long i) const {
+        const unsigned long long c = count(i);
+        cache[i] = c;
+        return c;
+    }
+};
+struct ScanLoadCount {
+    const uint64_t* cache;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long i) const { return cache[i]; }
+};
+template <typename F>
+static void launch_exclusive_scan_cached(F count, size_t n, unsigned long long* sums, uint64_t* cache, uint64_t* out, cudaStream_t s) {
+    const unsigned long long n_blocks = ceil_div(n, kScanTile);
+    scan_block_sums_kernel<1><<<(unsigned)n_blocks, kThreads, 0, s>>>(ScanStoreCount<F>{count, cache}, n, n_blocks, sums);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n_blocks);
+    scan_offsets_kernel<1><<<(unsigned)n_blocks, kThreads, 0, s>>>(ScanLoadCount{cache}, n, sums, n_blocks, out, nullptr, ScanNoHook());
+}
+
 // two channels: count(i) returns (a, b) as a ulonglong2
 template <typename F, typename H = ScanNoHook>
 static void launch_exclusive_scan2(F count, size_t n, unsigned long long* sums, uint64_t* out_a, uint64_t* out_b, cudaStream_t s,

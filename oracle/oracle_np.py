@@ -168,8 +168,8 @@ def fastq_scan(text: bytes):
 
 # ---- the aarch64 paths where they differ from x86-64: plain-Python restatements ----------------
 
-_VALID = b"ACGTacgt"
-_CODE = {65: 0, 97: 0, 67: 1, 99: 1, 71: 2, 103: 2, 84: 3, 116: 3}
+_A64_VALID = b"ACGTacgt"
+_A64_CODE = {65: 0, 97: 0, 67: 1, 99: 1, 71: 2, 103: 2, 84: 3, 116: 3}
 
 
 class Aarch64Error(Exception):
@@ -190,9 +190,9 @@ def _as_2bit_aarch64(seq: bytes) -> int:
     if len(seq) > 32:
         raise Aarch64Error("SequenceTooLong", len(seq))
     for b in seq:
-        if b not in _VALID:
+        if b not in _A64_VALID:
             raise Aarch64Error("InvalidBase", b)
-    return sum(_CODE[b] << (2 * i) for i, b in enumerate(seq))
+    return sum(_A64_CODE[b] << (2 * i) for i, b in enumerate(seq))
 
 
 def encode_aarch64(seq: bytes, ebuf: list) -> None:
@@ -211,16 +211,16 @@ def encode_aarch64(seq: bytes, ebuf: list) -> None:
     full = len(seq) // 32
     for blk in range(full):
         chunk = seq[32 * blk : 32 * blk + 32]
-        if any(b not in _VALID for b in chunk):
+        if any(b not in _A64_VALID for b in chunk):
             raise Aarch64Error("InvalidBase", chunk[0])      # InvalidBase(*ip), :194-196
-        ebuf[blk] = sum(_CODE[b] << (2 * i) for i, b in enumerate(chunk))
+        ebuf[blk] = sum(_A64_CODE[b] << (2 * i) for i, b in enumerate(chunk))
     tail = seq[32 * full :]
     if tail:
         word = 0
         for i, b in enumerate(tail):
             if (b | 0x20) not in b"acgt":
                 raise Aarch64Error("InvalidBase", b)         # :213
-            word |= _CODE[b] << (2 * i)
+            word |= _A64_CODE[b] << (2 * i)
         ebuf[full] = word
 
 

@@ -222,3 +222,27 @@ def test_truncated_text_and_large_text(bn, dv):
     assert check(bn, dv, cut)[0] == "fault"
     cut = text[: text.rfind(b"+")]                 # ends before the last separator
     assert check(bn, dv, cut) == ("fault", 59_999, 4)
+
+
+def test_fastq_output_feeds_the_packed_domain_calls(bn):
+    """The layout bn_fastq_encode produces (words, word offsets, lengths) is the one the packed-domain batch calls take:
+    per-read base counts / GC, split at a barcode boundary and slices run on it directly, and agree with the oracle's
+    PackedSequence of every record."""
+    rng = np.random.default_rng(21)
+    lens = rng.integers(30, 200, 400)
+    text = make_fastq(rng, lens, alphabet=b"ACGTacgt")
+    w, wo, so, sl = bn.fastq_encode(np.frombuffer(text, dtype=np.uint8))
+    seqs = [text[int(s) : int(s) + int(l)] for s, l in zip(so, sl)]
+    counts, gc, totals = bn.base_counts_batch(w, wo, sl)
+    for r in (0, 1, 57, 399):
+        ps = oracle.PackedSequence(seqs[r])
+        assert [int(x) for x in counts[r]] == ps.base_counts() and gc[r] == ps.gc_content()
+    assert sum(totals) == int(lens.sum())
+    idx = np.full(400, 16, dtype=np.uint64)
+    left, lo, right, ro = bn.split_packed_batch(w, wo, sl, idx)
+    for r in (0, 3, 399):
+        ol, orr = oracle.split_packed(oracle.encode_alloc(seqs[r]), int(sl[r]), 16)
+        assert [int(x) for x in left[int(lo[r]) : int(lo[r + 1])]] == ol and [int(x) for x in right[int(ro[r]) : int(ro[r + 1])]] == orr
+    q = np.arange(400, dtype=np.uint64)
+    data, oo = bn.slice_batch(w, wo[:-1], sl, q, np.full(400, 5, dtype=np.uint64), np.full(400, 25, dtype=np.uint64))
+    assert data.tobytes() == b"".join(s[5:25].upper() for s in seqs)

@@ -49,6 +49,43 @@ def shard_reads_by_volume(offsets: np.ndarray, world: int) -> list[tuple[int, in
     return [(cuts[g], cuts[g + 1]) for g in range(world)]
 
 
+def fastq_record_start(text, pos: int) -> int:
+    """The first record boundary at or after byte ``pos`` of a FASTQ text (``len(text)`` when there is none): the
+    start of a line that opens with '@' and whose second-next line opens with '+'.  The second condition is what
+    tells a header from a quality line that happens to start with '@' (its second-next line is a sequence)."""
+    t = memoryview(text).cast("B") if not isinstance(text, np.ndarray) else text
+    n = len(t)
+    p = pos
+    if p > 0:  # move to the start of the next line
+        while p < n and t[p - 1] != 10:
+            p += 1
+    while p < n:
+        if t[p] == 64:  # '@'
+            q, lines = p, 0
+            while q < n and lines < 2:
+                if t[q] == 10:
+                    lines += 1
+                q += 1
+            if lines == 2 and q < n and t[q] == 43:  # '+'
+                return p
+        while p < n and t[p] != 10:
+            p += 1
+        p += 1
+    return n
+
+
+def shard_fastq_text(text, world: int) -> list[tuple[int, int]]:
+    """Cut a FASTQ text into ``world`` contiguous byte ranges of near-equal size on record boundaries: every rank
+    parses and encodes its own range (``bn_fastq_*``), read indices / word offsets of rank g are then offset by the
+    totals of ranks < g, and the first fault is the MIN over ranks.  No data-path collective."""
+    n = len(text)
+    cuts = [0]
+    for g in range(1, world):
+        cuts.append(max(cuts[-1], fastq_record_start(text, n * g // world)))
+    cuts.append(n)
+    return [(cuts[g], cuts[g + 1]) for g in range(world)]
+
+
 def allreduce_counts(counts: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the four base counters (int64[4]) over all ranks, in place.  32 bytes: latency-bound."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

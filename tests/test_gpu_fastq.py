@@ -246,3 +246,23 @@ def test_fastq_output_feeds_the_packed_domain_calls(bn):
     q = np.arange(400, dtype=np.uint64)
     data, oo = bn.slice_batch(w, wo[:-1], sl, q, np.full(400, 5, dtype=np.uint64), np.full(400, 25, dtype=np.uint64))
     assert data.tobytes() == b"".join(s[5:25].upper() for s in seqs)
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_text_reassembles_to_the_whole(bn, world):
+    """Multi-GPU shape on one device: the text is cut on record boundaries (sharding.shard_fastq_text), every shard goes
+    through bn_fastq_* on its own, offsets are rebased by the totals of the shards before it."""
+    from bitnuc_b200 import sharding as sh
+    rng = np.random.default_rng(world)
+    text = make_fastq(rng, rng.integers(0, 400, 3000), alphabet=b"ACGTacgt")
+    w, wo, so, sl = bn.fastq_encode(np.frombuffer(text, dtype=np.uint8))
+    parts_w, parts_wo, parts_so, parts_sl, word_base = [], [], [], [], 0
+    for lo, hi in sh.shard_fastq_text(text, world):
+        pw, pwo, pso, psl = bn.fastq_encode(np.frombuffer(text[lo:hi], dtype=np.uint8))
+        parts_w.append(pw.copy())
+        parts_wo.append(pwo[:-1] + np.uint64(word_base))
+        parts_so.append(pso + np.uint64(lo))
+        parts_sl.append(psl.copy())
+        word_base += int(pwo[-1])
+    assert np.array_equal(np.concatenate(parts_w), w) and np.array_equal(np.concatenate(parts_wo), wo[:-1])
+    assert np.array_equal(np.concatenate(parts_so), so) and np.array_equal(np.concatenate(parts_sl), sl)

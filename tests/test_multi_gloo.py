@@ -79,3 +79,75 @@ def test_two_rank_sharding_matches_unsharded_oracle():
     assert res["only1"] == (cut + 3, ord("Q"))
     from bitnuc_b200 import sharding as sh
     assert sh.gc_from_counts(res["counts"]) == oracle.gc_content(words, N_BASES)
+
+
+def _fastq_worker(rank, port, text, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from bitnuc_b200 import sharding as sh
+    try:
+        lo, hi = sh.shard_fastq_text(text, WORLD)[rank]
+        words, wo, so, sl = oracle.fastq_encode(text[lo:hi])          # the oracle stands in for bn_fastq_* (no GPU here)
+        sizes = torch.tensor([sl.size, words.size], dtype=torch.int64)
+        gathered = [torch.zeros(2, dtype=torch.int64) for _ in range(WORLD)]
+        dist.all_gather(gathered, sizes)
+        read_base = sum(int(g[0]) for g in gathered[:rank])
+        word_base = sum(int(g[1]) for g in gathered[:rank])
+        parts = [None] * WORLD
+        dist.all_gather_object(parts, {"words": words.tolist(), "wo": [int(x) + word_base for x in wo[:-1]],
+                                       "so": [int(x) + lo for x in so], "sl": sl.tolist(), "read_base": read_base})
+        if rank == 0:
+            results.put(parts)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_fastq_sharding_matches_the_whole_text():
+    from test_oracle_fastq import make_fastq
+    rng = np.random.default_rng(8)
+    text = make_fastq(rng, rng.integers(0, 300, 500), alphabet=b"ACGTacgt")
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fastq_worker, args=(r, port, text, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    parts = q.get()
+    words, wo, so, sl = oracle.fastq_encode(text)
+    assert sum((p["words"] for p in parts), []) == [int(x) for x in words]
+    assert sum((p["wo"] for p in parts), []) == [int(x) for x in wo[:-1]]
+    assert sum((p["so"] for p in parts), []) == [int(x) for x in so]
+    assert sum((p["sl"] for p in parts), []) == [int(x) for x in sl]
+    assert parts[1]["read_base"] == len(parts[0]["sl"]) > 0
+
+
+def test_fastq_cuts_fall_on_record_boundaries():
+    from bitnuc_b200 import sharding as sh
+    from test_oracle_fastq import make_fastq
+    rng = np.random.default_rng(2)
+    # quality lines full of '@' and '+': the boundary rule must not be fooled by them
+    lens = rng.integers(1, 60, 200)
+    recs = []
+    for r, n in enumerate(lens):
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), int(n)))
+        qual = bytes(rng.choice(np.frombuffer(b"@+I", dtype=np.uint8), int(n)))
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (r, seq, qual))
+    text = b"".join(recs)
+    starts = set(np.cumsum([0] + [len(x) for x in recs]).tolist())
+    for world in (1, 2, 3, 8, 64):
+        shards = sh.shard_fastq_text(text, world)
+        assert shards[0][0] == 0 and shards[-1][1] == len(text)
+        assert all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+        assert all(lo in starts for lo, _ in shards)
+    for pos in range(0, len(text), 37):
+        assert sh.fastq_record_start(text, pos) == min(s for s in starts if s >= pos)
+    assert sh.fastq_record_start(text, len(text)) == len(text)
+    # a text cut at these points parses shard by shard to the same records
+    total = 0
+    for lo, hi in sh.shard_fastq_text(text, 5):
+        total += oracle.fastq_scan(text[lo:hi])[0].size
+    assert total == 200
+    assert make_fastq is not None

@@ -266,3 +266,24 @@ def test_sharded_text_reassembles_to_the_whole(bn, world):
         word_base += int(pwo[-1])
     assert np.array_equal(np.concatenate(parts_w), w) and np.array_equal(np.concatenate(parts_wo), wo[:-1])
     assert np.array_equal(np.concatenate(parts_so), so) and np.array_equal(np.concatenate(parts_sl), sl)
+
+
+@pytest.mark.parametrize("size", [16384, 65536, 2 * 65536])
+@pytest.mark.parametrize("delta", [-1, 0, 1])
+@pytest.mark.parametrize("final_newline", [False, True])
+def test_text_lengths_around_tile_multiples(bn, dv, size, delta, final_newline):
+    """The last line may lack its newline: the kernels read a virtual one at byte n, which sits in a tile of its own
+    when n is a multiple of the tile size."""
+    rng = np.random.default_rng(size + delta)
+    body = b""
+    while len(body) < size - 1500:                                       # whole records, well short of the target
+        body += make_fastq(rng, rng.integers(50, 150, 1))
+    tail_len = 100
+    fixed = len(body) + 1 + 1 + tail_len + 3 + tail_len + (1 if final_newline else 0)   # '@' + header pad + '\n' ...
+    pad = size + delta - fixed
+    assert pad >= 0
+    seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), tail_len))
+    text = body + b"@" + b"p" * pad + b"\n" + seq + b"\n+\n" + b"I" * tail_len + (b"\n" if final_newline else b"")
+    assert len(text) == size + delta
+    exp = check(bn, dv, text)
+    assert exp[0] == "ok" and int(exp[4][-1]) == tail_len

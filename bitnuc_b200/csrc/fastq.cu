@@ -412,6 +412,33 @@ __device__ __forceinline__ bool strip_range_invalid(const uint32_t* __restrict__
     return bad != 0u;
 }
 
+// The same test without maps: the two partial end vectors are fetched again, as single 32-byte sectors
+// (ld.global.nc.L1::no_allocate -- a plain cached load was served as a 128-byte line fill).
+__device__ __forceinline__ uint4 enc_load_stream(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long pos) {
+    return pos + 16 <= n ? ld128<LD_NC_NOALLOC>(reinterpret_cast<const uint4*>(bytes + pos)) : enc_load_edge(bytes, n, pos);
+}
+__device__ __forceinline__ bool strip_range_invalid_reload(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0,
+                                                           const uint32_t* __restrict__ flags, unsigned lo, unsigned hi) {
+    const unsigned v_lo = (lo + 15u) >> 4, v_hi = hi >> 4;
+    bool bad = false;
+    if (v_lo <= v_hi) {
+        if (lo & 15u) bad |= bad_in_range(enc_load_stream(bytes, n, tile0 + 16ull * (v_lo - 1)), (int)(lo & 15u), 16);
+        if (hi & 15u) bad |= bad_in_range(enc_load_stream(bytes, n, tile0 + 16ull * v_hi), 0, (int)(hi & 15u));
+        if (v_lo < v_hi) {
+            const unsigned w_lo = v_lo >> 5, w_hi = (v_hi - 1u) >> 5;
+            for (unsigned w = w_lo; w <= w_hi; ++w) {
+                uint32_t f = flags[w];
+                if (w == w_lo) f &= 0xFFFFFFFFu << (v_lo & 31u);
+                if (w == w_hi) f &= 0xFFFFFFFFu >> (31u - ((v_hi - 1u) & 31u));
+                bad |= f != 0u;
+            }
+        }
+    } else {
+        bad = bad_in_range(enc_load_stream(bytes, n, tile0 + 16ull * (lo >> 4)), (int)(lo & 15u), (int)(hi & 15u));
+    }
+    return bad;
+}
+
 // the output word whose first base sits `rel` bytes into the strip (same window as batch.cu)
 __device__ __forceinline__ uint64_t fq_cut_word(const uint32_t* __restrict__ codes, unsigned rel) {
     const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
@@ -449,7 +476,7 @@ struct FqLongSeg {
     unsigned pad;
 };
 
-template <int kTile, int kBThreads, int kMinCtas>
+template <int kTile, int kBThreads, int kMinCtas, bool kMaps = true>
 __global__ void __launch_bounds__(kBThreads, kMinCtas)
 fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
                     unsigned long long n_tiles1, unsigned long long n_reads, const uint64_t* __restrict__ seq_off,
@@ -462,7 +489,7 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
     constexpr int kWarps = kBThreads / 32;
     static_assert(kMainVecs % (4 * kBThreads) == 0, "tile must be a whole number of load rounds");
     __shared__ uint32_t codes[kMainVecs + 8];
-    __shared__ uint16_t maps[kMainVecs + 8];                  // per vector: which bytes are outside ACGTacgt
+    __shared__ uint16_t maps[kMaps ? kMainVecs + 8 : 1];      // per vector: which bytes are outside ACGTacgt
     __shared__ uint32_t flags[kMainVecs / 32 + 1];            // per vector: any
     __shared__ FqLongSeg segs[kLongCap];
     __shared__ uint16_t chunks[kMainVecs / 32 + kLongCap + 2];
@@ -494,8 +521,14 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
         for (int j = 0; j < 4; ++j) {
             const unsigned v = vb + j * kBThreads + tid;
             uint32_t map16;
-            codes[v] = pack16_map(x[j], map16);
-            maps[v] = (uint16_t)map16;
+            if constexpr (kMaps) {
+                codes[v] = pack16_map(x[j], map16);
+                maps[v] = (uint16_t)map16;
+            } else {
+                map16 = 0;
+                codes[v] = pack16(x[j], map16);
+                map16 &= kValidMask;
+            }
             const unsigned fb = __ballot_sync(0xffffffffu, map16 != 0u);
             if (lane == 0) flags[v >> 5] = fb;
         }
@@ -506,7 +539,7 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
         if (lane < kOver) c = pack16_map(enc_load_cached(bytes, n, tile0 + 16ull * v), map16);
         if (lane < 8) {
             codes[v] = c;
-            maps[v] = (uint16_t)map16;
+            if constexpr (kMaps) maps[v] = (uint16_t)map16;
         }
         const unsigned fb = __ballot_sync(0xffffffffu, map16 != 0u);
         if (lane == 0) flags[kMainVecs >> 5] = fb;
@@ -521,7 +554,10 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
         const unsigned cap = (kTile + 16u - rel + 31u) >> 5;                     // words whose first base is < kTile + 16
         const unsigned n_in = nw < cap ? (unsigned)nw : cap;
         const unsigned bases_in = len < 32ull * n_in ? (unsigned)len : 32u * n_in;
-        if (strip_range_invalid(flags, maps, rel, rel + bases_in)) fq_report_range(bytes, s, s + len, status);
+        bool invalid;
+        if constexpr (kMaps) invalid = strip_range_invalid(flags, maps, rel, rel + bases_in);
+        else invalid = strip_range_invalid_reload(bytes, n, tile0, flags, rel, rel + bases_in);
+        if (invalid) fq_report_range(bytes, s, s + len, status);
         if (n_in < nw) {   // at most one read runs past the strip
             spill_r = r;
             spill_j0 = n_in;
@@ -644,19 +680,25 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
                                 uint64_t* d_out_words, unsigned long long* d_status, cudaStream_t s) {
     if (n_reads == 0 || n_bytes == 0) return cudaSuccess;
     const FqScratch sc(d_scratch, n_bytes);
-    // tile / CTA shape: BN_FQ_VARIANT picks one of the measured shapes (profiles/r01_sweep_fastq.txt); default = the fastest
-    static const int variant = [] {
+    // tile / CTA shape: BN_FQ_VARIANT picks one of the measured shapes (profiles/r01_sweep_fastq.txt).  By default the
+    // average record size decides how a read's two partial end vectors are validated: from per-vector maps kept in shared
+    // memory (short reads: two end vectors per ~20 vectors of text; 1.61 ms against 1.89 on 150 bp reads), or by
+    // fetching them again while phase 1 stays lighter (long reads: 1.23 ms against 1.50 on 10 kbp reads).
+    static const int forced = [] {
         const char* v = getenv("BN_FQ_VARIANT");
-        return v ? atoi(v) : 0;
+        return v ? atoi(v) : -1;
     }();
-#define BN_FQ_LAUNCH(TILE, THREADS, CTAS)                                                                                              \
-    fastq_encode_kernel<TILE, THREADS, CTAS><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \
+    const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 6 : 0);
+#define BN_FQ_LAUNCH(TILE, THREADS, CTAS, ...)                                                                                         \
+    fastq_encode_kernel<TILE, THREADS, CTAS, ##__VA_ARGS__><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \
         d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status)
     switch (variant) {
     case 1: BN_FQ_LAUNCH(65536, 256, 4); break;
     case 2: BN_FQ_LAUNCH(32768, 128, 8); break;
     case 3: BN_FQ_LAUNCH(32768, 128, 12); break;
     case 4: BN_FQ_LAUNCH(32768, 256, 6); break;
+    case 5: BN_FQ_LAUNCH(65536, 128, 8, false); break;     // no maps: partial end vectors re-read as single sectors
+    case 6: BN_FQ_LAUNCH(65536, 128, 10, false); break;
     default: BN_FQ_LAUNCH(kFqEncTile, 128, 8); break;
     }
 #undef BN_FQ_LAUNCH

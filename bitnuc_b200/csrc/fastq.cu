@@ -682,13 +682,13 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
     const FqScratch sc(d_scratch, n_bytes);
     // tile / CTA shape: BN_FQ_VARIANT picks one of the measured shapes (profiles/r01_sweep_fastq.txt).  By default the
     // average record size decides how a read's two partial end vectors are validated: from per-vector maps kept in shared
-    // memory (short reads: two end vectors per ~20 vectors of text; 1.61 ms against 1.89 on 150 bp reads), or by
-    // fetching them again while phase 1 stays lighter (long reads: 1.23 ms against 1.50 on 10 kbp reads).
+    // memory (short reads: two end vectors per ~20 vectors of text; 1.57 ms against 1.86 on 150 bp reads), or by
+    // fetching them again while phase 1 stays lighter (long reads: 1.21 ms against 1.51 on 10 kbp reads).
     static const int forced = [] {
         const char* v = getenv("BN_FQ_VARIANT");
         return v ? atoi(v) : -1;
     }();
-    const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 6 : 0);
+    const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 11 : 7);
 #define BN_FQ_LAUNCH(TILE, THREADS, CTAS, ...)                                                                                         \
     fastq_encode_kernel<TILE, THREADS, CTAS, ##__VA_ARGS__><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \
         d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status)
@@ -699,6 +699,11 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
     case 4: BN_FQ_LAUNCH(32768, 256, 6); break;
     case 5: BN_FQ_LAUNCH(65536, 128, 8, false); break;     // no maps: partial end vectors re-read as single sectors
     case 6: BN_FQ_LAUNCH(65536, 128, 10, false); break;
+    case 7: BN_FQ_LAUNCH(49152, 128, 10, true); break;
+    case 8: BN_FQ_LAUNCH(32768, 128, 10, true); break;
+    case 9: BN_FQ_LAUNCH(65536, 128, 12, false); break;
+    case 10: BN_FQ_LAUNCH(32768, 128, 12, false); break;
+    case 11: BN_FQ_LAUNCH(49152, 128, 12, false); break;
     default: BN_FQ_LAUNCH(kFqEncTile, 128, 8); break;
     }
 #undef BN_FQ_LAUNCH

@@ -682,13 +682,13 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
     const FqScratch sc(d_scratch, n_bytes);
     // tile / CTA shape: BN_FQ_VARIANT picks one of the measured shapes (profiles/r01_sweep_fastq.txt).  By default the
     // average record size decides how a read's two partial end vectors are validated: from per-vector maps kept in shared
-    // memory (short reads: two end vectors per ~20 vectors of text; 1.57 ms against 1.86 on 150 bp reads), or by
+    // memory (short reads: two end vectors per ~20 vectors of text; 1.59 ms against 1.86 on 150 bp reads), or by
     // fetching them again while phase 1 stays lighter (long reads: 1.21 ms against 1.51 on 10 kbp reads).
     static const int forced = [] {
         const char* v = getenv("BN_FQ_VARIANT");
         return v ? atoi(v) : -1;
     }();
-    const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 11 : 7);
+    const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 11 : 13);
 #define BN_FQ_LAUNCH(TILE, THREADS, CTAS, ...)                                                                                         \
     fastq_encode_kernel<TILE, THREADS, CTAS, ##__VA_ARGS__><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \
         d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status)
@@ -704,6 +704,8 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
     case 9: BN_FQ_LAUNCH(65536, 128, 12, false); break;
     case 10: BN_FQ_LAUNCH(32768, 128, 12, false); break;
     case 11: BN_FQ_LAUNCH(49152, 128, 12, false); break;
+    case 12: BN_FQ_LAUNCH(49152, 128, 8, true); break;
+    case 13: BN_FQ_LAUNCH(49152, 128, 9, true); break;
     default: BN_FQ_LAUNCH(kFqEncTile, 128, 8); break;
     }
 #undef BN_FQ_LAUNCH

@@ -60,7 +60,7 @@ def test_library_targets_sm_100a_only(sass):
     ("kmer_windows_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E\.EF\.64"),
     ("as_2bit_tight_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E\.EF\.64"),
     ("fastq_lines_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E"),              # the text in 128-bit loads, 32-bit line entries out
-    ("fastq_encode_kernelILi49152ELi128ELi10ELb1", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
+    ("fastq_encode_kernelILi49152ELi128ELi9ELb1", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
 ])
 def test_hot_kernels_use_wide_accesses_and_no_local_memory(sass, needle, loads, stores):
     funcs, _ = sass

@@ -10,9 +10,11 @@
 // may lack its newline.  A format error wins over an invalid base; among errors of a kind the first in file order.
 //
 // Device steps (tiles of 16 KiB of text, handed out by the hardware CTA scheduler):
-//   1. fastq_lines_kernel    one pass over the text: newlines per tile (word-parallel exact byte compare), and every
-//                            newline leaves a 32-bit entry in its tile's slot row: position inside the tile, "a '\r'
-//                            precedes it", "the next line opens with '@'", "... with '+'"
+//   1. fastq_lines_kernel    one pass over the text.  A two-op-per-word filter that cannot miss a newline leaves one
+//                            vector in five; a ballot makes a bitmap of the survivors and the CTA finishes them densely,
+//                            one per thread: exact newline mask, rank by a CTA scan, and every newline leaves a 32-bit
+//                            entry in its tile's slot row: position inside the tile, "a '\r' precedes it", "the next
+//                            line opens with '@'", "... with '+'"
 //      + exclusive scan      -> line index of every tile's first newline, number of lines
 //   2. fastq_records_slots_kernel   a warp per tile: record r takes its four entries (walking into the following
 //                            tiles where a line crosses a tile boundary) -> seq_offsets[r], seq_lens[r]; header,
@@ -47,7 +49,6 @@ constexpr int kFqEncTile = 65536;            // bytes of text per encode tile
 constexpr int kFqLongWords = 64;             // a read with more words than this inside the strip is cut by whole warps
 constexpr unsigned long long kCrBit = 1ull << 63;
 constexpr int kFqSlots = 2048;               // line entries per tile (more lines than this: the dense fallback)
-constexpr int kFqListCap = kFqSlots;        // newlines of a tile finished by the slot path (beyond: overflow anyway)
 constexpr uint32_t kSlotPos = 0x3FFFu, kSlotCr = 1u << 14, kSlotAt = 1u << 15, kSlotPlus = 1u << 16;
 
 enum { FQ_BAD_HEADER = 1, FQ_BAD_SEPARATOR = 2, FQ_BAD_QUALITY_LENGTH = 3 };   // kinds of format error (4 = truncated: host)
@@ -96,15 +97,6 @@ __device__ __forceinline__ void report_min(unsigned long long* word, unsigned lo
 
 // ---------------------------------------------------------------- 1. newlines per tile -----------------------------
 
-// per vector: bit 8k + i set iff byte 4i + k (byte k of word i) is '\n' -- three ALU ops per word, no gather
-__device__ __forceinline__ uint32_t nl_flags(uint32_t w) {       // exact, 0x80 per matching byte
-    const uint32_t t = ((w ^ kNl4) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;  // bit 7 set iff the low seven bits differ from '\n'
-    return ~(t | w | 0x7F7F7F7Fu);                                // ... and bit 7 of the byte itself is clear ('\n' < 0x80)
-}
-__device__ __forceinline__ uint32_t newline_bits_by_word(uint4 v) {
-    return (nl_flags(v.x) >> 7) | (nl_flags(v.y) >> 6) | (nl_flags(v.z) >> 5) | (nl_flags(v.w) >> 4);
-}
-
 // the four vectors a thread loads of a tile (lane-consecutive: coalesced)
 __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0, unsigned tid,
                                                 uint4 (&x)[4]) {
@@ -121,76 +113,99 @@ __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ byte
 
 // One tile per CTA, handed out by the hardware scheduler.  (Persistent CTAs that prefetch the next tile's vectors into
 // registers while working on the current one were measured: 54 registers, 4 CTAs per SM, 16 % slower.)
+//
+// FILTER, THEN FINISH DENSELY.  An exact per-byte compare costs ~8 ALU ops per 32-bit word, and ncu showed this kernel
+// instruction-bound.  So every vector first takes a 2-op-per-word test that cannot miss a newline: adding 0x60 to every
+// byte sets bit 7 of every byte >= 0x20 (no carry leaves a byte of ASCII text; a carry from a byte >= 0xA0 only adds 1 to
+// its neighbour, and 0x0A + 0x60 + 1 still has bit 7 clear), so a vector whose four sums AND to 0x80 in every byte holds
+// no '\n'.  In FASTQ text one vector in five survives.  A ballot turns the survivors into a bitmap in file order, and the
+// CTA then works on the survivors only, one per thread: exact newline mask, rank by a CTA scan, the bytes next to each
+// newline from the shared-memory copy of the tile, one slot entry per newline.
 __global__ void __launch_bounds__(kFqThreads)
 fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
                    uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long n_tiles) {
-    __shared__ uint4 raw[kFqTile / 16];                   // the tile's text: the bytes next to a newline are looked up here
-    __shared__ __align__(16) uint32_t nlg[kFqTile / 16];  // newline bits of every vector
-    __shared__ uint16_t list[kFqListCap];                 // positions of the tile's newlines
+    __shared__ uint4 raw[kFqTile / 16];                   // the tile's text
+    __shared__ uint32_t hitbits[kFqTile / 512];           // one bit per vector: may hold a newline
     __shared__ unsigned warp_tot[kFqThreads / 32];
+    static_assert(kFqTile / 512 == 32, "one bitmap word per lane");
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-    const unsigned long long tile = blockIdx.x;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const unsigned long long tile0 = tile * kFqTile;
     uint4 x[4];
     lines_load_tile(bytes, n, tile0, tid, x);
+    constexpr uint32_t kAdd = 0x60606060u, kTop = 0x80808080u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        raw[tid + j * kFqThreads] = x[j];
-        nlg[tid + j * kFqThreads] = newline_bits_by_word(x[j]);
+        const unsigned v = tid + j * kFqThreads;
+        raw[v] = x[j];
+        const uint32_t t = (x[j].x + kAdd) & (x[j].y + kAdd) & (x[j].z + kAdd) & (x[j].w + kAdd);
+        const unsigned b = __ballot_sync(0xffffffffu, (t & kTop) != kTop);
+        if (lane == 0) hitbits[v >> 5] = b;
     }
     __syncthreads();
-    // thread t owns bytes [64 t, 64 t + 64) of the tile: four consecutive vectors
-    const uint4 g4 = *reinterpret_cast<const uint4*>(nlg + 4 * tid);
-    // the four vectors' bits in one 64-bit word: bit 32 h + 8 k + 4 jj + i <-> vector 2 h + jj, byte 4 i + k
-    unsigned long long G = ((unsigned long long)(g4.z | (g4.w << 4)) << 32) | (g4.x | (g4.y << 4));
-    const unsigned cnt = __popcll(G);
-    unsigned inc = cnt;
+    // every warp: inclusive prefix of the 32 bitmap words' popcounts
+    const uint32_t hw = hitbits[lane];
+    unsigned inc = __popc(hw);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= (unsigned)o) inc += t;
     }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    unsigned rank = inc - cnt, total = 0;
+    const unsigned n_hit = __shfl_sync(0xffffffffu, inc, 31);
+    const uint8_t* rb = reinterpret_cast<const uint8_t*>(raw);
+    uint32_t* row = slots + tile * kFqSlots;
+    unsigned total = 0;                                    // newlines of the hit vectors handled so far (CTA-uniform)
+    for (unsigned i0 = 0; i0 < n_hit; i0 += kFqThreads) {
+        const unsigned i = i0 + tid;
+        const bool active = i < n_hit;
+        const unsigned ii = active ? i : n_hit - 1;
+        // hit vector #ii: the bitmap word k that holds it (= number of words whose inclusive prefix is <= ii), then the bit
+        unsigned k = 0;
 #pragma unroll
-    for (unsigned w = 0; w < kFqThreads / 32; ++w) {
-        const unsigned wt = warp_tot[w];
-        rank += w < warp ? wt : 0u;
-        total += wt;
+        for (unsigned step = 16; step; step >>= 1) {
+            const unsigned t = __shfl_sync(0xffffffffu, inc, k + step - 1);
+            if (t <= ii) k += step;
+        }
+        const unsigned prev_inc = __shfl_sync(0xffffffffu, inc, k ? k - 1 : 0);
+        const uint32_t word = __shfl_sync(0xffffffffu, hw, k);
+        const unsigned v = 32u * k + __fns(word, 0, (int)(ii - (k ? prev_inc : 0u)) + 1);
+        uint32_t m = active ? newline_mask16(raw[v]) : 0u;   // exact; bit b <-> byte b of the vector
+        const unsigned cnt = __popc(m);
+        unsigned c_inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, c_inc, o);
+            if (lane >= (unsigned)o) c_inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = c_inc;
+        __syncthreads();
+        unsigned rank = total + c_inc - cnt, round_total = 0;
+#pragma unroll
+        for (unsigned w = 0; w < kFqThreads / 32; ++w) {
+            const unsigned wt = warp_tot[w];
+            rank += w < warp ? wt : 0u;
+            round_total += wt;
+        }
+        while (m) {
+            const unsigned q = 16u * v + (__ffs((int)m) - 1);
+            m &= m - 1;
+            uint32_t prev, next;
+            if (q > 0) prev = rb[q - 1];
+            else prev = tile0 ? bytes[tile0 - 1] : 0u;
+            if (q + 1 < (unsigned)kFqTile) next = rb[q + 1];        // past the text the staged bytes are the virtual newline / NUL
+            else next = tile0 + q + 1 < n ? bytes[tile0 + q + 1] : 0u;
+            if (rank < (unsigned)kFqSlots)
+                row[rank] = q | (prev == '\r' ? kSlotCr : 0u) | (next == '@' ? kSlotAt : 0u) | (next == '+' ? kSlotPlus : 0u);
+            ++rank;
+        }
+        total += round_total;
+        __syncthreads();   // warp_tot is reused by the next round
     }
     if (tid == 0) {
         counts[tile] = total;
         if (total > (unsigned)kFqSlots) *overflow = 1u;
     }
-    // ---- the thread's newlines go to a shared list at its rank, in any order inside its 64 bytes ...
-    while (G) {
-        const unsigned b = __ffsll((long long)G) - 1;
-        G &= G - 1;
-        const unsigned q = 64u * tid + 32u * (b >> 5) + 16u * ((b >> 2) & 1u) + 4u * (b & 3u) + ((b >> 3) & 3u);
-        if (rank < (unsigned)kFqListCap) list[rank] = (uint16_t)q;
-        ++rank;
-    }
-    __syncthreads();
-    // ---- ... and are finished densely, one list entry per thread: its rank in file order, the bytes next to it, the slot
-    const uint8_t* rb = reinterpret_cast<const uint8_t*>(raw);
-    uint32_t* row = slots + tile * kFqSlots;
-    const unsigned n_list = total < (unsigned)kFqListCap ? total : (unsigned)kFqListCap;
-    for (unsigned e = tid; e < n_list; e += kFqThreads) {
-        const unsigned q = list[e], span = q >> 6;
-        unsigned first = e, smaller = 0;                       // entries of one span are adjacent in the list
-        while (first > 0 && (list[first - 1] >> 6) == span) --first;
-        for (unsigned f = first; f < n_list && (list[f] >> 6) == span; ++f) smaller += list[f] < q ? 1u : 0u;
-        const unsigned slot = first + smaller;
-        uint32_t prev, next;
-        if (q > 0) prev = rb[q - 1];
-        else prev = tile0 ? bytes[tile0 - 1] : 0u;
-        if (q + 1 < (unsigned)kFqTile) next = rb[q + 1];        // past the text the staged bytes are the virtual newline / NUL
-        else next = tile0 + q + 1 < n ? bytes[tile0 + q + 1] : 0u;
-        if (slot < (unsigned)kFqSlots)
-            row[slot] = q | (prev == '\r' ? kSlotCr : 0u) | (next == '@' ? kSlotAt : 0u) | (next == '+' ? kSlotPlus : 0u);
-    }
+    __syncthreads();   // raw / hitbits are reused by the next tile
     }
 }
 
@@ -639,13 +654,20 @@ struct FqScratch {
     }
 };
 
-cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
+cudaError_t launch_fastq_count(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
                                cudaStream_t s) {
     if (n_bytes == 0) return cudaMemsetAsync(d_n_lines, 0, sizeof(uint64_t), s);
     const FqScratch sc(d_scratch, n_bytes);
     cudaError_t e = cudaMemsetAsync(sc.overflow, 0, 16, s);
     if (e != cudaSuccess) return e;
-    fastq_lines_kernel<<<(unsigned)sc.n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles);
+    static const int lines_mode = [] {
+        const char* v = getenv("BN_FQ_LINES");
+        return v ? atoi(v) : 0;
+    }();
+    static const int resident = resident_blocks(fastq_lines_kernel, kFqThreads, di);
+    const unsigned lines_grid = lines_mode == 1 ? grid_for(sc.n_tiles, resident) : lines_mode == 2 ? grid_for(sc.n_tiles, 2 * resident)
+                                                                                                 : (unsigned)sc.n_tiles;
+    fastq_lines_kernel<<<lines_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles);
     launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -137,8 +137,8 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const unsigned v = tid + j * kFqThreads;
-        raw[v] = x[j];
         const uint32_t t = (x[j].x + kAdd) & (x[j].y + kAdd) & (x[j].z + kAdd) & (x[j].w + kAdd);
+        raw[v] = x[j];   // (staging only the survivors and fetching the bytes at their ends from global memory: 25 % slower)
         const unsigned b = __ballot_sync(0xffffffffu, (t & kTop) != kTop);
         if (lane == 0) hitbits[v >> 5] = b;
     }
@@ -158,24 +158,28 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
     for (unsigned i0 = 0; i0 < n_hit; i0 += kFqThreads) {
         const unsigned i = i0 + tid;
         const bool active = i < n_hit;
-        const unsigned ii = active ? i : n_hit - 1;
-        // hit vector #ii: the bitmap word k that holds it (= number of words whose inclusive prefix is <= ii), then the bit
-        unsigned k = 0;
+        unsigned v = 0, cnt = 0, c_inc = 0;
+        uint32_t m = 0;
+        if (i0 + 32u * warp < n_hit) {   // warp-uniform: a warp with no survivor of this round only joins the barriers
+            const unsigned ii = active ? i : n_hit - 1;
+            // hit vector #ii: the bitmap word k that holds it (= number of words whose inclusive prefix is <= ii), then the bit
+            unsigned k = 0;
 #pragma unroll
-        for (unsigned step = 16; step; step >>= 1) {
-            const unsigned t = __shfl_sync(0xffffffffu, inc, k + step - 1);
-            if (t <= ii) k += step;
-        }
-        const unsigned prev_inc = __shfl_sync(0xffffffffu, inc, k ? k - 1 : 0);
-        const uint32_t word = __shfl_sync(0xffffffffu, hw, k);
-        const unsigned v = 32u * k + __fns(word, 0, (int)(ii - (k ? prev_inc : 0u)) + 1);
-        uint32_t m = active ? newline_mask16(raw[v]) : 0u;   // exact; bit b <-> byte b of the vector
-        const unsigned cnt = __popc(m);
-        unsigned c_inc = cnt;
+            for (unsigned step = 16; step; step >>= 1) {
+                const unsigned t = __shfl_sync(0xffffffffu, inc, k + step - 1);
+                if (t <= ii) k += step;
+            }
+            const unsigned prev_inc = __shfl_sync(0xffffffffu, inc, k ? k - 1 : 0);
+            const uint32_t word = __shfl_sync(0xffffffffu, hw, k);
+            v = 32u * k + __fns(word, 0, (int)(ii - (k ? prev_inc : 0u)) + 1);
+            m = active ? newline_mask16(raw[v]) : 0u;   // exact; bit b <-> byte b of the vector
+            cnt = __popc(m);
+            c_inc = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, c_inc, o);
-            if (lane >= (unsigned)o) c_inc += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, c_inc, o);
+                if (lane >= (unsigned)o) c_inc += t;
+            }
         }
         if (lane == 31) warp_tot[warp] = c_inc;
         __syncthreads();
@@ -654,19 +658,15 @@ struct FqScratch {
     }
 };
 
-cudaError_t launch_fastq_count(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
+cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
                                cudaStream_t s) {
     if (n_bytes == 0) return cudaMemsetAsync(d_n_lines, 0, sizeof(uint64_t), s);
     const FqScratch sc(d_scratch, n_bytes);
     cudaError_t e = cudaMemsetAsync(sc.overflow, 0, 16, s);
     if (e != cudaSuccess) return e;
-    static const int lines_mode = [] {
-        const char* v = getenv("BN_FQ_LINES");
-        return v ? atoi(v) : 0;
-    }();
-    static const int resident = resident_blocks(fastq_lines_kernel, kFqThreads, di);
-    const unsigned lines_grid = lines_mode == 1 ? grid_for(sc.n_tiles, resident) : lines_mode == 2 ? grid_for(sc.n_tiles, 2 * resident)
-                                                                                                 : (unsigned)sc.n_tiles;
+    // one tile per CTA: a resident grid striding over the tiles was measured at 1x and 2x the resident CTA count and is
+    // 10-15 % slower (as for the codec kernels: the two dies finish at different times)
+    const unsigned lines_grid = (unsigned)sc.n_tiles;
     fastq_lines_kernel<<<lines_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles);
     launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
     e = cudaGetLastError();

@@ -23,7 +23,7 @@
 //      A tile with more than 2048 lines (average line under 8 bytes) does not fit its slot row: the count pass raises a
 //      flag and step 2 runs the dense form instead (fastq_index_kernel re-reads the text and writes nl[line], then
 //      fastq_records_kernel) -- both forms are launched, the device-side flag decides which one works.
-//   3. fastq_encode_kernel   PACK THEN CUT over tiles of 64 KiB of text: the whole tile (headers and qualities too) is
+//   3. fastq_encode_kernel   PACK THEN CUT over tiles of 48 KiB of text: the whole tile (headers and qualities too) is
 //                            packed like the contiguous encode -- aligned coalesced 128-bit loads, 16 bytes -> one
 //                            32-bit code, one "contains a non-ACGT byte" flag per vector via a ballot -- into a
 //                            shared-memory strip; then one thread per read that starts in the tile cuts the read's
@@ -310,13 +310,23 @@ fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __
     for (unsigned long long r = ra + lane; r < rb; r += 32) {
         unsigned long long pos[4] = {0, 0, 0, 0};
         uint32_t ent[4] = {0, 0, 0, 0};
-        unsigned long long tt = t;
-        for (int k = 0; k < 4; ++k) {
-            const unsigned long long L = 4 * r + k;
-            if (L >= n_lines) break;
-            while (L >= line_base[tt + 1]) ++tt;                      // a line that ends in a later tile
-            ent[k] = slots[tt * kFqSlots + (L - line_base[tt])];
-            pos[k] = tt * kFqTile + (ent[k] & kSlotPos);
+        if (4 * r + 3 < le) {   // the usual case: all four lines end in this tile -- four neighbouring entries, 32-bit arithmetic
+            const uint32_t* e4 = slots + t * kFqSlots + (unsigned)(4 * r - lb);
+            const unsigned long long base = t * kFqTile;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ent[k] = e4[k];
+                pos[k] = base + (ent[k] & kSlotPos);
+            }
+        } else {
+            unsigned long long tt = t;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned long long L = 4 * r + k;
+                if (L >= n_lines) break;
+                while (L >= line_base[tt + 1]) ++tt;                      // a line that ends in a later tile
+                ent[k] = slots[tt * kFqSlots + (L - line_base[tt])];
+                pos[k] = tt * kFqTile + (ent[k] & kSlotPos);
+            }
         }
         if (4 * r + 2 < n_lines && !(ent[1] & kSlotPlus)) report_min(status + 1, (r << 8) | FQ_BAD_SEPARATOR);
         if (4 * r + 4 < n_lines && !(ent[3] & kSlotAt)) report_min(status + 1, ((r + 1) << 8) | FQ_BAD_HEADER);

@@ -102,6 +102,59 @@ def main():
     assert sum(t) == 150 * n_reads
     out["base_counts"] = {"reads": n_reads, "ms": ms, "Greads_s": n_reads / ms / 1e6, "totals": t, "gc_global": sh.gc_from_counts(t),
                           "GB_s_aggregate": 80 * n_reads / ms / 1e6}
+    del words, counts4, gcs
+
+    # ---- FASTQ text -> records -> packed reads, strong scaling: 2 x 10^7 reads of 150 bp in all (6.5 GB of text), every
+    # rank builds and parses only its own contiguous range of records (what sharding.shard_fastq_text cuts from a real
+    # file); the number of reads and of output words is all-reduced, no data-path collective
+    n_reads = int(20_000_000 * args.scale)
+    r0, r1 = sh.shard_range(n_reads, rank, world)
+    nr, rl, hdr = r1 - r0, 150, 23
+    rec = hdr + rl + 1 + 2 + rl + 1
+    t2 = torch.full((nr, rec), ord("I"), dtype=torch.uint8, device=dev)
+    t2[:, 0] = ord("@")
+    t2[:, 1 : hdr - 1] = ord("h")
+    t2[:, hdr - 1] = 10
+    b0 = (r0 * rl) // 32 * 32                                   # the generator starts on a word boundary
+    seqs = dv.synth_ascii(SEED, 7, b0, nr * rl + 32, device=dev)[r0 * rl - b0 : r0 * rl - b0 + nr * rl]
+    t2[:, hdr : hdr + rl] = seqs.view(nr, rl)
+    del seqs
+    t2[:, hdr + rl] = 10
+    t2[:, hdr + rl + 1] = ord("+")
+    t2[:, hdr + rl + 2] = 10
+    t2[:, rec - 1] = 10
+    text = t2.view(-1)
+    ctx = dv.api.default_context(local)
+    n_bytes = text.numel()
+    P = dv._ptr
+    scratch = torch.empty(ctx.lib.bn_fastq_scratch_bytes(n_bytes), dtype=torch.uint8, device=dev)
+    iscratch = torch.empty(ctx.lib.bn_fastq_index_scratch_bytes(nr), dtype=torch.uint8, device=dev)
+    n_lines = torch.zeros(1, dtype=torch.int64, device=dev)
+    so, sl = torch.empty(nr, dtype=torch.int64, device=dev), torch.empty(nr, dtype=torch.int64, device=dev)
+    wo = torch.empty(nr + 1, dtype=torch.int64, device=dev)
+    wpr = (rl + 31) // 32
+    fwords = torch.empty(nr * wpr, dtype=torch.int64, device=dev)
+    st = dv.FastqStatus(dev)
+
+    def fq():
+        dv.raise_for(ctx.lib.bn_fastq_count_dev(ctx.handle, dv._stream(), P(text), n_bytes, P(scratch), P(n_lines)))
+        dv.raise_for(ctx.lib.bn_fastq_index_dev(ctx.handle, dv._stream(), P(text), n_bytes, nr, P(scratch), P(iscratch), P(so), P(sl), P(wo),
+                                                P(st.word)))
+        dv.raise_for(ctx.lib.bn_fastq_encode_dev(ctx.handle, dv._stream(), P(text), n_bytes, nr, P(scratch), P(so), P(sl), P(wo), P(fwords),
+                                                 P(st.word)))
+
+    ms = timed(fq)
+    st.n_lines, st.seq_offsets, st.n_reads = int(n_lines.item()), so, nr
+    st.check()
+    sizes = torch.tensor([st.n_lines // 4, int(wo[-1].item())], dtype=torch.int64, device=dev)
+    sh.allreduce_sum(sizes)
+    assert sizes.tolist() == [n_reads, n_reads * wpr]
+    # the first packed word of this rank's first read is the generator's own word (reads are 150 bases: word-aligned every 16 reads)
+    if (r0 * rl) % 32 == 0:
+        assert int(fwords[0].item()) == int(dv.synth_words(SEED, 7, r0 * rl // 32, 1, device=dev)[0].item())
+    text_total = n_reads * rec
+    out["fastq"] = {"reads": n_reads, "text_bytes": text_total, "ms": ms, "Gbases_s": n_reads * rl / ms / 1e6,
+                    "text_GB_s_aggregate": text_total / ms / 1e6}
     if rank == 0:
         print(json.dumps(out), file=_STDOUT, flush=True)
     if world > 1:

@@ -183,13 +183,10 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
         }
         if (lane == 31) warp_tot[warp] = c_inc;
         __syncthreads();
-        unsigned rank = total + c_inc - cnt, round_total = 0;
-#pragma unroll
-        for (unsigned w = 0; w < kFqThreads / 32; ++w) {
-            const unsigned wt = warp_tot[w];
-            rank += w < warp ? wt : 0u;
-            round_total += wt;
-        }
+        // this warp's base and the round's total from the eight warp totals: two warp reductions (REDUX), no loop
+        const unsigned wt = lane < kFqThreads / 32 ? warp_tot[lane] : 0u;
+        const unsigned round_total = __reduce_add_sync(0xffffffffu, wt);
+        unsigned rank = total + c_inc - cnt + __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u);
         while (m) {
             const unsigned q = 16u * v + (__ffs((int)m) - 1);
             m &= m - 1;

@@ -287,3 +287,42 @@ def test_text_lengths_around_tile_multiples(bn, dv, size, delta, final_newline):
     assert len(text) == size + delta
     exp = check(bn, dv, text)
     assert exp[0] == "ok" and int(exp[4][-1]) == tail_len
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_mutated_texts_fuzz(bn, dv, seed):
+    """Random damage to valid texts -- a byte turned into a newline / '@' / '+' / '\\r' / junk, a byte deleted, the text cut,
+    a line duplicated -- must give the oracle's answer whatever it is: the same records, the same first fault, or the same
+    first invalid base."""
+    rng = np.random.default_rng(500 + seed)
+    outcomes = set()
+    for _ in range(25):
+        kind = int(rng.integers(0, 3))
+        lens = [rng.integers(0, 40, int(rng.integers(1, 30))), rng.integers(100, 152, int(rng.integers(1, 400))),
+                rng.integers(1, 6000, int(rng.integers(1, 20)))][kind]
+        text = bytearray(make_fastq(rng, lens, crlf=bool(rng.integers(0, 2)), final_newline=bool(rng.integers(0, 2)), alphabet=b"ACGTacgt"))
+        for _ in range(int(rng.integers(1, 4))):
+            if not text:
+                break
+            i = int(rng.integers(0, len(text)))
+            k = int(rng.integers(0, 8))
+            if k == 0:
+                text[i] = 10
+            elif k == 1:
+                text[i] = ord("@")
+            elif k == 2:
+                text[i] = ord("+")
+            elif k == 3:
+                text[i] = 13
+            elif k == 4:
+                text[i] = int(rng.integers(0, 256))
+            elif k == 5:
+                del text[i]
+            elif k == 6:
+                del text[i:]
+            else:
+                e = text.find(b"\n", i)
+                if e >= 0:
+                    text[e + 1 : e + 1] = text[text.rfind(b"\n", 0, i) + 1 : e + 1]
+        outcomes.add(check(bn, dv, bytes(text))[0])
+    assert outcomes   # usually all three of ok / fault / base

@@ -765,3 +765,38 @@ def test_host_pointer_calls_are_chunk_invariant(bn):
     err = gpu_error(bn, bn.kmers, seq, 27, ctx)
     assert err.offset == 77_777 and err.record == 77_777 - 26 and err.partial.size == 77_777 - 26
     assert [int(x) for x in err.partial[-50:]] == [oracle.as_2bit(seq[i : i + 27]) for i in range(77_777 - 26 - 50, 77_777 - 26)]
+
+
+def test_base_counts_batch_chunked_pipeline_matches_the_staged_call(bn):
+    """bn_base_counts_batch cuts reads laid out in order into chunks of whole reads (3-stage pipeline); out-of-order
+    layouts take the staged path.  Both must equal the oracle per read, whatever the chunk size."""
+    rng = np.random.default_rng(17)
+    lens = np.concatenate([rng.integers(0, 400, 3000), [5000, 0, 0, 33, 9000], rng.integers(1, 64, 500)]).astype(np.uint64)
+    seqs = [ACGT[rng.integers(0, 4, int(n))].tobytes() for n in lens]
+    words, wo = [], [0]
+    for s in seqs:
+        words += oracle.encode_alloc(s) if s else []
+        wo.append(len(words))
+    w, wo = np.array(words, dtype=np.uint64), np.array(wo, dtype=np.uint64)
+    exp_counts = np.array([oracle.base_counts(oracle.encode_alloc(s), len(s)) if s else [0, 0, 0, 0] for s in seqs], dtype=np.uint64)
+    exp_gc = np.array([oracle.gc_content(oracle.encode_alloc(s), len(s)) if s else 0.0 for s in seqs])
+    for chunk in (0, 4096, 65536):
+        ctx = bn.Context(0)
+        if chunk:
+            ctx.set_chunk_bytes(chunk)
+        counts, gc, totals = bn.base_counts_batch(w, wo, lens, ctx=ctx)
+        assert np.array_equal(counts, exp_counts) and np.array_equal(gc, exp_gc)
+        assert totals == [int(x) for x in exp_counts.sum(axis=0)]
+        # overlapping but ordered reads: read r+1 starts inside read r (every read is a window of one long sequence)
+        starts = np.sort(rng.integers(0, max(1, w.size - 40), 2000)).astype(np.uint64)
+        olens = np.minimum(rng.integers(1, 1200, 2000), (w.size - starts) * 32).astype(np.uint64)
+        c2, g2, t2 = bn.base_counts_batch(w, np.concatenate([starts, [w.size]]).astype(np.uint64), olens, ctx=ctx)
+        for r in (0, 1, 999, 1999):
+            sl = w[int(starts[r]) : int(starts[r]) + (int(olens[r]) + 31) // 32]
+            assert [int(x) for x in c2[r]] == oracle.base_counts(sl, int(olens[r])) and g2[r] == oracle.gc_content(sl, int(olens[r]))
+        assert sum(t2) == int(olens.sum())
+        # out of order: the staged path
+        perm = rng.permutation(len(lens))
+        c3, g3, t3 = bn.base_counts_batch(w, np.concatenate([wo[:-1][perm], [w.size]]).astype(np.uint64), lens[perm], ctx=ctx)
+        assert np.array_equal(c3, exp_counts[perm]) and np.array_equal(g3, exp_gc[perm]) and t3 == totals
+        ctx.close()

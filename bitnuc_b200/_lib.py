@@ -76,6 +76,12 @@ PROTOTYPES = {
     "bn_get_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "bn_fastq_scan": (_int, [_vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), _errp]),
     "bn_fastq_encode": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _errp]),
+    "bn_fasta_scan": (_int, [_vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), _errp]),
+    "bn_fasta_encode": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _errp]),
+    "bn_fasta_count_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "bn_fasta_index_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bn_fasta_encode_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bn_fasta_status_fetch": (_int, [_vp, _vp, _vp, _u64, _vp, _sz, _errp]),
     "bn_fastq_scratch_bytes": (_sz, [_sz]),
     "bn_fastq_index_scratch_bytes": (_sz, [_sz]),
     "bn_fastq_count_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),

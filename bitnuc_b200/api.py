@@ -319,7 +319,12 @@ def encode_batch(data, offsets, ctx: Context | None = None, per_read_status: boo
     return (words, wo, status[:n]) if per_read_status else (words, wo)
 
 
-def fastq_encode(text, ctx: Context | None = None):
+def fasta_encode(text, ctx: Context | None = None):
+    """FASTA text with one sequence line per record -> (words, word_offsets, seq_offsets, seq_lens); see ``fastq_encode``."""
+    return fastq_encode(text, ctx, _fasta=True)
+
+
+def fastq_encode(text, ctx: Context | None = None, _fasta: bool = False):
     """FASTQ text -> (words, word_offsets, seq_offsets, seq_lens), parsed and encoded on the device: the caller's loop
     ``for record in reader { PackedSequence::new(record.seq())? }`` (README.md:160-180, src/sequence.rs:40-52) without a
     host-side parser.  Raises ``FastqError`` for the first malformed record, else ``InvalidBase`` (with ``.record``,
@@ -327,12 +332,13 @@ def fastq_encode(text, ctx: Context | None = None):
     ctx = ctx or default_context()
     t = _u8(text)
     nr, nw, err = C.c_size_t(0), C.c_size_t(0), BnError()
-    raise_for(ctx.lib.bn_fastq_scan(ctx.handle, _p(t), t.size, C.byref(nr), C.byref(nw), C.byref(err)), err)
+    scan, enc = (ctx.lib.bn_fasta_scan, ctx.lib.bn_fasta_encode) if _fasta else (ctx.lib.bn_fastq_scan, ctx.lib.bn_fastq_encode)
+    raise_for(scan(ctx.handle, _p(t), t.size, C.byref(nr), C.byref(nw), C.byref(err)), err)
     n, w = nr.value, nw.value
     words = np.empty(max(1, w), dtype=np.uint64)
     wo = np.zeros(n + 1, dtype=np.uint64)
     so, sl = np.empty(max(1, n), dtype=np.uint64), np.empty(max(1, n), dtype=np.uint64)
-    rc = ctx.lib.bn_fastq_encode(ctx.handle, _p(t), t.size, n, w, _p(words), _p(wo), _p(so), _p(sl), C.byref(err))
+    rc = enc(ctx.handle, _p(t), t.size, n, w, _p(words), _p(wo), _p(so), _p(sl), C.byref(err))
     if rc == 1:
         e = NucleotideError.InvalidBase(err.base)
         e.record, e.position, e.offset = int(err.record), int(err.b), int(err.offset)

@@ -54,6 +54,7 @@ struct bn_ctx {
     const void* fq_text = nullptr;
     size_t fq_bytes = 0, fq_reads = 0, fq_words = 0;
     bool fq_valid = false;
+    int fq_fasta = 0;
     int compat = BN_COMPAT_X86_64;
     std::mutex mu;
 };
@@ -211,9 +212,9 @@ int bn_error_string(const bn_error_t* e, char* buf, size_t cap) {
     case BN_ERR_EMPTY_ENCODE: return snprintf(buf, cap, "encode of an empty sequence (the reference panics)");
     case BN_ERR_NOMEM: return snprintf(buf, cap, "out of memory");
     case BN_ERR_FASTQ: {
-        static const char* const what[] = {"malformed record", "header line does not start with '@'", "separator line does not start with '+'",
+        static const char* const what[] = {"malformed record", "header line does not start with '@' (FASTA: '>')", "separator line does not start with '+'",
                                            "quality and sequence lengths differ", "text ends inside the record"};
-        return snprintf(buf, cap, "FASTQ record %llu: %s", (unsigned long long)e->record, what[e->a <= 4 ? e->a : 0]);
+        return snprintf(buf, cap, "record %llu: %s", (unsigned long long)e->record, what[e->a <= 4 ? e->a : 0]);
     }
     default: return snprintf(buf, cap, "unknown error %d", e->code);
     }
@@ -518,35 +519,61 @@ int bn_get_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const u
 size_t bn_fastq_scratch_bytes(size_t n_bytes) { return bn::fastq_scratch_bytes(n_bytes); }
 size_t bn_fastq_index_scratch_bytes(size_t n_reads) { return bn::fastq_index_scratch_bytes(n_reads); }
 
-int bn_fastq_count_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines) {
+static int fastx_count_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines, int fasta) {
     if (!ctx || !d_n_lines || (n_bytes && (!d_text || !d_scratch)) || (reinterpret_cast<uintptr_t>(d_text) & 15u)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
-    BN_LAUNCH(bn::launch_fastq_count(ctx->di, d_text, n_bytes, d_scratch, d_n_lines, pick(ctx, stream)));
+    BN_LAUNCH(bn::launch_fastq_count(ctx->di, d_text, n_bytes, d_scratch, d_n_lines, fasta, pick(ctx, stream)));
     return BN_OK;
 }
 
-int bn_fastq_index_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
-                       void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_status) {
+static int fastx_index_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                           void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_status,
+                           int fasta) {
     if (!ctx || !d_status || !d_word_offsets || (reinterpret_cast<uintptr_t>(d_text) & 15u) ||
         (reinterpret_cast<uintptr_t>(d_index_scratch) & 15u) ||
         (n_bytes && (!d_text || !d_scratch)) || (n_reads && (!d_index_scratch || !d_seq_offsets || !d_seq_lens)))
         return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
     BN_LAUNCH(bn::launch_fastq_index(ctx->di, d_text, n_bytes, n_reads, d_scratch, d_index_scratch, d_seq_offsets, d_seq_lens, d_word_offsets,
-                                     reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+                                     reinterpret_cast<unsigned long long*>(d_status), fasta, pick(ctx, stream)));
     return BN_OK;
 }
 
-int bn_fastq_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
-                        const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets, uint64_t* d_out_words,
-                        uint64_t* d_status) {
+static int fastx_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                            const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets, uint64_t* d_out_words,
+                            uint64_t* d_status, int fasta) {
     if (!ctx || !d_status || (reinterpret_cast<uintptr_t>(d_text) & 15u) ||
         (n_reads && (!d_text || !d_scratch || !d_seq_offsets || !d_seq_lens || !d_word_offsets)))
         return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
     BN_LAUNCH(bn::launch_fastq_encode(ctx->di, d_text, n_bytes, n_reads, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,
-                                      reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
+                                      reinterpret_cast<unsigned long long*>(d_status), fasta, pick(ctx, stream)));
     return BN_OK;
+}
+
+int bn_fastq_count_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines) {
+    return fastx_count_dev(ctx, stream, d_text, n_bytes, d_scratch, d_n_lines, 0);
+}
+int bn_fasta_count_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines) {
+    return fastx_count_dev(ctx, stream, d_text, n_bytes, d_scratch, d_n_lines, 1);
+}
+int bn_fastq_index_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                       void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_status) {
+    return fastx_index_dev(ctx, stream, d_text, n_bytes, n_reads, d_scratch, d_index_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_status, 0);
+}
+int bn_fasta_index_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                       void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_status) {
+    return fastx_index_dev(ctx, stream, d_text, n_bytes, n_reads, d_scratch, d_index_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_status, 1);
+}
+int bn_fastq_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                        const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets, uint64_t* d_out_words,
+                        uint64_t* d_status) {
+    return fastx_encode_dev(ctx, stream, d_text, n_bytes, n_reads, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status, 0);
+}
+int bn_fasta_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t n_reads, void* d_scratch,
+                        const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets, uint64_t* d_out_words,
+                        uint64_t* d_status) {
+    return fastx_encode_dev(ctx, stream, d_text, n_bytes, n_reads, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status, 1);
 }
 
 static int fastq_fault(bn_error_t* err, unsigned long long key) {
@@ -555,8 +582,20 @@ static int fastq_fault(bn_error_t* err, unsigned long long key) {
     return BN_ERR_FASTQ;
 }
 
+static int fastx_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, uint64_t n_lines, const uint64_t* d_seq_offsets,
+                              size_t n_reads, bn_error_t* err, unsigned lines_per_record);
+
 int bn_fastq_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, uint64_t n_lines, const uint64_t* d_seq_offsets,
                           size_t n_reads, bn_error_t* err) {
+    return fastx_status_fetch(ctx, stream, d_status, n_lines, d_seq_offsets, n_reads, err, 4);
+}
+int bn_fasta_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, uint64_t n_lines, const uint64_t* d_seq_offsets,
+                          size_t n_reads, bn_error_t* err) {
+    return fastx_status_fetch(ctx, stream, d_status, n_lines, d_seq_offsets, n_reads, err, 2);
+}
+
+static int fastx_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, uint64_t n_lines, const uint64_t* d_seq_offsets,
+                              size_t n_reads, bn_error_t* err, unsigned lines_per_record) {
     if (!ctx || !d_status) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -565,7 +604,7 @@ int bn_fastq_status_fetch(bn_ctx* ctx, void* stream, const uint64_t* d_status, u
     BN_CUDA(cudaStreamSynchronize(s));
     unsigned long long fault = ctx->h_words[1];
     const unsigned long long key = ctx->h_words[0];
-    if (n_lines % 4) fault = std::min<unsigned long long>(fault, ((n_lines / 4) << 8) | BN_FASTQ_TRUNCATED);
+    if (n_lines % lines_per_record) fault = std::min<unsigned long long>(fault, ((n_lines / lines_per_record) << 8) | BN_FASTQ_TRUNCATED);
     if (fault != kNoError) return fastq_fault(err, fault);
     if (key == kNoError) return set_err(err, BN_OK);
     invalid_base(err, key, 0);
@@ -1441,8 +1480,9 @@ extern "C" {
 
 // FASTQ text -> records -> packed words.  The text is staged whole (pageable text in chunks through pinned buffers);
 // scan and encode are two calls because the caller has to allocate the outputs in between.
-int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err) {
+static int fastx_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err, int fasta) {
     if (!ctx || !n_reads || !n_words || (n_bytes && !text)) return set_err(err, BN_ERR_ARGUMENT);
+    const unsigned lpr = fasta ? 2u : 4u;   // lines per record
     *n_reads = *n_words = 0;
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1450,6 +1490,7 @@ int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_re
     ctx->fq_text = text;
     ctx->fq_bytes = n_bytes;
     ctx->fq_reads = ctx->fq_words = 0;
+    ctx->fq_fasta = fasta;
     if (n_bytes == 0) {
         ctx->fq_valid = true;
         return set_err(err, BN_OK);
@@ -1459,23 +1500,23 @@ int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_re
     BN_CUDA(ensure(ctx->fq[1], bn::fastq_scratch_bytes(n_bytes)));
     const uint8_t* d_text = static_cast<const uint8_t*>(ctx->fq[0].p);
     if (const int rc = upload_whole(ctx, ctx->fq[0].p, text, n_bytes, err)) return rc;
-    BN_CUDA(bn::launch_fastq_count(ctx->di, d_text, n_bytes, ctx->fq[1].p, reinterpret_cast<uint64_t*>(ctx->d_words + 10), st));
+    BN_CUDA(bn::launch_fastq_count(ctx->di, d_text, n_bytes, ctx->fq[1].p, reinterpret_cast<uint64_t*>(ctx->d_words + 10), fasta, st));
     BN_CUDA(cudaMemcpyAsync(ctx->h_words + 10, ctx->d_words + 10, 8, cudaMemcpyDeviceToHost, st));
     BN_CUDA(cudaStreamSynchronize(st));
     const unsigned long long n_lines = ctx->h_words[10];
-    const size_t nr = (size_t)(n_lines / 4);
+    const size_t nr = (size_t)(n_lines / lpr);
     BN_CUDA(ensure(ctx->fq[2], bn::fastq_index_scratch_bytes(nr)));
     BN_CUDA(ensure(ctx->fq[3], nr * 8 + 8));
     BN_CUDA(ensure(ctx->fq[4], nr * 8 + 8));
     BN_CUDA(ensure(ctx->fq[5], (nr + 1) * 8));
     uint64_t* d_wo = static_cast<uint64_t*>(ctx->fq[5].p);
     BN_CUDA(bn::launch_fastq_index(ctx->di, d_text, n_bytes, nr, ctx->fq[1].p, ctx->fq[2].p, static_cast<uint64_t*>(ctx->fq[3].p),
-                                   static_cast<uint64_t*>(ctx->fq[4].p), d_wo, ctx->d_words + 12, st));
+                                   static_cast<uint64_t*>(ctx->fq[4].p), d_wo, ctx->d_words + 12, fasta, st));
     BN_CUDA(cudaMemcpyAsync(ctx->h_words + 11, d_wo + nr, 8, cudaMemcpyDeviceToHost, st));
     BN_CUDA(cudaMemcpyAsync(ctx->h_words + 12, ctx->d_words + 12, 16, cudaMemcpyDeviceToHost, st));
     BN_CUDA(cudaStreamSynchronize(st));
     unsigned long long fault = ctx->h_words[13];
-    if (n_lines % 4) fault = std::min<unsigned long long>(fault, ((unsigned long long)nr << 8) | BN_FASTQ_TRUNCATED);
+    if (n_lines % lpr) fault = std::min<unsigned long long>(fault, ((unsigned long long)nr << 8) | BN_FASTQ_TRUNCATED);
     if (fault != kNoError) return fastq_fault(err, fault);
     ctx->fq_reads = nr;
     ctx->fq_words = (size_t)ctx->h_words[11];
@@ -1485,13 +1526,14 @@ int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_re
     return set_err(err, BN_OK);
 }
 
-int bn_fastq_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t* out_words,
-                    uint64_t* out_word_offsets, uint64_t* seq_offsets, uint64_t* seq_lens, bn_error_t* err) {
+static int fastx_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t* out_words,
+                        uint64_t* out_word_offsets, uint64_t* seq_offsets, uint64_t* seq_lens, bn_error_t* err, int fasta) {
     if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     // only valid right after bn_fastq_scan of the same text on this context
-    if (!ctx->fq_valid || ctx->fq_text != text || ctx->fq_bytes != n_bytes || ctx->fq_reads != n_reads || ctx->fq_words != n_words ||
+    if (!ctx->fq_valid || ctx->fq_fasta != fasta || ctx->fq_text != text || ctx->fq_bytes != n_bytes || ctx->fq_reads != n_reads ||
+        ctx->fq_words != n_words ||
         (n_words && !out_words))
         return set_err(err, BN_ERR_ARGUMENT);
     if (n_reads == 0) {
@@ -1504,7 +1546,7 @@ int bn_fastq_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_r
     BN_CUDA(cudaMemsetAsync(ctx->d_words + 12, 0xFF, 8, st));
     BN_CUDA(bn::launch_fastq_encode(ctx->di, static_cast<const uint8_t*>(ctx->fq[0].p), n_bytes, n_reads, ctx->fq[1].p, d_so,
                                     static_cast<const uint64_t*>(ctx->fq[4].p), static_cast<const uint64_t*>(ctx->fq[5].p),
-                                    static_cast<uint64_t*>(ctx->fq[6].p), ctx->d_words + 12, st));
+                                    static_cast<uint64_t*>(ctx->fq[6].p), ctx->d_words + 12, fasta, st));
     if (n_words) BN_CUDA(cudaMemcpyAsync(out_words, ctx->fq[6].p, n_words * 8, cudaMemcpyDeviceToHost, st));
     if (out_word_offsets) BN_CUDA(cudaMemcpyAsync(out_word_offsets, ctx->fq[5].p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (seq_offsets) BN_CUDA(cudaMemcpyAsync(seq_offsets, ctx->fq[3].p, n_reads * 8, cudaMemcpyDeviceToHost, st));
@@ -1526,6 +1568,21 @@ int bn_fastq_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_r
         return BN_INVALID_BASE;
     }
     return set_err(err, BN_OK);
+}
+
+int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err) {
+    return fastx_scan(ctx, text, n_bytes, n_reads, n_words, err, 0);
+}
+int bn_fasta_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err) {
+    return fastx_scan(ctx, text, n_bytes, n_reads, n_words, err, 1);
+}
+int bn_fastq_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t* out_words,
+                    uint64_t* out_word_offsets, uint64_t* seq_offsets, uint64_t* seq_lens, bn_error_t* err) {
+    return fastx_encode(ctx, text, n_bytes, n_reads, n_words, out_words, out_word_offsets, seq_offsets, seq_lens, err, 0);
+}
+int bn_fasta_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t* out_words,
+                    uint64_t* out_word_offsets, uint64_t* seq_offsets, uint64_t* seq_lens, bn_error_t* err) {
+    return fastx_encode(ctx, text, n_bytes, n_reads, n_words, out_words, out_word_offsets, seq_offsets, seq_lens, err, 1);
 }
 
 }  // extern "C"

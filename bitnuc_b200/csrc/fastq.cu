@@ -51,6 +51,14 @@ constexpr unsigned long long kCrBit = 1ull << 63;
 constexpr int kFqSlots = 2048;               // line entries per tile (more lines than this: the dense fallback)
 constexpr uint32_t kSlotPos = 0x3FFFu, kSlotCr = 1u << 14, kSlotAt = 1u << 15, kSlotPlus = 1u << 16;
 
+// Record format: FASTQ = four lines per record opening with '@'; FASTA (one sequence line per record, the form read
+// processors emit) = two lines per record opening with '>'.  shift = log2(lines per record).
+struct TextFormat {
+    unsigned shift;
+    uint32_t header;
+};
+static inline TextFormat text_format(int fasta) { return fasta ? TextFormat{1u, (uint32_t)'>'} : TextFormat{2u, (uint32_t)'@'}; }
+
 enum { FQ_BAD_HEADER = 1, FQ_BAD_SEPARATOR = 2, FQ_BAD_QUALITY_LENGTH = 3 };   // kinds of format error (4 = truncated: host)
 
 static inline unsigned long long fastq_tiles(size_t n_bytes) { return (unsigned long long)n_bytes / kFqTile + 1; }   // covers position n_bytes
@@ -123,7 +131,7 @@ __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ byte
 // newline from the shared-memory copy of the tile, one slot entry per newline.
 __global__ void __launch_bounds__(kFqThreads)
 fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
-                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long n_tiles) {
+                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long n_tiles, uint32_t header) {
     __shared__ uint4 raw[kFqTile / 16];                   // the tile's text
     __shared__ uint32_t hitbits[kFqTile / 512];           // one bit per vector: may hold a newline
     __shared__ unsigned warp_tot[kFqThreads / 32];
@@ -196,7 +204,7 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
             if (q + 1 < (unsigned)kFqTile) next = rb[q + 1];        // past the text the staged bytes are the virtual newline / NUL
             else next = tile0 + q + 1 < n ? bytes[tile0 + q + 1] : 0u;
             if (rank < (unsigned)kFqSlots)
-                row[rank] = q | (prev == '\r' ? kSlotCr : 0u) | (next == '@' ? kSlotAt : 0u) | (next == '+' ? kSlotPlus : 0u);
+                row[rank] = q | (prev == '\r' ? kSlotCr : 0u) | (next == header ? kSlotAt : 0u) | (next == '+' ? kSlotPlus : 0u);
             ++rank;
         }
         total += round_total;
@@ -220,7 +228,7 @@ struct CountOfTile {
 __global__ void __launch_bounds__(kFqThreads)
 fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
                    unsigned long long n_reads, uint64_t* __restrict__ nl, unsigned long long* __restrict__ status,
-                   const unsigned* __restrict__ overflow, unsigned long long n_tiles) {
+                   const unsigned* __restrict__ overflow, unsigned long long n_tiles, TextFormat fmt) {
     __shared__ __align__(8) uint16_t nlb[kFqTile / 16];
     __shared__ unsigned warp_tot[kFqThreads / 32];
     if (*overflow == 0u) return;   // the slot rows hold every line: fastq_records_slots_kernel does the work
@@ -249,9 +257,10 @@ fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, cons
     __syncthreads();
     unsigned rank = inc - cnt;
     for (unsigned w = 0; w < warp; ++w) rank += warp_tot[w];
-    const unsigned long long n_whole = 4 * n_reads;              // nl[] holds the lines of whole records
+    const unsigned long long n_whole = n_reads << fmt.shift;     // nl[] holds the lines of whole records
+    const unsigned last_kind = (1u << fmt.shift) - 1u;
     const unsigned long long n_lines = line_base[n_tiles];     // all lines, a trailing partial record included
-    if (tile == 0 && tid == 0 && n_lines && bytes[0] != '@') report_min(status + 1, FQ_BAD_HEADER);
+    if (tile == 0 && tid == 0 && n_lines && bytes[0] != fmt.header) report_min(status + 1, FQ_BAD_HEADER);
     unsigned long long L = line_base[tile] + rank;
     while (m) {
         const int b = __ffsll((long long)m) - 1;
@@ -261,12 +270,14 @@ fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, cons
             const bool cr = p > 0 && bytes[p - 1] == '\r';
             nl[L] = p | (cr ? kCrBit : 0ull);
         }
-        const unsigned kind = (unsigned)(L & 3);
-        if (L + 1 < n_lines && (kind == 3 || kind == 1)) {
-            // a quality line ends here: the next record must open with '@'; a sequence line: the separator opens with '+'
+        const unsigned kind = (unsigned)L & last_kind;
+        const bool ends_record = kind == last_kind, ends_sequence = fmt.shift == 2 && kind == 1;
+        if (L + 1 < n_lines && (ends_record || ends_sequence)) {
+            // a record's last line ends here: the next record must open with the header character; a FASTQ sequence line:
+            // the separator opens with '+'
             const uint32_t c = p + 1 < n ? bytes[p + 1] : '\n';
-            if (c != (kind == 3 ? '@' : '+'))
-                report_min(status + 1, kind == 3 ? (((L + 1) >> 2) << 8) | FQ_BAD_HEADER : ((L >> 2) << 8) | FQ_BAD_SEPARATOR);
+            if (c != (ends_record ? fmt.header : (uint32_t)'+'))
+                report_min(status + 1, ends_record ? (((L + 1) >> fmt.shift) << 8) | FQ_BAD_HEADER : ((L >> fmt.shift) << 8) | FQ_BAD_SEPARATOR);
         }
         ++L;
     }
@@ -276,13 +287,17 @@ fastq_index_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, cons
 
 __global__ void __launch_bounds__(kThreads)
 fastq_records_kernel(const uint64_t* __restrict__ nl, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
-                     uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow) {
+                     uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow,
+                     unsigned shift) {
     if (*overflow == 0u) return;
     for (unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; r < n_reads; r += (unsigned long long)gridDim.x * kThreads) {
-    const ulonglong2 ab = reinterpret_cast<const ulonglong2*>(nl)[2 * r], cd = reinterpret_cast<const ulonglong2*>(nl)[2 * r + 1];
+    const ulonglong2 ab = reinterpret_cast<const ulonglong2*>(nl)[r << (shift - 1)];
     const unsigned long long s = (ab.x & ~kCrBit) + 1, e = (ab.y & ~kCrBit) - (ab.y >> 63);
-    const unsigned long long qs = (cd.x & ~kCrBit) + 1, qe = (cd.y & ~kCrBit) - (cd.y >> 63);
-    if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
+    if (shift == 2) {   // FASTQ: the quality line is as long as the sequence
+        const ulonglong2 cd = reinterpret_cast<const ulonglong2*>(nl)[2 * r + 1];
+        const unsigned long long qs = (cd.x & ~kCrBit) + 1, qe = (cd.y & ~kCrBit) - (cd.y >> 63);
+        if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
+    }
     seq_off[r] = s;
     seq_len[r] = e - s;
     }
@@ -290,47 +305,54 @@ fastq_records_kernel(const uint64_t* __restrict__ nl, unsigned long long n_reads
 
 // records from the slot rows, a warp per tile: the records whose header line ends in the tile
 constexpr int kFqRecWarps = 8;
+template <unsigned kShift>   // log2(lines per record): compile-time, so the per-record arrays stay in registers
 __global__ void __launch_bounds__(32 * kFqRecWarps)
 fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ line_base, const uint32_t* __restrict__ slots,
                            unsigned long long n_tiles, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
-                           uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow) {
+                           uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow,
+                           TextFormat fmt) {
     if (*overflow != 0u) return;
     const unsigned long long t = (unsigned long long)blockIdx.x * kFqRecWarps + (threadIdx.x >> 5);
     if (t >= n_tiles) return;
     const unsigned lane = threadIdx.x & 31;
+    constexpr unsigned shift = kShift, lpr = 1u << kShift;              // lines per record
     const unsigned long long n_lines = line_base[n_tiles];
     const unsigned long long lb = line_base[t], le = line_base[t + 1];
-    const unsigned long long n_records = (n_lines + 3) >> 2;            // a trailing partial record included (its faults count)
-    unsigned long long ra = (lb + 3) >> 2, rb = (le + 3) >> 2;
+    const unsigned long long n_records = (n_lines + lpr - 1) >> shift;  // a trailing partial record included (its faults count)
+    unsigned long long ra = (lb + lpr - 1) >> shift, rb = (le + lpr - 1) >> shift;
     rb = rb < n_records ? rb : n_records;
-    if (t == 0 && lane == 0 && n_lines && bytes[0] != '@') report_min(status + 1, FQ_BAD_HEADER);
+    if (t == 0 && lane == 0 && n_lines && bytes[0] != fmt.header) report_min(status + 1, FQ_BAD_HEADER);
     for (unsigned long long r = ra + lane; r < rb; r += 32) {
         unsigned long long pos[4] = {0, 0, 0, 0};
         uint32_t ent[4] = {0, 0, 0, 0};
-        if (4 * r + 3 < le) {   // the usual case: all four lines end in this tile -- four neighbouring entries, 32-bit arithmetic
-            const uint32_t* e4 = slots + t * kFqSlots + (unsigned)(4 * r - lb);
+        const unsigned long long l0 = r << shift;                       // the record's header line
+        if (l0 + lpr - 1 < le) {   // the usual case: all its lines end in this tile -- neighbouring entries, 32-bit arithmetic
+            const uint32_t* e4 = slots + t * kFqSlots + (unsigned)(l0 - lb);
             const unsigned long long base = t * kFqTile;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < (int)lpr; ++k) {
                 ent[k] = e4[k];
                 pos[k] = base + (ent[k] & kSlotPos);
             }
         } else {
             unsigned long long tt = t;
-            for (int k = 0; k < 4; ++k) {
-                const unsigned long long L = 4 * r + k;
+#pragma unroll
+            for (int k = 0; k < (int)lpr; ++k) {
+                const unsigned long long L = l0 + k;
                 if (L >= n_lines) break;
                 while (L >= line_base[tt + 1]) ++tt;                      // a line that ends in a later tile
                 ent[k] = slots[tt * kFqSlots + (L - line_base[tt])];
                 pos[k] = tt * kFqTile + (ent[k] & kSlotPos);
             }
         }
-        if (4 * r + 2 < n_lines && !(ent[1] & kSlotPlus)) report_min(status + 1, (r << 8) | FQ_BAD_SEPARATOR);
-        if (4 * r + 4 < n_lines && !(ent[3] & kSlotAt)) report_min(status + 1, ((r + 1) << 8) | FQ_BAD_HEADER);
+        if (shift == 2 && l0 + 2 < n_lines && !(ent[1] & kSlotPlus)) report_min(status + 1, (r << 8) | FQ_BAD_SEPARATOR);
+        if (l0 + lpr < n_lines && !(ent[lpr - 1] & kSlotAt)) report_min(status + 1, ((r + 1) << 8) | FQ_BAD_HEADER);
         if (r < n_reads) {
             const unsigned long long s = pos[0] + 1, e = pos[1] - ((ent[1] & kSlotCr) ? 1 : 0);
-            const unsigned long long qs = pos[2] + 1, qe = pos[3] - ((ent[3] & kSlotCr) ? 1 : 0);
-            if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
+            if (shift == 2) {   // FASTQ: the quality line is as long as the sequence
+                const unsigned long long qs = pos[2] + 1, qe = pos[3] - ((ent[3] & kSlotCr) ? 1 : 0);
+                if (qe - qs != e - s) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
+            }
             seq_off[r] = s;
             seq_len[r] = e - s;
         }
@@ -507,7 +529,7 @@ __global__ void __launch_bounds__(kBThreads, kMinCtas)
 fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ line_base,
                     unsigned long long n_tiles1, unsigned long long n_reads, const uint64_t* __restrict__ seq_off,
                     const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off, uint64_t* __restrict__ out,
-                    unsigned long long* __restrict__ status) {
+                    unsigned long long* __restrict__ status, unsigned shift) {
     constexpr int kMainVecs = kTile / 16;
     constexpr int kOver = 3;                                  // a word that starts in the tile ends at most 47 bytes past it
     constexpr int kRatio = kTile / kFqTile;
@@ -526,7 +548,8 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
     // reads whose header line ends in this tile (so their sequence starts in it, or on the first byte after it)
     const unsigned long long t1a = (unsigned long long)blockIdx.x * kRatio;
     const unsigned long long t1b = t1a + kRatio < n_tiles1 ? t1a + kRatio : n_tiles1;
-    unsigned long long ra = (line_base[t1a] + 3) >> 2, rb = (line_base[t1b] + 3) >> 2;
+    const unsigned long long round_up = (1ull << shift) - 1ull;   // records whose header line ends in the tile
+    unsigned long long ra = (line_base[t1a] + round_up) >> shift, rb = (line_base[t1b] + round_up) >> shift;
     ra = ra < n_reads ? ra : n_reads;
     rb = rb < n_reads ? rb : n_reads;
     if (ra >= rb) return;   // nothing starts here (e.g. the inside of a long read): the tile is not even loaded
@@ -666,7 +689,8 @@ struct FqScratch {
 };
 
 cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
-                               cudaStream_t s) {
+                               int fasta, cudaStream_t s) {
+    const TextFormat fmt = text_format(fasta);
     if (n_bytes == 0) return cudaMemsetAsync(d_n_lines, 0, sizeof(uint64_t), s);
     const FqScratch sc(d_scratch, n_bytes);
     cudaError_t e = cudaMemsetAsync(sc.overflow, 0, 16, s);
@@ -674,7 +698,7 @@ cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t
     // one tile per CTA: a resident grid striding over the tiles was measured at 1x and 2x the resident CTA count and is
     // 10-15 % slower (as for the codec kernels: the two dies finish at different times)
     const unsigned lines_grid = (unsigned)sc.n_tiles;
-    fastq_lines_kernel<<<lines_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles);
+    fastq_lines_kernel<<<lines_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles, fmt.header);
     launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -683,7 +707,8 @@ cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t
 
 cudaError_t launch_fastq_index(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
                                void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets,
-                               unsigned long long* d_status, cudaStream_t s) {
+                               unsigned long long* d_status, int fasta, cudaStream_t s) {
+    const TextFormat fmt = text_format(fasta);
     cudaError_t e = cudaMemsetAsync(d_status, 0xFF, 2 * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
     if (n_bytes == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
@@ -691,23 +716,28 @@ cudaError_t launch_fastq_index(const DeviceInfo&, const uint8_t* d_bytes, size_t
     uint64_t* nl = static_cast<uint64_t*>(d_index_scratch);
     // both forms are enqueued; the overflow flag left by the count pass lets exactly one of them work.  They run even
     // without a whole record: the faults of a partial one are found here.
-    fastq_records_slots_kernel<<<(unsigned)ceil_div(sc.n_tiles, kFqRecWarps), 32 * kFqRecWarps, 0, s>>>(
-        d_bytes, sc.line_base, sc.slots, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow);
+    if (fasta)
+        fastq_records_slots_kernel<1><<<(unsigned)ceil_div(sc.n_tiles, kFqRecWarps), 32 * kFqRecWarps, 0, s>>>(
+            d_bytes, sc.line_base, sc.slots, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow, fmt);
+    else
+        fastq_records_slots_kernel<2><<<(unsigned)ceil_div(sc.n_tiles, kFqRecWarps), 32 * kFqRecWarps, 0, s>>>(
+            d_bytes, sc.line_base, sc.slots, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_status, sc.overflow, fmt);
     const unsigned long long dense_grid = sc.n_tiles < 148ull * 8 ? sc.n_tiles : 148ull * 8;
-    fastq_index_kernel<<<(unsigned)dense_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status, sc.overflow, sc.n_tiles);
+    fastq_index_kernel<<<(unsigned)dense_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_reads, nl, d_status, sc.overflow, sc.n_tiles, fmt);
     if (n_reads == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
     unsigned long long* sums2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(d_index_scratch) + align16(n_reads * 32));
     const unsigned long long rec_blocks = ceil_div(n_reads, kThreads);
     fastq_records_kernel<<<(unsigned)(rec_blocks < 148ull * 8 ? rec_blocks : 148ull * 8), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens,
-                                                                                                      d_status, sc.overflow);
+                                                                                                      d_status, sc.overflow, fmt.shift);
     launch_exclusive_scan(WordsOfLen{d_seq_lens}, n_reads, sums2, d_word_offsets, s);
     return cudaGetLastError();
 }
 
 cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
                                 const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets,
-                                uint64_t* d_out_words, unsigned long long* d_status, cudaStream_t s) {
+                                uint64_t* d_out_words, unsigned long long* d_status, int fasta, cudaStream_t s) {
     if (n_reads == 0 || n_bytes == 0) return cudaSuccess;
+    const TextFormat fmt = text_format(fasta);
     const FqScratch sc(d_scratch, n_bytes);
     // tile / CTA shape: BN_FQ_VARIANT picks one of the measured shapes (profiles/r01_sweep_fastq.txt).  By default the
     // average record size decides how a read's two partial end vectors are validated: from per-vector maps kept in shared
@@ -720,7 +750,7 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
     const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 11 : 13);
 #define BN_FQ_LAUNCH(TILE, THREADS, CTAS, ...)                                                                                         \
     fastq_encode_kernel<TILE, THREADS, CTAS, ##__VA_ARGS__><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \
-        d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status)
+        d_bytes, n_bytes, sc.line_base, sc.n_tiles, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status, fmt.shift)
     switch (variant) {
     case 1: BN_FQ_LAUNCH(65536, 256, 4); break;
     case 2: BN_FQ_LAUNCH(32768, 128, 8); break;

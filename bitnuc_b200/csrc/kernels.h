@@ -74,14 +74,15 @@ cudaError_t launch_kmer_windows_batch(const DeviceInfo& di, const uint8_t* d_byt
 // fastq.cu
 size_t fastq_scratch_bytes(size_t n_bytes);
 size_t fastq_index_scratch_bytes(size_t n_reads);
+// fasta = 0: FASTQ (four lines per record, '@'); 1: FASTA with one sequence line per record (two lines, '>')
 cudaError_t launch_fastq_count(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines,
-                               cudaStream_t s);
+                               int fasta, cudaStream_t s);
 cudaError_t launch_fastq_index(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
                                void* d_index_scratch, uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets,
-                               unsigned long long* d_status, cudaStream_t s);
+                               unsigned long long* d_status, int fasta, cudaStream_t s);
 cudaError_t launch_fastq_encode(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
                                 const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets,
-                                uint64_t* d_out_words, unsigned long long* d_status, cudaStream_t s);
+                                uint64_t* d_out_words, unsigned long long* d_status, int fasta, cudaStream_t s);
 
 // synth.cu
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,

@@ -192,12 +192,13 @@ class FastqStatus:
     def __init__(self, device):
         self.word = torch.empty(2, dtype=torch.int64, device=device)
         self.ctx = api.default_context(torch.device(device).index or 0)
-        self.n_lines, self.seq_offsets, self.n_reads = 0, None, 0
+        self.n_lines, self.seq_offsets, self.n_reads, self.fasta = 0, None, 0, False
 
     def check(self):
         """Synchronises the current stream; raises ``FastqError`` first, else ``NucleotideError.InvalidBase``."""
         err = BnError()
-        rc = self.ctx.lib.bn_fastq_status_fetch(self.ctx.handle, _stream(), _ptr(self.word), self.n_lines, _ptr(self.seq_offsets),
+        fetch = self.ctx.lib.bn_fasta_status_fetch if self.fasta else self.ctx.lib.bn_fastq_status_fetch
+        rc = fetch(self.ctx.handle, _stream(), _ptr(self.word), self.n_lines, _ptr(self.seq_offsets),
                                                 self.n_reads, C.byref(err))
         if rc == 1:
             e = _lib.NucleotideError.InvalidBase(err.base)
@@ -206,7 +207,12 @@ class FastqStatus:
         raise_for(rc, err)
 
 
-def fastq_encode(text: torch.Tensor, status: FastqStatus | None = None):
+def fasta_encode(text: torch.Tensor, status: FastqStatus | None = None):
+    """One-sequence-line FASTA text resident in HBM -> the same outputs as ``fastq_encode``."""
+    return fastq_encode(text, status, _fasta=True)
+
+
+def fastq_encode(text: torch.Tensor, status: FastqStatus | None = None, _fasta: bool = False):
     """FASTQ text resident in HBM -> (words, word_offsets, seq_offsets, seq_lens, status), all on the device.  Two small
     read-backs size the outputs (number of lines, number of words); ``status.check()`` reports faults."""
     ctx = _ctx_for(text)
@@ -214,20 +220,23 @@ def fastq_encode(text: torch.Tensor, status: FastqStatus | None = None):
     status = status or FastqStatus(dev)
     scratch = torch.empty(max(16, ctx.lib.bn_fastq_scratch_bytes(n_bytes)), dtype=torch.uint8, device=dev)
     n_lines_t = torch.zeros(1, dtype=torch.int64, device=dev)
-    raise_for(ctx.lib.bn_fastq_count_dev(ctx.handle, _stream(), _ptr(text), n_bytes, _ptr(scratch), _ptr(n_lines_t)))
+    L = ctx.lib
+    count, index, encode_ = (L.bn_fasta_count_dev, L.bn_fasta_index_dev, L.bn_fasta_encode_dev) if _fasta else \
+        (L.bn_fastq_count_dev, L.bn_fastq_index_dev, L.bn_fastq_encode_dev)
+    raise_for(count(ctx.handle, _stream(), _ptr(text), n_bytes, _ptr(scratch), _ptr(n_lines_t)))
     n_lines = int(n_lines_t.item())
-    n = n_lines // 4
+    n = n_lines // (2 if _fasta else 4)
     iscratch = torch.empty(max(16, ctx.lib.bn_fastq_index_scratch_bytes(n)), dtype=torch.uint8, device=dev)
     so = torch.empty(max(1, n), dtype=torch.int64, device=dev)
     sl = torch.empty(max(1, n), dtype=torch.int64, device=dev)
     wo = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    raise_for(ctx.lib.bn_fastq_index_dev(ctx.handle, _stream(), _ptr(text), n_bytes, n, _ptr(scratch), _ptr(iscratch), _ptr(so), _ptr(sl),
+    raise_for(index(ctx.handle, _stream(), _ptr(text), n_bytes, n, _ptr(scratch), _ptr(iscratch), _ptr(so), _ptr(sl),
                                          _ptr(wo), _ptr(status.word)))
     n_words = int(wo[n].item())
     words = torch.empty(max(1, n_words), dtype=torch.int64, device=dev)
-    raise_for(ctx.lib.bn_fastq_encode_dev(ctx.handle, _stream(), _ptr(text), n_bytes, n, _ptr(scratch), _ptr(so), _ptr(sl), _ptr(wo),
+    raise_for(encode_(ctx.handle, _stream(), _ptr(text), n_bytes, n, _ptr(scratch), _ptr(so), _ptr(sl), _ptr(wo),
                                           _ptr(words), _ptr(status.word)))
-    status.n_lines, status.seq_offsets, status.n_reads = n_lines, so, n
+    status.n_lines, status.seq_offsets, status.n_reads, status.fasta = n_lines, so, n, _fasta
     return words[:n_words], wo, so[:n], sl[:n], status
 
 

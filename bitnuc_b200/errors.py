@@ -80,14 +80,14 @@ class BitnucCudaError(RuntimeError):
 
 
 class FastqError(ValueError):
-    """Malformed FASTQ text (``BN_ERR_FASTQ``): ``record`` is the first faulty record in file order, ``fault`` is
+    """Malformed FASTQ / FASTA text (``BN_ERR_FASTQ``): ``record`` is the first faulty record in file order, ``fault`` is
     1 header without '@', 2 separator without '+', 3 quality and sequence lengths differ, 4 text ends inside the record."""
 
-    FAULTS = {1: "header line does not start with '@'", 2: "separator line does not start with '+'",
+    FAULTS = {1: "header line does not start with '@' (FASTA: '>')", 2: "separator line does not start with '+'",
               3: "quality and sequence lengths differ", 4: "text ends inside the record"}
 
     def __init__(self, record: int, fault: int):
-        super().__init__(f"FASTQ record {record}: {self.FAULTS.get(fault, 'malformed record')}")
+        super().__init__(f"record {record}: {self.FAULTS.get(fault, 'malformed record')}")
         self.record, self.fault = int(record), int(fault)
 
     def key(self):

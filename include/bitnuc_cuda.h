@@ -50,11 +50,11 @@ typedef enum bn_status {
     BN_ERR_EMPTY_ENCODE = -3,   /* encode of an empty sequence: the reference panics
                                    (src/utils/packing/avx.rs:138); bindings should panic too */
     BN_ERR_NOMEM = -4,
-    BN_ERR_FASTQ = -5           /* malformed FASTQ text (bn_fastq_*): err->record = the record, err->a = bn_fastq_fault */
+    BN_ERR_FASTQ = -5           /* malformed FASTQ / FASTA text (bn_fastq_*, bn_fasta_*): err->record = the record, err->a = bn_fastq_fault */
 } bn_status;
 
 typedef enum bn_fastq_fault {
-    BN_FASTQ_BAD_HEADER = 1,          /* line 4r does not start with '@' */
+    BN_FASTQ_BAD_HEADER = 1,          /* the record's first line does not start with '@' (FASTA: '>') */
     BN_FASTQ_BAD_SEPARATOR = 2,       /* line 4r+2 does not start with '+' */
     BN_FASTQ_BAD_QUALITY_LENGTH = 3,  /* line 4r+3 is not as long as the sequence */
     BN_FASTQ_TRUNCATED = 4            /* the text ends inside record r */
@@ -212,6 +212,11 @@ int bn_get_batch(bn_ctx *ctx, const uint64_t *words, size_t n_words, const uint6
  * err->b = its position inside the read, err->offset = its offset in the text). */
 int bn_fastq_scan(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t *n_reads, size_t *n_words, bn_error_t *err);
 int bn_fastq_encode(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t *out_words, uint64_t *out_word_offsets, uint64_t *seq_offsets, uint64_t *seq_lens, bn_error_t *err);
+/* The same for FASTA text with ONE sequence line per record (the form read processors emit: '>' header line, sequence
+ * line): two-line records, same outputs, same errors (BN_FASTQ_BAD_HEADER / BN_FASTQ_TRUNCATED are the faults that can
+ * occur).  A sequence wrapped over several lines is not this format: its second line is reported as a bad header. */
+int bn_fasta_scan(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t *n_reads, size_t *n_words, bn_error_t *err);
+int bn_fasta_encode(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t *out_words, uint64_t *out_word_offsets, uint64_t *seq_offsets, uint64_t *seq_lens, bn_error_t *err);
 
 /* ------------------------------------------------------------------ device-pointer calls ---- */
 /* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.
@@ -276,6 +281,11 @@ int bn_fastq_count_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t 
 int bn_fastq_index_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, void *d_index_scratch, uint64_t *d_seq_offsets, uint64_t *d_seq_lens, uint64_t *d_word_offsets, uint64_t *d_status);
 int bn_fastq_encode_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, const uint64_t *d_seq_offsets, const uint64_t *d_seq_lens, const uint64_t *d_word_offsets, uint64_t *d_out_words, uint64_t *d_status);
 int bn_fastq_status_fetch(bn_ctx *ctx, void *stream, const uint64_t *d_status, uint64_t n_lines, const uint64_t *d_seq_offsets, size_t n_reads, bn_error_t *err);
+/* One-sequence-line FASTA on the device: the same three steps (same scratch sizes), n_reads = n_lines / 2. */
+int bn_fasta_count_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, void *d_scratch, uint64_t *d_n_lines);
+int bn_fasta_index_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, void *d_index_scratch, uint64_t *d_seq_offsets, uint64_t *d_seq_lens, uint64_t *d_word_offsets, uint64_t *d_status);
+int bn_fasta_encode_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, const uint64_t *d_seq_offsets, const uint64_t *d_seq_lens, const uint64_t *d_word_offsets, uint64_t *d_out_words, uint64_t *d_status);
+int bn_fasta_status_fetch(bn_ctx *ctx, void *stream, const uint64_t *d_status, uint64_t n_lines, const uint64_t *d_seq_offsets, size_t n_reads, bn_error_t *err);
 
 /* d_out needs n - k + 1 words; any alignment of d_seq. */
 int bn_kmers_dev(bn_ctx *ctx, void *stream, const uint8_t *d_seq, size_t n, uint32_t k, uint64_t *d_out, uint64_t *d_status);

@@ -89,6 +89,7 @@ def lib():
             "orc_gc_content": (C.c_double, [C.c_void_p, sz]),
             "orc_split_packed": (C.c_int, [C.c_void_p, sz, sz, sz, C.c_void_p, szp, C.c_void_p, szp, ep]),
             "orc_fastq_scan": (C.c_int, [C.c_void_p, sz, C.c_void_p, C.c_void_p, sz, szp, u64p, C.POINTER(C.c_int)]),
+            "orc_fasta_scan": (C.c_int, [C.c_void_p, sz, C.c_void_p, C.c_void_p, sz, szp, u64p, C.POINTER(C.c_int)]),
             "orc_splitmix64": (u64, [u64]),
             "orc_synth_word": (u64, [u64, u64, u64]),
             "orc_synth_ascii": (None, [u64, u64, u64, sz, C.c_void_p]),
@@ -303,23 +304,28 @@ class FastqFault(Exception):
         self.record, self.fault = record, fault
 
 
-def fastq_scan(text):
-    """(starts, lens) of every sequence line of a FASTQ text, or FastqFault (orc_fastq_scan)."""
+def fastq_scan(text, fasta: bool = False):
+    """(starts, lens) of every sequence line of a FASTQ text (or a one-sequence-line FASTA text), or FastqFault."""
     t = _bytes_arr(text)
-    cap = t.size // 4 + 1
+    cap = t.size // 2 + 1
     starts, lens = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
     n_reads, bad, fault = C.c_size_t(0), C.c_uint64(0), C.c_int(0)
-    rc = lib().orc_fastq_scan(_ptr(t), t.size, _ptr(starts), _ptr(lens), cap, C.byref(n_reads), C.byref(bad), C.byref(fault))
+    scan = lib().orc_fasta_scan if fasta else lib().orc_fastq_scan
+    rc = scan(_ptr(t), t.size, _ptr(starts), _ptr(lens), cap, C.byref(n_reads), C.byref(bad), C.byref(fault))
     if rc != 0:
         raise FastqFault(bad.value, fault.value)
     return starts[: n_reads.value].copy(), lens[: n_reads.value].copy()
 
 
-def fastq_encode(text):
+def fasta_scan(text):
+    return fastq_scan(text, fasta=True)
+
+
+def fastq_encode(text, fasta: bool = False):
     """The caller's loop of README.md:160-180 over a FASTQ text: (words, word_offsets, starts, lens); every read is
     PackedSequence::new(record.seq()) on fresh words.  FastqFault first, then the first InvalidBase in file order."""
     t = _bytes_arr(text)
-    starts, lens = fastq_scan(t)
+    starts, lens = fastq_scan(t, fasta)
     words, offs = [], [0]
     for s, l in zip(starts.tolist(), lens.tolist()):
         if l:

@@ -336,6 +336,40 @@ int orc_fastq_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *le
     return 0;
 }
 
+/* FASTA with one sequence line per record: the same walk, two lines per record. */
+int orc_fasta_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *lens, size_t cap, size_t *n_reads,
+                   uint64_t *bad_record, int *fault) {
+    size_t pos = 0, r = 0;
+    *n_reads = 0;
+    while (pos < n) {
+        size_t ls[2], ll[2];
+        int have = 0;
+        for (int k = 0; k < 2 && pos < n; ++k) {
+            size_t e = pos;
+            while (e < n && text[e] != '\n') ++e;
+            size_t len = e - pos;
+            if (len && text[e - 1] == '\r') --len;
+            ls[k] = pos;
+            ll[k] = len;
+            pos = e < n ? e + 1 : n;
+            have = k + 1;
+        }
+        const int f = text[ls[0]] != '>' ? 1 : (have < 2 ? 4 : 0);
+        if (f) {
+            *bad_record = r;
+            *fault = f;
+            return -5;
+        }
+        if (r < cap) {
+            starts[r] = ls[1];
+            lens[r] = ll[1];
+        }
+        ++r;
+        *n_reads = r;
+    }
+    return 0;
+}
+
 uint64_t orc_splitmix64(uint64_t x) {
     uint64_t z = x + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -94,6 +94,11 @@ int orc_split_packed(const uint64_t *ebuf, size_t n_words, size_t slen, size_t i
 int orc_fastq_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *lens, size_t cap, size_t *n_reads,
                    uint64_t *bad_record, int *fault);
 
+/* The same for FASTA text with one sequence line per record ('>' header line, sequence line): faults 1 (header) and 4
+ * (text ends inside the record).  A sequence wrapped over several lines is not this format. */
+int orc_fasta_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *lens, size_t cap, size_t *n_reads,
+                   uint64_t *bad_record, int *fault);
+
 /* ---- synthetic input: counter-based splitmix64 stream --------------------- */
 uint64_t orc_splitmix64(uint64_t x);
 uint64_t orc_synth_word(uint64_t seed, uint64_t stream, uint64_t j);

@@ -137,10 +137,16 @@ def synth_ascii(seed: int, stream: int, n_bases: int) -> np.ndarray:
     return decode(w, n_bases)
 
 
-def fastq_scan(text: bytes):
+def fasta_scan(text: bytes):
+    """Independent restatement of orc_fasta_scan (one sequence line per record)."""
+    return fastq_scan(text, lines_per_record=2)
+
+
+def fastq_scan(text: bytes, lines_per_record: int = 4):
     """Independent restatement of orc_fastq_scan with Python's own line splitting: [(start, length)] of the sequence
     lines, or ("fault", record, kind)."""
     text = bytes(text)
+    lpr, hdr = lines_per_record, (b"@" if lines_per_record == 4 else b">")
     lines, pos = [], 0
     while pos < len(text):
         e = text.find(b"\n", pos)
@@ -152,15 +158,15 @@ def fastq_scan(text: bytes):
         lines.append((pos, ln))
         pos = e + 1
     out = []
-    for r in range((len(lines) + 3) // 4):
-        rec = lines[4 * r : 4 * r + 4]
-        if text[rec[0][0] : rec[0][0] + 1] != b"@":
+    for r in range((len(lines) + lpr - 1) // lpr):
+        rec = lines[lpr * r : lpr * r + lpr]
+        if text[rec[0][0] : rec[0][0] + 1] != hdr:
             return ("fault", r, 1)
-        if len(rec) >= 3 and text[rec[2][0] : rec[2][0] + 1] != b"+":
+        if lpr == 4 and len(rec) >= 3 and text[rec[2][0] : rec[2][0] + 1] != b"+":
             return ("fault", r, 2)
-        if len(rec) == 4 and rec[3][1] != rec[1][1]:
+        if lpr == 4 and len(rec) == 4 and rec[3][1] != rec[1][1]:
             return ("fault", r, 3)
-        if len(rec) < 4:
+        if len(rec) < lpr:
             return ("fault", r, 4)
         out.append(rec[1])
     return out

@@ -31,7 +31,20 @@ CASES = [
     ("earlier_record_wins", "@a\nAC\n+\nI\n@b\nAC\n-\nII\n", {"fault": [0, 3]}),
 ]
 
+FASTA_CASES = [   # one sequence line per record
+    ("fa_one_record", ">r\nACGT\n", {"reads": [[3, 4]]}),
+    ("fa_no_final_newline", ">r desc\nACGT", {"reads": [[8, 4]]}),
+    ("fa_crlf_and_empty", ">a\r\nACG\r\n>b\r\n\r\n>c\r\nT\r\n", {"reads": [[4, 3], [13, 0], [19, 1]]}),
+    ("fa_lower_case_and_n", ">a\nacgtn\n", {"reads": [[3, 5]]}),
+    ("fa_empty_text", "", {"reads": []}),
+    ("fa_bad_header", "r\nACGT\n", {"fault": [0, 1]}),
+    ("fa_wrapped_sequence_is_not_this_format", ">a\nACGT\nACGT\n>b\nAC\n", {"fault": [1, 1]}),
+    ("fa_truncated", ">a\nAC\n>b\n", {"fault": [1, 4]}),
+    ("fa_header_only", ">a", {"fault": [0, 4]}),
+    ("fa_fastq_is_not_fasta", "@a\nAC\n+\nII\n", {"fault": [0, 1]}),
+]
+
 if __name__ == "__main__":
-    out = [{"name": n, "text": t, **e} for n, t, e in CASES]
+    out = [{"name": n, "text": t, **e} for n, t, e in CASES] + [{"name": n, "text": t, "fasta": True, **e} for n, t, e in FASTA_CASES]
     Path(__file__).with_name("fastq_cases.json").write_text(json.dumps(out, indent=1) + "\n")
     print(len(out), "cases")

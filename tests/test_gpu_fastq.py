@@ -29,10 +29,10 @@ def dv():
     return device
 
 
-def expected(text: bytes):
+def expected(text: bytes, fasta: bool = False):
     """('ok', words, wo, so, sl) | ('fault', record, kind) | ('base', byte, record, position, offset)"""
     try:
-        starts, lens = oracle.fastq_scan(text)
+        starts, lens = oracle.fastq_scan(text, fasta)
     except oracle.FastqFault as e:
         return ("fault", e.record, e.fault)
     t = np.frombuffer(text, dtype=np.uint8)
@@ -51,9 +51,9 @@ def expected(text: bytes):
     return ("ok", w, np.asarray(offs, dtype=np.uint64), starts, lens)
 
 
-def run_host(bn, text: bytes):
+def run_host(bn, text: bytes, fasta: bool = False):
     try:
-        w, wo, so, sl = bn.fastq_encode(np.frombuffer(text, dtype=np.uint8))
+        w, wo, so, sl = (bn.fasta_encode if fasta else bn.fastq_encode)(np.frombuffer(text, dtype=np.uint8))
     except bn.FastqError as e:
         return ("fault", e.record, e.fault)
     except bn.NucleotideError as e:
@@ -62,10 +62,10 @@ def run_host(bn, text: bytes):
     return ("ok", w, wo, so, sl)
 
 
-def run_dev(dv, bn, text: bytes):
+def run_dev(dv, bn, text: bytes, fasta: bool = False):
     import torch
     t = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).cuda() if text else torch.empty(0, dtype=torch.uint8, device="cuda")
-    w, wo, so, sl, st = dv.fastq_encode(t)
+    w, wo, so, sl, st = (dv.fasta_encode if fasta else dv.fastq_encode)(t)
     try:
         st.check()
     except bn.FastqError as e:
@@ -84,9 +84,9 @@ def same(a, b):
     return all(np.array_equal(np.asarray(x, dtype=np.uint64), np.asarray(y, dtype=np.uint64)) for x, y in zip(a[1:], b[1:]))
 
 
-def check(bn, dv, text: bytes):
-    exp = expected(text)
-    got_h, got_d = run_host(bn, text), run_dev(dv, bn, text)
+def check(bn, dv, text: bytes, fasta: bool = False):
+    exp = expected(text, fasta)
+    got_h, got_d = run_host(bn, text, fasta), run_dev(dv, bn, text, fasta)
     assert same(got_h, exp), (got_h[:1], exp[:1], got_h[1:] if got_h[0] != "ok" else "", exp[1:] if exp[0] != "ok" else "")
     assert same(got_d, exp), (got_d[:1], exp[:1], got_d[1:] if got_d[0] != "ok" else "", exp[1:] if exp[0] != "ok" else "")
     return exp
@@ -94,7 +94,7 @@ def check(bn, dv, text: bytes):
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_golden_cases(bn, dv, case):
-    exp = check(bn, dv, case["text"].encode())
+    exp = check(bn, dv, case["text"].encode(), case.get("fasta", False))
     if "fault" in case:
         assert exp == ("fault", *case["fault"])
     elif exp[0] == "ok":
@@ -326,3 +326,59 @@ def test_mutated_texts_fuzz(bn, dv, seed):
                     text[e + 1 : e + 1] = text[text.rfind(b"\n", 0, i) + 1 : e + 1]
         outcomes.add(check(bn, dv, bytes(text))[0])
     assert outcomes   # usually all three of ok / fault / base
+
+
+# ---- FASTA with one sequence line per record: the same kernels with two-line records -------------------------------
+
+@pytest.mark.parametrize("kind", ["short", "tiny", "long", "mixed"])
+@pytest.mark.parametrize("crlf", [False, True])
+def test_fasta_random_texts(bn, dv, kind, crlf):
+    rng = np.random.default_rng(len(kind) + 3 * crlf)
+    n = int(rng.integers(1, 800))
+    lens = {"short": rng.integers(100, 152, n), "tiny": rng.integers(0, 6, 8 * n), "long": rng.integers(1500, 40000, min(n, 30)),
+            "mixed": (rng.pareto(1.1, n) * 60).astype(np.int64) % 90_000}[kind]
+    text = make_fastq(rng, lens, crlf=crlf, final_newline=bool(rng.integers(0, 2)), alphabet=b"ACGTacgt", fasta=True)
+    exp = check(bn, dv, text, fasta=True)
+    assert exp[0] == "ok" and [int(x) for x in exp[4]] == [int(x) for x in lens]
+
+
+def test_fasta_faults_and_invalid_bases(bn, dv):
+    rng = np.random.default_rng(12)
+    lens = rng.integers(50, 3000, 400)
+    text = bytearray(make_fastq(rng, lens, alphabet=b"ACGT", fasta=True))
+    starts, _ = oracle.fastq_scan(bytes(text), fasta=True)
+    bad = bytearray(text)
+    bad[int(starts[300]) + 17] = ord("N")
+    bad[int(starts[120]) + int(lens[120]) - 1] = ord("n")
+    assert check(bn, dv, bytes(bad), fasta=True) == ("base", ord("n"), 120, int(lens[120]) - 1, int(starts[120]) + int(lens[120]) - 1)
+    wrapped = bytearray(text)
+    wrapped[int(starts[200]) + 20] = 10                    # a sequence broken over two lines: the next "record" has no '>'
+    assert check(bn, dv, bytes(wrapped), fasta=True) == ("fault", 201, 1)
+    assert check(bn, dv, bytes(text[: int(starts[399])]), fasta=True) == ("fault", 399, 4)
+    assert check(bn, dv, bytes(text), fasta=False)[0] == "fault"      # FASTA is not FASTQ
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fasta_mutated_texts_fuzz(bn, dv, seed):
+    rng = np.random.default_rng(900 + seed)
+    for _ in range(25):
+        lens = [rng.integers(0, 40, int(rng.integers(1, 60))), rng.integers(100, 152, int(rng.integers(1, 400))),
+                rng.integers(1, 30000, int(rng.integers(1, 12)))][int(rng.integers(0, 3))]
+        text = bytearray(make_fastq(rng, lens, crlf=bool(rng.integers(0, 2)), final_newline=bool(rng.integers(0, 2)), alphabet=b"ACGTacgt",
+                                    fasta=True))
+        for _ in range(int(rng.integers(0, 3))):
+            if not text:
+                break
+            i = int(rng.integers(0, len(text)))
+            k = int(rng.integers(0, 5))
+            if k == 0:
+                text[i] = 10
+            elif k == 1:
+                text[i] = ord(">")
+            elif k == 2:
+                text[i] = int(rng.integers(0, 256))
+            elif k == 3:
+                del text[i]
+            else:
+                del text[i:]
+        check(bn, dv, bytes(text), fasta=True)

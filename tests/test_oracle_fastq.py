@@ -12,13 +12,13 @@ from oracle import oracle_np as onp
 CASES = json.loads((Path(__file__).parent / "golden" / "fastq_cases.json").read_text())
 
 
-def both(text: bytes):
+def both(text: bytes, fasta: bool = False):
     try:
-        s, l = oracle.fastq_scan(text)
+        s, l = oracle.fastq_scan(text, fasta)
         a = [[int(x), int(y)] for x, y in zip(s, l)]
     except oracle.FastqFault as e:
         a = ("fault", e.record, e.fault)
-    b = onp.fastq_scan(text)
+    b = onp.fasta_scan(text) if fasta else onp.fastq_scan(text)
     if not isinstance(b, tuple):
         b = [[int(x), int(y)] for x, y in b]
     return a, b
@@ -26,34 +26,35 @@ def both(text: bytes):
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_golden_cases(case):
-    a, b = both(case["text"].encode())
+    a, b = both(case["text"].encode(), case.get("fasta", False))
     exp = ("fault", *case["fault"]) if "fault" in case else case["reads"]
     assert a == exp
     assert b == exp
 
 
-def make_fastq(rng, lens, crlf=False, final_newline=True, alphabet=b"ACGT"):
+def make_fastq(rng, lens, crlf=False, final_newline=True, alphabet=b"ACGT", fasta=False):
     eol = b"\r\n" if crlf else b"\n"
     al = np.frombuffer(alphabet, dtype=np.uint8)
     parts = []
     for r, n in enumerate(lens):
-        name = b"@r%d" % r + b" x" * int(rng.integers(0, 4))
+        name = (b">r%d" if fasta else b"@r%d") % r + b" x" * int(rng.integers(0, 4))
         seq = al[rng.integers(0, al.size, int(n))].tobytes()
         qual = bytes(rng.integers(33, 74, int(n)).astype(np.uint8))
-        parts += [name, eol, seq, eol, b"+", eol, qual, eol]
+        parts += [name, eol, seq, eol] if fasta else [name, eol, seq, eol, b"+", eol, qual, eol]
     text = b"".join(parts)
     if not final_newline and text and int(lens[-1]) > 0:   # an empty last quality line needs its newline to exist at all
         text = text[: -len(eol)]
     return text
 
 
+@pytest.mark.parametrize("fasta", [False, True])
 @pytest.mark.parametrize("seed", range(6))
-def test_restatements_agree_on_random_and_mutated_texts(seed):
+def test_restatements_agree_on_random_and_mutated_texts(seed, fasta):
     rng = np.random.default_rng(seed)
     for _ in range(60):
         lens = rng.integers(0, 90, int(rng.integers(0, 12)))
-        text = bytearray(make_fastq(rng, lens, crlf=bool(rng.integers(0, 2)), final_newline=bool(rng.integers(0, 2))))
-        a, b = both(bytes(text))
+        text = bytearray(make_fastq(rng, lens, crlf=bool(rng.integers(0, 2)), final_newline=bool(rng.integers(0, 2)), fasta=fasta))
+        a, b = both(bytes(text), fasta)
         assert a == b and not isinstance(a, tuple)
         assert [x[1] for x in a] == [int(n) for n in lens]
         for _ in range(4):   # mutations: flip a byte to a newline / '@' / '+' / delete a byte / cut the text
@@ -72,7 +73,7 @@ def test_restatements_agree_on_random_and_mutated_texts(seed):
                 t = t[:i]
             else:
                 t[i] = ord("x")
-            a, b = both(bytes(t))
+            a, b = both(bytes(t), fasta)
             assert a == b
 
 

@@ -202,11 +202,11 @@ struct FastqBatch {
     std::vector<uint64_t> seq_offsets, seq_lens; // where each sequence line sits in the text
     size_t size() const { return seq_lens.size(); }
 };
-inline FastqBatch fastq_encode(Bytes text) {
+inline FastqBatch fastq_encode(Bytes text, bool fasta = false) {   // fasta: '>' header line + ONE sequence line per record
     FastqBatch out;
     size_t n_reads = 0, n_words = 0;
     bn_error_t e{};
-    int rc = bn_fastq_scan(detail::ctx(), text.ptr, text.len, &n_reads, &n_words, &e);
+    int rc = (fasta ? bn_fasta_scan : bn_fastq_scan)(detail::ctx(), text.ptr, text.len, &n_reads, &n_words, &e);
     if (rc == BN_ERR_FASTQ) {
         char buf[160];
         bn_error_string(&e, buf, sizeof buf);
@@ -217,10 +217,11 @@ inline FastqBatch fastq_encode(Bytes text) {
     out.word_offsets.resize(n_reads + 1);
     out.seq_offsets.resize(n_reads);
     out.seq_lens.resize(n_reads);
-    detail::check(bn_fastq_encode(detail::ctx(), text.ptr, text.len, n_reads, n_words, out.words.data(), out.word_offsets.data(),
-                                  out.seq_offsets.data(), out.seq_lens.data(), &e), e);
+    detail::check((fasta ? bn_fasta_encode : bn_fastq_encode)(detail::ctx(), text.ptr, text.len, n_reads, n_words, out.words.data(),
+                                                             out.word_offsets.data(), out.seq_offsets.data(), out.seq_lens.data(), &e), e);
     return out;
 }
+inline FastqBatch fasta_encode(Bytes text) { return fastq_encode(text, true); }
 
 // src/utils/functions/split.rs:14-20 -- validates idx <= slen, then clears both buffers and fills them
 inline void split_packed(Words ebuf, size_t slen, size_t idx, std::vector<uint64_t>& lbuf, std::vector<uint64_t>& rbuf) {

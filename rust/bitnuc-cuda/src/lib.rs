@@ -145,16 +145,29 @@ pub enum FastqError {
 /// The caller's loop `for record in reader { PackedSequence::new(record.seq())? }` (bitnuc README.md:160-180) in two
 /// calls on the raw text: records are found and encoded on the device.
 pub fn fastq_encode(text: &[u8]) -> Result<FastqBatch, FastqError> {
+    fastx_encode(text, false)
+}
+
+/// The same for FASTA text with one sequence line per record ('>' header line, sequence line).
+pub fn fasta_encode(text: &[u8]) -> Result<FastqBatch, FastqError> {
+    fastx_encode(text, true)
+}
+
+fn fastx_encode(text: &[u8], fasta: bool) -> Result<FastqBatch, FastqError> {
     let (mut n_reads, mut n_words, mut e) = (0usize, 0usize, bn_error_t::default());
-    let rc = with_ctx(|c| unsafe { bn_fastq_scan(c, text.as_ptr(), text.len(), &mut n_reads, &mut n_words, &mut e) });
+    let rc = with_ctx(|c| unsafe {
+        if fasta { bn_fasta_scan(c, text.as_ptr(), text.len(), &mut n_reads, &mut n_words, &mut e) }
+        else { bn_fastq_scan(c, text.as_ptr(), text.len(), &mut n_reads, &mut n_words, &mut e) }
+    });
     if rc == -5 {
         return Err(FastqError::Malformed { record: e.record, fault: e.a as u8 });
     }
     check(rc, &e).map_err(|error| FastqError::Nucleotide { error, record: e.record, position: e.b })?;
     let mut b = FastqBatch { words: vec![0; n_words], word_offsets: vec![0; n_reads + 1], seq_offsets: vec![0; n_reads], seq_lens: vec![0; n_reads] };
     let rc = with_ctx(|c| unsafe {
-        bn_fastq_encode(c, text.as_ptr(), text.len(), n_reads, n_words, b.words.as_mut_ptr(), b.word_offsets.as_mut_ptr(),
-                        b.seq_offsets.as_mut_ptr(), b.seq_lens.as_mut_ptr(), &mut e)
+        let f = if fasta { bn_fasta_encode } else { bn_fastq_encode };
+        f(c, text.as_ptr(), text.len(), n_reads, n_words, b.words.as_mut_ptr(), b.word_offsets.as_mut_ptr(), b.seq_offsets.as_mut_ptr(),
+          b.seq_lens.as_mut_ptr(), &mut e)
     });
     check(rc, &e).map_err(|error| FastqError::Nucleotide { error, record: e.record, position: e.b })?;
     Ok(b)

@@ -261,6 +261,9 @@ static void test_fastq_records() {
     }
     CHECK(threw);
     CHECK(fastq_encode(std::string()).size() == 0);
+    const std::string fa = ">a\nACGTACGT\n>b second\nacgtt\n";
+    const FastqBatch f = fasta_encode(fa);
+    CHECK(f.size() == 2 && f.seq_lens[1] == 5 && f.words[1] == as_2bit("ACGTT") && fa.substr(f.seq_offsets[0], 8) == "ACGTACGT");
 }
 
 int main() {

@@ -1023,71 +1023,19 @@ int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_
 int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens,
                          size_t n_reads, uint64_t* counts4, double* gc, uint64_t totals[4], bn_error_t* err) {
     if (!ctx || (n_reads && (!word_offsets || !lens))) return set_err(err, BN_ERR_ARGUMENT);
-    // One pass over the read table: every read must lie inside `words` (InvalidLength as in decode/hdist); are the reads
-    // laid out in order (word offsets never decrease: what bn_encode_batch / bn_fastq_encode produce)?  If so, where do
-    // chunks of whole reads of about ctx->chunk bytes start, and where does each chunk's furthest-reaching read end?
-    const size_t chunk_words = ctx->chunk / 8;
-    bool in_order = true;
-    std::vector<size_t> cut{0};            // chunk c = reads [cut[c], cut[c+1])
-    std::vector<uint64_t> cut_end{0};      // ... and words [word_offsets[cut[c]], cut_end[c])
-    for (size_t r = 0; r < n_reads; ++r) {
-        const uint64_t off = word_offsets[r], need = (lens[r] + 31) / 32;
-        if (off > n_words || need > n_words - off) {
+    for (size_t r = 0; r < n_reads; ++r) {  // every read must lie inside `words` (InvalidLength as in decode/hdist)
+        const uint64_t need = (lens[r] + 31) / 32;
+        if (word_offsets[r] > n_words || need > n_words - word_offsets[r]) {
             set_err(err, BN_INVALID_LENGTH, lens[r]);
             if (err) err->record = r;
             return BN_INVALID_LENGTH;
         }
-        if (r && off < word_offsets[r - 1]) in_order = false;
-        if (in_order && r > cut.back() && off + need - word_offsets[cut.back()] > chunk_words) {
-            cut.push_back(r);
-            cut_end.push_back(off);
-        }
-        if (need) cut_end.back() = std::max(cut_end.back(), off + need);
     }
-    cut.push_back(n_reads);
     if (totals) totals[0] = totals[1] = totals[2] = totals[3] = 0;
     if (n_reads == 0) return set_err(err, BN_OK);
     if (n_words && !words) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    // Reads in order are cut into chunks of whole reads and run through the 3-stage pipeline: the upload of chunk c+1
-    // (40 B of words + 16 B of offsets / lengths per 150 bp read) overlaps the kernel of chunk c and the download of
-    // chunk c-1 (32 B + 8 B).
-    if (in_order && n_words * 8 > ctx->chunk) {
-        uint64_t acc[4] = {0, 0, 0, 0};
-        const int rc = run_pipeline(
-            ctx, cut.size() - 1, err,
-            [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
-                const size_t r0 = cut[c], r1 = cut[c + 1], cnt = r1 - r0;
-                const uint64_t w0 = word_offsets[r0], w1 = std::max(w0, cut_end[c]);
-                const size_t nw = (size_t)(w1 - w0);
-                BN_TRY(ensure(ctx->stage_in[s], nw ? nw * 8 : 8));
-                BN_TRY(ensure(ctx->stage_aux[s][0], cnt * 8));
-                BN_TRY(ensure(ctx->stage_aux[s][1], cnt * 8));
-                if (counts4) BN_TRY(ensure(ctx->stage_out[s], cnt * 32));
-                if (gc) BN_TRY(ensure(ctx->stage_aux[s][2], cnt * 8));
-                if (nw) BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, words + w0, nw * 8, cudaMemcpyHostToDevice, st));
-                BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][0].p, word_offsets + r0, cnt * 8, cudaMemcpyHostToDevice, st));
-                BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][1].p, lens + r0, cnt * 8, cudaMemcpyHostToDevice, st));
-                unsigned long long* d_tot = ctx->d_words + 4 + 4 * s;
-                // the kernel indexes with the caller's absolute word offsets: hand it the chunk's base moved back by w0
-                BN_TRY(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p) - w0,
-                                                    static_cast<const uint64_t*>(ctx->stage_aux[s][0].p),
-                                                    static_cast<const uint64_t*>(ctx->stage_aux[s][1].p), cnt, 0, nw,
-                                                    counts4 ? static_cast<unsigned long long*>(ctx->stage_out[s].p) : nullptr,
-                                                    gc ? static_cast<double*>(ctx->stage_aux[s][2].p) : nullptr, d_tot, st));
-                if (counts4) BN_TRY(cudaMemcpyAsync(counts4 + 4 * r0, ctx->stage_out[s].p, cnt * 32, cudaMemcpyDeviceToHost, st));
-                if (gc) BN_TRY(cudaMemcpyAsync(gc + r0, ctx->stage_aux[s][2].p, cnt * 8, cudaMemcpyDeviceToHost, st));
-                return cudaMemcpyAsync(ctx->h_words + 4 + 4 * s, d_tot, 4 * 8, cudaMemcpyDeviceToHost, st);
-            },
-            [&](size_t, int s) {
-                for (int i = 0; i < 4; ++i) acc[i] += ctx->h_words[4 + 4 * s + i];
-            });
-        if (rc != BN_OK) return rc;
-        if (totals)
-            for (int i = 0; i < 4; ++i) totals[i] = acc[i];
-        return set_err(err, BN_OK);
-    }
     cudaStream_t st = ctx->stream;
     BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
     BN_CUDA(ensure(ctx->slot[1], n_reads * 8));

@@ -767,9 +767,9 @@ def test_host_pointer_calls_are_chunk_invariant(bn):
     assert [int(x) for x in err.partial[-50:]] == [oracle.as_2bit(seq[i : i + 27]) for i in range(77_777 - 26 - 50, 77_777 - 26)]
 
 
-def test_base_counts_batch_chunked_pipeline_matches_the_staged_call(bn):
-    """bn_base_counts_batch cuts reads laid out in order into chunks of whole reads (3-stage pipeline); out-of-order
-    layouts take the staged path.  Both must equal the oracle per read, whatever the chunk size."""
+def test_base_counts_batch_layouts(bn):
+    """bn_base_counts_batch on read tables in order, overlapping and out of order, whatever the context's chunk size:
+    every read equals the oracle's PackedSequence."""
     rng = np.random.default_rng(17)
     lens = np.concatenate([rng.integers(0, 400, 3000), [5000, 0, 0, 33, 9000], rng.integers(1, 64, 500)]).astype(np.uint64)
     seqs = [ACGT[rng.integers(0, 4, int(n))].tobytes() for n in lens]

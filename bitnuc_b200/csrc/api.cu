@@ -1023,19 +1023,101 @@ int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_
 int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens,
                          size_t n_reads, uint64_t* counts4, double* gc, uint64_t totals[4], bn_error_t* err) {
     if (!ctx || (n_reads && (!word_offsets || !lens))) return set_err(err, BN_ERR_ARGUMENT);
-    for (size_t r = 0; r < n_reads; ++r) {  // every read must lie inside `words` (InvalidLength as in decode/hdist)
-        const uint64_t need = (lens[r] + 31) / 32;
-        if (word_offsets[r] > n_words || need > n_words - word_offsets[r]) {
-            set_err(err, BN_INVALID_LENGTH, lens[r]);
-            if (err) err->record = r;
-            return BN_INVALID_LENGTH;
+    // One pass over the read table, in blocks of 65536 reads spread over a few host threads (10 M reads are 160 MB of
+    // offsets and lengths: single-threaded, this pass cost more than the PCIe transfers): every read must lie inside
+    // `words` (InvalidLength as in decode/hdist); are the reads laid out in order (word offsets never decrease: what
+    // bn_encode_batch / bn_fastq_encode produce)?  Where does each block's furthest-reaching read end?
+    constexpr size_t kBlockReads = 65536;
+    const size_t n_blocks = (n_reads + kBlockReads - 1) / kBlockReads;
+    std::vector<uint64_t> block_end(n_blocks, 0);
+    const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency(), n_blocks / 4}));
+    std::vector<size_t> first_bad(n_thr, SIZE_MAX);
+    std::vector<char> ordered(n_thr, 1);
+    auto scan_blocks = [&](unsigned t) {
+        for (size_t b = n_blocks * t / n_thr; b < n_blocks * (t + 1) / n_thr; ++b) {
+            uint64_t end = 0;
+            const size_t r1 = std::min(n_reads, (b + 1) * kBlockReads);
+            for (size_t r = b * kBlockReads; r < r1; ++r) {
+                const uint64_t off = word_offsets[r], need = (lens[r] + 31) / 32;
+                if (off > n_words || need > n_words - off) {
+                    first_bad[t] = std::min(first_bad[t], r);
+                    return;
+                }
+                if (r && off < word_offsets[r - 1]) ordered[t] = 0;
+                if (need) end = std::max(end, off + need);
+            }
+            block_end[b] = end;
         }
+    };
+    {
+        std::vector<std::thread> workers;
+        for (unsigned t = 1; t < n_thr; ++t) workers.emplace_back(scan_blocks, t);
+        scan_blocks(0);
+        for (auto& w : workers) w.join();
     }
+    const size_t bad = *std::min_element(first_bad.begin(), first_bad.end());
+    if (bad != SIZE_MAX) {   // the first failing read in index order
+        set_err(err, BN_INVALID_LENGTH, lens[bad]);
+        if (err) err->record = bad;
+        return BN_INVALID_LENGTH;
+    }
+    const bool in_order = std::all_of(ordered.begin(), ordered.end(), [](char c) { return c != 0; });
+    // chunks of whole blocks of about ctx->chunk bytes of words: chunk c = reads [cut[c], cut[c+1]), words up to cut_end[c]
+    const size_t chunk_words = ctx->chunk / 8;
+    std::vector<size_t> cut{0};
+    std::vector<uint64_t> cut_end{0};
+    for (size_t b = 0; in_order && b < n_blocks; ++b) {
+        const size_t r = b * kBlockReads;
+        if (r > cut.back() && std::max(cut_end.back(), block_end[b]) > word_offsets[cut.back()] + chunk_words) {
+            cut.push_back(r);
+            cut_end.push_back(0);
+        }
+        cut_end.back() = std::max(cut_end.back(), block_end[b]);
+    }
+    cut.push_back(n_reads);
     if (totals) totals[0] = totals[1] = totals[2] = totals[3] = 0;
     if (n_reads == 0) return set_err(err, BN_OK);
     if (n_words && !words) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    // Reads in order are cut into chunks of whole reads and run through the 3-stage pipeline: the upload of chunk c+1
+    // (40 B of words + 16 B of offsets / lengths per 150 bp read) overlaps the kernel of chunk c and the download of
+    // chunk c-1 (32 B + 8 B).
+    if (in_order && n_words * 8 > ctx->chunk) {
+        uint64_t acc[4] = {0, 0, 0, 0};
+        const int rc = run_pipeline(
+            ctx, cut.size() - 1, err,
+            [&](size_t c, int s, cudaStream_t st) -> cudaError_t {
+                const size_t r0 = cut[c], r1 = cut[c + 1], cnt = r1 - r0;
+                const uint64_t w0 = word_offsets[r0], w1 = std::max(w0, cut_end[c]);
+                const size_t nw = (size_t)(w1 - w0);
+                BN_TRY(ensure(ctx->stage_in[s], nw ? nw * 8 : 8));
+                BN_TRY(ensure(ctx->stage_aux[s][0], cnt * 8));
+                BN_TRY(ensure(ctx->stage_aux[s][1], cnt * 8));
+                if (counts4) BN_TRY(ensure(ctx->stage_out[s], cnt * 32));
+                if (gc) BN_TRY(ensure(ctx->stage_aux[s][2], cnt * 8));
+                if (nw) BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, words + w0, nw * 8, cudaMemcpyHostToDevice, st));
+                BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][0].p, word_offsets + r0, cnt * 8, cudaMemcpyHostToDevice, st));
+                BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][1].p, lens + r0, cnt * 8, cudaMemcpyHostToDevice, st));
+                unsigned long long* d_tot = ctx->d_words + 4 + 4 * s;
+                // the kernel indexes with the caller's absolute word offsets: hand it the chunk's base moved back by w0
+                BN_TRY(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p) - w0,
+                                                    static_cast<const uint64_t*>(ctx->stage_aux[s][0].p),
+                                                    static_cast<const uint64_t*>(ctx->stage_aux[s][1].p), cnt, 0, nw,
+                                                    counts4 ? static_cast<unsigned long long*>(ctx->stage_out[s].p) : nullptr,
+                                                    gc ? static_cast<double*>(ctx->stage_aux[s][2].p) : nullptr, d_tot, st));
+                if (counts4) BN_TRY(cudaMemcpyAsync(counts4 + 4 * r0, ctx->stage_out[s].p, cnt * 32, cudaMemcpyDeviceToHost, st));
+                if (gc) BN_TRY(cudaMemcpyAsync(gc + r0, ctx->stage_aux[s][2].p, cnt * 8, cudaMemcpyDeviceToHost, st));
+                return cudaMemcpyAsync(ctx->h_words + 4 + 4 * s, d_tot, 4 * 8, cudaMemcpyDeviceToHost, st);
+            },
+            [&](size_t, int s) {
+                for (int i = 0; i < 4; ++i) acc[i] += ctx->h_words[4 + 4 * s + i];
+            });
+        if (rc != BN_OK) return rc;
+        if (totals)
+            for (int i = 0; i < 4; ++i) totals[i] = acc[i];
+        return set_err(err, BN_OK);
+    }
     cudaStream_t st = ctx->stream;
     BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
     BN_CUDA(ensure(ctx->slot[1], n_reads * 8));
@@ -1043,7 +1125,7 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
     if (counts4) BN_CUDA(ensure(ctx->slot[3], n_reads * 32));
     if (gc) BN_CUDA(ensure(ctx->slot[4], n_reads * 8));
     if (n_words) BN_CUDA(cudaMemcpyAsync(ctx->slot[0].p, words, n_words * 8, cudaMemcpyHostToDevice, st));
-    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->slot[1].p, word_offsets, n_reads * 8, cudaMemcpyHostToDevice, st));
     BN_CUDA(cudaMemcpyAsync(ctx->slot[2].p, lens, n_reads * 8, cudaMemcpyHostToDevice, st));
     BN_CUDA(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->slot[0].p),
                                          static_cast<const uint64_t*>(ctx->slot[1].p), static_cast<const uint64_t*>(ctx->slot[2].p),

@@ -768,8 +768,9 @@ def test_host_pointer_calls_are_chunk_invariant(bn):
 
 
 def test_base_counts_batch_layouts(bn):
-    """bn_base_counts_batch on read tables in order, overlapping and out of order, whatever the context's chunk size:
-    every read equals the oracle's PackedSequence."""
+    """bn_base_counts_batch cuts read tables that are in order into chunks of whole reads (3-stage pipeline); overlapping
+    reads stay in order, out-of-order tables take the staged path.  Whatever the context's chunk size, every read equals
+    the oracle's PackedSequence."""
     rng = np.random.default_rng(17)
     lens = np.concatenate([rng.integers(0, 400, 3000), [5000, 0, 0, 33, 9000], rng.integers(1, 64, 500)]).astype(np.uint64)
     seqs = [ACGT[rng.integers(0, 4, int(n))].tobytes() for n in lens]
@@ -800,3 +801,28 @@ def test_base_counts_batch_layouts(bn):
         c3, g3, t3 = bn.base_counts_batch(w, np.concatenate([wo[:-1][perm], [w.size]]).astype(np.uint64), lens[perm], ctx=ctx)
         assert np.array_equal(c3, exp_counts[perm]) and np.array_equal(g3, exp_gc[perm]) and t3 == totals
         ctx.close()
+
+
+def test_base_counts_batch_offsets_table_has_n_reads_entries(bn):
+    """Regression: the staged call copied n_reads + 1 offsets into a device buffer sized for n_reads -- with n_reads a
+    multiple of 32 (8 n_reads a multiple of the 256-byte allocation granule) the copy failed with a CUDA error, and it
+    read one entry past a caller's table of exactly n_reads offsets."""
+    import ctypes as C
+    from bitnuc_b200._lib import BnError
+    ctx = bn.Context(0)
+    for n in (32, 64, 4096):
+        seqs = [ACGT[np.random.default_rng(r).integers(0, 4, 40 + r % 7)].tobytes() for r in range(n)]
+        words, wo = [], []
+        for s in seqs:
+            wo.append(len(words))
+            words += oracle.encode_alloc(s)
+        w, wo = np.array(words, dtype=np.uint64), np.array(wo, dtype=np.uint64)       # exactly n offsets
+        lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+        counts, gc = np.zeros((n, 4), dtype=np.uint64), np.zeros(n)
+        totals, err = (C.c_uint64 * 4)(), BnError()
+        rc = ctx.lib.bn_base_counts_batch(ctx.handle, w.ctypes.data, w.size, wo.ctypes.data, lens.ctypes.data, n, counts.ctypes.data,
+                                          gc.ctypes.data, totals, C.byref(err))
+        assert rc == 0
+        assert [int(x) for x in counts[n - 1]] == oracle.base_counts(oracle.encode_alloc(seqs[-1]), len(seqs[-1]))
+        assert sum(totals) == int(lens.sum())
+    ctx.close()

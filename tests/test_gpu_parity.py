@@ -826,3 +826,33 @@ def test_base_counts_batch_offsets_table_has_n_reads_entries(bn):
         assert [int(x) for x in counts[n - 1]] == oracle.base_counts(oracle.encode_alloc(seqs[-1]), len(seqs[-1]))
         assert sum(totals) == int(lens.sum())
     ctx.close()
+
+
+def test_base_counts_batch_many_chunks(bn):
+    """More reads than one 65536-read block, a small chunk size: several pipeline chunks, each a whole number of blocks;
+    totals and sampled reads against the oracle, and the first read that does not fit `words` is reported by index."""
+    rng = np.random.default_rng(23)
+    n = 200_000
+    lens = rng.integers(0, 61, n).astype(np.uint64)
+    nw = (lens + np.uint64(31)) // np.uint64(32)
+    wo = np.concatenate([[0], np.cumsum(nw)]).astype(np.uint64)
+    w = rng.integers(0, 1 << 63, int(wo[-1]), dtype=np.int64).view(np.uint64)
+    ctx = bn.Context(0)
+    ctx.set_chunk_bytes(65536)
+    counts, gc, totals = bn.base_counts_batch(w, wo, lens, ctx=ctx)
+    assert sum(totals) == int(lens.sum())
+    assert np.array_equal(counts.sum(axis=0), np.array(totals, dtype=np.uint64))
+    for r in (0, 65535, 65536, 131071, 131072, n - 1):
+        sl = w[int(wo[r]) : int(wo[r + 1])]
+        assert [int(x) for x in counts[r]] == oracle.base_counts(sl, int(lens[r])) and gc[r] == oracle.gc_content(sl, int(lens[r]))
+    big = bn.Context(0)
+    c2, g2, t2 = bn.base_counts_batch(w, wo, lens, ctx=big)          # default chunk: the staged path (small input)
+    assert np.array_equal(c2, counts) and np.array_equal(g2, gc) and t2 == totals
+    bad = lens.copy()
+    bad[150_000] = np.uint64(64 * (w.size + 5))
+    bad[170_000] = np.uint64(64 * (w.size + 5))
+    with pytest.raises(bn.NucleotideError) as ei:
+        bn.base_counts_batch(w, wo, bad, ctx=ctx)
+    assert ei.value.key() == ("InvalidLength", int(bad[150_000]))
+    ctx.close()
+    big.close()

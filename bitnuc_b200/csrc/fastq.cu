@@ -105,6 +105,20 @@ __device__ __forceinline__ void report_min(unsigned long long* word, unsigned lo
 
 // ---------------------------------------------------------------- 1. newlines per tile -----------------------------
 
+// position of the n-th (0-based) set bit of m, n < popc(m): a binary search on popcounts (__fns does the same for either
+// direction and any base in ~55 instructions; this is ~25)
+__device__ __forceinline__ unsigned nth_set_bit(uint32_t m, unsigned n) {
+    unsigned pos = 0, c = __popc(m & 0xFFFFu);
+    if (n >= c) n -= c, pos = 16, m >>= 16;
+    c = __popc(m & 0xFFu);
+    if (n >= c) n -= c, pos += 8, m >>= 8;
+    c = __popc(m & 0xFu);
+    if (n >= c) n -= c, pos += 4, m >>= 4;
+    c = __popc(m & 0x3u);
+    if (n >= c) n -= c, pos += 2, m >>= 2;
+    return pos + (n >= (m & 1u) ? 1u : 0u);
+}
+
 // the four vectors a thread loads of a tile (lane-consecutive: coalesced)
 __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0, unsigned tid,
                                                 uint4 (&x)[4]) {
@@ -170,7 +184,7 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
         uint32_t m = 0;
         if (i0 + 32u * warp < n_hit) {   // warp-uniform: a warp with no survivor of this round only joins the barriers
             const unsigned ii = active ? i : n_hit - 1;
-            // hit vector #ii: the bitmap word k that holds it (= number of words whose inclusive prefix is <= ii), then the bit
+            // hit vector #ii: the bitmap word k that holds it (= number of words whose inclusive prefix is <= ii), then its bit
             unsigned k = 0;
 #pragma unroll
             for (unsigned step = 16; step; step >>= 1) {
@@ -179,7 +193,7 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
             }
             const unsigned prev_inc = __shfl_sync(0xffffffffu, inc, k ? k - 1 : 0);
             const uint32_t word = __shfl_sync(0xffffffffu, hw, k);
-            v = 32u * k + __fns(word, 0, (int)(ii - (k ? prev_inc : 0u)) + 1);
+            v = 32u * k + nth_set_bit(word, ii - (k ? prev_inc : 0u));
             m = active ? newline_mask16(raw[v]) : 0u;   // exact; bit b <-> byte b of the vector
             cnt = __popc(m);
             c_inc = cnt;

@@ -222,7 +222,7 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
             ++rank;
         }
         total += round_total;
-        __syncthreads();   // warp_tot is reused by the next round
+        if (i0 + kFqThreads < n_hit) __syncthreads();   // warp_tot is reused by the next round (CTA-uniform: usually there is none)
     }
     if (tid == 0) {
         counts[tile] = total;

@@ -144,11 +144,12 @@ def run_reference(args):
     value = 2 * sample * args.steps / dt / 1e9
     single, _ = cpu_codec_gbases(min(sample, 1 << 26), 1, 2)
     line = {
-        "impl": "reference", "metric": METRIC.replace("device-timed", "host wall-clock"), "value": value, "unit": UNIT,
+        "impl": "reference", "metric": METRIC, "timing": "host wall-clock around the CPU implementation (there is no device in this arm)",
+        "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"encode+decode of a contiguous random sequence, CPU, bounded sample of {sample} bases per step "
-                               "(BASELINE.json configs[1] is 1e9 bases)", "bases_per_step": sample},
+        "config": {"workload": "BASELINE.json configs[1]: encode + decode of one contiguous random sequence, device-resident",
+                   "sample": f"CPU arm: a bounded sample of {sample} bases per step of the 1e9-base workload", "bases_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} bases/step, {args.steps} steps, oracle C restatement of packing/avx.rs + "
                                    f"unpacking/avx.rs ({'AVX2' if path == oracle.PATH_AVX2 else 'scalar'}), chunked over {threads} threads; "

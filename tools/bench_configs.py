@@ -324,18 +324,20 @@ def fastq(scale, reps):
     (count + index + encode), on 20 M x 150 bp reads (23-byte header lines, so every alignment occurs) and on
     10 kbp reads.  Checked against bn_encode_batch_dev of the same sequences."""
     ctx = dv.api.default_context(0)
-    for n_reads, rl, hdr in ((int(20_000_000 * scale), 150, 23), (int(300_000 * scale), 10_000, 37)):
-        rec = hdr + rl + 1 + 2 + rl + 1
+    for n_reads, rl, hdr, fasta in ((int(20_000_000 * scale), 150, 23, False), (int(300_000 * scale), 10_000, 37, False),
+                                    (int(20_000_000 * scale), 150, 23, True)):
+        rec = hdr + rl + 1 if fasta else hdr + rl + 1 + 2 + rl + 1
         seqs = dv.synth_ascii(SEED, 7, 0, n_reads * rl).view(n_reads, rl)
         text2 = torch.full((n_reads, rec), ord("I"), dtype=torch.uint8, device="cuda")
-        text2[:, 0] = ord("@")
+        text2[:, 0] = ord(">") if fasta else ord("@")
         text2[:, 1 : hdr - 1] = ord("h")
         text2[:, hdr - 1] = 10
         text2[:, hdr : hdr + rl] = seqs
         text2[:, hdr + rl] = 10
-        text2[:, hdr + rl + 1] = ord("+")
-        text2[:, hdr + rl + 2] = 10
-        text2[:, rec - 1] = 10
+        if not fasta:
+            text2[:, hdr + rl + 1] = ord("+")
+            text2[:, hdr + rl + 2] = 10
+            text2[:, rec - 1] = 10
         text = text2.view(-1)
         n_bytes = text.numel()
         scratch = torch.empty(ctx.lib.bn_fastq_scratch_bytes(n_bytes), dtype=torch.uint8, device="cuda")
@@ -349,24 +351,26 @@ def fastq(scale, reps):
         st = dv.FastqStatus("cuda")
         P = dv._ptr
 
+        L = ctx.lib
+        f_count, f_index, f_encode = (L.bn_fasta_count_dev, L.bn_fasta_index_dev, L.bn_fasta_encode_dev) if fasta else \
+            (L.bn_fastq_count_dev, L.bn_fastq_index_dev, L.bn_fastq_encode_dev)
+
         def count():
-            dv.raise_for(ctx.lib.bn_fastq_count_dev(ctx.handle, dv._stream(), P(text), n_bytes, P(scratch), P(n_lines)))
+            dv.raise_for(f_count(ctx.handle, dv._stream(), P(text), n_bytes, P(scratch), P(n_lines)))
 
         def index():
-            dv.raise_for(ctx.lib.bn_fastq_index_dev(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, P(scratch), P(iscratch), P(so), P(sl),
-                                                    P(wo), P(st.word)))
+            dv.raise_for(f_index(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, P(scratch), P(iscratch), P(so), P(sl), P(wo), P(st.word)))
 
         def encode():
-            dv.raise_for(ctx.lib.bn_fastq_encode_dev(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, P(scratch), P(so), P(sl), P(wo),
-                                                     P(words), P(st.word)))
+            dv.raise_for(f_encode(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, P(scratch), P(so), P(sl), P(wo), P(words), P(st.word)))
 
         def whole():
             count(), index(), encode()
 
         ms_c, ms_i, ms_e, ms = timed(count, reps), timed(index, reps), timed(encode, reps), timed(whole, reps)
-        st.n_lines, st.seq_offsets, st.n_reads = int(n_lines.item()), so, n_reads
+        st.n_lines, st.seq_offsets, st.n_reads, st.fasta = int(n_lines.item()), so, n_reads, fasta
         st.check()
-        assert st.n_lines == 4 * n_reads and int(wo[-1].item()) == n_reads * wpr
+        assert st.n_lines == (2 if fasta else 4) * n_reads and int(wo[-1].item()) == n_reads * wpr
         assert torch.equal(sl, torch.full_like(sl, rl)) and torch.equal(so, torch.arange(n_reads, device="cuda") * rec + hdr)
         offs = torch.arange(n_reads + 1, dtype=torch.int64, device="cuda") * rl
         ref_words, ref_wo, _, bst = dv.encode_batch(seqs.reshape(-1), offs)
@@ -376,7 +380,7 @@ def fastq(scale, reps):
         alg = n_bytes + 8 * n_reads * wpr + 24 * n_reads
         extra = {"count_ms": round(ms_c, 4), "index_ms": round(ms_i, 4), "encode_ms": round(ms_e, 4), "text_bytes": n_bytes,
                  "text_GB/s": round(n_bytes / (ms * 1e-3) / 1e9, 1)}
-        report(f"fastq scan+encode reads={n_reads} x {rl} bp", ms, alg, n_reads * rl, "bases", extra)
+        report(f"{'fasta' if fasta else 'fastq'} scan+encode reads={n_reads} x {rl} bp", ms, alg, n_reads * rl, "bases", extra)
         del text, text2, seqs, words, scratch, iscratch
 
 

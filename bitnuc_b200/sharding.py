@@ -74,6 +74,32 @@ def fastq_record_start(text, pos: int) -> int:
     return n
 
 
+def fasta_record_start(text, pos: int) -> int:
+    """The first record boundary at or after byte ``pos`` of a FASTA text: the start of a line that opens with '>'
+    (a sequence line never does)."""
+    t = memoryview(text).cast("B") if not isinstance(text, np.ndarray) else text
+    n = len(t)
+    p = pos
+    if p > 0:
+        while p < n and t[p - 1] != 10:
+            p += 1
+    while p < n and t[p] != 62:  # '>'
+        while p < n and t[p] != 10:
+            p += 1
+        p += 1
+    return min(p, n)
+
+
+def shard_fasta_text(text, world: int) -> list[tuple[int, int]]:
+    """``shard_fastq_text`` for FASTA text (``bn_fasta_*``)."""
+    n = len(text)
+    cuts = [0]
+    for g in range(1, world):
+        cuts.append(max(cuts[-1], fasta_record_start(text, n * g // world)))
+    cuts.append(n)
+    return [(cuts[g], cuts[g + 1]) for g in range(world)]
+
+
 def shard_fastq_text(text, world: int) -> list[tuple[int, int]]:
     """Cut a FASTQ text into ``world`` contiguous byte ranges of near-equal size on record boundaries: every rank
     parses and encodes its own range (``bn_fastq_*``), read indices / word offsets of rank g are then offset by the

@@ -151,3 +151,18 @@ def test_fastq_cuts_fall_on_record_boundaries():
         total += oracle.fastq_scan(text[lo:hi])[0].size
     assert total == 200
     assert make_fastq is not None
+
+
+def test_fasta_cuts_fall_on_record_boundaries():
+    from bitnuc_b200 import sharding as sh
+    from test_oracle_fastq import make_fastq
+    rng = np.random.default_rng(4)
+    text = make_fastq(rng, rng.integers(0, 200, 300), crlf=True, fasta=True)
+    starts = {0} | {i + 1 for i in range(len(text) - 1) if text[i] == 10 and text[i + 1] == ord(">")}
+    for world in (1, 2, 7, 50):
+        shards = sh.shard_fasta_text(text, world)
+        assert shards[0][0] == 0 and shards[-1][1] == len(text) and all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+        assert all(lo in starts or lo == len(text) for lo, _ in shards)
+        assert sum(oracle.fasta_scan(text[lo:hi])[0].size for lo, hi in shards) == 300
+    for pos in range(0, len(text), 53):
+        assert sh.fasta_record_start(text, pos) == min([s for s in starts if s >= pos] + [len(text)])

@@ -90,6 +90,7 @@ def lib():
             "orc_split_packed": (C.c_int, [C.c_void_p, sz, sz, sz, C.c_void_p, szp, C.c_void_p, szp, ep]),
             "orc_fastq_scan": (C.c_int, [C.c_void_p, sz, C.c_void_p, C.c_void_p, sz, szp, u64p, C.POINTER(C.c_int)]),
             "orc_fasta_scan": (C.c_int, [C.c_void_p, sz, C.c_void_p, C.c_void_p, sz, szp, u64p, C.POINTER(C.c_int)]),
+            "orc_fastx_encode": (C.c_int, [C.c_void_p, sz, C.c_int, C.c_int, C.c_void_p, sz, C.c_void_p, sz, szp, u64p, C.POINTER(C.c_int), ep]),
             "orc_splitmix64": (u64, [u64]),
             "orc_synth_word": (u64, [u64, u64, u64]),
             "orc_synth_ascii": (None, [u64, u64, u64, sz, C.c_void_p]),
@@ -333,6 +334,28 @@ def fastq_encode(text, fasta: bool = False):
         offs.append(offs[-1] + (l + 31) // 32)
     w = np.concatenate(words) if words else np.zeros(0, dtype=np.uint64)
     return w, np.asarray(offs, dtype=np.uint64), starts, lens
+
+
+def fastx_encode_timed(text, fasta: bool = False, path: int = PATH_AVX2, reps: int = 3):
+    """(seconds, words, word_offsets) of the single-threaded CPU form of the FASTQ / FASTA row: reader + per-record encode
+    in C (orc_fastx_encode), best of ``reps``.  bench tools only."""
+    import time
+    t = _bytes_arr(text)
+    reads_cap = t.size // (2 if fasta else 4) + 1
+    words = np.empty(t.size // 32 + reads_cap, dtype=np.uint64)
+    wo = np.empty(reads_cap + 1, dtype=np.uint64)
+    n_reads, bad, fault, e = C.c_size_t(0), C.c_uint64(0), C.c_int(0), _Err()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc = lib().orc_fastx_encode(_ptr(t), t.size, int(fasta), path, _ptr(words), words.size, _ptr(wo), reads_cap, C.byref(n_reads),
+                                    C.byref(bad), C.byref(fault), C.byref(e))
+        best = min(best, time.perf_counter() - t0)
+        if rc == -5:
+            raise FastqFault(bad.value, fault.value)
+        _raise(rc, e)
+    n = n_reads.value
+    return best, words[: int(wo[n])], wo[: n + 1]
 
 
 def synth_word(seed: int, stream: int, j: int) -> int:

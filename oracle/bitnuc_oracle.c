@@ -17,6 +17,7 @@
 #include <immintrin.h>
 #include <pthread.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -368,6 +369,36 @@ int orc_fasta_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *le
         *n_reads = r;
     }
     return 0;
+}
+
+int orc_fastx_encode(const uint8_t *text, size_t n, int fasta, int path, uint64_t *words, size_t words_cap,
+                     uint64_t *word_offsets, size_t reads_cap, size_t *n_reads, uint64_t *bad_record, int *fault,
+                     orc_error *err) {
+    /* the reader first (a streaming reader would interleave; the work is the same) */
+    uint64_t *starts = (uint64_t *)malloc((reads_cap ? reads_cap : 1) * 2 * sizeof(uint64_t));
+    if (!starts) return -2;
+    uint64_t *lens = starts + (reads_cap ? reads_cap : 1);
+    int rc = fasta ? orc_fasta_scan(text, n, starts, lens, reads_cap, n_reads, bad_record, fault)
+                   : orc_fastq_scan(text, n, starts, lens, reads_cap, n_reads, bad_record, fault);
+    if (rc == 0 && *n_reads > reads_cap) rc = -2;
+    size_t w = 0;
+    for (size_t r = 0; rc == 0 && r < *n_reads; ++r) {
+        word_offsets[r] = w;
+        const size_t need = (size_t)((lens[r] + 31) / 32);
+        if (need == 0) continue; /* PackedSequence::new(b"") is Ok and empty, src/sequence.rs:42-46 */
+        if (w + need > words_cap) {
+            rc = -2;
+            break;
+        }
+        size_t got = 0;
+        rc = path == ORC_PATH_AVX2 && orc_have_avx2() ? orc_encode_avx2(text + starts[r], (size_t)lens[r], words + w, &got, err)
+                                                      : orc_encode(text + starts[r], (size_t)lens[r], words + w, &got, err);
+        if (rc) *bad_record = r;
+        w += need;
+    }
+    if (rc == 0) word_offsets[*n_reads] = w;
+    free(starts);
+    return rc;
 }
 
 uint64_t orc_splitmix64(uint64_t x) {

@@ -99,6 +99,14 @@ int orc_fastq_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *le
 int orc_fasta_scan(const uint8_t *text, size_t n, uint64_t *starts, uint64_t *lens, size_t cap, size_t *n_reads,
                    uint64_t *bad_record, int *fault);
 
+/* The caller's loop over a FASTQ / FASTA reader (README.md:160-180) in one call, for the timed CPU baseline of that row:
+ * scan the records, then PackedSequence::new(record.seq()) = the AVX2 (or naive) encode of every sequence line onto
+ * fresh words.  words needs sum(ceil(len/32)) entries (words_cap available), word_offsets n_reads + 1.  Returns 0,
+ * -5 (format fault, as orc_fastq_scan), 1 (InvalidBase, err filled), or -2 when a buffer is too small. */
+int orc_fastx_encode(const uint8_t *text, size_t n, int fasta, int path, uint64_t *words, size_t words_cap,
+                     uint64_t *word_offsets, size_t reads_cap, size_t *n_reads, uint64_t *bad_record, int *fault,
+                     orc_error *err);
+
 /* ---- synthetic input: counter-based splitmix64 stream --------------------- */
 uint64_t orc_splitmix64(uint64_t x);
 uint64_t orc_synth_word(uint64_t seed, uint64_t stream, uint64_t j);

@@ -92,3 +92,22 @@ def test_fastq_encode_is_the_callers_loop():
     with pytest.raises(oracle.OracleError) as ei:
         oracle.fastq_encode(bytes(bad))
     assert ei.value.key() == ("InvalidBase", ord("N"))
+
+
+@pytest.mark.parametrize("fasta", [False, True])
+def test_one_call_cpu_form_equals_the_callers_loop(fasta):
+    """orc_fastx_encode (the timed CPU baseline of the FASTQ / FASTA row) against fastq_scan + per-record encode."""
+    rng = np.random.default_rng(31 + fasta)
+    text = make_fastq(rng, rng.integers(0, 300, 500), crlf=bool(fasta), alphabet=b"ACGTacgt", fasta=fasta)
+    _, w, wo = oracle.fastx_encode_timed(text, fasta, reps=1)
+    ew, ewo, _, _ = oracle.fastq_encode(text, fasta)
+    assert np.array_equal(w, ew) and np.array_equal(wo, ewo)
+    _, w2, _ = oracle.fastx_encode_timed(text, fasta, path=oracle.PATH_NAIVE, reps=1)
+    assert np.array_equal(w2, ew)
+    bad = bytearray(text)
+    bad[bad.find(b"\n") + 2] = ord("N")
+    with pytest.raises(oracle.OracleError) as ei:
+        oracle.fastx_encode_timed(bytes(bad), fasta, reps=1)
+    assert ei.value.key() == ("InvalidBase", ord("N"))
+    with pytest.raises(oracle.FastqFault):
+        oracle.fastx_encode_timed(text[1:], fasta, reps=1)

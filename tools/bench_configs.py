@@ -319,7 +319,7 @@ def next_rows(scale, reps):
     report(f"slice gathers: {reads} windows of 50 bases out of 150 bp reads", ms, (16 + 16 + 24 + 50 + 8) * reads, reads, "queries")
 
 
-def fastq(scale, reps):
+def fastq(scale, reps, cpu_port=None):
     """SURVEY.md 8(f) row 3, first half: FASTQ text resident in HBM -> record offsets -> per-read packed words
     (count + index + encode), on 20 M x 150 bp reads (23-byte header lines, so every alignment occurs) and on
     10 kbp reads.  Checked against bn_encode_batch_dev of the same sequences."""
@@ -378,7 +378,16 @@ def fastq(scale, reps):
         assert torch.equal(ref_wo, wo) and torch.equal(ref_words[: n_reads * wpr], words)
         del ref_words, ref_wo
         alg = n_bytes + 8 * n_reads * wpr + 24 * n_reads
-        extra = {"count_ms": round(ms_c, 4), "index_ms": round(ms_i, 4), "encode_ms": round(ms_e, 4), "text_bytes": n_bytes,
+        extra = {}
+        if cpu_port is not None:
+            # the CPU form of this row beside it (tests/test_gpu_full_size.py passes the oracle's reader + per-record AVX2
+            # encode, the caller's loop of README.md:160-180): one host thread, a bounded sample of the same text
+            sample_reads = min(n_reads, max(1, 60_000_000 // rec))
+            cpu_s, cpu_w, _ = cpu_port(text[: sample_reads * rec].cpu().numpy(), fasta)
+            assert np.array_equal(cpu_w.view(np.int64), words[: sample_reads * wpr].cpu().numpy())
+            extra = {"cpu_port_1thread_Gbases_s": round(sample_reads * rl / cpu_s / 1e9, 3),
+                     "cpu_sample": f"{sample_reads} reads, {sample_reads * rec} bytes of text"}
+        extra |= {"count_ms": round(ms_c, 4), "index_ms": round(ms_i, 4), "encode_ms": round(ms_e, 4), "text_bytes": n_bytes,
                  "text_GB/s": round(n_bytes / (ms * 1e-3) / 1e9, 1)}
         report(f"{'fasta' if fasta else 'fastq'} scan+encode reads={n_reads} x {rl} bp", ms, alg, n_reads * rl, "bases", extra)
         del text, text2, seqs, words, scratch, iscratch

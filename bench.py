@@ -420,8 +420,10 @@ def report(args, world, rank, n, K, total_ms, enc_ms, dec_ms, e2e_ms, e2e_serial
                 threads = host_threads()
                 v_all, isa = cpu_codec_gbases(SAMPLE_BASES, threads, 3)
                 v_one, _ = cpu_codec_gbases(1 << 26, 1, 3)
+                v_cfg0, _ = cpu_codec_gbases(1_000_000, 1, 5)   # BASELINE.json configs[0]: the reference's own CPU-runnable case
                 line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port",
                                         "single_thread_value": v_one,
+                                        "configs0_1e6_bases_single_thread_value": v_cfg0,
                                         "sample": f"{SAMPLE_BASES} bases encode+decode, best of 3, C restatement of the reference's "
                                                   f"{isa} path (oracle/bitnuc_oracle.c), chunked over {threads} host threads"}
             except Exception as ex:  # the baseline is reported, never required for the GPU number

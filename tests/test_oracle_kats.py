@@ -248,3 +248,19 @@ def test_avx2_restatement_matches_scalar_on_random_input():
             assert keys[0] == keys[1] and len(keys[0][1]) == pos // 32
     t = oracle.bench_codec(alphabet[rng.integers(0, 4, 100000)], threads=2, reps=1)
     assert t > 0
+
+
+def test_baseline_config0_round_trip_on_cpu():
+    """BASELINE.json configs[0]: encode + decode round trip of one 1,000,000-base random sequence on the CPU -- both
+    restatements (naive and AVX2 paths) return the input, and the packed words are the generator's own words."""
+    import numpy as np
+    import oracle
+    from oracle import oracle_np as onp
+    n = 1_000_000
+    seq = onp.synth_ascii(oracle.DEFAULT_SEED, 0, n)
+    words = oracle.encode_np(seq, avx2=oracle.have_avx2())
+    assert np.array_equal(words, oracle.encode_np(seq)) and words.size == 31_250
+    assert [int(w) for w in words[:4]] == [oracle.synth_word(oracle.DEFAULT_SEED, 0, j) for j in range(4)]
+    for path in (oracle.PATH_NAIVE, oracle.PATH_AVX2):
+        assert np.array_equal(oracle.decode_np(words, n, path=path), seq)
+    assert np.array_equal(onp.encode(seq), words)

@@ -12,6 +12,7 @@ from .errors import BitnucCudaError, FastqError, NucleotideError, ReferencePanic
 from .api import (Context, as_2bit, as_2bit_batch, base_counts_batch, base_counts_gc, decode, decode_np,
                   default_context, encode, encode_alloc, encode_batch, encode_np, fasta_encode, fastq_encode, from_2bit, from_2bit_alloc,
                   from_2bit_batch, hdist, hdist_pairs, hdist_scalar, hdist_total, get_batch, kmers, kmers_batch, slice_batch, split_packed, split_packed_batch)
+from .multi import MultiContext
 from .sequence import PackedSequence
 
 __all__ = [
@@ -19,5 +20,5 @@ __all__ = [
     "as_2bit", "from_2bit", "from_2bit_alloc", "encode", "encode_alloc", "decode", "hdist", "hdist_scalar",
     "encode_np", "decode_np", "as_2bit_batch", "from_2bit_batch", "hdist_pairs", "hdist_total",
     "base_counts_gc", "base_counts_batch", "encode_batch", "split_packed", "split_packed_batch", "slice_batch", "get_batch", "kmers", "kmers_batch",
-    "fastq_encode", "fasta_encode", "FastqError",
+    "fastq_encode", "fasta_encode", "FastqError", "MultiContext",
 ]

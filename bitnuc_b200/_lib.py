@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libbitnuc_cuda.so"
 
 BN_OK = 0
-BN_ERR_CUDA, BN_ERR_ARGUMENT, BN_ERR_EMPTY_ENCODE, BN_ERR_NOMEM, BN_ERR_FASTQ = -1, -2, -3, -4, -5
+BN_ERR_CUDA, BN_ERR_ARGUMENT, BN_ERR_EMPTY_ENCODE, BN_ERR_NOMEM, BN_ERR_FASTQ, BN_ERR_COLLECTIVE = -1, -2, -3, -4, -5, -6
 
 
 class BnError(C.Structure):
@@ -35,6 +35,8 @@ PROTOTYPES = {
     "bn_ctx_set_chunk_bytes": (_int, [_vp, _sz]),
     "bn_ctx_set_compat": (_int, [_vp, _int]),
     "bn_ctx_compat": (_int, [_vp]),
+    "bn_ctx_set_timing": (_int, [_vp, _int]),
+    "bn_last_kernel_ms": (_int, [_vp, C.POINTER(C.c_float)]),
     "bn_dev_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
     "bn_dev_free": (_int, [_vp, _vp]),
     "bn_host_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
@@ -91,6 +93,31 @@ PROTOTYPES = {
     "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),
     "bn_synth_words_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
     "bn_synth_ascii_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
+    # multi-GPU (one process, N devices)
+    "bn_multi_create": (_int, [C.POINTER(_int), _int, _int, C.POINTER(_vp)]),
+    "bn_multi_destroy": (None, [_vp]),
+    "bn_multi_size": (_int, [_vp]),
+    "bn_multi_ctx": (_vp, [_vp, _int]),
+    "bn_multi_reduce": (_int, [_vp]),
+    "bn_multi_nccl_version": (_int, [_vp]),
+    "bn_multi_set_chunk_bytes": (_int, [_vp, _sz]),
+    "bn_multi_synchronize": (_int, [_vp]),
+    "bn_multi_shard_units": (_int, [_vp, _sz, _sz, C.POINTER(_sz)]),
+    "bn_multi_shard_reads": (_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "bn_multi_encode": (_int, [_vp, _vp, _sz, _vp, C.POINTER(_sz), _errp]),
+    "bn_multi_decode": (_int, [_vp, _vp, _sz, _sz, _vp, _errp]),
+    "bn_multi_as_2bit_batch": (_int, [_vp, _vp, _sz, _u32, _sz, _vp, _errp]),
+    "bn_multi_from_2bit_batch": (_int, [_vp, _vp, _sz, _u32, _vp, _sz, _errp]),
+    "bn_multi_hdist": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(_u64), _errp]),
+    "bn_multi_hdist_pairs": (_int, [_vp, _vp, _vp, _sz, _u32, _vp, _errp]),
+    "bn_multi_base_counts": (_int, [_vp, _vp, _sz, _sz, C.POINTER(_u64), C.POINTER(C.c_double), _errp]),
+    "bn_multi_base_counts_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _errp]),
+    "bn_multi_encode_batch": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _errp]),
+    "bn_multi_base_counts_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "bn_multi_base_counts_fixed_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "bn_multi_hdist_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "bn_multi_allreduce_u64_dev": (_int, [_vp, _vp, _int]),
+    "bn_multi_last_ms": (_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -141,4 +168,6 @@ def raise_for(rc: int, err: BnError | None = None):
     if err is not None and err.code == rc:
         raise BitnucCudaError(error_string(err))
     raise BitnucCudaError({BN_ERR_CUDA: "CUDA failure (no usable sm_100 device?)", BN_ERR_ARGUMENT: "invalid argument",
-                           BN_ERR_NOMEM: "out of memory"}.get(rc, f"bn_status {rc}"))
+                           BN_ERR_NOMEM: "out of memory",
+                           BN_ERR_COLLECTIVE: "collective failed (libnccl.so.2 missing or failing, no NVLink peer access, or a peer "
+                                              "never arrived)"}.get(rc, f"bn_status {rc}"))

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 
 import numpy as np
 
@@ -34,6 +35,11 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
+            for ref in getattr(self, "_pinned", []):  # page-locked buffers handed out by pinned_empty
+                owner = ref()
+                if owner is not None:
+                    owner.release()
+            self._pinned = []
             self.lib.bn_ctx_destroy(self.handle)
             self.handle = None
 
@@ -59,15 +65,42 @@ class Context:
         return ("x86_64", "aarch64")[self.lib.bn_ctx_compat(self.handle)]
 
     def pinned_empty(self, n: int, dtype=np.uint8) -> np.ndarray:
-        """A page-locked numpy array (freed with the context); host-pointer calls on it overlap."""
+        """A page-locked numpy array; host-pointer calls on it run at the PCIe link rate and overlap.  The allocation
+        is owned by the array (its ``base`` chain holds a ``_Pinned`` that calls ``bn_host_free`` when the last view
+        goes away) and is released at the latest by ``Context.close()`` -- do not use the array after that."""
         dtype = np.dtype(dtype)
-        p = C.c_void_p()
-        raise_for(self.lib.bn_host_alloc(self.handle, max(1, n * dtype.itemsize), C.byref(p)))
-        buf = (C.c_uint8 * (n * dtype.itemsize)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=n)
-        self._pinned = getattr(self, "_pinned", [])
-        self._pinned.append(p)
+        owner = _Pinned(self, max(1, n * dtype.itemsize))
+        arr = np.frombuffer(owner, dtype=dtype, count=n)   # arr.base -> memoryview -> owner (buffer protocol)
+        self._pinned = [r for r in getattr(self, "_pinned", []) if r() is not None]
+        self._pinned.append(weakref.ref(owner))
         return arr
+
+
+class _Pinned:
+    """Owner of one bn_host_alloc allocation, exported through the buffer protocol (PEP 688)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self._lib, self._ctx_handle, self.nbytes = ctx.lib, ctx.handle, nbytes
+        p = C.c_void_p()
+        raise_for(ctx.lib.bn_host_alloc(ctx.handle, nbytes, C.byref(p)))
+        self.ptr = p
+        self._view = (C.c_uint8 * nbytes).from_address(p.value)
+
+    def __buffer__(self, flags):
+        if self.ptr is None:
+            raise BufferError("pinned buffer already released")
+        return memoryview(self._view)
+
+    def release(self):
+        if self.ptr is not None:
+            self._lib.bn_host_free(self._ctx_handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 _default = {}
@@ -99,6 +132,12 @@ def _u64(words) -> np.ndarray:
     if isinstance(words, np.ndarray) and words.dtype == np.uint64:
         return np.ascontiguousarray(words)
     return np.array([int(w) & M64 for w in words], dtype=np.uint64)
+
+
+def _check_offsets(off: np.ndarray, n_bytes: int) -> None:
+    """Read offsets must never decrease and must end inside the byte buffer (checked before any arithmetic on them)."""
+    if off.size and (bool(np.any(off[1:] < off[:-1])) or int(off[-1]) > n_bytes):
+        raise ValueError("offsets must be non-decreasing and offsets[-1] <= len(data)")
 
 
 def _p(a: np.ndarray):
@@ -302,6 +341,7 @@ def encode_batch(data, offsets, ctx: Context | None = None, per_read_status: boo
     n = off.size - 1
     if n < 0:
         raise ValueError("offsets needs n_reads + 1 entries")
+    _check_offsets(off, a.size)   # the C ABI takes no byte-buffer length: a bad offsets array would read past `data`
     max_words = int((off[-1] - off[0]) // np.uint64(32)) + n if n else 0
     words = np.empty(max(1, max_words), dtype=np.uint64)
     wo = np.zeros(n + 1, dtype=np.uint64)
@@ -462,6 +502,7 @@ def kmers_batch(data, offsets, k: int, ctx: Context | None = None):
     n = off.size - 1
     if n < 0 or k <= 0:
         raise ValueError("offsets needs n_reads + 1 entries; window size must be non-zero")
+    _check_offsets(off, a.size)
     lens = (off[1:] - off[:-1]).astype(np.int64)
     cap = int(np.maximum(lens - k + 1, 0).sum()) if n else 0
     out = np.empty(max(1, cap), dtype=np.uint64)

@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libbitnuc_cuda.so"
-SOURCES = ["api.cu", "codec.cu", "kmer.cu", "hamming.cu", "counts.cu", "batch.cu", "split.cu", "gather.cu", "windows.cu", "fastq.cu", "synth.cu"]
+SOURCES = ["api.cu", "codec.cu", "kmer.cu", "hamming.cu", "counts.cu", "batch.cu", "split.cu", "gather.cu", "windows.cu", "fastq.cu", "synth.cu", "multi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

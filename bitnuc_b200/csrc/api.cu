@@ -2,181 +2,7 @@
 // entry points (enqueue only) and the host-pointer entry points (H2D -> kernel -> D2H; the stream-, record- and
 // read-parallel ones are chunked over a 3-stage multi-stream pipeline so PCIe copies overlap the kernels, and
 // pageable caller memory is bounced through pinned stage buffers by a multi-threaded memcpy).
-#include "../../include/bitnuc_cuda.h"
-
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-
-#include <algorithm>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <thread>
-#include <vector>
-
-#include "kernels.h"
-
-using bn::DeviceInfo;
-
-namespace {
-
-constexpr int kStages = 3;                       // pipeline depth of the host-pointer codec calls
-constexpr size_t kDefaultChunk = 64ull << 20;    // ASCII bytes per stage
-constexpr int kSlots = 8;                        // reusable device scratch buffers
-constexpr unsigned long long kNoError = ~0ull;
-
-struct Buffer {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-struct HostBuffer {  // pinned
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-}  // namespace
-
-struct bn_ctx {
-    DeviceInfo di;
-    cudaStream_t stream = nullptr;               // context stream (device-pointer calls default to it)
-    cudaStream_t stage_stream[kStages] = {};
-    cudaEvent_t stage_done[kStages] = {};
-    Buffer stage_in[kStages], stage_out[kStages];
-    Buffer stage_aux[kStages][4];                // batch calls: offsets, word offsets, per-read status, scratch
-    HostBuffer hstage_in[kStages][2], hstage_out[kStages];   // pinned bounce buffers for pageable caller memory
-    Buffer slot[kSlots];
-    unsigned long long* d_words = nullptr;       // 16 device status / accumulator words
-    unsigned long long* h_words = nullptr;       // pinned mirror
-    size_t chunk = kDefaultChunk;
-    // bn_fastq_scan -> bn_fastq_encode: the uploaded text and its index stay resident between the two calls
-    Buffer fq[7];                                // text, scratch, index scratch, seq offsets, seq lens, word offsets, out words
-    const void* fq_text = nullptr;
-    size_t fq_bytes = 0, fq_reads = 0, fq_words = 0;
-    bool fq_valid = false;
-    int fq_fasta = 0;
-    int compat = BN_COMPAT_X86_64;
-    std::mutex mu;
-};
-
-namespace {
-
-// True when the calling thread already has a CUDA context bound (it chose a device at some point).  A fresh thread
-// reports device 0 without having asked for it, and "restoring" that would create a primary context on GPU 0 --
-// hundreds of milliseconds, on a GPU that may belong to another rank.  Asked through the driver API, resolved at
-// run time so that the library has no link-time dependency on libcuda.
-bool thread_has_context() {
-    using Fn = int (*)(void**);
-    static const Fn fn = [] {
-        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-        return h ? reinterpret_cast<Fn>(dlsym(h, "cuCtxGetCurrent")) : nullptr;
-    }();
-    void* cur = nullptr;
-    return fn == nullptr || (fn(&cur) == 0 && cur != nullptr);
-}
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        const bool bound = thread_has_context();
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        if (!bound || prev == dev) prev = -1;  // nothing to restore
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-int set_err(bn_error_t* err, int code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
-    if (err) {
-        std::memset(err, 0, sizeof(*err));
-        err->code = code;
-        err->a = a;
-        err->b = b;
-        err->c = c;
-        if (code == BN_INVALID_BASE) err->base = (uint8_t)a;
-    }
-    return code;
-}
-
-int cuda_fail(bn_error_t* err, cudaError_t e) {
-    set_err(err, BN_ERR_CUDA);
-    if (err) err->cuda_error = (int32_t)e;
-    cudaGetLastError();  // clear the sticky-less error state
-    return BN_ERR_CUDA;
-}
-
-int invalid_base(bn_error_t* err, unsigned long long key, uint64_t base_offset) {
-    set_err(err, BN_INVALID_BASE, key & 0xFFu);
-    if (err) err->offset = (key >> 8) + base_offset;
-    return BN_INVALID_BASE;
-}
-
-#define BN_CUDA(expr)                                   \
-    do {                                                \
-        cudaError_t e__ = (expr);                       \
-        if (e__ != cudaSuccess) return cuda_fail(err, e__); \
-    } while (0)
-
-cudaError_t ensure(Buffer& b, size_t bytes) {
-    if (bytes <= b.cap) return cudaSuccess;
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr;
-    b.cap = 0;
-    const size_t want = (bytes + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e == cudaSuccess) b.cap = want;
-    return e;
-}
-
-cudaError_t ensure_host(HostBuffer& b, size_t bytes) {
-    if (bytes <= b.cap) return cudaSuccess;
-    if (b.p) cudaFreeHost(b.p);
-    b.p = nullptr;
-    b.cap = 0;
-    const size_t want = (bytes + 4095) & ~(size_t)4095;
-    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
-    if (e == cudaSuccess) b.cap = want;
-    return e;
-}
-
-// Caller memory that is neither pinned nor device memory: cudaMemcpyAsync on it is staged by the driver through one
-// thread (~10 GB/s here).  The host-pointer calls bounce such buffers through their own pinned stage buffers with a
-// multi-threaded memcpy instead, which keeps the PCIe pipeline fed at several times that rate.
-bool is_pageable(const void* p) {
-    if (!p) return false;
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return true;
-    }
-    return a.type == cudaMemoryTypeUnregistered;
-}
-
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-    const size_t kMinSlice = 4u << 20;
-    const unsigned t = (unsigned)std::min<size_t>(hw, bytes / kMinSlice);
-    if (t <= 1) {
-        std::memcpy(dst, src, bytes);
-        return;
-    }
-    const size_t slice = ((bytes + t - 1) / t + 4095) & ~(size_t)4095;
-    std::vector<std::thread> workers;
-    workers.reserve(t - 1);
-    for (unsigned i = 1; i < t; ++i) {
-        const size_t off = i * slice;
-        if (off >= bytes) break;
-        workers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(slice, bytes - off)); });
-    }
-    std::memcpy(dst, src, std::min(slice, bytes));
-    for (auto& w : workers) w.join();
-}
-
-cudaStream_t pick(bn_ctx* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
-
-}  // namespace
+#include "ctx.h"
 
 extern "C" {
 
@@ -216,6 +42,7 @@ int bn_error_string(const bn_error_t* e, char* buf, size_t cap) {
                                            "quality and sequence lengths differ", "text ends inside the record"};
         return snprintf(buf, cap, "record %llu: %s", (unsigned long long)e->record, what[e->a <= 4 ? e->a : 0]);
     }
+    case BN_ERR_COLLECTIVE: return snprintf(buf, cap, "collective failed (NCCL result %d)", e->cuda_error);
     default: return snprintf(buf, cap, "unknown error %d", e->code);
     }
 }
@@ -271,6 +98,8 @@ void bn_ctx_destroy(bn_ctx* ctx) {
             if (b.p) cudaFree(b.p);
         if (ctx->d_words) cudaFree(ctx->d_words);
         if (ctx->h_words) cudaFreeHost(ctx->h_words);
+        if (ctx->t0) cudaEventDestroy(ctx->t0);
+        if (ctx->t1) cudaEventDestroy(ctx->t1);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
     }
@@ -305,6 +134,33 @@ int bn_ctx_set_compat(bn_ctx* ctx, int mode) {
 }
 
 int bn_ctx_compat(const bn_ctx* ctx) { return ctx ? ctx->compat : BN_ERR_ARGUMENT; }
+
+int bn_ctx_set_timing(bn_ctx* ctx, int on) {
+    if (!ctx) return BN_ERR_ARGUMENT;
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (on && !ctx->t0) {
+        if (cudaEventCreate(&ctx->t0) != cudaSuccess || cudaEventCreate(&ctx->t1) != cudaSuccess) {
+            cudaGetLastError();
+            return BN_ERR_CUDA;
+        }
+    }
+    ctx->timing = on != 0;
+    ctx->timed = false;
+    return BN_OK;
+}
+
+int bn_last_kernel_ms(bn_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return BN_ERR_ARGUMENT;
+    *ms = 0.0f;
+    if (!ctx->timing || !ctx->timed) return BN_ERR_ARGUMENT;   // timing is off, or no device-pointer call since it was turned on
+    DeviceGuard g(ctx->di.device);
+    if (cudaEventSynchronize(ctx->t1) != cudaSuccess || cudaEventElapsedTime(ms, ctx->t0, ctx->t1) != cudaSuccess) {
+        cudaGetLastError();
+        return BN_ERR_CUDA;
+    }
+    return BN_OK;
+}
 
 int bn_dev_alloc(bn_ctx* ctx, size_t bytes, void** out) {
     bn_error_t* err = nullptr;
@@ -366,6 +222,7 @@ int bn_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_seq, size_t n, uin
     if (!ctx || !d_status || (n && (!d_seq || !d_out))) return BN_ERR_ARGUMENT;
     if (n == 0) return BN_ERR_EMPTY_ENCODE;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_encode(ctx->di, d_seq, n, d_out, reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
     return BN_OK;
 }
@@ -375,6 +232,7 @@ int bn_decode_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_w
     if (n_words < (n_bases + 31) / 32) return BN_INVALID_LENGTH;
     if (n_bases && (!d_words || !d_out)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_decode(ctx->di, d_words, n_bases, d_out, pick(ctx, stream)));
     return BN_OK;
 }
@@ -385,6 +243,7 @@ int bn_as_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_recs, size_
     if (k > 32) return BN_SEQUENCE_TOO_LONG;
     if (stride < k || !d_status || (n && (!d_out || (k && !d_recs)))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_as_2bit_batch(ctx->di, d_recs, n, k, stride, d_out, reinterpret_cast<unsigned long long*>(d_status),
                                        pick(ctx, stream)));
     return BN_OK;
@@ -396,6 +255,7 @@ int bn_from_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_packed, 
     if (k > 32) return BN_INVALID_LENGTH;
     if (stride < k || (n && k && (!d_packed || !d_out))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_from_2bit_batch(ctx->di, d_packed, n, k, d_out, stride, pick(ctx, stream)));
     return BN_OK;
 }
@@ -403,6 +263,7 @@ int bn_from_2bit_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_packed, 
 int bn_hdist_dev(bn_ctx* ctx, void* stream, const uint64_t* d_a, const uint64_t* d_b, size_t n_bases, uint64_t* d_total) {
     if (!ctx || !d_total || (n_bases && (!d_a || !d_b))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_hdist(ctx->di, d_a, d_b, n_bases, reinterpret_cast<unsigned long long*>(d_total), pick(ctx, stream)));
     return BN_OK;
 }
@@ -413,6 +274,7 @@ int bn_hdist_pairs_dev(bn_ctx* ctx, void* stream, const uint64_t* d_u, const uin
     if (len > 32) return BN_INVALID_LENGTH;
     if (n_pairs && (!d_u || !d_v || !d_out)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_hdist_pairs(ctx->di, d_u, d_v, n_pairs, len, d_out, pick(ctx, stream)));
     return BN_OK;
 }
@@ -420,6 +282,7 @@ int bn_hdist_pairs_dev(bn_ctx* ctx, void* stream, const uint64_t* d_u, const uin
 int bn_base_counts_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, size_t n_bases, uint64_t* d_counts, double* d_gc) {
     if (!ctx || !d_counts || (n_bases && !d_words)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_base_counts(ctx->di, d_words, n_bases, reinterpret_cast<unsigned long long*>(d_counts), d_gc,
                                      pick(ctx, stream)));
     return BN_OK;
@@ -430,6 +293,7 @@ int bn_base_counts_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words,
                              double* d_gc, uint64_t* d_totals) {
     if (!ctx || (n_reads && (!d_word_offsets || !d_lens))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_base_counts_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, 0, n_words,
                                            reinterpret_cast<unsigned long long*>(d_counts4), d_gc,
                                            reinterpret_cast<unsigned long long*>(d_totals), pick(ctx, stream)));
@@ -440,6 +304,7 @@ int bn_base_counts_fixed_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words,
                              uint64_t* d_counts4, double* d_gc, uint64_t* d_totals) {
     if (!ctx || (n_reads && read_len && !d_words)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_base_counts_batch(ctx->di, d_words, nullptr, nullptr, n_reads, read_len, n_reads * ((read_len + 31) / 32),
                                            reinterpret_cast<unsigned long long*>(d_counts4), d_gc,
                                            reinterpret_cast<unsigned long long*>(d_totals), pick(ctx, stream)));
@@ -453,6 +318,7 @@ int bn_encode_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const
                         void* d_scratch) {
     if (!ctx || !d_status || !d_out_word_offsets || (n_reads && (!d_offsets || !d_scratch))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_encode_batch(ctx->di, d_bytes, d_offsets, n_reads, n_bytes, d_out_words, d_out_word_offsets, d_read_status,
                                       reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
     return BN_OK;
@@ -467,6 +333,7 @@ int bn_split_packed_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words
     if (!ctx || !d_status || !d_left_offsets || !d_right_offsets || (n_reads && (!d_word_offsets || !d_lens || !d_idx || !d_scratch)))
         return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_split_packed_batch(ctx->di, d_words, d_word_offsets, d_lens, d_idx, n_reads, d_left, d_left_offsets, d_right,
                                             d_right_offsets, reinterpret_cast<unsigned long long*>(d_status), d_scratch,
                                             pick(ctx, stream)));
@@ -478,6 +345,7 @@ int bn_kmers_dev(bn_ctx* ctx, void* stream, const uint8_t* d_seq, size_t n, uint
     if (n >= k && k > 32) return BN_SEQUENCE_TOO_LONG;
     if (n >= k && (!d_seq || !d_out)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_kmer_windows(ctx->di, d_seq, n, k, d_out, reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
     return BN_OK;
 }
@@ -489,6 +357,7 @@ int bn_kmers_batch_dev(bn_ctx* ctx, void* stream, const uint8_t* d_bytes, const 
     if (!ctx || !d_status || !d_out_offsets || k == 0 || (n_reads && (!d_offsets || !d_scratch))) return BN_ERR_ARGUMENT;
     if (k > 32) return BN_SEQUENCE_TOO_LONG;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_kmer_windows_batch(ctx->di, d_bytes, d_offsets, n_reads, n_bytes, k, d_out, d_out_offsets,
                                             reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
     return BN_OK;
@@ -502,6 +371,7 @@ int bn_slice_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const
     if (!ctx || !d_status || !d_out_offsets || (nq && (!d_q_read || !d_q_start || !d_q_end || !d_scratch || !d_word_offsets || !d_lens)))
         return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_slice_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start, d_q_end, nq, d_out, d_out_offsets,
                                      reinterpret_cast<unsigned long long*>(d_status), d_scratch, pick(ctx, stream)));
     return BN_OK;
@@ -511,6 +381,7 @@ int bn_get_batch_dev(bn_ctx* ctx, void* stream, const uint64_t* d_words, const u
                      const uint64_t* d_q_read, const uint64_t* d_q_index, size_t nq, uint8_t* d_out, uint64_t* d_status) {
     if (!ctx || !d_status || (nq && (!d_q_read || !d_q_index || !d_out || !d_word_offsets || !d_lens))) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_get_batch(ctx->di, d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_index, nq, d_out,
                                    reinterpret_cast<unsigned long long*>(d_status), pick(ctx, stream)));
     return BN_OK;
@@ -522,6 +393,7 @@ size_t bn_fastq_index_scratch_bytes(size_t n_reads) { return bn::fastq_index_scr
 static int fastx_count_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, void* d_scratch, uint64_t* d_n_lines, int fasta) {
     if (!ctx || !d_n_lines || (n_bytes && (!d_text || !d_scratch)) || (reinterpret_cast<uintptr_t>(d_text) & 15u)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_fastq_count(ctx->di, d_text, n_bytes, d_scratch, d_n_lines, fasta, pick(ctx, stream)));
     return BN_OK;
 }
@@ -534,6 +406,7 @@ static int fastx_index_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, siz
         (n_bytes && (!d_text || !d_scratch)) || (n_reads && (!d_index_scratch || !d_seq_offsets || !d_seq_lens)))
         return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_fastq_index(ctx->di, d_text, n_bytes, n_reads, d_scratch, d_index_scratch, d_seq_offsets, d_seq_lens, d_word_offsets,
                                      reinterpret_cast<unsigned long long*>(d_status), fasta, pick(ctx, stream)));
     return BN_OK;
@@ -546,6 +419,7 @@ static int fastx_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, si
         (n_reads && (!d_text || !d_scratch || !d_seq_offsets || !d_seq_lens || !d_word_offsets)))
         return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_fastq_encode(ctx->di, d_text, n_bytes, n_reads, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,
                                       reinterpret_cast<unsigned long long*>(d_status), fasta, pick(ctx, stream)));
     return BN_OK;
@@ -642,6 +516,7 @@ int bn_synth_words_dev(bn_ctx* ctx, void* stream, uint64_t seed, uint64_t stream
                        uint64_t* d_out) {
     if (!ctx || (n_words && !d_out)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_synth_words(ctx->di, seed, stream_id, first_word, n_words, d_out, pick(ctx, stream)));
     return BN_OK;
 }
@@ -650,6 +525,7 @@ int bn_synth_ascii_dev(bn_ctx* ctx, void* stream, uint64_t seed, uint64_t stream
                        uint8_t* d_out) {
     if (!ctx || (n && !d_out) || (first_base % 32)) return BN_ERR_ARGUMENT;
     DeviceGuard g(ctx->di.device);
+    LaunchTimer lt(ctx, pick(ctx, stream));
     BN_LAUNCH(bn::launch_synth_ascii(ctx->di, seed, stream_id, first_base, n, d_out, pick(ctx, stream)));
     return BN_OK;
 }
@@ -672,6 +548,7 @@ int bn_encode(bn_ctx* ctx, const uint8_t* seq, size_t n, uint64_t* out, size_t* 
     }
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t chunk = ctx->chunk;
     const size_t n_chunks = (n + chunk - 1) / chunk;
     const bool in_pageable = is_pageable(seq), out_pageable = is_pageable(out);
@@ -745,6 +622,7 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
     if (!words || !out) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t chunk = ctx->chunk;
     const size_t n_chunks = (n_bases + chunk - 1) / chunk;
     const bool in_pageable = is_pageable(words), out_pageable = is_pageable(out);
@@ -853,6 +731,7 @@ int bn_as_2bit_batch(bn_ctx* ctx, const uint8_t* recs, size_t n, uint32_t k, siz
     if (n == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t per = units_per_chunk(ctx, stride, 64), n_chunks = (n + per - 1) / per;
     const bool in_pg = is_pageable(recs), out_pg = is_pageable(out);
     unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
@@ -893,6 +772,7 @@ int bn_from_2bit_batch(bn_ctx* ctx, const uint64_t* packed, size_t n, uint32_t k
     if (n == 0 || k == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t per = units_per_chunk(ctx, stride, 64), n_chunks = (n + per - 1) / per;
     const bool in_pg = is_pageable(packed), out_pg = is_pageable(out);
     const int rc = run_pipeline(
@@ -929,6 +809,7 @@ int bn_hdist(bn_ctx* ctx, const uint64_t* a, size_t n_words_a, const uint64_t* b
     if (!a || !b) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t per = units_per_chunk(ctx, 16, 2), n_chunks = (need + per - 1) / per;  // words per chunk, 16-byte aligned shards
     const bool a_pg = is_pageable(a), b_pg = is_pageable(b);
     unsigned long long sum = 0;
@@ -960,6 +841,7 @@ int bn_hdist_pairs(bn_ctx* ctx, const uint64_t* u, const uint64_t* v, size_t n_p
     if (!u || !v || !out) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t per = units_per_chunk(ctx, 16, 4), n_chunks = (n_pairs + per - 1) / per;
     const bool u_pg = is_pageable(u), v_pg = is_pageable(v), out_pg = is_pageable(out);
     const int rc = run_pipeline(
@@ -995,6 +877,7 @@ int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_
     if (n_bases == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t per = units_per_chunk(ctx, 8, 2), n_chunks = (need + per - 1) / per;
     const bool in_pg = is_pageable(words);
     const int rc = run_pipeline(
@@ -1080,6 +963,7 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
     if (n_words && !words) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     // Reads in order are cut into chunks of whole reads and run through the 3-stage pipeline: the upload of chunk c+1
     // (40 B of words + 16 B of offsets / lengths per 150 bp read) overlaps the kernel of chunk c and the download of
     // chunk c-1 (32 B + 8 B).
@@ -1174,6 +1058,7 @@ int bn_encode_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, 
     if (hi > lo && (!bytes || !out_words)) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     unsigned long long best = kNoError;  // smallest global (offset << 8 | byte)
     const bool in_pg = is_pageable(bytes), out_pg = is_pageable(out_words);
     auto retire = [&](size_t c) -> cudaError_t {
@@ -1259,6 +1144,7 @@ int bn_split_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, co
     if (n_words && (!words || !left || !right)) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     cudaStream_t st = ctx->stream;
     BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
     BN_CUDA(ensure(ctx->slot[1], (n_reads + 1) * 8));
@@ -1329,6 +1215,7 @@ int bn_slice_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uin
     if (total > out_cap || (total && !out)) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     cudaStream_t st = ctx->stream;
     const int rc = stage_packed_batch(ctx, words, n_words, word_offsets, lens, n_reads, st, err);
     if (rc != BN_OK) return rc;
@@ -1364,6 +1251,7 @@ int bn_get_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint6
     if (nq == 0) return set_err(err, BN_OK);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     cudaStream_t st = ctx->stream;
     const int rc = stage_packed_batch(ctx, words, n_words, word_offsets, lens, n_reads, st, err);
     if (rc != BN_OK) return rc;
@@ -1388,6 +1276,7 @@ int bn_kmers(bn_ctx* ctx, const uint8_t* seq, size_t n, uint32_t k, uint64_t* ou
     if (!seq || !out) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     const size_t n_win = n - k + 1;
     const size_t per = units_per_chunk(ctx, 8, 2048), n_chunks = (n_win + per - 1) / per;  // the output (8 B per window) dominates
     const bool in_pg = is_pageable(seq), out_pg = is_pageable(out);
@@ -1447,6 +1336,7 @@ int bn_kmers_batch(bn_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, s
     if (total > out_cap || (total && (!bytes || !out))) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     cudaStream_t st = ctx->stream;
     const size_t phase = lo & 15u;  // staged at the same 16-byte phase as bytes + lo, so the offsets are used unchanged
     BN_CUDA(ensure(ctx->slot[0], (hi - lo) + phase + 16));
@@ -1516,6 +1406,7 @@ static int fastx_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* 
     *n_reads = *n_words = 0;
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     ctx->fq_valid = false;
     ctx->fq_text = text;
     ctx->fq_bytes = n_bytes;
@@ -1561,6 +1452,7 @@ static int fastx_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t
     if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
     DeviceGuard g(ctx->di.device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
     // only valid right after bn_fastq_scan of the same text on this context
     if (!ctx->fq_valid || ctx->fq_fasta != fasta || ctx->fq_text != text || ctx->fq_bytes != n_bytes || ctx->fq_reads != n_reads ||
         ctx->fq_words != n_words ||

@@ -268,7 +268,8 @@ static cudaError_t launch_encode_batch_variant(const DeviceInfo& di, const uint8
                                                unsigned long long* tile_owner, cudaStream_t s) {
     const unsigned long long max_tiles = batch_max_tiles(n_reads, n_bytes, kTileWords);
     launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s, NoteTileOwners<kTileWords>{tile_owner, max_tiles});
-    static const int resident = resident_blocks(encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU>, kBThreads, di);
+    static const int per_sm = blocks_per_sm(encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU>, kBThreads);
+    const int resident = per_sm * di.sm_count;
     // the number of output words is only known on the device: launch a full persistent grid
     encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU><<<resident, kBThreads, 0, s>>>(
         d_bytes, d_offsets, n_reads, d_out_word_offsets, d_out_words, d_read_status, d_status, tile_counter, tile_owner, max_tiles);

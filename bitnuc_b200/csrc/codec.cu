@@ -59,7 +59,8 @@ cudaError_t launch_encode(const DeviceInfo& di, const uint8_t* d_seq, size_t n, 
     const unsigned long long total32 = 2ull * ((n + 31) / 32);
     uint32_t* out32 = reinterpret_cast<uint32_t*>(d_out);
     if (reinterpret_cast<uintptr_t>(d_seq) & 15u) {
-        static const int resident = resident_blocks(encode_unaligned_kernel, kThreads, di);
+        static const int per_sm = blocks_per_sm(encode_unaligned_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
         encode_unaligned_kernel<<<grid_for((total32 + kThreads - 1) / kThreads, resident), kThreads, 0, s>>>(
             d_seq, out32, n, total32, d_status);
         return cudaGetLastError();
@@ -75,7 +76,8 @@ cudaError_t launch_decode(const DeviceInfo& di, const uint64_t* d_words, size_t 
                           cudaStream_t s) {
     if (n_bases == 0) return cudaSuccess;
     if (reinterpret_cast<uintptr_t>(d_out) & 15u) {
-        static const int resident = resident_blocks(decode_unaligned_kernel, kThreads, di);
+        static const int per_sm = blocks_per_sm(decode_unaligned_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
         const unsigned long long groups = (n_bases + 3) / 4;
         decode_unaligned_kernel<<<grid_for((groups + kThreads - 1) / kThreads, resident), kThreads, 0, s>>>(
             reinterpret_cast<const uint8_t*>(d_words), d_out, n_bases);

@@ -198,7 +198,8 @@ cudaError_t launch_base_counts(const DeviceInfo& di, const uint64_t* d_words, si
     if (e != cudaSuccess) return e;
     if (n_bases) {
         if (reinterpret_cast<uintptr_t>(d_words) & 15u) {
-            static const int resident = resident_blocks(base_counts_scalar_kernel, kThreads, di);
+            static const int per_sm = blocks_per_sm(base_counts_scalar_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
             base_counts_scalar_kernel<<<grid_for(ceil_div(ceil_div(n_bases, 32), kThreads), resident), kThreads, 0, s>>>(
                 d_words, n_bases, d_counts);
         } else {

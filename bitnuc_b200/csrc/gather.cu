@@ -206,7 +206,8 @@ cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, co
     launch_exclusive_scan_cached(SliceLen{d_lens, d_q_read, d_q_start, d_q_end, n_reads, d_status}, nq, sums, cache, d_out_offsets, s);
     slice_short_kernel<<<(unsigned)ceil_div(nq, kThreads), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, nq, d_out,
                                                                            d_out_offsets, long_count, long_count + 1);
-    static const int resident = resident_blocks(slice_long_kernel, kThreads, di);
+    static const int per_sm = blocks_per_sm(slice_long_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
     slice_long_kernel<<<grid_for(ceil_div(nq, kWarpsPerBlock), resident), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, d_q_end,
                                                                                           d_out, d_out_offsets, long_count, long_count + 1);
     return cudaGetLastError();

@@ -146,7 +146,8 @@ cudaError_t launch_hdist(const DeviceInfo& di, const uint64_t* d_a, const uint64
     cudaError_t e = cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess || n_bases == 0) return e;
     if ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b)) & 15u) {
-        static const int resident = resident_blocks(hdist_sum_scalar_kernel, kThreads, di);
+        static const int per_sm = blocks_per_sm(hdist_sum_scalar_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
         hdist_sum_scalar_kernel<<<grid_for(ceil_div(ceil_div(n_bases, 32), kThreads), resident), kThreads, 0, s>>>(
             d_a, d_b, n_bases, d_total);
         return cudaGetLastError();
@@ -175,7 +176,8 @@ cudaError_t launch_hdist_pairs(const DeviceInfo& di, const uint64_t* d_u, const 
         first_scalar = n_vec * 2;
     }
     if (first_scalar < n_pairs) {
-        static const int resident = resident_blocks(hdist_pairs_scalar_kernel, kThreads, di);
+        static const int per_sm = blocks_per_sm(hdist_pairs_scalar_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
         hdist_pairs_scalar_kernel<<<grid_for(ceil_div(n_pairs - first_scalar, kThreads), resident), kThreads, 0, s>>>(
             d_u, d_v, d_out, first_scalar, n_pairs, mlo, mhi);
     }

@@ -366,7 +366,8 @@ cudaError_t launch_as_2bit_batch(const DeviceInfo& di, const uint8_t* d_recs, si
         as_2bit_staged_kernel<<<(unsigned)ceil_div(n, kStageRecords), kThreads, 0, s>>>(d_recs, n, k, (unsigned)stride, d_out,
                                                                                          d_status);
     } else {
-        static const int resident = resident_blocks(as_2bit_generic_kernel, kThreads, di);
+        static const int per_sm = blocks_per_sm(as_2bit_generic_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
         as_2bit_generic_kernel<<<grid_for(ceil_div(n, kThreads), resident), kThreads, 0, s>>>(d_recs, n, k, stride, d_out,
                                                                                                d_status);
     }
@@ -387,7 +388,8 @@ cudaError_t launch_from_2bit_batch(const DeviceInfo& di, const uint64_t* d_packe
         from_2bit_tight_kernel<<<(unsigned)ceil_div(chunks + 1, kKmerThreads * kTightChunks), kKmerThreads, 0, s>>>(d_packed, n, k,
                                                                                                                  d_out);
     } else {
-        static const int resident = resident_blocks(from_2bit_generic_kernel, kThreads, di);
+        static const int per_sm = blocks_per_sm(from_2bit_generic_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
         from_2bit_generic_kernel<<<grid_for(ceil_div(n, kThreads), resident), kThreads, 0, s>>>(d_packed, n, k, d_out, stride);
     }
     return cudaGetLastError();

@@ -8,12 +8,15 @@ namespace bn {
 constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 
+// CTAs of `kernel` resident per SM.  A property of the kernel on sm_100a (the only target), so it is cached per
+// process by the launchers; the persistent grid is this times the SM count of the context's own device (contexts on
+// different devices of one host must not share a cached grid size).
 template <typename K>
-static int resident_blocks(K kernel, int threads, const DeviceInfo& di, size_t dyn_smem = 0) {
+static int blocks_per_sm(K kernel, int threads, size_t dyn_smem = 0) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1)
         per_sm = 1;
-    return per_sm * di.sm_count;
+    return per_sm;
 }
 
 static inline unsigned grid_for(unsigned long long work_blocks, int resident) {

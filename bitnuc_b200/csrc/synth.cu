@@ -49,7 +49,8 @@ static unsigned long long stream_base(uint64_t seed, uint64_t stream_id) {
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,
                                size_t n_words, uint64_t* d_out, cudaStream_t s) {
     if (n_words == 0) return cudaSuccess;
-    static const int resident = resident_blocks(synth_words_kernel, kThreads, di);
+    static const int per_sm = blocks_per_sm(synth_words_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
     synth_words_kernel<<<grid_for(ceil_div(n_words, kThreads), resident), kThreads, 0, s>>>(stream_base(seed, stream_id),
                                                                                              first_word, n_words, d_out);
     return cudaGetLastError();
@@ -58,7 +59,8 @@ cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t str
 cudaError_t launch_synth_ascii(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_base,
                                size_t n, uint8_t* d_out, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    static const int resident = resident_blocks(synth_ascii_kernel, kThreads, di);
+    static const int per_sm = blocks_per_sm(synth_ascii_kernel, kThreads);
+    const int resident = per_sm * di.sm_count;
     const int aligned = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
     synth_ascii_kernel<<<grid_for(ceil_div(ceil_div(n, 32), kThreads), resident), kThreads, 0, s>>>(
         stream_base(seed, stream_id), first_base / 32, n, d_out, aligned);

@@ -34,12 +34,20 @@ def _ctx_for(t: torch.Tensor) -> api.Context:
     return api.default_context(t.device.index)
 
 
+def _want(t: torch.Tensor, dtype, numel: int, what: str) -> None:
+    """The *_dev entry points take raw pointers: refuse tensors whose dtype, layout or size would make a kernel read or
+    write outside them."""
+    if t.dtype != dtype or not t.is_contiguous() or t.numel() < numel:
+        raise ValueError(f"{what}: need a contiguous {dtype} tensor of at least {numel} elements, got {t.dtype}[{t.numel()}]"
+                         f"{'' if t.is_contiguous() else ' (not contiguous)'}")
+
+
 class Status:
     """Device-side validation status: min over invalid bases of (offset << 8 | byte)."""
 
     def __init__(self, device):
         self.word = torch.empty(1, dtype=torch.int64, device=device)
-        self.ctx = api.default_context(torch.device(device).index or 0)
+        self.ctx = api.default_context(self.word.device.index)   # a bare "cuda" resolves to the current device
 
     def check(self):
         """Synchronises the current stream; raises ``NucleotideError.InvalidBase`` if set."""
@@ -81,8 +89,13 @@ def decode(words: torch.Tensor, n_bases: int, out: torch.Tensor | None = None) -
 def as_2bit_batch(recs: torch.Tensor, n: int, k: int, stride: int | None = None, out=None, status=None):
     ctx = _ctx_for(recs)
     stride = k if stride is None else stride
+    if n < 0 or stride < k:
+        raise ValueError("n >= 0 and stride >= k")
+    if 0 < k <= 32 and n:
+        _want(recs, torch.uint8, (n - 1) * stride + k, "as_2bit_batch(recs)")
     if out is None:
         out = torch.empty(n, dtype=torch.int64, device=recs.device)
+    _want(out, torch.int64, n, "as_2bit_batch(out)")
     status = status or Status(recs.device)
     rc = ctx.lib.bn_as_2bit_batch_dev(ctx.handle, _stream(), _ptr(recs), n, k, stride, _ptr(out), _ptr(status.word))
     if rc == 2:
@@ -95,8 +108,13 @@ def from_2bit_batch(packed: torch.Tensor, k: int, stride: int | None = None, out
     ctx = _ctx_for(packed)
     stride = k if stride is None else stride
     n = packed.numel()
+    if stride < k:
+        raise ValueError("stride >= k")
+    _want(packed, torch.int64, n, "from_2bit_batch(packed)")
     if out is None:
         out = torch.zeros((n - 1) * stride + k if n and k <= 32 else 0, dtype=torch.uint8, device=packed.device)
+    elif n and 0 < k <= 32:
+        _want(out, torch.uint8, (n - 1) * stride + k, "from_2bit_batch(out)")
     rc = ctx.lib.bn_from_2bit_batch_dev(ctx.handle, _stream(), _ptr(packed), n, k, _ptr(out), stride)
     if rc == 3:
         raise _lib.NucleotideError.InvalidLength(k)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BN_ABI_VERSION 1
+#define BN_ABI_VERSION 2
 
 typedef enum bn_status {
     BN_OK = 0,
@@ -50,7 +50,8 @@ typedef enum bn_status {
     BN_ERR_EMPTY_ENCODE = -3,   /* encode of an empty sequence: the reference panics
                                    (src/utils/packing/avx.rs:138); bindings should panic too */
     BN_ERR_NOMEM = -4,
-    BN_ERR_FASTQ = -5           /* malformed FASTQ / FASTA text (bn_fastq_*, bn_fasta_*): err->record = the record, err->a = bn_fastq_fault */
+    BN_ERR_FASTQ = -5,          /* malformed FASTQ / FASTA text (bn_fastq_*, bn_fasta_*): err->record = the record, err->a = bn_fastq_fault */
+    BN_ERR_COLLECTIVE = -6      /* bn_multi_*: NCCL missing / failed (err->cuda_error = ncclResult_t) or a peer never arrived */
 } bn_status;
 
 typedef enum bn_fastq_fault {
@@ -100,6 +101,13 @@ int bn_ctx_set_chunk_bytes(bn_ctx *ctx, size_t bytes);
 typedef enum bn_compat { BN_COMPAT_X86_64 = 0, BN_COMPAT_AARCH64 = 1 } bn_compat;
 int bn_ctx_set_compat(bn_ctx *ctx, int mode);
 int bn_ctx_compat(const bn_ctx *ctx);
+
+/* Device timing of the device-pointer calls (SURVEY.md 8b `bn_last_kernel_ms`).  With timing on, every *_dev call on
+ * this context brackets the launches it enqueues with two CUDA events on the stream it uses; bn_last_kernel_ms waits
+ * for the last such call and returns its duration (the kernels only: no copies, no host time).  Off by default.
+ * BN_ERR_ARGUMENT when timing is off or nothing has been timed yet. */
+int bn_ctx_set_timing(bn_ctx *ctx, int on);
+int bn_last_kernel_ms(bn_ctx *ctx, float *ms);
 
 /* Memory helpers for callers without their own CUDA runtime binding. */
 int bn_dev_alloc(bn_ctx *ctx, size_t bytes, void **out);
@@ -293,6 +301,75 @@ int bn_kmers_dev(bn_ctx *ctx, void *stream, const uint8_t *d_seq, size_t n, uint
 /* Synchronises `stream`, reads *d_status back and translates it: BN_OK, or BN_INVALID_BASE with
  * err->base / err->offset filled (record/a are filled by the host-pointer wrappers). */
 int bn_status_fetch(bn_ctx *ctx, void *stream, const uint64_t *d_status, bn_error_t *err);
+
+/* ------------------------------------------------------------------ multi-GPU (one process, N devices) ------ */
+/* The path shards with no exchange step: every 32-base word, record, pair and read is independent
+ * (src/utils/packing/avx.rs:138-145 carries nothing between words).  A bn_multi owns one bn_ctx per device (own
+ * streams, own pinned staging) and one host worker thread per device; a bn_multi_* host-pointer call cuts its input
+ * into contiguous shards -- base ranges on multiples of 64 bases (64 B of ASCII / 16 B packed, so every shard keeps
+ * 128-bit accesses), records / pairs / reads by index, variable-length reads by byte volume on read boundaries -- and
+ * runs the single-device call of the same name on every shard at once.  Results are those of the single-device call
+ * on the whole input: the first failing shard in input order reports the error, with offsets and record indices
+ * rebased to the caller's buffers.  The reference has nothing here (it is single-threaded).
+ *
+ * One collective exists on the path: the sum of the four base counters (and of the hdist total) over the shards.
+ *   BN_REDUCE_NCCL  ncclAllReduce(4 x uint64, ncclSum) over per-device communicators from ncclCommInitAll, grouped
+ *                   (libnccl.so.2 is resolved with dlopen at bn_multi_create: no link-time dependency);
+ *   BN_REDUCE_P2P   our own all-reduce kernel over NVLink peer memory: every device stores its four counters into a
+ *                   mailbox on every peer and sums the n mailboxes it received -- one 32-thread launch per device
+ *                   instead of NCCL's, for a 32-byte message that is pure latency.  Also the mode for device lists
+ *                   that name one device twice (NCCL refuses those), which is how a one-GPU box tests the sharding.
+ * After a reduction every device holds the global value. */
+typedef struct bn_multi bn_multi;
+typedef enum bn_reduce { BN_REDUCE_NCCL = 0, BN_REDUCE_P2P = 1 } bn_reduce;
+
+/* devs = n device ordinals (NULL: devices 0..n-1; n <= 0: every visible device). */
+int bn_multi_create(const int *devs, int n, int reduce, bn_multi **out);
+void bn_multi_destroy(bn_multi *m);
+int bn_multi_size(const bn_multi *m);
+bn_ctx *bn_multi_ctx(bn_multi *m, int i);            /* the context of shard i (device-resident calls, memory helpers) */
+int bn_multi_reduce(const bn_multi *m);              /* bn_reduce in use */
+int bn_multi_nccl_version(const bn_multi *m);        /* ncclGetVersion() of the library in use, 0 in P2P mode */
+int bn_multi_set_chunk_bytes(bn_multi *m, size_t bytes);
+int bn_multi_synchronize(bn_multi *m);               /* all streams of all devices; reports a collective that timed out */
+
+/* The shard plan, for callers that place device-resident shards themselves: starts[n+1], shard i = units
+ * [starts[i], starts[i+1]).  bn_multi_shard_units cuts n_units into near-equal ranges whose interior cuts are multiples
+ * of `align` (bases: 64); bn_multi_shard_reads cuts an offset-indexed read batch into ranges of near-equal byte volume
+ * on read boundaries (the first read whose start reaches the ideal cut). */
+int bn_multi_shard_units(const bn_multi *m, size_t n_units, size_t align, size_t *starts);
+int bn_multi_shard_reads(const bn_multi *m, const uint64_t *offsets, size_t n_reads, size_t *starts);
+
+/* Host-pointer calls: the signatures and results of bn_encode ... bn_encode_batch with a bn_multi in place of the
+ * bn_ctx.  bn_multi_base_counts[_batch] reduce the four counters with the collective above; bn_multi_hdist sums its
+ * per-shard totals on the host (one uint64 per shard is already there). */
+int bn_multi_encode(bn_multi *m, const uint8_t *seq, size_t n, uint64_t *out, size_t *n_words, bn_error_t *err);
+int bn_multi_decode(bn_multi *m, const uint64_t *words, size_t n_words, size_t n_bases, uint8_t *out, bn_error_t *err);
+int bn_multi_as_2bit_batch(bn_multi *m, const uint8_t *recs, size_t n, uint32_t k, size_t stride, uint64_t *out, bn_error_t *err);
+int bn_multi_from_2bit_batch(bn_multi *m, const uint64_t *packed, size_t n, uint32_t k, uint8_t *out, size_t stride, bn_error_t *err);
+int bn_multi_hdist(bn_multi *m, const uint64_t *a, size_t n_words_a, const uint64_t *b, size_t n_words_b, size_t n_bases, uint64_t *total, bn_error_t *err);
+int bn_multi_hdist_pairs(bn_multi *m, const uint64_t *u, const uint64_t *v, size_t n_pairs, uint32_t len, uint32_t *out, bn_error_t *err);
+int bn_multi_base_counts(bn_multi *m, const uint64_t *words, size_t n_words, size_t n_bases, uint64_t counts[4], double *gc, bn_error_t *err);
+int bn_multi_base_counts_batch(bn_multi *m, const uint64_t *words, size_t n_words, const uint64_t *word_offsets, const uint64_t *lens, size_t n_reads, uint64_t *counts4, double *gc, uint64_t totals[4], bn_error_t *err);
+int bn_multi_encode_batch(bn_multi *m, const uint8_t *bytes, const uint64_t *offsets, size_t n_reads, uint64_t *out_words, uint64_t *out_word_offsets, uint32_t *read_status, bn_error_t *err);
+
+/* Device-resident sharded reductions: shard i lives on the device of bn_multi_ctx(m, i); every argument is an array of
+ * n per-shard values.  Enqueue-only on each context's own stream (order other work against it with bn_ctx_stream),
+ * all devices are launched before anything waits, and the collective follows on the same streams: when the streams
+ * drain, d_counts[i] / d_totals[i] / d_total[i] on EVERY device hold the global [A,C,G,T] / total and d_gc[i] (array or
+ * entries may be NULL) the global gc_content from those counts, (gc as f64 / len as f64) * 100.0 (analysis.rs:14).
+ *   bn_multi_base_counts_dev        one long packed sequence, shard i = n_bases[i] bases at d_words[i]
+ *   bn_multi_base_counts_fixed_dev  n_reads[i] reads of read_len bases each at d_words[i]; per-read d_counts4[i] /
+ *                                   d_gc_reads[i] (arrays or entries may be NULL) stay local to their shard
+ *   bn_multi_hdist_dev              whole-sequence mismatch total of shard pairs (d_a[i], d_b[i]) */
+int bn_multi_base_counts_dev(bn_multi *m, const uint64_t *const *d_words, const size_t *n_bases, uint64_t *const *d_counts, double *const *d_gc);
+int bn_multi_base_counts_fixed_dev(bn_multi *m, const uint64_t *const *d_words, const size_t *n_reads, size_t read_len, uint64_t *const *d_counts4, double *const *d_gc_reads, uint64_t *const *d_totals, double *const *d_gc);
+int bn_multi_hdist_dev(bn_multi *m, const uint64_t *const *d_a, const uint64_t *const *d_b, const size_t *n_bases, uint64_t *const *d_total);
+/* The collective alone, in place on n per-device buffers of count <= 4 uint64_t each (sum). */
+int bn_multi_allreduce_u64_dev(bn_multi *m, uint64_t *const *d_buf, int count);
+/* Device time of the last bn_multi_*_dev call per shard: ms[i] = first launch to end of the collective on device i's
+ * stream (CUDA events).  The job's time is the maximum over i.  Synchronises those streams. */
+int bn_multi_last_ms(bn_multi *m, float *ms);
 
 /* ------------------------------------------------------------------ synthetic input --------- */
 /* Counter-based generator used by the benchmarks and parity tests: word j of

@@ -7,7 +7,7 @@ fn main() {
     let csrc = root.join("bitnuc_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let sources = ["api.cu", "codec.cu", "kmer.cu", "hamming.cu", "counts.cu", "batch.cu", "split.cu", "gather.cu", "windows.cu", "synth.cu"];
+    let sources = ["api.cu", "codec.cu", "kmer.cu", "hamming.cu", "counts.cu", "batch.cu", "split.cu", "gather.cu", "windows.cu", "fastq.cu", "synth.cu", "multi.cu"];
     let mut objects = Vec::new();
     for src in sources {
         let obj = out.join(format!("{src}.o"));

@@ -39,6 +39,7 @@ pub(crate) fn check(rc: i32, e: &bn_error_t) -> Result<(), NucleotideError> {
         5 => Err(NucleotideError::InvalidRange { start: e.a as usize, end: e.b as usize, length: e.c as usize }),
         6 => Err(NucleotideError::Unsupported),
         -3 => panic!("attempt to subtract with overflow"), // encode(b""): what the reference does (packing/avx.rs:138)
+        -6 => panic!("bitnuc-cuda: collective failed (NCCL result {})", e.cuda_error),
         other => panic!("bitnuc-cuda: CUDA/argument failure {} (cuda error {})", other, e.cuda_error),
     }
 }

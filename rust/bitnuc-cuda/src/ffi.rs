@@ -22,8 +22,16 @@ pub struct bn_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct bn_multi {
+    _private: [u8; 0],
+}
+
 pub const BN_OK: c_int = 0;
 pub const BN_ERR_EMPTY_ENCODE: c_int = -3;
+pub const BN_ERR_COLLECTIVE: c_int = -6;
+pub const BN_REDUCE_NCCL: c_int = 0;
+pub const BN_REDUCE_P2P: c_int = 1;
 
 extern "C" {
     pub fn bn_abi_version() -> c_int;
@@ -95,4 +103,32 @@ extern "C" {
     pub fn bn_status_fetch(ctx: *mut bn_ctx, stream: *mut c_void, d_status: *const u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_synth_words_dev(ctx: *mut bn_ctx, stream: *mut c_void, seed: u64, stream_id: u64, first_word: u64, n_words: usize, d_out: *mut u64) -> c_int;
     pub fn bn_synth_ascii_dev(ctx: *mut bn_ctx, stream: *mut c_void, seed: u64, stream_id: u64, first_base: u64, n: usize, d_out: *mut u8) -> c_int;
+    pub fn bn_ctx_set_timing(ctx: *mut bn_ctx, on: c_int) -> c_int;
+    pub fn bn_last_kernel_ms(ctx: *mut bn_ctx, ms: *mut f32) -> c_int;
+
+    // multi-GPU: one process, N devices (include/bitnuc_cuda.h, "multi-GPU")
+    pub fn bn_multi_create(devs: *const c_int, n: c_int, reduce: c_int, out: *mut *mut bn_multi) -> c_int;
+    pub fn bn_multi_destroy(m: *mut bn_multi);
+    pub fn bn_multi_size(m: *const bn_multi) -> c_int;
+    pub fn bn_multi_ctx(m: *mut bn_multi, i: c_int) -> *mut bn_ctx;
+    pub fn bn_multi_reduce(m: *const bn_multi) -> c_int;
+    pub fn bn_multi_nccl_version(m: *const bn_multi) -> c_int;
+    pub fn bn_multi_set_chunk_bytes(m: *mut bn_multi, bytes: usize) -> c_int;
+    pub fn bn_multi_synchronize(m: *mut bn_multi) -> c_int;
+    pub fn bn_multi_shard_units(m: *const bn_multi, n_units: usize, align: usize, starts: *mut usize) -> c_int;
+    pub fn bn_multi_shard_reads(m: *const bn_multi, offsets: *const u64, n_reads: usize, starts: *mut usize) -> c_int;
+    pub fn bn_multi_encode(m: *mut bn_multi, seq: *const u8, n: usize, out: *mut u64, n_words: *mut usize, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_decode(m: *mut bn_multi, words: *const u64, n_words: usize, n_bases: usize, out: *mut u8, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_as_2bit_batch(m: *mut bn_multi, recs: *const u8, n: usize, k: u32, stride: usize, out: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_from_2bit_batch(m: *mut bn_multi, packed: *const u64, n: usize, k: u32, out: *mut u8, stride: usize, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_hdist(m: *mut bn_multi, a: *const u64, n_words_a: usize, b: *const u64, n_words_b: usize, n_bases: usize, total: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_hdist_pairs(m: *mut bn_multi, u: *const u64, v: *const u64, n_pairs: usize, len: u32, out: *mut u32, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_base_counts(m: *mut bn_multi, words: *const u64, n_words: usize, n_bases: usize, counts: *mut u64, gc: *mut f64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_base_counts_batch(m: *mut bn_multi, words: *const u64, n_words: usize, word_offsets: *const u64, lens: *const u64, n_reads: usize, counts4: *mut u64, gc: *mut f64, totals: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_encode_batch(m: *mut bn_multi, bytes: *const u8, offsets: *const u64, n_reads: usize, out_words: *mut u64, out_word_offsets: *mut u64, read_status: *mut u32, err: *mut bn_error_t) -> c_int;
+    pub fn bn_multi_base_counts_dev(m: *mut bn_multi, d_words: *const *const u64, n_bases: *const usize, d_counts: *const *mut u64, d_gc: *const *mut f64) -> c_int;
+    pub fn bn_multi_base_counts_fixed_dev(m: *mut bn_multi, d_words: *const *const u64, n_reads: *const usize, read_len: usize, d_counts4: *const *mut u64, d_gc_reads: *const *mut f64, d_totals: *const *mut u64, d_gc: *const *mut f64) -> c_int;
+    pub fn bn_multi_hdist_dev(m: *mut bn_multi, d_a: *const *const u64, d_b: *const *const u64, n_bases: *const usize, d_total: *const *mut u64) -> c_int;
+    pub fn bn_multi_allreduce_u64_dev(m: *mut bn_multi, d_buf: *const *mut u64, count: c_int) -> c_int;
+    pub fn bn_multi_last_ms(m: *mut bn_multi, ms: *mut f32) -> c_int;
 }

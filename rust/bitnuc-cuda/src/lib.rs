@@ -8,8 +8,10 @@
 //! NOT COMPILED IN THE AUTHORING ENVIRONMENT (no Rust toolchain there); see INTEGRATION.md.
 mod error;
 pub mod ffi;
+pub mod multi;
 
 pub use error::NucleotideError;
+pub use multi::{Multi, Reduce};
 use error::check;
 use ffi::*;
 use std::cell::RefCell;

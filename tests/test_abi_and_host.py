@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.bn_abi_version() == 1
+    assert lib.bn_abi_version() == 2
     assert lib.bn_device_count() >= 0
     assert lib.bn_encode_batch_scratch_bytes(1, 100) >= 16
     assert C.sizeof(L.BnError) == 56  # layout of bn_error_t in the header

@@ -51,6 +51,14 @@ class _Err(C.Structure):
     _fields_ = [("code", C.c_int32), ("a", C.c_uint64), ("b", C.c_uint64), ("c", C.c_uint64)]
 
 
+class _BenchDesc(C.Structure):
+    _fields_ = [("op", C.c_int32), ("path", C.c_int32), ("n_units", C.c_uint64), ("k", C.c_uint64), ("stride", C.c_uint64),
+                ("in0", C.c_void_p), ("in1", C.c_void_p), ("out0", C.c_void_p), ("out1", C.c_void_p)]
+
+
+OP_ENCODE, OP_DECODE, OP_AS_2BIT, OP_FROM_2BIT, OP_HDIST, OP_HDIST_PAIRS, OP_BASE_COUNTS_GC, OP_ENCODE_BATCH = range(8)
+
+
 def build(native: bool = False, force: bool = False) -> Path:
     """Compile the oracle with gcc (seconds).  Building the checker is not using it."""
     src = _HERE / "bitnuc_oracle.c"
@@ -97,6 +105,7 @@ def lib():
             "orc_bench_codec": (C.c_double, [C.c_void_p, sz, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_void_p, C.c_void_p]),
             "orc_have_avx2": (C.c_int, []),
+            "orc_bench_op": (C.c_int, [C.POINTER(_BenchDesc), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), u64p]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -390,3 +399,18 @@ class CodecBench:
 def bench_codec(seq: np.ndarray, threads: int, reps: int, path: int = PATH_AVX2,
                 do_encode: bool = True, do_decode: bool = True) -> float:
     return CodecBench(seq, threads).run(reps, path, do_encode, do_decode)
+
+
+def bench_op(op: int, n_units: int, *, in0: np.ndarray, in1: np.ndarray | None = None, out0: np.ndarray | None = None,
+             out1: np.ndarray | None = None, k: int = 0, stride: int = 0, path: int = PATH_AVX2, threads: int = 1,
+             reps: int = 5, pin: bool = True):
+    """Times one op of the reference's CPU path (orc_bench_op): returns (seconds per repetition, checksum).
+    Buffers belong to the caller and are reused by every repetition (touch outputs before timing)."""
+    d = _BenchDesc(op, path, n_units, k, stride, _ptr(in0), _ptr(in1) if in1 is not None else None,
+                   _ptr(out0) if out0 is not None else None, _ptr(out1) if out1 is not None else None)
+    times = (C.c_double * reps)()
+    check = C.c_uint64(0)
+    rc = lib().orc_bench_op(C.byref(d), threads, reps, int(pin), times, C.byref(check))
+    if rc:
+        raise RuntimeError(f"orc_bench_op({op}) failed: {rc}")
+    return list(times), int(check.value)

@@ -16,6 +16,7 @@
 
 #include <immintrin.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -635,4 +636,278 @@ double orc_bench_codec(const uint8_t *seq, size_t n, int n_threads, int reps, in
         if (best < 0 || dt < best) best = dt;
     }
     return best;
+}
+
+/* ================================================================== timed baselines, all ops == */
+/* bench.py's cpu_baseline legs for the rows other than the codec:
+ * the caller's loop over the reference's per-item functions, chunked across pinned threads by the harness
+ * (the reference itself is single-threaded).  Threads are created once and meet at a barrier around
+ * every repetition, so thread start-up is never inside a timed repetition. */
+
+/* src/sequence.rs:198-212 + :260-262 as the reference runs it inside analysis.rs: to_vec() allocates a
+ * Vec::with_capacity(len) and pushes one checked get() per base. */
+static uint8_t *to_vec_ref(const uint64_t *data, size_t length) {
+    uint8_t *v = (uint8_t *)malloc(length ? length : 1);
+    size_t n = 0;
+    for (size_t i = 0; i < length; ++i) {
+        uint8_t b;
+        if (orc_seq_get(data, length, i, &b, NULL)) break; /* `?` */
+        v[n++] = b;
+    }
+    return v;
+}
+
+/* src/utils/analysis.rs:19-39 with its own to_vec() */
+static void base_counts_ref(const uint64_t *data, size_t length, uint64_t counts[4]) {
+    uint8_t *seq = to_vec_ref(data, length);
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (size_t i = 0; i < length; ++i) {
+        switch (seq[i]) {
+        case 'A': counts[0]++; break;
+        case 'C': counts[1]++; break;
+        case 'G': counts[2]++; break;
+        case 'T': counts[3]++; break;
+        default: continue;
+        }
+    }
+    free(seq);
+}
+
+/* src/utils/analysis.rs:3-17 with its own (second) to_vec() */
+static double gc_content_ref(const uint64_t *data, size_t length) {
+    uint8_t *seq = to_vec_ref(data, length);
+    double r = 0.0;
+    if (length) {
+        size_t gc = 0;
+        for (size_t i = 0; i < length; ++i) gc += (seq[i] == 'G' || seq[i] == 'C');
+        volatile double q = (double)gc / (double)length;
+        r = q * 100.0;
+    }
+    free(seq);
+    return r;
+}
+
+typedef struct {
+    const orc_bench_desc *d;
+    pthread_barrier_t *bar;
+    int tid, n_threads, reps, cpu, rc;
+    uint64_t check;
+} op_job;
+
+static void op_range(const orc_bench_desc *d, int tid, int n_threads, size_t align, size_t *u0, size_t *u1) {
+    size_t n = d->n_units;
+    size_t blocks = (n + align - 1) / align;
+    size_t per = (blocks + (size_t)n_threads - 1) / (size_t)n_threads;
+    size_t b0 = (size_t)tid * per, b1 = b0 + per;
+    *u0 = b0 * align < n ? b0 * align : n;
+    *u1 = b1 * align < n ? b1 * align : n;
+}
+
+__attribute__((target("avx2,popcnt"))) static int op_run_avx2(const orc_bench_desc *d, size_t u0, size_t u1, uint64_t *check) {
+    orc_error e;
+    switch (d->op) {
+    case ORC_OP_AS_2BIT: {
+        const uint8_t *recs = (const uint8_t *)d->in0;
+        uint64_t *out = (uint64_t *)d->out0;
+        size_t total = (d->n_units - 1) * d->stride + d->k; /* bytes readable in the record buffer */
+        for (size_t r = u0; r < u1; ++r) {
+            int rc = as_2bit_avx2_impl(recs + r * d->stride, d->k, total - r * d->stride, &out[r], &e);
+            if (rc) return rc;
+        }
+        *check = u1 > u0 ? out[u1 - 1] : 0;
+        return 0;
+    }
+    case ORC_OP_FROM_2BIT: {
+        const uint64_t *in = (const uint64_t *)d->in0;
+        uint8_t *out = (uint8_t *)d->out0;
+        for (size_t r = u0; r < u1; ++r) {
+            int rc = orc_from_2bit_avx2(in[r], d->k, out + r * d->stride, &e);
+            if (rc) return rc;
+        }
+        *check = u1 > u0 ? out[(u1 - 1) * d->stride] : 0;
+        return 0;
+    }
+    default:
+        return -3;
+    }
+}
+
+static int op_run(const orc_bench_desc *d, size_t u0, size_t u1, uint64_t *check) {
+    orc_error e;
+    *check = 0;
+    if (u1 <= u0) return 0;
+    switch (d->op) {
+    case ORC_OP_ENCODE: {
+        size_t nw;
+        uint64_t *out = (uint64_t *)d->out0 + u0 / 32;
+        int rc = (d->path == ORC_PATH_AVX2 ? orc_encode_avx2 : orc_encode)((const uint8_t *)d->in0 + u0, u1 - u0, out, &nw, &e);
+        *check = out[nw ? nw - 1 : 0];
+        return rc;
+    }
+    case ORC_OP_DECODE: {
+        const uint64_t *in = (const uint64_t *)d->in0 + u0 / 32;
+        uint8_t *out = (uint8_t *)d->out0 + u0;
+        if (d->path == ORC_PATH_AVX2) {
+            decode_avx2(in, u1 - u0, out);
+        } else {
+            size_t n_out;
+            int rc = orc_decode(in, (u1 - u0 + 31) / 32, u1 - u0, out, &n_out, ORC_PATH_NAIVE, &e);
+            if (rc) return rc;
+        }
+        *check = out[u1 - u0 - 1];
+        return 0;
+    }
+    case ORC_OP_AS_2BIT:
+        if (d->path == ORC_PATH_AVX2) return op_run_avx2(d, u0, u1, check);
+        {
+            const uint8_t *recs = (const uint8_t *)d->in0;
+            uint64_t *out = (uint64_t *)d->out0;
+            for (size_t r = u0; r < u1; ++r) {
+                int rc = orc_as_2bit(recs + r * d->stride, d->k, &out[r], &e);
+                if (rc) return rc;
+            }
+            *check = out[u1 - 1];
+            return 0;
+        }
+    case ORC_OP_FROM_2BIT:
+        if (d->path == ORC_PATH_AVX2) return op_run_avx2(d, u0, u1, check);
+        {
+            const uint64_t *in = (const uint64_t *)d->in0;
+            uint8_t *out = (uint8_t *)d->out0;
+            for (size_t r = u0; r < u1; ++r) {
+                int rc = orc_from_2bit(in[r], d->k, out + r * d->stride, &e);
+                if (rc) return rc;
+            }
+            *check = out[(u1 - 1) * d->stride];
+            return 0;
+        }
+    case ORC_OP_HDIST: { /* units = bases; the thread's slice is a whole-sequence hdist call of its own */
+        uint32_t t32;
+        uint64_t t64;
+        size_t nw = (u1 - u0 + 31) / 32;
+        int rc = orc_hdist((const uint64_t *)d->in0 + u0 / 32, nw, (const uint64_t *)d->in1 + u0 / 32, nw, u1 - u0, &t32, &t64,
+                           d->path, &e);
+        *check = t64;
+        return rc;
+    }
+    case ORC_OP_HDIST_PAIRS: {
+        const uint64_t *u = (const uint64_t *)d->in0, *v = (const uint64_t *)d->in1;
+        uint32_t *out = (uint32_t *)d->out0;
+        uint64_t sum = 0;
+        for (size_t r = u0; r < u1; ++r) {
+            int rc = orc_hdist_scalar(u[r], v[r], d->k, &out[r], &e);
+            if (rc) return rc;
+            sum += out[r];
+        }
+        *check = sum;
+        return 0;
+    }
+    case ORC_OP_ENCODE_BATCH: { /* the caller's loop of PackedSequence::new(read) (sequence.rs:40-52): encode onto fresh words */
+        const uint8_t *bytes = (const uint8_t *)d->in0;
+        const uint64_t *off = (const uint64_t *)d->in1, *woff = (const uint64_t *)d->out1;
+        uint64_t *words = (uint64_t *)d->out0;
+        uint64_t sum = 0;
+        for (size_t r = u0; r < u1; ++r) {
+            size_t len = off[r + 1] - off[r], nw = 0;
+            if (len == 0) continue; /* PackedSequence::new(b"") -> empty data, no encode call (sequence.rs:42-46) */
+            int rc = (d->path == ORC_PATH_AVX2 ? orc_encode_avx2 : orc_encode)(bytes + off[r], len, words + woff[r], &nw, &e);
+            if (rc) return rc;
+            sum += nw;
+        }
+        *check = sum;
+        return 0;
+    }
+    case ORC_OP_BASE_COUNTS_GC: { /* fixed-length reads, each its own PackedSequence of ceil(k/32) words */
+        const uint64_t *w = (const uint64_t *)d->in0;
+        uint64_t *counts4 = (uint64_t *)d->out0;
+        double *gc = (double *)d->out1;
+        size_t wpr = (d->k + 31) / 32;
+        uint64_t sum = 0;
+        for (size_t r = u0; r < u1; ++r) {
+            base_counts_ref(w + r * wpr, d->k, counts4 + 4 * r);
+            gc[r] = gc_content_ref(w + r * wpr, d->k);
+            sum += counts4[4 * r + 1] + counts4[4 * r + 2];
+        }
+        *check = sum;
+        return 0;
+    }
+    default:
+        return -3;
+    }
+}
+
+static void *op_worker(void *p) {
+    op_job *j = (op_job *)p;
+    if (j->cpu >= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(j->cpu, &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    size_t align = (j->d->op == ORC_OP_ENCODE || j->d->op == ORC_OP_DECODE || j->d->op == ORC_OP_HDIST) ? 128 : 1;
+    size_t u0, u1;
+    if (j->d->op == ORC_OP_ENCODE_BATCH) { /* reads cut by byte volume: the first read whose start reaches the ideal cut */
+        const uint64_t *off = (const uint64_t *)j->d->in1;
+        size_t n = j->d->n_units, cut[2];
+        for (int e = 0; e < 2; ++e) {
+            uint64_t target = off[0] + (off[n] - off[0]) / (uint64_t)j->n_threads * (uint64_t)(j->tid + e);
+            size_t lo = 0, hi = n;
+            while (lo < hi) {
+                size_t mid = (lo + hi) / 2;
+                if (off[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            cut[e] = (j->tid + e == j->n_threads) ? n : lo;
+        }
+        u0 = cut[0];
+        u1 = cut[1];
+    } else {
+        op_range(j->d, j->tid, j->n_threads, align, &u0, &u1);
+    }
+    for (int r = 0; r < j->reps; ++r) {
+        pthread_barrier_wait(j->bar);
+        uint64_t c = 0;
+        int rc = op_run(j->d, u0, u1, &c);
+        if (rc) j->rc = rc;
+        j->check = c;
+        pthread_barrier_wait(j->bar);
+    }
+    return NULL;
+}
+
+int orc_bench_op(const orc_bench_desc *d, int n_threads, int reps, int pin, double *times, uint64_t *check) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 1024) n_threads = 1024;
+    if (reps < 1) return -2;
+    if (d->path == ORC_PATH_AVX2 && !orc_have_avx2()) return -2;
+    int cpus[1024], n_cpus = 0;
+    cpu_set_t mine;
+    if (pin && sched_getaffinity(0, sizeof(mine), &mine) == 0)
+        for (int c = 0; c < CPU_SETSIZE && n_cpus < 1024; ++c)
+            if (CPU_ISSET(c, &mine)) cpus[n_cpus++] = c;
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, NULL, (unsigned)n_threads + 1);
+    op_job *jobs = (op_job *)calloc((size_t)n_threads, sizeof(op_job));
+    pthread_t *tids = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t] = (op_job){d, &bar, t, n_threads, reps, n_cpus ? cpus[t % n_cpus] : -1, 0, 0};
+        pthread_create(&tids[t], NULL, op_worker, &jobs[t]);
+    }
+    for (int r = 0; r < reps; ++r) {
+        pthread_barrier_wait(&bar);
+        double t0 = now_s();
+        pthread_barrier_wait(&bar);
+        times[r] = now_s() - t0;
+    }
+    int rc = 0;
+    uint64_t sum = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(tids[t], NULL);
+        if (jobs[t].rc) rc = jobs[t].rc;
+        sum += jobs[t].check;
+    }
+    if (check) *check = sum;
+    pthread_barrier_destroy(&bar);
+    free(jobs);
+    free(tids);
+    return rc;
 }

@@ -121,6 +121,32 @@ double orc_bench_codec(const uint8_t *seq, size_t n, int n_threads, int reps, in
                        int do_encode, int do_decode, uint64_t *ebuf, uint8_t *dbuf);
 int orc_have_avx2(void);
 
+/* ---- timed CPU baselines for every row (bench.py only) -----------------------------------------
+ * One op over n_units units split across n_threads threads created once (pinned to the CPUs of the
+ * process's affinity mask when pin != 0) that meet at a barrier around each of `reps` repetitions;
+ * times[r] = wall seconds of repetition r; *check = a checksum of the outputs (the hdist total, the sum of
+ * the pair distances, the G+C total ...) so the work cannot be optimised away and can be compared.
+ * The chunking is the harness's: the reference is single-threaded (src/lib.rs has no threads).
+ *   ORC_OP_ENCODE / DECODE   units = bases (in0 ASCII -> out0 words / in0 words -> out0 ASCII), cut on 128-base bounds
+ *   ORC_OP_AS_2BIT           units = records of k bytes at in0 + r*stride -> out0[r]      (packing/avx.rs:76-128 | naive.rs:4-20)
+ *   ORC_OP_FROM_2BIT         units = words in0[r] -> k bytes at out0 + r*stride           (unpacking/avx.rs:50-114 | naive.rs:3-25)
+ *   ORC_OP_HDIST             units = bases of the packed sequences in0, in1               (hamming/multi.rs:122-160, :12-67)
+ *   ORC_OP_HDIST_PAIRS       units = pairs (in0[r], in1[r]), len k -> out0[r] (u32)       (hamming/scalar.rs:11-48)
+ *   ORC_OP_BASE_COUNTS_GC    units = reads of k bases, ceil(k/32) words each at in0 -> out0[4r..] (u64), out1[r] (f64):
+ *                            base_counts() then gc_content(), each with its own to_vec()  (analysis.rs:3-39, sequence.rs:198-212)
+ *   ORC_OP_ENCODE_BATCH      units = reads: bytes in0, byte offsets in1[n+1], word offsets out1[n+1] (given by the caller) ->
+ *                            words out0; one PackedSequence::new per read (sequence.rs:40-52), threads cut by byte volume
+ * Returns 0, a NucleotideError code from the data, or <0 for a bad request. */
+enum { ORC_OP_ENCODE = 0, ORC_OP_DECODE = 1, ORC_OP_AS_2BIT = 2, ORC_OP_FROM_2BIT = 3, ORC_OP_HDIST = 4,
+       ORC_OP_HDIST_PAIRS = 5, ORC_OP_BASE_COUNTS_GC = 6, ORC_OP_ENCODE_BATCH = 7 };
+typedef struct {
+    int32_t op, path;
+    uint64_t n_units, k, stride;
+    const void *in0, *in1;
+    void *out0, *out1;
+} orc_bench_desc;
+int orc_bench_op(const orc_bench_desc *d, int n_threads, int reps, int pin, double *times, uint64_t *check);
+
 #ifdef __cplusplus
 }
 #endif

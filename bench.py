@@ -421,7 +421,7 @@ def leg_e2e(job: Job, asc, n: int, K: int):
         bn.decode_np(h_words[0], n, ctx, out=h_back)
     bn.encode_np(h_seq, ctx_a, out=h_words[1])
 
-    pcie = leg_pcie_ceiling(job, h_seq, h_back, n + nw * 8)
+    pcie = leg_pcie_ceiling(job, h_seq, h_back, n)
 
     def wall(fn):
         job.barrier()

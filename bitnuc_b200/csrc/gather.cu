@@ -14,26 +14,9 @@
 // per range (slice_long_kernel).
 #include "common.cuh"
 #include "launch.cuh"
-#include "scan.cuh"
+#include "lookback.cuh"
 
 namespace bn {
-
-// Length of query q's range, evaluated ONCE per query (the scan caches it): the only place a query is validated and
-// the only place lens[read] -- a random 32-byte sector per query -- is fetched.  A failing query is reported here
-// (status = min failing query index) and takes no room, so the kernels below see it as an empty range.
-struct SliceLen {
-    const uint64_t *lens, *q_read, *q_start, *q_end;
-    unsigned long long n_reads;
-    unsigned long long* status;
-    __device__ __forceinline__ unsigned long long operator()(unsigned long long q) const {
-        const unsigned long long r = q_read[q], s = q_start[q], e = q_end[q];
-        if (r >= n_reads || s > e || e > lens[r]) {
-            if (q < ld_volatile_u64(status)) atomicMin(status, q);
-            return 0;
-        }
-        return e - s;
-    }
-};
 
 // ASCII of the 4 bases starting at base b of the read whose words (viewed as 32-bit halves) start at w32:
 // a funnel shift of two halves, the low byte spread to one code per nibble, PRMT as a 4-entry LUT.
@@ -54,40 +37,81 @@ __device__ __forceinline__ uint8_t ascii1_at(const uint32_t* __restrict__ w32, u
 constexpr unsigned kSliceShort = 64;                      // ranges up to this many bases are cut by one thread each
 constexpr unsigned kSliceStage = 32 * kSliceShort + 16;   // bytes a warp stages for its 32 queries (+ alignment slack)
 
-// Short ranges (<= 64 bases): one thread per query, so a warp keeps 32 independent gathers in flight (this path is
+// ONE pass over the queries.  A CTA takes a tile of 256 consecutive queries (tiles numbered by a ticket), validates each
+// (the only place lens[read] -- a random sector per query -- is fetched; a failing query is reported as
+// status = min failing query index and takes no room), scans the range lengths inside the CTA, gets the bytes of all
+// earlier tiles by decoupled look-back (lookback.cuh) and writes out_offsets -- the three-launch cached scan this
+// replaces wrote every length to HBM and read it, q_read, q_start and the offsets back.
+// Short ranges (<= 64 bases) are then cut one per thread, so a warp keeps 32 independent gathers in flight (this path is
 // a latency-bound chain query -> read offsets -> words).  The 2n bits of a range are pulled into a 128-bit register
 // window (<= 3 words) and leave 4 bases at a time (spread + PRMT as a 4-entry LUT).  The 32 ranges of a warp are
 // adjacent in the output (prefix sums of consecutive queries), so the threads write into a shared-memory image of
 // that span -- laid out at the same 16-byte phase as the global span -- and the warp then stores it with coalesced
 // 128-bit stores.  Longer ranges are queued for slice_long_kernel.
 __global__ void __launch_bounds__(kThreads)
-slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ q_read,
-                   const uint64_t* __restrict__ q_start, unsigned long long nq, uint8_t* __restrict__ out,
-                   const uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ long_count,
-                   unsigned long long* __restrict__ long_list) {
+slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ lens,
+                   unsigned long long n_reads, const uint64_t* __restrict__ q_read, const uint64_t* __restrict__ q_start,
+                   const uint64_t* __restrict__ q_end, unsigned long long nq, uint8_t* __restrict__ out,
+                   uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ status, unsigned long long* __restrict__ long_count,
+                   unsigned long long* __restrict__ long_list, unsigned long long* __restrict__ lb, unsigned long long n_tiles) {
     __shared__ __align__(16) uint8_t stage[kWarpsPerBlock][kSliceStage];
+    __shared__ unsigned long long s_tile, s_warp[kWarpsPerBlock + 1], s_base;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long q = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
-    // this thread's query: n = 0 for lanes past the end, failing queries and ranges left to the long kernel
-    unsigned n = 0, sh_head = 0;
-    unsigned long long s = 0, oo = out_offsets[q < nq ? q : nq];
-    const uint64_t* w = words;
+    if (threadIdx.x == 0) s_tile = atomicAdd(lb, 1ull);
+    __syncthreads();
+    const unsigned long long tile = s_tile;
+    const unsigned long long q = tile * kThreads + threadIdx.x;
+    // this thread's query: cnt = 0 for lanes past the end and failing queries
+    unsigned long long cnt = 0, s = 0, rd = 0;
     if (q < nq) {
-        // the range length is the difference of two output offsets (the scan validated the query: a failing one is
-        // empty here), so neither lens[read] nor q_end is fetched again
-        const unsigned long long cnt = out_offsets[q + 1] - oo;
-        if (cnt > kSliceShort) {
-            long_list[atomicAdd(long_count, 1ull)] = q;
-        } else if (cnt) {
-            n = (unsigned)cnt;
-            s = q_start[q];
-            w = words + word_offsets[q_read[q]];
+        rd = q_read[q];
+        s = q_start[q];
+        const unsigned long long e = q_end[q];
+        if (rd >= n_reads || s > e || e > __ldg(lens + rd)) {
+            if (q < ld_volatile_u64(status)) atomicMin(status, q);
+        } else {
+            cnt = e - s;
         }
+    }
+    unsigned long long inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long a = lane < kWarpsPerBlock ? s_warp[lane] : 0ull;
+        unsigned long long ia = a;
+#pragma unroll
+        for (int o = 1; o < kWarpsPerBlock; o <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= (unsigned)o) ia += x;
+        }
+        const unsigned long long agg[1] = {__shfl_sync(0xffffffffu, ia, kWarpsPerBlock - 1)};
+        unsigned long long excl[1];
+        lookback_exclusive<1>(lb + 1, n_tiles, tile, agg, excl);
+        if (lane < kWarpsPerBlock) s_warp[lane] = ia - a;   // exclusive prefix of the warp totals
+        if (lane == 0) s_base = excl[0];
+    }
+    __syncthreads();
+    const unsigned long long oo = s_base + s_warp[warp] + inc - cnt;   // where this query's bytes start
+    if (q < nq) {
+        out_offsets[q] = oo;
+        if (q + 1 == nq) out_offsets[nq] = oo + cnt;
+    }
+    unsigned n = 0, sh_head = 0;
+    const uint64_t* w = words;
+    if (cnt > kSliceShort) {
+        long_list[atomicAdd(long_count, 1ull)] = q;
+    } else if (cnt) {
+        n = (unsigned)cnt;
+        w = words + __ldg(word_offsets + rd);
     }
     // the warp's output span [span_lo, span_hi) and its staged image; a span with a long range inside is too big to stage
     const unsigned long long span_lo = __shfl_sync(0xffffffffu, oo, 0);
-    const unsigned long long q_last = (unsigned long long)blockIdx.x * kThreads + 32ull * warp + 32;
-    const unsigned long long span_hi = out_offsets[q_last < nq ? q_last : nq];
+    const unsigned long long span_hi = __shfl_sync(0xffffffffu, oo + cnt, 31);
     const uintptr_t g_lo = reinterpret_cast<uintptr_t>(out) + span_lo, g_base = g_lo & ~(uintptr_t)15;
     const bool staged = g_lo - g_base + (span_hi - span_lo) <= kSliceStage;
     uint8_t* o = staged ? stage[warp] + (reinterpret_cast<uintptr_t>(out) + oo - g_base) : out + oo;
@@ -189,8 +213,9 @@ get_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
     out[q] = (uint8_t)(0x54474341u >> (8 * ((x >> (2 * (i & 31))) & 3)));
 }
 
-// scan state, the queue of long ranges (count + one entry per query), the cached range lengths
-size_t slice_batch_scratch_bytes(size_t nq) { return scan_scratch_bytes(nq) + (2 * nq + 1) * sizeof(unsigned long long); }
+// ticket + tile descriptors, then the queue of long ranges (count + one entry per query)
+static inline size_t slice_lb_words(size_t nq) { return lookback_bytes(ceil_div(nq ? nq : 1, kThreads), 1) / sizeof(unsigned long long); }
+size_t slice_batch_scratch_bytes(size_t nq) { return (slice_lb_words(nq) + nq + 1) * sizeof(unsigned long long); }
 
 cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
                                size_t n_reads, const uint64_t* d_q_read, const uint64_t* d_q_start, const uint64_t* d_q_end, size_t nq,
@@ -198,14 +223,13 @@ cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, co
     cudaError_t e = cudaMemsetAsync(d_status, 0xFF, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
     if (nq == 0) return cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s);
-    unsigned long long* sums = static_cast<unsigned long long*>(d_scratch);
-    unsigned long long* long_count = sums + scan_scratch_bytes(nq) / sizeof(unsigned long long);
-    e = cudaMemsetAsync(long_count, 0, sizeof(unsigned long long), s);
+    unsigned long long* lb = static_cast<unsigned long long*>(d_scratch);
+    unsigned long long* long_count = lb + slice_lb_words(nq);
+    const unsigned long long n_tiles = ceil_div(nq, kThreads);
+    e = cudaMemsetAsync(lb, 0, (slice_lb_words(nq) + 1) * sizeof(unsigned long long), s);   // ticket, descriptors, long_count
     if (e != cudaSuccess) return e;
-    uint64_t* cache = reinterpret_cast<uint64_t*>(long_count + 1 + nq);
-    launch_exclusive_scan_cached(SliceLen{d_lens, d_q_read, d_q_start, d_q_end, n_reads, d_status}, nq, sums, cache, d_out_offsets, s);
-    slice_short_kernel<<<(unsigned)ceil_div(nq, kThreads), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, nq, d_out,
-                                                                           d_out_offsets, long_count, long_count + 1);
+    slice_short_kernel<<<(unsigned)n_tiles, kThreads, 0, s>>>(d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start, d_q_end, nq, d_out,
+                                                             d_out_offsets, d_status, long_count, long_count + 1, lb, n_tiles);
     static const int per_sm = blocks_per_sm(slice_long_kernel, kThreads);
     const int resident = per_sm * di.sm_count;
     slice_long_kernel<<<grid_for(ceil_div(nq, kWarpsPerBlock), resident), kThreads, 0, s>>>(d_words, d_word_offsets, d_q_read, d_q_start, d_q_end,

@@ -85,3 +85,27 @@ def test_more_than_2_pow_32_bases(cfg):
     mid = dv.decode(bw[32 : 32 + (lens[1] + 31) // 32].contiguous(), lens[1])
     assert torch.equal(mid[:4096], asc[1000:5096]) and torch.equal(mid[-4096:], asc[n - 5 - 4096 : n - 5])
     assert torch.equal(dv.decode(bw[-1:].contiguous(), 5), asc[n - 5 :])
+
+
+def test_full_size_hdist_pairs_against_the_oracle_on_a_strided_sample(cfg):
+    """cfg 4 at its full 2^30 pairs: a strided sample across the WHOLE range (not a prefix) through the oracle's
+    hdist_scalar (hamming/scalar.rs:11-48), plus the whole-sequence total of the sampled words through orc_hdist."""
+    import numpy as np
+    import torch
+    import oracle
+    from bitnuc_b200 import device as dv
+    n = 1 << 30
+    u, v = dv.synth_words(cfg.SEED, 2, 0, n), dv.synth_words(cfg.SEED, 3, 0, n)
+    out = dv.hdist_pairs(u, v, 32)
+    idx = torch.arange(0, n, 4099, device="cuda")          # 262 k pairs, every region of the buffers
+    idx = torch.cat([idx, torch.tensor([n - 1], device="cuda")])
+    su, sv = (x[idx].cpu().numpy().view(np.uint64) for x in (u, v))
+    got = out[idx].cpu().numpy().astype(np.uint32)
+    exp = np.zeros(su.size, dtype=np.uint32)
+    _, s = oracle.bench_op(oracle.OP_HDIST_PAIRS, su.size, in0=su, in1=sv, out0=exp, k=32, threads=1, reps=1)
+    assert np.array_equal(got, exp) and s == int(exp.sum())
+    assert oracle.hdist(su, sv, 32 * su.size, wide=True) == s
+    for ln in (1, 17, 31):                                   # shorter pair lengths on the same sample
+        o2 = dv.hdist_pairs(u[idx].contiguous(), v[idx].contiguous(), ln).cpu().numpy().astype(np.uint32)
+        oracle.bench_op(oracle.OP_HDIST_PAIRS, su.size, in0=su, in1=sv, out0=exp, k=ln, threads=1, reps=1)
+        assert np.array_equal(o2, exp), ln

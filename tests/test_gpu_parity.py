@@ -856,3 +856,53 @@ def test_base_counts_batch_many_chunks(bn):
     assert ei.value.key() == ("InvalidLength", int(bad[150_000]))
     ctx.close()
     big.close()
+
+
+# ------------------------------------------------------------------ look-back chains longer than the resident grid ----
+
+def test_split_and_slice_lookback_over_many_tiles(bn):
+    """split_packed / slice place their outputs with a single-pass look-back across 256-item tiles (lookback.cuh): far more
+    tiles than CTAs fit on the device at once, offsets against numpy prefix sums, spot reads against the oracle."""
+    import torch
+    from bitnuc_b200 import device as dv
+    rng = np.random.default_rng(5)
+    n = 1_500_000                                        # ~5900 tiles
+    lens = rng.integers(0, 97, n).astype(np.uint64)      # 0..3 words
+    nw = (lens + np.uint64(31)) // np.uint64(32)
+    wo = np.concatenate([[0], np.cumsum(nw)]).astype(np.uint64)
+    words = rng.integers(0, 2**63, int(wo[-1]), dtype=np.int64).view(np.uint64)
+    last = wo[1:][nw > 0] - np.uint64(1)                 # zero padding of every read's last word
+    rem = (lens[nw > 0] % np.uint64(32)).astype(np.uint64)
+    mask = np.where(rem == 0, np.uint64(2**64 - 1), (np.uint64(1) << (np.uint64(2) * rem)) - np.uint64(1))
+    words[last.astype(np.int64)] &= mask
+    idx = (rng.random(n) * (lens + np.uint64(1)).astype(np.float64)).astype(np.uint64)
+    idx = np.minimum(idx, lens)
+    t = [torch.from_numpy(a.view(np.int64)).cuda() for a in (words, wo, lens, idx)]
+    left, lo, right, ro, st = dv.split_packed_batch(*t)
+    st.check(t[2], t[3])
+    inner = (idx > 0) & (idx < lens)
+    nl = np.where(idx == 0, 0, np.where(idx == lens, nw, np.where(inner & (nw > 0), idx // np.uint64(32) + np.uint64(1), 0))).astype(np.uint64)
+    nr = np.where(idx == 0, nw, np.where(idx == lens, 0, np.where(inner & (nw > 0), nw - idx // np.uint64(32), 0))).astype(np.uint64)
+    assert np.array_equal(lo.cpu().numpy().view(np.uint64), np.concatenate([[0], np.cumsum(nl)]).astype(np.uint64))
+    assert np.array_equal(ro.cpu().numpy().view(np.uint64), np.concatenate([[0], np.cumsum(nr)]).astype(np.uint64))
+    h_left, h_right = left.cpu().numpy().view(np.uint64), right.cpu().numpy().view(np.uint64)
+    h_lo, h_ro = lo.cpu().numpy().view(np.uint64), ro.cpu().numpy().view(np.uint64)
+    for r in list(range(0, n, 7919)) + [n - 1]:
+        el, er = oracle.split_packed(words[int(wo[r]): int(wo[r + 1])], int(lens[r]), int(idx[r]))
+        assert [int(x) for x in h_left[int(h_lo[r]): int(h_lo[r + 1])]] == list(el), r
+        assert [int(x) for x in h_right[int(h_ro[r]): int(h_ro[r + 1])]] == list(er), r
+    # slice: one window per read
+    qr = np.arange(n, dtype=np.uint64)
+    qs = idx // np.uint64(2)
+    qe = idx
+    tq = [torch.from_numpy(a.view(np.int64)).cuda() for a in (qr, qs, qe)]
+    total = int((qe - qs).sum())
+    d_out, d_oo, qst = dv.slice_batch(t[0], t[1][:-1].contiguous(), t[2], *tq, out_bytes=total)
+    assert qst.first_failing() is None
+    oo = d_oo.cpu().numpy().view(np.uint64)
+    assert np.array_equal(oo, np.concatenate([[0], np.cumsum(qe - qs)]).astype(np.uint64))
+    h_out = d_out.cpu().numpy()
+    for r in list(range(0, n, 7919)) + [n - 1]:
+        if lens[r]:
+            exp = oracle.decode_np(words[int(wo[r]): int(wo[r + 1])], int(lens[r]))[int(qs[r]): int(qe[r])]
+            assert np.array_equal(h_out[int(oo[r]): int(oo[r + 1])], exp), r

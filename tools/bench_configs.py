@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -34,7 +35,7 @@ def peak():
 
 
 def timed(fn, reps):
-    for _ in range(3):
+    for _ in range(int(os.environ.get("BN_WARM", "3"))):   # BN_WARM=0: profiling runs (one launch to capture)
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -182,9 +182,14 @@ def e2e(chunk_mib: int, mode: str, pinned_cores: bool):
 
 if rank == 0:
     print(json.dumps({"host_threads": len(os.sched_getaffinity(0)), "cpu_count": os.cpu_count()}), flush=True)
-raw_copies()
+if os.environ.get('PROBE_RAW', '1') == '1':
+    raw_copies()
 which = os.environ.get("PROBE_E2E", "full")
-if which != "none":
+if which.startswith("sweep"):   # PROBE_E2E=sweep:8,16,32 -> the pipelined and serial schedules at those chunk sizes
+    for mib in [int(x) for x in which.split(":")[1].split(",")]:
+        e2e(mib, "pipelined", False)
+        e2e(mib, "serial", False)
+elif which != "none":
     e2e(64, "serial", False)
     e2e(64, "pipelined", False)
     e2e(64, "staggered", False)

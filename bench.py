@@ -834,17 +834,33 @@ def leg_multi(job: Job, reps: int, n_bases: int):
     return out
 
 
-def cpu_baselines(args):
-    """cpu_baseline legs (rank 0, N = 1): every row's CPU form, AVX2 and scalar, one pinned thread and all threads."""
-    build_oracle()
+def cpu_suite_main(args):
+    """`bench.py --cpu-suite`: the cpu_baseline legs in a process of their own (no CUDA context, no torch threads -- the
+    same conditions as the --impl reference arm), one JSON object on stdout."""
+    oracle = build_oracle()
     from oracle import baselines as B
     s = B.Suite(reps=5)
     t0 = time.time()
-    rows = {"codec": s.codec(), "kmers": s.kmers(), "hdist": s.hdist(), "base_counts": s.base_counts(),
-            "encode_batch": B.encode_batch(s)}
-    cfg0 = B.Suite(threads=1, reps=7).codec(n_single=1_000_000, n_many=1_000_000, grid=[(s.paths[0], 1)])[0]  # BASELINE.json configs[0]
-    log(f"cpu baselines took {time.time() - t0:.1f} s")
-    return rows, cfg0, B
+    seq = B.synth_ascii_mt(0, 0, args.bases)
+    path = s.paths[0]
+    rows = {"codec_full": s.codec(seq=seq, grid=[(path, s.threads)]),                      # the whole workload, as the reference arm
+            "codec": B.Suite(reps=5).codec(n_many=1 << 28, seq=seq[: 1 << 28]),
+            "kmers": s.kmers(), "hdist": s.hdist(), "base_counts": s.base_counts(), "encode_batch": B.encode_batch(s)}
+    rows["cfg0"] = B.Suite(threads=1, reps=7).codec(n_single=1_000_000, n_many=1_000_000, seq=seq[:1_000_000], grid=[(path, 1)])  # configs[0]
+    rows["seconds"] = time.time() - t0
+    print(json.dumps(rows))
+
+
+def cpu_baselines(args):
+    """cpu_baseline legs (rank 0, N = 1): every row's CPU form, AVX2 and scalar, one pinned thread and all threads, timed in a
+    fresh process (`--cpu-suite`)."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-suite", "--bases", str(args.bases)], capture_output=True, text=True,
+                       timeout=600)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-400:])
+    rows = json.loads(r.stdout.strip().splitlines()[-1])
+    log(f"cpu baselines took {rows['seconds']:.1f} s")
+    return rows
 
 
 def run_ours(args):
@@ -951,18 +967,19 @@ def report(args, job, n, K, W, total_ms, enc_ms, dec_ms, clocks, e2e, strong, cf
     else:
         line["e2e"] = None
 
-    cpu_rows = cfg0 = B = None
+    cpu_rows = None
     if world == 1 and not args.skip_cpu:
         try:
-            cpu_rows, cfg0, B = cpu_baselines(args)
-            allc = B.pick(cpu_rows["codec"], "avx2", True) or cpu_rows["codec"][-1]
-            one = B.pick(cpu_rows["codec"], "avx2", False) or cpu_rows["codec"][0]
+            cpu_rows = cpu_baselines(args)
+            allc = cpu_rows["codec_full"][0]
+            one = next((r for r in cpu_rows["codec"] if r["isa"] == allc["isa"] and r["cores"] == 1), cpu_rows["codec"][0])
             line["cpu_baseline"] = {
                 "value": allc["value"], "unit": UNIT, "cores": allc["cores"], "kind": "port",
                 "best": allc["best"], "worst": allc["worst"], "reps": allc["reps"],
-                "single_thread_value": one["value"], "configs0_1e6_bases_single_thread_value": cfg0["value"],
-                "sample": f"{allc['sample']}, encode + decode, median of {allc['reps']} repetitions on {allc['cores']} pinned threads; C restatement of "
-                          f"the reference's {allc['isa']} path (oracle/bitnuc_oracle.c, -march=native)",
+                "single_thread_value": one["value"], "configs0_1e6_bases_single_thread_value": cpu_rows["cfg0"][0]["value"],
+                "sample": f"the whole workload ({allc['sample']}), encode + decode, median of {allc['reps']} repetitions on {allc['cores']} pinned "
+                          f"threads in a process of its own; C restatement of the reference's {allc['isa']} path (oracle/bitnuc_oracle.c, "
+                          f"-march=native)",
                 "rows": cpu_rows["codec"]}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"error": str(ex)}
@@ -1052,8 +1069,11 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the cpu_baseline legs")
     ap.add_argument("--skip-configs", action="store_true", help="profiling runs only: skip strong / configs[2..4] / multi")
+    ap.add_argument("--cpu-suite", action="store_true", help="internal: run the cpu_baseline legs and print them as JSON")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.cpu_suite:
+        cpu_suite_main(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -65,8 +65,8 @@ int bn_ctx_create(int device, bn_ctx** out) {
         ok = cudaStreamCreateWithFlags(&ctx->stage_stream[s], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->stage_done[s], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     }
-    ok = ok && cudaMalloc(&ctx->d_words, 16 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&ctx->h_words, 16 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_words, (5 * kStages + 4) * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_words, (5 * kStages + 4) * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         bn_ctx_destroy(ctx);
@@ -662,7 +662,7 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
 // The record- and stream-parallel calls below use the same 3-stage pipeline through one helper: chunk c is issued on
 // stage c % kStages (its own stream: H2D -> kernel -> D2H) once the chunk that used the stage before has retired, so
 // with pinned host buffers uploads, kernels and downloads of neighbouring chunks overlap.  Per-stage status /
-// accumulator words live at d_words[s] (status) and d_words[4 + 4 s ..] (up to four accumulators).
+// accumulator words live at d_words[s] (status) and d_words[kStages + 4 s ..] (up to four accumulators).
 
 }  // extern "C"
 
@@ -888,11 +888,11 @@ int bn_base_counts(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_
             const void* src = words + w0;
             BN_TRY(bounce_in(ctx, s, 0, src, cnt * 8, in_pg));
             BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, src, cnt * 8, cudaMemcpyHostToDevice, st));
-            BN_TRY(bn::launch_base_counts(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), bases, ctx->d_words + 4 + 4 * s, nullptr, st));
-            return cudaMemcpyAsync(ctx->h_words + 4 + 4 * s, ctx->d_words + 4 + 4 * s, 4 * 8, cudaMemcpyDeviceToHost, st);
+            BN_TRY(bn::launch_base_counts(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p), bases, ctx->d_words + kStages + 4 * s, nullptr, st));
+            return cudaMemcpyAsync(ctx->h_words + kStages + 4 * s, ctx->d_words + kStages + 4 * s, 4 * 8, cudaMemcpyDeviceToHost, st);
         },
         [&](size_t, int s) {
-            for (int i = 0; i < 4; ++i) counts[i] += ctx->h_words[4 + 4 * s + i];
+            for (int i = 0; i < 4; ++i) counts[i] += ctx->h_words[kStages + 4 * s + i];
         });
     if (rc != BN_OK) return rc;
     // analysis.rs:14, exactly this operation order on exact integer counts: (gc as f64 / len as f64) * 100.0
@@ -983,7 +983,7 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
                 if (nw) BN_TRY(cudaMemcpyAsync(ctx->stage_in[s].p, words + w0, nw * 8, cudaMemcpyHostToDevice, st));
                 BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][0].p, word_offsets + r0, cnt * 8, cudaMemcpyHostToDevice, st));
                 BN_TRY(cudaMemcpyAsync(ctx->stage_aux[s][1].p, lens + r0, cnt * 8, cudaMemcpyHostToDevice, st));
-                unsigned long long* d_tot = ctx->d_words + 4 + 4 * s;
+                unsigned long long* d_tot = ctx->d_words + kStages + 4 * s;
                 // the kernel indexes with the caller's absolute word offsets: hand it the chunk's base moved back by w0
                 BN_TRY(bn::launch_base_counts_batch(ctx->di, static_cast<const uint64_t*>(ctx->stage_in[s].p) - w0,
                                                     static_cast<const uint64_t*>(ctx->stage_aux[s][0].p),
@@ -992,10 +992,10 @@ int bn_base_counts_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, con
                                                     gc ? static_cast<double*>(ctx->stage_aux[s][2].p) : nullptr, d_tot, st));
                 if (counts4) BN_TRY(cudaMemcpyAsync(counts4 + 4 * r0, ctx->stage_out[s].p, cnt * 32, cudaMemcpyDeviceToHost, st));
                 if (gc) BN_TRY(cudaMemcpyAsync(gc + r0, ctx->stage_aux[s][2].p, cnt * 8, cudaMemcpyDeviceToHost, st));
-                return cudaMemcpyAsync(ctx->h_words + 4 + 4 * s, d_tot, 4 * 8, cudaMemcpyDeviceToHost, st);
+                return cudaMemcpyAsync(ctx->h_words + kStages + 4 * s, d_tot, 4 * 8, cudaMemcpyDeviceToHost, st);
             },
             [&](size_t, int s) {
-                for (int i = 0; i < 4; ++i) acc[i] += ctx->h_words[4 + 4 * s + i];
+                for (int i = 0; i < 4; ++i) acc[i] += ctx->h_words[kStages + 4 * s + i];
             });
         if (rc != BN_OK) return rc;
         if (totals)

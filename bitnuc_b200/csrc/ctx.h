@@ -43,7 +43,7 @@ struct bn_ctx {
     Buffer stage_aux[kStages][4];                // batch calls: offsets, word offsets, per-read status, scratch
     HostBuffer hstage_in[kStages][2], hstage_out[kStages];   // pinned bounce buffers for pageable caller memory
     Buffer slot[kSlots];
-    unsigned long long* d_words = nullptr;       // 16 device status / accumulator words
+    unsigned long long* d_words = nullptr;       // 5 kStages + 4 device status / accumulator words
     unsigned long long* h_words = nullptr;       // pinned mirror
     size_t chunk = kDefaultChunk;
     // bn_fastq_scan -> bn_fastq_encode: the uploaded text and its index stay resident between the two calls

@@ -37,7 +37,8 @@ __device__ __forceinline__ uint8_t ascii1_at(const uint32_t* __restrict__ w32, u
 constexpr unsigned kSliceShort = 64;                      // ranges up to this many bases are cut by one thread each
 constexpr unsigned kSliceStage = 32 * kSliceShort + 16;   // bytes a warp stages for its 32 queries (+ alignment slack)
 
-// ONE pass over the queries.  A CTA takes a tile of 256 consecutive queries (tiles numbered by a ticket), validates each
+// ONE pass over the queries.  A CTA takes a tile of 2048 consecutive queries (tiles numbered by a ticket; warp w owns 8 rows of 32
+// of them, one look-back per tile -- per 256 queries the chain of spinning tiles was slower than the scan), validates each
 // (the only place lens[read] -- a random sector per query -- is fetched; a failing query is reported as
 // status = min failing query index and takes no room), scans the range lengths inside the CTA, gets the bytes of all
 // earlier tiles by decoupled look-back (lookback.cuh) and writes out_offsets -- the three-launch cached scan this
@@ -48,6 +49,9 @@ constexpr unsigned kSliceStage = 32 * kSliceShort + 16;   // bytes a warp stages
 // adjacent in the output (prefix sums of consecutive queries), so the threads write into a shared-memory image of
 // that span -- laid out at the same 16-byte phase as the global span -- and the warp then stores it with coalesced
 // 128-bit stores.  Longer ranges are queued for slice_long_kernel.
+constexpr int kSlRows = 8;                        // rows of 32 queries per warp: a CTA tile holds 8 warps x 8 rows x 32 = 2048 queries
+constexpr int kSlTile = kThreads * kSlRows;
+
 __global__ void __launch_bounds__(kThreads)
 slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ lens,
                    unsigned long long n_reads, const uint64_t* __restrict__ q_read, const uint64_t* __restrict__ q_start,
@@ -55,31 +59,38 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
                    uint64_t* __restrict__ out_offsets, unsigned long long* __restrict__ status, unsigned long long* __restrict__ long_count,
                    unsigned long long* __restrict__ long_list, unsigned long long* __restrict__ lb, unsigned long long n_tiles) {
     __shared__ __align__(16) uint8_t stage[kWarpsPerBlock][kSliceStage];
-    __shared__ unsigned long long s_tile, s_warp[kWarpsPerBlock + 1], s_base;
+    __shared__ uint32_t s_cnt[kSlRows][kThreads];               // range lengths from pass A (written and read by the same thread);
+                                                                // 0xFFFFFFFF: longer than that, derived again from the query in pass B
+    __shared__ unsigned long long s_src[kSlRows][kThreads];     // (index of the word holding the range's first base) << 5 | its place in the word
+    __shared__ unsigned long long s_tile, s_warp[kWarpsPerBlock], s_base;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(lb, 1ull);
     __syncthreads();
     const unsigned long long tile = s_tile;
-    const unsigned long long q = tile * kThreads + threadIdx.x;
-    // this thread's query: cnt = 0 for lanes past the end and failing queries
-    unsigned long long cnt = 0, s = 0, rd = 0;
-    if (q < nq) {
-        rd = q_read[q];
-        s = q_start[q];
-        const unsigned long long e = q_end[q];
-        if (rd >= n_reads || s > e || e > __ldg(lens + rd)) {
-            if (q < ld_volatile_u64(status)) atomicMin(status, q);
-        } else {
-            cnt = e - s;
-        }
-    }
-    unsigned long long inc = cnt;
+    const unsigned long long row0 = tile * kSlTile + warp * (32 * kSlRows) + lane;   // this lane's query in row 0
+    // ---- pass A: validate every query of the warp's rows, add up the range lengths
+    unsigned long long wsum = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (unsigned)o) inc += t;
+    for (int i = 0; i < kSlRows; ++i) {
+        const unsigned long long q = row0 + 32 * i;
+        unsigned long long cnt = 0, src = 0;
+        if (q < nq) {
+            const unsigned long long rd = q_read[q], s = q_start[q], e = q_end[q];
+            if (rd >= n_reads || s > e || e > __ldg(lens + rd)) {
+                if (q < ld_volatile_u64(status)) atomicMin(status, q);
+            } else {
+                cnt = e - s;
+                // fetched here, next to lens[rd] (one round trip for both): the word that holds base `start` and the base's
+                // place inside it -- pass B then goes straight to the words instead of chasing q_read -> word_offsets again
+                src = ((__ldg(word_offsets + rd) + (s >> 5)) << 5) | (s & 31u);
+            }
+        }
+        s_cnt[i][threadIdx.x] = cnt < 0xFFFFFFFFull ? (uint32_t)cnt : 0xFFFFFFFFu;
+        s_src[i][threadIdx.x] = src;
+        wsum += cnt;
     }
-    if (lane == 31) s_warp[warp] = inc;
+    wsum = warp_sum_u64(wsum);
+    if (lane == 0) s_warp[warp] = wsum;
     __syncthreads();
     if (warp == 0) {
         const unsigned long long a = lane < kWarpsPerBlock ? s_warp[lane] : 0ull;
@@ -96,18 +107,35 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
         if (lane == 0) s_base = excl[0];
     }
     __syncthreads();
-    const unsigned long long oo = s_base + s_warp[warp] + inc - cnt;   // where this query's bytes start
+    // ---- pass B: row by row, the warp on its own
+    unsigned long long row_base = s_base + s_warp[warp];
+#pragma unroll 1
+    for (int row = 0; row < kSlRows; ++row) {
+    const unsigned long long q = row0 + 32 * row;
+    unsigned long long cnt = s_cnt[row][threadIdx.x];
+    if (cnt == 0xFFFFFFFFull) cnt = q_end[q] - q_start[q];
+    unsigned long long inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    const unsigned long long oo = row_base + inc - cnt;   // where this query's bytes start
+    row_base += __shfl_sync(0xffffffffu, inc, 31);
     if (q < nq) {
         out_offsets[q] = oo;
         if (q + 1 == nq) out_offsets[nq] = oo + cnt;
     }
     unsigned n = 0, sh_head = 0;
+    unsigned long long s = 0;
     const uint64_t* w = words;
     if (cnt > kSliceShort) {
         long_list[atomicAdd(long_count, 1ull)] = q;
     } else if (cnt) {
         n = (unsigned)cnt;
-        w = words + __ldg(word_offsets + rd);
+        const unsigned long long src = s_src[row][threadIdx.x];
+        s = src & 31u;              // the range starts at base s of the word at words[src >> 5]
+        w = words + (src >> 5);
     }
     // the warp's output span [span_lo, span_hi) and its staged image; a span with a long range inside is too big to stage
     const unsigned long long span_lo = __shfl_sync(0xffffffffu, oo, 0);
@@ -169,6 +197,8 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
                 for (unsigned i = c < a ? a : c; i < c + 16 && i < b; ++i) *reinterpret_cast<uint8_t*>(g_base + i) = stage[warp][i];
             }
         }
+        __syncwarp();   // the image is reused by the next row
+    }
     }
 }
 
@@ -214,7 +244,7 @@ get_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
 }
 
 // ticket + tile descriptors, then the queue of long ranges (count + one entry per query)
-static inline size_t slice_lb_words(size_t nq) { return lookback_bytes(ceil_div(nq ? nq : 1, kThreads), 1) / sizeof(unsigned long long); }
+static inline size_t slice_lb_words(size_t nq) { return lookback_bytes(ceil_div(nq ? nq : 1, kSlTile), 1) / sizeof(unsigned long long); }
 size_t slice_batch_scratch_bytes(size_t nq) { return (slice_lb_words(nq) + nq + 1) * sizeof(unsigned long long); }
 
 cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, const uint64_t* d_word_offsets, const uint64_t* d_lens,
@@ -225,7 +255,7 @@ cudaError_t launch_slice_batch(const DeviceInfo& di, const uint64_t* d_words, co
     if (nq == 0) return cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s);
     unsigned long long* lb = static_cast<unsigned long long*>(d_scratch);
     unsigned long long* long_count = lb + slice_lb_words(nq);
-    const unsigned long long n_tiles = ceil_div(nq, kThreads);
+    const unsigned long long n_tiles = ceil_div(nq, kSlTile);
     e = cudaMemsetAsync(lb, 0, (slice_lb_words(nq) + 1) * sizeof(unsigned long long), s);   // ticket, descriptors, long_count
     if (e != cudaSuccess) return e;
     slice_short_kernel<<<(unsigned)n_tiles, kThreads, 0, s>>>(d_words, d_word_offsets, d_lens, n_reads, d_q_read, d_q_start, d_q_end, nq, d_out,

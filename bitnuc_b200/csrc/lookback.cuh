@@ -39,11 +39,14 @@ __device__ __forceinline__ void lookback_exclusive(unsigned long long* __restric
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) excl[ch] = 0;
+    unsigned long long mine = agg[0];   // channel `lane`'s aggregate, selected without indexing (the array stays in registers)
+#pragma unroll
+    for (int ch = 1; ch < NCH; ++ch) mine = lane == (unsigned)ch ? agg[ch] : mine;
     if (tile == 0) {
-        if (lane < NCH) lb_store(desc + lane * n_tiles, kLbPrefix | agg[lane < NCH ? lane : 0]);
+        if (lane < NCH) lb_store(desc + lane * n_tiles, kLbPrefix | mine);
         return;
     }
-    if (lane < NCH) lb_store(desc + lane * n_tiles + tile, kLbAggregate | agg[lane < NCH ? lane : 0]);
+    if (lane < NCH) lb_store(desc + lane * n_tiles + tile, kLbAggregate | mine);
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
         const unsigned long long* d = desc + ch * n_tiles;

@@ -23,110 +23,189 @@
 
 namespace bn {
 
-// split_one: the words of one read, written to lo / ro (global memory or the CTA's staged image of its output spans)
+// split_one: the words of one read, written to lo / ro (global memory or the warp's staged image of its output spans).
+// A read of up to kSpPre words is fetched with kSpPre independent predicated loads BEFORE anything is stored: the plain
+// loop (load a word, store a word) serialises one L2 / HBM round trip per word -- the kernel was latency-bound on it.
+constexpr int kSpPre = 8;
 __device__ __forceinline__ void split_one(const uint64_t* __restrict__ w, unsigned long long nw, unsigned long long slen,
                                           unsigned long long i, uint64_t* __restrict__ lo, uint64_t* __restrict__ ro) {
-    if (i == 0) {
-        for (unsigned long long j = 0; j < nw; ++j) ro[j] = __ldg(w + j);
-    } else if (i == slen) {
-        for (unsigned long long j = 0; j < nw; ++j) lo[j] = __ldg(w + j);
-    } else if (nw) {
-        const unsigned long long c = i / 32;
-        const unsigned sh = 2 * (unsigned)(i % 32);
-        for (unsigned long long j = 0; j < c; ++j) lo[j] = __ldg(w + j);
-        uint64_t prev = __ldg(w + c);
-        lo[c] = sh ? prev & ((1ull << sh) - 1ull) : 0ull;
-        ro[0] = prev >> sh;
-        for (unsigned long long j = 1; c + j < nw; ++j) {
-            const uint64_t cur = __ldg(w + c + j);
-            ro[j] = sh ? (cur >> sh) | (prev << (64 - sh)) : cur;
-            prev = cur;
+    if (nw == 0) return;
+    // c = index of the word holding base i; left takes words [0, c] (word c masked), right words [c, nw) shifted down;
+    // idx == 0 / idx == len copy the read through to one side (split.rs:33-42)
+    const bool all_right = i == 0, all_left = i == slen && i != 0;
+    const unsigned long long c = all_right ? 0 : i / 32;
+    const unsigned sh = all_right || all_left ? 0u : 2 * (unsigned)(i % 32);
+    if (nw <= kSpPre) {
+        uint64_t x[kSpPre];
+#pragma unroll
+        for (int j = 0; j < kSpPre; ++j) x[j] = (unsigned long long)j < nw ? __ldg(w + j) : 0ull;
+        if (all_left) {
+#pragma unroll
+            for (int j = 0; j < kSpPre; ++j)
+                if ((unsigned long long)j < nw) lo[j] = x[j];
+            return;
         }
+        if (!all_right) {
+#pragma unroll
+            for (int j = 0; j < kSpPre; ++j) {
+                if ((unsigned long long)j < c) lo[j] = x[j];
+                else if ((unsigned long long)j == c) lo[j] = sh ? x[j] & ((1ull << sh) - 1ull) : 0ull;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kSpPre; ++j) {
+            if ((unsigned long long)j >= c && (unsigned long long)j < nw) {
+                const uint64_t prev = j > 0 ? x[j > 0 ? j - 1 : 0] : 0ull;
+                ro[j - c] = sh ? (x[j] >> sh) | ((unsigned long long)j > c ? prev << (64 - sh) : 0ull) : x[j];
+            }
+        }
+        return;
+    }
+    if (all_left) {
+        for (unsigned long long j = 0; j < nw; ++j) lo[j] = __ldg(w + j);
+        return;
+    }
+    if (!all_right) {
+        for (unsigned long long j = 0; j < c; ++j) lo[j] = __ldg(w + j);
+        lo[c] = sh ? __ldg(w + c) & ((1ull << sh) - 1ull) : 0ull;
+    }
+    uint64_t prev = 0;
+    for (unsigned long long j = c; j < nw; ++j) {
+        const uint64_t cur = __ldg(w + j);
+        ro[j - c] = sh ? (cur >> sh) | (j > c ? prev << (64 - sh) : 0ull) : cur;
+        prev = cur;
     }
 }
 
-constexpr int kSpCap = 2048;   // words of each output span a CTA can stage (256 reads x 8 words: reads up to 256 bases on average)
+constexpr int kSpRows = 8;                            // rows of 32 reads per warp: a CTA tile holds 8 warps x 8 rows x 32 = 2048 reads
+constexpr int kSpTile = kThreads * kSpRows;
+constexpr int kSpCap = 256;                           // words of each output span a warp can stage per row (32 reads x 8 words)
 
-// ONE pass: a CTA takes a tile of 256 consecutive reads (tiles numbered by a ticket, so look-back never waits for a CTA
-// that is not running), reads their (word_offsets, lens, idx) once, scans the two word counts inside the CTA, gets the
-// totals of all earlier tiles by decoupled look-back (lookback.cuh), writes the offsets, and splits one read per thread
-// into a shared-memory image of the tile's two output spans -- which are contiguous in `left` / `right` because the
-// reads are consecutive -- stored with coalesced 8-byte-per-lane stores.  (The three-launch scan + thread-per-read
-// kernel it replaces read the shapes three times and wrote every output word as a lone 8-byte store: 0.50 of the HBM
-// roofline on 40 M short reads.)  A tile whose spans do not fit the image writes straight to global memory.
+// (left, right) word counts of a read; an error takes no room and is reported when `status` is given
+__device__ __forceinline__ bool split_shape(unsigned long long r, unsigned long long nw, unsigned long long slen, unsigned long long i,
+                                            unsigned& nl, unsigned& nr, unsigned long long* status) {
+    nl = nr = 0;
+    const bool oob = i > slen;
+    if (oob || (i && i < slen && nw && nw < (slen + 31) / 32)) {
+        if (status) {
+            const unsigned long long key = r << 1 | (oob ? 0ull : 1ull);
+            if (key < ld_volatile_u64(status)) atomicMin(status, key);
+        }
+        return false;
+    }
+    if (i == 0) nr = (unsigned)nw;
+    else if (i == slen) nl = (unsigned)nw;
+    else if (nw) nl = (unsigned)(i / 32 + 1), nr = (unsigned)(nw - i / 32);
+    return true;
+}
+
+// ONE pass.  A CTA takes a tile of 2048 consecutive reads (tiles numbered by a ticket, so look-back never waits for a CTA
+// that is not running); warp w owns reads [256 w, 256 w + 256) of the tile as 8 rows of 32 (lane l <-> read 32 i + l: every
+// load of the shape arrays and every offset store is a coalesced 256-byte warp transaction).
+//   pass A  the warp reads (word_offsets, lens, idx) of its rows and adds up the two word counts;
+//           the 8 warp totals are scanned, and warp 0 gets the totals of all earlier tiles by decoupled look-back
+//           (lookback.cuh) -- one look-back per 2048 reads (per 256 reads the chain of spinning tiles was slower than
+//           the three-launch scan it replaces: 2.39 ms against 1.46 on 40 M reads);
+//   pass B  row by row the warp reads the shapes again (L1 / L2 hits: the tile's 48 KiB were fetched microseconds ago),
+//           scans the row, writes the offsets, splits one read per lane into a shared-memory image of the row's two
+//           output spans -- contiguous in `left` / `right` because the reads are consecutive -- and stores the image with
+//           coalesced 8-byte-per-lane stores.  A row whose spans do not fit the image writes straight to global memory.
 __global__ void __launch_bounds__(kThreads)
 split_packed_fused_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets,
                           const uint64_t* __restrict__ lens, const uint64_t* __restrict__ idx, unsigned long long n_reads,
                           uint64_t* __restrict__ left, uint64_t* __restrict__ left_offsets, uint64_t* __restrict__ right,
                           uint64_t* __restrict__ right_offsets, unsigned long long* __restrict__ status,
                           unsigned long long* __restrict__ lb, unsigned long long n_tiles) {
-    __shared__ uint64_t s_left[kSpCap], s_right[kSpCap];
-    __shared__ unsigned long long s_tile, s_warp[2][kWarpsPerBlock], s_base[2], s_tot[2];
+    __shared__ uint64_t s_left[kWarpsPerBlock][kSpCap], s_right[kWarpsPerBlock][kSpCap];
+    __shared__ unsigned long long s_tile, s_warp[2][kWarpsPerBlock], s_base[2];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(lb, 1ull);
     __syncthreads();
     const unsigned long long tile = s_tile;
-    const unsigned long long r = tile * kThreads + tid;
-    unsigned long long wo = 0, nw = 0, slen = 0, i = 0, nl = 0, nr = 0;
-    bool live = false;
-    if (r < n_reads) {
-        wo = word_offsets[r];
-        nw = word_offsets[r + 1] - wo;
-        slen = lens[r];
-        i = idx[r];
-        const bool oob = i > slen;
-        if (oob || (i && i < slen && nw && nw < (slen + 31) / 32)) {   // an error: takes no room
-            const unsigned long long key = r << 1 | (oob ? 0ull : 1ull);
-            if (key < ld_volatile_u64(status)) atomicMin(status, key);
-        } else {
-            live = true;
-            if (i == 0) nr = nw;
-            else if (i == slen) nl = nw;
-            else if (nw) nl = i / 32 + 1, nr = nw - i / 32;
-        }
-    }
-    // exclusive scan of (nl, nr) over the CTA
-    unsigned long long il = nl, ir = nr;
+    const unsigned long long row0 = tile * kSpTile + warp * (32 * kSpRows) + lane;   // this lane's read in row 0
+    // ---- pass A: the warp's totals
+    unsigned long long wl = 0, wr = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, ir, o);
-        if (lane >= (unsigned)o) il += a, ir += b;
+    for (int i = 0; i < kSpRows; ++i) {
+        const unsigned long long r = row0 + 32 * i;
+        unsigned nl = 0, nr = 0;
+        if (r < n_reads) {
+            const unsigned long long wo = word_offsets[r];
+            split_shape(r, word_offsets[r + 1] - wo, lens[r], idx[r], nl, nr, status);
+        }
+        wl += nl;
+        wr += nr;
     }
-    if (lane == 31) s_warp[0][warp] = il, s_warp[1][warp] = ir;
+    wl = warp_sum_u64(wl);
+    wr = warp_sum_u64(wr);
+    if (lane == 0) s_warp[0][warp] = wl, s_warp[1][warp] = wr;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long a = lane < kWarpsPerBlock ? s_warp[0][lane] : 0ull, b = lane < kWarpsPerBlock ? s_warp[1][lane] : 0ull;
+        const unsigned long long a = lane < kWarpsPerBlock ? s_warp[0][lane] : 0ull, b = lane < kWarpsPerBlock ? s_warp[1][lane] : 0ull;
         unsigned long long ia = a, ib = b;
 #pragma unroll
         for (int o = 1; o < kWarpsPerBlock; o <<= 1) {
             const unsigned long long x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o);
             if (lane >= (unsigned)o) ia += x, ib += y;
         }
-        if (lane < kWarpsPerBlock) s_warp[0][lane] = ia - a, s_warp[1][lane] = ib - b;
+        if (lane < kWarpsPerBlock) s_warp[0][lane] = ia - a, s_warp[1][lane] = ib - b;   // exclusive prefix of the warp totals
         const unsigned long long agg[2] = {__shfl_sync(0xffffffffu, ia, kWarpsPerBlock - 1), __shfl_sync(0xffffffffu, ib, kWarpsPerBlock - 1)};
         unsigned long long excl[2];
         lookback_exclusive<2>(lb + 1, n_tiles, tile, agg, excl);
-        if (lane == 0) s_base[0] = excl[0], s_base[1] = excl[1], s_tot[0] = agg[0], s_tot[1] = agg[1];
+        if (lane == 0) s_base[0] = excl[0], s_base[1] = excl[1];
     }
     __syncthreads();
-    const unsigned long long ll = s_warp[0][warp] + il - nl, lr = s_warp[1][warp] + ir - nr;   // offsets inside the tile's spans
-    const unsigned long long base_l = s_base[0], base_r = s_base[1], tot_l = s_tot[0], tot_r = s_tot[1];
-    if (r < n_reads) {
-        left_offsets[r] = base_l + ll;
-        right_offsets[r] = base_r + lr;
-        if (r + 1 == n_reads) left_offsets[n_reads] = base_l + ll + nl, right_offsets[n_reads] = base_r + lr + nr;
+    // ---- pass B: row by row, the warp on its own
+    unsigned long long base_l = s_base[0] + s_warp[0][warp], base_r = s_base[1] + s_warp[1][warp];
+    // the shapes of row i + 1 are fetched while row i is split (a row is two dependent round trips otherwise: shapes, then words)
+    unsigned long long p_wo = 0, p_nw = 0, p_slen = 0, p_ix = 0;
+    if (row0 < n_reads) {
+        p_wo = word_offsets[row0];
+        p_nw = word_offsets[row0 + 1] - p_wo;
+        p_slen = lens[row0];
+        p_ix = idx[row0];
     }
-    const bool staged = tot_l <= kSpCap && tot_r <= kSpCap;
-    if (live) split_one(words + wo, nw, slen, i, staged ? s_left + ll : left + base_l + ll, staged ? s_right + lr : right + base_r + lr);
-    if (staged) {
-        __syncthreads();
-        for (unsigned long long k = tid; k < tot_l; k += kThreads) left[base_l + k] = s_left[k];
-        for (unsigned long long k = tid; k < tot_r; k += kThreads) right[base_r + k] = s_right[k];
+#pragma unroll 1
+    for (int i = 0; i < kSpRows; ++i) {
+        const unsigned long long r = row0 + 32 * i;
+        const unsigned long long wo = p_wo, nw = p_nw, slen = p_slen, ix = p_ix;
+        if (i + 1 < kSpRows && r + 32 < n_reads) {
+            p_wo = word_offsets[r + 32];
+            p_nw = word_offsets[r + 33] - p_wo;
+            p_slen = lens[r + 32];
+            p_ix = idx[r + 32];
+        }
+        unsigned nl = 0, nr = 0;
+        bool live = false;
+        if (r < n_reads) live = split_shape(r, nw, slen, ix, nl, nr, nullptr);
+        unsigned il = nl, ir = nr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, ir, o);
+            if (lane >= (unsigned)o) il += a, ir += b;
+        }
+        const unsigned tot_l = __shfl_sync(0xffffffffu, il, 31), tot_r = __shfl_sync(0xffffffffu, ir, 31);
+        const unsigned ll = il - nl, lr = ir - nr;               // offsets inside the row's spans
+        if (r < n_reads) {
+            left_offsets[r] = base_l + ll;
+            right_offsets[r] = base_r + lr;
+            if (r + 1 == n_reads) left_offsets[n_reads] = base_l + il, right_offsets[n_reads] = base_r + ir;
+        }
+        const bool staged = tot_l <= (unsigned)kSpCap && tot_r <= (unsigned)kSpCap;   // warp-uniform
+        if (live) split_one(words + wo, nw, slen, ix, staged ? s_left[warp] + ll : left + base_l + ll, staged ? s_right[warp] + lr : right + base_r + lr);
+        if (staged) {
+            __syncwarp();
+            for (unsigned k = lane; k < tot_l; k += 32) left[base_l + k] = s_left[warp][k];
+            for (unsigned k = lane; k < tot_r; k += 32) right[base_r + k] = s_right[warp][k];
+            __syncwarp();
+        }
+        base_l += tot_l;
+        base_r += tot_r;
     }
 }
 
 // ticket + two channels of tile descriptors
-size_t split_packed_scratch_bytes(size_t n_reads) { return lookback_bytes(ceil_div(n_reads ? n_reads : 1, kThreads), 2); }
+size_t split_packed_scratch_bytes(size_t n_reads) { return lookback_bytes(ceil_div(n_reads ? n_reads : 1, kSpTile), 2); }
 
 cudaError_t launch_split_packed_batch(const DeviceInfo&, const uint64_t* d_words, const uint64_t* d_word_offsets,
                                       const uint64_t* d_lens, const uint64_t* d_idx, size_t n_reads, uint64_t* d_left,
@@ -138,7 +217,7 @@ cudaError_t launch_split_packed_batch(const DeviceInfo&, const uint64_t* d_words
         e = cudaMemsetAsync(d_left_offsets, 0, sizeof(uint64_t), s);
         return e != cudaSuccess ? e : cudaMemsetAsync(d_right_offsets, 0, sizeof(uint64_t), s);
     }
-    const unsigned long long n_tiles = ceil_div(n_reads, kThreads);
+    const unsigned long long n_tiles = ceil_div(n_reads, kSpTile);
     e = cudaMemsetAsync(d_scratch, 0, lookback_bytes(n_tiles, 2), s);
     if (e != cudaSuccess) return e;
     split_packed_fused_kernel<<<(unsigned)n_tiles, kThreads, 0, s>>>(d_words, d_word_offsets, d_lens, d_idx, n_reads, d_left, d_left_offsets,

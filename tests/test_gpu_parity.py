@@ -351,7 +351,8 @@ def make_reads(rng, lens, mixed=True):
     return data, offsets
 
 
-@pytest.mark.parametrize("profile", ["short", "cfg5", "with_empties", "single", "mostly_empty", "illumina", "mixed"])
+@pytest.mark.parametrize("profile", ["short", "cfg5", "with_empties", "single", "mostly_empty", "illumina", "mixed", "short_with_long",
+                                     "strip_edge", "many_tiles"])
 def test_encode_batch_matches_oracle(bn, profile):
     rng = np.random.default_rng(23)
     lens = {
@@ -362,6 +363,11 @@ def test_encode_batch_matches_oracle(bn, profile):
         "mostly_empty": np.where(rng.random(20000) < 0.97, 0, rng.integers(1, 40, 20000)),   # > 32 reads start in one group
         "illumina": rng.integers(100, 152, 6000),
         "mixed": np.where(rng.random(2500) < 0.9, rng.integers(20, 300, 2500), rng.integers(300, 20000, 2500)),
+        # the one-pass short-read kernel (average <= 192 bytes per read) with rows that do not fit a warp's strip: a long read among
+        # short ones, and rows of 32 reads right at the strip's capacity (32 x 256 bytes / 288 words) between rows of small reads
+        "short_with_long": np.where(rng.random(6000) < 0.99, rng.integers(50, 151, 6000), rng.integers(2000, 5000, 6000)),
+        "strip_edge": np.concatenate([np.concatenate([rng.integers(250, 262, 32), rng.integers(0, 120, 96)]) for _ in range(30)]),
+        "many_tiles": rng.integers(0, 70, 150_000),   # 74 tiles of 2048 reads: the look-back chain
     }[profile]
     data, offsets = make_reads(rng, lens)
     words, wo = bn.encode_batch(data, offsets)

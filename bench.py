@@ -84,11 +84,15 @@ def recorded_traffic():
 def roofline(kernel: str, algorithmic_bytes: float, ms: float, traffic_key: str | None = None) -> dict:
     peak, src = measured_peak()
     achieved = algorithmic_bytes / (ms * 1e-3) / 1e9
-    t = (recorded_traffic() or {}).get(traffic_key or kernel)
+    rec = (recorded_traffic() or {}).get(traffic_key or kernel)
+    t = None
+    if isinstance(rec, dict) and rec.get("algorithmic") and abs(algorithmic_bytes - rec["algorithmic"]) <= 0.01 * rec["algorithmic"]:
+        t = rec["traffic"]   # the committed capture is of a launch of this size
     return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": src, "frac_of_nominal_8000": achieved / 8000.0, "algorithmic_bytes_per_launch": algorithmic_bytes,
             "ms_per_launch": ms, "traffic": t,
-            "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture committed with the repo; not measured in this run)" if t else None}
+            "traffic_source": ("profiles/roofline_traffic.json: dram bytes of one launch of this size from the ncu --set full capture committed "
+                               "with the repo -- a constant of the repo, NOT measured in this run") if t else None}
 
 
 class ClockSampler:
@@ -397,6 +401,62 @@ def leg_pcie_ceiling(job: Job, h_up, h_dn, nbytes: int):
                    "wall clock between barriers, max over ranks, best of 4"}
 
 
+def leg_pcie_pattern(job: Job, h_big_up, h_small_dn, h_small_up, h_big_dn, n: int, steps: int):
+    """The same denominator, for the COPY PATTERN of the pipelined schedule rather than for two monolithic copies: thread A
+    moves the chunks of an encode (64 MiB up, 16 MiB down per chunk), thread B those of a decode (16 MiB up, 64 MiB down),
+    each through three rotating streams exactly as bn_encode / bn_decode issue them -- but with NO kernel in between.  What
+    this gives is all the link offers the pipelined round trip (tools/pcie_pattern.cu is the C++ form of this probe)."""
+    torch = job.torch
+    rt = cudart()
+    chunk = 64 << 20
+    n_chunks = (n + chunk - 1) // chunk
+    d_a = torch.empty(3 * chunk + 3 * (chunk // 4), dtype=torch.uint8, device=job.dev)
+    d_b = torch.empty(3 * chunk + 3 * (chunk // 4), dtype=torch.uint8, device=job.dev)
+
+    def call(d, h_up, h_dn, up_unit, dn_unit, streams, events):
+        # chunk c: up_unit bytes per base-chunk up, dn_unit down (1 or 1/4 byte per base)
+        for c in range(n_chunks):
+            k = c % 3
+            bases = min(chunk, n - c * chunk)
+            if c >= 3:
+                events[k].synchronize()
+            up, dn = int(bases * up_unit) & ~7, int(bases * dn_unit) & ~7
+            big, small = d.data_ptr() + k * chunk, d.data_ptr() + 3 * chunk + k * (chunk // 4)   # the stage's two device buffers
+            rt.cudaMemcpyAsync(big if up_unit == 1.0 else small, h_up.ctypes.data + int(c * chunk * up_unit), up, 1, streams[k].cuda_stream)
+            rt.cudaMemcpyAsync(h_dn.ctypes.data + int(c * chunk * dn_unit), big if dn_unit == 1.0 else small, dn, 2, streams[k].cuda_stream)
+            events[k].record(streams[k])
+        for k in range(min(3, n_chunks)):
+            events[k].synchronize()
+
+    sa, sb = [torch.cuda.Stream() for _ in range(3)], [torch.cuda.Stream() for _ in range(3)]
+    ea, eb = [torch.cuda.Event(blocking=True) for _ in range(3)], [torch.cuda.Event(blocking=True) for _ in range(3)]
+
+    def run():
+        def a():
+            torch.cuda.set_device(job.local)
+            for _ in range(steps):
+                call(d_a, h_big_up, h_small_dn.view(job.np.uint8), 1.0, 0.25, sa, ea)
+
+        def b():
+            torch.cuda.set_device(job.local)
+            for _ in range(steps):
+                call(d_b, h_small_up.view(job.np.uint8), h_big_dn, 0.25, 1.0, sb, eb)
+
+        job.barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=a), threading.Thread(target=b)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps
+
+    run()
+    (t,) = job.rmax(run())
+    return t
+
+
 def leg_e2e(job: Job, asc, n: int, K: int):
     """End to end through the host-pointer API (bn_encode / bn_decode) on pinned host buffers, every H2D and D2H copy inside
     the timed region.  Three schedules of the same calls:
@@ -422,6 +482,9 @@ def leg_e2e(job: Job, asc, n: int, K: int):
     bn.encode_np(h_seq, ctx_a, out=h_words[1])
 
     pcie = leg_pcie_ceiling(job, h_seq, h_back, n)
+    pcie["pattern_s"] = leg_pcie_pattern(job, h_seq, h_words[0], h_words[1], h_back, n, 4)
+    h_seq[:] = asc.cpu().numpy()   # the probes overwrote nothing of h_seq, but h_back / h_words hold copies of device scratch now
+    bn.encode_np(h_seq, ctx_a, out=h_words[1])
 
     def wall(fn):
         job.barrier()
@@ -956,14 +1019,20 @@ def report(args, job, n, K, W, total_ms, enc_ms, dec_ms, clocks, e2e, strong, cf
             "serial_value": gb(e2e["serial"]), "serial_ms_per_step": e2e["serial"] * 1e3,
             "staggered_value": gb(e2e["staggered"]), "staggered_ms_per_step": e2e["staggered"] * 1e3,
             "pageable_value": gb(e2e["pageable"]),
-            "pcie_ceiling_gbs": pc, "pcie_gbs_moved": moved, "frac_of_pcie_ceiling": moved / pc["both"],
+            "pcie_ceiling_gbs": {k: v for k, v in pc.items() if k != "pattern_s"}, "pcie_gbs_moved": moved,
+            "frac_of_pcie_ceiling": moved / pc["both"],
+            "pcie_pattern_ms_per_step": pc["pattern_s"] * 1e3, "pcie_pattern_gbs": 2 * per_step * world / pc["pattern_s"] / 1e9,
+            "frac_of_pcie_pattern": pc["pattern_s"] / e2e["pipelined"],
             "api": "bitnuc_b200.encode_np + decode_np (bn_encode / bn_decode, pinned host buffers, chunked 3-stage pipeline inside each "
                    "call), every H2D / D2H copy inside the timed region.  value = the pipelined schedule (two host threads, one bn_ctx "
                    "each: encode of step i+1 overlaps decode of step i over the full-duplex link) at every N.  serial_value: one "
                    "thread, encode then decode; staggered_value: serial with odd ranks decoding first; pageable_value: the serial "
                    "schedule on pageable numpy buffers, bounced through pinned stage buffers by the library (informational).  "
                    "pcie_ceiling_gbs: raw pinned copies of the same bytes on all N ranks at once -- the host of this box, not the "
-                   "kernels, bounds e2e (frac_of_pcie_ceiling = bytes moved per second / the both-directions ceiling)"}
+                   "kernels, bounds e2e (frac_of_pcie_ceiling = bytes moved per second / the both-directions ceiling of two monolithic "
+                   "copies).  pcie_pattern_*: the chunked copy sequence of the pipelined schedule itself (64 MiB up + 16 MiB down per "
+                   "encode chunk, the reverse per decode chunk, three rotating streams per call) issued with NO kernels: what the link "
+                   "gives that pattern; frac_of_pcie_pattern = its time / the e2e step time"}
     else:
         line["e2e"] = None
 

@@ -287,6 +287,86 @@ private:
     size_t length_;
 };
 
+// The hot path sharded over the GPUs of one box from one process (bn_multi_* of bitnuc_cuda.h).  The reference is
+// single-threaded and has no analogue (src/lib.rs:214-220 is its whole surface); the methods keep the reference's
+// argument order and Vec semantics so that `multi.encode(seq, ebuf)` reads like `bitnuc::encode(seq, ebuf)`.  Shards are
+// contiguous (base ranges on 64-base boundaries, pairs / reads by index, variable-length reads by byte volume); the four
+// base counters are summed over the shards by ncclAllReduce (Reduce::Nccl) or by the library's own all-reduce kernel over
+// NVLink peer memory (Reduce::P2p; also the mode for a device list that names one device twice).
+class Multi {
+public:
+    enum class Reduce { Nccl = BN_REDUCE_NCCL, P2p = BN_REDUCE_P2P };
+    struct PackedBatch {
+        std::vector<uint64_t> words, word_offsets;   // read r = words[word_offsets[r] .. word_offsets[r+1])
+    };
+    // devices empty = every visible device
+    explicit Multi(const std::vector<int>& devices = {}, Reduce reduce = Reduce::Nccl) {
+        bn_error_t e{};
+        const int rc = bn_multi_create(devices.empty() ? nullptr : devices.data(), static_cast<int>(devices.size()), static_cast<int>(reduce), &m_);
+        e.code = rc;
+        detail::check(rc, e);
+    }
+    ~Multi() { bn_multi_destroy(m_); }
+    Multi(const Multi&) = delete;
+    Multi& operator=(const Multi&) = delete;
+    int size() const { return bn_multi_size(m_); }
+    bn_multi* handle() const { return m_; }
+
+    void encode(Bytes sequence, std::vector<uint64_t>& ebuf) const {   // src/utils/mod.rs:22, over all devices
+        if (sequence.len == 0) detail::check(BN_ERR_EMPTY_ENCODE, bn_error_t{});
+        ebuf.clear();
+        ebuf.resize((sequence.len + 31) / 32);
+        size_t n_words = 0;
+        bn_error_t e{};
+        const int rc = bn_multi_encode(m_, sequence.ptr, sequence.len, ebuf.data(), &n_words, &e);
+        ebuf.resize(n_words);
+        detail::check(rc, e);
+    }
+    void decode(Words ebuf, size_t n_bases, std::vector<uint8_t>& dbuf) const {   // src/utils/mod.rs:60 -- appends
+        const size_t old = dbuf.size();
+        dbuf.resize(old + n_bases);
+        bn_error_t e{};
+        const int rc = bn_multi_decode(m_, ebuf.ptr, ebuf.len, n_bases, dbuf.data() + old, &e);
+        if (rc != BN_OK) dbuf.resize(old);
+        detail::check(rc, e);
+    }
+    uint64_t hdist_total(Words ebuf1, Words ebuf2, size_t n_bases) const {
+        uint64_t total = 0;
+        bn_error_t e{};
+        detail::check(bn_multi_hdist(m_, ebuf1.ptr, ebuf1.len, ebuf2.ptr, ebuf2.len, n_bases, &total, &e), e);
+        return total;
+    }
+    uint32_t hdist(Words ebuf1, Words ebuf2, size_t n_bases) const { return static_cast<uint32_t>(hdist_total(ebuf1, ebuf2, n_bases)); }
+    std::vector<uint32_t> hdist_pairs(Words u, Words v, size_t len) const {   // hdist_scalar per pair, hamming/scalar.rs:11
+        const size_t n = u.len < v.len ? u.len : v.len;
+        std::vector<uint32_t> out(n);
+        bn_error_t e{};
+        detail::check(bn_multi_hdist_pairs(m_, u.ptr, v.ptr, n, static_cast<uint32_t>(len > 0xFFFFFFFFu ? 0xFFFFFFFFu : len), out.data(), &e), e);
+        return out;
+    }
+    // BaseCount::base_counts + GCContent::gc_content of one packed sequence; the counters are all-reduced over the shards
+    PackedSequence::Counts base_counts(Words words, size_t n_bases, double* gc = nullptr) const {
+        PackedSequence::Counts c{};
+        bn_error_t e{};
+        detail::check(bn_multi_base_counts(m_, words.ptr, words.len, n_bases, c.v, gc, &e), e);
+        return c;
+    }
+    // the caller's loop `for read in reads { PackedSequence::new(read)? }` over a batch of offset-indexed reads
+    PackedBatch encode_batch(Bytes bytes, const std::vector<uint64_t>& offsets) const {
+        PackedBatch out;
+        const size_t n_reads = offsets.empty() ? 0 : offsets.size() - 1;
+        out.word_offsets.assign(n_reads + 1, 0);
+        out.words.resize(n_reads ? static_cast<size_t>((offsets[n_reads] - offsets[0]) / 32) + n_reads : 0);
+        bn_error_t e{};
+        detail::check(bn_multi_encode_batch(m_, bytes.ptr, offsets.data(), n_reads, out.words.data(), out.word_offsets.data(), nullptr, &e), e);
+        out.words.resize(out.word_offsets[n_reads]);
+        return out;
+    }
+
+private:
+    bn_multi* m_ = nullptr;
+};
+
 }  // namespace bitnuc
 
 namespace std {

@@ -2,6 +2,7 @@
 // (include/bitnuc.hpp) of the drop-in API.  One function per #[test] of the reference, same inputs,
 // same assertions; every call runs on the GPU through libbitnuc_cuda.so.
 //   build: g++ -std=c++17 -O1 -I include tests/cpp/test_reference_suite.cpp -L bitnuc_b200 -lbitnuc_cuda -Wl,-rpath,$PWD/bitnuc_b200
+#include <cctype>
 #include <cstdio>
 #include <functional>
 #include <random>
@@ -266,12 +267,51 @@ static void test_fastq_records() {
     CHECK(f.size() == 2 && f.seq_lens[1] == 5 && f.words[1] == as_2bit("ACGTT") && fa.substr(f.seq_offsets[0], 8) == "ACGTACGT");
 }
 
+// bitnuc::Multi: the reference's functions with the work cut over two shards (device 0 named twice -- the way a one-GPU
+// box exercises the sharding; that needs the NVLink-mailbox reduce, NCCL refuses a repeated device).  Results must equal
+// the single-context calls.
+static void test_multi() {
+    Multi m({0, 0}, Multi::Reduce::P2p);
+    CHECK(m.size() == 2);
+    std::string seq;
+    for (int i = 0; i < 5000; ++i) seq += "ACGTTGCAacgt"[(i * 7 + i / 13) % 12];
+    std::vector<uint64_t> a, b;
+    encode(seq, a);
+    m.encode(seq, b);
+    CHECK(a == b);
+    std::vector<uint8_t> back{'x'};
+    m.decode(b, seq.size(), back);                       // appends
+    CHECK(back.size() == seq.size() + 1 && back[0] == 'x');
+    for (size_t i = 0; i < seq.size(); ++i) CHECK(back[i + 1] == (uint8_t)std::toupper(seq[i]));
+    std::string other = seq;
+    for (size_t i = 0; i < other.size(); i += 17) other[i] = other[i] == 'A' ? 'C' : 'A';
+    std::vector<uint64_t> c;
+    encode(other, c);
+    CHECK(m.hdist(a, c, seq.size()) == hdist(a, c, seq.size()));
+    PackedSequence ps(seq);
+    double gc = -1.0;
+    CHECK(m.base_counts(a, seq.size(), &gc) == ps.base_counts() && gc == ps.gc_content());
+    bool threw = false;
+    try {
+        std::string bad = seq;
+        bad[4321] = 'N';
+        m.encode(bad, b);
+    } catch (const NucleotideError& e) {
+        threw = e.variant == NucleotideError::InvalidBase && e.a == 'N';
+    }
+    CHECK(threw && b.size() == 4321 / 32);               // the words of the chunks before the failing chunk (avx.rs:142-143)
+    const std::vector<uint64_t> offsets{0, 10, 10, 75, 5000};
+    const Multi::PackedBatch pb = m.encode_batch(seq, offsets);
+    CHECK(pb.word_offsets == (std::vector<uint64_t>{0, 1, 1, 4, 4 + (4925 + 31) / 32}));
+    CHECK(pb.words[0] == as_2bit(seq.substr(0, 10)) && pb.words[1] == as_2bit(seq.substr(10, 32)));
+}
+
 int main() {
     const std::pair<const char*, std::function<void()>> tests[] = {
         {"as_2bit", test_as_2bit}, {"from_2bit", test_from_2bit}, {"roundtrips", test_roundtrips},
         {"hdist", test_hdist},     {"packed_sequence", test_packed_sequence}, {"errors", test_errors},
         {"split_packed", test_split_packed}, {"readme_kmer_counting", test_readme_kmer_counting},
-        {"fastq_records", test_fastq_records}};
+        {"fastq_records", test_fastq_records}, {"multi", test_multi}};
     for (const auto& t : tests) {
         t.second();
         std::printf("ok %s\n", t.first);

@@ -482,9 +482,8 @@ def leg_e2e(job: Job, asc, n: int, K: int):
     bn.encode_np(h_seq, ctx_a, out=h_words[1])
 
     pcie = leg_pcie_ceiling(job, h_seq, h_back, n)
-    pcie["pattern_s"] = leg_pcie_pattern(job, h_seq, h_words[0], h_words[1], h_back, n, 4)
-    h_seq[:] = asc.cpu().numpy()   # the probes overwrote nothing of h_seq, but h_back / h_words hold copies of device scratch now
-    bn.encode_np(h_seq, ctx_a, out=h_words[1])
+    pcie["pattern_s"] = leg_pcie_pattern(job, h_seq, h_words[0], h_words[1], h_back, n, 4)   # h_words[0] / h_back now hold device scratch:
+                                                                                             # every schedule below rewrites them first
 
     def wall(fn):
         job.barrier()
@@ -911,6 +910,8 @@ def cpu_suite_main(args):
             "kmers": s.kmers(), "hdist": s.hdist(), "base_counts": s.base_counts(), "encode_batch": B.encode_batch(s)}
     rows["cfg0"] = B.Suite(threads=1, reps=7).codec(n_single=1_000_000, n_many=1_000_000, seq=seq[:1_000_000], grid=[(path, 1)])  # configs[0]
     rows["seconds"] = time.time() - t0
+    model = next((l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")), "unknown")
+    rows["host"] = {"cpu": model, "threads": s.threads, "compiler": "gcc -O3 -march=native -ffp-contract=off (oracle/Makefile, target `native`)"}
     print(json.dumps(rows))
 
 
@@ -1049,7 +1050,7 @@ def report(args, job, n, K, W, total_ms, enc_ms, dec_ms, clocks, e2e, strong, cf
                 "sample": f"the whole workload ({allc['sample']}), encode + decode, median of {allc['reps']} repetitions on {allc['cores']} pinned "
                           f"threads in a process of its own; C restatement of the reference's {allc['isa']} path (oracle/bitnuc_oracle.c, "
                           f"-march=native)",
-                "rows": cpu_rows["codec"]}
+                "rows": cpu_rows["codec"], "host": cpu_rows.get("host")}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"error": str(ex)}
 

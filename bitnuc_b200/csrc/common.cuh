@@ -40,6 +40,7 @@ __device__ __forceinline__ void st_stream_v2(uint2* p, uint2 v) {
 __device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long r;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p));

@@ -112,6 +112,14 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
 #pragma unroll 1
     for (int row = 0; row < kSlRows; ++row) {
     const unsigned long long q = row0 + 32 * row;
+    if (row + 1 < kSlRows) {   // ask for the next row's words now: its cut then starts on L1 hits
+        const unsigned long long nsrc = s_src[row + 1][threadIdx.x];
+        const unsigned ncnt = s_cnt[row + 1][threadIdx.x];
+        if (ncnt && ncnt <= kSliceShort) {
+            prefetch_l1(words + (nsrc >> 5));
+            prefetch_l1(words + ((nsrc + ncnt - 1) >> 5));
+        }
+    }
     unsigned long long cnt = s_cnt[row][threadIdx.x];
     if (cnt == 0xFFFFFFFFull) cnt = q_end[q] - q_start[q];
     unsigned long long inc = cnt;

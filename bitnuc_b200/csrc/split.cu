@@ -157,24 +157,34 @@ split_packed_fused_kernel(const uint64_t* __restrict__ words, const uint64_t* __
     __syncthreads();
     // ---- pass B: row by row, the warp on its own
     unsigned long long base_l = s_base[0] + s_warp[0][warp], base_r = s_base[1] + s_warp[1][warp];
-    // the shapes of row i + 1 are fetched while row i is split (a row is two dependent round trips otherwise: shapes, then words)
-    unsigned long long p_wo = 0, p_nw = 0, p_slen = 0, p_ix = 0;
-    if (row0 < n_reads) {
-        p_wo = word_offsets[row0];
-        p_nw = word_offsets[row0 + 1] - p_wo;
-        p_slen = lens[row0];
-        p_ix = idx[row0];
-    }
+    // Software pipeline over the rows (a row is two dependent round trips otherwise: shapes, then words): while row i is
+    // split, the words of row i + 1 are on their way into L1 (its shapes arrived an iteration ago) and the shapes of row
+    // i + 2 are being fetched.
+    struct Shape {
+        unsigned long long wo, nw, slen, ix;
+    };
+    auto load_shape = [&](unsigned long long r) {
+        Shape sh{0, 0, 0, 0};
+        if (r < n_reads) {
+            sh.wo = word_offsets[r];
+            sh.nw = word_offsets[r + 1] - sh.wo;
+            sh.slen = lens[r];
+            sh.ix = idx[r];
+        }
+        return sh;
+    };
+    Shape cur = load_shape(row0), nxt = load_shape(row0 + 32);
 #pragma unroll 1
     for (int i = 0; i < kSpRows; ++i) {
         const unsigned long long r = row0 + 32 * i;
-        const unsigned long long wo = p_wo, nw = p_nw, slen = p_slen, ix = p_ix;
-        if (i + 1 < kSpRows && r + 32 < n_reads) {
-            p_wo = word_offsets[r + 32];
-            p_nw = word_offsets[r + 33] - p_wo;
-            p_slen = lens[r + 32];
-            p_ix = idx[r + 32];
+        if (i + 1 < kSpRows && nxt.nw && nxt.nw <= 64) {   // (a hint for sane shapes only: a bogus word count must not form an address)
+            prefetch_l1(words + nxt.wo);
+            prefetch_l1(words + nxt.wo + nxt.nw - 1);
         }
+        const Shape nn = i + 2 < kSpRows ? load_shape(r + 64) : Shape{0, 0, 0, 0};
+        const unsigned long long wo = cur.wo, nw = cur.nw, slen = cur.slen, ix = cur.ix;
+        cur = nxt;
+        nxt = nn;
         unsigned nl = 0, nr = 0;
         bool live = false;
         if (r < n_reads) live = split_shape(r, nw, slen, ix, nl, nr, nullptr);

@@ -80,6 +80,8 @@ PROTOTYPES = {
     "bn_fastq_encode": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _errp]),
     "bn_fasta_scan": (_int, [_vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), _errp]),
     "bn_fasta_encode": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _errp]),
+    "bn_fasta_wrapped_scan": (_int, [_vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), _errp]),
+    "bn_fasta_wrapped_encode": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _errp]),
     "bn_fasta_count_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "bn_fasta_index_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bn_fasta_encode_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -387,6 +387,28 @@ def fastq_encode(text, ctx: Context | None = None, _fasta: bool = False):
     return words[:w], wo, so[:n], sl[:n]
 
 
+def fasta_wrapped_encode(text, ctx: Context | None = None):
+    """Wrapped (multi-line) FASTA text -> (words, word_offsets, header_offsets, seq_lens): a ``>`` header line, then any
+    number of sequence lines per record, whose concatenation is the record's sequence -- what a FASTA reader hands to
+    ``PackedSequence::new(record.seq())`` (README.md:160-180).  Raises ``FastqError`` when the text does not open with a
+    header, else ``InvalidBase`` (``.record``, ``.position`` inside the record's sequence) for the first bad byte."""
+    ctx = ctx or default_context()
+    t = _u8(text)
+    nr, nb, nw, err = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), BnError()
+    rc = ctx.lib.bn_fasta_wrapped_scan(ctx.handle, _p(t), t.size, C.byref(nr), C.byref(nb), C.byref(nw), C.byref(err))
+    if rc == 1:
+        e = NucleotideError.InvalidBase(err.base)
+        e.record, e.position, e.offset = int(err.record), int(err.b), int(err.offset)
+        raise e
+    raise_for(rc, err)
+    n, w = nr.value, nw.value
+    words = np.empty(max(1, w), dtype=np.uint64)
+    wo = np.zeros(n + 1, dtype=np.uint64)
+    ho, sl = np.empty(max(1, n), dtype=np.uint64), np.empty(max(1, n), dtype=np.uint64)
+    raise_for(ctx.lib.bn_fasta_wrapped_encode(ctx.handle, _p(t), t.size, n, w, _p(words), _p(wo), _p(ho), _p(sl), C.byref(err)), err)
+    return words[:w], wo, ho[:n], sl[:n]
+
+
 # ------------------------------------------------------------------ split_packed -------------
 
 def split_packed_batch(words, word_offsets, lens, idx, ctx: Context | None = None):

@@ -1492,6 +1492,107 @@ static int fastx_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t
     return set_err(err, BN_OK);
 }
 
+// Wrapped (multi-line) FASTA: '>' header line, then any number of sequence lines per record.  bn_fasta_wrapped_scan uploads
+// the text and does all the device work (line table, compaction of the sequence bytes, batch encode of the records); the
+// results stay resident on the context and bn_fasta_wrapped_encode copies them out into buffers the caller sized from the scan.
+int bn_fasta_wrapped_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_records, size_t* n_bases, size_t* n_words, bn_error_t* err) {
+    if (!ctx || !n_records || !n_bases || !n_words || (n_bytes && !text)) return set_err(err, BN_ERR_ARGUMENT);
+    *n_records = *n_bases = *n_words = 0;
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
+    ctx->fq_valid = false;
+    ctx->fq_text = text;
+    ctx->fq_bytes = n_bytes;
+    ctx->fq_reads = ctx->fq_words = 0;
+    ctx->fq_fasta = 2;   // wrapped
+    if (n_bytes == 0) {
+        ctx->fq_valid = true;
+        return set_err(err, BN_OK);
+    }
+    cudaStream_t st = ctx->stream;
+    BN_CUDA(ensure(ctx->fq[0], n_bytes + 16));
+    BN_CUDA(ensure(ctx->fq[1], bn::fastq_scratch_bytes(n_bytes)));
+    const uint8_t* d_text = static_cast<const uint8_t*>(ctx->fq[0].p);
+    if (const int rc = upload_whole(ctx, ctx->fq[0].p, text, n_bytes, err)) return rc;
+    BN_CUDA(bn::launch_fastq_count(ctx->di, d_text, n_bytes, ctx->fq[1].p, reinterpret_cast<uint64_t*>(ctx->d_words + 10), 1, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 10, ctx->d_words + 10, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const size_t n_lines = (size_t)ctx->h_words[10];
+    BN_CUDA(ensure(ctx->fq[2], bn::fasta_wrapped_scratch_bytes(n_lines)));
+    BN_CUDA(bn::launch_fasta_wrapped_index(ctx->di, d_text, n_bytes, n_lines, ctx->fq[1].p, ctx->fq[2].p,
+                                           reinterpret_cast<uint64_t*>(ctx->d_words + 14), ctx->d_words + 12, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 12, ctx->d_words + 12, 32, cudaMemcpyDeviceToHost, st));   // status pair, records, bases
+    BN_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_words[13] != kNoError) return fastq_fault(err, ctx->h_words[13]);
+    const size_t nr = (size_t)ctx->h_words[14], nb = (size_t)ctx->h_words[15];
+    // fq[3] header offsets | fq[4] record offsets into the compacted sequence | fq[5] word offsets | fq[6] words; slot[0] the compacted bytes
+    BN_CUDA(ensure(ctx->fq[3], nr * 8 + 8));
+    BN_CUDA(ensure(ctx->fq[4], (nr + 1) * 8));
+    BN_CUDA(ensure(ctx->fq[5], (nr + 1) * 8));
+    BN_CUDA(ensure(ctx->fq[6], (nb / 32 + nr) * 8 + 8));
+    BN_CUDA(ensure(ctx->slot[0], nb + 16));
+    BN_CUDA(ensure(ctx->slot[7], bn::encode_batch_scratch_bytes(nr, nb)));
+    BN_CUDA(bn::launch_fasta_wrapped_compact(ctx->di, d_text, n_lines, ctx->fq[2].p, nr, static_cast<uint8_t*>(ctx->slot[0].p),
+                                             static_cast<uint64_t*>(ctx->fq[4].p), static_cast<uint64_t*>(ctx->fq[3].p), st));
+    BN_CUDA(bn::launch_encode_batch(ctx->di, static_cast<const uint8_t*>(ctx->slot[0].p), static_cast<const uint64_t*>(ctx->fq[4].p), nr, nb,
+                                    static_cast<uint64_t*>(ctx->fq[6].p), static_cast<uint64_t*>(ctx->fq[5].p), nullptr, ctx->d_words + 12,
+                                    ctx->slot[7].p, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 11, static_cast<uint64_t*>(ctx->fq[5].p) + nr, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaMemcpyAsync(ctx->h_words + 12, ctx->d_words + 12, 8, cudaMemcpyDeviceToHost, st));
+    BN_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long key = ctx->h_words[12];
+    if (key != kNoError) {   // the first invalid base in file order: record and position inside the record's sequence
+        invalid_base(err, key, 0);
+        if (err && nr) {
+            std::vector<uint64_t> ro(nr + 1);
+            BN_CUDA(cudaMemcpyAsync(ro.data(), ctx->fq[4].p, (nr + 1) * 8, cudaMemcpyDeviceToHost, st));
+            BN_CUDA(cudaStreamSynchronize(st));
+            const uint64_t off = key >> 8;   // offset in the concatenated sequence bytes
+            const size_t r = (size_t)(std::upper_bound(ro.begin(), ro.end(), off) - ro.begin()) - 1;
+            err->record = r;
+            err->b = off - ro[r];
+        }
+        return BN_INVALID_BASE;
+    }
+    ctx->fq_reads = nr;
+    ctx->fq_words = nr ? (size_t)ctx->h_words[11] : 0;
+    ctx->fq_valid = true;
+    *n_records = nr;
+    *n_bases = nb;
+    *n_words = ctx->fq_words;
+    return set_err(err, BN_OK);
+}
+
+int bn_fasta_wrapped_encode(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t n_records, size_t n_words, uint64_t* out_words,
+                            uint64_t* out_word_offsets, uint64_t* header_offsets, uint64_t* seq_lens, bn_error_t* err) {
+    if (!ctx) return set_err(err, BN_ERR_ARGUMENT);
+    DeviceGuard g(ctx->di.device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    StageDrain drain{ctx};
+    // only valid right after bn_fasta_wrapped_scan of the same text on this context
+    if (!ctx->fq_valid || ctx->fq_fasta != 2 || ctx->fq_text != text || ctx->fq_bytes != n_bytes || ctx->fq_reads != n_records ||
+        ctx->fq_words != n_words || (n_words && !out_words))
+        return set_err(err, BN_ERR_ARGUMENT);
+    if (n_records == 0) {
+        if (out_word_offsets) out_word_offsets[0] = 0;
+        return set_err(err, BN_OK);
+    }
+    cudaStream_t st = ctx->stream;
+    if (n_words) BN_CUDA(cudaMemcpyAsync(out_words, ctx->fq[6].p, n_words * 8, cudaMemcpyDeviceToHost, st));
+    if (out_word_offsets) BN_CUDA(cudaMemcpyAsync(out_word_offsets, ctx->fq[5].p, (n_records + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (header_offsets) BN_CUDA(cudaMemcpyAsync(header_offsets, ctx->fq[3].p, n_records * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<uint64_t> ro;
+    if (seq_lens) {
+        ro.resize(n_records + 1);
+        BN_CUDA(cudaMemcpyAsync(ro.data(), ctx->fq[4].p, (n_records + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    BN_CUDA(cudaStreamSynchronize(st));
+    if (seq_lens)
+        for (size_t r = 0; r < n_records; ++r) seq_lens[r] = ro[r + 1] - ro[r];
+    return set_err(err, BN_OK);
+}
+
 int bn_fastq_scan(bn_ctx* ctx, const uint8_t* text, size_t n_bytes, size_t* n_reads, size_t* n_words, bn_error_t* err) {
     return fastx_scan(ctx, text, n_bytes, n_reads, n_words, err, 0);
 }

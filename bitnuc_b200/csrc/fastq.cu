@@ -785,4 +785,124 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- wrapped (multi-line) FASTA ------------------------
+// A record = a '>' header line followed by any number of sequence lines (genome FASTA is wrapped at 60-80 columns); its
+// sequence is the concatenation of those lines, so its bases are NOT contiguous in the text.  Done as: line table ->
+// compaction -> the batch encode.
+//   1. fastq_lines_kernel + scan (the count pass above)            -> number of lines, first line index of every tile
+//   2. fastq_index_kernel in its dense form (forced)               -> nl[L] = position of line L's newline (| "a '\r' precedes it")
+//   3. fasta_wrapped_lines_kernel, a thread per line               -> start, sequence length (0 for a header) and "is a header"
+//      + a two-channel exclusive scan over the lines               -> H[L] = headers before line L, B[L] = sequence bytes before line L
+//   4. fasta_wrapped_compact_kernel, a warp per line               -> header line: rec_off[H[L]] = B[L], hdr_off[H[L]] = start;
+//                                                                     sequence line: its bytes to compact[B[L] ..)
+//   5. launch_encode_batch(compact, rec_off)                        -> words, word offsets (every record on a fresh word)
+// One more pass over the text than the one-line form and a copy of the sequence bytes: this is the convenience path for
+// genome-style files, not a roofline row.  A text whose first line is not a header is a fault (record 0, FQ_BAD_HEADER).
+
+__global__ void __launch_bounds__(kThreads)
+fasta_wrapped_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ nl, unsigned long long n_lines,
+                           uint64_t* __restrict__ line_start, uint64_t* __restrict__ line_seq, uint8_t* __restrict__ line_hdr,
+                           unsigned long long* __restrict__ status) {
+    for (unsigned long long L = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; L < n_lines; L += (unsigned long long)gridDim.x * kThreads) {
+        const unsigned long long e = nl[L], pos = e & ~kCrBit, cr = e >> 63;
+        const unsigned long long s = L ? (nl[L - 1] & ~kCrBit) + 1 : 0ull;
+        const bool hdr = s < n && bytes[s] == '>';
+        line_start[L] = s;
+        line_seq[L] = hdr ? 0ull : pos - cr - s;
+        line_hdr[L] = hdr ? 1 : 0;
+        if (L == 0 && !hdr) report_min(status + 1, FQ_BAD_HEADER);   // record 0: the text does not open with a header
+    }
+}
+
+struct HeaderAndSeqLen {
+    const uint8_t* line_hdr;
+    const uint64_t* line_seq;
+    __device__ __forceinline__ ulonglong2 operator()(unsigned long long L) const { return make_ulonglong2(line_hdr[L], line_seq[L]); }
+};
+
+__global__ void __launch_bounds__(kThreads)
+fasta_wrapped_compact_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ line_start, const uint64_t* __restrict__ line_seq,
+                             const uint8_t* __restrict__ line_hdr, const uint64_t* __restrict__ H, const uint64_t* __restrict__ B,
+                             unsigned long long n_lines, uint8_t* __restrict__ compact, uint64_t* __restrict__ rec_off,
+                             uint64_t* __restrict__ hdr_off) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
+    for (unsigned long long L = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); L < n_lines; L += n_warps) {
+        const unsigned long long s = line_start[L], b = B[L];
+        if (line_hdr[L]) {
+            if (lane == 0) {
+                rec_off[H[L]] = b;
+                hdr_off[H[L]] = s;
+            }
+        } else {
+            const unsigned long long len = line_seq[L];
+            for (unsigned long long i = lane; i < len; i += 32) compact[b + i] = bytes[s + i];
+        }
+    }
+}
+
+// nl | line_start | line_seq | H | B (n_lines + 1 entries each) | line_hdr | scan sums | forced "dense" flag + a throw-away status pair
+size_t fasta_wrapped_scratch_bytes(size_t n_lines) {
+    const size_t m = n_lines + 1;
+    return 5 * align16(m * 8) + align16(m) + align16(scan2_scratch_bytes(m)) + 48;
+}
+
+struct FwScratch {
+    uint64_t *nl, *line_start, *line_seq, *H, *B;
+    uint8_t* line_hdr;
+    unsigned long long* sums;
+    unsigned* force;
+    unsigned long long* dummy_status;
+    FwScratch(void* p, size_t n_lines) {
+        const size_t m = n_lines + 1;
+        char* c = static_cast<char*>(p);
+        nl = reinterpret_cast<uint64_t*>(c), c += align16(m * 8);
+        line_start = reinterpret_cast<uint64_t*>(c), c += align16(m * 8);
+        line_seq = reinterpret_cast<uint64_t*>(c), c += align16(m * 8);
+        H = reinterpret_cast<uint64_t*>(c), c += align16(m * 8);
+        B = reinterpret_cast<uint64_t*>(c), c += align16(m * 8);
+        line_hdr = reinterpret_cast<uint8_t*>(c), c += align16(m);
+        sums = reinterpret_cast<unsigned long long*>(c), c += align16(scan2_scratch_bytes(m));
+        force = reinterpret_cast<unsigned*>(c);
+        dummy_status = reinterpret_cast<unsigned long long*>(c + 16);
+    }
+};
+
+// after launch_fastq_count(..., fasta = 1): d_totals[0] = records, d_totals[1] = sequence bytes; d_status as launch_fastq_index
+cudaError_t launch_fasta_wrapped_index(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, size_t n_lines, void* d_scratch,
+                                       void* d_wscratch, uint64_t* d_totals, unsigned long long* d_status, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_status, 0xFF, 2 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    if (n_bytes == 0 || n_lines == 0) return cudaMemsetAsync(d_totals, 0, 2 * sizeof(uint64_t), s);
+    const FqScratch sc(d_scratch, n_bytes);
+    const FwScratch fw(d_wscratch, n_lines);
+    e = cudaMemsetAsync(fw.force, 0x01, 4, s);   // non-zero: the dense index form runs whatever the count pass found
+    if (e != cudaSuccess) return e;
+    const unsigned long long dense_grid = sc.n_tiles < 148ull * 8 ? sc.n_tiles : 148ull * 8;
+    fastq_index_kernel<<<(unsigned)dense_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.line_base, n_lines, fw.nl, fw.dummy_status, fw.force,
+                                                                   sc.n_tiles, TextFormat{0u, (uint32_t)'>'});
+    const unsigned long long blocks = ceil_div(n_lines, kThreads);
+    fasta_wrapped_lines_kernel<<<(unsigned)(blocks < 148ull * 16 ? blocks : 148ull * 16), kThreads, 0, s>>>(
+        d_bytes, n_bytes, fw.nl, n_lines, fw.line_start, fw.line_seq, fw.line_hdr, d_status);
+    launch_exclusive_scan2(HeaderAndSeqLen{fw.line_hdr, fw.line_seq}, n_lines, fw.sums, fw.H, fw.B, s);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(d_totals, fw.H + n_lines, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(d_totals + 1, fw.B + n_lines, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s);
+}
+
+// d_compact: n_seq_bytes bytes (16-byte aligned); d_rec_off: n_records + 1 entries; d_hdr_off: n_records entries
+cudaError_t launch_fasta_wrapped_compact(const DeviceInfo&, const uint8_t* d_bytes, size_t n_lines, void* d_wscratch, size_t n_records,
+                                         uint8_t* d_compact, uint64_t* d_rec_off, uint64_t* d_hdr_off, cudaStream_t s) {
+    if (n_lines == 0) return cudaMemsetAsync(d_rec_off, 0, sizeof(uint64_t), s);
+    const FwScratch fw(d_wscratch, n_lines);
+    const unsigned long long blocks = ceil_div(n_lines, kWarpsPerBlock);
+    fasta_wrapped_compact_kernel<<<(unsigned)(blocks < 148ull * 32 ? blocks : 148ull * 32), kThreads, 0, s>>>(
+        d_bytes, fw.line_start, fw.line_seq, fw.line_hdr, fw.H, fw.B, n_lines, d_compact, d_rec_off, d_hdr_off);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(d_rec_off + n_records, fw.B + n_lines, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s);
+}
+
 }  // namespace bn

@@ -83,6 +83,13 @@ cudaError_t launch_fastq_index(const DeviceInfo& di, const uint8_t* d_bytes, siz
 cudaError_t launch_fastq_encode(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
                                 const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets,
                                 uint64_t* d_out_words, unsigned long long* d_status, int fasta, cudaStream_t s);
+// wrapped (multi-line) FASTA: after launch_fastq_count(fasta = 1) -- line table, then compaction of the sequence bytes; the
+// caller runs launch_encode_batch on (d_compact, d_rec_off)
+size_t fasta_wrapped_scratch_bytes(size_t n_lines);
+cudaError_t launch_fasta_wrapped_index(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, size_t n_lines, void* d_scratch,
+                                       void* d_wscratch, uint64_t* d_totals, unsigned long long* d_status, cudaStream_t s);
+cudaError_t launch_fasta_wrapped_compact(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_lines, void* d_wscratch, size_t n_records,
+                                         uint8_t* d_compact, uint64_t* d_rec_off, uint64_t* d_hdr_off, cudaStream_t s);
 
 // synth.cu
 cudaError_t launch_synth_words(const DeviceInfo& di, uint64_t seed, uint64_t stream_id, uint64_t first_word,

@@ -222,6 +222,27 @@ inline FastqBatch fastq_encode(Bytes text, bool fasta = false) {   // fasta: '>'
     return out;
 }
 inline FastqBatch fasta_encode(Bytes text) { return fastq_encode(text, true); }
+// wrapped (multi-line) FASTA: a '>' header line, then any number of sequence lines per record (genome files); seq_offsets holds
+// the byte offset of every HEADER line (a record's bases are not contiguous in the text)
+inline FastqBatch fasta_wrapped_encode(Bytes text) {
+    FastqBatch out;
+    size_t n_records = 0, n_bases = 0, n_words = 0;
+    bn_error_t e{};
+    const int rc = bn_fasta_wrapped_scan(detail::ctx(), text.ptr, text.len, &n_records, &n_bases, &n_words, &e);
+    if (rc == BN_ERR_FASTQ) {
+        char buf[160];
+        bn_error_string(&e, buf, sizeof buf);
+        throw FastqError(e.record, static_cast<int>(e.a), buf);
+    }
+    detail::check(rc, e);
+    out.words.resize(n_words);
+    out.word_offsets.resize(n_records + 1);
+    out.seq_offsets.resize(n_records);
+    out.seq_lens.resize(n_records);
+    detail::check(bn_fasta_wrapped_encode(detail::ctx(), text.ptr, text.len, n_records, n_words, out.words.data(), out.word_offsets.data(),
+                                          out.seq_offsets.data(), out.seq_lens.data(), &e), e);
+    return out;
+}
 
 // src/utils/functions/split.rs:14-20 -- validates idx <= slen, then clears both buffers and fills them
 inline void split_packed(Words ebuf, size_t slen, size_t idx, std::vector<uint64_t>& lbuf, std::vector<uint64_t>& rbuf) {

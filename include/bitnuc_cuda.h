@@ -222,9 +222,22 @@ int bn_fastq_scan(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t *n_re
 int bn_fastq_encode(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t *out_words, uint64_t *out_word_offsets, uint64_t *seq_offsets, uint64_t *seq_lens, bn_error_t *err);
 /* The same for FASTA text with ONE sequence line per record (the form read processors emit: '>' header line, sequence
  * line): two-line records, same outputs, same errors (BN_FASTQ_BAD_HEADER / BN_FASTQ_TRUNCATED are the faults that can
- * occur).  A sequence wrapped over several lines is not this format: its second line is reported as a bad header. */
+ * occur).  A sequence wrapped over several lines is not this format (its second line is reported as a bad header): see
+ * bn_fasta_wrapped_* below. */
 int bn_fasta_scan(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t *n_reads, size_t *n_words, bn_error_t *err);
 int bn_fasta_encode(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t n_reads, size_t n_words, uint64_t *out_words, uint64_t *out_word_offsets, uint64_t *seq_offsets, uint64_t *seq_lens, bn_error_t *err);
+/* WRAPPED (multi-line) FASTA, the genome-file form: a '>' header line, then any number of sequence lines per record; a
+ * record's sequence is the concatenation of its lines ("\n" or "\r\n", empty lines add nothing, the last newline may be
+ * missing).  The caller's loop is the same `PackedSequence::new(record.seq())` (README.md:160-180, src/sequence.rs:40-52)
+ * -- a FASTA reader hands it the joined sequence.  bn_fasta_wrapped_scan uploads the text and returns *n_records,
+ * *n_bases (all sequence bytes) and *n_words = sum of ceil(len/32); a text that does not open with a header ->
+ * BN_ERR_FASTQ (record 0, BN_FASTQ_BAD_HEADER); the first byte outside ACGTacgt in file order -> BN_INVALID_BASE
+ * (err->record = the record, err->b = its position inside the record's sequence, err->offset = its position in the
+ * concatenation of all sequences).  bn_fasta_wrapped_encode (same text, right after the scan) fills out_words[n_words],
+ * out_word_offsets[n_records+1], header_offsets[n_records] (byte offset of every header line in the text) and
+ * seq_lens[n_records]; any of the last three may be NULL. */
+int bn_fasta_wrapped_scan(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t *n_records, size_t *n_bases, size_t *n_words, bn_error_t *err);
+int bn_fasta_wrapped_encode(bn_ctx *ctx, const uint8_t *text, size_t n_bytes, size_t n_records, size_t n_words, uint64_t *out_words, uint64_t *out_word_offsets, uint64_t *header_offsets, uint64_t *seq_lens, bn_error_t *err);
 
 /* ------------------------------------------------------------------ device-pointer calls ---- */
 /* All of these only enqueue work on `stream` (NULL = context stream) and never synchronise.

@@ -345,6 +345,49 @@ def fastq_encode(text, fasta: bool = False):
     return w, np.asarray(offs, dtype=np.uint64), starts, lens
 
 
+def fasta_wrapped_encode(text):
+    """Wrapped (multi-line) FASTA: the definition the CUDA path is held to (the reference has no parser; README.md:160-180
+    shows the caller's loop over a FASTA reader, which joins a record's sequence lines before `PackedSequence::new`).
+    Lines end in "\n" or "\r\n", the last newline may be missing; a line that opens with '>' starts a record; every other
+    line is sequence of the current record (an empty line adds nothing).  A non-empty text whose first line is not a
+    header -> FastqFault(0, 1).  Returns (words, word_offsets, header_offsets, seq_lens); the first byte outside ACGTacgt in
+    file order raises OracleError(InvalidBase) carrying .record and .position (inside the record's joined sequence)."""
+    t = _bytes_arr(text).tobytes()
+    if not t:
+        z = np.zeros(0, dtype=np.uint64)
+        return z, np.zeros(1, dtype=np.uint64), z.copy(), z.copy()
+    lines, pos = [], 0
+    while pos < len(t):                       # (start, end without "\n" / "\r\n") of every line
+        nl = t.find(b"\n", pos)
+        end = len(t) if nl < 0 else nl
+        stop = end - 1 if end > pos and t[end - 1:end] == b"\r" else end   # as orc_fastq_scan: a '\r' at the end of a line is stripped
+        lines.append((pos, stop))
+        pos = end + 1
+    if t[lines[0][0]:lines[0][0] + 1] != b">":
+        raise FastqFault(0, 1)
+    hdr, seqs = [], []
+    for s, e in lines:
+        if t[s:s + 1] == b">":
+            hdr.append(s)
+            seqs.append([])
+        else:
+            seqs[-1].append(t[s:e])
+    words, offs, lens = [], [0], []
+    for r, parts in enumerate(seqs):
+        seq = b"".join(parts)
+        lens.append(len(seq))
+        if seq:
+            try:
+                words.append(encode_np(np.frombuffer(seq, dtype=np.uint8)))
+            except OracleError as e:
+                bad = next(i for i, b in enumerate(seq) if b not in b"ACGTacgt")
+                e.record, e.position = r, bad
+                raise
+        offs.append(offs[-1] + (len(seq) + 31) // 32)
+    w = np.concatenate(words) if words else np.zeros(0, dtype=np.uint64)
+    return w, np.asarray(offs, dtype=np.uint64), np.asarray(hdr, dtype=np.uint64), np.asarray(lens, dtype=np.uint64)
+
+
 def fastx_encode_timed(text, fasta: bool = False, path: int = PATH_AVX2, reps: int = 3):
     """(seconds, words, word_offsets) of the single-threaded CPU form of the FASTQ / FASTA row: reader + per-record encode
     in C (orc_fastx_encode), best of ``reps``.  bench tools only."""

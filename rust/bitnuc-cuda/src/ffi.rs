@@ -78,6 +78,8 @@ extern "C" {
     pub fn bn_fastq_encode(ctx: *mut bn_ctx, text: *const u8, n_bytes: usize, n_reads: usize, n_words: usize, out_words: *mut u64, out_word_offsets: *mut u64, seq_offsets: *mut u64, seq_lens: *mut u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_fasta_scan(ctx: *mut bn_ctx, text: *const u8, n_bytes: usize, n_reads: *mut usize, n_words: *mut usize, err: *mut bn_error_t) -> c_int;
     pub fn bn_fasta_encode(ctx: *mut bn_ctx, text: *const u8, n_bytes: usize, n_reads: usize, n_words: usize, out_words: *mut u64, out_word_offsets: *mut u64, seq_offsets: *mut u64, seq_lens: *mut u64, err: *mut bn_error_t) -> c_int;
+    pub fn bn_fasta_wrapped_scan(ctx: *mut bn_ctx, text: *const u8, n_bytes: usize, n_records: *mut usize, n_bases: *mut usize, n_words: *mut usize, err: *mut bn_error_t) -> c_int;
+    pub fn bn_fasta_wrapped_encode(ctx: *mut bn_ctx, text: *const u8, n_bytes: usize, n_records: usize, n_words: usize, out_words: *mut u64, out_word_offsets: *mut u64, header_offsets: *mut u64, seq_lens: *mut u64, err: *mut bn_error_t) -> c_int;
     pub fn bn_fasta_count_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, d_scratch: *mut c_void, d_n_lines: *mut u64) -> c_int;
     pub fn bn_fasta_index_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, n_reads: usize, d_scratch: *mut c_void, d_index_scratch: *mut c_void, d_seq_offsets: *mut u64, d_seq_lens: *mut u64, d_word_offsets: *mut u64, d_status: *mut u64) -> c_int;
     pub fn bn_fasta_encode_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, n_reads: usize, d_scratch: *mut c_void, d_seq_offsets: *const u64, d_seq_lens: *const u64, d_word_offsets: *const u64, d_out_words: *mut u64, d_status: *mut u64) -> c_int;

@@ -155,6 +155,25 @@ pub fn fasta_encode(text: &[u8]) -> Result<FastqBatch, FastqError> {
     fastx_encode(text, true)
 }
 
+/// Wrapped (multi-line) FASTA, the genome-file form: a '>' header line, then any number of sequence lines per record,
+/// joined into the record's sequence (what a FASTA reader hands to `PackedSequence::new(record.seq())`).
+/// `seq_offsets` holds the byte offset of every HEADER line: a record's bases are not contiguous in the text.
+pub fn fasta_wrapped_encode(text: &[u8]) -> Result<FastqBatch, FastqError> {
+    let (mut n_records, mut n_bases, mut n_words, mut e) = (0usize, 0usize, 0usize, bn_error_t::default());
+    let rc = with_ctx(|c| unsafe { bn_fasta_wrapped_scan(c, text.as_ptr(), text.len(), &mut n_records, &mut n_bases, &mut n_words, &mut e) });
+    if rc == -5 {
+        return Err(FastqError::Malformed { record: e.record, fault: e.a as u8 });
+    }
+    check(rc, &e).map_err(|error| FastqError::Nucleotide { error, record: e.record, position: e.b })?;
+    let mut b = FastqBatch { words: vec![0; n_words], word_offsets: vec![0; n_records + 1], seq_offsets: vec![0; n_records], seq_lens: vec![0; n_records] };
+    let rc = with_ctx(|c| unsafe {
+        bn_fasta_wrapped_encode(c, text.as_ptr(), text.len(), n_records, n_words, b.words.as_mut_ptr(), b.word_offsets.as_mut_ptr(),
+                                b.seq_offsets.as_mut_ptr(), b.seq_lens.as_mut_ptr(), &mut e)
+    });
+    check(rc, &e).map_err(|error| FastqError::Nucleotide { error, record: e.record, position: e.b })?;
+    Ok(b)
+}
+
 fn fastx_encode(text: &[u8], fasta: bool) -> Result<FastqBatch, FastqError> {
     let (mut n_reads, mut n_words, mut e) = (0usize, 0usize, bn_error_t::default());
     let rc = with_ctx(|c| unsafe {

@@ -265,6 +265,11 @@ static void test_fastq_records() {
     const std::string fa = ">a\nACGTACGT\n>b second\nacgtt\n";
     const FastqBatch f = fasta_encode(fa);
     CHECK(f.size() == 2 && f.seq_lens[1] == 5 && f.words[1] == as_2bit("ACGTT") && fa.substr(f.seq_offsets[0], 8) == "ACGTACGT");
+    const std::string wrapped = ">chr1 x\nACGTAC\nGT\n>chr2\n>chr3\r\nacg\r\ntt\r\n";   // lines of one record are joined
+    const FastqBatch w = fasta_wrapped_encode(wrapped);
+    CHECK(w.size() == 3 && w.seq_lens[0] == 8 && w.seq_lens[1] == 0 && w.seq_lens[2] == 5);
+    CHECK(w.word_offsets == (std::vector<uint64_t>{0, 1, 1, 2}) && w.words[0] == as_2bit("ACGTACGT") && w.words[1] == as_2bit("ACGTT"));
+    CHECK(wrapped.substr(w.seq_offsets[2], 5) == ">chr3");
 }
 
 // bitnuc::Multi: the reference's functions with the work cut over two shards (device 0 named twice -- the way a one-GPU

@@ -111,3 +111,21 @@ def test_one_call_cpu_form_equals_the_callers_loop(fasta):
     assert ei.value.key() == ("InvalidBase", ord("N"))
     with pytest.raises(oracle.FastqFault):
         oracle.fastx_encode_timed(text[1:], fasta, reps=1)
+
+
+def test_wrapped_fasta_definition():
+    """oracle.fasta_wrapped_encode on hand-written texts: joined lines, empty records, CRLF, a missing final newline."""
+    w, wo, ho, sl = oracle.fasta_wrapped_encode(b">chr1 test\nACGTAC\nGTTT\n\nAC\n>chr2\n>chr3\r\nacgt\r\nTTGG")
+    assert wo.tolist() == [0, 1, 1, 2] and ho.tolist() == [0, 27, 33] and sl.tolist() == [12, 0, 8]
+    assert [int(x) for x in w] == [oracle.as_2bit(b"ACGTACGTTTAC"), oracle.as_2bit(b"ACGTTTGG")]
+    assert oracle.fasta_wrapped_encode(b"")[1].tolist() == [0]
+    w, wo, ho, sl = oracle.fasta_wrapped_encode(b">a\n" + b"A" * 31 + b"\n" + b"C" * 33 + b"\nG\r")   # a trailing '\r' is a line end's
+    assert sl.tolist() == [65] and wo.tolist() == [0, 3]
+    assert oracle.decode_np(w, 65).tobytes() == b"A" * 31 + b"C" * 33 + b"G"
+    import pytest
+    with pytest.raises(oracle.FastqFault) as ei:
+        oracle.fasta_wrapped_encode(b"\n>a\nAC\n")          # the text must open with a header
+    assert (ei.value.record, ei.value.fault) == (0, 1)
+    with pytest.raises(oracle.OracleError) as eo:
+        oracle.fasta_wrapped_encode(b">a\nAC\n>b\nAC\nGN\n")
+    assert eo.value.key() == ("InvalidBase", ord("N")) and (eo.value.record, eo.value.position) == (1, 3)

@@ -131,3 +131,33 @@ for name, text in (("pinned", text_pin), ("pageable", text_page)):
     s = timed(lambda: fastq(text))
     assert int(wo[n_reads]) == n_reads * wpr and int(sl[7]) == rl and int(so[1]) == rec + hdr
     line(f"bn_fastq_scan + bn_fastq_encode ({name} text)", s, nb, 8 * n_reads * wpr + 24 * n_reads, n_reads * rl, "bases")
+
+# wrapped FASTA, the genome-file form: 64 records of 8 Mbases wrapped at 60 columns (0.52 GB of text) -> joined sequences -> packed
+del t2, text_pin, text_page
+n_rec, rec_bases, width = 64, 8_000_040, 60
+lines_per = rec_bases // width
+body = torch.empty((n_rec, lines_per, width + 1), dtype=torch.uint8, device="cuda")
+body[:, :, :width] = dv.synth_ascii(SEED, 8, 0, n_rec * rec_bases).view(n_rec, lines_per, width)
+body[:, :, width] = 10
+hdr_line = torch.tensor(list(b">chromosome_xx description\n"), dtype=torch.uint8, device="cuda")
+wtext = torch.cat([torch.cat([hdr_line, body[r].reshape(-1)]) for r in range(n_rec)])
+wtext_pin = pinned(wtext, np.uint8)
+wnb = wtext_pin.size
+w_words = (rec_bases + 31) // 32
+w_out = ctx.pinned_empty(n_rec * w_words, np.uint64)
+w_wo, w_ho, w_sl = (ctx.pinned_empty(n_rec + 1, np.uint64) for _ in range(3))
+
+
+def fasta_wrapped():
+    nr, nbase, nw = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    assert ctx.lib.bn_fasta_wrapped_scan(ctx.handle, wtext_pin.ctypes.data, wnb, C.byref(nr), C.byref(nbase), C.byref(nw), None) == 0
+    assert (nr.value, nbase.value, nw.value) == (n_rec, n_rec * rec_bases, n_rec * w_words)
+    assert ctx.lib.bn_fasta_wrapped_encode(ctx.handle, wtext_pin.ctypes.data, wnb, nr.value, nw.value, w_out.ctypes.data, w_wo.ctypes.data,
+                                           w_ho.ctypes.data, w_sl.ctypes.data, None) == 0
+
+
+s = timed(fasta_wrapped)
+assert int(w_sl[3]) == rec_bases and int(w_ho[1]) == hdr_line.numel() + lines_per * (width + 1)
+expect = dv.synth_words(SEED, 8, 0, 4).cpu().numpy().view(np.uint64)   # record 0 is the generator's stream 8 from base 0
+assert np.array_equal(w_out[:4], expect)
+line("bn_fasta_wrapped_scan + bn_fasta_wrapped_encode (60-column genome FASTA, pinned text)", s, wnb, 8 * n_rec * w_words, n_rec * rec_bases, "bases")

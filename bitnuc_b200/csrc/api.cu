@@ -1125,18 +1125,42 @@ int bn_split_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, co
                           const uint64_t* idx, size_t n_reads, uint64_t* left, uint64_t* left_offsets, uint64_t* right,
                           uint64_t* right_offsets, bn_error_t* err) {
     if (!ctx || !left_offsets || !right_offsets || (n_reads && (!word_offsets || !lens || !idx))) return set_err(err, BN_ERR_ARGUMENT);
-    for (size_t r = 0; r < n_reads; ++r) {  // first failing read in index order, as the caller's loop with `?` would report
-        if (idx[r] > lens[r]) {
-            set_err(err, BN_INDEX_OUT_OF_BOUNDS, idx[r], lens[r]);  // split.rs:22-27
+    // The first failing read in index order, as the caller's loop with `?` would report -- found by a few host threads over
+    // blocks of reads (10 M reads are 240 MB of offsets, lengths and indices: single-threaded, this pass cost as much as the
+    // PCIe transfers of the call).  kind 1: idx > len (split.rs:22-27); 2: a malformed read table; 3: an ebuf too short for
+    // slen (the reference panics at split.rs:77 or truncates the right half).
+    {
+        const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency(), n_reads / 262144}));
+        std::vector<size_t> first_bad(n_thr, SIZE_MAX);
+        std::vector<int> kind(n_thr, 0);
+        auto check = [&](unsigned t) {
+            for (size_t r = n_reads * t / n_thr; r < n_reads * (t + 1) / n_thr; ++r) {
+                int k = 0;
+                if (idx[r] > lens[r]) k = 1;
+                else if (word_offsets[r + 1] < word_offsets[r] || word_offsets[r + 1] > n_words) k = 2;
+                else {
+                    const uint64_t have = word_offsets[r + 1] - word_offsets[r];
+                    if (idx[r] && idx[r] < lens[r] && have && have < (lens[r] + 31) / 32) k = 3;
+                }
+                if (k) {
+                    first_bad[t] = r;
+                    kind[t] = k;
+                    return;   // the first of this thread's range
+                }
+            }
+        };
+        std::vector<std::thread> workers;
+        for (unsigned t = 1; t < n_thr; ++t) workers.emplace_back(check, t);
+        check(0);
+        for (auto& w : workers) w.join();
+        for (unsigned t = 0; t < n_thr; ++t) {   // ranges are in index order: the first thread with a failure holds the first failing read
+            if (first_bad[t] == SIZE_MAX) continue;
+            const size_t r = first_bad[t];
+            if (kind[t] == 2) return set_err(err, BN_ERR_ARGUMENT);
+            if (kind[t] == 1) set_err(err, BN_INDEX_OUT_OF_BOUNDS, idx[r], lens[r]);
+            else set_err(err, BN_INVALID_LENGTH, lens[r]);
             if (err) err->record = r;
-            return BN_INDEX_OUT_OF_BOUNDS;
-        }
-        if (word_offsets[r + 1] < word_offsets[r] || word_offsets[r + 1] > n_words) return set_err(err, BN_ERR_ARGUMENT);
-        const uint64_t have = word_offsets[r + 1] - word_offsets[r];
-        if (idx[r] && idx[r] < lens[r] && have && have < (lens[r] + 31) / 32) {  // the reference panics (split.rs:77) or truncates the right half
-            set_err(err, BN_INVALID_LENGTH, lens[r]);
-            if (err) err->record = r;
-            return BN_INVALID_LENGTH;
+            return kind[t] == 1 ? BN_INDEX_OUT_OF_BOUNDS : BN_INVALID_LENGTH;
         }
     }
     left_offsets[0] = right_offsets[0] = 0;

@@ -161,3 +161,23 @@ assert int(w_sl[3]) == rec_bases and int(w_ho[1]) == hdr_line.numel() + lines_pe
 expect = dv.synth_words(SEED, 8, 0, 4).cpu().numpy().view(np.uint64)   # record 0 is the generator's stream 8 from base 0
 assert np.array_equal(w_out[:4], expect)
 line("bn_fasta_wrapped_scan + bn_fasta_wrapped_encode (60-column genome FASTA, pinned text)", s, wnb, 8 * n_rec * w_words, n_rec * rec_bases, "bases")
+
+# split_packed over 10 M x 150 bp packed reads at base 26 (barcode | insert), pinned buffers (the call stages whole buffers)
+del wtext, wtext_pin, body, w_out
+n_reads = 10_000_000
+s_words = pinned(dv.synth_words(SEED, 4, 0, 5 * n_reads), np.uint64)
+s_wo = ctx.pinned_empty(n_reads + 1, np.uint64); s_wo[:] = np.arange(n_reads + 1, dtype=np.uint64) * 5
+s_len = ctx.pinned_empty(n_reads, np.uint64); s_len[:] = 150
+s_idx = ctx.pinned_empty(n_reads, np.uint64); s_idx[:] = 26
+s_left, s_right = ctx.pinned_empty(6 * n_reads, np.uint64), ctx.pinned_empty(5 * n_reads, np.uint64)
+s_lo, s_ro = ctx.pinned_empty(n_reads + 1, np.uint64), ctx.pinned_empty(n_reads + 1, np.uint64)
+
+
+def split():
+    assert ctx.lib.bn_split_packed_batch(ctx.handle, s_words.ctypes.data, s_words.size, s_wo.ctypes.data, s_len.ctypes.data, s_idx.ctypes.data,
+                                         n_reads, s_left.ctypes.data, s_lo.ctypes.data, s_right.ctypes.data, s_ro.ctypes.data, None) == 0
+
+
+s = timed(split)
+assert int(s_lo[n_reads]) == n_reads and int(s_ro[n_reads]) == 5 * n_reads and int(s_left[0]) == int(s_words[0]) & ((1 << 52) - 1)
+line("bn_split_packed_batch 10 M x 150 bp at base 26", s, (5 + 3) * 8 * n_reads, (1 + 5 + 2) * 8 * n_reads, n_reads, "reads")

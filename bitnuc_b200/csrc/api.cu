@@ -668,6 +668,36 @@ int bn_decode(bn_ctx* ctx, const uint64_t* words, size_t n_words, size_t n_bases
 
 namespace {
 
+// check(r, t) over r in [0, n) on up to eight host threads (thread t takes a contiguous range, ranges in index order); a
+// non-zero result stops that thread.  Returns the smallest failing r (SIZE_MAX: none) and its result in *kind.  The read and
+// query tables of the batch calls are hundreds of megabytes: single-threaded, these passes cost as much as the PCIe transfers.
+constexpr unsigned kHostCheckThreads = 8;
+template <class F>
+static size_t parallel_first_failing(size_t n, F check, int* kind) {
+    const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>({kHostCheckThreads, std::thread::hardware_concurrency(), n / 262144}));
+    std::vector<size_t> first_bad(n_thr, SIZE_MAX);
+    std::vector<int> kinds(n_thr, 0);
+    auto run = [&](unsigned t) {
+        for (size_t r = n * t / n_thr; r < n * (t + 1) / n_thr; ++r)
+            if (const int k = check(r, t)) {
+                first_bad[t] = r;
+                kinds[t] = k;
+                return;
+            }
+    };
+    std::vector<std::thread> workers;
+    for (unsigned t = 1; t < n_thr; ++t) workers.emplace_back(run, t);
+    run(0);
+    for (auto& w : workers) w.join();
+    for (unsigned t = 0; t < n_thr; ++t)
+        if (first_bad[t] != SIZE_MAX) {
+            *kind = kinds[t];
+            return first_bad[t];
+        }
+    return SIZE_MAX;
+}
+
+
 // issue(c, s, stream) -> cudaError_t enqueues chunk c; retire(c, s) runs on the host once chunk c has completed.
 template <class Issue, class Retire>
 int run_pipeline(bn_ctx* ctx, size_t n_chunks, bn_error_t* err, Issue issue, Retire retire) {
@@ -1125,42 +1155,22 @@ int bn_split_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, co
                           const uint64_t* idx, size_t n_reads, uint64_t* left, uint64_t* left_offsets, uint64_t* right,
                           uint64_t* right_offsets, bn_error_t* err) {
     if (!ctx || !left_offsets || !right_offsets || (n_reads && (!word_offsets || !lens || !idx))) return set_err(err, BN_ERR_ARGUMENT);
-    // The first failing read in index order, as the caller's loop with `?` would report -- found by a few host threads over
-    // blocks of reads (10 M reads are 240 MB of offsets, lengths and indices: single-threaded, this pass cost as much as the
-    // PCIe transfers of the call).  kind 1: idx > len (split.rs:22-27); 2: a malformed read table; 3: an ebuf too short for
-    // slen (the reference panics at split.rs:77 or truncates the right half).
+    // The first failing read in index order, as the caller's loop with `?` would report.  kind 1: idx > len (split.rs:22-27);
+    // 2: a malformed read table; 3: an ebuf too short for slen (the reference panics at split.rs:77 or truncates the right half).
     {
-        const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency(), n_reads / 262144}));
-        std::vector<size_t> first_bad(n_thr, SIZE_MAX);
-        std::vector<int> kind(n_thr, 0);
-        auto check = [&](unsigned t) {
-            for (size_t r = n_reads * t / n_thr; r < n_reads * (t + 1) / n_thr; ++r) {
-                int k = 0;
-                if (idx[r] > lens[r]) k = 1;
-                else if (word_offsets[r + 1] < word_offsets[r] || word_offsets[r + 1] > n_words) k = 2;
-                else {
-                    const uint64_t have = word_offsets[r + 1] - word_offsets[r];
-                    if (idx[r] && idx[r] < lens[r] && have && have < (lens[r] + 31) / 32) k = 3;
-                }
-                if (k) {
-                    first_bad[t] = r;
-                    kind[t] = k;
-                    return;   // the first of this thread's range
-                }
-            }
-        };
-        std::vector<std::thread> workers;
-        for (unsigned t = 1; t < n_thr; ++t) workers.emplace_back(check, t);
-        check(0);
-        for (auto& w : workers) w.join();
-        for (unsigned t = 0; t < n_thr; ++t) {   // ranges are in index order: the first thread with a failure holds the first failing read
-            if (first_bad[t] == SIZE_MAX) continue;
-            const size_t r = first_bad[t];
-            if (kind[t] == 2) return set_err(err, BN_ERR_ARGUMENT);
-            if (kind[t] == 1) set_err(err, BN_INDEX_OUT_OF_BOUNDS, idx[r], lens[r]);
+        int kind = 0;
+        const size_t r = parallel_first_failing(n_reads, [&](size_t q, unsigned) {
+            if (idx[q] > lens[q]) return 1;
+            if (word_offsets[q + 1] < word_offsets[q] || word_offsets[q + 1] > n_words) return 2;
+            const uint64_t have = word_offsets[q + 1] - word_offsets[q];
+            return idx[q] && idx[q] < lens[q] && have && have < (lens[q] + 31) / 32 ? 3 : 0;
+        }, &kind);
+        if (r != SIZE_MAX) {
+            if (kind == 2) return set_err(err, BN_ERR_ARGUMENT);
+            if (kind == 1) set_err(err, BN_INDEX_OUT_OF_BOUNDS, idx[r], lens[r]);
             else set_err(err, BN_INVALID_LENGTH, lens[r]);
             if (err) err->record = r;
-            return kind[t] == 1 ? BN_INDEX_OUT_OF_BOUNDS : BN_INVALID_LENGTH;
+            return kind == 1 ? BN_INDEX_OUT_OF_BOUNDS : BN_INVALID_LENGTH;
         }
     }
     left_offsets[0] = right_offsets[0] = 0;
@@ -1201,12 +1211,17 @@ int bn_split_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, co
 // (the caller's loop with `?` stops at the first failing query), so the device never sees a bad query here.
 static int stage_packed_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens,
                               size_t n_reads, cudaStream_t st, bn_error_t* err) {
-    for (size_t r = 0; r < n_reads; ++r)
-        if (word_offsets[r] > n_words || (lens[r] + 31) / 32 > n_words - word_offsets[r]) {
+    {
+        int kind = 0;
+        const size_t r = parallel_first_failing(n_reads, [&](size_t q, unsigned) {
+            return word_offsets[q] > n_words || (lens[q] + 31) / 32 > n_words - word_offsets[q] ? 1 : 0;
+        }, &kind);
+        if (r != SIZE_MAX) {
             set_err(err, BN_INVALID_LENGTH, lens[r]);
             if (err) err->record = r;
             return BN_INVALID_LENGTH;
         }
+    }
     BN_CUDA(ensure(ctx->slot[0], n_words ? n_words * 8 : 8));
     BN_CUDA(ensure(ctx->slot[1], n_reads ? n_reads * 8 : 8));
     BN_CUDA(ensure(ctx->slot[2], n_reads ? n_reads * 8 : 8));
@@ -1224,15 +1239,22 @@ int bn_slice_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uin
     if (!ctx || !out_offsets || (n_reads && (!word_offsets || !lens)) || (nq && (!q_read || !q_start || !q_end)))
         return set_err(err, BN_ERR_ARGUMENT);
     size_t total = 0;
-    for (size_t q = 0; q < nq; ++q) {
-        if (q_read[q] >= n_reads) return set_err(err, BN_ERR_ARGUMENT);
-        const uint64_t len = lens[q_read[q]];
-        if (q_start[q] > q_end[q] || q_end[q] > len) {  // sequence.rs:199-205
-            set_err(err, BN_INVALID_RANGE, q_start[q], q_end[q], len);
-            if (err) err->record = q;
+    {
+        size_t sums[kHostCheckThreads] = {};
+        int kind = 0;
+        const size_t bad = parallel_first_failing(nq, [&](size_t q, unsigned t) {
+            if (q_read[q] >= n_reads) return 2;
+            if (q_start[q] > q_end[q] || q_end[q] > lens[q_read[q]]) return 1;  // sequence.rs:199-205
+            sums[t] += q_end[q] - q_start[q];
+            return 0;
+        }, &kind);
+        if (bad != SIZE_MAX) {
+            if (kind == 2) return set_err(err, BN_ERR_ARGUMENT);
+            set_err(err, BN_INVALID_RANGE, q_start[bad], q_end[bad], lens[q_read[bad]]);
+            if (err) err->record = bad;
             return BN_INVALID_RANGE;
         }
-        total += q_end[q] - q_start[q];
+        for (size_t v : sums) total += v;
     }
     out_offsets[0] = 0;
     if (nq == 0) return set_err(err, BN_OK);
@@ -1264,11 +1286,16 @@ int bn_slice_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uin
 int bn_get_batch(bn_ctx* ctx, const uint64_t* words, size_t n_words, const uint64_t* word_offsets, const uint64_t* lens, size_t n_reads,
                  const uint64_t* q_read, const uint64_t* q_index, size_t nq, uint8_t* out, bn_error_t* err) {
     if (!ctx || (n_reads && (!word_offsets || !lens)) || (nq && (!q_read || !q_index || !out))) return set_err(err, BN_ERR_ARGUMENT);
-    for (size_t q = 0; q < nq; ++q) {
-        if (q_read[q] >= n_reads) return set_err(err, BN_ERR_ARGUMENT);
-        if (q_index[q] >= lens[q_read[q]]) {  // sequence.rs:117-122
-            set_err(err, BN_INDEX_OUT_OF_BOUNDS, q_index[q], lens[q_read[q]]);
-            if (err) err->record = q;
+    {
+        int kind = 0;
+        const size_t bad = parallel_first_failing(nq, [&](size_t q, unsigned) {
+            if (q_read[q] >= n_reads) return 2;
+            return q_index[q] >= lens[q_read[q]] ? 1 : 0;  // sequence.rs:117-122
+        }, &kind);
+        if (bad != SIZE_MAX) {
+            if (kind == 2) return set_err(err, BN_ERR_ARGUMENT);
+            set_err(err, BN_INDEX_OUT_OF_BOUNDS, q_index[bad], lens[q_read[bad]]);
+            if (err) err->record = bad;
             return BN_INDEX_OUT_OF_BOUNDS;
         }
     }

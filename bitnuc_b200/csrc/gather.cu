@@ -9,9 +9,10 @@
 // The first failing query in index order is reported (status word = min failing query index); failing queries
 // produce no output (slice) or 0 (get).
 //
-// slice: an exclusive scan of (end - start) places every query's bytes.  Ranges of up to 64 bases are cut one query
-// per thread and staged per warp for coalesced stores (slice_short_kernel); longer ranges are queued and cut a warp
-// per range (slice_long_kernel).
+// slice: an exclusive prefix sum of (end - start) places every query's bytes -- computed inside slice_short_kernel itself
+// (2048-query tiles, decoupled look-back: lookback.cuh), which also validates the queries and cuts the ranges of up to 64
+// bases, one query per lane, staged per warp for coalesced stores; longer ranges are queued and cut a warp per range
+// (slice_long_kernel).
 #include "common.cuh"
 #include "launch.cuh"
 #include "lookback.cuh"

@@ -13,8 +13,9 @@
 // ceil(len/32) words, because ceil(len/32) - idx/32 >= ceil((len-idx)/32); a shorter ebuf is rejected here
 // (the reference either panics at split.rs:77 or returns a truncated right half).
 //
-// Every output word depends on at most two input words: one thread per read here (reads on this path
-// are short: barcode | insert splits, benches/functions_benchmark.rs:59 uses 30-280 bases).
+// Every output word depends on at most two input words: one lane per read (reads on this path are short: barcode |
+// insert splits, benches/functions_benchmark.rs:59 uses 30-280 bases), in ONE launch that also places the outputs
+// (split_packed_fused_kernel below: 2048-read tiles, decoupled look-back, rows software-pipelined).
 // Status word = min over failing reads of (read index << 1 | kind): kind 0 = idx > len ->
 // IndexOutOfBounds{idx, len} (split.rs:22-27), kind 1 = 0 < idx < len and a non-empty ebuf shorter than ceil(len/32) words.
 #include "common.cuh"

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -154,7 +155,11 @@ inline bool is_pageable(const void* p) {
 }
 
 inline void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    static const unsigned hw = [] {   // BN_MEMCPY_THREADS overrides the default of min(8, hardware threads)
+        const char* v = std::getenv("BN_MEMCPY_THREADS");
+        const unsigned want = v ? (unsigned)std::atoi(v) : 8u;
+        return std::max(1u, std::min(want ? want : 8u, std::thread::hardware_concurrency()));
+    }();
     const size_t kMinSlice = 4u << 20;
     const unsigned t = (unsigned)std::min<size_t>(hw, bytes / kMinSlice);
     if (t <= 1) {

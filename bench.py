@@ -1068,7 +1068,7 @@ def report(args, job, n, K, W, total_ms, enc_ms, dec_ms, clocks, e2e, strong, cf
             "as_2bit_ms": cfg2["as_2bit_ms"], "from_2bit_ms": cfg2["from_2bit_ms"],
             "as_2bit_gkmers_s": nt / (cfg2["as_2bit_ms"] * 1e-3) / 1e9, "from_2bit_gkmers_s": nt / (cfg2["from_2bit_ms"] * 1e-3) / 1e9,
             "roofline": roofline("as_2bit_tight_kernel", 39.0 * nl, cfg2["as_2bit_ms"]),
-            "roofline_from_2bit": roofline("from_2bit_tight_kernel", 39.0 * nl, cfg2["from_2bit_ms"]),
+            "roofline_from_2bit": roofline("from_2bit_tight31_kernel", 39.0 * nl, cfg2["from_2bit_ms"]),
             "bytes_per_unit": "39 B per k-mer per kernel (31 ASCII + 8 packed); x the k-mers of one rank's launch",
             "check": "as_2bit(from_2bit(W)) == W & (2^62 - 1) on every record; from_2bit against its definition on a strided sample",
             "cpu_baseline": cpu("kmers")}

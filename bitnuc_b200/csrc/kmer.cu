@@ -315,6 +315,48 @@ from_2bit_tight_kernel(const uint64_t* __restrict__ packed, unsigned long long n
     }
 }
 
+// k = 31, tightly packed (the 31-mer batch of BASELINE configs[2]): 16 records are exactly 31 output chunks of 16 bytes
+// (lcm(31, 16) = 496), so a warp takes groups of 16 records and lane l < 31 always owns chunk l of the group -- the record
+// it starts in (16 l / 31), its first base there (16 l mod 31) and whether it spills into the next record are constants
+// of the lane, computed once.  The generic tight kernel above re-derives (record, position) for every chunk and always
+// fetches two words; here a chunk is one or two loads, two shifts and the 16-base decode.  Lane 31 idles (3 % of the lanes).
+constexpr int kK31Groups = 4;   // groups per warp step, all loads issued before the first use
+__global__ void __launch_bounds__(kKmerThreads, 2)
+from_2bit_tight31_kernel(const uint64_t* __restrict__ packed, unsigned long long n, uint8_t* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long n_groups = n / 16;              // whole groups; the remainder goes through the tail below
+    const unsigned rec = (16u * lane) / 31u, pos = (16u * lane) % 31u;
+    const unsigned avail = 31u - pos;                        // bases of this chunk that come from its first record
+    const bool spills = avail < 16u, active = lane < 31u;
+    const unsigned sh0 = 2u * pos, sh1 = 2u * avail;
+    const uint32_t keep = spills ? (1u << sh1) - 1u : 0xFFFFFFFFu;
+    const TileWalk<kKmerThreads, 1, 1> walk(ceil_div(n_groups, kK31Groups));
+    for (unsigned long long t = walk.first; t < walk.end; t += walk.step) {
+        const unsigned long long g0 = t * kK31Groups;
+        uint64_t w0[kK31Groups], w1[kK31Groups];
+#pragma unroll
+        for (int j = 0; j < kK31Groups; ++j) {
+            const bool live = active && g0 + j < n_groups;
+            const uint64_t* p = packed + (g0 + j) * 16 + rec;
+            w0[j] = live ? __ldg(p) : 0ull;
+            w1[j] = live && spills ? __ldg(p + 1) : 0ull;   // (a spilling chunk never starts in a group's last record)
+        }
+#pragma unroll
+        for (int j = 0; j < kK31Groups; ++j) {
+            if (active && g0 + j < n_groups) {
+                const uint32_t x = ((uint32_t)(w0[j] >> sh0) & keep) | (spills ? (uint32_t)(w1[j] << sh1) : 0u);
+                st_stream_v4(reinterpret_cast<uint4*>(out) + (g0 + j) * 31 + lane, decode16_prmt(x));
+            }
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // the records past the last whole group (< 16 of them)
+        for (unsigned long long b = n_groups * 496; b < n * 31; ++b) {
+            const uint64_t w = packed[b / 31];
+            out[b] = (uint8_t)(0x54474341u >> (8 * (unsigned)((w >> (2 * (b % 31))) & 3u)));
+        }
+    }
+}
+
 // stride == 32, 16-byte aligned output: word r -> vectors 2r, 2r+1 (all 32 slots are written).
 __global__ void __launch_bounds__(kKmerThreads)
 from_2bit_padded_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, unsigned long long n_w32) {
@@ -383,6 +425,10 @@ cudaError_t launch_from_2bit_batch(const DeviceInfo& di, const uint64_t* d_packe
         const unsigned long long ctas = TileWalk<kKmerThreads, 1, 1>::ctas(n_w32 / (32 * kKmerU));
         from_2bit_padded_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(
             reinterpret_cast<const uint32_t*>(d_packed), reinterpret_cast<uint4*>(d_out), n_w32);
+    } else if (aligned && stride == 31 && k == 31) {
+        const unsigned long long steps = ceil_div(n / 16, kK31Groups);
+        const unsigned long long ctas = TileWalk<kKmerThreads, 1, 1>::ctas(steps);
+        from_2bit_tight31_kernel<<<(unsigned)(ctas ? ctas : 1), kKmerThreads, 0, s>>>(d_packed, n, d_out);
     } else if (aligned && stride == k && k >= 16) {
         const unsigned long long chunks = (unsigned long long)n * k / 16;
         from_2bit_tight_kernel<<<(unsigned)ceil_div(chunks + 1, kKmerThreads * kTightChunks), kKmerThreads, 0, s>>>(d_packed, n, k,

@@ -59,6 +59,7 @@ def test_library_targets_sm_100a_only(sass):
     ("encode_batch_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
     ("kmer_windows_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E\.EF\.64"),
     ("as_2bit_tight_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E\.EF\.64"),
+    ("from_2bit_tight31_kernel", r"LDG\.E", r"STG\.E\.EF\.128"),            # one or two 64-bit words in, 16 bases per 128-bit streaming store
     ("fastq_lines_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E"),              # the text in 128-bit loads, 32-bit line entries out
     ("fastq_encode_kernelILi49152ELi128ELi9ELb1", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
 ])

@@ -360,10 +360,22 @@ def leg_codec(job: Job, n: int, first_base: int, K: int, warm: int, sample_clock
 
 
 def cudart():
-    rt = C.CDLL("libcudart.so.12")
-    rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
-    rt.cudaMemcpyAsync.restype = C.c_int
-    return rt
+    """libcudart through ctypes (cudaMemcpyAsync on raw pointers for the copy probes): the copy torch has already loaded is found by
+    its soname; otherwise the wheels' and the toolkit's copies are tried."""
+    import glob
+    import site
+    cands = ["libcudart.so.12", "libcudart.so"]
+    for base in site.getsitepackages() + ["/usr/local/cuda/lib64"]:
+        cands += sorted(glob.glob(os.path.join(base, "nvidia", "cuda_runtime", "lib", "libcudart.so*"))) + sorted(glob.glob(os.path.join(base, "libcudart.so*")))
+    for c in cands:
+        try:
+            rt = C.CDLL(c)
+            rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+            rt.cudaMemcpyAsync.restype = C.c_int
+            return rt
+        except OSError:
+            continue
+    raise SystemExit("bench.py: libcudart not found for the PCIe probes")
 
 
 def leg_pcie_ceiling(job: Job, h_up, h_dn, nbytes: int):

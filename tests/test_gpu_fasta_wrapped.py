@@ -103,3 +103,41 @@ def test_faults_and_invalid_bases(bn):
     with pytest.raises(OracleError) as eo:
         oracle.fasta_wrapped_encode(bytes(text))
     assert eo.value.key() == ei.value.key() and (eo.value.record, eo.value.position) == (r0, where[r0])
+
+
+@pytest.mark.parametrize("kind", ["dense_lines", "tile_edges", "one_long_line", "headers_only", "crlf_dense", "mixed"])
+def test_adversarial_shapes(bn, kind):
+    """Shapes chosen against the implementation: more than 2048 lines in a 16 KiB tile (the slot rows overflow: the dense index must
+    carry the result), newlines and headers on tile boundaries, one line of several tiles, records without sequence."""
+    rng = np.random.default_rng(sum(kind.encode()))
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def seq(n):
+        return acgt[rng.integers(0, 4, n)].tobytes()
+
+    if kind == "dense_lines":                       # 1-3 byte lines: ~8000 lines per tile
+        text = b">d\n" + b"".join(seq(int(rng.integers(0, 3))) + b"\n" for _ in range(60000)) + b">e\n" + seq(100) + b"\n"
+    elif kind == "crlf_dense":
+        text = b">d\r\n" + b"".join(seq(int(rng.integers(0, 2))) + b"\r\n" for _ in range(40000))
+    elif kind == "tile_edges":                      # every record is exactly one 16 KiB tile: the header starts on the boundary
+        recs = []
+        for r in range(12):
+            hdr = b">r%02d\n" % r
+            body = 16384 - len(hdr)
+            lines = [seq(62) + b"\n" for _ in range(body // 63)]
+            last = body - 63 * (body // 63)
+            recs.append(hdr + b"".join(lines) + (seq(last - 1) + b"\n" if last else b""))
+        text = b"".join(recs)
+        assert len(text) == 12 * 16384
+    elif kind == "one_long_line":                   # a sequence line spanning ~20 tiles, then short ones
+        text = b">long\n" + seq(333_333) + b"\n" + seq(10) + b"\n>short\n" + seq(5)
+    elif kind == "headers_only":
+        text = b"".join(b">h%d\n" % i for i in range(5000))
+    else:
+        parts = []
+        for r in range(300):
+            parts.append(b">m%d\n" % r)
+            for _ in range(int(rng.integers(0, 6))):
+                parts.append(seq(int(rng.choice([0, 1, 15, 16, 17, 31, 32, 33, 60, 500, 20000]))) + (b"\r\n" if rng.random() < 0.3 else b"\n"))
+        text = b"".join(parts)
+    _same(bn, text)

@@ -669,6 +669,76 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
     }
 }
 
+// ---------------------------------------------------------------- 3'. encode, a thread per read (short reads) --------
+// In FASTQ text of short reads less than half the bytes are sequence (150 of ~330 per record): the pack-then-cut kernel
+// above loads and packs all of them.  Here a thread takes ONE read and fetches only the 32-byte blocks its sequence line
+// touches, as 256-bit loads (LDG.256, sm_100): a block is exactly one DRAM sector, so nothing is fetched twice and nothing
+// relies on L1; three blocks are in flight per thread before the first is packed (a 150-base read is five or six).  A block packs to one
+// 64-bit code word; output word j is the 64-bit window 2 * (start mod 32) bits into code words j, j + 1.  Bytes of the
+// first and last vector that lie outside the line are replaced by 'A' before packing (valid, code 00: they shift out at
+// the front and are the zero padding at the back).  No shared memory, no barrier.  Long reads keep the tiled kernel.
+
+// bytes [l, h) of the vector stay, the others become 'A'
+__device__ __forceinline__ uint4 keep_bytes(uint4 v, int l, int h) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t m = byte_range_mask(l - 4 * i, h - 4 * i);
+        w[i] = (w[i] & m) | (0x41414141u & ~m);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int kFqReadU, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
+fastq_encode_reads_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_reads,
+                          const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ seq_len,
+                          const uint64_t* __restrict__ word_off, uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n_reads) return;
+    const unsigned long long s = seq_off[r], len = seq_len[r];
+    if (len == 0) return;
+    const unsigned long long e = s + len, a0 = s & ~31ull;
+    const unsigned sh2 = 2u * (unsigned)(s & 31ull);
+    const unsigned long long nb = (e - a0 + 31) / 32, nw = (len + 31) / 32;   // blocks touched, words written (nb = nw or nw + 1)
+    uint64_t* o = out + word_off[r];
+    const bool wide = (reinterpret_cast<uintptr_t>(bytes) & 31u) == 0;        // 256-bit loads need the text itself 32-byte aligned
+    uint64_t carry = 0;
+    uint32_t bad = 0;
+    for (unsigned long long b0 = 0; b0 < nb; b0 += kFqReadU) {
+        uint4 lo[kFqReadU], hi[kFqReadU];
+#pragma unroll
+        for (int u = 0; u < kFqReadU; ++u) {
+            const unsigned long long pos = a0 + 32 * (b0 + u);
+            if (b0 + u >= nb) {
+                lo[u] = hi[u] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+            } else if (wide && pos + 32 <= n) {
+                const uint8x x = ld256<LD_NC_NOALLOC>(bytes + pos);
+                lo[u] = x.lo;
+                hi[u] = x.hi;
+            } else {
+                lo[u] = enc_load_cached(bytes, n, pos);
+                hi[u] = enc_load_cached(bytes, n, pos + 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kFqReadU; ++u) {
+            const unsigned long long b = b0 + u;
+            if (b >= nb) break;
+            const unsigned long long pos = a0 + 32 * b;
+            uint4 v0 = lo[u], v1 = hi[u];
+            if (pos < s || pos + 16 > e) v0 = keep_bytes(v0, pos < s ? (int)(s - pos) : 0, pos + 16 > e ? (e > pos ? (int)(e - pos) : 0) : 16);
+            if (pos + 16 < s || pos + 32 > e)
+                v1 = keep_bytes(v1, pos + 16 < s ? (int)(s - pos - 16) : 0, pos + 32 > e ? (e > pos + 16 ? (int)(e - pos - 16) : 0) : 16);
+            const uint64_t c = ((uint64_t)pack16(v1, bad) << 32) | pack16(v0, bad);
+            if (b >= 1) o[b - 1] = sh2 ? (carry >> sh2) | (c << (64 - sh2)) : carry;   // word b - 1 < nw always (b <= nb - 1 <= nw)
+            carry = c;
+        }
+    }
+    if (nb == nw) o[nw - 1] = sh2 ? carry >> sh2 : carry;
+    if (bad & kValidMask) fq_report_range(bytes, s, e, status);
+}
+
 // ---------------------------------------------------------------- launchers ----------------------------------------
 // d_scratch (fastq_scratch_bytes): counts[n_tiles] | line_base[n_tiles + 1] | scan sums
 // d_index_scratch (fastq_index_scratch_bytes): nl[4 n_reads] | scan sums
@@ -761,6 +831,13 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
         const char* v = getenv("BN_FQ_VARIANT");
         return v ? atoi(v) : -1;
     }();
+    if (forced < 0 && n_bytes / n_reads <= 1024) {   // short records: a thread per read, only the sequence bytes are fetched
+        // (blocks in flight per thread, CTAs per SM) swept on 20 M x 150 bp: (6,3) 1.13 ms, (6,4) 1.19, (4,3) 1.23, (4,4) 1.08, (3,4) 1.10,
+        // (3,5) 1.04, (2,6) 1.09, (6,2) 1.45 -- residency beats loads in flight per thread
+        fastq_encode_reads_kernel<3, 5><<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(d_bytes, n_bytes, n_reads, d_seq_offsets,
+                                                                                                  d_seq_lens, d_word_offsets, d_out_words, d_status);
+        return cudaGetLastError();
+    }
     const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 11 : 13);
 #define BN_FQ_LAUNCH(TILE, THREADS, CTAS, ...)                                                                                         \
     fastq_encode_kernel<TILE, THREADS, CTAS, ##__VA_ARGS__><<<(unsigned)ceil_div(sc.n_tiles, TILE / kFqTile), THREADS, 0, s>>>(                        \

@@ -382,3 +382,26 @@ def test_fasta_mutated_texts_fuzz(bn, dv, seed):
             else:
                 del text[i:]
         check(bn, dv, bytes(text), fasta=True)
+
+
+def test_device_text_that_is_16_but_not_32_byte_aligned(bn, dv):
+    """The thread-per-read encode uses 256-bit loads when the text itself is 32-byte aligned and falls back to 128-bit ones when it
+    is only 16-byte aligned (the documented requirement): both against the oracle, on reads that end at the end of the text."""
+    import torch
+    rng = np.random.default_rng(77)
+    recs = []
+    for r in range(3000):
+        n = int(rng.integers(1, 300))
+        seq = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, n)].tobytes()
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (r, seq, b"I" * n))
+    text = b"".join(recs)[:-1]                                   # no final newline: the last quality line ends the text
+    exp = expected(text)
+    for shift in (0, 16):
+        buf = torch.zeros(len(text) + 64, dtype=torch.uint8, device="cuda")
+        view = buf[shift: shift + len(text)]
+        view.copy_(torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()))
+        assert view.data_ptr() % 32 == shift
+        w, wo, so, sl, st = dv.fastq_encode(view)
+        st.check()
+        u = lambda x: x.cpu().numpy().view(np.uint64)
+        assert same(("ok", u(w), u(wo), u(so), u(sl)), exp), shift

@@ -120,9 +120,10 @@ __device__ __forceinline__ unsigned nth_set_bit(uint32_t m, unsigned n) {
 }
 
 // the four vectors a thread loads of a tile (lane-consecutive: coalesced)
+template <bool kEdge>
 __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0, unsigned tid,
                                                 uint4 (&x)[4]) {
-    if (tile0 + kFqTile <= n) {
+    if (!kEdge) {
         const uint4* src = reinterpret_cast<const uint4*>(bytes + tile0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = ld128<LD_NC_NOALLOC>(src + tid + j * kFqThreads);
@@ -143,18 +144,17 @@ __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ byte
 // no '\n'.  In FASTQ text one vector in five survives.  A ballot turns the survivors into a bitmap in file order, and the
 // CTA then works on the survivors only, one per thread: exact newline mask, rank by a CTA scan, the bytes next to each
 // newline from the shared-memory copy of the tile, one slot entry per newline.
-__global__ void __launch_bounds__(kFqThreads)
-fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
-                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long n_tiles, uint32_t header) {
+template <bool kEdge>
+__device__ __forceinline__ void lines_filter_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
+                                                  uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long tile, uint32_t header) {
     __shared__ uint4 raw[kFqTile / 16];                   // the tile's text
     __shared__ uint32_t hitbits[kFqTile / 512];           // one bit per vector: may hold a newline
     __shared__ unsigned warp_tot[kFqThreads / 32];
     static_assert(kFqTile / 512 == 32, "one bitmap word per lane");
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const unsigned long long tile0 = tile * kFqTile;
     uint4 x[4];
-    lines_load_tile(bytes, n, tile0, tid, x);
+    lines_load_tile<kEdge>(bytes, n, tile0, tid, x);
     constexpr uint32_t kAdd = 0x60606060u, kTop = 0x80808080u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -229,7 +229,22 @@ fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsi
         if (total > (unsigned)kFqSlots) *overflow = 1u;
     }
     __syncthreads();   // raw / hitbits are reused by the next tile
-    }
+}
+
+// One tile per CTA, NO loop over tiles in the kernel, and the edge loader in an instantiation of its own: the grid-stride
+// loop that used to wrap this body and the rarely taken call of the edge loader cost 6 registers (37 against 31: 6
+// against 8 CTAs per SM), and this latency-bound kernel pays for residency -- 1.33 -> 1.16 ms on 20 M x 150 bp FASTQ,
+// 1.17 -> 1.00 ms on 10 kbp reads, 0.70 -> 0.63 ms on FASTA (profiles/README.md).
+// (A BLOCKED form -- a thread owns 64 or 128 consecutive bytes as 256-bit loads, exact mask in registers, one CTA scan, a walk
+// over its own set bits -- was measured beside it: 0.92 ms with 128 bytes per thread and 1.02 ms with 64 on 10 kbp reads,
+// 1.48 / 1.20 ms on 150 bp reads; the choice would have to be made on the device from a probe of the text -- two kernels
+// enqueued over the same tiles cost 0.2 ms for the loser's 400 000 empty CTAs, two bodies in one kernel 38 registers.  Dropped.)
+// kEdge = false: the tiles wholly inside the text; true: the last tile(s) -- virtual newline, NUL padding (the edge loader)
+template <bool kEdge>
+__global__ void __launch_bounds__(kFqThreads, kEdge ? 1 : 8)
+fastq_lines_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long* __restrict__ counts,
+                   uint32_t* __restrict__ slots, unsigned* __restrict__ overflow, unsigned long long first_tile, uint32_t header) {
+    lines_filter_tile<kEdge>(bytes, n, counts, slots, overflow, first_tile + blockIdx.x, header);
 }
 
 struct CountOfTile {
@@ -781,8 +796,9 @@ cudaError_t launch_fastq_count(const DeviceInfo&, const uint8_t* d_bytes, size_t
     if (e != cudaSuccess) return e;
     // one tile per CTA: a resident grid striding over the tiles was measured at 1x and 2x the resident CTA count and is
     // 10-15 % slower (as for the codec kernels: the two dies finish at different times)
-    const unsigned lines_grid = (unsigned)sc.n_tiles;
-    fastq_lines_kernel<<<lines_grid, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, sc.n_tiles, fmt.header);
+    const unsigned long long n_full = (unsigned long long)n_bytes / kFqTile;   // < n_tiles
+    if (n_full) fastq_lines_kernel<false><<<(unsigned)n_full, kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, 0, fmt.header);
+    fastq_lines_kernel<true><<<(unsigned)(sc.n_tiles - n_full), kFqThreads, 0, s>>>(d_bytes, n_bytes, sc.counts, sc.slots, sc.overflow, n_full, fmt.header);
     launch_exclusive_scan(CountOfTile{sc.counts}, sc.n_tiles, sc.sums, sc.line_base, s);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -92,9 +92,6 @@ PROTOTYPES = {
     "bn_fastq_index_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bn_fastq_encode_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bn_fastq_status_fetch": (_int, [_vp, _vp, _vp, _u64, _vp, _sz, _errp]),
-    "bn_fastq_onepass_scratch_bytes": (_sz, [_sz]),
-    "bn_fastq_onepass_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "bn_fasta_onepass_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bn_status_fetch": (_int, [_vp, _vp, _vp, _errp]),
     "bn_synth_words_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),
     "bn_synth_ascii_dev": (_int, [_vp, _vp, _u64, _u64, _u64, _sz, _vp]),

@@ -450,35 +450,6 @@ int bn_fasta_encode_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t
     return fastx_encode_dev(ctx, stream, d_text, n_bytes, n_reads, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status, 1);
 }
 
-size_t bn_fastq_onepass_scratch_bytes(size_t n_bytes) { return bn::fastq_onepass_scratch_bytes(n_bytes); }
-
-static int fastx_onepass_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t cap_reads, size_t cap_words, void* d_scratch,
-                             uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_out_words, uint64_t* d_totals,
-                             uint64_t* d_status, int fasta) {
-    if (!ctx || !d_status || !d_totals || !d_word_offsets || (reinterpret_cast<uintptr_t>(d_text) & 15u) ||
-        (reinterpret_cast<uintptr_t>(d_scratch) & 7u) || (n_bytes && (!d_text || !d_scratch)) || (cap_reads && (!d_seq_offsets || !d_seq_lens)) ||
-        (cap_words && !d_out_words) || n_bytes >= (1ull << 36))
-        return BN_ERR_ARGUMENT;
-    DeviceGuard g(ctx->di.device);
-    LaunchTimer lt(ctx, pick(ctx, stream));
-    BN_LAUNCH(bn::launch_fastq_onepass(ctx->di, d_text, n_bytes, cap_reads, cap_words, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,
-                                       reinterpret_cast<unsigned long long*>(d_totals), reinterpret_cast<unsigned long long*>(d_status), fasta,
-                                       pick(ctx, stream)));
-    return BN_OK;
-}
-int bn_fastq_onepass_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t cap_reads, size_t cap_words, void* d_scratch,
-                         uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_out_words, uint64_t* d_totals,
-                         uint64_t* d_status) {
-    return fastx_onepass_dev(ctx, stream, d_text, n_bytes, cap_reads, cap_words, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,
-                             d_totals, d_status, 0);
-}
-int bn_fasta_onepass_dev(bn_ctx* ctx, void* stream, const uint8_t* d_text, size_t n_bytes, size_t cap_reads, size_t cap_words, void* d_scratch,
-                         uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_out_words, uint64_t* d_totals,
-                         uint64_t* d_status) {
-    return fastx_onepass_dev(ctx, stream, d_text, n_bytes, cap_reads, cap_words, d_scratch, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,
-                             d_totals, d_status, 1);
-}
-
 static int fastq_fault(bn_error_t* err, unsigned long long key) {
     set_err(err, BN_ERR_FASTQ, key & 0xFFu);
     if (err) err->record = key >> 8;

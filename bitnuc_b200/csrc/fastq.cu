@@ -39,7 +39,6 @@
 
 #include "common.cuh"
 #include "launch.cuh"
-#include "lookback.cuh"
 #include "scan.cuh"
 
 namespace bn {
@@ -121,7 +120,7 @@ __device__ __forceinline__ unsigned nth_set_bit(uint32_t m, unsigned n) {
 }
 
 // the four vectors a thread loads of a tile (lane-consecutive: coalesced)
-template <int kEdge>   // 0: the tile lies wholly inside the text, 1: it does not, 2: decided here
+template <int kEdge>   // 0: the tile lies wholly inside the text, 1: it does not, 2: decided here (unused since the one-pass experiment)
 __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0, unsigned tid,
                                                 uint4 (&x)[4]) {
     if (kEdge == 0 || (kEdge == 2 && tile0 + kFqTile <= n)) {
@@ -145,7 +144,7 @@ __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ byte
 // no '\n'.  In FASTQ text one vector in five survives.  A ballot turns the survivors into a bitmap in file order, and the
 // CTA then works on the survivors only, one per thread: exact newline mask, rank by a CTA scan, the bytes next to each
 // newline from the shared-memory copy of the tile, one slot entry per newline.
-// row = the tile's slot row (global memory, or shared memory in the one-pass kernel); returns the tile's number of newlines
+// row = the tile's slot row; returns the tile's number of newlines
 template <int kEdge>
 __device__ __forceinline__ unsigned lines_filter_tile(const uint8_t* __restrict__ bytes, unsigned long long n, uint32_t* __restrict__ row,
                                                       unsigned long long tile, uint32_t header) {
@@ -225,7 +224,6 @@ __device__ __forceinline__ unsigned lines_filter_tile(const uint8_t* __restrict_
         total += round_total;
         if (i0 + kFqThreads < n_hit) __syncthreads();   // warp_tot is reused by the next round (CTA-uniform: usually there is none)
     }
-    __syncthreads();   // raw / hitbits / warp_tot may be reused by the caller; a row in shared memory is complete
     return total;
 }
 
@@ -763,205 +761,6 @@ fastq_encode_reads_kernel(const uint8_t* __restrict__ bytes, unsigned long long 
     fq_encode_read<kFqReadU>(bytes, n, seq_off[r], len, out + word_off[r], status);
 }
 
-// ---------------------------------------------------------------- 4. everything in ONE pass over the text ----------
-// The capacity-based form (bn_fastq_onepass_dev): the caller sizes the outputs from what it knows about the file (or from a
-// first attempt's totals) instead of from a count pass, and the text is read from HBM once.  A CTA takes a 16 KiB tile in
-// ticket order and
-//   A. finds its newlines exactly as fastq_lines_kernel does (filter, then finish densely), the slot row in shared memory;
-//   B. warp 0 publishes the tile's line count and gets the number of lines before the tile by decoupled look-back
-//      (lookback.cuh), while warp 1 looks AHEAD in the text for the next lines-per-record - 1 newlines after the tile: a
-//      tile owns the records whose header line ends in it, whichever tile their other lines end in;
-//   C. with the line index known every entry knows its kind: the owners of header-line ends build their record (faults as
-//      in fastq_records_slots_kernel), a CTA scan gives record numbers and word offsets inside the tile, and a second
-//      look-back (published only now: the words of a tile depend on the phase of its lines) the words before the tile;
-//   D. thread j writes record j's three table entries (coalesced) and encodes its read with fq_encode_read: the blocks it
-//      fetches were loaded by this CTA a moment ago and come from L2.
-// Reads longer than a few tiles make step B's look-ahead and step D's thread-per-read slow: this is the entry for short
-// records; the three-step path has a tiled encode for long ones.  A tile with more than kFqSlots lines raises totals[2]
-// (the caller falls back to the three-step path, whose dense index handles such texts).
-constexpr int kOpMaxRec = kFqSlots / 2;   // records a tile can own: slots / (lines per record >= 2)
-constexpr unsigned kOpLook = 3;
-           // look-ahead entries: lines per record - 1 <= 3
-
-template <unsigned kShift, int kOpCtas, int kOpU>
-__global__ void __launch_bounds__(kFqThreads, kOpCtas)
-fastq_onepass_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_tiles, unsigned long long* __restrict__ ticket,
-                     unsigned long long* __restrict__ desc_lines, unsigned long long* __restrict__ desc_words, unsigned long long cap_reads,
-                     unsigned long long cap_words, uint64_t* __restrict__ seq_off, uint64_t* __restrict__ seq_len,
-                     uint64_t* __restrict__ word_off, uint64_t* __restrict__ out, unsigned long long* __restrict__ totals,
-                     unsigned long long* __restrict__ status, uint32_t header) {
-    constexpr unsigned lpr = 1u << kShift;
-    __shared__ uint32_t ent[kFqSlots];
-    __shared__ unsigned long long la_pos[kOpLook];
-    __shared__ uint32_t la_ent[kOpLook];
-    __shared__ uint16_t rec_ent[kOpMaxRec];
-    __shared__ uint32_t rec_wo[kOpMaxRec];
-    __shared__ unsigned long long s_lines_before, s_words_before, warp_key[kFqThreads / 32];
-    __shared__ unsigned s_nla;
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // tiles in blockIdx order: CTAs are dispatched in that order, so every tile a CTA waits for is running or done (the
-    // assumption cub::DeviceScan makes too); a ticket counter would put one more memory round trip in front of every tile
-    if (tid == 0) s_nla = 0;
-    const unsigned long long tile = blockIdx.x, tile0 = tile * kFqTile;
-    // A
-    const unsigned n_lines_here = lines_filter_tile<2>(bytes, n, ent, tile, header);
-    const unsigned n_ent = n_lines_here < (unsigned)kFqSlots ? n_lines_here : (unsigned)kFqSlots;
-    if (n_lines_here > (unsigned)kFqSlots && tid == 0) totals[2] = 1ull;   // every writer stores the same value
-    // B
-    if (warp == 0) {
-        const unsigned long long agg[1] = {n_lines_here};
-        unsigned long long excl[1];
-        lookback_exclusive<1>(desc_lines, n_tiles, tile, agg, excl);
-        if (lane == 0) s_lines_before = excl[0];
-    } else if (warp == 1 && n_ent) {
-        const bool virt = n && bytes[n - 1] != '\n';
-        unsigned found = 0;
-        for (unsigned long long pos = tile0 + kFqTile; found < lpr - 1 && pos <= n; pos += 512) {   // position n: the virtual newline
-            const unsigned long long p = pos + 16ull * lane;
-            const uint4 v = fq_load(bytes, n, virt, p);
-            uint32_t m = newline_mask16(v);
-            const unsigned cnt = __popc(m);
-            unsigned inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= (unsigned)o) inc += t;
-            }
-            unsigned k = found + inc - cnt;
-            while (m && k < lpr - 1) {
-                const unsigned b = __ffs((int)m) - 1;
-                const unsigned long long q = p + b;
-                m &= m - 1;
-                // the bytes next to it: from the lane's own vector when they lie inside it (no second trip to memory)
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                uint32_t prev, next;
-                if (b > 0) {
-                    uint32_t wsel = w4[0];
-#pragma unroll
-                    for (int t = 1; t < 4; ++t) wsel = ((b - 1) >> 2) == (unsigned)t ? w4[t] : wsel;
-                    prev = (wsel >> (8 * ((b - 1) & 3))) & 0xFFu;
-                } else {
-                    prev = q ? bytes[q - 1] : 0u;
-                }
-                if (b < 15) {
-                    uint32_t wsel = w4[0];
-#pragma unroll
-                    for (int t = 1; t < 4; ++t) wsel = ((b + 1) >> 2) == (unsigned)t ? w4[t] : wsel;
-                    next = q + 1 < n ? (wsel >> (8 * ((b + 1) & 3))) & 0xFFu : 0u;
-                } else {
-                    next = q + 1 < n ? bytes[q + 1] : 0u;
-                }
-                la_pos[k] = q;
-                la_ent[k] = (prev == '\r' ? kSlotCr : 0u) | (next == header ? kSlotAt : 0u) | (next == '+' ? kSlotPlus : 0u);
-                ++k;
-            }
-            found += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) s_nla = found < lpr - 1 ? found : lpr - 1;
-    }
-    __syncthreads();
-    // C
-    const unsigned long long lines_before = s_lines_before;
-    const unsigned n_all = n_ent + s_nla;   // entries this tile can see: its own and the look-ahead
-    if (tile == 0 && tid == 0 && n && bytes[0] != header) report_min(status + 1, FQ_BAD_HEADER);
-    unsigned long long key_before = 0;      // (records << 40 | words) of the rounds done
-    for (unsigned i0 = 0; i0 < n_ent; i0 += kFqThreads) {
-        const unsigned i = i0 + tid;
-        unsigned long long key = 0;
-        if (i < n_ent && ((lines_before + i) & (lpr - 1)) == 0) {   // a header line ends here: record r
-            const unsigned long long r = (lines_before + i) >> kShift;
-            const unsigned n_have = n_all - i < lpr ? n_all - i : lpr;   // how many of its lines end inside the text
-            unsigned long long pos[lpr];
-            uint32_t e[lpr];
-#pragma unroll
-            for (unsigned k = 0; k < lpr; ++k) {
-                pos[k] = 0;
-                e[k] = 0;
-                if (k < n_have) {
-                    if (i + k < n_ent) {
-                        e[k] = ent[i + k];
-                        pos[k] = tile0 + (e[k] & kSlotPos);
-                    } else {
-                        e[k] = la_ent[i + k - n_ent];
-                        pos[k] = la_pos[i + k - n_ent];
-                    }
-                }
-            }
-            if (kShift == 2 && n_have > 2 && !(e[1] & kSlotPlus)) report_min(status + 1, (r << 8) | FQ_BAD_SEPARATOR);
-            if (n_have == lpr && pos[lpr - 1] + 1 < n && !(e[lpr - 1] & kSlotAt)) report_min(status + 1, ((r + 1) << 8) | FQ_BAD_HEADER);
-            if (n_have == lpr) {
-                const unsigned long long s = pos[0] + 1, len = pos[1] - ((e[1] & kSlotCr) ? 1 : 0) - s;
-                if (kShift == 2) {
-                    const unsigned long long qs = pos[lpr - 2] + 1, qe = pos[lpr - 1] - ((e[lpr - 1] & kSlotCr) ? 1 : 0);
-                    if (qe - qs != len) report_min(status + 1, (r << 8) | FQ_BAD_QUALITY_LENGTH);
-                }
-                key = (1ull << 40) | ((len + 31) / 32);
-            }
-        }
-        unsigned long long inc = key;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (unsigned)o) inc += t;
-        }
-        if (lane == 31) warp_key[warp] = inc;
-        __syncthreads();
-        unsigned long long before = key_before, round = 0;
-#pragma unroll
-        for (unsigned w = 0; w < kFqThreads / 32; ++w) {
-            const unsigned long long t = warp_key[w];
-            if (w < warp) before += t;
-            round += t;
-        }
-        if (key) {
-            const unsigned long long x = before + inc - key;
-            rec_ent[x >> 40] = (uint16_t)i;
-            rec_wo[x >> 40] = (uint32_t)(x & ((1ull << 40) - 1));
-        }
-        key_before += round;
-        __syncthreads();   // warp_key is reused; rec_* complete after the last round
-    }
-    const unsigned n_rec = (unsigned)(key_before >> 40);
-    const unsigned long long words_here = key_before & ((1ull << 40) - 1);
-    if (warp == 0) {
-        const unsigned long long agg[1] = {words_here};
-        unsigned long long excl[1];
-        lookback_exclusive<1>(desc_words, n_tiles, tile, agg, excl);
-        if (lane == 0) {
-            s_words_before = excl[0];
-            if (tile == n_tiles - 1) {   // the last tile in ticket order is the last tile of the text: everything before it is published
-                const unsigned long long lines = lines_before + n_lines_here, words = excl[0] + words_here;
-                totals[0] = lines;
-                totals[1] = words;
-                if ((lines >> kShift) <= cap_reads) word_off[lines >> kShift] = words;
-            }
-        }
-    }
-    __syncthreads();
-    // D
-    const unsigned long long words_before = s_words_before, rec_before = (lines_before + lpr - 1) >> kShift;
-    for (unsigned j = tid; j < n_rec; j += kFqThreads) {
-        const unsigned i = rec_ent[j];
-        const unsigned long long r = rec_before + j, wo = words_before + rec_wo[j];
-        const unsigned long long s = tile0 + (ent[i] & kSlotPos) + 1;
-        unsigned long long p1;
-        uint32_t e1;
-        if (i + 1 < n_ent) {
-            e1 = ent[i + 1];
-            p1 = tile0 + (e1 & kSlotPos);
-        } else {
-            e1 = la_ent[i + 1 - n_ent];
-            p1 = la_pos[i + 1 - n_ent];
-        }
-        const unsigned long long len = p1 - ((e1 & kSlotCr) ? 1 : 0) - s;
-        if (r >= cap_reads) continue;
-        seq_off[r] = s;
-        seq_len[r] = len;
-        word_off[r] = wo;
-        if (len && wo + (len + 31) / 32 <= cap_words) fq_encode_read<kOpU>(bytes, n, s, len, out + wo, status);
-    }
-}
-
 // ---------------------------------------------------------------- launchers ----------------------------------------
 // d_scratch (fastq_scratch_bytes): counts[n_tiles] | line_base[n_tiles + 1] | scan sums
 // d_index_scratch (fastq_index_scratch_bytes): nl[4 n_reads] | scan sums
@@ -1038,42 +837,6 @@ cudaError_t launch_fastq_index(const DeviceInfo&, const uint8_t* d_bytes, size_t
     fastq_records_kernel<<<(unsigned)(rec_blocks < 148ull * 8 ? rec_blocks : 148ull * 8), kThreads, 0, s>>>(nl, n_reads, d_seq_offsets, d_seq_lens,
                                                                                                       d_status, sc.overflow, fmt.shift);
     launch_exclusive_scan(WordsOfLen{d_seq_lens}, n_reads, sums2, d_word_offsets, s);
-    return cudaGetLastError();
-}
-
-size_t fastq_onepass_scratch_bytes(size_t n_bytes) { return (2 + 2 * (size_t)fastq_tiles(n_bytes)) * sizeof(unsigned long long); }
-
-// d_scratch: ticket | (unused) | line descriptors[n_tiles] | word descriptors[n_tiles]; d_totals: lines, words, flags
-cudaError_t launch_fastq_onepass(const DeviceInfo&, const uint8_t* d_bytes, size_t n_bytes, size_t cap_reads, size_t cap_words, void* d_scratch,
-                                 uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_out_words,
-                                 unsigned long long* d_totals, unsigned long long* d_status, int fasta, cudaStream_t s) {
-    const TextFormat fmt = text_format(fasta);
-    cudaError_t e = cudaMemsetAsync(d_status, 0xFF, 2 * sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(d_totals, 0, 3 * sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return e;
-    if (n_bytes == 0) return cudaMemsetAsync(d_word_offsets, 0, sizeof(uint64_t), s);
-    const unsigned long long n_tiles = fastq_tiles(n_bytes);
-    e = cudaMemsetAsync(d_scratch, 0, fastq_onepass_scratch_bytes(n_bytes), s);
-    if (e != cudaSuccess) return e;
-    unsigned long long* sc = static_cast<unsigned long long*>(d_scratch);
-    static const int variant = [] {
-        const char* v = getenv("BN_OP_VARIANT");
-        return v ? atoi(v) : 0;
-    }();
-#define BN_OP_LAUNCH(SHIFT, CTAS, U)                                                                                                        \
-    fastq_onepass_kernel<SHIFT, CTAS, U><<<(unsigned)n_tiles, kFqThreads, 0, s>>>(d_bytes, n_bytes, n_tiles, sc, sc + 2, sc + 2 + n_tiles, cap_reads, \
-                                                                                 cap_words, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words,  \
-                                                                                 d_totals, d_status, fmt.header)
-    if (fasta) BN_OP_LAUNCH(1, 5, 3);
-    else switch (variant) {
-        case 1: BN_OP_LAUNCH(2, 4, 3); break;
-        case 2: BN_OP_LAUNCH(2, 6, 3); break;
-        case 3: BN_OP_LAUNCH(2, 4, 6); break;
-        case 4: BN_OP_LAUNCH(2, 3, 6); break;
-        default: BN_OP_LAUNCH(2, 5, 3); break;
-    }
-#undef BN_OP_LAUNCH
     return cudaGetLastError();
 }
 

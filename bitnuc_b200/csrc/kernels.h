@@ -83,11 +83,6 @@ cudaError_t launch_fastq_index(const DeviceInfo& di, const uint8_t* d_bytes, siz
 cudaError_t launch_fastq_encode(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, size_t n_reads, void* d_scratch,
                                 const uint64_t* d_seq_offsets, const uint64_t* d_seq_lens, const uint64_t* d_word_offsets,
                                 uint64_t* d_out_words, unsigned long long* d_status, int fasta, cudaStream_t s);
-// everything in one pass over the text, outputs sized by the caller's capacities; d_totals = {lines, words, flags}
-size_t fastq_onepass_scratch_bytes(size_t n_bytes);
-cudaError_t launch_fastq_onepass(const DeviceInfo& di, const uint8_t* d_bytes, size_t n_bytes, size_t cap_reads, size_t cap_words, void* d_scratch,
-                                 uint64_t* d_seq_offsets, uint64_t* d_seq_lens, uint64_t* d_word_offsets, uint64_t* d_out_words,
-                                 unsigned long long* d_totals, unsigned long long* d_status, int fasta, cudaStream_t s);
 // wrapped (multi-line) FASTA: after launch_fastq_count(fasta = 1) -- line table, then compaction of the sequence bytes; the
 // caller runs launch_encode_batch on (d_compact, d_rec_off)
 size_t fasta_wrapped_scratch_bytes(size_t n_lines);

@@ -258,44 +258,6 @@ def fastq_encode(text: torch.Tensor, status: FastqStatus | None = None, _fasta: 
     return words[:n_words], wo, so[:n], sl[:n], status
 
 
-def fasta_encode_onepass(text: torch.Tensor, cap_reads: int | None = None, cap_words: int | None = None, status: FastqStatus | None = None):
-    """``fastq_encode_onepass`` for one-sequence-line FASTA."""
-    return fastq_encode_onepass(text, cap_reads, cap_words, status, _fasta=True)
-
-
-def fastq_encode_onepass(text: torch.Tensor, cap_reads: int | None = None, cap_words: int | None = None,
-                         status: FastqStatus | None = None, _fasta: bool = False):
-    """The outputs of ``fastq_encode`` from ONE pass over the text (``bn_fastq_onepass_dev``): the caller bounds the number of
-    reads and of output words instead of a count pass (defaults: a record of at least 64 bytes, sequence at most half of
-    the text -- 7/8 for FASTA); when a bound turns out too small the call is repeated with the totals of the first attempt,
-    and a text with more than 2048 lines in some 16 KiB goes through the three-step path."""
-    ctx = _ctx_for(text)
-    dev, n_bytes = text.device, text.numel()
-    status = status or FastqStatus(dev)
-    lpr = 2 if _fasta else 4
-    cap_reads = n_bytes // 64 + 1 if cap_reads is None else cap_reads
-    cap_words = (n_bytes * (7 if _fasta else 4) // 8) // 32 + cap_reads + 1 if cap_words is None else cap_words
-    scratch = torch.empty(max(16, ctx.lib.bn_fastq_onepass_scratch_bytes(n_bytes)), dtype=torch.uint8, device=dev)
-    totals = torch.zeros(3, dtype=torch.int64, device=dev)
-    call = ctx.lib.bn_fasta_onepass_dev if _fasta else ctx.lib.bn_fastq_onepass_dev
-    for _ in range(2):
-        so = torch.empty(max(1, cap_reads), dtype=torch.int64, device=dev)
-        sl = torch.empty(max(1, cap_reads), dtype=torch.int64, device=dev)
-        wo = torch.empty(cap_reads + 1, dtype=torch.int64, device=dev)
-        words = torch.empty(max(1, cap_words), dtype=torch.int64, device=dev)
-        raise_for(call(ctx.handle, _stream(), _ptr(text), n_bytes, cap_reads, cap_words, _ptr(scratch), _ptr(so), _ptr(sl), _ptr(wo),
-                       _ptr(words), _ptr(totals), _ptr(status.word)))
-        n_lines, n_words, dense = (int(x) for x in totals.tolist())
-        if dense:
-            return fastq_encode(text, status, _fasta)
-        n = n_lines // lpr
-        if n <= cap_reads and n_words <= cap_words:
-            status.n_lines, status.seq_offsets, status.n_reads, status.fasta = n_lines, so, n, _fasta
-            return words[:n_words], wo[: n + 1], so[:n], sl[:n], status
-        cap_reads, cap_words = n, n_words
-    raise RuntimeError("bn_fastq_onepass_dev: totals changed between two calls on the same text")
-
-
 class SplitStatus:
     """Device-side status of ``split_packed_batch``: min over failing reads of (read << 1 | kind)."""
 

@@ -307,17 +307,6 @@ int bn_fasta_count_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t 
 int bn_fasta_index_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, void *d_index_scratch, uint64_t *d_seq_offsets, uint64_t *d_seq_lens, uint64_t *d_word_offsets, uint64_t *d_status);
 int bn_fasta_encode_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t n_reads, void *d_scratch, const uint64_t *d_seq_offsets, const uint64_t *d_seq_lens, const uint64_t *d_word_offsets, uint64_t *d_out_words, uint64_t *d_status);
 int bn_fasta_status_fetch(bn_ctx *ctx, void *stream, const uint64_t *d_status, uint64_t n_lines, const uint64_t *d_seq_offsets, size_t n_reads, bn_error_t *err);
-/* The same outputs in ONE pass over the text, for callers that can bound the outputs without a count pass (they know the
- * read length of the run, or retry): d_seq_offsets[cap_reads], d_seq_lens[cap_reads], d_word_offsets[cap_reads + 1],
- * d_out_words[cap_words]; d_scratch: bn_fastq_onepass_scratch_bytes(n_bytes) bytes, 16-byte aligned; d_status as above.
- * d_totals = three device uint64_t: [0] number of lines (n_reads = lines / 4, FASTA: / 2), [1] number of output words,
- * [2] non-zero when the text has a 16 KiB stretch with more than 2048 lines (nothing usable was written: use the three-step
- * calls).  When lines / 4 > cap_reads or words > cap_words the tables / words beyond the capacities were not written: call
- * again with the totals as capacities.  Meant for short records (a thread encodes a read); texts of long reads are correct
- * but faster through the three-step calls.  Replaces the caller's loop of /root/reference/README.md:160-180 like they do. */
-size_t bn_fastq_onepass_scratch_bytes(size_t n_bytes);
-int bn_fastq_onepass_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t cap_reads, size_t cap_words, void *d_scratch, uint64_t *d_seq_offsets, uint64_t *d_seq_lens, uint64_t *d_word_offsets, uint64_t *d_out_words, uint64_t *d_totals, uint64_t *d_status);
-int bn_fasta_onepass_dev(bn_ctx *ctx, void *stream, const uint8_t *d_text, size_t n_bytes, size_t cap_reads, size_t cap_words, void *d_scratch, uint64_t *d_seq_offsets, uint64_t *d_seq_lens, uint64_t *d_word_offsets, uint64_t *d_out_words, uint64_t *d_totals, uint64_t *d_status);
 
 /* d_out needs n - k + 1 words; any alignment of d_seq. */
 int bn_kmers_dev(bn_ctx *ctx, void *stream, const uint8_t *d_seq, size_t n, uint32_t k, uint64_t *d_out, uint64_t *d_status);

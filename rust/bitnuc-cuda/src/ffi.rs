@@ -92,9 +92,6 @@ extern "C" {
     pub fn bn_fastq_index_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, n_reads: usize, d_scratch: *mut c_void, d_index_scratch: *mut c_void, d_seq_offsets: *mut u64, d_seq_lens: *mut u64, d_word_offsets: *mut u64, d_status: *mut u64) -> c_int;
     pub fn bn_fastq_encode_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, n_reads: usize, d_scratch: *mut c_void, d_seq_offsets: *const u64, d_seq_lens: *const u64, d_word_offsets: *const u64, d_out_words: *mut u64, d_status: *mut u64) -> c_int;
     pub fn bn_fastq_status_fetch(ctx: *mut bn_ctx, stream: *mut c_void, d_status: *const u64, n_lines: u64, d_seq_offsets: *const u64, n_reads: usize, err: *mut bn_error_t) -> c_int;
-    pub fn bn_fastq_onepass_scratch_bytes(n_bytes: usize) -> usize;
-    pub fn bn_fastq_onepass_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, cap_reads: usize, cap_words: usize, d_scratch: *mut c_void, d_seq_offsets: *mut u64, d_seq_lens: *mut u64, d_word_offsets: *mut u64, d_out_words: *mut u64, d_totals: *mut u64, d_status: *mut u64) -> c_int;
-    pub fn bn_fasta_onepass_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_text: *const u8, n_bytes: usize, cap_reads: usize, cap_words: usize, d_scratch: *mut c_void, d_seq_offsets: *mut u64, d_seq_lens: *mut u64, d_word_offsets: *mut u64, d_out_words: *mut u64, d_totals: *mut u64, d_status: *mut u64) -> c_int;
     pub fn bn_kmers(ctx: *mut bn_ctx, seq: *const u8, n: usize, k: u32, out: *mut u64, n_out: *mut usize, err: *mut bn_error_t) -> c_int;
     pub fn bn_kmers_dev(ctx: *mut bn_ctx, stream: *mut c_void, d_seq: *const u8, n: usize, k: u32, d_out: *mut u64, d_status: *mut u64) -> c_int;
     pub fn bn_kmers_batch(ctx: *mut bn_ctx, bytes: *const u8, offsets: *const u64, n_reads: usize, k: u32, out: *mut u64, out_cap: usize, out_offsets: *mut u64, err: *mut bn_error_t) -> c_int;

@@ -388,25 +388,6 @@ def fastq(scale, reps, cpu_port=None):
             assert np.array_equal(cpu_w.view(np.int64), words[: sample_reads * wpr].cpu().numpy())
             extra = {"cpu_port_1thread_Gbases_s": round(sample_reads * rl / cpu_s / 1e9, 3),
                      "cpu_sample": f"{sample_reads} reads, {sample_reads * rec} bytes of text"}
-        if rl <= 1000 or os.environ.get("BN_BENCH_ONEPASS_LONG"):
-            # the capacity-based one-pass form (bn_fastq_onepass_dev), exact capacities, against the three-step outputs
-            f_one = L.bn_fasta_onepass_dev if fasta else L.bn_fastq_onepass_dev
-            oscratch = torch.empty(L.bn_fastq_onepass_scratch_bytes(n_bytes), dtype=torch.uint8, device="cuda")
-            so1, sl1, wo1, words1 = torch.zeros_like(so), torch.zeros_like(sl), torch.zeros_like(wo), torch.zeros_like(words)
-            totals = torch.zeros(3, dtype=torch.int64, device="cuda")
-            st1 = dv.FastqStatus("cuda")
-
-            def onepass():
-                dv.raise_for(f_one(ctx.handle, dv._stream(), P(text), n_bytes, n_reads, n_reads * wpr, P(oscratch), P(so1), P(sl1), P(wo1),
-                                   P(words1), P(totals), P(st1.word)))
-
-            ms_1 = timed(onepass, reps)
-            assert totals.tolist() == [st.n_lines, n_reads * wpr, 0], totals.tolist()
-            st1.n_lines, st1.seq_offsets, st1.n_reads, st1.fasta = st.n_lines, so1, n_reads, fasta
-            st1.check()
-            assert torch.equal(so1, so) and torch.equal(sl1, sl) and torch.equal(wo1, wo) and torch.equal(words1, words)
-            extra |= {"onepass_ms": round(ms_1, 4), "onepass_frac_of_measured_peak": round(alg / (ms_1 * 1e-3) / 1e9 / peak(), 4)}
-            del oscratch, so1, sl1, wo1, words1
         extra |= {"count_ms": round(ms_c, 4), "index_ms": round(ms_i, 4), "encode_ms": round(ms_e, 4), "text_bytes": n_bytes,
                  "text_GB/s": round(n_bytes / (ms * 1e-3) / 1e9, 1)}
         report(f"{'fasta' if fasta else 'fastq'} scan+encode reads={n_reads} x {rl} bp", ms, alg, n_reads * rl, "bases", extra)

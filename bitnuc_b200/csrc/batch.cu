@@ -270,7 +270,10 @@ static cudaError_t launch_encode_batch_variant(const DeviceInfo& di, const uint8
     launch_exclusive_scan(WordsOfRead{d_offsets}, n_reads, sums, d_out_word_offsets, s, NoteTileOwners<kTileWords>{tile_owner, max_tiles});
     static const int per_sm = blocks_per_sm(encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU>, kBThreads);
     const int resident = per_sm * di.sm_count;
-    // the number of output words is only known on the device: launch a full persistent grid
+    // the number of output words is only known on the device: launch a full persistent grid.  (One tile per CTA over a grid
+    // sized for the upper bound of the word count -- the form that took fastq_lines_kernel from 1.33 to 1.12 ms -- was measured
+    // here too: 7.76 against 6.77 ms on the cfg 5 mix, 1.53 against 1.42 ms on short reads; this kernel sits at its register
+    // cap either way and the empty CTAs past the real tile count cost more than the ticket.)
     encode_batch_kernel<kTileWords, kBThreads, kMinCtas, kPackU><<<resident, kBThreads, 0, s>>>(
         d_bytes, d_offsets, n_reads, d_out_word_offsets, d_out_words, d_read_status, d_status, tile_counter, tile_owner, max_tiles);
     return cudaGetLastError();

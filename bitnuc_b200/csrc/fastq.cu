@@ -336,7 +336,7 @@ fastq_records_kernel(const uint64_t* __restrict__ nl, unsigned long long n_reads
 // records from the slot rows, a warp per tile: the records whose header line ends in the tile
 constexpr int kFqRecWarps = 8;
 template <unsigned kShift>   // log2(lines per record): compile-time, so the per-record arrays stay in registers
-__global__ void __launch_bounds__(32 * kFqRecWarps)
+__global__ void __launch_bounds__(32 * kFqRecWarps, 8)   // 32 registers: 8 CTAs per SM (index step 0.358 -> 0.335 ms)
 fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ line_base, const uint32_t* __restrict__ slots,
                            unsigned long long n_tiles, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
                            uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow,

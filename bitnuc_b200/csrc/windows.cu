@@ -130,10 +130,20 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
     __shared__ int s_end[kWinBatchReads];
     __shared__ uint64_t* s_obase[kWinBatchReads];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long b_lo = offsets[0], b_hi = offsets[n_reads];             // the batch's bytes
+    // the four values everything else depends on, in one trip to memory (the owner entries of a tile past the end are
+    // allocated but unset: such a CTA returns before using them)
+    const unsigned long long b_lo = __ldg(offsets), b_hi = __ldg(offsets + n_reads);  // the batch's bytes
+    const unsigned long long own0 = __ldg(tile_owner + blockIdx.x), own1 = __ldg(tile_owner + blockIdx.x + 1);
     const unsigned long long t_lo = b_lo + (unsigned long long)blockIdx.x * kWinBatchTile;
     if (t_lo >= b_hi) return;   // the grid is sized from the caller's bound on the byte count
     n_tiles = ceil_div(b_hi - b_lo, kWinBatchTile);
+    // reads of the tile: r_first holds byte t_lo, r_last holds byte t_hi (or is the last read)
+    const unsigned long long r_first = own0, r_last = blockIdx.x + 1 < n_tiles ? own1 : n_reads - 1;
+    const bool table = r_last - r_first < (unsigned long long)kWinBatchReads;       // the tile's reads fit the shared table
+    const unsigned nr = table ? (unsigned)(r_last - r_first) + 1 : 0u;
+    // this thread's first table entry: fetched now, beside the text (a 4 KiB tile of 125-bp reads has ~33 entries)
+    unsigned long long e_st = 0, e_en = 0, e_out = 0;
+    if (tid < nr) e_st = __ldg(offsets + r_first + tid), e_en = __ldg(offsets + r_first + tid + 1), e_out = __ldg(out_offsets + r_first + tid);
     const unsigned long long t_hi = t_lo + kWinBatchTile < b_hi ? t_lo + kWinBatchTile : b_hi;
     const unsigned long long s_hi = t_hi + k - 1 < b_hi ? t_hi + k - 1 : b_hi;        // the strip also holds the k-1 bytes after the tile
     const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(bytes) + t_lo) & 15u);
@@ -155,26 +165,22 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
         codes[v] = pack16(x, bad);
         if (bad & kValidMask) win_batch_report(x, off, offsets, n_reads, k, status);
     }
+    // per read of the table: its end relative to the tile (clamped: only compared with positions < 4096) and the address
+    // of the window that would start at tile position 0
+    for (unsigned i = tid; i < nr; i += kWinThreads) {
+        if (i != tid) e_st = __ldg(offsets + r_first + i), e_en = __ldg(offsets + r_first + i + 1), e_out = __ldg(out_offsets + r_first + i);
+        const long long st = (long long)(e_st - t_lo), en = (long long)(e_en - t_lo);
+        s_end[i] = en > (1 << 30) ? (1 << 30) : (int)en;
+        s_obase[i] = out + e_out - st;
+    }
     __syncthreads();
-    // reads of the tile: r_first holds byte t_lo, r_last holds byte t_hi (or is the last read)
-    const unsigned long long r_first = tile_owner[blockIdx.x];
-    const unsigned long long r_last = blockIdx.x + 1 < n_tiles ? tile_owner[blockIdx.x + 1] : n_reads - 1;
     const uint32_t mlo = k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u;
     const uint32_t mhi = k >= 32 ? 0xFFFFFFFFu : k <= 16 ? 0u : (1u << (2 * k - 32)) - 1u;
     const unsigned long long w_end = t_lo + 1024ull * (warp + 1) < t_hi ? t_lo + 1024ull * (warp + 1) : t_hi;
     unsigned long long p = t_lo + 1024ull * warp + lane;                             // this lane's first byte position
     const uint2 keep = make_uint2(mlo, mhi);
-    if (r_last - r_first < (unsigned long long)kWinBatchReads) {
-        // the tile's reads fit the shared table: per read, its end relative to the tile (clamped: only compared with
-        // positions < 4096) and the address of the window that would start at tile position 0 -- fetched once,
-        // coalesced; lanes then search and advance in shared memory, and a window costs one add for its address
-        const unsigned nr = (unsigned)(r_last - r_first) + 1;
-        for (unsigned i = tid; i < nr; i += kWinThreads) {
-            const long long st = (long long)(__ldg(offsets + r_first + i) - t_lo), en = (long long)(__ldg(offsets + r_first + i + 1) - t_lo);
-            s_end[i] = en > (1 << 30) ? (1 << 30) : (int)en;
-            s_obase[i] = out + __ldg(out_offsets + r_first + i) - st;
-        }
-        __syncthreads();
+    if (table) {
+        // lanes search and advance in the shared table, and a window costs one add for its address
         // The warp owns the windows that start in its 1024 bytes of the tile.  It walks the reads overlapping that
         // range one after the other (warp-uniform), and its lanes stride over the window starts of the current read:
         // no per-lane bookkeeping, consecutive lanes -> consecutive output words.

@@ -137,33 +137,46 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
     const unsigned long long t_lo = b_lo + (unsigned long long)blockIdx.x * kWinBatchTile;
     if (t_lo >= b_hi) return;   // the grid is sized from the caller's bound on the byte count
     n_tiles = ceil_div(b_hi - b_lo, kWinBatchTile);
-    // reads of the tile: r_first holds byte t_lo, r_last holds byte t_hi (or is the last read)
-    const unsigned long long r_first = own0, r_last = blockIdx.x + 1 < n_tiles ? own1 : n_reads - 1;
-    const bool table = r_last - r_first < (unsigned long long)kWinBatchReads;       // the tile's reads fit the shared table
-    const unsigned nr = table ? (unsigned)(r_last - r_first) + 1 : 0u;
-    // this thread's first table entry: fetched now, beside the text (a 4 KiB tile of 125-bp reads has ~33 entries)
-    unsigned long long e_st = 0, e_en = 0, e_out = 0;
-    if (tid < nr) e_st = __ldg(offsets + r_first + tid), e_en = __ldg(offsets + r_first + tid + 1), e_out = __ldg(out_offsets + r_first + tid);
     const unsigned long long t_hi = t_lo + kWinBatchTile < b_hi ? t_lo + kWinBatchTile : b_hi;
     const unsigned long long s_hi = t_hi + k - 1 < b_hi ? t_hi + k - 1 : b_hi;        // the strip also holds the k-1 bytes after the tile
     const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(bytes) + t_lo) & 15u);
     const long long a0 = (long long)t_lo - mis;                                      // batch offset of the strip's first byte
     const unsigned nvec = (unsigned)((s_hi - a0 + 15) / 16);
-    for (unsigned v = tid; v < nvec; v += kWinThreads) {
+    // the thread's (up to three) vectors of the strip first: their addresses need the batch bounds only, so they leave
+    // before the owner entries have arrived; then its first table entry, which needs them; then the packing
+    constexpr int kVecPerThread = (kWinBatchStrip + kWinThreads - 1) / kWinThreads;
+    uint4 x[kVecPerThread];
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+        const unsigned v = tid + j * kWinThreads;
         const long long off = a0 + 16ll * v;
-        uint4 x;
-        if (off >= (long long)b_lo && (unsigned long long)off + 16 <= b_hi) {
-            x = ld128<LD_NC_NOALLOC>(reinterpret_cast<const uint4*>(bytes + off));
-        } else {  // a vector at the edge of the batch: byte-wise, 'A' outside
-            uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
-            for (int j = 0; j < 16; ++j)
-                if (off + j >= (long long)b_lo && (unsigned long long)(off + j) < b_hi)
-                    w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)bytes[off + j] << (8 * (j & 3)));
-            x = make_uint4(w[0], w[1], w[2], w[3]);
+        x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+        if (v < nvec) {
+            if (off >= (long long)b_lo && (unsigned long long)off + 16 <= b_hi) {
+                x[j] = ld128<LD_NC_NOALLOC>(reinterpret_cast<const uint4*>(bytes + off));
+            } else {  // a vector at the edge of the batch: byte-wise, 'A' outside
+                uint32_t w[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
+                for (int b = 0; b < 16; ++b)
+                    if (off + b >= (long long)b_lo && (unsigned long long)(off + b) < b_hi)
+                        w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | ((uint32_t)bytes[off + b] << (8 * (b & 3)));
+                x[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
-        uint32_t bad = 0;
-        codes[v] = pack16(x, bad);
-        if (bad & kValidMask) win_batch_report(x, off, offsets, n_reads, k, status);
+    }
+    // reads of the tile: r_first holds byte t_lo, r_last holds byte t_hi (or is the last read)
+    const unsigned long long r_first = own0, r_last = blockIdx.x + 1 < n_tiles ? own1 : n_reads - 1;
+    const bool table = r_last - r_first < (unsigned long long)kWinBatchReads;       // the tile's reads fit the shared table
+    const unsigned nr = table ? (unsigned)(r_last - r_first) + 1 : 0u;
+    unsigned long long e_st = 0, e_en = 0, e_out = 0;   // a 4 KiB tile of 125-bp reads has ~33 entries
+    if (tid < nr) e_st = __ldg(offsets + r_first + tid), e_en = __ldg(offsets + r_first + tid + 1), e_out = __ldg(out_offsets + r_first + tid);
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+        const unsigned v = tid + j * kWinThreads;
+        if (v < nvec) {
+            uint32_t bad = 0;
+            codes[v] = pack16(x[j], bad);
+            if (bad & kValidMask) win_batch_report(x[j], a0 + 16ll * v, offsets, n_reads, k, status);
+        }
     }
     // per read of the table: its end relative to the tile (clamped: only compared with positions < 4096) and the address
     // of the window that would start at tile position 0

@@ -346,6 +346,9 @@ fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __
     if (t >= n_tiles) return;
     const unsigned lane = threadIdx.x & 31;
     constexpr unsigned shift = kShift, lpr = 1u << kShift;              // lines per record
+    // the head of the tile's slot row (1 KiB = 256 entries; FASTQ text of 150-bp reads has ~200 lines per tile) is asked for
+    // now, beside the line bases its addresses would otherwise wait for
+    if (lane < 8) prefetch_l1(slots + t * kFqSlots + 32u * lane);
     const unsigned long long n_lines = line_base[n_tiles];
     const unsigned long long lb = line_base[t], le = line_base[t + 1];
     const unsigned long long n_records = (n_lines + lpr - 1) >> shift;  // a trailing partial record included (its faults count)

@@ -15,6 +15,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall",
+    *os.environ.get("BN_NVCC_EXTRA", "").split(),   # experiments only (-DNAME=value knobs of a kernel under test)
 ]
 
 

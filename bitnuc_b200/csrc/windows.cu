@@ -135,7 +135,10 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
     const unsigned long long b_lo = __ldg(offsets), b_hi = __ldg(offsets + n_reads);  // the batch's bytes
     const unsigned long long own0 = __ldg(tile_owner + blockIdx.x), own1 = __ldg(tile_owner + blockIdx.x + 1);
     const unsigned long long t_lo = b_lo + (unsigned long long)blockIdx.x * kWinBatchTile;
-    if (t_lo >= b_hi) return;   // the grid is sized from the caller's bound on the byte count
+    // the grid is sized from the caller's bound on the byte count.  (The second condition is never true for a tile inside the
+    // batch -- own0 is a read index there.  It makes the exit DEPEND on the owner entries: without it ptxas sinks their two
+    // loads below the exit, i.e. behind the round trip of the batch bounds, whatever the order they are written in.)
+    if (t_lo >= b_hi || (own0 & own1) == ~0ull) return;
     n_tiles = ceil_div(b_hi - b_lo, kWinBatchTile);
     const unsigned long long t_hi = t_lo + kWinBatchTile < b_hi ? t_lo + kWinBatchTile : b_hi;
     const unsigned long long s_hi = t_hi + k - 1 < b_hi ? t_hi + k - 1 : b_hi;        // the strip also holds the k-1 bytes after the tile
@@ -209,13 +212,22 @@ kmer_windows_batch_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __r
             const int r_hi = s_end[i];
             uint64_t* obase = s_obase[i];
             const int a = r_lo > lo ? r_lo : lo, b = r_hi - kk + 1 < hi ? r_hi - kk + 1 : hi;   // window starts [a, b)
+            // a lane's windows are 32 positions apart: the same shift every time, two code words further on, 256 bytes further
+            // out -- written with exactly those three induction variables (ncu: the kernel is issue-bound, and the loop as the
+            // compiler derived it from `q` spent 18 instructions per trip, 5 of them re-deriving these)
+            const int q0 = a + (int)lane;
+            if (q0 < b) {
+                const unsigned rel = (unsigned)q0 + mis, sh = 2u * (rel & 15u);
+                const uint32_t* cp = codes + (rel >> 4);
+                uint2* op = reinterpret_cast<uint2*>(obase + q0);
+                int trips = (b - q0 + 31) >> 5;
 #pragma unroll 1   // three or four trips per 125-bp read: an unrolled body with its remainder ladder costs more than it saves
-            for (int q = a + (int)lane; q < b; q += 32) {
-                const unsigned rel = (unsigned)q + mis;
-                const unsigned vi = rel >> 4, sh = 2u * (rel & 15u);
-                const uint32_t c0 = codes[vi], c1 = codes[vi + 1], c2 = codes[vi + 2];
-                st_stream_v2(reinterpret_cast<uint2*>(obase + q),
-                             make_uint2(__funnelshift_r(c0, c1, sh) & keep.x, __funnelshift_r(c1, c2, sh) & keep.y));
+                do {
+                    const uint32_t c0 = cp[0], c1 = cp[1], c2 = cp[2];
+                    st_stream_v2(op, make_uint2(__funnelshift_r(c0, c1, sh) & keep.x, __funnelshift_r(c1, c2, sh) & keep.y));
+                    cp += 2;
+                    op += 32;
+                } while (--trips);
             }
             if (r_hi >= hi) break;
             r_lo = r_hi;

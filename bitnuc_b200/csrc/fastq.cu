@@ -341,7 +341,6 @@ fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __
                            unsigned long long n_tiles, unsigned long long n_reads, uint64_t* __restrict__ seq_off,
                            uint64_t* __restrict__ seq_len, unsigned long long* __restrict__ status, const unsigned* __restrict__ overflow,
                            TextFormat fmt) {
-    if (*overflow != 0u) return;
     const unsigned long long t = (unsigned long long)blockIdx.x * kFqRecWarps + (threadIdx.x >> 5);
     if (t >= n_tiles) return;
     const unsigned lane = threadIdx.x & 31;
@@ -351,6 +350,9 @@ fastq_records_slots_kernel(const uint8_t* __restrict__ bytes, const uint64_t* __
     if (lane < 8) prefetch_l1(slots + t * kFqSlots + 32u * lane);
     const unsigned long long n_lines = line_base[n_tiles];
     const unsigned long long lb = line_base[t], le = line_base[t + 1];
+    // (lb <= le always: the second condition only makes the exit depend on the line bases, so that their loads leave
+    // together with the flag's instead of after it has arrived)
+    if (*overflow != 0u || lb > le) return;
     const unsigned long long n_records = (n_lines + lpr - 1) >> shift;  // a trailing partial record included (its faults count)
     unsigned long long ra = (lb + lpr - 1) >> shift, rb = (le + lpr - 1) >> shift;
     rb = rb < n_records ? rb : n_records;
@@ -759,9 +761,11 @@ fastq_encode_reads_kernel(const uint8_t* __restrict__ bytes, unsigned long long 
                           const uint64_t* __restrict__ word_off, uint64_t* __restrict__ out, unsigned long long* __restrict__ status) {
     const unsigned long long r = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
     if (r >= n_reads) return;
-    const unsigned long long len = seq_len[r];
-    if (len == 0) return;
-    fq_encode_read<kFqReadU>(bytes, n, seq_off[r], len, out + word_off[r], status);
+    const unsigned long long len = seq_len[r], s = seq_off[r], wo = word_off[r];
+    // (the second condition is never true -- two offsets into buffers.  It makes the exit DEPEND on all three table entries:
+    // otherwise ptxas sinks the loads of `s` and `wo` below the exit, and their round trip starts when `len` has arrived)
+    if (len == 0 || (s & wo) == ~0ull) return;
+    fq_encode_read<kFqReadU>(bytes, n, s, len, out + wo, status);
 }
 
 // ---------------------------------------------------------------- launchers ----------------------------------------

@@ -243,12 +243,16 @@ get_batch_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
     const unsigned long long q = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
     if (q >= nq) return;
     const unsigned long long r = q_read[q], i = q_index[q];
-    if (r >= n_reads || i >= lens[r]) {
+    // lens[r] and word_offsets[r] leave together (asked for after the validity test, the word offset would start its
+    // round trip only when the length has arrived: ptxas sinks a load below an exit that does not need it)
+    const bool in_table = r < n_reads;
+    const unsigned long long len = in_table ? __ldg(lens + r) : 0ull, wo = in_table ? __ldg(word_offsets + r) : 0ull;
+    if (i >= len || wo == ~0ull) {   // (wo == ~0 never holds: it makes the exit depend on wo)
         out[q] = 0;
         if (q < ld_volatile_u64(status)) atomicMin(status, q);
         return;
     }
-    const uint64_t x = __ldg(words + word_offsets[r] + (i >> 5));
+    const uint64_t x = __ldg(words + wo + (i >> 5));
     out[q] = (uint8_t)(0x54474341u >> (8 * ((x >> (2 * (i & 31))) & 3)));
 }
 

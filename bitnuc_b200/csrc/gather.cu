@@ -181,29 +181,25 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
     const bool staged = g_lo - g_base + (span_hi - span_lo) <= kSliceStage;
     uint8_t* o = staged ? stage[warp] + (reinterpret_cast<uintptr_t>(out) + oo - g_base) : out + oo;
     if (n) {
-        // head: bases up to the first 4-byte aligned output address (global and staged addresses share their phase)
-        const unsigned head = min((4u - (unsigned)((reinterpret_cast<uintptr_t>(out) + oo) & 3u)) & 3u, n);
-        if (head) {
-            const unsigned long long wi = s >> 5;
-            const unsigned sh = 2u * (unsigned)(s & 31u);
-            uint64_t x = __ldg(w + wi) >> sh;
-            if (sh + 2u * head > 64u) x |= __ldg(w + wi + 1) << (64 - sh);   // 3 bases may straddle two words (a valid range: the word exists)
-            for (unsigned i = 0; i < head; ++i) o[i] = (uint8_t)(0x54474341u >> (8u * ((unsigned)(x >> (2 * i)) & 3u)));
-            s += head;
-            n -= head;
-            sh_head = head;
-        }
-    }
-    if (n) {
-        // 128-bit window of the remaining 2n bits
+        // the range's <= 64 bases as one 128-bit window, from ONE set of loads (the head bytes used to fetch their words
+        // first, then the body fetched them again: two dependent trips, even if the second hit L1)
         const unsigned long long wi = s >> 5;
         const unsigned sh = 2u * (unsigned)(s & 31u);
         const unsigned need_bits = sh + 2u * n;                      // bits needed counted from the start of word wi
         const uint64_t w0 = __ldg(w + wi);
         const uint64_t w1 = need_bits > 64 ? __ldg(w + wi + 1) : 0ull;
         const uint64_t w2 = need_bits > 128 ? __ldg(w + wi + 2) : 0ull;
-        const uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
-        const uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+        uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+        uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+        // head: bases up to the first 4-byte aligned output address (global and staged addresses share their phase)
+        const unsigned head = min((4u - (unsigned)((reinterpret_cast<uintptr_t>(out) + oo) & 3u)) & 3u, n);
+        if (head) {
+            for (unsigned i = 0; i < head; ++i) o[i] = (uint8_t)(0x54474341u >> (8u * ((unsigned)(lo >> (2 * i)) & 3u)));
+            lo = (lo >> (2 * head)) | (hi << (64 - 2 * head));
+            hi >>= 2 * head;
+            n -= head;
+            sh_head = head;
+        }
         uint32_t* o32 = reinterpret_cast<uint32_t*>(o + sh_head);
         const unsigned body = n / 4;
 #pragma unroll

@@ -126,9 +126,12 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
                     uint64_t* __restrict__ out_a, uint64_t* __restrict__ out_b, H hook) {
     __shared__ unsigned long long warp_tot[NCH][32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long c[kScanItems][NCH], excl[kScanItems][NCH], carry[NCH];
+    unsigned long long c[kScanItems][NCH], excl[kScanItems][NCH], carry[NCH], tile_base[NCH];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) carry[ch] = 0;
+    for (int ch = 0; ch < NCH; ++ch) {
+        carry[ch] = 0;
+        tile_base[ch] = sums[ch * (n_blocks + 1) + blockIdx.x];   // asked for with the items (read after the barriers it was one more trip)
+    }
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {  // all loads first (independent), the row scans below
         const unsigned long long r = scan_item(i);
@@ -173,7 +176,7 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
     __syncthreads();
     unsigned long long base[NCH];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) base[ch] = sums[ch * (n_blocks + 1) + blockIdx.x] + warp_tot[ch][warp];
+    for (int ch = 0; ch < NCH; ++ch) base[ch] = tile_base[ch] + warp_tot[ch][warp];
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
         const unsigned long long r = scan_item(i);

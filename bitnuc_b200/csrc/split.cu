@@ -37,27 +37,28 @@ __device__ __forceinline__ void split_one(const uint64_t* __restrict__ w, unsign
     const unsigned long long c = all_right ? 0 : i / 32;
     const unsigned sh = all_right || all_left ? 0u : 2 * (unsigned)(i % 32);
     if (nw <= kSpPre) {
+        const unsigned n = (unsigned)nw, cc = (unsigned)c;   // 32-bit from here on: every `j < nw` on 64 bits is two instructions
         uint64_t x[kSpPre];
 #pragma unroll
-        for (int j = 0; j < kSpPre; ++j) x[j] = (unsigned long long)j < nw ? __ldg(w + j) : 0ull;
+        for (int j = 0; j < kSpPre; ++j) x[j] = (unsigned)j < n ? __ldg(w + j) : 0ull;
         if (all_left) {
 #pragma unroll
             for (int j = 0; j < kSpPre; ++j)
-                if ((unsigned long long)j < nw) lo[j] = x[j];
+                if ((unsigned)j < n) lo[j] = x[j];
             return;
         }
         if (!all_right) {
 #pragma unroll
             for (int j = 0; j < kSpPre; ++j) {
-                if ((unsigned long long)j < c) lo[j] = x[j];
-                else if ((unsigned long long)j == c) lo[j] = sh ? x[j] & ((1ull << sh) - 1ull) : 0ull;
+                if ((unsigned)j < cc) lo[j] = x[j];
+                else if ((unsigned)j == cc) lo[j] = sh ? x[j] & ((1ull << sh) - 1ull) : 0ull;
             }
         }
 #pragma unroll
         for (int j = 0; j < kSpPre; ++j) {
-            if ((unsigned long long)j >= c && (unsigned long long)j < nw) {
+            if ((unsigned)j >= cc && (unsigned)j < n) {
                 const uint64_t prev = j > 0 ? x[j > 0 ? j - 1 : 0] : 0ull;
-                ro[j - c] = sh ? (x[j] >> sh) | ((unsigned long long)j > c ? prev << (64 - sh) : 0ull) : x[j];
+                ro[(unsigned)j - cc] = sh ? (x[j] >> sh) | ((unsigned)j > cc ? prev << (64 - sh) : 0ull) : x[j];
             }
         }
         return;
@@ -218,7 +219,10 @@ split_packed_fused_kernel(const uint64_t* __restrict__ words, const uint64_t* __
             if (r + 1 == n_reads) left_offsets[n_reads] = base_l + il, right_offsets[n_reads] = base_r + ir;
         }
         const bool staged = tot_l <= (unsigned)kSpCap && tot_r <= (unsigned)kSpCap;   // warp-uniform
-        if (live) split_one(words + wo, nw, slen, ix, staged ? s_left[warp] + ll : left + base_l + ll, staged ? s_right[warp] + lr : right + base_r + lr);
+        if (live) {   // two call sites: behind one `staged ? shared : global` pointer every store was a generic ST behind a branch
+            if (staged) split_one(words + wo, nw, slen, ix, s_left[warp] + ll, s_right[warp] + lr);
+            else split_one(words + wo, nw, slen, ix, left + base_l + ll, right + base_r + lr);
+        }
         if (staged) {
             __syncwarp();
             for (unsigned k = lane; k < tot_l; k += 32) left[base_l + k] = s_left[warp][k];

@@ -60,6 +60,45 @@ constexpr int kSlTile = kThreads * kSlRows;
 #endif
 constexpr int kSlBatch = BN_SL_BATCH;             // rows of pass A whose loads are in flight together
 
+// One short range (n <= kSliceShort bases from base s of the words at w) -> n ASCII bytes at o; `phase` = the low two bits
+// of the output address (o may be the staged image: same phase).
+__device__ __forceinline__ void slice_cut(const uint64_t* __restrict__ w, unsigned long long s, unsigned n, unsigned phase, uint8_t* __restrict__ o) {
+    // the range's <= 64 bases as one 128-bit window, from ONE set of loads (the head bytes used to fetch their words
+    // first, then the body fetched them again: two dependent trips, even if the second hit L1)
+    const unsigned long long wi = s >> 5;
+    const unsigned sh = 2u * (unsigned)(s & 31u);
+    const unsigned need_bits = sh + 2u * n;                      // bits needed counted from the start of word wi
+    const uint64_t w0 = __ldg(w + wi);
+    const uint64_t w1 = need_bits > 64 ? __ldg(w + wi + 1) : 0ull;
+    const uint64_t w2 = need_bits > 128 ? __ldg(w + wi + 2) : 0ull;
+    uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+    // head: bases up to the first 4-byte aligned output address
+    const unsigned head = min((4u - phase) & 3u, n);
+    if (head) {
+        for (unsigned i = 0; i < head; ++i) o[i] = (uint8_t)(0x54474341u >> (8u * ((unsigned)(lo >> (2 * i)) & 3u)));
+        lo = (lo >> (2 * head)) | (hi << (64 - 2 * head));
+        hi >>= 2 * head;
+        n -= head;
+    }
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(o + head);
+    const unsigned body = n / 4;
+#pragma unroll
+    for (unsigned g = 0; g < kSliceShort / 4; ++g) {
+        if (g < body) {
+            uint32_t t = (uint32_t)((g < 8 ? lo >> (8 * g) : hi >> (8 * (g - 8))) & 0xFFu);
+            t = (t | (t << 4)) & 0x0F0Fu;
+            t = (t | (t << 2)) & 0x3333u;
+            o32[g] = __byte_perm(0x54474341u, 0u, t);
+        }
+    }
+    const unsigned done = 4 * body;
+    if (done < n) {
+        const uint32_t t = (uint32_t)((body < 8 ? lo >> (8 * body) : hi >> (8 * (body - 8))) & 0xFFu);
+        for (unsigned i = 0; done + i < n; ++i) o[head + done + i] = (uint8_t)(0x54474341u >> (8u * ((t >> (2 * i)) & 3u)));
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_offsets, const uint64_t* __restrict__ lens,
                    unsigned long long n_reads, const uint64_t* __restrict__ q_read, const uint64_t* __restrict__ q_start,
@@ -163,7 +202,7 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
         out_offsets[q] = oo;
         if (q + 1 == nq) out_offsets[nq] = oo + cnt;
     }
-    unsigned n = 0, sh_head = 0;
+    unsigned n = 0;
     unsigned long long s = 0;
     const uint64_t* w = words;
     if (cnt > kSliceShort) {
@@ -179,43 +218,10 @@ slice_short_kernel(const uint64_t* __restrict__ words, const uint64_t* __restric
     const unsigned long long span_hi = __shfl_sync(0xffffffffu, oo + cnt, 31);
     const uintptr_t g_lo = reinterpret_cast<uintptr_t>(out) + span_lo, g_base = g_lo & ~(uintptr_t)15;
     const bool staged = g_lo - g_base + (span_hi - span_lo) <= kSliceStage;
-    uint8_t* o = staged ? stage[warp] + (reinterpret_cast<uintptr_t>(out) + oo - g_base) : out + oo;
-    if (n) {
-        // the range's <= 64 bases as one 128-bit window, from ONE set of loads (the head bytes used to fetch their words
-        // first, then the body fetched them again: two dependent trips, even if the second hit L1)
-        const unsigned long long wi = s >> 5;
-        const unsigned sh = 2u * (unsigned)(s & 31u);
-        const unsigned need_bits = sh + 2u * n;                      // bits needed counted from the start of word wi
-        const uint64_t w0 = __ldg(w + wi);
-        const uint64_t w1 = need_bits > 64 ? __ldg(w + wi + 1) : 0ull;
-        const uint64_t w2 = need_bits > 128 ? __ldg(w + wi + 2) : 0ull;
-        uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
-        uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
-        // head: bases up to the first 4-byte aligned output address (global and staged addresses share their phase)
-        const unsigned head = min((4u - (unsigned)((reinterpret_cast<uintptr_t>(out) + oo) & 3u)) & 3u, n);
-        if (head) {
-            for (unsigned i = 0; i < head; ++i) o[i] = (uint8_t)(0x54474341u >> (8u * ((unsigned)(lo >> (2 * i)) & 3u)));
-            lo = (lo >> (2 * head)) | (hi << (64 - 2 * head));
-            hi >>= 2 * head;
-            n -= head;
-            sh_head = head;
-        }
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(o + sh_head);
-        const unsigned body = n / 4;
-#pragma unroll
-        for (unsigned g = 0; g < kSliceShort / 4; ++g) {
-            if (g < body) {
-                uint32_t t = (uint32_t)((g < 8 ? lo >> (8 * g) : hi >> (8 * (g - 8))) & 0xFFu);
-                t = (t | (t << 4)) & 0x0F0Fu;
-                t = (t | (t << 2)) & 0x3333u;
-                o32[g] = __byte_perm(0x54474341u, 0u, t);
-            }
-        }
-        const unsigned done = 4 * body;
-        if (done < n) {
-            const uint32_t t = (uint32_t)((body < 8 ? lo >> (8 * body) : hi >> (8 * (body - 8))) & 0xFFu);
-            for (unsigned i = 0; done + i < n; ++i) o[sh_head + done + i] = (uint8_t)(0x54474341u >> (8u * ((t >> (2 * i)) & 3u)));
-        }
+    if (n) {   // two call sites: behind one `staged ? shared : global` pointer every store is a generic ST behind a branch
+        const unsigned phase = (unsigned)((reinterpret_cast<uintptr_t>(out) + oo) & 3u);   // global and staged addresses share it
+        if (staged) slice_cut(w, s, n, phase, stage[warp] + (reinterpret_cast<uintptr_t>(out) + oo - g_base));
+        else slice_cut(w, s, n, phase, out + oo);
     }
     // (A span can hold one long range and still fit the stage when its other queries are empty: the copy-out below
     // then also writes that range's bytes, with whatever the image holds.  slice_long_kernel runs after this kernel on

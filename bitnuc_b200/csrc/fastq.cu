@@ -48,6 +48,7 @@ constexpr int kFqThreads = 256;              // x 4 vectors of 16 bytes
 constexpr int kFqEncTile = 65536;            // bytes of text per encode tile
 constexpr int kFqLongWords = 64;             // a read with more words than this inside the strip is cut by whole warps
 constexpr unsigned long long kCrBit = 1ull << 63;
+constexpr unsigned long long kFqGiantBases = 1ull << 20;   // a read longer than this is cut by the whole grid, not by one warp
 constexpr int kFqSlots = 2048;               // line entries per tile (more lines than this: the dense fallback)
 constexpr uint32_t kSlotPos = 0x3FFFu, kSlotCr = 1u << 14, kSlotAt = 1u << 15, kSlotPlus = 1u << 16;
 
@@ -768,6 +769,94 @@ fastq_encode_reads_kernel(const uint8_t* __restrict__ bytes, unsigned long long 
     fq_encode_read<kFqReadU>(bytes, n, s, len, out + wo, status);
 }
 
+// ---------------------------------------------------------------- 3''. encode, a warp per read (long reads) ----------
+// In FASTQ text half the bytes are quality values; the tiled kernel above loads and packs them with everything else
+// (6.0 GB of text for 3.0 Gbases of 10 kbp reads).  Here a warp takes ONE read and walks its sequence line in chunks of 64
+// output words: the (up to 130) aligned 16-byte vectors behind a chunk are fetched lane-consecutively -- all of a lane's
+// loads before anything is packed --, packed into a per-warp code strip in shared memory (bytes of the first and last vector
+// outside the chunk become 'A': valid, and code 00 is the zero padding of a ragged last word), and every lane cuts two words
+// out of the strip: 512-byte coalesced loads, 256-byte coalesced stores, only sequence bytes cross the memory system.
+// A read of more than kFqGiant bases is queued instead and cut by the whole grid (fastq_encode_giant_kernel): one warp
+// would crawl through a chromosome on one line.
+constexpr int kFqChunkWords = 64;
+constexpr int kFqChunkVecs = kFqChunkWords * 2 + 2;          // 2048 bases + the misalignment of both ends
+constexpr int kFqChunkPerLane = (kFqChunkVecs + 31) / 32;    // 5
+constexpr int kFqLongWarps = 8;
+constexpr unsigned long long kFqGiant = kFqGiantBases;
+
+// chunks first, first + stride, ... of the read text[s, s + len) -> o[..]; strip = kFqChunkVecs + 4 codes owned by the warp
+__device__ __forceinline__ void fq_encode_chunks(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long s,
+                                                 unsigned long long len, uint64_t* __restrict__ o, uint32_t* __restrict__ strip,
+                                                 unsigned long long first, unsigned long long stride,
+                                                 unsigned long long* __restrict__ status) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long nw = (len + 31) / 32, e = s + len;
+    for (unsigned long long w0 = first * kFqChunkWords; w0 < nw; w0 += stride * kFqChunkWords) {
+        const unsigned cnt = nw - w0 < (unsigned long long)kFqChunkWords ? (unsigned)(nw - w0) : (unsigned)kFqChunkWords;
+        const unsigned long long p0 = s + 32 * w0, p1 = p0 + 32ull * cnt < e ? p0 + 32ull * cnt : e;   // the chunk's bytes
+        const unsigned long long a0 = p0 & ~15ull;
+        const unsigned nvec = (unsigned)((p1 - a0 + 15) >> 4);                                          // <= kFqChunkVecs
+        uint4 x[kFqChunkPerLane];
+#pragma unroll
+        for (int j = 0; j < kFqChunkPerLane; ++j) {
+            const unsigned v = lane + 32 * j;
+            x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+            if (v < nvec) x[j] = enc_load_stream(bytes, n, a0 + 16ull * v);
+        }
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < kFqChunkPerLane; ++j) {
+            const unsigned v = lane + 32 * j;
+            if (v < nvec + 2) {   // two more codes: the window of the chunk's last word reaches past its last vector
+                const unsigned long long pos = a0 + 16ull * v;
+                uint4 y = x[j];
+                if (pos < p0 || pos + 16 > p1)
+                    y = keep_bytes(y, pos < p0 ? (int)(p0 - pos) : 0, pos + 16 > p1 ? (p1 > pos ? (int)(p1 - pos) : 0) : 16);
+                strip[v] = pack16(y, bad);
+            }
+        }
+        __syncwarp();
+        const unsigned rel0 = (unsigned)(p0 - a0);
+#pragma unroll
+        for (int k = 0; k < kFqChunkWords / 32; ++k) {
+            const unsigned j = lane + 32 * k;
+            if (j < cnt) o[w0 + j] = fq_cut_word(strip, rel0 + 32u * j);
+        }
+        if (__any_sync(0xffffffffu, (bad & kValidMask) != 0u) && lane == 0) fq_report_range(bytes, p0, p1, status);
+        __syncwarp();   // the strip is reused by the next chunk
+    }
+}
+
+__global__ void __launch_bounds__(32 * kFqLongWarps)
+fastq_encode_long_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_reads,
+                         const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off,
+                         uint64_t* __restrict__ out, unsigned long long* __restrict__ status, unsigned long long* __restrict__ giants) {
+    __shared__ uint32_t strip[kFqLongWarps][kFqChunkVecs + 6];
+    const unsigned long long r = (unsigned long long)blockIdx.x * kFqLongWarps + (threadIdx.x >> 5);
+    if (r >= n_reads) return;
+    const unsigned long long len = seq_len[r], s = seq_off[r], wo = word_off[r];
+    if (len == 0 || (s & wo) == ~0ull) return;   // (the second term only keeps the three loads together, see fastq_encode_reads_kernel)
+    if (len > kFqGiant) {
+        if ((threadIdx.x & 31) == 0) giants[1 + atomicAdd(giants, 1ull)] = r;
+        return;
+    }
+    fq_encode_chunks(bytes, n, s, len, out + wo, strip[threadIdx.x >> 5], 0, 1, status);
+}
+
+// the queued giant reads, one after the other, the whole grid striding over the chunks of each
+__global__ void __launch_bounds__(32 * kFqLongWarps)
+fastq_encode_giant_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ seq_off,
+                          const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off, uint64_t* __restrict__ out,
+                          unsigned long long* __restrict__ status, const unsigned long long* __restrict__ giants) {
+    __shared__ uint32_t strip[kFqLongWarps][kFqChunkVecs + 6];
+    const unsigned long long n_giants = giants[0];
+    const unsigned long long warp = (unsigned long long)blockIdx.x * kFqLongWarps + (threadIdx.x >> 5), n_warps = (unsigned long long)gridDim.x * kFqLongWarps;
+    for (unsigned long long i = 0; i < n_giants; ++i) {
+        const unsigned long long r = giants[1 + i];
+        fq_encode_chunks(bytes, n, seq_off[r], seq_len[r], out + word_off[r], strip[threadIdx.x >> 5], warp, n_warps, status);
+    }
+}
+
 // ---------------------------------------------------------------- launchers ----------------------------------------
 // d_scratch (fastq_scratch_bytes): counts[n_tiles] | line_base[n_tiles + 1] | scan sums
 // d_index_scratch (fastq_index_scratch_bytes): nl[4 n_reads] | scan sums
@@ -776,7 +865,9 @@ static inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 size_t fastq_scratch_bytes(size_t n_bytes) {
     const size_t t = fastq_tiles(n_bytes);
-    return align16(t * 8) + align16((t + 1) * 8) + align16(scan_scratch_bytes(t)) + 16 + t * kFqSlots * sizeof(uint32_t);
+    // ... + the queue of giant reads of the long-read encode (a count, then at most n_bytes / kFqGiantBases entries)
+    return align16(t * 8) + align16((t + 1) * 8) + align16(scan_scratch_bytes(t)) + 16 + t * kFqSlots * sizeof(uint32_t) +
+           (2 + n_bytes / kFqGiantBases) * sizeof(unsigned long long);
 }
 size_t fastq_index_scratch_bytes(size_t n_reads) { return align16((n_reads ? n_reads : 1) * 32) + scan_scratch_bytes(n_reads ? n_reads : 1); }
 
@@ -786,6 +877,7 @@ struct FqScratch {
     unsigned long long* sums;
     unsigned* overflow;
     uint32_t* slots;
+    unsigned long long* giants;
     unsigned long long n_tiles;
     FqScratch(void* p, size_t n_bytes) {
         n_tiles = fastq_tiles(n_bytes);
@@ -798,6 +890,7 @@ struct FqScratch {
         c += align16(scan_scratch_bytes(n_tiles));
         overflow = reinterpret_cast<unsigned*>(c);
         slots = reinterpret_cast<uint32_t*>(c + 16);
+        giants = reinterpret_cast<unsigned long long*>(slots + n_tiles * kFqSlots);
     }
 };
 
@@ -866,6 +959,16 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
         // (3,5) 1.04, (2,6) 1.09, (6,2) 1.45 -- residency beats loads in flight per thread
         fastq_encode_reads_kernel<3, 5><<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(d_bytes, n_bytes, n_reads, d_seq_offsets,
                                                                                                   d_seq_lens, d_word_offsets, d_out_words, d_status);
+        return cudaGetLastError();
+    }
+    if (forced < 0 && n_bytes / n_reads > 4096) {   // long records: a warp per read, only the sequence bytes are fetched
+        unsigned long long* giants = sc.giants;
+        cudaError_t e = cudaMemsetAsync(giants, 0, sizeof(unsigned long long), s);
+        if (e != cudaSuccess) return e;
+        fastq_encode_long_kernel<<<(unsigned)ceil_div(n_reads, kFqLongWarps), 32 * kFqLongWarps, 0, s>>>(d_bytes, n_bytes, n_reads, d_seq_offsets, d_seq_lens,
+                                                                                                     d_word_offsets, d_out_words, d_status, giants);
+        fastq_encode_giant_kernel<<<148 * 4, 32 * kFqLongWarps, 0, s>>>(d_bytes, n_bytes, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status,
+                                                                        giants);
         return cudaGetLastError();
     }
     const int variant = forced >= 0 ? forced : (n_bytes / n_reads > 4096 ? 11 : 13);

@@ -795,39 +795,62 @@ __device__ __forceinline__ void fq_encode_chunks(const uint8_t* __restrict__ byt
         const unsigned cnt = nw - w0 < (unsigned long long)kFqChunkWords ? (unsigned)(nw - w0) : (unsigned)kFqChunkWords;
         const unsigned long long p0 = s + 32 * w0, p1 = p0 + 32ull * cnt < e ? p0 + 32ull * cnt : e;   // the chunk's bytes
         const unsigned long long a0 = p0 & ~15ull;
-        const unsigned nvec = (unsigned)((p1 - a0 + 15) >> 4);                                          // <= kFqChunkVecs
+        // everything below in 32-bit offsets from a0 (ncu: the kernel is bound by instruction issue, and positions compared
+        // on 64 bits were a good part of its 515 warp instructions per chunk)
+        const unsigned rel0 = (unsigned)(p0 - a0), span = (unsigned)(p1 - a0), nvec = (span + 15u) >> 4;   // <= kFqChunkVecs
+        const uint4* src = reinterpret_cast<const uint4*>(bytes + a0);
         uint4 x[kFqChunkPerLane];
+        if (a0 + 16ull * nvec <= n) {   // warp-uniform: the chunk's vectors lie inside the text
 #pragma unroll
-        for (int j = 0; j < kFqChunkPerLane; ++j) {
-            const unsigned v = lane + 32 * j;
-            x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-            if (v < nvec) x[j] = enc_load_stream(bytes, n, a0 + 16ull * v);
+            for (int j = 0; j < kFqChunkPerLane; ++j) {
+                const unsigned v = lane + 32 * j;
+                x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+                if (v < nvec) x[j] = ld128<LD_NC_NOALLOC>(src + v);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kFqChunkPerLane; ++j) {
+                const unsigned v = lane + 32 * j;
+                x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+                if (v < nvec) x[j] = enc_load_stream(bytes, n, a0 + 16ull * v);
+            }
         }
         uint32_t bad = 0;
+        // An inner chunk -- it starts on a vector boundary or inside the read, and ends inside the read -- is packed as it is:
+        // the bytes of its end vectors that lie outside it are bases of the same read (an invalid one among them is found by
+        // the neighbouring chunk too; here it costs one needless scan).  The read's first and last chunk mask their end vectors.
+        if ((w0 != 0 || rel0 == 0) && p1 != e) {   // warp-uniform
 #pragma unroll
-        for (int j = 0; j < kFqChunkPerLane; ++j) {
-            const unsigned v = lane + 32 * j;
-            if (v < nvec + 2) {   // two more codes: the window of the chunk's last word reaches past its last vector
-                const unsigned long long pos = a0 + 16ull * v;
-                uint4 y = x[j];
-                if (pos < p0 || pos + 16 > p1)
-                    y = keep_bytes(y, pos < p0 ? (int)(p0 - pos) : 0, pos + 16 > p1 ? (p1 > pos ? (int)(p1 - pos) : 0) : 16);
-                strip[v] = pack16(y, bad);
+            for (int j = 0; j < kFqChunkPerLane; ++j) {
+                const unsigned v = lane + 32 * j;
+                if (v < nvec) strip[v] = pack16(x[j], bad);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kFqChunkPerLane; ++j) {
+                const unsigned v = lane + 32 * j;
+                if (v < nvec + 2) {   // two more codes (zero): the window of a ragged last word reaches past the last vector
+                    const unsigned pos = 16u * v;
+                    uint4 y = x[j];
+                    if (pos < rel0 || pos + 16 > span)
+                        y = keep_bytes(y, pos < rel0 ? (int)(rel0 - pos) : 0, pos + 16 > span ? (span > pos ? (int)(span - pos) : 0) : 16);
+                    strip[v] = pack16(y, bad);
+                }
             }
         }
         __syncwarp();
-        const unsigned rel0 = (unsigned)(p0 - a0);
+        uint64_t* oc = o + w0;
 #pragma unroll
         for (int k = 0; k < kFqChunkWords / 32; ++k) {
             const unsigned j = lane + 32 * k;
-            if (j < cnt) o[w0 + j] = fq_cut_word(strip, rel0 + 32u * j);
+            if (j < cnt) oc[j] = fq_cut_word(strip, rel0 + 32u * j);
         }
         if (__any_sync(0xffffffffu, (bad & kValidMask) != 0u) && lane == 0) fq_report_range(bytes, p0, p1, status);
         __syncwarp();   // the strip is reused by the next chunk
     }
 }
 
-__global__ void __launch_bounds__(32 * kFqLongWarps)
+__global__ void __launch_bounds__(32 * kFqLongWarps, 4)   // 64 registers; 3 / 4 / 5 CTAs per SM: 0.918 / 0.894 / 1.012 ms
 fastq_encode_long_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_reads,
                          const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off,
                          uint64_t* __restrict__ out, unsigned long long* __restrict__ status, unsigned long long* __restrict__ giants) {

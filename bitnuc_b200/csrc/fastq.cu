@@ -698,7 +698,8 @@ fastq_encode_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, con
 // relies on L1; three blocks are in flight per thread before the first is packed (a 150-base read is five or six).  A block packs to one
 // 64-bit code word; output word j is the 64-bit window 2 * (start mod 32) bits into code words j, j + 1.  Bytes of the
 // first and last vector that lie outside the line are replaced by 'A' before packing (valid, code 00: they shift out at
-// the front and are the zero padding at the back).  No shared memory, no barrier.  Long reads keep the tiled kernel.
+// the front and are the zero padding at the back).  No shared memory, no barrier.  Records of 1-4 KiB keep the tiled kernel,
+// longer ones take fastq_encode_long_kernel below.
 
 // bytes [l, h) of the vector stay, the others become 'A'
 __device__ __forceinline__ uint4 keep_bytes(uint4 v, int l, int h) {
@@ -984,7 +985,11 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
                                                                                                   d_seq_lens, d_word_offsets, d_out_words, d_status);
         return cudaGetLastError();
     }
-    if (forced < 0 && n_bytes / n_reads > 4096) {   // long records: a warp per read, only the sequence bytes are fetched
+    static const size_t long_min = [] {
+        const char* v = getenv("BN_FQ_LONG_MIN");
+        return v ? (size_t)atoll(v) : (size_t)4096;
+    }();
+    if (forced < 0 && n_bytes / n_reads > long_min) {   // long records: a warp per read, only the sequence bytes are fetched
         unsigned long long* giants = sc.giants;
         cudaError_t e = cudaMemsetAsync(giants, 0, sizeof(unsigned long long), s);
         if (e != cudaSuccess) return e;

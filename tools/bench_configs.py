@@ -326,6 +326,7 @@ def fastq(scale, reps, cpu_port=None):
     10 kbp reads.  Checked against bn_encode_batch_dev of the same sequences."""
     ctx = dv.api.default_context(0)
     for n_reads, rl, hdr, fasta in ((int(20_000_000 * scale), 150, 23, False), (int(300_000 * scale), 10_000, 37, False),
+                                    (int(3_000_000 * scale), 1_000, 37, False),
                                     (int(20_000_000 * scale), 150, 23, True)):
         rec = hdr + rl + 1 if fasta else hdr + rl + 1 + 2 + rl + 1
         seqs = dv.synth_ascii(SEED, 7, 0, n_reads * rl).view(n_reads, rl)

@@ -779,39 +779,49 @@ fastq_encode_reads_kernel(const uint8_t* __restrict__ bytes, unsigned long long 
 // out of the strip: 512-byte coalesced loads, 256-byte coalesced stores, only sequence bytes cross the memory system.
 // A read of more than kFqGiant bases is queued instead and cut by the whole grid (fastq_encode_giant_kernel): one warp
 // would crawl through a chromosome on one line.
-constexpr int kFqChunkWords = 64;
-constexpr int kFqChunkVecs = kFqChunkWords * 2 + 2;          // 2048 bases + the misalignment of both ends
-constexpr int kFqChunkPerLane = (kFqChunkVecs + 31) / 32;    // 5
+// Records between the two (1 - 4 KiB) take the same walk with G = 16 or 8 lanes per read -- two or four reads per warp, chunks
+// of 2 G words, the group synchronising on its own lane mask -- instead of the tiled kernel.
+constexpr int kFqChunkPerLane = 5;          // a chunk of 2 G words is 4 G + 2 vectors (+ 2 padding codes): five per lane
 constexpr int kFqLongWarps = 8;
 constexpr unsigned long long kFqGiant = kFqGiantBases;
+template <int G>
+struct FqGroup {
+    static constexpr int kWords = 2 * G, kVecs = 4 * G + 2, kStrip = kVecs + 6;
+    static_assert(G == 8 || G == 16 || G == 32, "lanes per read");
+    static_assert(kFqChunkPerLane * G >= kVecs + 2, "five vectors per lane cover a chunk and its padding codes");
+};
 
-// chunks first, first + stride, ... of the read text[s, s + len) -> o[..]; strip = kFqChunkVecs + 4 codes owned by the warp
+// chunks first, first + stride, ... of the read text[s, s + len) -> o[..], by the G lanes of this thread's group;
+// strip = FqGroup<G>::kStrip codes owned by the group
+template <int G>
 __device__ __forceinline__ void fq_encode_chunks(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long s,
                                                  unsigned long long len, uint64_t* __restrict__ o, uint32_t* __restrict__ strip,
                                                  unsigned long long first, unsigned long long stride,
                                                  unsigned long long* __restrict__ status) {
-    const unsigned lane = threadIdx.x & 31;
+    constexpr int kWords = FqGroup<G>::kWords;
+    const unsigned lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));   // the lanes of this group
     const unsigned long long nw = (len + 31) / 32, e = s + len;
-    for (unsigned long long w0 = first * kFqChunkWords; w0 < nw; w0 += stride * kFqChunkWords) {
-        const unsigned cnt = nw - w0 < (unsigned long long)kFqChunkWords ? (unsigned)(nw - w0) : (unsigned)kFqChunkWords;
+    for (unsigned long long w0 = first * kWords; w0 < nw; w0 += stride * kWords) {
+        const unsigned cnt = nw - w0 < (unsigned long long)kWords ? (unsigned)(nw - w0) : (unsigned)kWords;
         const unsigned long long p0 = s + 32 * w0, p1 = p0 + 32ull * cnt < e ? p0 + 32ull * cnt : e;   // the chunk's bytes
         const unsigned long long a0 = p0 & ~15ull;
         // everything below in 32-bit offsets from a0 (ncu: the kernel is bound by instruction issue, and positions compared
         // on 64 bits were a good part of its 515 warp instructions per chunk)
-        const unsigned rel0 = (unsigned)(p0 - a0), span = (unsigned)(p1 - a0), nvec = (span + 15u) >> 4;   // <= kFqChunkVecs
+        const unsigned rel0 = (unsigned)(p0 - a0), span = (unsigned)(p1 - a0), nvec = (span + 15u) >> 4;   // <= kVecs
         const uint4* src = reinterpret_cast<const uint4*>(bytes + a0);
         uint4 x[kFqChunkPerLane];
-        if (a0 + 16ull * nvec <= n) {   // warp-uniform: the chunk's vectors lie inside the text
+        if (a0 + 16ull * nvec <= n) {   // group-uniform: the chunk's vectors lie inside the text
 #pragma unroll
             for (int j = 0; j < kFqChunkPerLane; ++j) {
-                const unsigned v = lane + 32 * j;
+                const unsigned v = gl + G * j;
                 x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
                 if (v < nvec) x[j] = ld128<LD_NC_NOALLOC>(src + v);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < kFqChunkPerLane; ++j) {
-                const unsigned v = lane + 32 * j;
+                const unsigned v = gl + G * j;
                 x[j] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
                 if (v < nvec) x[j] = enc_load_stream(bytes, n, a0 + 16ull * v);
             }
@@ -820,16 +830,16 @@ __device__ __forceinline__ void fq_encode_chunks(const uint8_t* __restrict__ byt
         // An inner chunk -- it starts on a vector boundary or inside the read, and ends inside the read -- is packed as it is:
         // the bytes of its end vectors that lie outside it are bases of the same read (an invalid one among them is found by
         // the neighbouring chunk too; here it costs one needless scan).  The read's first and last chunk mask their end vectors.
-        if ((w0 != 0 || rel0 == 0) && p1 != e) {   // warp-uniform
+        if ((w0 != 0 || rel0 == 0) && p1 != e) {   // group-uniform
 #pragma unroll
             for (int j = 0; j < kFqChunkPerLane; ++j) {
-                const unsigned v = lane + 32 * j;
+                const unsigned v = gl + G * j;
                 if (v < nvec) strip[v] = pack16(x[j], bad);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < kFqChunkPerLane; ++j) {
-                const unsigned v = lane + 32 * j;
+                const unsigned v = gl + G * j;
                 if (v < nvec + 2) {   // two more codes (zero): the window of a ragged last word reaches past the last vector
                     const unsigned pos = 16u * v;
                     uint4 y = x[j];
@@ -839,32 +849,36 @@ __device__ __forceinline__ void fq_encode_chunks(const uint8_t* __restrict__ byt
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
         uint64_t* oc = o + w0;
 #pragma unroll
-        for (int k = 0; k < kFqChunkWords / 32; ++k) {
-            const unsigned j = lane + 32 * k;
+        for (int k = 0; k < 2; ++k) {
+            const unsigned j = gl + G * k;
             if (j < cnt) oc[j] = fq_cut_word(strip, rel0 + 32u * j);
         }
-        if (__any_sync(0xffffffffu, (bad & kValidMask) != 0u) && lane == 0) fq_report_range(bytes, p0, p1, status);
-        __syncwarp();   // the strip is reused by the next chunk
+        if (__any_sync(gmask, (bad & kValidMask) != 0u) && gl == 0) fq_report_range(bytes, p0, p1, status);
+        __syncwarp(gmask);   // the strip is reused by the next chunk
     }
 }
 
-__global__ void __launch_bounds__(32 * kFqLongWarps, 4)   // 64 registers; 3 / 4 / 5 CTAs per SM: 0.918 / 0.894 / 1.012 ms
+// G lanes per read
+template <int G>
+__global__ void __launch_bounds__(32 * kFqLongWarps, 4)   // 64 registers; G = 32: 3 / 4 / 5 CTAs per SM 0.918 / 0.894 / 1.012 ms
 fastq_encode_long_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_reads,
                          const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off,
                          uint64_t* __restrict__ out, unsigned long long* __restrict__ status, unsigned long long* __restrict__ giants) {
-    __shared__ uint32_t strip[kFqLongWarps][kFqChunkVecs + 6];
-    const unsigned long long r = (unsigned long long)blockIdx.x * kFqLongWarps + (threadIdx.x >> 5);
+    constexpr int kGroups = 32 * kFqLongWarps / G;   // reads per CTA
+    __shared__ uint32_t strip[kGroups][FqGroup<G>::kStrip];
+    const unsigned group = threadIdx.x / G;
+    const unsigned long long r = (unsigned long long)blockIdx.x * kGroups + group;
     if (r >= n_reads) return;
     const unsigned long long len = seq_len[r], s = seq_off[r], wo = word_off[r];
     if (len == 0 || (s & wo) == ~0ull) return;   // (the second term only keeps the three loads together, see fastq_encode_reads_kernel)
     if (len > kFqGiant) {
-        if ((threadIdx.x & 31) == 0) giants[1 + atomicAdd(giants, 1ull)] = r;
+        if ((threadIdx.x & (G - 1)) == 0) giants[1 + atomicAdd(giants, 1ull)] = r;
         return;
     }
-    fq_encode_chunks(bytes, n, s, len, out + wo, strip[threadIdx.x >> 5], 0, 1, status);
+    fq_encode_chunks<G>(bytes, n, s, len, out + wo, strip[group], 0, 1, status);
 }
 
 // the queued giant reads, one after the other, the whole grid striding over the chunks of each
@@ -872,12 +886,12 @@ __global__ void __launch_bounds__(32 * kFqLongWarps)
 fastq_encode_giant_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, const uint64_t* __restrict__ seq_off,
                           const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off, uint64_t* __restrict__ out,
                           unsigned long long* __restrict__ status, const unsigned long long* __restrict__ giants) {
-    __shared__ uint32_t strip[kFqLongWarps][kFqChunkVecs + 6];
+    __shared__ uint32_t strip[kFqLongWarps][FqGroup<32>::kStrip];
     const unsigned long long n_giants = giants[0];
     const unsigned long long warp = (unsigned long long)blockIdx.x * kFqLongWarps + (threadIdx.x >> 5), n_warps = (unsigned long long)gridDim.x * kFqLongWarps;
     for (unsigned long long i = 0; i < n_giants; ++i) {
         const unsigned long long r = giants[1 + i];
-        fq_encode_chunks(bytes, n, seq_off[r], seq_len[r], out + word_off[r], strip[threadIdx.x >> 5], warp, n_warps, status);
+        fq_encode_chunks<32>(bytes, n, seq_off[r], seq_len[r], out + word_off[r], strip[threadIdx.x >> 5], warp, n_warps, status);
     }
 }
 
@@ -978,23 +992,34 @@ cudaError_t launch_fastq_encode(const DeviceInfo&, const uint8_t* d_bytes, size_
         const char* v = getenv("BN_FQ_VARIANT");
         return v ? atoi(v) : -1;
     }();
-    if (forced < 0 && n_bytes / n_reads <= 1024) {   // short records: a thread per read, only the sequence bytes are fetched
+    static const size_t short_max = [] {
+        const char* v = getenv("BN_FQ_SHORT_MAX");
+        return v ? (size_t)atoll(v) : (size_t)1024;
+    }();
+    if (forced < 0 && n_bytes / n_reads <= short_max) {   // short records: a thread per read, only the sequence bytes are fetched
         // (blocks in flight per thread, CTAs per SM) swept on 20 M x 150 bp: (6,3) 1.13 ms, (6,4) 1.19, (4,3) 1.23, (4,4) 1.08, (3,4) 1.10,
         // (3,5) 1.04, (2,6) 1.09, (6,2) 1.45 -- residency beats loads in flight per thread
         fastq_encode_reads_kernel<3, 5><<<(unsigned)ceil_div(n_reads, kThreads), kThreads, 0, s>>>(d_bytes, n_bytes, n_reads, d_seq_offsets,
                                                                                                   d_seq_lens, d_word_offsets, d_out_words, d_status);
         return cudaGetLastError();
     }
-    static const size_t long_min = [] {
-        const char* v = getenv("BN_FQ_LONG_MIN");
-        return v ? (size_t)atoll(v) : (size_t)4096;
+    static const size_t group_min = [] {
+        const char* v = getenv("BN_FQ_GROUP_MIN");   // records above this many bytes on average take the lanes-per-read kernels
+        return v ? (size_t)atoll(v) : (size_t)1024;
     }();
-    if (forced < 0 && n_bytes / n_reads > long_min) {   // long records: a warp per read, only the sequence bytes are fetched
+    if (forced < 0 && n_bytes / n_reads > group_min) {   // long records: G lanes per read, only the sequence bytes are fetched
         unsigned long long* giants = sc.giants;
         cudaError_t e = cudaMemsetAsync(giants, 0, sizeof(unsigned long long), s);
         if (e != cudaSuccess) return e;
-        fastq_encode_long_kernel<<<(unsigned)ceil_div(n_reads, kFqLongWarps), 32 * kFqLongWarps, 0, s>>>(d_bytes, n_bytes, n_reads, d_seq_offsets, d_seq_lens,
-                                                                                                     d_word_offsets, d_out_words, d_status, giants);
+        // words of an average sequence line: half of a FASTQ record is sequence, nearly all of a FASTA record
+        const size_t avg_words = n_bytes / n_reads / (fasta ? 32 : 64);
+#define BN_FQ_GROUPS(G)                                                                                                                  \
+    fastq_encode_long_kernel<G><<<(unsigned)ceil_div(n_reads, 32 * kFqLongWarps / G), 32 * kFqLongWarps, 0, s>>>(                        \
+        d_bytes, n_bytes, n_reads, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status, giants)
+        if (avg_words > 48) BN_FQ_GROUPS(32);
+        else if (avg_words > 20) BN_FQ_GROUPS(16);
+        else BN_FQ_GROUPS(8);
+#undef BN_FQ_GROUPS
         fastq_encode_giant_kernel<<<148 * 4, 32 * kFqLongWarps, 0, s>>>(d_bytes, n_bytes, d_seq_offsets, d_seq_lens, d_word_offsets, d_out_words, d_status,
                                                                         giants);
         return cudaGetLastError();

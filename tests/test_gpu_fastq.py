@@ -125,6 +125,34 @@ def test_random_texts(bn, dv, kind, crlf, seed):
     assert exp[0] == "ok" and [int(x) for x in exp[4]] == [int(x) for x in lens]
 
 
+@pytest.mark.parametrize("fasta", [False, True])
+@pytest.mark.parametrize("crlf", [False, True])
+@pytest.mark.parametrize("mean_len", [300, 600, 1000, 1600, 2500, 5000, 70_000])
+def test_every_encode_path_by_record_size(bn, dv, mean_len, crlf, fasta):
+    """The launcher picks the encode kernel from the average record size: a thread per read, 8 / 16 / 32 lanes per read (chunks of
+    16 / 32 / 64 words), the giant-read queue above 2^20 bases.  Reads of mixed lengths around each mean (so chunks end ragged, on
+    a chunk boundary, one word past it), then one invalid byte at a time at the positions a chunked walk can get wrong."""
+    rng = np.random.default_rng(mean_len + crlf + 2 * fasta)
+    n = max(6, 200_000 // mean_len)
+    lens = np.maximum(1, (mean_len * (0.5 + rng.random(n))).astype(np.int64))
+    for k, extra in enumerate((0, 1, 31, 32, 33, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049)):   # around every chunk size
+        lens[k % n] = max(1, (mean_len // 2048) * 2048 + extra)
+    if mean_len == 70_000:
+        lens[n // 2] = (1 << 20) + 77   # one read for the whole-grid queue
+    text = make_fastq(rng, lens, crlf=crlf, final_newline=bool(rng.integers(0, 2)), alphabet=b"ACGTacgt", fasta=fasta)
+    exp = check(bn, dv, text, fasta)
+    assert exp[0] == "ok" and [int(x) for x in exp[4]] == [int(x) for x in lens]
+    starts = [int(x) for x in exp[3]]
+    for r in (0, n // 2, n - 1):
+        s0, ln = starts[r], int(lens[r])
+        for pos in sorted({0, 1, 15, 16, 31, 32, 511, 512, 1023, 1024, 2047, 2048, ln - 33, ln - 32, ln - 2, ln - 1}):
+            if 0 <= pos < ln:
+                bad = bytearray(text)
+                bad[s0 + pos] = ord("N")
+                got = check(bn, dv, bytes(bad), fasta)
+                assert got == ("base", ord("N"), r, pos, s0 + pos), (r, pos, got[:5])
+
+
 @pytest.mark.parametrize("mix", ["all_dense", "dense_then_normal", "normal_then_dense"])
 def test_dense_lines_take_the_fallback_index(bn, dv, mix):
     """More than 2048 lines in a 16 KiB tile (average line under 8 bytes) overflow the slot rows: the dense index runs."""

@@ -1,5 +1,8 @@
-// scan.cuh -- exclusive prefix sums of per-item counts (u64) over n items, as three small kernels: per-CTA sums, a
-// one-CTA scan of the sums, CTA-local scan + offset.  out[i] = sum of count(j), j < i, for i in [0, n].
+// scan.cuh -- exclusive prefix sums of per-item counts (u64) over n items, as two small kernels: per-CTA sums (each CTA also
+// adds its sum to the total of its group of 256 CTAs), then CTA-local scan + offset, where a CTA gets the sum of everything
+// before it from at most 255 block sums of its own group plus the totals of the groups before (two loads per thread and one
+// block reduction).  The one-CTA scan of the block sums that used to sit between the two (37 us for the 39 K sums of 40 M
+// reads: five rounds of load - scan - store by a single CTA) is gone.  out[i] = sum of count(j), j < i, for i in [0, n].
 //
 // Item layout inside a CTA tile of 1024 items is WARP-STRIPED: warp w owns items [128 w, 128 w + 128) of the tile and
 // lane l touches items 128 w + 32 i + l, i < 4 -- every load the count functor makes and every offset store is a
@@ -42,7 +45,13 @@ __device__ __forceinline__ unsigned long long scan_item(unsigned i) {
     return (unsigned long long)blockIdx.x * kScanTile + (threadIdx.x >> 5) * (32 * kScanItems) + 32 * i + (threadIdx.x & 31);
 }
 
-// sums[ch * (n_blocks + 1) + b] = sum of channel ch over tile b
+constexpr int kScanGroup = 256;   // CTAs per group (= kThreads: a thread fetches one block sum of its group and one group total)
+static_assert(kScanGroup == kThreads, "one block sum per thread");
+// per channel: block sums [n_blocks] | group totals [ceil(n_blocks / kScanGroup)] (zeroed before the first kernel)
+__host__ __device__ __forceinline__ unsigned long long scan_groups(unsigned long long n_blocks) { return (n_blocks + kScanGroup - 1) / kScanGroup; }
+__host__ __device__ __forceinline__ unsigned long long scan_channel_words(unsigned long long n_blocks) { return n_blocks + scan_groups(n_blocks); }
+
+// sums[ch * scan_channel_words + b] = sum of channel ch over tile b; the group totals behind them
 template <int NCH, typename F>
 __global__ void __launch_bounds__(kThreads)
 scan_block_sums_kernel(F count, unsigned long long n, unsigned long long n_blocks, unsigned long long* __restrict__ sums) {
@@ -63,60 +72,12 @@ scan_block_sums_kernel(F count, unsigned long long n, unsigned long long n_block
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
         const unsigned long long t = block_sum_u64(s[ch], scratch);
-        if (threadIdx.x == 0) sums[ch * (n_blocks + 1) + blockIdx.x] = t;
+        if (threadIdx.x == 0) {
+            unsigned long long* ch_sums = sums + ch * scan_channel_words(n_blocks);
+            ch_sums[blockIdx.x] = t;
+            if (t) atomicAdd(ch_sums + n_blocks + blockIdx.x / kScanGroup, t);
+        }
     }
-}
-
-// exclusive scan of each channel's n sums in place, one CTA per channel; entry n receives the channel's total.
-// A thread takes kSumsPer consecutive sums per round (all loads issued before the first add), so a round covers 8192 sums:
-// 40 M reads are 39 K block sums = 5 rounds instead of the 39 single-item rounds (one L2 round trip + four barriers each,
-// ~45 us in all) of the first form.
-constexpr int kSumsPer = 8;
-static __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long long* __restrict__ all_sums, unsigned long long n) {
-    unsigned long long* sums = all_sums + blockIdx.x * (n + 1);
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned long long base = 0; base < n; base += (unsigned long long)blockDim.x * kSumsPer) {
-        const unsigned long long i0 = base + (unsigned long long)threadIdx.x * kSumsPer;
-        unsigned long long v[kSumsPer];
-#pragma unroll
-        for (int j = 0; j < kSumsPer; ++j) v[j] = i0 + j < n ? sums[i0 + j] : 0;
-        unsigned long long mine = 0;
-#pragma unroll
-        for (int j = 0; j < kSumsPer; ++j) mine += v[j];
-        unsigned long long inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (unsigned)o) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_tot[lane], winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= (unsigned)o) winc += t;
-            }
-            warp_tot[lane] = winc - w;  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const unsigned long long carry = carry_s;
-        unsigned long long run = carry + warp_tot[warp] + inc - mine;   // exclusive prefix of this thread's first sum
-#pragma unroll
-        for (int j = 0; j < kSumsPer; ++j) {
-            if (i0 + j < n) sums[i0 + j] = run;
-            run += v[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = run;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) sums[n] = carry_s;
 }
 
 // hook(i, out[i], count(i)) -- or hook(i, out_a[i], a(i), out_b[i], b(i)) with two channels -- once per item
@@ -126,11 +87,17 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
                     uint64_t* __restrict__ out_a, uint64_t* __restrict__ out_b, H hook) {
     __shared__ unsigned long long warp_tot[NCH][32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long c[kScanItems][NCH], excl[kScanItems][NCH], carry[NCH], tile_base[NCH];
+    __shared__ unsigned long long warp_before[NCH][kWarpsPerBlock], tile_before[NCH];
+    unsigned long long c[kScanItems][NCH], excl[kScanItems][NCH], carry[NCH], before[NCH];
+    // everything before this tile: thread t takes the block sum of tile (first tile of the group) + t if that tile precedes
+    // this one, and the total of group t if that group precedes this one's -- asked for with the items, reduced below
+    const unsigned long long group = blockIdx.x / kScanGroup, in_group = blockIdx.x % kScanGroup;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
+        const unsigned long long* ch_sums = sums + ch * scan_channel_words(n_blocks);
         carry[ch] = 0;
-        tile_base[ch] = sums[ch * (n_blocks + 1) + blockIdx.x];   // asked for with the items (read after the barriers it was one more trip)
+        before[ch] = threadIdx.x < in_group ? ch_sums[group * kScanGroup + threadIdx.x] : 0ull;
+        for (unsigned long long g = threadIdx.x; g < group; g += kThreads) before[ch] += ch_sums[n_blocks + g];
     }
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {  // all loads first (independent), the row scans below
@@ -157,12 +124,16 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
         }
     }
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-        if (lane == 0) warp_tot[ch][warp] = carry[ch];
+    for (int ch = 0; ch < NCH; ++ch) {
+        const unsigned long long b = warp_sum_u64(before[ch]);   // rides on the two barriers the tile scan needs anyway
+        if (lane == 0) warp_tot[ch][warp] = carry[ch], warp_before[ch][warp] = b;
+    }
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
+            const unsigned long long wb = warp_sum_u64(lane < kWarpsPerBlock ? warp_before[ch][lane] : 0ull);
+            if (lane == 0) tile_before[ch] = wb;
             const unsigned long long w = lane < kWarpsPerBlock ? warp_tot[ch][lane] : 0;
             unsigned long long winc = w;
 #pragma unroll
@@ -176,7 +147,7 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
     __syncthreads();
     unsigned long long base[NCH];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) base[ch] = tile_base[ch] + warp_tot[ch][warp];
+    for (int ch = 0; ch < NCH; ++ch) base[ch] = tile_before[ch] + warp_tot[ch][warp];
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
         const unsigned long long r = scan_item(i);
@@ -190,21 +161,22 @@ scan_offsets_kernel(F count, unsigned long long n, const unsigned long long* __r
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        out_a[n] = sums[n_blocks];
-        if constexpr (NCH == 2) out_b[n] = sums[(n_blocks + 1) + n_blocks];
+    if (blockIdx.x == n_blocks - 1 && threadIdx.x == kThreads - 1) {   // the tile's last item slot: everything before it + itself = the total
+        out_a[n] = base[0] + excl[kScanItems - 1][0] + c[kScanItems - 1][0];
+        if constexpr (NCH == 2) out_b[n] = base[1] + excl[kScanItems - 1][1] + c[kScanItems - 1][1];
     }
 }
 
 // bytes of scratch (`sums`) the scans need for n items
-static inline size_t scan_scratch_bytes(size_t n) { return (ceil_div(n ? n : 1, kScanTile) + 1) * sizeof(unsigned long long); }
+static inline size_t scan_scratch_bytes(size_t n) { return (size_t)scan_channel_words(ceil_div(n ? n : 1, kScanTile)) * sizeof(unsigned long long); }
 static inline size_t scan2_scratch_bytes(size_t n) { return 2 * scan_scratch_bytes(n); }
 
 template <int NCH, typename F, typename H>
 static void launch_scan_impl(F count, size_t n, unsigned long long* sums, uint64_t* out_a, uint64_t* out_b, cudaStream_t s, H hook) {
     const unsigned long long n_blocks = ceil_div(n, kScanTile);
+    for (int ch = 0; ch < NCH; ++ch)   // the group totals are accumulated with atomics
+        cudaMemsetAsync(sums + ch * scan_channel_words(n_blocks) + n_blocks, 0, scan_groups(n_blocks) * sizeof(unsigned long long), s);
     scan_block_sums_kernel<NCH><<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, n_blocks, sums);
-    scan_sums_kernel<<<NCH, 1024, 0, s>>>(sums, n_blocks);
     scan_offsets_kernel<NCH><<<(unsigned)n_blocks, kThreads, 0, s>>>(count, n, sums, n_blocks, out_a, out_b, hook);
 }
 
@@ -233,8 +205,8 @@ struct ScanLoadCount {
 template <typename F>
 static void launch_exclusive_scan_cached(F count, size_t n, unsigned long long* sums, uint64_t* cache, uint64_t* out, cudaStream_t s) {
     const unsigned long long n_blocks = ceil_div(n, kScanTile);
+    cudaMemsetAsync(sums + n_blocks, 0, scan_groups(n_blocks) * sizeof(unsigned long long), s);
     scan_block_sums_kernel<1><<<(unsigned)n_blocks, kThreads, 0, s>>>(ScanStoreCount<F>{count, cache}, n, n_blocks, sums);
-    scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n_blocks);
     scan_offsets_kernel<1><<<(unsigned)n_blocks, kThreads, 0, s>>>(ScanLoadCount{cache}, n, sums, n_blocks, out, nullptr, ScanNoHook());
 }
 

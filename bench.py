@@ -487,14 +487,15 @@ def leg_e2e(job: Job, asc, n: int, K: int):
     h_words = [ctx_a.pinned_empty(nw, np.uint64) for _ in range(2)]
     h_back = ctx_b.pinned_empty(n, np.uint8)
     h_seq[:] = asc.cpu().numpy()
-    steps = max(2, min(K, 8))   # enough steps for the encode-ahead pipeline to amortise its fill and drain
+    steps = max(2, min(K, 32))  # the K steps of the run (bounded): the encode-ahead pipeline pays one encode alone to fill and
+                                # one decode alone to drain, once per leg -- over 8 steps that was 5 % of the figure
     for ctx in (ctx_a, ctx_b):  # warm-up: allocates the staging buffers of both contexts
         bn.encode_np(h_seq, ctx, out=h_words[0])
         bn.decode_np(h_words[0], n, ctx, out=h_back)
     bn.encode_np(h_seq, ctx_a, out=h_words[1])
 
     pcie = leg_pcie_ceiling(job, h_seq, h_back, n)
-    pcie["pattern_s"] = leg_pcie_pattern(job, h_seq, h_words[0], h_words[1], h_back, n, 4)   # h_words[0] / h_back now hold device scratch:
+    pcie["pattern_s"] = leg_pcie_pattern(job, h_seq, h_words[0], h_words[1], h_back, n, steps)   # h_words[0] / h_back now hold device scratch:
                                                                                              # every schedule below rewrites them first
 
     def wall(fn):

@@ -121,10 +121,10 @@ __device__ __forceinline__ unsigned nth_set_bit(uint32_t m, unsigned n) {
 }
 
 // the four vectors a thread loads of a tile (lane-consecutive: coalesced)
-template <int kEdge>   // 0: the tile lies wholly inside the text, 1: it does not, 2: decided here (unused since the one-pass experiment)
+template <int kEdge>   // 0: the tile lies wholly inside the text, 1: it does not
 __device__ __forceinline__ void lines_load_tile(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long tile0, unsigned tid,
                                                 uint4 (&x)[4]) {
-    if (kEdge == 0 || (kEdge == 2 && tile0 + kFqTile <= n)) {
+    if (kEdge == 0) {
         const uint4* src = reinterpret_cast<const uint4*>(bytes + tile0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = ld128<LD_NC_NOALLOC>(src + tid + j * kFqThreads);

@@ -62,6 +62,11 @@ def test_library_targets_sm_100a_only(sass):
     ("from_2bit_tight31_kernel", r"LDG\.E", r"STG\.E\.EF\.128"),            # one or two 64-bit words in, 16 bases per 128-bit streaming store
     ("fastq_lines_kernel", r"LDG\.E(\.NA)?\.128", r"STG\.E"),              # the text in 128-bit loads, 32-bit line entries out
     ("fastq_encode_kernelILi49152ELi128ELi9ELb1", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
+    ("fastq_encode_long_kernelILi32", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),   # a warp per read: the sequence line in 128-bit loads
+    ("fastq_encode_long_kernelILi16", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
+    ("fastq_encode_long_kernelILi8", r"LDG\.E(\.NA)?\.128", r"STG\.E\.64"),
+    ("split_packed_fused_kernel", r"LDG\.E\.64", r"STS\.64"),                   # the staged destination is written with STS, not generic ST
+    ("slice_short_kernel", r"LDG\.E\.64", r"STS"),
 ])
 def test_hot_kernels_use_wide_accesses_and_no_local_memory(sass, needle, loads, stores):
     funcs, _ = sass

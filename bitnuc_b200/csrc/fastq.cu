@@ -782,7 +782,10 @@ fastq_encode_reads_kernel(const uint8_t* __restrict__ bytes, unsigned long long 
 // Records between the two (1 - 4 KiB) take the same walk with G = 16 or 8 lanes per read -- two or four reads per warp, chunks
 // of 2 G words, the group synchronising on its own lane mask -- instead of the tiled kernel.
 constexpr int kFqChunkPerLane = 5;          // a chunk of 2 G words is 4 G + 2 vectors (+ 2 padding codes): five per lane
-constexpr int kFqLongWarps = 8;
+#ifndef BN_FQL_WARPS
+#define BN_FQL_WARPS 4   // warps per CTA: 2 / 4 / 8 / 16 -> 0.693 / 0.693 / 0.706 / 0.741 ms (10 kbp), 0.989 / 0.992 / 1.045 / 1.163 ms (1 kbp)
+#endif
+constexpr int kFqLongWarps = BN_FQL_WARPS;
 constexpr unsigned long long kFqGiant = kFqGiantBases;
 template <int G>
 struct FqGroup {
@@ -863,7 +866,7 @@ __device__ __forceinline__ void fq_encode_chunks(const uint8_t* __restrict__ byt
 
 // G lanes per read
 template <int G>
-__global__ void __launch_bounds__(32 * kFqLongWarps, 4)   // 64 registers; G = 32: 3 / 4 / 5 CTAs per SM 0.918 / 0.894 / 1.012 ms
+__global__ void __launch_bounds__(32 * kFqLongWarps, 32 / kFqLongWarps)   // 64 registers; G = 32: 3 / 4 / 5 CTAs per SM 0.918 / 0.894 / 1.012 ms
 fastq_encode_long_kernel(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_reads,
                          const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ seq_len, const uint64_t* __restrict__ word_off,
                          uint64_t* __restrict__ out, unsigned long long* __restrict__ status, unsigned long long* __restrict__ giants) {

@@ -23,7 +23,12 @@
 //      A tile with more than 2048 lines (average line under 8 bytes) does not fit its slot row: the count pass raises a
 //      flag and step 2 runs the dense form instead (fastq_index_kernel re-reads the text and writes nl[line], then
 //      fastq_records_kernel) -- both forms are launched, the device-side flag decides which one works.
-//   3. fastq_encode_kernel   PACK THEN CUT over tiles of 48 KiB of text: the whole tile (headers and qualities too) is
+//   3. the encode, picked by the average record size (launch_fastq_encode):
+//        <= 1 KiB   fastq_encode_reads_kernel   a thread per read: only the 32-byte blocks of its sequence line, 256-bit loads
+//        >  1 KiB   fastq_encode_long_kernel<G> 8 / 16 / 32 lanes per read walk the sequence line in chunks of 2 G words
+//                   (+ fastq_encode_giant_kernel for reads above 2^20 bases: the whole grid on one read)
+//      and, reachable through BN_FQ_VARIANT only, the first form:
+//      fastq_encode_kernel   PACK THEN CUT over tiles of 48 KiB of text: the whole tile (headers and qualities too) is
 //                            packed like the contiguous encode -- aligned coalesced 128-bit loads, 16 bytes -> one
 //                            32-bit code, one "contains a non-ACGT byte" flag per vector via a ballot -- into a
 //                            shared-memory strip; then one thread per read that starts in the tile cuts the read's
@@ -33,8 +38,8 @@
 //                            (the first version re-read the end vectors from global memory: ncu showed 128-byte
 //                            line fills for them, +70 % DRAM traffic).
 //                            The one read that runs past the tile is finished straight from global memory.
-// HBM traffic: the text is read twice (lines, encode).  Algorithmic bytes: text once + 8 B per word out
-// + 24 B per read of offsets.
+// HBM traffic: the text is read by the count pass, and its sequence lines (in whole DRAM granules) by the encode.
+// Algorithmic bytes: text once + 8 B per word out + 24 B per read of offsets.
 #include <cstdlib>
 
 #include "common.cuh"
